@@ -1,0 +1,156 @@
+/*
+ * tgis_engine.h — C ABI of libtgis_engine.so, the B200-native continuous-batching engine that replaces the
+ * vLLM AsyncLLMEngine behind the TGIS gRPC adapter's generation path.
+ *
+ * Drop-in boundary.  The reference has no FFI; its seam is the `EngineClient` object that
+ * `TextGenerationService` holds.  Each entry point below cites the reference call site it serves
+ * (paths relative to /root/reference/src/vllm_tgis_adapter):
+ *
+ *   tgis_engine_create / _load_weight / _start   <- __main__.py:48   `build_async_engine_client(args)`
+ *   tgis_engine_add_request                      <- grpc/grpc_server.py:205-225 `_make_generator` -> engine.generate(
+ *                                                   prompt=TokensPrompt(prompt_token_ids=...), sampling_params=...,
+ *                                                   request_id=...)
+ *   tgis_engine_poll                             <- the AsyncGenerator[RequestOutput] consumed at
+ *                                                   grpc_server.py:281 (Generate) and :367 (GenerateStream)
+ *   tgis_engine_abort                            <- grpc_server.py:292, :388  `await self.engine.abort(request_id)`
+ *   tgis_engine_status                           <- grpc_server.py:117 `engine.errored and not engine.is_running`,
+ *                                                   __main__.py:71
+ *   tgis_engine_max_model_len                    <- grpc_server.py:196-199 `engine.vllm_config.model_config`
+ *   tgis_engine_shutdown / _destroy              <- __main__.py:48 (exit of the `async with`)
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Every function returns 0 on success, <0 on error;
+ * tgis_last_error() returns a thread-local message valid until the next call on the same thread.  The caller owns
+ * input buffers until the call returns (the engine copies).  One dedicated engine thread per process runs the step
+ * loop (scheduler + kernel launches); all entry points are thread-safe enqueue/dequeue operations.
+ * There is NO CPU fallback: tgis_engine_create fails if no sm_100 device is present.
+ */
+#ifndef TGIS_ENGINE_H_
+#define TGIS_ENGINE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGIS_ABI_VERSION 1
+#define TGIS_MAX_REQUEST_ID 96
+#define TGIS_MAX_TOPN 12 /* reference forces max_logprobs >= 11: tgis_utils/args.py:214-216 */
+#define TGIS_MAX_STOP_TOKEN_IDS 8
+
+typedef struct tgis_engine tgis_engine;
+
+/* Model + runtime configuration (Llama-architecture decoder: RMSNorm, neox RoPE, GQA, SwiGLU; bf16). */
+typedef struct tgis_config {
+  int32_t abi_version; /* must be TGIS_ABI_VERSION */
+  int32_t n_layers;
+  int32_t hidden;
+  int32_t n_q_heads;
+  int32_t n_kv_heads;
+  int32_t head_dim; /* must be 128 */
+  int32_t ffn;
+  int32_t vocab;
+  float rope_theta;
+  float rms_eps;
+  int32_t max_model_len;      /* reference: --max-sequence-length / --max-model-len (tgis_utils/args.py:187-192) */
+  int32_t max_num_seqs;       /* concurrent sequences in the running batch */
+  int32_t max_batched_tokens; /* token budget of one step (prefill chunk size) */
+  int64_t kv_cache_bytes;     /* 0 = size from gpu_mem_fraction */
+  float gpu_mem_fraction;     /* fraction of free HBM the KV cache may take when kv_cache_bytes == 0 */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t tp_size;            /* tensor-parallel world (1 = single GPU) */
+  int32_t tp_rank;
+  int32_t use_cuda_graphs;    /* capture decode steps into CUDA graphs */
+  int32_t debug_gemm_ref;     /* debug only: route GEMMs through the SIMT cross-check kernel */
+  uint64_t seed;              /* engine RNG for unseeded sampling requests */
+} tgis_config;
+
+/* What the adapter's proto->SamplingParams mapping (grpc_server.py:508-628) hands to the engine. */
+typedef struct tgis_sampling_params {
+  int32_t greedy;             /* method == GREEDY or temperature == 0.0 (grpc_server.py:593-596) */
+  float temperature;          /* used when !greedy */
+  int32_t top_k;              /* <= 0: disabled (grpc_server.py:600) */
+  float top_p;                /* >= 1: disabled (grpc_server.py:601) */
+  float typical_p;            /* in (0,1): TypicalLogitsWarper mass, applied only when sampling (:562-565); else off */
+  float repetition_penalty;   /* 1.0: disabled (:614) */
+  int32_t has_length_penalty; /* DecodingParameters.length_penalty set (:567-578) */
+  uint32_t lp_start_index;
+  float lp_decay_factor;
+  int32_t eos_token_id;       /* tokenizer.eos_token_id */
+  int32_t min_tokens;         /* (:530) */
+  int32_t max_tokens;         /* effective per-request maximum (:787-798) */
+  int32_t num_logprobs;       /* vLLM `logprobs`: 0 = none, n>=1 = sampled-token logprob+rank and n top entries */
+  int32_t prompt_logprobs;    /* 0 = none (reserved) */
+  int32_t has_seed;
+  uint64_t seed;
+  int32_t n_stop_token_ids;
+  int32_t stop_token_ids[TGIS_MAX_STOP_TOKEN_IDS];
+} tgis_sampling_params;
+
+enum tgis_finish_reason {
+  TGIS_FINISH_NONE = 0,
+  TGIS_FINISH_LENGTH = 1,     /* vLLM finish_reason "length" */
+  TGIS_FINISH_STOP_EOS = 2,   /* "stop", stop_reason None     */
+  TGIS_FINISH_STOP_TOKEN = 3, /* "stop", stop_reason = int    */
+  TGIS_FINISH_ABORT = 4,      /* "abort"                      */
+  TGIS_FINISH_ERROR = 5
+};
+
+/* One record per request per engine step that produced a token or a terminal event
+ * (the fields RequestOutput/CompletionOutput/Logprob expose at grpc_server.py:430-493, 701-756). */
+typedef struct tgis_step_output {
+  char request_id[TGIS_MAX_REQUEST_ID];
+  int32_t n_new_tokens;   /* 0 or 1 */
+  int32_t token_id;
+  float logprob;          /* raw log-softmax of token_id (valid when num_logprobs > 0) */
+  int32_t rank;           /* 1-based rank on the raw log-softmax */
+  int32_t n_topn;
+  int32_t topn_ids[TGIS_MAX_TOPN];
+  float topn_logprobs[TGIS_MAX_TOPN];
+  int32_t finish_reason;  /* enum tgis_finish_reason */
+  int32_t stop_token_id;  /* valid for TGIS_FINISH_STOP_TOKEN */
+  int32_t n_prompt_tokens;
+  int32_t n_output_tokens; /* cumulative */
+  double ts_arrival, ts_first_scheduled, ts_first_token, ts_last_token; /* CLOCK_MONOTONIC seconds */
+} tgis_step_output;
+
+typedef struct tgis_status {
+  int32_t errored;     /* sticky after a fatal CUDA error */
+  int32_t is_running;  /* step loop alive */
+  int32_t n_running, n_waiting;
+  int32_t free_blocks, total_blocks;
+  int64_t steps;             /* engine steps executed */
+  int64_t tokens_generated;
+  int64_t kernel_launches;   /* kernels launched by this library since start */
+  double gpu_busy_ms;        /* CUDA-event time of all steps */
+} tgis_status;
+
+const char* tgis_last_error(void);
+int tgis_abi_version(void);
+
+int tgis_engine_create(const tgis_config* cfg, tgis_engine** out);
+/* name: HF Llama parameter name ("model.layers.3.self_attn.q_proj.weight", "lm_head.weight", ...) or
+ * "tgis.rope_cos_sin" ([max_model_len,128] bf16 = cos|sin).  ptr may be host or device memory (cudaMemcpyDefault);
+ * dtype 0 = bf16.  rows/cols describe the full (unsharded) tensor. */
+int tgis_engine_load_weight(tgis_engine* e, const char* name, const void* ptr, int64_t rows, int64_t cols, int32_t dtype);
+int tgis_engine_start(tgis_engine* e);
+int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_t* prompt_ids, int32_t n_prompt,
+                            const tgis_sampling_params* params);
+int tgis_engine_abort(tgis_engine* e, const char* request_id);
+/* Blocks up to timeout_ms for at least one record; returns the number written to out[0..cap) (>= 0) or <0 on error. */
+int tgis_engine_poll(tgis_engine* e, tgis_step_output* out, int32_t cap, int32_t timeout_ms);
+int tgis_engine_status(tgis_engine* e, tgis_status* out);
+int tgis_engine_max_model_len(tgis_engine* e);
+int tgis_engine_shutdown(tgis_engine* e);
+void tgis_engine_destroy(tgis_engine* e);
+
+/* Synchronous driver used by bench.py / tests: run the step loop on the calling thread until every queued request has
+ * finished (no engine thread needed).  Returns the number of steps, <0 on error.  Step wall/GPU times accumulate in
+ * tgis_status. */
+int tgis_engine_run_until_idle(tgis_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGIS_ENGINE_H_ */

@@ -1,0 +1,49 @@
+/*
+ * tgis_kernels.h — C ABI test hooks of libtgis_engine.so: each sm_100a kernel of the hot path callable on raw device
+ * pointers, so the parity tests (tests/ -m gpu) can compare every kernel with the CPU oracle through the same shared
+ * library the server loads.  All pointers marked "dev" are device memory; metadata arrays are HOST memory and are
+ * staged internally.  Every call synchronises before returning; 0 = ok, <0 = error (tgis_last_error()).
+ *
+ * Reference semantics restated by these kernels (vLLM 0.22 = the arithmetic behind
+ * /root/reference/src/vllm_tgis_adapter/grpc/grpc_server.py:222):
+ *   tgis_k_gemm        vllm model_executor/layers/linear.py (F.linear, bf16 in, fp32 accumulate, bf16 out)
+ *   tgis_k_rmsnorm     vllm model_executor/layers/layernorm.py:104,173 (rms_norm / fused_add_rms_norm)
+ *   tgis_k_silu_mul    vllm model_executor/layers/activation.py:117-143
+ *   tgis_k_rope_kv     vllm model_executor/layers/rotary_embedding/base.py:200 + reshape_and_cache_flash
+ *   tgis_k_attention   vllm v1/attention/backends/flashinfer.py:1665,1803 (paged prefill / decode)
+ *   tgis_k_sampler     vllm v1/sample/sampler.py:67-144 + tgis_utils/logits_processors.py:7-47
+ */
+#ifndef TGIS_KERNELS_H_
+#define TGIS_KERNELS_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* y[T,N] = x[T,K] . w[N,K]^T ; impl 0 = tcgen05 kernel, 1 = SIMT cross-check kernel.  x must have >= 256 rows
+ * allocated (TMA box height) or T rows when impl == 1. */
+int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t N, int32_t K, int32_t x_rows_alloc,
+                int32_t impl, int32_t iters, float* ms_out);
+/* residual_dev may be NULL (plain rmsnorm); otherwise residual is updated in place */
+int tgis_k_rmsnorm(const void* x_dev, void* residual_dev, const void* w_dev, void* out_dev, int32_t T, int32_t hidden,
+                   float eps);
+int tgis_k_silu_mul(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn);
+int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* slot_mapping_host,
+                   const void* cos_sin_dev, void* k_cache_dev, void* v_cache_dev, int32_t T, int32_t n_q, int32_t n_kv);
+/* seqs_host: n_seqs x {q_start, q_len, kv_len, block_row}; block_table_host: [rows][bt_stride] */
+int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev, const int32_t* seqs_host,
+                     int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows, int32_t bt_stride, void* out_dev,
+                     int32_t n_q, int32_t n_kv, float scale);
+/* rows_host: n_rows x 64-byte SampleRow records (see csrc/kernels.h); out_host: n_rows x 112-byte SampleOut records;
+ * seen_bitmap_dev: [slots][ceil(vocab/32)] uint32 or NULL */
+int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
+                   void* seen_bitmap_dev, void* out_host);
+const char* tgis_k_last_error(void);
+int tgis_k_sizeof_sample_row(void);
+int tgis_k_sizeof_sample_out(void);
+int tgis_k_kv_block(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

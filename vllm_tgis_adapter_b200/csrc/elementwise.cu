@@ -1,0 +1,208 @@
+// HBM-bound elementwise / row-reduction kernels of the Llama layer stack (SURVEY.md §2.2 K1, K2, K4+K5, K9):
+// embedding gather, RMSNorm, fused residual-add + RMSNorm, neox RoPE fused with the paged-KV scatter, SiLU*mul.
+// Rounding points follow vLLM's CUDA ops / HF eager so that the CPU oracle (oracle/llama_oracle.py) can match them:
+//   vllm: csrc/layernorm_kernels.cu (residual add in model dtype, fp32 variance, bf16(x*rs) * w)
+//   vllm: csrc/pos_encoding_kernels.cu (bf16 cos/sin table, each mul/sub rounded to bf16)
+//   vllm: csrc/activation_kernels.cu  (bf16(silu(x)) * y)
+// All of them are 16-byte vectorised, coalesced, one row (or 8 elements) per thread group; no shared-memory reuse is
+// possible (each byte is touched once) so the design target is simply full-width coalesced traffic.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace tgis {
+
+struct alignas(16) BF8 {
+  __nv_bfloat16 v[8];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < THREADS / 32) ? red[l] : 0.f;
+  t = warp_sum(t);
+  __syncthreads();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------ embedding / gather
+__global__ void gather_rows_kernel(const int32_t* __restrict__ idx, const __nv_bfloat16* __restrict__ table,
+                                   __nv_bfloat16* __restrict__ out, int hidden, int n_table_rows) {
+  const int t = blockIdx.x;
+  int row = idx[t];
+  if (row < 0 || row >= n_table_rows) row = 0;  // padding rows: any valid row (never consumed)
+  const BF8* src = reinterpret_cast<const BF8*>(table + (size_t)row * hidden);
+  BF8* dst = reinterpret_cast<BF8*>(out + (size_t)t * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+cudaError_t embed_gather_launch(const int32_t* token_ids, const __nv_bfloat16* table, __nv_bfloat16* out, int T,
+                                int hidden, int vocab, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  gather_rows_kernel<<<T, 128, 0, stream>>>(token_ids, table, out, hidden, vocab);
+  return cudaGetLastError();
+}
+
+cudaError_t gather_rows_launch(const __nv_bfloat16* x, const int32_t* rows, __nv_bfloat16* out, int R, int hidden,
+                               cudaStream_t stream) {
+  if (R <= 0) return cudaSuccess;
+  gather_rows_kernel<<<R, 128, 0, stream>>>(rows, x, out, hidden, 1 << 30);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm
+constexpr int NORM_THREADS = 256;
+constexpr int NORM_MAX_VEC = 4;  // hidden <= 256 * 8 * 4 = 8192
+
+template <bool ADD>
+__global__ void __launch_bounds__(NORM_THREADS)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
+               const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int hidden, float eps) {
+  __shared__ float red[NORM_THREADS / 32];
+  const size_t base = (size_t)blockIdx.x * hidden;
+  const int nvec = hidden / 8;
+  BF8 z[NORM_MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) {
+      BF8 a = reinterpret_cast<const BF8*>(x + base)[i];
+      if (ADD) {
+        BF8 r = reinterpret_cast<const BF8*>(residual + base)[i];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a.v[e] = __float2bfloat16_rn(__bfloat162float(a.v[e]) + __bfloat162float(r.v[e]));
+        reinterpret_cast<BF8*>(residual + base)[i] = a;
+      }
+      z[j] = a;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float f = __bfloat162float(a.v[e]);
+        ss += f * f;
+      }
+    }
+  }
+  const float tot = block_sum<NORM_THREADS>(ss, red);
+  const float rs = rsqrtf(tot / (float)hidden + eps);
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) {
+      BF8 wv = reinterpret_cast<const BF8*>(w)[i];
+      BF8 o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float nrm = bf16_round(__bfloat162float(z[j].v[e]) * rs);
+        o.v[e] = __float2bfloat16_rn(nrm * __bfloat162float(wv.v[e]));
+      }
+      reinterpret_cast<BF8*>(out + base)[i] = o;
+    }
+  }
+}
+
+cudaError_t rmsnorm_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
+                           float eps, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
+  rmsnorm_kernel<false><<<T, NORM_THREADS, 0, stream>>>(x, nullptr, w, out, hidden, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, const __nv_bfloat16* w,
+                               __nv_bfloat16* out, int T, int hidden, float eps, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
+  rmsnorm_kernel<true><<<T, NORM_THREADS, 0, stream>>>(x, residual, w, out, hidden, eps);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ SiLU * mul
+__global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gate_up, __nv_bfloat16* __restrict__ act, int T,
+                                int ffn) {
+  const int vec_per_row = ffn / 8;
+  const long long total = (long long)T * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / vec_per_row), c = (int)(i % vec_per_row);
+    const BF8 g = reinterpret_cast<const BF8*>(gate_up + (size_t)t * 2 * ffn)[c];
+    const BF8 u = reinterpret_cast<const BF8*>(gate_up + (size_t)t * 2 * ffn + ffn)[c];
+    BF8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = __bfloat162float(g.v[e]);
+      const float s = bf16_round(x / (1.0f + expf(-x)));
+      o.v[e] = __float2bfloat16_rn(s * __bfloat162float(u.v[e]));
+    }
+    reinterpret_cast<BF8*>(act + (size_t)t * ffn)[c] = o;
+  }
+}
+
+cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (ffn % 8 != 0) return cudaErrorInvalidValue;
+  const long long total = (long long)T * (ffn / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  silu_mul_kernel<<<(int)blocks, 256, 0, stream>>>(gate_up, act, T, ffn);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ RoPE + KV scatter
+// grid = (T, ceil(heads/4)); 256 threads = 4 heads x 64 rotary pairs.
+__global__ void __launch_bounds__(256)
+rope_kvwrite_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ positions,
+                    const int32_t* __restrict__ slot_mapping, const __nv_bfloat16* __restrict__ cos_sin,
+                    __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int n_q, int n_kv) {
+  const int t = blockIdx.x;
+  const int head = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int i = threadIdx.x & 63;
+  const int n_heads = n_q + 2 * n_kv;
+  if (head >= n_heads) return;
+  __nv_bfloat16* h = qkv + ((size_t)t * n_heads + head) * HEAD_DIM;
+  const int slot = slot_mapping[t];
+  if (head < n_q + n_kv) {
+    const int pos = positions[t];
+    const float c = __bfloat162float(cos_sin[(size_t)pos * HEAD_DIM + i]);
+    const float s = __bfloat162float(cos_sin[(size_t)pos * HEAD_DIM + 64 + i]);
+    const float x1 = __bfloat162float(h[i]), x2 = __bfloat162float(h[i + 64]);
+    const __nv_bfloat16 o1 = __float2bfloat16_rn(bf16_round(x1 * c) - bf16_round(x2 * s));
+    const __nv_bfloat16 o2 = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
+    h[i] = o1;
+    h[i + 64] = o2;
+    if (head >= n_q && slot >= 0) {
+      const int kvh = head - n_q;
+      const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
+      __nv_bfloat16* kb = k_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM);
+      // K layout: [chunk = d/8][token][d%8]
+      kb[((i >> 3) * KV_BLOCK + off) * 8 + (i & 7)] = o1;
+      kb[(((i + 64) >> 3) * KV_BLOCK + off) * 8 + (i & 7)] = o2;
+    }
+  } else if (slot >= 0) {
+    const int kvh = head - n_q - n_kv;
+    const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
+    __nv_bfloat16* vb = v_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM) + (size_t)off * HEAD_DIM;
+    // V layout: [token][16-byte chunk ^ (token & 7)][8]  (bank-conflict-free ldmatrix / LDS.64 in attention.cu)
+    vb[(((i >> 3) ^ (off & 7)) << 3) + (i & 7)] = h[i];
+    vb[((((i + 64) >> 3) ^ (off & 7)) << 3) + (i & 7)] = h[i + 64];
+  }
+}
+
+cudaError_t rope_kvwrite_launch(__nv_bfloat16* qkv, const int32_t* positions, const int32_t* slot_mapping,
+                                const __nv_bfloat16* cos_sin, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int T,
+                                int n_q, int n_kv, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  const int n_heads = n_q + 2 * n_kv;
+  dim3 grid(T, (n_heads + 3) / 4);
+  rope_kvwrite_kernel<<<grid, 256, 0, stream>>>(qkv, positions, slot_mapping, cos_sin, k_cache, v_cache, n_q, n_kv);
+  return cudaGetLastError();
+}
+
+}  // namespace tgis

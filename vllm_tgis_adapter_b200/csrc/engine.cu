@@ -1,0 +1,913 @@
+// libtgis_engine.so — continuous-batching engine + C ABI (include/tgis_engine.h).
+//
+// This is the B200-native replacement for what sits behind `self.engine.generate(...)`
+// (/root/reference/src/vllm_tgis_adapter/grpc/grpc_server.py:222): vLLM's EngineCore busy loop, scheduler,
+// KV block manager, GPUModelRunner and Sampler (SURVEY.md §2.2 K1-K15, §3.2 "THE HOT LOOP").
+//
+//   host side (this file, C++): request queues, paged-KV block allocator, continuous-batching scheduler with chunked
+//       prefill + recompute preemption, stop checks (vllm v1/core/sched/utils.py:94-130), output ring.
+//   device side: one flat token batch per step -> Llama layer stack built from the sm_100a kernels in this directory.
+//       All per-step metadata is packed into ONE pinned staging buffer and shipped with ONE H2D copy; results come
+//       back with ONE D2H copy of SampleOut records.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tgis_engine.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+int fail(const std::string& msg, int code = -1) {
+  g_last_error = msg;
+  return code;
+}
+double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+#define CK(expr)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" +   \
+                      std::to_string(__LINE__) + ")");                                                  \
+  } while (0)
+
+using bf16 = __nv_bfloat16;
+using namespace tgis;
+
+struct Request {
+  std::string id;
+  std::vector<int32_t> tokens;  // prompt + generated
+  int n_prompt = 0;
+  int n_computed = 0;  // tokens whose K/V are in the cache
+  tgis_sampling_params sp{};
+  int slot = -1;
+  std::vector<int32_t> blocks;
+  bool aborted = false;
+  uint64_t seed = 0;
+  double ts_arrival = 0, ts_first_sched = 0, ts_first_token = 0, ts_last_token = 0;
+  int n_out() const { return (int)tokens.size() - n_prompt; }
+};
+
+struct Sched {  // one scheduled sequence of the current step
+  Request* r;
+  int q_len;
+  bool sample;
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    n = count;
+    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  void zero() { CK(cudaMemset(p, 0, n * sizeof(T))); }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+struct LayerW {
+  bf16 *wqkv, *wo, *wgu, *wd, *ln1, *ln2;
+  CUtensorMap m_qkv, m_o, m_gu, m_d;
+};
+
+constexpr int N_BT = 5;
+const int BT_VALUES[N_BT] = {16, 32, 64, 128, 256};
+int bt_index(int T) {
+  int bt = gemm_pick_bt(T);
+  for (int i = 0; i < N_BT; ++i)
+    if (BT_VALUES[i] == bt) return i;
+  return N_BT - 1;
+}
+
+}  // namespace
+
+struct tgis_engine {
+  tgis_config cfg{};
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int q_dim = 0, qkv_dim = 0, bt_stride = 0, max_splits_cap = 0, bitmap_words = 0;
+  int T_max = 0, S_max = 0, tiles_max = 0;
+
+  // weights
+  DevBuf<bf16> w_arena;
+  bf16 *embed = nullptr, *lm_head = nullptr, *final_norm = nullptr, *cos_sin = nullptr;
+  bool lm_head_loaded = false, cos_sin_loaded = false;
+  std::vector<LayerW> layers;
+  CUtensorMap m_lm{};
+  // kv cache
+  DevBuf<bf16> k_cache, v_cache;
+  size_t kv_layer_elems = 0;
+  int num_blocks = 0;
+  std::vector<int32_t> free_blocks;
+  // activations
+  DevBuf<bf16> resid, xn, qkv, attn_out, tmp, gate_up, act, last_hidden, logits;
+  CUtensorMap xm_xn[N_BT], xm_attn[N_BT], xm_act[N_BT], xm_last[N_BT];
+  DevBuf<float> gemm_ws, part_o, part_ml, samp_scratch;
+  DevBuf<int> gemm_counters, dec_counters;
+  DevBuf<uint32_t> seen_bitmap;
+  DevBuf<SampleOut> d_samp_out;
+  SampleOut* h_samp_out = nullptr;
+  // staging
+  uint8_t* h_stage = nullptr;
+  DevBuf<uint8_t> d_stage;
+  size_t off_tok = 0, off_pos = 0, off_slotmap = 0, off_tokslot = 0, off_seqs = 0, off_decids = 0, off_tileseq = 0,
+         off_tileq0 = 0, off_samplesrc = 0, off_rows = 0, off_bt = 0, stage_bytes = 0;
+
+  // host state
+  std::mutex mu;
+  std::condition_variable cv_in, cv_out;
+  std::deque<std::unique_ptr<Request>> incoming;
+  std::vector<std::string> abort_ids;
+  std::deque<std::unique_ptr<Request>> waiting;
+  std::vector<std::unique_ptr<Request>> running;
+  std::deque<tgis_step_output> outputs;
+  std::vector<int> free_slots;
+  std::thread th;
+  std::atomic<bool> stop_flag{false}, thread_alive{false}, errored{false};
+  std::string error_msg;
+  bool started = false, ready = false;
+  std::mt19937_64 rng;
+  // stats
+  std::atomic<long long> n_steps{0}, n_tokens{0}, n_launches{0};
+  double gpu_ms = 0;
+
+  ~tgis_engine() {
+    if (h_stage) cudaFreeHost(h_stage);
+    if (h_samp_out) cudaFreeHost(h_samp_out);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // ------------------------------------------------------------------------------------------------ setup
+  void init() {
+    const tgis_config& c = cfg;
+    CK(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10) throw CudaError("tgis_engine requires an sm_100 (B200) device; found sm_" +
+                                          std::to_string(prop.major) + std::to_string(prop.minor));
+    num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    q_dim = c.n_q_heads * HEAD_DIM;
+    qkv_dim = (c.n_q_heads + 2 * c.n_kv_heads) * HEAD_DIM;
+    bt_stride = (c.max_model_len + KV_BLOCK - 1) / KV_BLOCK;
+    max_splits_cap = (c.max_model_len + DECODE_SPLIT - 1) / DECODE_SPLIT;
+    bitmap_words = (c.vocab + 31) / 32;
+    T_max = c.max_batched_tokens;
+    S_max = c.max_num_seqs;
+    // TMA boxes are up to 256 rows tall: keep every activation tensor at least that tall
+    const size_t T_alloc = std::max(T_max, 256), S_alloc = std::max(S_max, 256);
+    tiles_max = T_max / 16 + S_max + 1;
+    rng.seed(c.seed ? c.seed : 0x5DEECE66Dull);
+
+    // ---- weights: one arena
+    const size_t H = c.hidden, F = c.ffn, V = c.vocab, L = c.n_layers;
+    const size_t per_layer = (size_t)qkv_dim * H + H * q_dim + 2 * F * H + H * F + 2 * H;
+    const size_t total = V * H /*embed*/ + V * H /*lm_head*/ + H /*norm*/ + (size_t)c.max_model_len * HEAD_DIM +
+                         L * per_layer + 64 * (6 * L + 8);
+    w_arena.alloc(total);
+    bf16* p = w_arena.p;
+    auto take = [&](size_t n) {
+      bf16* r = p;
+      p += (n + 63) / 64 * 64;  // 128-B aligned slices (TMA needs 16 B)
+      return r;
+    };
+    embed = take(V * H);
+    lm_head = take(V * H);
+    final_norm = take(H);
+    cos_sin = take((size_t)c.max_model_len * HEAD_DIM);
+    layers.resize(L);
+    for (auto& l : layers) {
+      l.wqkv = take((size_t)qkv_dim * H);
+      l.wo = take(H * q_dim);
+      l.wgu = take(2 * F * H);
+      l.wd = take(H * F);
+      l.ln1 = take(H);
+      l.ln2 = take(H);
+    }
+    default_rope_table();
+
+    // ---- activations
+    resid.alloc(T_alloc * H);
+    xn.alloc(T_alloc * H);
+    qkv.alloc(T_alloc * qkv_dim);
+    attn_out.alloc(T_alloc * q_dim);
+    tmp.alloc(T_alloc * H);
+    gate_up.alloc(T_alloc * 2 * F);
+    act.alloc(T_alloc * F);
+    last_hidden.alloc(S_alloc * H);
+    logits.alloc((size_t)S_max * V);
+    xn.zero(); attn_out.zero(); act.zero(); last_hidden.zero();
+    gemm_ws.alloc(gemm_workspace_bytes(num_sms) / sizeof(float));
+    gemm_counters.alloc(1 << 16);
+    gemm_counters.zero();
+    const int G = c.n_q_heads / c.n_kv_heads;
+    part_o.alloc((size_t)S_max * c.n_kv_heads * max_splits_cap * G * HEAD_DIM);
+    part_ml.alloc((size_t)S_max * c.n_kv_heads * max_splits_cap * G * 2);
+    dec_counters.alloc((size_t)S_max * c.n_kv_heads);
+    dec_counters.zero();
+    samp_scratch.alloc((size_t)S_max * V);
+    seen_bitmap.alloc((size_t)S_max * bitmap_words);
+    seen_bitmap.zero();
+    d_samp_out.alloc(S_max);
+    CK(cudaHostAlloc(&h_samp_out, sizeof(SampleOut) * S_max, cudaHostAllocDefault));
+
+    // ---- staging layout
+    size_t o = 0;
+    auto place = [&](size_t bytes) {
+      size_t r = o;
+      o += (bytes + 255) / 256 * 256;
+      return r;
+    };
+    off_tok = place(4 * (size_t)T_max);
+    off_pos = place(4 * (size_t)T_max);
+    off_slotmap = place(4 * (size_t)T_max);
+    off_tokslot = place(4 * (size_t)T_max);
+    off_seqs = place(sizeof(AttnSeq) * (size_t)S_max);
+    off_decids = place(4 * (size_t)S_max);
+    off_tileseq = place(4 * (size_t)tiles_max);
+    off_tileq0 = place(4 * (size_t)tiles_max);
+    off_samplesrc = place(4 * (size_t)S_max);
+    off_rows = place(sizeof(SampleRow) * (size_t)S_max);
+    off_bt = place(4 * (size_t)S_max * bt_stride);
+    stage_bytes = o;
+    CK(cudaHostAlloc(&h_stage, stage_bytes, cudaHostAllocDefault));
+    memset(h_stage, 0, stage_bytes);
+    d_stage.alloc(stage_bytes);
+    d_stage.zero();
+
+    // ---- tensor maps (weights: box 128 rows x 64 k; activations: box BT rows x 64 k)
+    auto wmap = [&](CUtensorMap* m, const bf16* w, size_t rows, size_t cols) {
+      if (make_tmap_bf16_2d(m, w, rows, cols, cols, 128, 64) != 0) throw CudaError("cuTensorMapEncodeTiled(weight) failed");
+    };
+    for (auto& l : layers) {
+      wmap(&l.m_qkv, l.wqkv, qkv_dim, H);
+      wmap(&l.m_o, l.wo, H, q_dim);
+      wmap(&l.m_gu, l.wgu, 2 * F, H);
+      wmap(&l.m_d, l.wd, H, F);
+    }
+    wmap(&m_lm, lm_head, V, H);
+    for (int i = 0; i < N_BT; ++i) {
+      const int bt = BT_VALUES[i];
+      auto xmap = [&](CUtensorMap* m, const bf16* x, size_t rows, size_t cols) {
+        if (make_tmap_bf16_2d(m, x, rows, cols, cols, bt, 64) != 0)
+          throw CudaError("cuTensorMapEncodeTiled(activation) failed");
+      };
+      xmap(&xm_xn[i], xn.p, T_alloc, H);
+      xmap(&xm_attn[i], attn_out.p, T_alloc, q_dim);
+      xmap(&xm_act[i], act.p, T_alloc, F);
+      xmap(&xm_last[i], last_hidden.p, S_alloc, H);
+    }
+
+    // ---- KV cache
+    const size_t block_elems = (size_t)c.n_kv_heads * KV_BLOCK * HEAD_DIM;  // per layer, per K or V
+    size_t kv_bytes = c.kv_cache_bytes;
+    if (kv_bytes == 0) {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      const float frac = c.gpu_mem_fraction > 0 ? c.gpu_mem_fraction : 0.85f;
+      kv_bytes = (size_t)(free_b * (double)frac);
+    }
+    const size_t bytes_per_block = 2 * L * block_elems * sizeof(bf16);
+    size_t nb = kv_bytes / bytes_per_block;
+    const size_t nb_cap = (size_t)S_max * bt_stride + 1;  // more can never be used
+    nb = std::min(nb, nb_cap);
+    if (nb < (size_t)bt_stride) throw CudaError("KV cache too small for one max_model_len sequence");
+    num_blocks = (int)nb;
+    kv_layer_elems = nb * block_elems;
+    k_cache.alloc(L * kv_layer_elems);
+    v_cache.alloc(L * kv_layer_elems);
+    k_cache.zero();  // finite garbage invariant: masked slots must never hold NaN/Inf (see attention.cu)
+    v_cache.zero();
+    free_blocks.resize(num_blocks);
+    for (int i = 0; i < num_blocks; ++i) free_blocks[i] = num_blocks - 1 - i;
+    free_slots.resize(S_max);
+    for (int i = 0; i < S_max; ++i) free_slots[i] = S_max - 1 - i;
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaDeviceSynchronize());
+    ready = true;
+  }
+
+  void default_rope_table() {
+    // HF LlamaRotaryEmbedding: inv_freq fp32, freqs = pos * inv_freq (fp32), cos/sin fp32 -> model dtype.
+    const int half = HEAD_DIM / 2;
+    std::vector<bf16> tab((size_t)cfg.max_model_len * HEAD_DIM);
+    for (int pos = 0; pos < cfg.max_model_len; ++pos)
+      for (int i = 0; i < half; ++i) {
+        const float inv = (float)(1.0 / std::pow((double)cfg.rope_theta, (double)(2 * i) / HEAD_DIM));
+        const float f = (float)pos * inv;
+        tab[(size_t)pos * HEAD_DIM + i] = __float2bfloat16_rn((float)std::cos((double)f));
+        tab[(size_t)pos * HEAD_DIM + half + i] = __float2bfloat16_rn((float)std::sin((double)f));
+      }
+    CK(cudaMemcpy(cos_sin, tab.data(), tab.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
+
+  int load_weight(const std::string& name, const void* ptr, int64_t rows, int64_t cols) {
+    const tgis_config& c = cfg;
+    const int64_t H = c.hidden, F = c.ffn, V = c.vocab;
+    bf16* dst = nullptr;
+    int64_t er = 0, ec = 0;
+    if (name == "model.embed_tokens.weight") { dst = embed; er = V; ec = H; }
+    else if (name == "lm_head.weight") { dst = lm_head; er = V; ec = H; lm_head_loaded = true; }
+    else if (name == "model.norm.weight") { dst = final_norm; er = H; ec = 1; }
+    else if (name == "tgis.rope_cos_sin") { dst = cos_sin; er = c.max_model_len; ec = HEAD_DIM; cos_sin_loaded = true; }
+    else if (name.rfind("model.layers.", 0) == 0) {
+      const size_t dot = name.find('.', 13);
+      if (dot == std::string::npos) return fail("bad weight name " + name);
+      const int li = atoi(name.substr(13, dot - 13).c_str());
+      if (li < 0 || li >= c.n_layers) return fail("layer index out of range in " + name);
+      LayerW& l = layers[li];
+      const std::string sub = name.substr(dot + 1);
+      const int64_t kvd = (int64_t)c.n_kv_heads * HEAD_DIM;
+      if (sub == "self_attn.q_proj.weight") { dst = l.wqkv; er = q_dim; ec = H; }
+      else if (sub == "self_attn.k_proj.weight") { dst = l.wqkv + (size_t)q_dim * H; er = kvd; ec = H; }
+      else if (sub == "self_attn.v_proj.weight") { dst = l.wqkv + (size_t)(q_dim + kvd) * H; er = kvd; ec = H; }
+      else if (sub == "self_attn.o_proj.weight") { dst = l.wo; er = H; ec = q_dim; }
+      else if (sub == "mlp.gate_proj.weight") { dst = l.wgu; er = F; ec = H; }
+      else if (sub == "mlp.up_proj.weight") { dst = l.wgu + (size_t)F * H; er = F; ec = H; }
+      else if (sub == "mlp.down_proj.weight") { dst = l.wd; er = H; ec = F; }
+      else if (sub == "input_layernorm.weight") { dst = l.ln1; er = H; ec = 1; }
+      else if (sub == "post_attention_layernorm.weight") { dst = l.ln2; er = H; ec = 1; }
+      else return fail("unknown layer weight " + name);
+    } else {
+      return fail("unknown weight " + name);
+    }
+    if (rows * cols != er * ec) return fail("shape mismatch for " + name + ": got " + std::to_string(rows) + "x" +
+                                            std::to_string(cols) + " expected " + std::to_string(er) + "x" + std::to_string(ec));
+    cudaError_t e = cudaMemcpy(dst, ptr, (size_t)(er * ec) * sizeof(bf16), cudaMemcpyDefault);
+    if (e != cudaSuccess) return fail(std::string("cudaMemcpy(weight) failed: ") + cudaGetErrorString(e));
+    return 0;
+  }
+
+  void finalize_weights() {
+    if (!lm_head_loaded)  // tie_word_embeddings
+      CK(cudaMemcpy(lm_head, embed, (size_t)cfg.vocab * cfg.hidden * sizeof(bf16), cudaMemcpyDeviceToDevice));
+  }
+
+  // ------------------------------------------------------------------------------------------------ device step
+  void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, bf16* Y, int T, int N, int K) {
+    if (cfg.debug_gemm_ref) {
+      CK(gemm_bf16_ref_launch(X, K, W, Y, N, T, N, K, stream));
+    } else {
+      CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, N, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream));
+    }
+    ++n_launches;
+  }
+
+  template <class T>
+  T* hs(size_t off) { return reinterpret_cast<T*>(h_stage + off); }
+  template <class T>
+  T* ds(size_t off) { return reinterpret_cast<T*>(d_stage.p + off); }
+
+  // returns number of sampled rows
+  int run_batch(std::vector<Sched>& batch) {
+    const tgis_config& c = cfg;
+    const int H = c.hidden, F = c.ffn, V = c.vocab;
+    int T = 0, n_dec = 0, n_tiles = 0, R = 0, max_dec_kv = 0;
+    int32_t* tok = hs<int32_t>(off_tok);
+    int32_t* pos = hs<int32_t>(off_pos);
+    int32_t* slotmap = hs<int32_t>(off_slotmap);
+    int32_t* tokslot = hs<int32_t>(off_tokslot);
+    AttnSeq* seqs = hs<AttnSeq>(off_seqs);
+    int32_t* decids = hs<int32_t>(off_decids);
+    int32_t* tileseq = hs<int32_t>(off_tileseq);
+    int32_t* tileq0 = hs<int32_t>(off_tileq0);
+    int32_t* samplesrc = hs<int32_t>(off_samplesrc);
+    SampleRow* rows = hs<SampleRow>(off_rows);
+    int32_t* bt = hs<int32_t>(off_bt);
+    const int S = (int)batch.size();
+    for (int s = 0; s < S; ++s) {
+      Request& r = *batch[s].r;
+      const int q_len = batch[s].q_len;
+      const int kv_len = r.n_computed + q_len;
+      seqs[s] = AttnSeq{T, q_len, kv_len, s};
+      memcpy(bt + (size_t)s * bt_stride, r.blocks.data(), sizeof(int32_t) * r.blocks.size());
+      for (int j = 0; j < q_len; ++j) {
+        const int p = r.n_computed + j;
+        tok[T + j] = r.tokens[p];
+        pos[T + j] = p;
+        slotmap[T + j] = r.blocks[p / KV_BLOCK] * KV_BLOCK + p % KV_BLOCK;
+        tokslot[T + j] = r.slot;
+      }
+      if (q_len == 1) {
+        decids[n_dec++] = s;
+        max_dec_kv = std::max(max_dec_kv, kv_len);
+      } else {
+        for (int q0 = 0; q0 < q_len; q0 += 16) {
+          tileseq[n_tiles] = s;
+          tileq0[n_tiles++] = q0;
+        }
+      }
+      if (batch[s].sample) {
+        const tgis_sampling_params& sp = r.sp;
+        SampleRow& row = rows[R];
+        memset(&row, 0, sizeof(row));
+        const int n_out = r.n_out();
+        row.flags = (sp.greedy ? SAMPLE_GREEDY : 0) | (sp.num_logprobs > 0 ? SAMPLE_LOGPROBS : 0) |
+                    ((!sp.greedy && sp.typical_p > 0.f && sp.typical_p < 1.f) ? SAMPLE_TYPICAL : 0);
+        row.n_topn = std::min<int>(sp.num_logprobs > 0 ? sp.num_logprobs : 0, MAX_TOPN);
+        row.temperature = sp.greedy ? 1.f : sp.temperature;
+        row.top_k = sp.greedy ? 0 : sp.top_k;
+        row.top_p = sp.greedy ? 1.f : ((sp.top_p > 0.f && sp.top_p < 1.f) ? sp.top_p : 1.f);
+        row.typical_p = sp.typical_p;
+        row.rep_penalty = sp.repetition_penalty > 0.f ? sp.repetition_penalty : 1.f;
+        row.len_decay_factor = 0.f;
+        if (sp.has_length_penalty) {
+          // reference: tgis_utils/logits_processors.py:38-46  p_factor = pow(penalty, max(0, n_out - start)) (python
+          // double); logit + |logit| * (p_factor - 1) with the scalar cast to fp32
+          const int past = std::max(0, n_out - (int)sp.lp_start_index);
+          const double pf = std::pow((double)sp.lp_decay_factor, (double)past);
+          if (pf != 1.0) {
+            row.flags |= SAMPLE_LENPEN;
+            row.len_decay_factor = (float)(pf - 1.0);
+          }
+        }
+        row.eos_id = sp.eos_token_id;
+        row.n_out = n_out;
+        row.min_tokens = sp.min_tokens;
+        row.seq_slot = r.slot;
+        row.seed_lo = (uint32_t)r.seed;
+        row.seed_hi = (uint32_t)(r.seed >> 32);
+        row.step = (uint32_t)n_out;
+        row.logits_row = R;
+        samplesrc[R] = T + q_len - 1;
+        ++R;
+      }
+      T += q_len;
+    }
+    // ---- ship metadata
+    const size_t copy_bytes = off_bt + sizeof(int32_t) * (size_t)S * bt_stride;
+    CK(cudaEventRecord(ev0, stream));
+    CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
+
+    const int32_t* d_tok = ds<int32_t>(off_tok);
+    const AttnSeq* d_seqs = ds<AttnSeq>(off_seqs);
+    const int32_t* d_bt = ds<int32_t>(off_bt);
+    const float scale = 1.0f / std::sqrt((float)HEAD_DIM);
+
+    CK(bitmap_set_launch(seen_bitmap.p, bitmap_words, ds<int32_t>(off_tokslot), d_tok, T, stream));
+    CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
+    n_launches += 2;
+    for (int li = 0; li < c.n_layers; ++li) {
+      LayerW& l = layers[li];
+      if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+      else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+      ++n_launches;
+      gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H);
+      bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
+      bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
+      CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, c.n_q_heads,
+                             c.n_kv_heads, stream));
+      ++n_launches;
+      if (n_dec > 0) {
+        const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_decids), n_dec, d_bt, bt_stride,
+                              max_splits, part_o.p, part_ml.p, dec_counters.p, attn_out.p, q_dim, c.n_q_heads,
+                              c.n_kv_heads, scale, stream));
+        ++n_launches;
+      }
+      if (n_tiles > 0) {
+        CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
+                               n_tiles, d_bt, bt_stride, attn_out.p, q_dim, c.n_q_heads, c.n_kv_heads, scale,
+                               stream));
+        ++n_launches;
+      }
+      gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim);
+      CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
+      ++n_launches;
+      gemm(xm_xn, l.m_gu, xn.p, l.wgu, gate_up.p, T, 2 * F, H);
+      CK(silu_mul_launch(gate_up.p, act.p, T, F, stream));
+      ++n_launches;
+      gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F);
+    }
+    if (R > 0) {
+      CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
+      CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
+      n_launches += 2;
+      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H);
+      CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words, samp_scratch.p,
+                        d_samp_out.p, stream));
+      ++n_launches;
+      CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    gpu_ms += ms;
+    return R;
+  }
+
+  // ------------------------------------------------------------------------------------------------ scheduler
+  void free_request(Request& r) {
+    for (int b : r.blocks) free_blocks.push_back(b);
+    r.blocks.clear();
+    if (r.slot >= 0) free_slots.push_back(r.slot);
+    r.slot = -1;
+  }
+  bool ensure_blocks(Request& r, int n_tokens) {
+    const int need = (n_tokens + KV_BLOCK - 1) / KV_BLOCK;
+    while ((int)r.blocks.size() < need) {
+      if (free_blocks.empty()) return false;
+      r.blocks.push_back(free_blocks.back());
+      free_blocks.pop_back();
+    }
+    return true;
+  }
+  void emit(const Request& r, bool new_token, const SampleOut* so, int finish, int stop_tok) {
+    tgis_step_output o;
+    memset(&o, 0, sizeof(o));
+    snprintf(o.request_id, sizeof(o.request_id), "%s", r.id.c_str());
+    o.n_new_tokens = new_token ? 1 : 0;
+    if (new_token && so) {
+      o.token_id = so->token;
+      o.logprob = so->logprob;
+      o.rank = so->rank;
+      o.n_topn = r.sp.num_logprobs > 0 ? so->n_topn : 0;
+      for (int i = 0; i < o.n_topn; ++i) {
+        o.topn_ids[i] = so->topn_ids[i];
+        o.topn_logprobs[i] = so->topn_lps[i];
+      }
+    }
+    o.finish_reason = finish;
+    o.stop_token_id = stop_tok;
+    o.n_prompt_tokens = r.n_prompt;
+    o.n_output_tokens = r.n_out();
+    o.ts_arrival = r.ts_arrival;
+    o.ts_first_scheduled = r.ts_first_sched;
+    o.ts_first_token = r.ts_first_token;
+    o.ts_last_token = r.ts_last_token;
+    std::lock_guard<std::mutex> lk(mu);
+    outputs.push_back(o);
+    cv_out.notify_all();
+  }
+
+  // one engine step; returns false when there was nothing to do
+  bool step() {
+    // ---- intake
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      while (!incoming.empty()) {
+        waiting.push_back(std::move(incoming.front()));
+        incoming.pop_front();
+      }
+      for (const std::string& id : abort_ids) {
+        for (auto& r : running)
+          if (r->id == id) r->aborted = true;
+        for (auto& r : waiting)
+          if (r->id == id) r->aborted = true;
+      }
+      abort_ids.clear();
+    }
+    for (size_t i = 0; i < running.size();) {
+      if (running[i]->aborted) {
+        emit(*running[i], false, nullptr, TGIS_FINISH_ABORT, -1);
+        free_request(*running[i]);
+        running.erase(running.begin() + i);
+      } else ++i;
+    }
+    for (size_t i = 0; i < waiting.size();) {
+      if (waiting[i]->aborted) {
+        emit(*waiting[i], false, nullptr, TGIS_FINISH_ABORT, -1);
+        waiting.erase(waiting.begin() + i);
+      } else ++i;
+    }
+    if (running.empty() && waiting.empty()) return false;
+
+    // ---- schedule
+    std::vector<Sched> dec, pre;
+    int budget = T_max;
+    for (size_t i = 0; i < running.size(); ++i) {
+      Request& r = *running[i];
+      int remaining = (int)r.tokens.size() - r.n_computed;
+      if (budget <= 0) break;
+      int q = std::min(remaining, budget);
+      bool ok = ensure_blocks(r, r.n_computed + q);
+      while (!ok && running.size() > i + 1) {  // preempt from the back (recompute later)
+        std::unique_ptr<Request> victim = std::move(running.back());
+        running.pop_back();
+        free_request(*victim);
+        victim->n_computed = 0;
+        waiting.push_front(std::move(victim));
+        ok = ensure_blocks(r, r.n_computed + q);
+      }
+      if (!ok) {  // r itself is the last one: preempt it
+        std::unique_ptr<Request> victim = std::move(running.back());
+        running.pop_back();
+        free_request(*victim);
+        victim->n_computed = 0;
+        waiting.push_front(std::move(victim));
+        break;
+      }
+      budget -= q;
+      Sched s{&r, q, r.n_computed + q == (int)r.tokens.size()};
+      (q == 1 ? dec : pre).push_back(s);
+    }
+    const double t_now = now_s();
+    while (!waiting.empty() && budget > 0 && (int)running.size() < S_max && !free_slots.empty()) {
+      Request& r = *waiting.front();
+      const int remaining = (int)r.tokens.size() - r.n_computed;
+      const int q = std::min(remaining, budget);
+      // admit only if the whole sequence so far fits (keeps chunked prefill from dead-locking the cache)
+      if ((int)free_blocks.size() < ((int)r.tokens.size() + KV_BLOCK) / KV_BLOCK) break;
+      r.slot = free_slots.back();
+      free_slots.pop_back();
+      ensure_blocks(r, r.n_computed + q);
+      CK(bitmap_clear_launch(seen_bitmap.p, bitmap_words, r.slot, stream));
+      ++n_launches;
+      if (r.ts_first_sched == 0) r.ts_first_sched = t_now;
+      budget -= q;
+      Sched s{&r, q, r.n_computed + q == (int)r.tokens.size()};
+      (q == 1 ? dec : pre).push_back(s);
+      running.push_back(std::move(waiting.front()));
+      waiting.pop_front();
+    }
+    std::vector<Sched> batch;
+    batch.reserve(dec.size() + pre.size());
+    batch.insert(batch.end(), dec.begin(), dec.end());
+    batch.insert(batch.end(), pre.begin(), pre.end());
+    if (batch.empty()) {
+      if (!waiting.empty() && running.empty())
+        throw CudaError("request does not fit in the KV cache (" + std::to_string(num_blocks) + " blocks)");
+      return false;
+    }
+
+    // ---- run
+    run_batch(batch);
+    ++n_steps;
+
+    // ---- post-process (vllm v1/core/sched/utils.py:94-130 check_stop)
+    const double t_done = now_s();
+    int R = 0;
+    std::vector<Request*> finished;
+    for (Sched& s : batch) {
+      Request& r = *s.r;
+      r.n_computed += s.q_len;
+      if (!s.sample) continue;
+      const SampleOut& so = h_samp_out[R++];
+      r.tokens.push_back(so.token);
+      ++n_tokens;
+      if (r.ts_first_token == 0) r.ts_first_token = t_done;
+      r.ts_last_token = t_done;
+      int finish = TGIS_FINISH_NONE, stop_tok = -1;
+      const int n_out = r.n_out();
+      if (n_out >= r.sp.min_tokens) {
+        if (so.token == r.sp.eos_token_id) finish = TGIS_FINISH_STOP_EOS;
+        else {
+          for (int k = 0; k < r.sp.n_stop_token_ids; ++k)
+            if (r.sp.stop_token_ids[k] == so.token) {
+              finish = TGIS_FINISH_STOP_TOKEN;
+              stop_tok = so.token;
+            }
+        }
+        if (finish == TGIS_FINISH_NONE && ((int)r.tokens.size() >= cfg.max_model_len || n_out >= r.sp.max_tokens))
+          finish = TGIS_FINISH_LENGTH;
+      }
+      emit(r, true, &so, finish, stop_tok);
+      if (finish != TGIS_FINISH_NONE) finished.push_back(&r);
+    }
+    for (Request* f : finished) {
+      for (size_t i = 0; i < running.size(); ++i)
+        if (running[i].get() == f) {
+          free_request(*running[i]);
+          running.erase(running.begin() + i);
+          break;
+        }
+    }
+    return true;
+  }
+
+  void fail_all(const std::string& msg) {
+    error_msg = msg;
+    errored = true;
+    std::vector<std::unique_ptr<Request>> all;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (auto& r : incoming) all.push_back(std::move(r));
+      incoming.clear();
+    }
+    for (auto& r : waiting) all.push_back(std::move(r));
+    waiting.clear();
+    for (auto& r : running) all.push_back(std::move(r));
+    running.clear();
+    for (auto& r : all) emit(*r, false, nullptr, TGIS_FINISH_ERROR, -1);
+  }
+
+  void loop() {
+    thread_alive = true;
+    cudaSetDevice(cfg.device);
+    while (!stop_flag) {
+      bool did = false;
+      try {
+        did = step();
+      } catch (const std::exception& e) {
+        fail_all(e.what());
+        break;
+      }
+      if (!did) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_in.wait_for(lk, std::chrono::milliseconds(50),
+                       [&] { return stop_flag || !incoming.empty() || !abort_ids.empty(); });
+      }
+    }
+    thread_alive = false;
+    cv_out.notify_all();
+  }
+};
+
+// ==================================================================================================== C ABI
+extern "C" {
+
+const char* tgis_last_error(void) { return g_last_error.c_str(); }
+int tgis_abi_version(void) { return TGIS_ABI_VERSION; }
+
+int tgis_engine_create(const tgis_config* cfg, tgis_engine** out) {
+  if (!cfg || !out) return fail("null argument");
+  if (cfg->abi_version != TGIS_ABI_VERSION) return fail("ABI version mismatch");
+  if (cfg->head_dim != HEAD_DIM) return fail("head_dim must be 128");
+  if (cfg->n_kv_heads <= 0 || cfg->n_q_heads % cfg->n_kv_heads != 0) return fail("n_q_heads must be a multiple of n_kv_heads");
+  const int G = cfg->n_q_heads / cfg->n_kv_heads;
+  if (!(G == 1 || G == 2 || G == 3 || G == 4 || G == 8)) return fail("GQA group size must be 1, 2, 3, 4 or 8");
+  if (cfg->hidden % 64 || cfg->ffn % 64 || cfg->vocab % 8) return fail("hidden/ffn must be multiples of 64, vocab of 8");
+  if (cfg->hidden > 8192) return fail("hidden > 8192 unsupported");
+  if (cfg->tp_size > 1) return fail("tensor parallelism is not built into this revision (tp_size must be 1)");
+  if (cfg->max_batched_tokens < 16 || cfg->max_num_seqs < 1 || cfg->max_model_len < 2) return fail("bad limits");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: the TGIS engine has no CPU fallback");
+  auto* e = new tgis_engine();
+  e->cfg = *cfg;
+  try {
+    e->init();
+  } catch (const std::exception& ex) {
+    std::string m = ex.what();
+    delete e;
+    return fail(m);
+  }
+  *out = e;
+  return 0;
+}
+
+int tgis_engine_load_weight(tgis_engine* e, const char* name, const void* ptr, int64_t rows, int64_t cols, int32_t dtype) {
+  if (!e || !name || !ptr) return fail("null argument");
+  if (dtype != 0) return fail("only bf16 (dtype 0) weights are supported");
+  if (e->started) return fail("engine already started");
+  return e->load_weight(name, ptr, rows, cols);
+}
+
+int tgis_engine_start(tgis_engine* e) {
+  if (!e) return fail("null engine");
+  if (e->started) return 0;
+  try {
+    e->finalize_weights();
+  } catch (const std::exception& ex) {
+    return fail(ex.what());
+  }
+  e->started = true;
+  e->th = std::thread([e] { e->loop(); });
+  return 0;
+}
+
+static int engine_prepare_sync(tgis_engine* e) {
+  if (e->th.joinable()) return fail("run_until_idle cannot be mixed with the engine thread");
+  if (!e->started) {
+    try {
+      e->finalize_weights();
+    } catch (const std::exception& ex) {
+      return fail(ex.what());
+    }
+    e->started = true;
+  }
+  return 0;
+}
+
+int tgis_engine_run_until_idle(tgis_engine* e) {
+  if (!e) return fail("null engine");
+  if (engine_prepare_sync(e) != 0) return -1;
+  int steps = 0;
+  try {
+    while (e->step()) ++steps;
+  } catch (const std::exception& ex) {
+    e->fail_all(ex.what());
+    return fail(ex.what());
+  }
+  return steps;
+}
+
+int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_t* prompt_ids, int32_t n_prompt,
+                            const tgis_sampling_params* params) {
+  if (!e || !request_id || !prompt_ids || !params) return fail("null argument");
+  if (e->errored) return fail("engine errored: " + e->error_msg);
+  if (n_prompt < 1) return fail("empty prompt");
+  if (n_prompt >= e->cfg.max_model_len) return fail("prompt longer than max_model_len");
+  if (strlen(request_id) >= TGIS_MAX_REQUEST_ID) return fail("request id too long");
+  if (params->max_tokens < 1) return fail("max_tokens must be >= 1");
+  if (params->n_stop_token_ids > TGIS_MAX_STOP_TOKEN_IDS || params->n_stop_token_ids < 0) return fail("too many stop token ids");
+  if (!params->greedy && !(params->temperature > 0.f)) return fail("temperature must be > 0 when sampling");
+  if (params->num_logprobs > TGIS_MAX_TOPN) return fail("num_logprobs too large");
+  for (int i = 0; i < n_prompt; ++i)
+    if (prompt_ids[i] < 0 || prompt_ids[i] >= e->cfg.vocab) return fail("prompt token id out of range");
+  auto r = std::make_unique<Request>();
+  r->id = request_id;
+  r->tokens.assign(prompt_ids, prompt_ids + n_prompt);
+  r->n_prompt = n_prompt;
+  r->sp = *params;
+  r->ts_arrival = now_s();
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    r->seed = params->has_seed ? params->seed : e->rng();
+    e->incoming.push_back(std::move(r));
+  }
+  e->cv_in.notify_all();
+  return 0;
+}
+
+int tgis_engine_abort(tgis_engine* e, const char* request_id) {
+  if (!e || !request_id) return fail("null argument");
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->abort_ids.emplace_back(request_id);
+  }
+  e->cv_in.notify_all();
+  return 0;
+}
+
+int tgis_engine_poll(tgis_engine* e, tgis_step_output* out, int32_t cap, int32_t timeout_ms) {
+  if (!e || !out || cap <= 0) return fail("bad argument");
+  std::unique_lock<std::mutex> lk(e->mu);
+  if (e->outputs.empty() && timeout_ms > 0)
+    e->cv_out.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !e->outputs.empty() || e->stop_flag.load(); });
+  int n = 0;
+  while (n < cap && !e->outputs.empty()) {
+    out[n++] = e->outputs.front();
+    e->outputs.pop_front();
+  }
+  return n;
+}
+
+int tgis_engine_status(tgis_engine* e, tgis_status* out) {
+  if (!e || !out) return fail("null argument");
+  memset(out, 0, sizeof(*out));
+  std::lock_guard<std::mutex> lk(e->mu);
+  out->errored = e->errored ? 1 : 0;
+  out->is_running = (e->thread_alive || (e->started && !e->th.joinable() && !e->errored)) ? 1 : 0;
+  out->n_running = (int)e->running.size();
+  out->n_waiting = (int)(e->waiting.size() + e->incoming.size());
+  out->free_blocks = (int)e->free_blocks.size();
+  out->total_blocks = e->num_blocks;
+  out->steps = e->n_steps;
+  out->tokens_generated = e->n_tokens;
+  out->kernel_launches = e->n_launches;
+  out->gpu_busy_ms = e->gpu_ms;
+  if (e->errored) g_last_error = e->error_msg;
+  return 0;
+}
+
+int tgis_engine_max_model_len(tgis_engine* e) { return e ? e->cfg.max_model_len : fail("null engine"); }
+
+int tgis_engine_shutdown(tgis_engine* e) {
+  if (!e) return fail("null engine");
+  e->stop_flag = true;
+  e->cv_in.notify_all();
+  if (e->th.joinable()) e->th.join();
+  e->cv_out.notify_all();
+  return 0;
+}
+
+void tgis_engine_destroy(tgis_engine* e) {
+  if (!e) return;
+  tgis_engine_shutdown(e);
+  cudaSetDevice(e->cfg.device);
+  delete e;
+}
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+// Dense bf16 linear layer  Y[T,N] = X[T,K] · W[N,K]^T  on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces, for the decode/prefill hot path, what the reference reaches through
+//   vllm: model_executor/layers/linear.py (QKVParallelLinear / RowParallelLinear / MergedColumnParallelLinear
+//   -> F.linear -> cuBLAS)  behind grpc_server.py:222 `self.engine.generate(...)`   (SURVEY.md §2.2 K3/K8/K9/K10).
+//
+// Design (B200-first, not a cuBLAS clone):
+//  * swap-AB: the WEIGHT tile [128 rows of N x 64 of K] is the MMA "A" operand (fills the 128 TMEM lanes), the
+//    TOKEN tile [BT x 64] is the "B" operand (UMMA_N = BT in {16..256}).  A decode step (T = 32..256 tokens)
+//    therefore streams every weight byte exactly once at HBM rate with full-width MMAs.
+//  * both operands K-major, 128-byte swizzled, staged by TMA into a STAGES-deep mbarrier ring.
+//  * warp roles: warp0 = TMA producer, warp1 = MMA issuer (single elected lane) + TMEM owner,
+//    warps2..5 = epilogue (TMEM -> registers -> bf16 global).  TMEM accumulator is double-buffered so the
+//    epilogue of unit i overlaps the mainloop of unit i+1.
+//  * persistent stream-K: the (tile, k-block) iteration space is cut into gridDim.x equal contiguous ranges, so all
+//    148 SMs stream the same number of weight bytes whatever N is.  A tile split across CTAs is reduced by the
+//    LAST-arriving CTA summing the fp32 partials in fixed CTA order -> bit-deterministic and independent of timing.
+#include "ptx.cuh"
+#include "kernels.h"
+
+namespace tgis {
+
+constexpr int GEMM_BN = 128;  // weight rows per tile (UMMA_M)
+constexpr int GEMM_BK = 64;   // k per stage (one 128-byte swizzle row of bf16)
+constexpr int GEMM_THREADS = 192;
+
+template <int BT>
+struct GemmCfg {
+  static constexpr int W_BYTES = GEMM_BN * GEMM_BK * 2;
+  static constexpr int X_BYTES = BT * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BT) < 32 ? 32 : (2 * BT);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct UnitIter {
+  // contiguous range [pos, end) of the global (tile, kblock) space owned by this CTA
+  long long pos, end;
+  int kb_per_tile;
+  bool first;
+  __device__ UnitIter(long long total, int kb, int cta, int ncta) : kb_per_tile(kb), first(true) {
+    pos = (total * cta) / ncta;
+    end = (total * (cta + 1)) / ncta;
+  }
+  __device__ bool next(int& tile, int& kb0, int& kb1, int& slot) {
+    if (pos >= end) return false;
+    tile = (int)(pos / kb_per_tile);
+    kb0 = (int)(pos % kb_per_tile);
+    long long rem = end - pos;
+    int room = kb_per_tile - kb0;
+    int take = rem < room ? (int)rem : room;
+    kb1 = kb0 + take;
+    slot = first ? 0 : 1;
+    first = false;
+    pos += take;
+    return true;
+  }
+};
+
+__device__ __forceinline__ int unit_owner(long long p, long long total, int ncta) {
+  return (int)(((p + 1) * ncta - 1) / total);
+}
+
+template <int BT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
+                         __nv_bfloat16* __restrict__ Y, int ldy, int T, int N, int K, float* __restrict__ ws,
+                         int* __restrict__ counters, int stream_weights) {
+  using Cfg = GemmCfg<BT>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + STAGES * Cfg::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  int* flag_smem = reinterpret_cast<int*>(tmem_base_smem + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
+  const int t_tiles = (T + BT - 1) / BT;
+  const int KB = (K + GEMM_BK - 1) / GEMM_BK;
+  const long long total = (long long)n_tiles * t_tiles * KB;
+  const int ncta = gridDim.x, cta = blockIdx.x;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&wmap);
+    tma_prefetch_desc(&xmap);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_base_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint64_t pol_w = policy_evict_first();
+      const uint64_t pol_x = policy_evict_last();
+      UnitIter it(total, KB, cta, ncta);
+      int tile, kb0, kb1, slot;
+      int stage = 0;
+      uint32_t phase = 0;
+      while (it.next(tile, kb0, kb1, slot)) {
+        const int n_tile = tile / t_tiles, t_tile = tile % t_tiles;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (stream_weights)
+            tma_load_2d_hint(&wmap, &full_bar[stage], smem_w + stage * Cfg::W_BYTES, kb * GEMM_BK,
+                             n_tile * GEMM_BN, pol_w);
+          else
+            tma_load_2d(&wmap, &full_bar[stage], smem_w + stage * Cfg::W_BYTES, kb * GEMM_BK, n_tile * GEMM_BN);
+          tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, kb * GEMM_BK, t_tile * BT,
+                           pol_x);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BN, BT);
+    UnitIter it(total, KB, cta, ncta);
+    int tile, kb0, kb1, slot;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_bits = 0;  // per-buffer phase parity
+    while (it.next(tile, kb0, kb1, slot)) {
+      mbar_wait(&tmem_empty[acc], ((acc_bits >> acc) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BT;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_w + stage * Cfg::W_BYTES));
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_x + stage * Cfg::X_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in 16-byte units on the start address
+            tc_mma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc_bits ^= (1u << acc);
+      acc ^= 1;
+    }
+  } else {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int sub = warp & 3;          // TMEM sub-partition this warp may read
+    const int row = sub * 32 + lane_id();  // weight row within the tile
+    const int ep_tid = (warp - 2) * 32 + lane_id();
+    UnitIter it(total, KB, cta, ncta);
+    int tile, kb0, kb1, slot;
+    int acc = 0;
+    uint32_t acc_bits = 0;  // per-buffer phase parity
+    while (it.next(tile, kb0, kb1, slot)) {
+      const int n_tile = tile / t_tiles, t_tile = tile % t_tiles;
+      const int n = n_tile * GEMM_BN + row;
+      const int t_base = t_tile * BT;
+      const int t_valid = min(BT, T - t_base);
+      const bool partial = (kb0 > 0) || (kb1 < KB);
+      mbar_wait(&tmem_full[acc], (acc_bits >> acc) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BT + ((uint32_t)(sub * 32) << 16);
+      float* my_ws = ws + ((size_t)(cta * 2 + slot) * BT) * GEMM_BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BT; c0 += 16) {
+        if (c0 >= t_valid) break;
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(taddr + c0, r);
+        tmem_ld_wait();
+        if (!partial) {
+          if (n < N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < t_valid)
+                Y[(size_t)(t_base + c0 + j) * ldy + n] = __float2bfloat16_rn(__uint_as_float(r[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < t_valid) my_ws[(size_t)(c0 + j) * GEMM_BN + row] = __uint_as_float(r[j]);
+        }
+      }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
+      acc_bits ^= (1u << acc);
+      acc ^= 1;
+
+      if (partial) {
+        // stream-K fix-up: last arriver reduces all partials of this tile in CTA order (deterministic)
+        __threadfence();
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        const long long p0 = (long long)tile * KB;
+        const int c_first = unit_owner(p0, total, ncta);
+        const int c_last = unit_owner(p0 + KB - 1, total, ncta);
+        if (ep_tid == 0) {
+          int old = atomicAdd(&counters[tile], 1);
+          *flag_smem = (old == (c_last - c_first)) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        const int is_last = *flag_smem;
+        if (is_last) {
+          __threadfence();
+          for (int t = 0; t < t_valid; ++t) {
+            float sum = 0.f;
+            for (int c = c_first; c <= c_last; ++c) {
+              const long long cb = (total * c) / ncta;
+              const int cslot = ((int)(cb / KB) == tile) ? 0 : 1;
+              const float* p = ws + ((size_t)(c * 2 + cslot) * BT + t) * GEMM_BN + row;
+              sum += __ldcg(p);
+            }
+            if (n < N) Y[(size_t)(t_base + t) * ldy + n] = __float2bfloat16_rn(sum);
+          }
+          if (ep_tid == 0) counters[tile] = 0;
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");  // flag_smem reuse safety
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+int gemm_pick_bt(int T) {
+  if (T <= 16) return 16;
+  if (T <= 32) return 32;
+  if (T <= 64) return 64;
+  if (T <= 128) return 128;
+  return 256;
+}
+
+size_t gemm_workspace_bytes(int num_sms) { return (size_t)num_sms * 2 * 256 * GEMM_BN * sizeof(float); }
+
+template <int BT>
+static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, __nv_bfloat16* Y, int ldy, int T,
+                             int N, int K, float* ws, int* counters, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
+  long long total = (long long)n_tiles * t_tiles * KB;
+  // do not cut finer than 4 k-blocks per CTA: tiny problems use fewer CTAs
+  long long max_ctas = (total + 3) / 4;
+  int grid = (int)(max_ctas < num_sms ? (max_ctas < 1 ? 1 : max_ctas) : num_sms);
+  const int stream_weights = (t_tiles == 1) ? 1 : 0;
+  gemm_bf16_tcgen05_kernel<BT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(wmap, xmap, Y, ldy, T, N, K, ws,
+                                                                                 counters, stream_weights);
+  return cudaGetLastError();
+}
+
+// xmap must have been built with box_rows == gemm_pick_bt(T)
+cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, __nv_bfloat16* Y, int ldy, int T,
+                             int N, int K, float* ws, int* counters, int num_sms, cudaStream_t stream) {
+  switch (gemm_pick_bt(T)) {
+    case 16: return launch_bt<16>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
+    case 32: return launch_bt<32>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
+    case 64: return launch_bt<64>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
+    case 128: return launch_bt<128>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
+    default: return launch_bt<256>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
+  }
+}
+
+}  // namespace tgis

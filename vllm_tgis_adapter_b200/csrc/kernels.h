@@ -1,0 +1,109 @@
+// Internal launcher declarations for the sm_100a kernels of the TGIS decode/prefill hot path.
+// (Internal C++ header; the drop-in C ABI is include/tgis_engine.h.)
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace tgis {
+
+// ---- gemm_tcgen05.cu --------------------------------------------------------------------------------------------
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols);
+int gemm_pick_bt(int T);
+size_t gemm_workspace_bytes(int num_sms);
+cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, __nv_bfloat16* Y, int ldy, int T,
+                             int N, int K, float* ws, int* counters, int num_sms, cudaStream_t stream);
+
+// ---- gemm_ref.cu (debug cross-check only; never on the product path) ---------------------------------------------
+cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, __nv_bfloat16* Y, int ldy,
+                                 int T, int N, int K, cudaStream_t stream);
+
+// ---- elementwise.cu ----------------------------------------------------------------------------------------------
+cudaError_t embed_gather_launch(const int32_t* token_ids, const __nv_bfloat16* table, __nv_bfloat16* out, int T,
+                                int hidden, int vocab, cudaStream_t stream);
+// out = rmsnorm(x) * w                                   (first layer: residual := x is done by the caller)
+cudaError_t rmsnorm_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
+                           float eps, cudaStream_t stream);
+// residual = bf16(x + residual); out = rmsnorm(residual) * w     (vllm: layernorm.py fused_add_rms_norm)
+cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, const __nv_bfloat16* w,
+                               __nv_bfloat16* out, int T, int hidden, float eps, cudaStream_t stream);
+// act[t, i] = bf16(silu(gate_up[t, i])) * gate_up[t, F + i]
+cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn, cudaStream_t stream);
+// gather rows: out[r, :] = x[rows[r], :]
+cudaError_t gather_rows_launch(const __nv_bfloat16* x, const int32_t* rows, __nv_bfloat16* out, int R, int hidden,
+                               cudaStream_t stream);
+
+// Paged KV cache layout (per layer), chosen for the decode kernel's TMA bulk loads:
+//   K: [num_blocks][n_kv][HEAD_DIM/8][BLOCK][8] bf16  (8-dim chunk major: lanes=tokens read conflict-free 16 B)
+//   V: [num_blocks][n_kv][BLOCK][16 chunks ^ (tok&7)][8] bf16  (row-major with the 16-B chunk index XOR-swizzled)
+// one (block, kv_head) K or V tile is a contiguous BLOCK*HEAD_DIM*2 bytes.
+constexpr int KV_BLOCK = 32;
+constexpr int HEAD_DIM = 128;
+
+// neox RoPE on q,k in-place inside qkv[T, (nq+2nkv)*128] and scatter of k,v into the paged cache.
+// cos_sin: [max_pos][128] bf16 = cos(64) | sin(64)   (vllm: rotary_embedding/base.py cache.to(dtype))
+cudaError_t rope_kvwrite_launch(__nv_bfloat16* qkv, const int32_t* positions, const int32_t* slot_mapping,
+                                const __nv_bfloat16* cos_sin, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int T,
+                                int n_q, int n_kv, cudaStream_t stream);
+
+// ---- attention.cu ------------------------------------------------------------------------------------------------
+struct AttnSeq {        // one entry per sequence scheduled this step (device array)
+  int32_t q_start;      // first row of this sequence's queries in the flat token batch
+  int32_t q_len;        // number of query tokens this step (1 = decode)
+  int32_t kv_len;       // context length INCLUDING this step's tokens
+  int32_t block_row;    // row in the block table
+};
+// Decode (q_len == 1): split-KV over chunks of DECODE_SPLIT tokens, GQA group packed per CTA.
+constexpr int DECODE_SPLIT = 128;
+cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
+                               const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs,
+                               const int32_t* block_table, int bt_stride, int max_splits, float* part_o,
+                               float* part_ml, int* counters, __nv_bfloat16* out, int out_ld, int n_q, int n_kv, float scale,
+                               cudaStream_t stream);
+// Prefill / chunked prefill (q_len >= 1), causal over the paged cache.
+cudaError_t attn_prefill_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
+                                const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* tile_seq,
+                                const int32_t* tile_q0, int n_tiles, const int32_t* block_table, int bt_stride,
+                                __nv_bfloat16* out, int out_ld, int n_q, int n_kv, float scale, cudaStream_t stream);
+
+// ---- sampler.cu --------------------------------------------------------------------------------------------------
+constexpr int MAX_TOPN = 12;  // reference forces max_logprobs >= 11 (tgis_utils/args.py:214-216)
+struct SampleRow {            // per sampled row parameters (device array, 64 B)
+  int32_t flags;              // bit0 greedy, bit1 want_logprobs, bit2 typical, bit3 len_penalty, bit4 seeded
+  int32_t n_topn;             // number of top-n entries to return (0..MAX_TOPN)
+  float temperature;
+  int32_t top_k;              // <=0: off
+  float top_p;                // >=1: off
+  float typical_p;
+  float rep_penalty;          // 1.0: off
+  float len_decay_factor;     // decay ** max(0, n_out - start)  precomputed on host in double, cast to fp32
+  int32_t eos_id;
+  int32_t n_out;              // tokens generated so far
+  int32_t min_tokens;
+  int32_t seq_slot;           // row of the seen-token bitmap
+  uint32_t seed_lo, seed_hi;  // philox key
+  uint32_t step;              // philox counter offset
+  int32_t logits_row;         // row in the logits matrix
+};
+struct SampleOut {            // per row result (pinned host readable)
+  int32_t token;
+  float logprob;
+  int32_t rank;
+  int32_t n_topn;
+  int32_t topn_ids[MAX_TOPN];
+  float topn_lps[MAX_TOPN];
+};
+constexpr int SAMPLE_GREEDY = 1, SAMPLE_LOGPROBS = 2, SAMPLE_TYPICAL = 4, SAMPLE_LENPEN = 8, SAMPLE_SEEDED = 16;
+cudaError_t sampler_launch(const __nv_bfloat16* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+                           const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
+                           cudaStream_t stream);
+// seen-token bitmap maintenance
+cudaError_t bitmap_clear_launch(uint32_t* bitmap, int bitmap_words, int slot, cudaStream_t stream);
+cudaError_t bitmap_set_launch(uint32_t* bitmap, int bitmap_words, const int32_t* slots, const int32_t* tokens, int n,
+                              cudaStream_t stream);
+size_t sampler_scratch_floats(int vocab);
+
+}  // namespace tgis

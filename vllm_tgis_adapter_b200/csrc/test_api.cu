@@ -1,0 +1,189 @@
+// C-ABI test hooks (include/tgis_kernels.h): every hot-path kernel callable on raw device pointers so that the GPU
+// parity tests exercise exactly the code the engine runs, through the same shared library.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tgis_kernels.h"
+#include "kernels.h"
+
+using namespace tgis;
+using bf16 = __nv_bfloat16;
+
+namespace {
+thread_local std::string t_err;
+}  // namespace
+extern "C" const char* tgis_k_last_error(void) { return t_err.c_str(); }
+
+namespace {
+int kfail(const std::string& m) {
+  t_err = m;
+  return -1;
+}
+#define KCK(expr)                                                                          \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) return kfail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+template <class T>
+struct Tmp {
+  T* p = nullptr;
+  ~Tmp() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+  cudaError_t upload(const T* h, size_t n) {
+    cudaError_t e = alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice);
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int tgis_k_sizeof_sample_row(void) { return (int)sizeof(SampleRow); }
+int tgis_k_sizeof_sample_out(void) { return (int)sizeof(SampleOut); }
+int tgis_k_kv_block(void) { return KV_BLOCK; }
+
+int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t N, int32_t K,
+                int32_t x_rows_alloc, int32_t impl, int32_t iters, float* ms_out) {
+  if (iters < 1) iters = 1;
+  cudaStream_t st = 0;
+  cudaEvent_t e0, e1;
+  KCK(cudaEventCreate(&e0));
+  KCK(cudaEventCreate(&e1));
+  if (impl == 1) {
+    KCK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i)
+      KCK(gemm_bf16_ref_launch((const bf16*)x_dev, K, (const bf16*)w_dev, (bf16*)y_dev, N, T, N, K, st));
+    KCK(cudaEventRecord(e1, st));
+  } else {
+    int dev = 0, sms = 148;
+    KCK(cudaGetDevice(&dev));
+    KCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUtensorMap wm, xm;
+    const int bt = gemm_pick_bt(T);
+    if (x_rows_alloc < bt) return kfail("x must have at least one TMA box of rows allocated");
+    if (make_tmap_bf16_2d(&wm, w_dev, N, K, K, 128, 64) != 0) return kfail("weight tensor map failed");
+    if (make_tmap_bf16_2d(&xm, x_dev, x_rows_alloc, K, K, bt, 64) != 0) return kfail("activation tensor map failed");
+    Tmp<float> ws;
+    Tmp<int> ctr;
+    KCK(ws.alloc(gemm_workspace_bytes(sms) / sizeof(float)));
+    KCK(ctr.alloc(1 << 16));
+    KCK(cudaMemset(ctr.p, 0, sizeof(int) << 16));
+    KCK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i)
+      KCK(gemm_bf16_launch(wm, xm, (bf16*)y_dev, N, T, N, K, ws.p, ctr.p, sms, st));
+    KCK(cudaEventRecord(e1, st));
+    KCK(cudaStreamSynchronize(st));
+  }
+  KCK(cudaDeviceSynchronize());
+  float ms = 0.f;
+  KCK(cudaEventElapsedTime(&ms, e0, e1));
+  if (ms_out) *ms_out = ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
+int tgis_k_rmsnorm(const void* x_dev, void* residual_dev, const void* w_dev, void* out_dev, int32_t T, int32_t hidden,
+                   float eps) {
+  if (residual_dev)
+    KCK(add_rmsnorm_launch((const bf16*)x_dev, (bf16*)residual_dev, (const bf16*)w_dev, (bf16*)out_dev, T, hidden, eps, 0));
+  else
+    KCK(rmsnorm_launch((const bf16*)x_dev, (const bf16*)w_dev, (bf16*)out_dev, T, hidden, eps, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tgis_k_silu_mul(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn) {
+  KCK(silu_mul_launch((const bf16*)gate_up_dev, (bf16*)act_dev, T, ffn, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* slot_mapping_host,
+                   const void* cos_sin_dev, void* k_cache_dev, void* v_cache_dev, int32_t T, int32_t n_q, int32_t n_kv) {
+  Tmp<int32_t> pos, sm;
+  KCK(pos.upload(positions_host, T));
+  KCK(sm.upload(slot_mapping_host, T));
+  KCK(rope_kvwrite_launch((bf16*)qkv_dev, pos.p, sm.p, (const bf16*)cos_sin_dev, (bf16*)k_cache_dev, (bf16*)v_cache_dev,
+                          T, n_q, n_kv, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev, const int32_t* seqs_host,
+                     int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows, int32_t bt_stride, void* out_dev,
+                     int32_t n_q, int32_t n_kv, float scale) {
+  if (n_kv <= 0 || n_q % n_kv) return kfail("bad head counts");
+  const int G = n_q / n_kv;
+  const int qkv_ld = (n_q + 2 * n_kv) * HEAD_DIM, out_ld = n_q * HEAD_DIM;
+  std::vector<AttnSeq> seqs(n_seqs);
+  std::vector<int32_t> dec, tseq, tq0;
+  int max_kv = 1;
+  for (int s = 0; s < n_seqs; ++s) {
+    seqs[s] = AttnSeq{seqs_host[4 * s], seqs_host[4 * s + 1], seqs_host[4 * s + 2], seqs_host[4 * s + 3]};
+    if (seqs[s].q_len == 1) {
+      dec.push_back(s);
+      max_kv = std::max(max_kv, seqs[s].kv_len);
+    } else {
+      for (int q0 = 0; q0 < seqs[s].q_len; q0 += 16) {
+        tseq.push_back(s);
+        tq0.push_back(q0);
+      }
+    }
+  }
+  Tmp<AttnSeq> d_seqs;
+  Tmp<int32_t> d_dec, d_tseq, d_tq0, d_bt;
+  Tmp<float> po, pml;
+  Tmp<int> ctr;
+  KCK(d_seqs.upload(seqs.data(), n_seqs));
+  KCK(d_dec.upload(dec.data(), dec.size()));
+  KCK(d_tseq.upload(tseq.data(), tseq.size()));
+  KCK(d_tq0.upload(tq0.data(), tq0.size()));
+  KCK(d_bt.upload(block_table_host, (size_t)bt_rows * bt_stride));
+  const int max_splits = (max_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+  const size_t nd = dec.size() ? dec.size() : 1;
+  KCK(po.alloc(nd * n_kv * max_splits * G * HEAD_DIM));
+  KCK(pml.alloc(nd * n_kv * max_splits * G * 2));
+  KCK(ctr.alloc(nd * n_kv));
+  KCK(cudaMemset(ctr.p, 0, sizeof(int) * nd * n_kv));
+  KCK(attn_decode_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)k_cache_dev, (const bf16*)v_cache_dev, d_seqs.p,
+                         d_dec.p, (int)dec.size(), d_bt.p, bt_stride, max_splits, po.p, pml.p, ctr.p, (bf16*)out_dev,
+                         out_ld, n_q, n_kv, scale, 0));
+  KCK(attn_prefill_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)k_cache_dev, (const bf16*)v_cache_dev, d_seqs.p,
+                          d_tseq.p, d_tq0.p, (int)tseq.size(), d_bt.p, bt_stride, (bf16*)out_dev, out_ld, n_q, n_kv,
+                          scale, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
+                   void* seen_bitmap_dev, void* out_host) {
+  Tmp<SampleRow> rows;
+  Tmp<SampleOut> outs;
+  Tmp<float> scratch;
+  Tmp<uint32_t> dummy_bm;
+  KCK(rows.upload((const SampleRow*)rows_host, n_rows));
+  KCK(outs.alloc(n_rows));
+  KCK(scratch.alloc((size_t)n_rows * vocab));
+  uint32_t* bm = (uint32_t*)seen_bitmap_dev;
+  const int words = (vocab + 31) / 32;
+  if (!bm) {
+    // rows may still carry seq_slot >= 0: give them a scratch bitmap big enough for the largest slot
+    int max_slot = 0;
+    for (int i = 0; i < n_rows; ++i) max_slot = std::max(max_slot, ((const SampleRow*)rows_host)[i].seq_slot);
+    KCK(dummy_bm.alloc((size_t)(max_slot + 1) * words));
+    KCK(cudaMemset(dummy_bm.p, 0, sizeof(uint32_t) * (size_t)(max_slot + 1) * words));
+    bm = dummy_bm.p;
+  }
+  KCK(sampler_launch((const bf16*)logits_dev, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
+  KCK(cudaMemcpy(out_host, outs.p, sizeof(SampleOut) * n_rows, cudaMemcpyDeviceToHost));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+}  // extern "C"
