@@ -1,0 +1,223 @@
+"""CPU oracle for the model half of the hot path — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this module; the
+product path (vllm_tgis_adapter_b200) never does and fails loudly without its CUDA library.
+
+It restates, in plain torch CPU ops, the arithmetic that sits behind the reference's single engine call
+`self.engine.generate(...)` (/root/reference/src/vllm_tgis_adapter/grpc/grpc_server.py:222).  That arithmetic is not in
+the reference tree: it is the un-vendored dependency vLLM (pyproject.toml:30 `vllm>=0.10.0`; installed 0.22.0) running a
+HF-format Llama checkpoint.  Restated here, with the file:line each step follows:
+
+  layer stack        vllm model_executor/models/llama.py:316-333 (decoder layer), :228-233 (attention), :117-121 (MLP)
+                     == transformers models/llama/modeling_llama.py (LlamaDecoderLayer.forward)
+  RMSNorm            vllm model_executor/layers/layernorm.py:104,173 ; HF LlamaRMSNorm.forward
+                     (fp32 variance, x*rsqrt -> model dtype, then * weight in model dtype;
+                      fused residual add is done in model dtype first)
+  RoPE (neox)        vllm model_executor/layers/rotary_embedding/base.py:200 ; HF apply_rotary_pos_emb
+                     (cos/sin table computed in fp32 then cast to model dtype, every product rounded to model dtype)
+  attention          causal softmax(q k^T / sqrt(d)) v with fp32 scores/probabilities (flash-attention semantics:
+                     vllm v1/attention/backends/flashinfer.py:1665,1803), output rounded to model dtype
+  SiLU * mul         vllm model_executor/layers/activation.py:117-143 ; HF LlamaMLP.forward
+  logits             vllm model_executor/layers/logits_processor.py:89-104 (lm_head on last-token rows, model dtype)
+
+PARITY PINNING: the reference's own tests hold no numeric golden vector for this path ("parity
+unpinned" for token ids / logprobs).  This oracle is therefore pinned against the third-party implementation it
+restates: tests/test_oracle_cpu.py checks it against transformers' LlamaForCausalLM (fp32, eager) on seeded weights and
+against the fixtures in tests/golden/ produced by oracle/gen_golden.py.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclasses.dataclass
+class LlamaConfig:
+    n_layers: int
+    hidden: int
+    n_q_heads: int
+    n_kv_heads: int
+    ffn: int
+    vocab: int
+    head_dim: int = 128
+    rope_theta: float = 500000.0
+    rms_eps: float = 1e-5
+    max_model_len: int = 2048
+
+    @property
+    def q_dim(self) -> int:
+        return self.n_q_heads * self.head_dim
+
+    @property
+    def kv_dim(self) -> int:
+        return self.n_kv_heads * self.head_dim
+
+
+# Named shapes used across tests / bench (real architectures' dims; weights are synthetic)
+CONFIGS = {
+    "tiny": LlamaConfig(n_layers=2, hidden=256, n_q_heads=4, n_kv_heads=2, ffn=512, vocab=1024, max_model_len=512),
+    "small": LlamaConfig(n_layers=4, hidden=512, n_q_heads=4, n_kv_heads=1, ffn=1536, vocab=4096, max_model_len=1024),
+    # "opt-125m-size" Llama-class stand-in for BASELINE.json configs[0] (12 layers, hidden 768)
+    "125m": LlamaConfig(n_layers=12, hidden=768, n_q_heads=6, n_kv_heads=2, ffn=3072, vocab=50272, max_model_len=2048),
+    "llama3-8b": LlamaConfig(n_layers=32, hidden=4096, n_q_heads=32, n_kv_heads=8, ffn=14336, vocab=128256,
+                             max_model_len=8192),
+    "llama3-70b": LlamaConfig(n_layers=80, hidden=8192, n_q_heads=64, n_kv_heads=8, ffn=28672, vocab=128256,
+                              max_model_len=8192),
+}
+
+
+def synthetic_weights(cfg: LlamaConfig, seed: int = 0, dtype: torch.dtype = torch.bfloat16, std: float = 0.02,
+                      device: str = "cpu") -> dict[str, torch.Tensor]:
+    """HF-style N(0, 0.02) init, norms = 1 (SURVEY.md §7 'hard parts').  HF parameter names."""
+    g = torch.Generator(device=device).manual_seed(seed)
+
+    def rnd(*shape: int) -> torch.Tensor:
+        return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * std).to(dtype)
+
+    w: dict[str, torch.Tensor] = {"model.embed_tokens.weight": rnd(cfg.vocab, cfg.hidden)}
+    for i in range(cfg.n_layers):
+        p = f"model.layers.{i}."
+        w[p + "self_attn.q_proj.weight"] = rnd(cfg.q_dim, cfg.hidden)
+        w[p + "self_attn.k_proj.weight"] = rnd(cfg.kv_dim, cfg.hidden)
+        w[p + "self_attn.v_proj.weight"] = rnd(cfg.kv_dim, cfg.hidden)
+        w[p + "self_attn.o_proj.weight"] = rnd(cfg.hidden, cfg.q_dim)
+        w[p + "mlp.gate_proj.weight"] = rnd(cfg.ffn, cfg.hidden)
+        w[p + "mlp.up_proj.weight"] = rnd(cfg.ffn, cfg.hidden)
+        w[p + "mlp.down_proj.weight"] = rnd(cfg.hidden, cfg.ffn)
+        w[p + "input_layernorm.weight"] = torch.ones(cfg.hidden, dtype=dtype, device=device)
+        w[p + "post_attention_layernorm.weight"] = torch.ones(cfg.hidden, dtype=dtype, device=device)
+    w["model.norm.weight"] = torch.ones(cfg.hidden, dtype=dtype, device=device)
+    w["lm_head.weight"] = rnd(cfg.vocab, cfg.hidden)
+    return w
+
+
+def rope_table(cfg: LlamaConfig, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """[max_model_len, head_dim] = cos(head_dim/2) | sin(head_dim/2) in model dtype.
+
+    HF LlamaRotaryEmbedding (default rope): inv_freq = 1/(theta^(arange(0,d,2)/d)) fp32; freqs = pos*inv_freq fp32;
+    cos/sin fp32 -> .to(dtype).  vLLM: rotary_embedding/base.py `_compute_cos_sin_cache` + `cache.to(dtype)`.
+    """
+    d = cfg.head_dim
+    inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    t = torch.arange(cfg.max_model_len, dtype=torch.float32)
+    freqs = torch.outer(t, inv_freq)
+    return torch.cat([freqs.cos(), freqs.sin()], dim=-1).to(dtype)
+
+
+class SeqState:
+    """Per-sequence KV history (what the paged cache holds for one request)."""
+
+    def __init__(self, cfg: LlamaConfig, dtype: torch.dtype):
+        self.k = [torch.empty(0, cfg.n_kv_heads, cfg.head_dim, dtype=dtype) for _ in range(cfg.n_layers)]
+        self.v = [torch.empty(0, cfg.n_kv_heads, cfg.head_dim, dtype=dtype) for _ in range(cfg.n_layers)]
+        self.n = 0
+
+
+class LlamaOracle:
+    """Flat-batch Llama forward with the model-dtype rounding points of the vLLM/HF path."""
+
+    def __init__(self, cfg: LlamaConfig, weights: dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16):
+        self.cfg = cfg
+        self.dtype = dtype
+        w = {k: v.to(dtype) for k, v in weights.items()}
+        self.embed = w["model.embed_tokens.weight"]
+        self.lm_head = w.get("lm_head.weight", self.embed)
+        self.norm = w["model.norm.weight"]
+        self.layers = []
+        for i in range(cfg.n_layers):
+            p = f"model.layers.{i}."
+            self.layers.append({
+                "qkv": torch.cat([w[p + "self_attn.q_proj.weight"], w[p + "self_attn.k_proj.weight"],
+                                  w[p + "self_attn.v_proj.weight"]], dim=0).contiguous(),
+                "o": w[p + "self_attn.o_proj.weight"],
+                "gu": torch.cat([w[p + "mlp.gate_proj.weight"], w[p + "mlp.up_proj.weight"]], dim=0).contiguous(),
+                "d": w[p + "mlp.down_proj.weight"],
+                "ln1": w[p + "input_layernorm.weight"],
+                "ln2": w[p + "post_attention_layernorm.weight"],
+            })
+        self.cos_sin = rope_table(cfg, dtype)
+
+    # -- building blocks ---------------------------------------------------------------------------------------
+    def _rms(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        xf = x.float()
+        var = xf.pow(2).mean(-1, keepdim=True)
+        return w * (xf * torch.rsqrt(var + self.cfg.rms_eps)).to(self.dtype)
+
+    def _rope(self, x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+        # x [T, heads, d] model dtype; every op below is a model-dtype tensor op (= rounded after each step)
+        half = self.cfg.head_dim // 2
+        cs = self.cos_sin[pos]  # [T, d]
+        cos, sin = cs[:, None, :half], cs[:, None, half:]
+        x1, x2 = x[..., :half], x[..., half:]
+        return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1)
+
+    def _attend(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, first_pos: int) -> torch.Tensor:
+        # q [Tq, nq, d]; k, v [Tk, nkv, d]; query i sits at absolute position first_pos + i
+        cfg = self.cfg
+        g = cfg.n_q_heads // cfg.n_kv_heads
+        kf = k.float().repeat_interleave(g, dim=1)  # [Tk, nq, d]
+        vf = v.float().repeat_interleave(g, dim=1)
+        s = torch.einsum("qhd,khd->hqk", q.float(), kf) * (1.0 / math.sqrt(cfg.head_dim))
+        tq, tk = q.shape[0], k.shape[0]
+        qpos = first_pos + torch.arange(tq)[:, None]
+        mask = torch.arange(tk)[None, :] <= qpos
+        s = s.masked_fill(~mask[None], float("-inf"))
+        p = torch.softmax(s, dim=-1)
+        o = torch.einsum("hqk,khd->qhd", p, vf)
+        return o.to(self.dtype)
+
+    # -- one engine step over a flat batch ----------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, work: list[tuple[SeqState, list[int]]], want_all_logits: bool = False) -> torch.Tensor:
+        """Append `tokens` to each sequence and return the fp32 view of the model-dtype logits of each sequence's
+        last new token ([n_seqs, vocab]); with want_all_logits, of every new token ([T, vocab])."""
+        cfg = self.cfg
+        toks = torch.tensor([t for _, ts in work for t in ts], dtype=torch.long)
+        pos = torch.tensor([st.n + j for st, ts in work for j in range(len(ts))], dtype=torch.long)
+        resid = self.embed[toks]
+        x = None
+        T = toks.numel()
+        for li, L in enumerate(self.layers):
+            if li == 0:
+                xn = self._rms(resid, L["ln1"])
+            else:
+                resid = x + resid
+                xn = self._rms(resid, L["ln1"])
+            qkv = F.linear(xn, L["qkv"])
+            q = qkv[:, : cfg.q_dim].reshape(T, cfg.n_q_heads, cfg.head_dim)
+            k = qkv[:, cfg.q_dim: cfg.q_dim + cfg.kv_dim].reshape(T, cfg.n_kv_heads, cfg.head_dim)
+            v = qkv[:, cfg.q_dim + cfg.kv_dim:].reshape(T, cfg.n_kv_heads, cfg.head_dim)
+            q = self._rope(q, pos)
+            k = self._rope(k, pos)
+            outs = []
+            off = 0
+            for st, ts in work:
+                n = len(ts)
+                st.k[li] = torch.cat([st.k[li], k[off: off + n]], dim=0)
+                st.v[li] = torch.cat([st.v[li], v[off: off + n]], dim=0)
+                outs.append(self._attend(q[off: off + n], st.k[li], st.v[li], st.n))
+                off += n
+            attn = torch.cat(outs, dim=0).reshape(T, cfg.q_dim)
+            x = F.linear(attn, L["o"])
+            resid = x + resid
+            xn = self._rms(resid, L["ln2"])
+            gu = F.linear(xn, L["gu"])
+            act = F.silu(gu[:, : cfg.ffn]) * gu[:, cfg.ffn:]
+            x = F.linear(act, L["d"])
+        resid = x + resid
+        xn = self._rms(resid, self.norm)
+        for st, ts in work:
+            st.n += len(ts)
+        if not want_all_logits:
+            last, off = [], 0
+            for _, ts in work:
+                off += len(ts)
+                last.append(off - 1)
+            xn = xn[torch.tensor(last)]
+        return F.linear(xn, self.lm_head).float()
+
+    def new_seq(self) -> SeqState:
+        return SeqState(self.cfg, self.dtype)

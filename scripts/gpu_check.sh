@@ -1,0 +1,22 @@
+#!/bin/bash
+# One gpurun call: kernel parity tests, engine parity tests, (optionally) bench + profiles.  Everything is wrapped in
+# `timeout` and logs into gpurun_out/ so a failure in one stage still returns the evidence of the others.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,driver_version --format=csv > gpurun_out/gpu_info.txt 2>&1
+nproc >> gpurun_out/gpu_info.txt; free -g | head -2 >> gpurun_out/gpu_info.txt
+STAGES="${1:-kernels engine}"
+for st in $STAGES; do
+  case $st in
+    kernels) timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x --no-header -p no:cacheprovider > gpurun_out/test_kernels.log 2>&1; echo "kernels rc=$?" ;;
+    kernels_all) timeout 1200 python -m pytest tests/test_kernels_gpu.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/test_kernels.log 2>&1; echo "kernels rc=$?" ;;
+    engine) timeout 900 python -m pytest tests/test_engine_gpu.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/test_engine.log 2>&1; echo "engine rc=$?" ;;
+    all) timeout 1800 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/test_all.log 2>&1; echo "all rc=$?" ;;
+    smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
+    bench) timeout 1500 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" ;;
+    gemmbench) timeout 600 python scripts/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
+    *) echo "unknown stage $st" ;;
+  esac
+done
+tail -n 25 gpurun_out/test_kernels.log gpurun_out/test_engine.log 2>/dev/null

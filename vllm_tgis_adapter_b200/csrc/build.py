@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread",
+    # bounded mbarrier spins: a pipeline-protocol bug traps (sticky CUDA error) instead of hanging the GPU box
+    "-DTGIS_MBAR_TIMEOUT=1",
 ]
 
 

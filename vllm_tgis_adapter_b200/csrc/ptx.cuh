@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace tgis {
 
@@ -56,7 +57,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded spin: a protocol bug traps (-> sticky CUDA error surfaced to the host) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifdef TGIS_MBAR_TIMEOUT
-  for (uint64_t it = 0; it < (1ull << 26); ++it)
+  for (uint64_t it = 0; it < (1ull << 22); ++it)
     if (mbar_try_wait(bar, parity)) return;
   printf("mbar_wait timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
   __trap();

@@ -1,0 +1,190 @@
+"""Thin object wrapper over the C ABI (include/tgis_engine.h).  No arithmetic happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Iterable
+
+from . import _lib
+from ._lib import TgisConfig, TgisSamplingParams, TgisStatus, TgisStepOutput
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+@dataclasses.dataclass
+class ModelConfig:
+    """Llama-architecture dims (HF config.json names in comments)."""
+
+    n_layers: int        # num_hidden_layers
+    hidden: int          # hidden_size
+    n_q_heads: int       # num_attention_heads
+    n_kv_heads: int      # num_key_value_heads
+    ffn: int             # intermediate_size
+    vocab: int           # vocab_size
+    head_dim: int = 128
+    rope_theta: float = 500000.0
+    rms_eps: float = 1e-5
+    max_model_len: int = 2048
+
+
+@dataclasses.dataclass
+class StepOutput:
+    request_id: str
+    new_token: int | None
+    logprob: float
+    rank: int
+    topn: list[tuple[int, float]]
+    finish_reason: int
+    stop_token_id: int
+    n_prompt_tokens: int
+    n_output_tokens: int
+    ts_arrival: float
+    ts_first_scheduled: float
+    ts_first_token: float
+    ts_last_token: float
+
+
+def make_sampling_params(*, greedy: bool = True, temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0,
+                         typical_p: float = 0.0, repetition_penalty: float = 1.0,
+                         length_penalty: tuple[int, float] | None = None, eos_token_id: int = 2, min_tokens: int = 0,
+                         max_tokens: int = 16, num_logprobs: int = 0, seed: int | None = None,
+                         stop_token_ids: Iterable[int] = ()) -> TgisSamplingParams:
+    sp = TgisSamplingParams()
+    sp.greedy = 1 if greedy else 0
+    sp.temperature = float(temperature)
+    sp.top_k = int(top_k)
+    sp.top_p = float(top_p)
+    sp.typical_p = float(typical_p)
+    sp.repetition_penalty = float(repetition_penalty)
+    sp.has_length_penalty = 1 if length_penalty is not None else 0
+    if length_penalty is not None:
+        sp.lp_start_index = int(length_penalty[0])
+        sp.lp_decay_factor = float(length_penalty[1])
+    sp.eos_token_id = int(eos_token_id)
+    sp.min_tokens = int(min_tokens)
+    sp.max_tokens = int(max_tokens)
+    sp.num_logprobs = int(num_logprobs)
+    sp.prompt_logprobs = 0
+    sp.has_seed = 1 if seed is not None else 0
+    sp.seed = int(seed or 0)
+    ids = list(stop_token_ids)
+    sp.n_stop_token_ids = len(ids)
+    for i, t in enumerate(ids):
+        sp.stop_token_ids[i] = int(t)
+    return sp
+
+
+class NativeEngine:
+    """Owns one `tgis_engine*`."""
+
+    def __init__(self, model: ModelConfig, *, max_num_seqs: int = 64, max_batched_tokens: int = 2048,
+                 kv_cache_bytes: int = 0, gpu_mem_fraction: float = 0.85, device: int = 0, seed: int = 0,
+                 debug_gemm_ref: bool = False):
+        self.lib = _lib.load_library()
+        self.model = model
+        cfg = TgisConfig()
+        cfg.abi_version = _lib.ABI_VERSION
+        cfg.n_layers, cfg.hidden, cfg.n_q_heads, cfg.n_kv_heads = model.n_layers, model.hidden, model.n_q_heads, model.n_kv_heads
+        cfg.head_dim, cfg.ffn, cfg.vocab = model.head_dim, model.ffn, model.vocab
+        cfg.rope_theta, cfg.rms_eps, cfg.max_model_len = model.rope_theta, model.rms_eps, model.max_model_len
+        cfg.max_num_seqs, cfg.max_batched_tokens = max_num_seqs, max_batched_tokens
+        cfg.kv_cache_bytes, cfg.gpu_mem_fraction = kv_cache_bytes, gpu_mem_fraction
+        cfg.device, cfg.tp_size, cfg.tp_rank = device, 1, 0
+        cfg.use_cuda_graphs, cfg.debug_gemm_ref, cfg.seed = 0, 1 if debug_gemm_ref else 0, seed
+        self._h = C.c_void_p()
+        if self.lib.tgis_engine_create(C.byref(cfg), C.byref(self._h)) != 0:
+            raise EngineError(f"tgis_engine_create failed: {_lib.last_error(self.lib)}")
+        self._poll_buf = (TgisStepOutput * 512)()
+
+    # -- weights ------------------------------------------------------------------------------------------------
+    def load_weight(self, name: str, tensor) -> None:
+        """tensor: contiguous torch bf16 tensor (host or device) — "PyTorch tensors for weights only"."""
+        import torch
+
+        t = tensor.detach()
+        if t.dtype != torch.bfloat16:
+            t = t.to(torch.bfloat16)
+        t = t.contiguous()
+        rows = t.shape[0]
+        cols = t.numel() // rows if rows else 0
+        if self.lib.tgis_engine_load_weight(self._h, name.encode(), C.c_void_p(t.data_ptr()), rows, cols, 0) != 0:
+            raise EngineError(f"load_weight({name}) failed: {_lib.last_error(self.lib)}")
+
+    def load_weights(self, weights: dict) -> None:
+        for k, v in weights.items():
+            self.load_weight(k, v)
+
+    # -- control ------------------------------------------------------------------------------------------------
+    def start(self) -> None:
+        if self.lib.tgis_engine_start(self._h) != 0:
+            raise EngineError(_lib.last_error(self.lib))
+
+    def add_request(self, request_id: str, prompt_ids: list[int], params: TgisSamplingParams) -> None:
+        arr = (C.c_int32 * len(prompt_ids))(*prompt_ids)
+        if self.lib.tgis_engine_add_request(self._h, request_id.encode(), arr, len(prompt_ids), C.byref(params)) != 0:
+            raise EngineError(f"add_request failed: {_lib.last_error(self.lib)}")
+
+    def abort(self, request_id: str) -> None:
+        self.lib.tgis_engine_abort(self._h, request_id.encode())
+
+    def poll(self, timeout_ms: int = 0) -> list[StepOutput]:
+        n = self.lib.tgis_engine_poll(self._h, self._poll_buf, len(self._poll_buf), timeout_ms)
+        if n < 0:
+            raise EngineError(_lib.last_error(self.lib))
+        outs = []
+        for i in range(n):
+            o = self._poll_buf[i]
+            outs.append(StepOutput(
+                request_id=o.request_id.decode(), new_token=o.token_id if o.n_new_tokens else None,
+                logprob=o.logprob, rank=o.rank,
+                topn=[(o.topn_ids[j], o.topn_logprobs[j]) for j in range(o.n_topn)],
+                finish_reason=o.finish_reason, stop_token_id=o.stop_token_id, n_prompt_tokens=o.n_prompt_tokens,
+                n_output_tokens=o.n_output_tokens, ts_arrival=o.ts_arrival, ts_first_scheduled=o.ts_first_scheduled,
+                ts_first_token=o.ts_first_token, ts_last_token=o.ts_last_token))
+        return outs
+
+    def run_until_idle(self) -> int:
+        n = self.lib.tgis_engine_run_until_idle(self._h)
+        if n < 0:
+            raise EngineError(f"run_until_idle failed: {_lib.last_error(self.lib)}")
+        return n
+
+    def status(self) -> TgisStatus:
+        st = TgisStatus()
+        self.lib.tgis_engine_status(self._h, C.byref(st))
+        return st
+
+    @property
+    def max_model_len(self) -> int:
+        return self.lib.tgis_engine_max_model_len(self._h)
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.tgis_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # noqa: D105
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- convenience for tests / bench --------------------------------------------------------------------------
+    def generate_sync(self, prompts: list[list[int]], params: list[TgisSamplingParams] | TgisSamplingParams
+                      ) -> list[list[StepOutput]]:
+        """Submit all prompts, drive the step loop on this thread, return per-request output records."""
+        if not isinstance(params, list):
+            params = [params] * len(prompts)
+        for i, (p, sp) in enumerate(zip(prompts, params)):
+            self.add_request(f"r{i}", p, sp)
+        self.run_until_idle()
+        res: list[list[StepOutput]] = [[] for _ in prompts]
+        while True:
+            outs = self.poll(0)
+            if not outs:
+                break
+            for o in outs:
+                res[int(o.request_id[1:])].append(o)
+        return res
