@@ -20,10 +20,11 @@
 extern "C" {
 #endif
 
-/* y[T,N] = x[T,K] . w[N,K]^T ; impl 0 = tcgen05 kernel, 1 = SIMT cross-check kernel.  x must have >= 256 rows
+/* y[T,N] = x[T,K] . w[N,K]^T ; y is bf16 (out_f32 = 0) or fp32 (out_f32 = 1, the lm_head logits path);
+ * impl 0 = tcgen05 kernel, 1 = SIMT cross-check kernel.  x must have >= 256 rows
  * allocated (TMA box height) or T rows when impl == 1. */
 int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t N, int32_t K, int32_t x_rows_alloc,
-                int32_t impl, int32_t iters, float* ms_out);
+                int32_t impl, int32_t iters, float* ms_out, int32_t out_f32);
 /* residual_dev may be NULL (plain rmsnorm); otherwise residual is updated in place */
 int tgis_k_rmsnorm(const void* x_dev, void* residual_dev, const void* w_dev, void* out_dev, int32_t T, int32_t hidden,
                    float eps);
@@ -36,6 +37,7 @@ int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v
                      int32_t n_q, int32_t n_kv, float scale);
 /* rows_host: n_rows x 64-byte SampleRow records (see csrc/kernels.h); out_host: n_rows x 112-byte SampleOut records;
  * seen_bitmap_dev: [slots][ceil(vocab/32)] uint32 or NULL */
+/* logits_dev: fp32 [rows, ld] */
 int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
                    void* seen_bitmap_dev, void* out_host);
 const char* tgis_k_last_error(void);

@@ -18,7 +18,9 @@ HF-format Llama checkpoint.  Restated here, with the file:line each step follows
   attention          causal softmax(q k^T / sqrt(d)) v with fp32 scores/probabilities (flash-attention semantics:
                      vllm v1/attention/backends/flashinfer.py:1665,1803), output rounded to model dtype
   SiLU * mul         vllm model_executor/layers/activation.py:117-143 ; HF LlamaMLP.forward
-  logits             vllm model_executor/layers/logits_processor.py:89-104 (lm_head on last-token rows, model dtype)
+  logits             vllm model_executor/layers/logits_processor.py:89-104 (lm_head on last-token rows); kept in fp32
+                     here and in the engine (strictly more precise than vLLM's bf16 logits, needed for the 1e-3
+                     logprob contract)
 
 PARITY PINNING: the reference's own tests hold no numeric golden vector for this path ("parity
 unpinned" for token ids / logprobs).  This oracle is therefore pinned against the third-party implementation it
@@ -217,7 +219,9 @@ class LlamaOracle:
                 off += len(ts)
                 last.append(off - 1)
             xn = xn[torch.tensor(last)]
-        return F.linear(xn, self.lm_head).float()
+        # logits stay fp32 (no model-dtype round trip): the engine's lm_head epilogue writes the fp32 accumulator.
+        # vLLM rounds them to bf16 first (logits_processor.py:89-104); see DESIGN.md 'logits precision'.
+        return xn.float() @ self.lm_head.float().t()
 
     def new_seq(self) -> SeqState:
         return SeqState(self.cfg, self.dtype)

@@ -92,20 +92,28 @@ def test_stop_conditions_and_abort(cfg_name="tiny"):
     cfg, weights, outs, _ = _run_engine(cfg_name, prompts, sp, max_num_seqs=4, max_batched_tokens=256,
                                         kv_cache_bytes=32 << 20)
     base = [[r.new_token for r in recs if r.new_token is not None] for recs in outs]
+
+    def first_new(seq, start):  # first index >= start whose token did not occur earlier in the continuation
+        for i in range(start, len(seq)):
+            if seq[i] not in seq[:i]:
+                return i
+        return 0
+
+    k0, k1, k2 = first_new(base[0], 1), first_new(base[1], 1), 0
     sps = [
-        make_sampling_params(greedy=True, max_tokens=8, eos_token_id=base[0][2]),
-        make_sampling_params(greedy=True, max_tokens=8, eos_token_id=2, stop_token_ids=[base[1][3]]),
-        make_sampling_params(greedy=True, max_tokens=8, min_tokens=5, eos_token_id=base[2][1]),
+        make_sampling_params(greedy=True, max_tokens=8, eos_token_id=base[0][k0]),
+        make_sampling_params(greedy=True, max_tokens=8, eos_token_id=2, stop_token_ids=[base[1][k1]]),
+        make_sampling_params(greedy=True, max_tokens=8, min_tokens=5, eos_token_id=base[2][k2]),
     ]
     _, _, outs2, _ = _run_engine(cfg_name, prompts, sps, max_num_seqs=4, max_batched_tokens=256,
                                  kv_cache_bytes=32 << 20)
     t0 = [r.new_token for r in outs2[0] if r.new_token is not None]
-    assert t0 == base[0][:3] and outs2[0][-1].finish_reason == 2
+    assert t0 == base[0][:k0 + 1] and outs2[0][-1].finish_reason == 2
     t1 = [r.new_token for r in outs2[1] if r.new_token is not None]
-    assert t1 == base[1][:4] and outs2[1][-1].finish_reason == 3 and outs2[1][-1].stop_token_id == base[1][3]
-    # min_tokens masks EOS while n_out < 5 -> sequence differs from base after position 1 but must not stop early
+    assert t1 == base[1][:k1 + 1] and outs2[1][-1].finish_reason == 3 and outs2[1][-1].stop_token_id == base[1][k1]
+    # min_tokens masks EOS (= the token greedy would pick first) while n_out < 5: must not appear, must not stop early
     t2 = [r.new_token for r in outs2[2] if r.new_token is not None]
-    assert len(t2) >= 5 and base[2][1] not in t2[:5]
+    assert len(t2) >= 5 and base[2][k2] not in t2[:5]
 
 
 def test_batch_invariance_and_preemption():

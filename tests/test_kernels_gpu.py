@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def g():
-    from tests import gpu_utils
+    import tgis_gpu_utils as gpu_utils
 
     assert torch.cuda.is_available()
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -48,6 +48,16 @@ def test_gemm_tcgen05_matches_fp32_reference(g, T, N, K):
     # bit-deterministic across launches (stream-K fix-up sums in fixed CTA order)
     y2, _ = g.gemm(x, w)
     assert torch.equal(y, y2)
+
+
+def test_gemm_fp32_output_for_logits(g):
+    """lm_head path: the epilogue stores the fp32 accumulator (no bf16 round trip)."""
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = (torch.randn(24, 512, generator=gen, device="cuda")).bfloat16()
+    w = (torch.randn(5000, 512, generator=gen, device="cuda") * 0.02).bfloat16()
+    y, _ = g.gemm(x, w, out_f32=True)
+    ref = x.float() @ w.float().t()
+    assert float((y - ref).abs().max()) < 2e-5 * float(ref.abs().max()) + 1e-5
 
 
 def test_gemm_crosscheck_kernel_agrees(g):
@@ -211,7 +221,7 @@ def test_sampler_greedy_logprobs_rank_topn(g, V):
 
     torch.manual_seed(V)
     n = 6
-    logits = (torch.randn(n, V) * 2).bfloat16()
+    logits = torch.randn(n, V) * 2
     logits[1, 77] = logits[1].max() + 1  # clear winner
     logits[2, 500] = logits[2, 9] = logits[2].max() + 0.5  # exact tie -> lowest index wins
     rows = _rows(g, n)
@@ -239,7 +249,7 @@ def test_sampler_greedy_processors_exact(g):
 
     V, n = 4096, 8
     torch.manual_seed(11)
-    logits = (torch.randn(n, V) * 1.5).bfloat16()
+    logits = torch.randn(n, V) * 1.5
     eos = 2
     words = (V + 31) // 32
     bm = np.zeros((n, words), dtype=np.uint32)
@@ -302,7 +312,7 @@ def test_sampler_random_sampling_paths(g, V):
         SamplingCase(greedy=False, temperature=2.0, top_p=0.05, seed=8),
     ]
     n = len(cases)
-    logits = (torch.randn(n, V) * 3).bfloat16()
+    logits = torch.randn(n, V) * 3
     from oracle.sampler_oracle import len_penalty_factor_m1
 
     rows = _rows(g, n)
@@ -342,7 +352,7 @@ def test_sampler_distribution_matches_softmax(g):
     """Exponential-race sampling (vllm topk_topp_sampler.py:395-416) is distributional: chi-square on 20k draws."""
     V, n = 64, 20000
     torch.manual_seed(0)
-    base = (torch.randn(V) * 1.5).bfloat16()
+    base = torch.randn(V) * 1.5
     logits = base[None, :].repeat(n, 1).contiguous()
     rows = _rows(g, n)
     rows["seed_lo"] = np.arange(n) * 2654435761 % (1 << 32)

@@ -126,7 +126,8 @@ struct tgis_engine {
   int num_blocks = 0;
   std::vector<int32_t> free_blocks;
   // activations
-  DevBuf<bf16> resid, xn, qkv, attn_out, tmp, gate_up, act, last_hidden, logits;
+  DevBuf<bf16> resid, xn, qkv, attn_out, tmp, gate_up, act, last_hidden;
+  DevBuf<float> logits;  // fp32 straight from the lm_head accumulator
   CUtensorMap xm_xn[N_BT], xm_attn[N_BT], xm_act[N_BT], xm_last[N_BT];
   DevBuf<float> gemm_ws, part_o, part_ml, samp_scratch;
   DevBuf<int> gemm_counters, dec_counters;
@@ -374,11 +375,12 @@ struct tgis_engine {
   }
 
   // ------------------------------------------------------------------------------------------------ device step
-  void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, bf16* Y, int T, int N, int K) {
+  void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, void* Y, int T, int N, int K,
+            int out_f32 = 0) {
     if (cfg.debug_gemm_ref) {
-      CK(gemm_bf16_ref_launch(X, K, W, Y, N, T, N, K, stream));
+      CK(gemm_bf16_ref_launch(X, K, W, Y, N, T, N, K, stream, out_f32));
     } else {
-      CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, N, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream));
+      CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, N, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32));
     }
     ++n_launches;
   }
@@ -513,7 +515,7 @@ struct tgis_engine {
       CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
       CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
       n_launches += 2;
-      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H);
+      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, /*out_f32=*/1);
       CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words, samp_scratch.p,
                         d_samp_out.p, stream));
       ++n_launches;

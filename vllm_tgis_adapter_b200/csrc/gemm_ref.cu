@@ -4,20 +4,21 @@
 namespace tgis {
 
 __global__ void gemm_ref_kernel(const __nv_bfloat16* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ W,
-                                __nv_bfloat16* __restrict__ Y, int ldy, int T, int N, int K) {
+                                void* __restrict__ Y, int ldy, int T, int N, int K, int out_f32) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
   if (n >= N || t >= T) return;
   float acc = 0.f;
   for (int k = 0; k < K; ++k) acc += __bfloat162float(X[(size_t)t * ldx + k]) * __bfloat162float(W[(size_t)n * K + k]);
-  Y[(size_t)t * ldy + n] = __float2bfloat16_rn(acc);
+  if (out_f32) reinterpret_cast<float*>(Y)[(size_t)t * ldy + n] = acc;
+  else reinterpret_cast<__nv_bfloat16*>(Y)[(size_t)t * ldy + n] = __float2bfloat16_rn(acc);
 }
 
-cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, __nv_bfloat16* Y, int ldy,
-                                 int T, int N, int K, cudaStream_t stream) {
+cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, void* Y, int ldy, int T,
+                                 int N, int K, cudaStream_t stream, int out_f32) {
   if (T <= 0) return cudaSuccess;
   dim3 grid((N + 127) / 128, T);
-  gemm_ref_kernel<<<grid, 128, 0, stream>>>(X, ldx, W, Y, ldy, T, N, K);
+  gemm_ref_kernel<<<grid, 128, 0, stream>>>(X, ldx, W, Y, ldy, T, N, K, out_f32);
   return cudaGetLastError();
 }
 

@@ -66,8 +66,11 @@ __device__ __forceinline__ int unit_owner(long long p, long long total, int ncta
 template <int BT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
-                         __nv_bfloat16* __restrict__ Y, int ldy, int T, int N, int K, float* __restrict__ ws,
-                         int* __restrict__ counters, int stream_weights) {
+                         void* __restrict__ Yv, int ldy, int T, int N, int K, float* __restrict__ ws,
+                         int* __restrict__ counters, int stream_weights, int out_f32) {
+  // output: bf16 (rounded once from the fp32 accumulator, = F.linear in model dtype) or raw fp32 (lm_head logits)
+  __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(Yv);
+  float* __restrict__ Yf = reinterpret_cast<float*>(Yv);
   using Cfg = GemmCfg<BT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -207,8 +210,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           if (n < N) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < t_valid)
-                Y[(size_t)(t_base + c0 + j) * ldy + n] = __float2bfloat16_rn(__uint_as_float(r[j]));
+              if (c0 + j < t_valid) {
+                const size_t o = (size_t)(t_base + c0 + j) * ldy + n;
+                if (out_f32) Yf[o] = __uint_as_float(r[j]);
+                else Y[o] = __float2bfloat16_rn(__uint_as_float(r[j]));
+              }
           }
         } else {
 #pragma unroll
@@ -246,7 +252,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
               const float* p = ws + ((size_t)(c * 2 + cslot) * BT + t) * GEMM_BN + row;
               sum += __ldcg(p);
             }
-            if (n < N) Y[(size_t)(t_base + t) * ldy + n] = __float2bfloat16_rn(sum);
+            if (n < N) {
+              const size_t o = (size_t)(t_base + t) * ldy + n;
+              if (out_f32) Yf[o] = sum;
+              else Y[o] = __float2bfloat16_rn(sum);
+            }
           }
           if (ep_tid == 0) counters[tile] = 0;
         }
@@ -305,8 +315,8 @@ int gemm_pick_bt(int T) {
 size_t gemm_workspace_bytes(int num_sms) { return (size_t)num_sms * 2 * 256 * GEMM_BN * sizeof(float); }
 
 template <int BT>
-static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, __nv_bfloat16* Y, int ldy, int T,
-                             int N, int K, float* ws, int* counters, int num_sms, cudaStream_t stream) {
+static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
+                             float* ws, int* counters, int num_sms, int out_f32, cudaStream_t stream) {
   using Cfg = GemmCfg<BT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -322,19 +332,19 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, _
   int grid = (int)(max_ctas < num_sms ? (max_ctas < 1 ? 1 : max_ctas) : num_sms);
   const int stream_weights = (t_tiles == 1) ? 1 : 0;
   gemm_bf16_tcgen05_kernel<BT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(wmap, xmap, Y, ldy, T, N, K, ws,
-                                                                                 counters, stream_weights);
+                                                                                 counters, stream_weights, out_f32);
   return cudaGetLastError();
 }
 
 // xmap must have been built with box_rows == gemm_pick_bt(T)
-cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, __nv_bfloat16* Y, int ldy, int T,
-                             int N, int K, float* ws, int* counters, int num_sms, cudaStream_t stream) {
+cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
+                             float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32) {
   switch (gemm_pick_bt(T)) {
-    case 16: return launch_bt<16>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
-    case 32: return launch_bt<32>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
-    case 64: return launch_bt<64>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
-    case 128: return launch_bt<128>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
-    default: return launch_bt<256>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, stream);
+    case 16: return launch_bt<16>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
+    case 32: return launch_bt<32>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
+    case 64: return launch_bt<64>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
+    case 128: return launch_bt<128>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
+    default: return launch_bt<256>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
   }
 }
 

@@ -14,12 +14,13 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols);
 int gemm_pick_bt(int T);
 size_t gemm_workspace_bytes(int num_sms);
-cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, __nv_bfloat16* Y, int ldy, int T,
-                             int N, int K, float* ws, int* counters, int num_sms, cudaStream_t stream);
+// Y: bf16 [T, ldy] (out_f32 = 0) or fp32 [T, ldy] (out_f32 = 1, used for the lm_head logits)
+cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
+                             float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32 = 0);
 
 // ---- gemm_ref.cu (debug cross-check only; never on the product path) ---------------------------------------------
-cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, __nv_bfloat16* Y, int ldy,
-                                 int T, int N, int K, cudaStream_t stream);
+cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, void* Y, int ldy, int T,
+                                 int N, int K, cudaStream_t stream, int out_f32 = 0);
 
 // ---- elementwise.cu ----------------------------------------------------------------------------------------------
 cudaError_t embed_gather_launch(const int32_t* token_ids, const __nv_bfloat16* table, __nv_bfloat16* out, int T,
@@ -97,7 +98,8 @@ struct SampleOut {            // per row result (pinned host readable)
   float topn_lps[MAX_TOPN];
 };
 constexpr int SAMPLE_GREEDY = 1, SAMPLE_LOGPROBS = 2, SAMPLE_TYPICAL = 4, SAMPLE_LENPEN = 8, SAMPLE_SEEDED = 16;
-cudaError_t sampler_launch(const __nv_bfloat16* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+// logits: fp32 [rows, ld] straight from the lm_head GEMM accumulator (no bf16 round trip)
+cudaError_t sampler_launch(const float* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
                            const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
                            cudaStream_t stream);
 // seen-token bitmap maintenance

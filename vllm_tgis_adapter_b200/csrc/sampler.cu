@@ -10,7 +10,7 @@
 // -> repetition penalty -> greedy argmax | temperature -> top-k -> top-p -> sample -> logprob / rank / top-n (raw).
 //
 // Shape of the problem: a [rows, V=128256] scan, HBM/L2 bound, integer-ish selection work.  One 1024-thread CTA owns
-// one row; the bf16 row (256 KiB) is read from HBM once and stays in the 126 MB L2 for the extra selection passes
+// one row; the fp32 row (512 KiB) is read from HBM once and stays in the 126 MB L2 for the extra selection passes
 // (radix-select thresholds instead of the reference's full sorts).  Loads are 16-byte vectorised and coalesced.
 #include "kernels.h"
 #include "ptx.cuh"
@@ -21,7 +21,7 @@ constexpr int SAMP_THREADS = 1024;
 constexpr int SAMP_WARPS = SAMP_THREADS / 32;
 
 struct RowCtx {
-  const __nv_bfloat16* x;  // raw logits (bf16)
+  const float* x;          // raw logits (fp32, straight from the lm_head accumulator)
   int V;
   const uint32_t* seen;    // bitmap of prompt U output tokens (may be null)
   SampleRow p;
@@ -32,7 +32,7 @@ struct RowCtx {
   float raw_max, raw_logz, ent, typ_thr;
 };
 
-__device__ __forceinline__ float load_x(const RowCtx& c, int i) { return __bfloat162float(c.x[i]); }
+__device__ __forceinline__ float load_x(const RowCtx& c, int i) { return c.x[i]; }
 
 __device__ __forceinline__ bool is_seen(const RowCtx& c, int i) {
   return c.seen != nullptr && ((c.seen[i >> 5] >> (i & 31)) & 1u);
@@ -248,7 +248,7 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(SAMP_THREADS, 1)
-tgis_sampler_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
+tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
                     uint32_t* __restrict__ seen_bitmap, int bitmap_words, float* __restrict__ scratch,
                     SampleOut* __restrict__ outs) {
   __shared__ float redf[2 * SAMP_WARPS];
@@ -275,11 +275,12 @@ tgis_sampler_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, con
   ValIdx best{-INFINITY, -1};
   const bool do_typ = !greedy && (c.p.flags & SAMPLE_TYPICAL);
   for (int i0 = threadIdx.x * 8; i0 < V; i0 += SAMP_THREADS * 8) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(c.x + i0);
-    const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+    const float4 ra = *reinterpret_cast<const float4*>(c.x + i0);
+    const float4 rb = *reinterpret_cast<const float4*>(c.x + i0 + 4);
+    const float xs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float x = __uint_as_float((e & 1) ? (wds[e >> 1] & 0xffff0000u) : (wds[e >> 1] << 16));
+      const float x = xs[e];
       if (x > ms.m) {
         ms.s = ms.s * __expf(ms.m - x) + 1.f;
         ms.m = x;
@@ -312,12 +313,12 @@ tgis_sampler_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, con
       }
       c.ent = -block_sumf(part, redf);
       const float rm = c.raw_max, lz = c.raw_logz, ent = c.ent;
-      const __nv_bfloat16* xx = c.x;
+      const float* xx = c.x;
       auto keyf = [=](int i) {
-        const float lp = (__bfloat162float(xx[i]) - rm) - lz;
+        const float lp = (xx[i] - rm) - lz;
         return __float_as_uint(fabsf((-lp) - ent));
       };
-      auto wf = [=](int i) { return expf((__bfloat162float(xx[i]) - rm) - lz); };
+      auto wf = [=](int i) { return expf((xx[i] - rm) - lz); };
       const uint32_t k = select_weighted_asc(V, keyf, wf, c.p.typical_p, false, histf, bcast);
       c.typ_thr = __uint_as_float(k);
       c.typical = true;
@@ -425,7 +426,7 @@ tgis_sampler_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, con
   }
 }
 
-cudaError_t sampler_launch(const __nv_bfloat16* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+cudaError_t sampler_launch(const float* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
                            const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
                            cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;

@@ -48,7 +48,7 @@ int tgis_k_sizeof_sample_out(void) { return (int)sizeof(SampleOut); }
 int tgis_k_kv_block(void) { return KV_BLOCK; }
 
 int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t N, int32_t K,
-                int32_t x_rows_alloc, int32_t impl, int32_t iters, float* ms_out) {
+                int32_t x_rows_alloc, int32_t impl, int32_t iters, float* ms_out, int32_t out_f32) {
   if (iters < 1) iters = 1;
   cudaStream_t st = 0;
   cudaEvent_t e0, e1;
@@ -57,7 +57,7 @@ int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, in
   if (impl == 1) {
     KCK(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i)
-      KCK(gemm_bf16_ref_launch((const bf16*)x_dev, K, (const bf16*)w_dev, (bf16*)y_dev, N, T, N, K, st));
+      KCK(gemm_bf16_ref_launch((const bf16*)x_dev, K, (const bf16*)w_dev, y_dev, N, T, N, K, st, out_f32));
     KCK(cudaEventRecord(e1, st));
   } else {
     int dev = 0, sms = 148;
@@ -75,7 +75,7 @@ int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, in
     KCK(cudaMemset(ctr.p, 0, sizeof(int) << 16));
     KCK(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i)
-      KCK(gemm_bf16_launch(wm, xm, (bf16*)y_dev, N, T, N, K, ws.p, ctr.p, sms, st));
+      KCK(gemm_bf16_launch(wm, xm, y_dev, N, T, N, K, ws.p, ctr.p, sms, st, out_f32));
     KCK(cudaEventRecord(e1, st));
     KCK(cudaStreamSynchronize(st));
   }
@@ -180,7 +180,7 @@ int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void
     KCK(cudaMemset(dummy_bm.p, 0, sizeof(uint32_t) * (size_t)(max_slot + 1) * words));
     bm = dummy_bm.p;
   }
-  KCK(sampler_launch((const bf16*)logits_dev, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
+  KCK(sampler_launch((const float*)logits_dev, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
   KCK(cudaMemcpy(out_host, outs.p, sizeof(SampleOut) * n_rows, cudaMemcpyDeviceToHost));
   KCK(cudaDeviceSynchronize());
   return 0;

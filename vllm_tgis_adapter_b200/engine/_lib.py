@@ -104,7 +104,7 @@ def load_library() -> C.CDLL:
     lib.tgis_engine_destroy.argtypes = [vp]
     lib.tgis_engine_destroy.restype = None
     lib.tgis_engine_run_until_idle.argtypes = [vp]
-    lib.tgis_k_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32)]
+    lib.tgis_k_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), i32]
     lib.tgis_k_rmsnorm.argtypes = [vp, vp, vp, vp, i32, i32, f32]
     lib.tgis_k_silu_mul.argtypes = [vp, vp, i32, i32]
     lib.tgis_k_rope_kv.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp, i32, i32, i32]

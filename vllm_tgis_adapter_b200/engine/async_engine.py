@@ -1,0 +1,216 @@
+"""`EngineClient`-shaped façade over the native engine: the object the TGIS gRPC servicer holds where the reference
+holds vLLM's AsyncLLM (/root/reference/src/vllm_tgis_adapter/grpc/grpc_server.py:166-176).
+
+Members implemented = exactly the ones the reference touches: generate / abort / get_tokenizer /
+is_tracing_enabled / errored / is_running / vllm_config.model_config.max_model_len / get_model_config.
+
+Threading: the C++ engine runs its own step-loop thread; one Python poller thread blocks in `tgis_engine_poll`
+(GIL released inside ctypes) and hands each batch of step records to the asyncio loop with ONE
+`call_soon_threadsafe` per engine step (not per request), so 256 concurrent streams cost one wake-up per step."""
+from __future__ import annotations
+
+import asyncio
+import itertools
+import threading
+import types as _types
+from collections.abc import AsyncGenerator
+
+from . import _lib
+from .core import ModelConfig, NativeEngine, StepOutput, make_sampling_params
+from .detokenizer import IncrementalDetokenizer
+from .types import (CompletionOutput, Logprob, RequestMetrics, RequestOutput, RequestOutputKind, SamplingParams,
+                    TokensPrompt)
+
+_FINISH = {_lib.FINISH_LENGTH: "length", _lib.FINISH_STOP_EOS: "stop", _lib.FINISH_STOP_TOKEN: "stop",
+           _lib.FINISH_ABORT: "abort", _lib.FINISH_ERROR: "abort"}
+
+
+class EngineDeadError(RuntimeError):
+    pass
+
+
+class _ReqState:
+    def __init__(self, request_id: str, prompt_ids: list[int], sp: SamplingParams, detok: IncrementalDetokenizer,
+                 queue: asyncio.Queue):
+        self.request_id = request_id
+        self.prompt_ids = prompt_ids
+        self.sp = sp
+        self.detok = detok
+        self.queue = queue
+        self.token_ids: list[int] = []
+        self.logprobs: list[dict[int, Logprob]] = []
+        self.done = False
+
+
+class AsyncTGISEngine:
+    def __init__(self, engine: NativeEngine, tokenizer, model_config: ModelConfig):
+        self.engine = engine
+        self.tokenizer = tokenizer
+        self._model_config = model_config
+        mc = _types.SimpleNamespace(max_model_len=model_config.max_model_len)
+        self.vllm_config = _types.SimpleNamespace(model_config=mc)   # grpc_server.py:196-199
+        self._states: dict[str, _ReqState] = {}
+        self._ids = itertools.count()
+        self._loop: asyncio.AbstractEventLoop | None = None
+        self._poller: threading.Thread | None = None
+        self._stopping = False
+        self._dead_error: str | None = None
+
+    # -- lifecycle ------------------------------------------------------------------------------------------------
+    def start(self, loop: asyncio.AbstractEventLoop | None = None) -> None:
+        self._loop = loop or asyncio.get_event_loop()
+        self.engine.start()
+        self._poller = threading.Thread(target=self._poll_loop, name="tgis-poller", daemon=True)
+        self._poller.start()
+
+    def shutdown(self) -> None:
+        self._stopping = True
+        if self._poller is not None:
+            self._poller.join(timeout=5)
+        self.engine.close()
+
+    def _poll_loop(self) -> None:
+        while not self._stopping:
+            try:
+                outs = self.engine.poll(timeout_ms=100)
+            except Exception as e:  # noqa: BLE001
+                self._dead_error = str(e)
+                outs = []
+            if self._dead_error is None and not outs:
+                st = self.engine.status()
+                if st.errored:
+                    self._dead_error = _lib.last_error(self.engine.lib) or "engine errored"
+            if (outs or self._dead_error) and self._loop is not None:
+                try:
+                    self._loop.call_soon_threadsafe(self._dispatch, outs, self._dead_error)
+                except RuntimeError:
+                    return  # loop closed
+            if self._dead_error:
+                return
+
+    def _dispatch(self, outs: list[StepOutput], dead: str | None) -> None:
+        for o in outs:
+            st = self._states.get(o.request_id)
+            if st is not None:
+                st.queue.put_nowait(o)
+        if dead:
+            for st in self._states.values():
+                st.queue.put_nowait(EngineDeadError(dead))
+
+    # -- EngineClient subset ----------------------------------------------------------------------------------------
+    @property
+    def errored(self) -> bool:
+        return self._dead_error is not None or bool(self.engine.status().errored)
+
+    @property
+    def is_running(self) -> bool:
+        return self._dead_error is None and bool(self.engine.status().is_running)
+
+    @property
+    def dead_error(self) -> BaseException:
+        return EngineDeadError(self._dead_error or "engine dead")
+
+    async def get_model_config(self):
+        return self.vllm_config.model_config
+
+    async def get_tokenizer(self, lora_request=None):  # noqa: ARG002
+        return self.tokenizer
+
+    async def is_tracing_enabled(self) -> bool:
+        return False
+
+    async def abort(self, request_id: str) -> None:
+        st = self._states.get(request_id)
+        if st is not None and not st.done:
+            self.engine.abort(st.request_id)   # st.request_id is the engine-side id
+
+    async def generate(self, prompt: TokensPrompt | dict, sampling_params: SamplingParams, request_id: str,
+                       lora_request=None, trace_headers=None, **_: object  # noqa: ARG002
+                       ) -> AsyncGenerator[RequestOutput, None]:
+        if self._dead_error is not None:
+            raise EngineDeadError(self._dead_error)
+        if lora_request is not None:
+            raise ValueError("LoRA adapters are not supported by this engine")
+        prompt_ids = list(prompt["prompt_token_ids"] if isinstance(prompt, dict) else prompt.prompt_token_ids)
+        sp = sampling_params
+        eos = sp.eos_token_id if sp.eos_token_id is not None else getattr(self.tokenizer, "eos_token_id", None)
+        max_tokens = sp.max_tokens if sp.max_tokens is not None else self._model_config.max_model_len - len(prompt_ids)
+        native = make_sampling_params(
+            greedy=sp.greedy, temperature=sp.temperature if not sp.greedy else 1.0,
+            top_k=sp.top_k if sp.top_k and sp.top_k > 0 else 0, top_p=sp.top_p, typical_p=sp.typical_p,
+            repetition_penalty=sp.repetition_penalty, length_penalty=sp.length_penalty,
+            eos_token_id=eos if eos is not None else -1, min_tokens=sp.min_tokens, max_tokens=max_tokens,
+            num_logprobs=sp.logprobs or 0, seed=sp.seed if not sp.greedy else None,
+            stop_token_ids=sp.stop_token_ids)
+        nid = f"q{next(self._ids)}"
+        queue: asyncio.Queue = asyncio.Queue()
+        detok = IncrementalDetokenizer(self.tokenizer, prompt_ids, stop=sp.stop, min_tokens=sp.min_tokens,
+                                       include_stop_str_in_output=sp.include_stop_str_in_output,
+                                       skip_special_tokens=sp.skip_special_tokens)
+        st = _ReqState(nid, prompt_ids, sp, detok, queue)
+        self._states[nid] = st
+        self._states[request_id] = st
+        delta = sp.output_kind == RequestOutputKind.DELTA
+        final_only = sp.output_kind == RequestOutputKind.FINAL_ONLY
+        try:
+            self.engine.add_request(nid, prompt_ids, native)
+            sent_tokens = 0
+            while True:
+                item = await queue.get()
+                if isinstance(item, BaseException):
+                    raise item
+                batch = [item]
+                while not queue.empty():   # coalesce everything already delivered for this request
+                    nxt = queue.get_nowait()
+                    if isinstance(nxt, BaseException):
+                        raise nxt
+                    batch.append(nxt)
+                finish_reason: str | None = None
+                stop_reason: int | str | None = None
+                last = batch[-1]
+                for o in batch:
+                    if o.new_token is not None:
+                        st.token_ids.append(o.new_token)
+                        if sp.logprobs:
+                            lp: dict[int, Logprob] = {o.new_token: Logprob(o.logprob, o.rank)}
+                            for r, (tid, tlp) in enumerate(o.topn, start=1):
+                                lp.setdefault(tid, Logprob(tlp, r))    # vllm logprobs.py:175-206 (dict merge dedups)
+                            st.logprobs.append(lp)
+                    if o.finish_reason != _lib.FINISH_NONE:
+                        finish_reason = _FINISH[o.finish_reason]
+                        if o.finish_reason == _lib.FINISH_STOP_TOKEN:
+                            stop_reason = o.stop_token_id
+                        if o.finish_reason == _lib.FINISH_ERROR:
+                            raise EngineDeadError(_lib.last_error(self.engine.lib) or "engine error")
+                new_ids = st.token_ids[detok.n_out:]
+                stop_str = detok.update(new_ids, stop_terminated=finish_reason == "stop")
+                if stop_str is not None and finish_reason is None:
+                    # S10: stop string hit -> the engine request is no longer needed
+                    finish_reason, stop_reason = "stop", stop_str
+                    self.engine.abort(nid)
+                finished = finish_reason is not None
+                if final_only and not finished:
+                    continue
+                text = detok.next_text(finished, delta)
+                ids = st.token_ids[sent_tokens:] if delta else list(st.token_ids)
+                lps = (st.logprobs[sent_tokens:] if delta else list(st.logprobs)) if sp.logprobs else None
+                sent_tokens = len(st.token_ids)
+                metrics = RequestMetrics(arrival_time=last.ts_arrival, first_scheduled_time=last.ts_first_scheduled,
+                                         first_token_time=last.ts_first_token, last_token_time=last.ts_last_token,
+                                         time_in_queue=(last.ts_first_scheduled - last.ts_arrival)
+                                         if last.ts_first_scheduled else None,
+                                         finished_time=last.ts_last_token if finished else None)
+                yield RequestOutput(
+                    request_id=request_id, prompt=None, prompt_token_ids=prompt_ids, prompt_logprobs=None,
+                    outputs=[CompletionOutput(index=0, text=text, token_ids=ids, logprobs=lps,
+                                              finish_reason=finish_reason, stop_reason=stop_reason)],
+                    finished=finished, metrics=metrics)
+                if finished:
+                    st.done = True
+                    return
+        finally:
+            if not st.done:   # client went away / generator closed early: free the sequence in the engine
+                self.engine.abort(nid)
+                st.done = True
+            self._states.pop(nid, None)
+            self._states.pop(request_id, None)
