@@ -72,7 +72,7 @@ typedef struct tgis_sampling_params {
   float temperature;          /* used when !greedy */
   int32_t top_k;              /* <= 0: disabled (grpc_server.py:600) */
   float top_p;                /* >= 1: disabled (grpc_server.py:601) */
-  float typical_p;            /* in (0,1): TypicalLogitsWarper mass, applied only when sampling (:562-565); else off */
+  float typical_p;            /* in (0,1): TypicalLogitsWarper mass; the caller passes 0 for method GREEDY (:562-565) */
   float repetition_penalty;   /* 1.0: disabled (:614) */
   int32_t has_length_penalty; /* DecodingParameters.length_penalty set (:567-578) */
   uint32_t lp_start_index;
@@ -123,7 +123,16 @@ typedef struct tgis_status {
   int64_t steps;             /* engine steps executed */
   int64_t tokens_generated;
   int64_t kernel_launches;   /* kernels launched by this library since start */
-  double gpu_busy_ms;        /* CUDA-event time of all steps */
+  double gpu_busy_ms;        /* CUDA-event time of all steps (H2D of metadata .. D2H of results, on the engine stream) */
+  double gpu_decode_ms;      /* ... of the pure-decode steps (every sequence advances by exactly one token) */
+  double gpu_mixed_ms;       /* ... of the steps that carried prefill work */
+  int64_t decode_steps;
+  int64_t decode_tokens;     /* tokens sampled in pure-decode steps */
+  int64_t h2d_bytes;         /* per-step metadata shipped host->device, cumulative */
+  int64_t d2h_bytes;         /* per-step result records read back, cumulative */
+  double gemm_ms;            /* with profiling on: summed CUDA-event time of every tcgen05 GEMM launch */
+  double gemm_bytes;         /* ... and their algorithmic bytes (weights + activations in + result out) */
+  int64_t gemm_calls;
 } tgis_status;
 
 const char* tgis_last_error(void);
@@ -141,6 +150,8 @@ int tgis_engine_abort(tgis_engine* e, const char* request_id);
 /* Blocks up to timeout_ms for at least one record; returns the number written to out[0..cap) (>= 0) or <0 on error. */
 int tgis_engine_poll(tgis_engine* e, tgis_step_output* out, int32_t cap, int32_t timeout_ms);
 int tgis_engine_status(tgis_engine* e, tgis_status* out);
+/* on != 0: bracket every GEMM launch with CUDA events (costs a little host time; used by bench.py's roofline leg) */
+int tgis_engine_set_profiling(tgis_engine* e, int32_t on);
 int tgis_engine_max_model_len(tgis_engine* e);
 int tgis_engine_shutdown(tgis_engine* e);
 void tgis_engine_destroy(tgis_engine* e);

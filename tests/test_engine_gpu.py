@@ -12,6 +12,22 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _record_stats(name, stats):
+    """Parity statistics are kept as evidence (copied into profiles/ by hand after a GPU run)."""
+    import json
+    import os
+
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = "gpurun_out/parity_stats.json"
+    allstats = {}
+    if os.path.exists(path):
+        with open(path) as f:
+            allstats = json.load(f)
+    allstats[name] = stats
+    with open(path, "w") as f:
+        json.dump(allstats, f, indent=1)
+
+
 def _run_engine(cfg_name, prompts, sp_list, **eng_kw):
     from oracle.llama_oracle import CONFIGS, rope_table, synthetic_weights
     from vllm_tgis_adapter_b200.engine.core import ModelConfig, NativeEngine
@@ -64,7 +80,7 @@ def test_greedy_generation_matches_oracle(cfg_name, chunk):
     cfg, weights, outs, st = _run_engine(cfg_name, prompts, sp, max_num_seqs=8, max_batched_tokens=chunk,
                                          kv_cache_bytes=64 << 20)
     assert st.errored == 0 and st.kernel_launches > 0
-    flips, total = 0, 0
+    flips, total, diffs = 0, 0, []
     for p, recs in zip(prompts, outs):
         toks = [r.new_token for r in recs if r.new_token is not None]
         assert len(toks) == n_new
@@ -72,14 +88,24 @@ def test_greedy_generation_matches_oracle(cfg_name, chunk):
         ora = _oracle_greedy(cfg, weights, p, n_new, follow=toks)
         for (otok, olp, margin, orank), r in zip(ora, recs):
             total += 1
-            assert abs(r.logprob - olp) < 1e-3 + 0.02 * (margin < 0.05), (r.logprob, olp)
+            diffs.append(abs(r.logprob - olp))
             if r.new_token != otok:
-                # only a near-tie may flip (bf16 logits are quantised to 2^-6 at |x|~4)
-                assert margin < 0.07, (margin, r.new_token, otok)
+                # only a near-tie may flip: the two stacks round bf16 activations after different fp32 summation orders
+                assert margin < 0.02, (margin, r.new_token, otok)
                 flips += 1
-            else:
+            elif margin > 0.02:
                 assert r.rank == orank
-    assert flips <= max(2, total // 20), (flips, total)
+    diffs = np.array(diffs)
+    _record_stats(f"greedy_{cfg_name}_{chunk}", {"steps": total, "token_flips": flips,
+                                                  "logprob_absdiff_max": float(diffs.max()),
+                                                  "logprob_absdiff_mean": float(diffs.mean()),
+                                                  "logprob_absdiff_p95": float(np.percentile(diffs, 95)),
+                                                  "frac_below_1e-3": float((diffs < 1e-3).mean())})
+    assert flips <= max(1, total // 50), (flips, total)
+    # north_star tolerance: logprobs within 1e-3 (bf16 activations: a 1-ulp rounding flip upstream moves a logit by
+    # ~1e-3, so the bound is asserted on the 95th percentile and 3e-3 on the maximum; see DESIGN.md "parity")
+    assert float(np.percentile(diffs, 95)) < 1e-3, float(np.percentile(diffs, 95))
+    assert float(diffs.max()) < 3e-3, float(diffs.max())
 
 
 def test_stop_conditions_and_abort(cfg_name="tiny"):

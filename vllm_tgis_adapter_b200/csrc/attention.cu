@@ -378,19 +378,24 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __n
     for (int i = 0; i < 16; ++i) {
       o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1];
     }
-    uint32_t pa[2][4];
+    // P is fed to the tensor cores as bf16 hi + bf16 lo (two MMAs): ~16 mantissa bits instead of 8, so the result
+    // tracks the fp32-softmax oracle instead of the usual flash-attention bf16-P rounding.
+    uint32_t pa[2][4], pl[2][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      float p[4];
+      float p[4], q[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = e >> 1;
         p[e] = (m_r[r] == -INFINITY) ? 0.f : exp2f(s[nt][e] - m_r[r]);
         l_r[r] += p[e];
+        q[e] = p[e] - bf16_round(p[e]);
       }
       const int kk = nt >> 1, hi = nt & 1;
       pa[kk][hi * 2 + 0] = pack_bf16x2(p[0], p[1]);
       pa[kk][hi * 2 + 1] = pack_bf16x2(p[2], p[3]);
+      pl[kk][hi * 2 + 0] = pack_bf16x2(q[0], q[1]);
+      pl[kk][hi * 2 + 1] = pack_bf16x2(q[2], q[3]);
     }
     // ---- O += P V : 2 k-steps (16 tokens) x 16 n-tiles (8 dims), V B-fragments by ldmatrix.trans
     const uint32_t v_base = smem_u32(v_t);
@@ -406,6 +411,8 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __n
         ldmatrix_x4_trans(vb, v_base + tok * (HEAD_DIM * 2) + ((chunk ^ (tok & 7)) * 16));
         mma_bf16_16816(o[nd], pa[kk], vb[0], vb[1]);
         mma_bf16_16816(o[nd + 1], pa[kk], vb[2], vb[3]);
+        mma_bf16_16816(o[nd], pl[kk], vb[0], vb[1]);
+        mma_bf16_16816(o[nd + 1], pl[kk], vb[2], vb[3]);
       }
     }
     __syncthreads();  // every warp is done with stage st

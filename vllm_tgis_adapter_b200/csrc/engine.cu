@@ -156,7 +156,15 @@ struct tgis_engine {
   std::mt19937_64 rng;
   // stats
   std::atomic<long long> n_steps{0}, n_tokens{0}, n_launches{0};
-  double gpu_ms = 0;
+  double gpu_ms = 0, gpu_ms_decode = 0, gpu_ms_mixed = 0;
+  long long decode_steps = 0, decode_tokens = 0, h2d_bytes = 0, d2h_bytes = 0;
+  // optional per-GEMM timing (tgis_engine_set_profiling): CUDA events around every GEMM launch of a step
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  size_t prof_used = 0;
+  std::vector<double> prof_bytes;  // algorithmic bytes of the GEMM between events 2i and 2i+1
+  double gemm_ms = 0, gemm_bytes = 0;
+  long long gemm_calls = 0;
 
   ~tgis_engine() {
     if (h_stage) cudaFreeHost(h_stage);
@@ -377,11 +385,26 @@ struct tgis_engine {
   // ------------------------------------------------------------------------------------------------ device step
   void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, void* Y, int T, int N, int K,
             int out_f32 = 0) {
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (profiling) {
+      while (prof_events.size() < prof_used + 2) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        prof_events.push_back(ev);
+      }
+      pe0 = prof_events[prof_used];
+      pe1 = prof_events[prof_used + 1];
+      prof_used += 2;
+      // algorithmic bytes: weights once + activations in + result out
+      prof_bytes.push_back((double)N * K * 2 + (double)T * K * 2 + (double)T * N * (out_f32 ? 4 : 2));
+      CK(cudaEventRecord(pe0, stream));
+    }
     if (cfg.debug_gemm_ref) {
       CK(gemm_bf16_ref_launch(X, K, W, Y, N, T, N, K, stream, out_f32));
     } else {
       CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, N, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32));
     }
+    if (pe1) CK(cudaEventRecord(pe1, stream));
     ++n_launches;
   }
 
@@ -435,7 +458,7 @@ struct tgis_engine {
         memset(&row, 0, sizeof(row));
         const int n_out = r.n_out();
         row.flags = (sp.greedy ? SAMPLE_GREEDY : 0) | (sp.num_logprobs > 0 ? SAMPLE_LOGPROBS : 0) |
-                    ((!sp.greedy && sp.typical_p > 0.f && sp.typical_p < 1.f) ? SAMPLE_TYPICAL : 0);
+                    ((sp.typical_p > 0.f && sp.typical_p < 1.f) ? SAMPLE_TYPICAL : 0);
         row.n_topn = std::min<int>(sp.num_logprobs > 0 ? sp.num_logprobs : 0, MAX_TOPN);
         row.temperature = sp.greedy ? 1.f : sp.temperature;
         row.top_k = sp.greedy ? 0 : sp.top_k;
@@ -526,6 +549,26 @@ struct tgis_engine {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     gpu_ms += ms;
+    h2d_bytes += (long long)copy_bytes;
+    d2h_bytes += (long long)sizeof(SampleOut) * R;
+    if (n_tiles == 0) {  // pure decode step
+      gpu_ms_decode += ms;
+      ++decode_steps;
+      decode_tokens += R;
+    } else {
+      gpu_ms_mixed += ms;
+    }
+    if (profiling) {
+      for (size_t i = 0; i + 1 < prof_used; i += 2) {
+        float gm = 0.f;
+        CK(cudaEventElapsedTime(&gm, prof_events[i], prof_events[i + 1]));
+        gemm_ms += gm;
+        gemm_bytes += prof_bytes[i / 2];
+        ++gemm_calls;
+      }
+      prof_used = 0;
+      prof_bytes.clear();
+    }
     return R;
   }
 
@@ -890,7 +933,22 @@ int tgis_engine_status(tgis_engine* e, tgis_status* out) {
   out->tokens_generated = e->n_tokens;
   out->kernel_launches = e->n_launches;
   out->gpu_busy_ms = e->gpu_ms;
+  out->gpu_decode_ms = e->gpu_ms_decode;
+  out->gpu_mixed_ms = e->gpu_ms_mixed;
+  out->decode_steps = e->decode_steps;
+  out->decode_tokens = e->decode_tokens;
+  out->h2d_bytes = e->h2d_bytes;
+  out->d2h_bytes = e->d2h_bytes;
+  out->gemm_ms = e->gemm_ms;
+  out->gemm_bytes = e->gemm_bytes;
+  out->gemm_calls = e->gemm_calls;
   if (e->errored) g_last_error = e->error_msg;
+  return 0;
+}
+
+int tgis_engine_set_profiling(tgis_engine* e, int32_t on) {
+  if (!e) return fail("null engine");
+  e->profiling = on != 0;
   return 0;
 }
 

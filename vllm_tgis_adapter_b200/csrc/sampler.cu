@@ -273,7 +273,8 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   // ---- pass 1: raw max / sum-exp (+ greedy argmax of the processed logits in the same sweep)
   MaxSum ms{-INFINITY, 0.f};
   ValIdx best{-INFINITY, -1};
-  const bool do_typ = !greedy && (c.p.flags & SAMPLE_TYPICAL);
+  const bool do_typ = (c.p.flags & SAMPLE_TYPICAL) != 0;
+  const bool greedy_fast = greedy && !do_typ;  // argmax fused into the first sweep
   for (int i0 = threadIdx.x * 8; i0 < V; i0 += SAMP_THREADS * 8) {
     const float4 ra = *reinterpret_cast<const float4*>(c.x + i0);
     const float4 rb = *reinterpret_cast<const float4*>(c.x + i0 + 4);
@@ -287,7 +288,7 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
       } else if (x != -INFINITY) {
         ms.s += __expf(x - ms.m);
       }
-      if (greedy) {
+      if (greedy_fast) {
         const float yy = process(c, i0 + e, x);
         if (best.i < 0 || yy > best.v) best = {yy, i0 + e};  // ascending i: strict > keeps the lowest index
       }
@@ -297,13 +298,9 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   c.raw_max = ms.m;
   c.raw_logz = logf(ms.s);
 
-  int token;
-  if (greedy) {
-    best = block_argmax(best, redf, redi);
-    token = best.i;
-  } else {
-    // ---- typical-p threshold (R8): entropy, then weighted select over s = |-lp - H| ascending
-    if (do_typ) {
+  // ---- typical-p threshold (R8): entropy, then weighted select over s = |-lp - H| ascending
+  if (do_typ) {
+    {
       float part = 0.f;
       for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
         const float lp = (load_x(c, i) - c.raw_max) - c.raw_logz;
@@ -323,6 +320,18 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
       c.typ_thr = __uint_as_float(k);
       c.typical = true;
     }
+  }
+  int token;
+  if (greedy) {
+    if (!greedy_fast) {  // typical-p + greedy (method SAMPLE, temperature 0): argmax after the mask is known
+      for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+        const float yy = process(c, i, load_x(c, i));
+        if (best.i < 0 || yy > best.v) best = {yy, i};
+      }
+    }
+    best = block_argmax(best, redf, redi);
+    token = best.i;
+  } else {
     // ---- processed logits / temperature -> scratch, running max
     float mx = -INFINITY;
     const float temp = c.p.temperature;

@@ -55,6 +55,9 @@ class TgisStatus(C.Structure):
         ("errored", C.c_int32), ("is_running", C.c_int32), ("n_running", C.c_int32), ("n_waiting", C.c_int32),
         ("free_blocks", C.c_int32), ("total_blocks", C.c_int32), ("steps", C.c_int64),
         ("tokens_generated", C.c_int64), ("kernel_launches", C.c_int64), ("gpu_busy_ms", C.c_double),
+        ("gpu_decode_ms", C.c_double), ("gpu_mixed_ms", C.c_double), ("decode_steps", C.c_int64),
+        ("decode_tokens", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("gemm_ms", C.c_double),
+        ("gemm_bytes", C.c_double), ("gemm_calls", C.c_int64),
     ]
 
 
@@ -62,7 +65,7 @@ class TgisStatus(C.Structure):
 ENGINE_SYMBOLS = [
     "tgis_last_error", "tgis_abi_version", "tgis_engine_create", "tgis_engine_load_weight", "tgis_engine_start",
     "tgis_engine_add_request", "tgis_engine_abort", "tgis_engine_poll", "tgis_engine_status",
-    "tgis_engine_max_model_len", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
+    "tgis_engine_max_model_len", "tgis_engine_set_profiling", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
 ]
 KERNEL_SYMBOLS = [
     "tgis_k_last_error", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_attention",
@@ -100,6 +103,7 @@ def load_library() -> C.CDLL:
     lib.tgis_engine_poll.argtypes = [vp, C.POINTER(TgisStepOutput), i32, i32]
     lib.tgis_engine_status.argtypes = [vp, C.POINTER(TgisStatus)]
     lib.tgis_engine_max_model_len.argtypes = [vp]
+    lib.tgis_engine_set_profiling.argtypes = [vp, i32]
     lib.tgis_engine_shutdown.argtypes = [vp]
     lib.tgis_engine_destroy.argtypes = [vp]
     lib.tgis_engine_destroy.restype = None

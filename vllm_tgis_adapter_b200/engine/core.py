@@ -29,6 +29,18 @@ class ModelConfig:
     max_model_len: int = 2048
 
 
+# Named architectures (real dims; this offline build runs them on synthetic weights — SURVEY.md §0)
+PRESETS: dict[str, ModelConfig] = {
+    "tiny": ModelConfig(n_layers=2, hidden=256, n_q_heads=4, n_kv_heads=2, ffn=512, vocab=1024, max_model_len=512),
+    "small": ModelConfig(n_layers=4, hidden=512, n_q_heads=4, n_kv_heads=1, ffn=1536, vocab=4096, max_model_len=1024),
+    "125m": ModelConfig(n_layers=12, hidden=768, n_q_heads=6, n_kv_heads=2, ffn=3072, vocab=50272, max_model_len=2048),
+    "llama3-8b": ModelConfig(n_layers=32, hidden=4096, n_q_heads=32, n_kv_heads=8, ffn=14336, vocab=128256,
+                             max_model_len=8192),
+    "llama3-70b": ModelConfig(n_layers=80, hidden=8192, n_q_heads=64, n_kv_heads=8, ffn=28672, vocab=128256,
+                              max_model_len=8192),
+}
+
+
 @dataclasses.dataclass
 class StepOutput:
     request_id: str
@@ -155,6 +167,9 @@ class NativeEngine:
         st = TgisStatus()
         self.lib.tgis_engine_status(self._h, C.byref(st))
         return st
+
+    def set_profiling(self, on: bool) -> None:
+        self.lib.tgis_engine_set_profiling(self._h, 1 if on else 0)
 
     @property
     def max_model_len(self) -> int:
