@@ -160,7 +160,9 @@ class AsyncTGISEngine:
                 if isinstance(item, BaseException):
                     raise item
                 batch = [item]
-                while not queue.empty():   # coalesce everything already delivered for this request
+                # DELTA streams emit one RequestOutput per engine step (the reference's tests pin "N tokens -> N+1
+                # messages", tests/test_grpc_server.py:60-69); FINAL_ONLY may swallow whatever has already arrived.
+                while not delta and not queue.empty():
                     nxt = queue.get_nowait()
                     if isinstance(nxt, BaseException):
                         raise nxt
@@ -168,7 +170,12 @@ class AsyncTGISEngine:
                 finish_reason: str | None = None
                 stop_reason: int | str | None = None
                 last = batch[-1]
-                for o in batch:
+                for o in batch:   # one engine step at a time: stop strings are evaluated per step (S10)
+                    step_finish: str | None = None
+                    if o.finish_reason != _lib.FINISH_NONE:
+                        if o.finish_reason == _lib.FINISH_ERROR:
+                            raise EngineDeadError(_lib.last_error(self.engine.lib) or "engine error")
+                        step_finish = _FINISH[o.finish_reason]
                     if o.new_token is not None:
                         st.token_ids.append(o.new_token)
                         if sp.logprobs:
@@ -176,18 +183,21 @@ class AsyncTGISEngine:
                             for r, (tid, tlp) in enumerate(o.topn, start=1):
                                 lp.setdefault(tid, Logprob(tlp, r))    # vllm logprobs.py:175-206 (dict merge dedups)
                             st.logprobs.append(lp)
-                    if o.finish_reason != _lib.FINISH_NONE:
-                        finish_reason = _FINISH[o.finish_reason]
+                        stop_str = detok.update([o.new_token], stop_terminated=step_finish == "stop")
+                        if stop_str is not None:
+                            # stop string hit: later tokens (if any were already produced) are discarded and the
+                            # engine-side sequence is released
+                            finish_reason, stop_reason = "stop", stop_str
+                            if step_finish is None:
+                                self.engine.abort(nid)
+                            last = o
+                            break
+                    if step_finish is not None:
+                        finish_reason = step_finish
                         if o.finish_reason == _lib.FINISH_STOP_TOKEN:
                             stop_reason = o.stop_token_id
-                        if o.finish_reason == _lib.FINISH_ERROR:
-                            raise EngineDeadError(_lib.last_error(self.engine.lib) or "engine error")
-                new_ids = st.token_ids[detok.n_out:]
-                stop_str = detok.update(new_ids, stop_terminated=finish_reason == "stop")
-                if stop_str is not None and finish_reason is None:
-                    # S10: stop string hit -> the engine request is no longer needed
-                    finish_reason, stop_reason = "stop", stop_str
-                    self.engine.abort(nid)
+                        last = o
+                        break
                 finished = finish_reason is not None
                 if final_only and not finished:
                     continue

@@ -1,0 +1,117 @@
+"""Build the engine the way `build_async_engine_client(args)` does for the reference
+(/root/reference/src/vllm_tgis_adapter/__main__.py:48): read the HF model directory (config.json + *.safetensors),
+stream each tensor into libtgis_engine.so ("PyTorch tensors for weights only"), attach a tokenizer.
+
+Offline builds have no checkpoints: `--model <preset> --synthetic-weights` creates seeded N(0, 0.02)
+weights of the named architecture on the device instead."""
+from __future__ import annotations
+
+import dataclasses
+import json
+import logging
+from pathlib import Path
+
+from .async_engine import AsyncTGISEngine
+from .core import PRESETS, ModelConfig, NativeEngine
+from .tokenizer import load_tokenizer
+
+logger = logging.getLogger("vllm_tgis_adapter.engine")
+
+
+def model_config_from_hf(path: Path, max_model_len: int | None) -> ModelConfig:
+    cfg = json.loads((path / "config.json").read_text())
+    archs = cfg.get("architectures") or []
+    if cfg.get("model_type") != "llama" and not any("Llama" in a for a in archs):
+        raise ValueError(f"unsupported model architecture {archs or cfg.get('model_type')}: only Llama-family "
+                         "decoders (RMSNorm, RoPE, GQA, SwiGLU) are implemented")
+    hidden, heads = cfg["hidden_size"], cfg["num_attention_heads"]
+    head_dim = cfg.get("head_dim") or hidden // heads
+    if head_dim != 128:
+        raise ValueError(f"head_dim {head_dim} unsupported (kernels are specialised for 128)")
+    if cfg.get("rope_scaling"):
+        raise ValueError("rope_scaling is not supported yet")
+    derived = cfg.get("max_position_embeddings", 8192)
+    if max_model_len is not None and max_model_len > derived:
+        raise ValueError(f"max_model_len {max_model_len} exceeds the model's max_position_embeddings {derived}")
+    return ModelConfig(n_layers=cfg["num_hidden_layers"], hidden=hidden, n_q_heads=heads,
+                       n_kv_heads=cfg.get("num_key_value_heads", heads), ffn=cfg["intermediate_size"],
+                       vocab=cfg["vocab_size"], head_dim=head_dim, rope_theta=float(cfg.get("rope_theta", 10000.0)),
+                       rms_eps=float(cfg.get("rms_norm_eps", 1e-5)), max_model_len=max_model_len or min(derived, 8192))
+
+
+def rope_cos_sin(mc: ModelConfig):
+    """HF LlamaRotaryEmbedding / vllm rotary_embedding base.py: fp32 table -> bf16."""
+    import torch
+
+    d = mc.head_dim
+    inv_freq = 1.0 / (mc.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    freqs = torch.outer(torch.arange(mc.max_model_len, dtype=torch.float32), inv_freq)
+    return torch.cat([freqs.cos(), freqs.sin()], dim=-1).to(torch.bfloat16)
+
+
+def load_synthetic_weights(eng: NativeEngine, mc: ModelConfig, seed: int, device: int) -> None:
+    import torch
+
+    gen = torch.Generator(device=f"cuda:{device}").manual_seed(seed)
+
+    def rnd(r, c):
+        return (torch.randn(r, c, generator=gen, device=f"cuda:{device}", dtype=torch.float32) * 0.02).to(torch.bfloat16)
+
+    q_dim, kv_dim = mc.n_q_heads * mc.head_dim, mc.n_kv_heads * mc.head_dim
+    ones = torch.ones(mc.hidden, dtype=torch.bfloat16, device=f"cuda:{device}")
+    eng.load_weight("model.embed_tokens.weight", rnd(mc.vocab, mc.hidden))
+    eng.load_weight("lm_head.weight", rnd(mc.vocab, mc.hidden))
+    eng.load_weight("model.norm.weight", ones)
+    for i in range(mc.n_layers):
+        p = f"model.layers.{i}."
+        eng.load_weight(p + "self_attn.q_proj.weight", rnd(q_dim, mc.hidden))
+        eng.load_weight(p + "self_attn.k_proj.weight", rnd(kv_dim, mc.hidden))
+        eng.load_weight(p + "self_attn.v_proj.weight", rnd(kv_dim, mc.hidden))
+        eng.load_weight(p + "self_attn.o_proj.weight", rnd(mc.hidden, q_dim))
+        eng.load_weight(p + "mlp.gate_proj.weight", rnd(mc.ffn, mc.hidden))
+        eng.load_weight(p + "mlp.up_proj.weight", rnd(mc.ffn, mc.hidden))
+        eng.load_weight(p + "mlp.down_proj.weight", rnd(mc.hidden, mc.ffn))
+        eng.load_weight(p + "input_layernorm.weight", ones)
+        eng.load_weight(p + "post_attention_layernorm.weight", ones)
+
+
+def load_safetensors_dir(eng: NativeEngine, path: Path) -> None:
+    from safetensors import safe_open
+
+    files = sorted(path.glob("*.safetensors"))
+    if not files:
+        raise ValueError(f"no *.safetensors files under {path}")
+    for f in files:
+        with safe_open(str(f), framework="pt", device="cpu") as sf:
+            for name in sf.keys():  # noqa: SIM118
+                if name.endswith("rotary_emb.inv_freq"):
+                    continue
+                eng.load_weight(name, sf.get_tensor(name))
+
+
+def build_engine(args) -> AsyncTGISEngine:
+    if args.tensor_parallel_size not in (None, 1):
+        raise ValueError("tensor parallelism is not available in this revision: run one replica per GPU")
+    if not args.model:
+        raise ValueError("--model / --model-name is required")
+    path = Path(args.model)
+    if path.is_dir():
+        mc = model_config_from_hf(path, args.max_model_len)
+    elif args.model in PRESETS:
+        if not args.synthetic_weights:
+            raise ValueError(f"--model {args.model} is a preset name: pass --synthetic-weights or a model directory")
+        mc = dataclasses.replace(PRESETS[args.model])
+        if args.max_model_len:
+            mc.max_model_len = args.max_model_len
+    else:
+        raise ValueError(f"model path {args.model} does not exist (no network access: hub ids cannot be resolved)")
+    eng = NativeEngine(mc, max_num_seqs=args.max_num_seqs, max_batched_tokens=args.max_num_batched_tokens,
+                       gpu_mem_fraction=args.gpu_memory_utilization, device=args.device, seed=args.seed)
+    if path.is_dir():
+        load_safetensors_dir(eng, path)
+    else:
+        load_synthetic_weights(eng, mc, args.seed, args.device)
+    eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
+    tokenizer = load_tokenizer(args.tokenizer or (str(path) if path.is_dir() else None), mc.vocab)
+    logger.info("engine ready: %s", mc)
+    return AsyncTGISEngine(eng, tokenizer, mc)
