@@ -46,7 +46,15 @@ def parse_args():
     ap.add_argument("--gen-len", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-decode-steps", type=int, default=4)
+    ap.add_argument("--cpu-budget-s", type=float, default=45.0, help="wall-clock bound of the CPU baseline sample")
     return ap.parse_args()
+
+
+_T0 = time.time()
+
+
+def log(msg: str) -> None:
+    print(f"[bench +{time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def peaks() -> tuple[float, str]:
@@ -110,7 +118,19 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
-    tile = (torch.randn(1024, 1024, generator=g) * 0.02).bfloat16()
+    # vLLM's CPU backend runs bf16 where the host has AMX / avx512_bf16 and fp32 otherwise: pick by a micro-benchmark
+    xa, wa = torch.randn(32, 4096), torch.randn(4096, 4096)
+
+    def _t(dt):
+        x_, w_ = xa.to(dt), wa.to(dt)
+        torch.nn.functional.linear(x_, w_)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.linear(x_, w_)
+        return time.perf_counter() - t0
+
+    dtype = torch.bfloat16 if _t(torch.bfloat16) <= 1.5 * _t(torch.float32) else torch.float32
+    tile = (torch.randn(1024, 1024, generator=g) * 0.02).to(dtype)
 
     def fake(rows: int, cols: int) -> torch.Tensor:  # values irrelevant for timing; avoids minutes of randn
         r = (rows + 1023) // 1024
@@ -118,7 +138,7 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
         return tile.repeat(r, c)[:rows, :cols].contiguous()
 
     w = {"model.embed_tokens.weight": fake(cfg.vocab, cfg.hidden), "lm_head.weight": fake(cfg.vocab, cfg.hidden),
-         "model.norm.weight": torch.ones(cfg.hidden, dtype=torch.bfloat16)}
+         "model.norm.weight": torch.ones(cfg.hidden, dtype=dtype)}
     for i in range(cfg.n_layers):
         p = f"model.layers.{i}."
         w[p + "self_attn.q_proj.weight"] = fake(cfg.q_dim, cfg.hidden)
@@ -128,16 +148,18 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
         w[p + "mlp.gate_proj.weight"] = fake(cfg.ffn, cfg.hidden)
         w[p + "mlp.up_proj.weight"] = fake(cfg.ffn, cfg.hidden)
         w[p + "mlp.down_proj.weight"] = fake(cfg.hidden, cfg.ffn)
-        w[p + "input_layernorm.weight"] = torch.ones(cfg.hidden, dtype=torch.bfloat16)
-        w[p + "post_attention_layernorm.weight"] = torch.ones(cfg.hidden, dtype=torch.bfloat16)
-    ora = LlamaOracle(cfg, w)
+        w[p + "input_layernorm.weight"] = torch.ones(cfg.hidden, dtype=dtype)
+        w[p + "post_attention_layernorm.weight"] = torch.ones(cfg.hidden, dtype=dtype)
+    log(f"cpu reference: dtype {dtype}, {cores} threads, building weights")
+    ora = LlamaOracle(cfg, w, dtype=dtype)
     del w
+    log("cpu reference: oracle ready")
     B, ctx = args.batch, args.prompt_len
 
     def fresh_states():
         sts = []
         for _ in range(B):
-            st = SeqState(cfg, torch.bfloat16)
+            st = SeqState(cfg, dtype)
             st.k = [fake(ctx, cfg.kv_dim).view(ctx, cfg.n_kv_heads, cfg.head_dim) for _ in range(cfg.n_layers)]
             st.v = [fake(ctx, cfg.kv_dim).view(ctx, cfg.n_kv_heads, cfg.head_dim) for _ in range(cfg.n_layers)]
             st.n = ctx
@@ -146,22 +168,32 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
 
     nd = args.cpu_decode_steps
     times = []
+    t_budget = time.perf_counter() + args.cpu_budget_s
     for it in range(warmup + steps):
         sts = fresh_states()
         toks = [5] * B
         t0 = time.perf_counter()
+        done = 0
         for _ in range(nd):
             logits = ora.step([(st, [t]) for st, t in zip(sts, toks)])
             toks = torch.argmax(logits, dim=-1).tolist()
+            done += 1
+            if time.perf_counter() > t_budget and (times or it >= warmup):
+                break
         dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    total = sum(times)
-    val = B * nd * len(times) / total
+        log(f"cpu reference: iteration {it}: {done} decode steps in {dt:.2f}s")
+        if it >= warmup or time.perf_counter() > t_budget:
+            times.append((dt, done))
+        if time.perf_counter() > t_budget:
+            break
+    total = sum(t for t, _ in times)
+    n_dec = sum(d for _, d in times)
+    val = B * n_dec / total
     return {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": f"{args.model} B={B} ctx={ctx} (synthetic KV history) x {nd} batched decode steps per bench "
-                      f"step, torch CPU bf16 oracle (oracle/llama_oracle.py), {len(times)} timed steps",
-            "ms_per_step": 1e3 * total / len(times)}
+            "sample": f"{args.model} B={B} ctx={ctx} (synthetic KV history), {n_dec} batched decode steps timed "
+                      f"(bounded to ~{args.cpu_budget_s:.0f}s), torch CPU {str(dtype).split('.')[-1]} oracle "
+                      f"(oracle/llama_oracle.py), {cores} threads",
+            "ms_per_step": 1e3 * total / max(len(times), 1)}
 
 
 # ----------------------------------------------------------------------------------------------------------- ours
@@ -210,6 +242,7 @@ def run_ours(args) -> dict | None:
         eng.load_weight(p + "post_attention_layernorm.weight", ones)
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
+    log(f"engine built and {cfg.n_layers}-layer synthetic weights loaded")
 
     import numpy as np
 
@@ -241,8 +274,9 @@ def run_ours(args) -> dict | None:
         if world > 1:
             dist.barrier()
 
-    for _ in range(args.warmup):
-        job()
+    for i in range(args.warmup):
+        dw, tt, nt = job()
+        log(f"warmup job {i}: {nt} tokens, decode wall {dw:.3f}s, ttft p50 {1e3 * statistics.median(tt):.1f} ms")
     barrier()
     st0 = eng.status()
     decode_wall, ttfts, n_tok = 0.0, [], 0
@@ -256,6 +290,7 @@ def run_ours(args) -> dict | None:
         barrier()
         wall = time.perf_counter() - t0
     st1 = eng.status()
+    log(f"timed region done: {args.steps} jobs in {wall:.3f}s")
     dec_ms = st1.gpu_decode_ms - st0.gpu_decode_ms
     dec_tok = st1.decode_tokens - st0.decode_tokens
     dec_steps = st1.decode_steps - st0.decode_steps
@@ -277,6 +312,7 @@ def run_ours(args) -> dict | None:
     gemm_ms = g1.gemm_ms - g0.gemm_ms
     gemm_bytes = g1.gemm_bytes - g0.gemm_bytes
     gemm_calls = g1.gemm_calls - g0.gemm_calls
+    log(f"profiled pass done: {gemm_calls} GEMM launches, {gemm_ms:.2f} ms")
 
     # ---- reduce over ranks (max time, sum tokens)
     vals = torch.tensor([dec_ms, decode_wall, wall], dtype=torch.float64, device="cuda")
@@ -348,6 +384,11 @@ def main():
     out = run_ours(args)
     if out is None:
         return
+    try:  # keep the GPU numbers even if the CPU baseline leg is cut short by a timeout
+        (ROOT / "gpurun_out").mkdir(exist_ok=True)
+        (ROOT / "gpurun_out" / "bench_ours_partial.json").write_text(json.dumps(out))
+    except OSError:
+        pass
     if not args.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         ref = cpu_reference(args, steps=2, warmup=1)
         out["cpu_baseline"] = {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")}

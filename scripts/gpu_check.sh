@@ -14,9 +14,12 @@ for st in $STAGES; do
     engine) timeout 900 python -m pytest tests/test_engine_gpu.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/test_engine.log 2>&1; echo "engine rc=$?" ;;
     all) timeout 1800 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/test_all.log 2>&1; echo "all rc=$?" ;;
     smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
-    bench) timeout 1500 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" ;;
+    bench) timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" ;;
+    bench_small) timeout 300 python bench.py --model small --batch 8 --prompt-len 128 --gen-len 32 --no-cpu-baseline > gpurun_out/bench_small.log 2> gpurun_out/bench_small.err; echo "bench_small rc=$?" ;;
+    bench_gpu) timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_gpu.log 2> gpurun_out/bench_gpu.err; echo "bench_gpu rc=$?" ;;
+    bench_ref) timeout 400 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "bench_ref rc=$?" ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
     *) echo "unknown stage $st" ;;
   esac
 done
-tail -n 25 gpurun_out/test_kernels.log gpurun_out/test_engine.log 2>/dev/null
+tail -n 6 gpurun_out/*.log gpurun_out/*.err 2>/dev/null | cut -c1-1500
