@@ -133,6 +133,7 @@ typedef struct tgis_status {
   double gemm_ms;            /* with profiling on: summed CUDA-event time of every tcgen05 GEMM launch */
   double gemm_bytes;         /* ... and their algorithmic bytes (weights + activations in + result out) */
   int64_t gemm_calls;
+  int64_t graph_launches;    /* decode steps replayed from a captured CUDA graph */
 } tgis_status;
 
 const char* tgis_last_error(void);

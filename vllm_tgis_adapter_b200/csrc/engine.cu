@@ -165,10 +165,16 @@ struct tgis_engine {
   std::vector<double> prof_bytes;  // algorithmic bytes of the GEMM between events 2i and 2i+1
   double gemm_ms = 0, gemm_bytes = 0;
   long long gemm_calls = 0;
+  // CUDA graphs of pure-decode steps, keyed by (batch size, number of KV splits)
+  std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
+  std::unordered_map<uint64_t, long long> graph_nodes;
+  long long n_graph_launches = 0;
 
   ~tgis_engine() {
     if (h_stage) cudaFreeHost(h_stage);
     if (h_samp_out) cudaFreeHost(h_samp_out);
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    for (cudaEvent_t ev : prof_events) cudaEventDestroy(ev);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -413,6 +419,65 @@ struct tgis_engine {
   template <class T>
   T* ds(size_t off) { return reinterpret_cast<T*>(d_stage.p + off); }
 
+  // Enqueue one step on `stream`: H2D metadata, layer stack, lm_head + sampler, D2H results.  Reads every per-step
+  // quantity from the device staging buffer, so the same sequence can be captured once into a CUDA graph and replayed.
+  void launch_step(size_t copy_bytes, int T, int n_dec, int n_tiles, int R, int max_dec_kv) {
+    const tgis_config& c = cfg;
+    const int H = c.hidden, F = c.ffn, V = c.vocab;
+    CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
+
+    const int32_t* d_tok = ds<int32_t>(off_tok);
+    const AttnSeq* d_seqs = ds<AttnSeq>(off_seqs);
+    const int32_t* d_bt = ds<int32_t>(off_bt);
+    const float scale = 1.0f / std::sqrt((float)HEAD_DIM);
+
+    CK(bitmap_set_launch(seen_bitmap.p, bitmap_words, ds<int32_t>(off_tokslot), d_tok, T, stream));
+    CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
+    n_launches += 2;
+    for (int li = 0; li < c.n_layers; ++li) {
+      LayerW& l = layers[li];
+      if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+      else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+      ++n_launches;
+      gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H);
+      bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
+      bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
+      CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, c.n_q_heads,
+                             c.n_kv_heads, stream));
+      ++n_launches;
+      if (n_dec > 0) {
+        const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_decids), n_dec, d_bt, bt_stride,
+                              max_splits, part_o.p, part_ml.p, dec_counters.p, attn_out.p, q_dim, c.n_q_heads,
+                              c.n_kv_heads, scale, stream));
+        ++n_launches;
+      }
+      if (n_tiles > 0) {
+        CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
+                               n_tiles, d_bt, bt_stride, attn_out.p, q_dim, c.n_q_heads, c.n_kv_heads, scale,
+                               stream));
+        ++n_launches;
+      }
+      gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim);
+      CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
+      ++n_launches;
+      gemm(xm_xn, l.m_gu, xn.p, l.wgu, gate_up.p, T, 2 * F, H);
+      CK(silu_mul_launch(gate_up.p, act.p, T, F, stream));
+      ++n_launches;
+      gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F);
+    }
+    if (R > 0) {
+      CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
+      CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
+      n_launches += 2;
+      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, /*out_f32=*/1);
+      CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words, samp_scratch.p,
+                        d_samp_out.p, stream));
+      ++n_launches;
+      CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
+    }
+  }
+
   // returns number of sampled rows
   int run_batch(std::vector<Sched>& batch) {
     const tgis_config& c = cfg;
@@ -489,60 +554,42 @@ struct tgis_engine {
       }
       T += q_len;
     }
-    // ---- ship metadata
+    // ---- ship metadata + run the layer stack (one CUDA graph launch for a pure-decode step when enabled)
     const size_t copy_bytes = off_bt + sizeof(int32_t) * (size_t)S * bt_stride;
     CK(cudaEventRecord(ev0, stream));
-    CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
-
-    const int32_t* d_tok = ds<int32_t>(off_tok);
-    const AttnSeq* d_seqs = ds<AttnSeq>(off_seqs);
-    const int32_t* d_bt = ds<int32_t>(off_bt);
-    const float scale = 1.0f / std::sqrt((float)HEAD_DIM);
-
-    CK(bitmap_set_launch(seen_bitmap.p, bitmap_words, ds<int32_t>(off_tokslot), d_tok, T, stream));
-    CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
-    n_launches += 2;
-    for (int li = 0; li < c.n_layers; ++li) {
-      LayerW& l = layers[li];
-      if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
-      else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
-      ++n_launches;
-      gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H);
-      bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
-      bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
-      CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, c.n_q_heads,
-                             c.n_kv_heads, stream));
-      ++n_launches;
-      if (n_dec > 0) {
-        const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
-        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_decids), n_dec, d_bt, bt_stride,
-                              max_splits, part_o.p, part_ml.p, dec_counters.p, attn_out.p, q_dim, c.n_q_heads,
-                              c.n_kv_heads, scale, stream));
-        ++n_launches;
+    const bool graphable = cfg.use_cuda_graphs && !profiling && n_tiles == 0 && n_dec == S && R == S;
+    if (graphable) {
+      const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+      const uint64_t key = ((uint64_t)S << 16) | (uint64_t)max_splits;
+      auto it = graphs.find(key);
+      if (it == graphs.end()) {
+        if (graphs.size() >= 64) {
+          for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+          graphs.clear();
+        }
+        const long long launches_before = n_launches;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        try {
+          launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv);
+        } catch (...) {
+          cudaStreamEndCapture(stream, &g);
+          if (g) cudaGraphDestroy(g);
+          throw;
+        }
+        CK(cudaStreamEndCapture(stream, &g));
+        cudaGraphExec_t ge = nullptr;
+        CK(cudaGraphInstantiate(&ge, g, 0));
+        CK(cudaGraphDestroy(g));
+        graph_nodes[key] = n_launches - launches_before;
+        n_launches = launches_before;
+        it = graphs.emplace(key, ge).first;
       }
-      if (n_tiles > 0) {
-        CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
-                               n_tiles, d_bt, bt_stride, attn_out.p, q_dim, c.n_q_heads, c.n_kv_heads, scale,
-                               stream));
-        ++n_launches;
-      }
-      gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim);
-      CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
-      ++n_launches;
-      gemm(xm_xn, l.m_gu, xn.p, l.wgu, gate_up.p, T, 2 * F, H);
-      CK(silu_mul_launch(gate_up.p, act.p, T, F, stream));
-      ++n_launches;
-      gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F);
-    }
-    if (R > 0) {
-      CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
-      CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
-      n_launches += 2;
-      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, /*out_f32=*/1);
-      CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words, samp_scratch.p,
-                        d_samp_out.p, stream));
-      ++n_launches;
-      CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
+      CK(cudaGraphLaunch(it->second, stream));
+      n_launches += graph_nodes[key];
+      ++n_graph_launches;
+    } else {
+      launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv);
     }
     CK(cudaEventRecord(ev1, stream));
     CK(cudaStreamSynchronize(stream));
@@ -942,6 +989,7 @@ int tgis_engine_status(tgis_engine* e, tgis_status* out) {
   out->gemm_ms = e->gemm_ms;
   out->gemm_bytes = e->gemm_bytes;
   out->gemm_calls = e->gemm_calls;
+  out->graph_launches = e->n_graph_launches;
   if (e->errored) g_last_error = e->error_msg;
   return 0;
 }

@@ -93,7 +93,7 @@ class NativeEngine:
 
     def __init__(self, model: ModelConfig, *, max_num_seqs: int = 64, max_batched_tokens: int = 2048,
                  kv_cache_bytes: int = 0, gpu_mem_fraction: float = 0.85, device: int = 0, seed: int = 0,
-                 debug_gemm_ref: bool = False):
+                 debug_gemm_ref: bool = False, use_cuda_graphs: bool = True):
         self.lib = _lib.load_library()
         self.model = model
         cfg = TgisConfig()
@@ -104,7 +104,7 @@ class NativeEngine:
         cfg.max_num_seqs, cfg.max_batched_tokens = max_num_seqs, max_batched_tokens
         cfg.kv_cache_bytes, cfg.gpu_mem_fraction = kv_cache_bytes, gpu_mem_fraction
         cfg.device, cfg.tp_size, cfg.tp_rank = device, 1, 0
-        cfg.use_cuda_graphs, cfg.debug_gemm_ref, cfg.seed = 0, 1 if debug_gemm_ref else 0, seed
+        cfg.use_cuda_graphs, cfg.debug_gemm_ref, cfg.seed = int(use_cuda_graphs), 1 if debug_gemm_ref else 0, seed
         self._h = C.c_void_p()
         if self.lib.tgis_engine_create(C.byref(cfg), C.byref(self._h)) != 0:
             raise EngineError(f"tgis_engine_create failed: {_lib.last_error(self.lib)}")
