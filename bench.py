@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--prompt-len", type=int, default=512)
     ap.add_argument("--gen-len", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-decode-steps", type=int, default=4)
+    ap.add_argument("--cpu-decode-steps", type=int, default=3)
+    ap.add_argument("--cpu-layers", type=int, default=2, help="layers timed by the CPU baseline (extrapolated)")
     ap.add_argument("--cpu-budget-s", type=float, default=45.0, help="wall-clock bound of the CPU baseline sample")
     return ap.parse_args()
 
@@ -108,15 +109,19 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------- CPU reference
 def cpu_reference(args, steps: int, warmup: int) -> dict:
-    """The oracle port of the reference's CPU path, all host threads, bounded sample: B sequences with a
-    prompt_len-token (synthetic) KV history, `cpu_decode_steps` batched decode steps per bench step."""
+    """The oracle port of the reference's CPU path on the host cores, bounded sample: B sequences with a
+    prompt_len-token (synthetic) KV history; `cpu_layers` of the model's layers + final norm + lm_head are timed over
+    batched decode steps and the per-layer time is extrapolated linearly to the full depth (stated in `sample`)."""
+    import dataclasses
+
     import torch
 
     from oracle.llama_oracle import CONFIGS, LlamaOracle, SeqState
 
-    cfg = CONFIGS[args.model]
+    cfg_full = CONFIGS[args.model]
+    L_s = min(cfg_full.n_layers, args.cpu_layers)
+    cfg = dataclasses.replace(cfg_full, n_layers=L_s)
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
     # vLLM's CPU backend runs bf16 where the host has AMX / avx512_bf16 and fp32 otherwise: pick by a micro-benchmark
     xa, wa = torch.randn(32, 4096), torch.randn(4096, 4096)
@@ -129,7 +134,10 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
             torch.nn.functional.linear(x_, w_)
         return time.perf_counter() - t0
 
-    dtype = torch.bfloat16 if _t(torch.bfloat16) <= 1.5 * _t(torch.float32) else torch.float32
+    torch.set_num_threads(min(cores, 32))
+    t16, t32 = _t(torch.bfloat16), _t(torch.float32)
+    dtype = torch.bfloat16 if t16 <= 1.5 * t32 else torch.float32
+    log(f"cpu reference: linear micro-bench bf16 {1e3 * t16:.1f} ms vs fp32 {1e3 * t32:.1f} ms -> {dtype}")
     tile = (torch.randn(1024, 1024, generator=g) * 0.02).to(dtype)
 
     def fake(rows: int, cols: int) -> torch.Tensor:  # values irrelevant for timing; avoids minutes of randn
@@ -150,10 +158,8 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
         w[p + "mlp.down_proj.weight"] = fake(cfg.hidden, cfg.ffn)
         w[p + "input_layernorm.weight"] = torch.ones(cfg.hidden, dtype=dtype)
         w[p + "post_attention_layernorm.weight"] = torch.ones(cfg.hidden, dtype=dtype)
-    log(f"cpu reference: dtype {dtype}, {cores} threads, building weights")
     ora = LlamaOracle(cfg, w, dtype=dtype)
     del w
-    log("cpu reference: oracle ready")
     B, ctx = args.batch, args.prompt_len
 
     def fresh_states():
@@ -166,34 +172,51 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
             sts.append(st)
         return sts
 
+    def decode_steps(n: int) -> float:
+        sts = fresh_states()
+        toks = [5] * B
+        t0 = time.perf_counter()
+        for _ in range(n):
+            logits = ora.step([(st, [t]) for st, t in zip(sts, toks)])
+            toks = torch.argmax(logits, dim=-1).tolist()
+        return (time.perf_counter() - t0) / n
+
+    # thread count: all host threads unless fewer are faster (OpenMP fork/join cost on very wide hosts)
+    best_thr, best_t = cores, None
+    for thr in sorted({cores, min(cores, 64), min(cores, 32)}, reverse=True):
+        torch.set_num_threads(thr)
+        t = decode_steps(1)
+        log(f"cpu reference: {thr} threads -> {t:.3f} s per {L_s}-layer decode step (probe)")
+        if best_t is None or t < best_t:
+            best_thr, best_t = thr, t
+    torch.set_num_threads(best_thr)
     nd = args.cpu_decode_steps
     times = []
     t_budget = time.perf_counter() + args.cpu_budget_s
     for it in range(warmup + steps):
-        sts = fresh_states()
-        toks = [5] * B
-        t0 = time.perf_counter()
-        done = 0
-        for _ in range(nd):
-            logits = ora.step([(st, [t]) for st, t in zip(sts, toks)])
-            toks = torch.argmax(logits, dim=-1).tolist()
-            done += 1
-            if time.perf_counter() > t_budget and (times or it >= warmup):
-                break
-        dt = time.perf_counter() - t0
-        log(f"cpu reference: iteration {it}: {done} decode steps in {dt:.2f}s")
+        t = decode_steps(nd)
+        log(f"cpu reference: iteration {it}: {t:.3f} s per {L_s}-layer decode step")
         if it >= warmup or time.perf_counter() > t_budget:
-            times.append((dt, done))
+            times.append(t)
         if time.perf_counter() > t_budget:
             break
-    total = sum(t for t, _ in times)
-    n_dec = sum(d for _, d in times)
-    val = B * n_dec / total
-    return {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": f"{args.model} B={B} ctx={ctx} (synthetic KV history), {n_dec} batched decode steps timed "
-                      f"(bounded to ~{args.cpu_budget_s:.0f}s), torch CPU {str(dtype).split('.')[-1]} oracle "
-                      f"(oracle/llama_oracle.py), {cores} threads",
-            "ms_per_step": 1e3 * total / max(len(times), 1)}
+    t_sample = sum(times) / len(times)
+    # head (final norm + lm_head + argmax) timed alone so the layer part can be scaled to the full depth
+    xh = torch.randn(B, cfg.hidden).to(dtype)
+    ora.head(xh)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ora.head(xh)
+    t_head = (time.perf_counter() - t0) / 3
+    t_layer = max(t_sample - t_head, 0.0) / L_s
+    t_full = t_head + t_layer * cfg_full.n_layers
+    val = B / t_full
+    return {"value": val, "unit": "tokens/s", "cores": best_thr, "kind": "port",
+            "sample": f"{args.model} B={B} ctx={ctx} (synthetic KV history): {L_s} of {cfg_full.n_layers} layers + lm_head "
+                      f"timed over {nd * len(times)} batched decode steps ({t_sample * 1e3:.0f} ms/step, head "
+                      f"{t_head * 1e3:.0f} ms), per-layer time extrapolated linearly to {cfg_full.n_layers} layers; torch "
+                      f"CPU {str(dtype).split('.')[-1]} oracle (oracle/llama_oracle.py), {best_thr} of {cores} threads",
+            "ms_per_step": 1e3 * t_full}
 
 
 # ----------------------------------------------------------------------------------------------------------- ours

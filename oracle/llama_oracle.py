@@ -141,6 +141,7 @@ class LlamaOracle:
                 "ln2": w[p + "post_attention_layernorm.weight"],
             })
         self.cos_sin = rope_table(cfg, dtype)
+        self._lm_head_f32 = None
 
     # -- building blocks ---------------------------------------------------------------------------------------
     def _rms(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
@@ -219,9 +220,17 @@ class LlamaOracle:
                 off += len(ts)
                 last.append(off - 1)
             xn = xn[torch.tensor(last)]
-        # logits stay fp32 (no model-dtype round trip): the engine's lm_head epilogue writes the fp32 accumulator.
-        # vLLM rounds them to bf16 first (logits_processor.py:89-104); see DESIGN.md 'logits precision'.
-        return xn.float() @ self.lm_head.float().t()
+        return self.head(xn, normed=True)
+
+    def head(self, x: torch.Tensor, normed: bool = False) -> torch.Tensor:
+        """final RMSNorm (unless already applied) + lm_head.  Logits stay fp32 (no model-dtype round trip): the
+        engine's lm_head epilogue writes the fp32 accumulator.  vLLM rounds them to bf16 first
+        (logits_processor.py:89-104); see DESIGN.md 'logits precision'."""
+        if not normed:
+            x = self._rms(x, self.norm)
+        if self._lm_head_f32 is None:
+            self._lm_head_f32 = self.lm_head.float()
+        return x.float() @ self._lm_head_f32.t()
 
     def new_seq(self) -> SeqState:
         return SeqState(self.cfg, self.dtype)

@@ -244,18 +244,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         const int is_last = *flag_smem;
         if (is_last) {
           __threadfence();
-          for (int t = 0; t < t_valid; ++t) {
-            float sum = 0.f;
-            for (int c = c_first; c <= c_last; ++c) {
-              const long long cb = (total * c) / ncta;
-              const int cslot = ((int)(cb / KB) == tile) ? 0 : 1;
-              const float* p = ws + ((size_t)(c * 2 + cslot) * BT + t) * GEMM_BN + row;
-              sum += __ldcg(p);
+          // Ordered (CTA-rank) reduction with many loads in flight: contributors are walked in groups of FIX_C, tokens
+          // in groups of FIX_T, all FIX_C*FIX_T L2 loads of a group are issued before the first add.
+          constexpr int FIX_C = 4, FIX_T = 8;
+          for (int t0 = 0; t0 < t_valid; t0 += FIX_T) {
+            float acc[FIX_T];
+#pragma unroll
+            for (int j = 0; j < FIX_T; ++j) acc[j] = 0.f;
+            for (int c0g = c_first; c0g <= c_last; c0g += FIX_C) {
+              float v[FIX_C][FIX_T];
+#pragma unroll
+              for (int ci = 0; ci < FIX_C; ++ci) {
+                const int c = c0g + ci;
+                const bool cv = c <= c_last;
+                const long long cb = cv ? (total * c) / ncta : 0;
+                const int cslot = ((int)(cb / KB) == tile) ? 0 : 1;
+                const float* p = ws + ((size_t)((cv ? c : c_first) * 2 + cslot) * BT + t0) * GEMM_BN + row;
+#pragma unroll
+                for (int j = 0; j < FIX_T; ++j)
+                  v[ci][j] = (cv && t0 + j < t_valid) ? __ldcg(p + (size_t)j * GEMM_BN) : 0.f;
+              }
+#pragma unroll
+              for (int ci = 0; ci < FIX_C; ++ci)
+#pragma unroll
+                for (int j = 0; j < FIX_T; ++j) acc[j] += v[ci][j];
             }
             if (n < N) {
-              const size_t o = (size_t)(t_base + t) * ldy + n;
-              if (out_f32) Yf[o] = sum;
-              else Y[o] = __float2bfloat16_rn(sum);
+#pragma unroll
+              for (int j = 0; j < FIX_T; ++j)
+                if (t0 + j < t_valid) {
+                  const size_t o = (size_t)(t_base + t0 + j) * ldy + n;
+                  if (out_f32) Yf[o] = acc[j];
+                  else Y[o] = __float2bfloat16_rn(acc[j]);
+                }
             }
           }
           if (ep_tid == 0) counters[tile] = 0;
