@@ -14,6 +14,7 @@
 // prefill (q_len >= 1): grid (16-query tile, kv_head); one warp per query head of the group; mma.sync m16n8k16 with
 //                      online softmax; KV blocks double-buffered through smem by TMA bulk copies.
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace tgis {
@@ -43,6 +44,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
                    int max_splits, float* __restrict__ part_o, float* __restrict__ part_ml,
                    int* __restrict__ counters, __nv_bfloat16* __restrict__ out, int out_ld, int n_kv, float scale) {
   extern __shared__ __align__(128) uint8_t smem[];
+  griddep_launch();
+  griddep_wait();
   uint8_t* kv_s = smem;                                                       // DEC_BLOCKS x (K 8K | V 8K)
   float* q_s = reinterpret_cast<float*>(smem + DEC_BLOCKS * 2 * TILE_BYTES);  // [G][128]
   float* p_s = q_s + G * HEAD_DIM;                                            // [4 warps][G][32]
@@ -225,10 +228,8 @@ static cudaError_t decode_launch_g(const __nv_bfloat16* qkv, int qkv_ld, const _
     attr = true;
   }
   dim3 grid(n_seqs * max_splits, n_kv);
-  attn_decode_kernel<G><<<grid, 128, smem, stream>>>(qkv, qkv_ld, k_cache, v_cache, seqs, seq_ids, block_table,
-                                                     bt_stride, max_splits, part_o, part_ml, counters, out, out_ld,
-                                                     n_kv, scale);
-  return cudaGetLastError();
+  return launch_k(attn_decode_kernel<G>, grid, dim3(128), smem, stream, qkv, qkv_ld, k_cache, v_cache, seqs, seq_ids,
+                  block_table, bt_stride, max_splits, part_o, part_ml, counters, out, out_ld, n_kv, scale);
 }
 
 cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
@@ -282,6 +283,8 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __n
                     int out_ld, int n_kv, int G, float scale) {
   __shared__ __align__(128) uint8_t kv_s[2 * 2 * TILE_BYTES];  // 2 stages x (K | V)
   __shared__ uint64_t bars[2];
+  griddep_launch();
+  griddep_wait();
   const int tile = blockIdx.x, kvh = blockIdx.y;
   const AttnSeq sq = seqs[tile_seq[tile]];
   const int q0 = tile_q0[tile];                      // first query (index within this step's q_len)
@@ -446,9 +449,8 @@ cudaError_t attn_prefill_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv
   const int G = n_q / n_kv;
   if (G > 8) return cudaErrorInvalidValue;
   dim3 grid(n_tiles, n_kv);
-  attn_prefill_kernel<<<grid, 32 * G, 0, stream>>>(qkv, qkv_ld, k_cache, v_cache, seqs, tile_seq, tile_q0,
-                                                   block_table, bt_stride, out, out_ld, n_kv, G, scale);
-  return cudaGetLastError();
+  return launch_k(attn_prefill_kernel, grid, dim3(32 * G), 0, stream, qkv, qkv_ld, k_cache, v_cache, seqs, tile_seq,
+                  tile_q0, block_table, bt_stride, out, out_ld, n_kv, G, scale);
 }
 
 }  // namespace tgis

@@ -7,6 +7,7 @@
 // All of them are 16-byte vectorised, coalesced, one row (or 8 elements) per thread group; no shared-memory reuse is
 // possible (each byte is touched once) so the design target is simply full-width coalesced traffic.
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace tgis {
@@ -36,6 +37,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ------------------------------------------------------------------------------------------------ embedding / gather
 __global__ void gather_rows_kernel(const int32_t* __restrict__ idx, const __nv_bfloat16* __restrict__ table,
                                    __nv_bfloat16* __restrict__ out, int hidden, int n_table_rows) {
+  griddep_launch();
+  griddep_wait();
   const int t = blockIdx.x;
   int row = idx[t];
   if (row < 0 || row >= n_table_rows) row = 0;  // padding rows: any valid row (never consumed)
@@ -47,15 +50,13 @@ __global__ void gather_rows_kernel(const int32_t* __restrict__ idx, const __nv_b
 cudaError_t embed_gather_launch(const int32_t* token_ids, const __nv_bfloat16* table, __nv_bfloat16* out, int T,
                                 int hidden, int vocab, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
-  gather_rows_kernel<<<T, 128, 0, stream>>>(token_ids, table, out, hidden, vocab);
-  return cudaGetLastError();
+  return launch_k(gather_rows_kernel, dim3(T), dim3(128), 0, stream, token_ids, table, out, hidden, vocab);
 }
 
 cudaError_t gather_rows_launch(const __nv_bfloat16* x, const int32_t* rows, __nv_bfloat16* out, int R, int hidden,
                                cudaStream_t stream) {
   if (R <= 0) return cudaSuccess;
-  gather_rows_kernel<<<R, 128, 0, stream>>>(rows, x, out, hidden, 1 << 30);
-  return cudaGetLastError();
+  return launch_k(gather_rows_kernel, dim3(R), dim3(128), 0, stream, rows, x, out, hidden, 1 << 30);
 }
 
 // ------------------------------------------------------------------------------------------------ RMSNorm
@@ -67,6 +68,8 @@ __global__ void __launch_bounds__(NORM_THREADS)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int hidden, float eps) {
   __shared__ float red[NORM_THREADS / 32];
+  griddep_launch();
+  griddep_wait();
   const size_t base = (size_t)blockIdx.x * hidden;
   const int nvec = hidden / 8;
   BF8 z[NORM_MAX_VEC];
@@ -112,21 +115,21 @@ cudaError_t rmsnorm_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
                            float eps, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   if (hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
-  rmsnorm_kernel<false><<<T, NORM_THREADS, 0, stream>>>(x, nullptr, w, out, hidden, eps);
-  return cudaGetLastError();
+  return launch_k(rmsnorm_kernel<false>, dim3(T), dim3(NORM_THREADS), 0, stream, x, (__nv_bfloat16*)nullptr, w, out, hidden, eps);
 }
 
 cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, const __nv_bfloat16* w,
                                __nv_bfloat16* out, int T, int hidden, float eps, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   if (hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
-  rmsnorm_kernel<true><<<T, NORM_THREADS, 0, stream>>>(x, residual, w, out, hidden, eps);
-  return cudaGetLastError();
+  return launch_k(rmsnorm_kernel<true>, dim3(T), dim3(NORM_THREADS), 0, stream, x, residual, w, out, hidden, eps);
 }
 
 // ------------------------------------------------------------------------------------------------ SiLU * mul
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gate_up, __nv_bfloat16* __restrict__ act, int T,
                                 int ffn) {
+  griddep_launch();
+  griddep_wait();
   const int vec_per_row = ffn / 8;
   const long long total = (long long)T * vec_per_row;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -151,8 +154,7 @@ cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, in
   const long long total = (long long)T * (ffn / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  silu_mul_kernel<<<(int)blocks, 256, 0, stream>>>(gate_up, act, T, ffn);
-  return cudaGetLastError();
+  return launch_k(silu_mul_kernel, dim3((int)blocks), dim3(256), 0, stream, gate_up, act, T, ffn);
 }
 
 // ------------------------------------------------------------------------------------------------ RoPE + KV scatter
@@ -161,6 +163,8 @@ __global__ void __launch_bounds__(256)
 rope_kvwrite_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ positions,
                     const int32_t* __restrict__ slot_mapping, const __nv_bfloat16* __restrict__ cos_sin,
                     __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int n_q, int n_kv) {
+  griddep_launch();
+  griddep_wait();
   const int t = blockIdx.x;
   const int head = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int i = threadIdx.x & 63;
@@ -201,8 +205,8 @@ cudaError_t rope_kvwrite_launch(__nv_bfloat16* qkv, const int32_t* positions, co
   if (T <= 0) return cudaSuccess;
   const int n_heads = n_q + 2 * n_kv;
   dim3 grid(T, (n_heads + 3) / 4);
-  rope_kvwrite_kernel<<<grid, 256, 0, stream>>>(qkv, positions, slot_mapping, cos_sin, k_cache, v_cache, n_q, n_kv);
-  return cudaGetLastError();
+  return launch_k(rope_kvwrite_kernel, grid, dim3(256), 0, stream, qkv, positions, slot_mapping, cos_sin, k_cache, v_cache,
+                  n_q, n_kv);
 }
 
 }  // namespace tgis

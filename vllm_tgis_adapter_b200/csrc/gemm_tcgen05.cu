@@ -15,8 +15,9 @@
 //  * persistent stream-K: the (tile, k-block) iteration space is cut into gridDim.x equal contiguous ranges, so all
 //    148 SMs stream the same number of weight bytes whatever N is.  A tile split across CTAs is reduced by the
 //    LAST-arriving CTA summing the fp32 partials in fixed CTA order -> bit-deterministic and independent of timing.
-#include "ptx.cuh"
 #include "kernels.h"
+#include "launch.cuh"
+#include "ptx.cuh"
 
 namespace tgis {
 
@@ -115,32 +116,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  griddep_launch();  // PDL: the next kernel may start its prologue now
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // The CTA's k-blocks are one contiguous range [begin, end) of the global (tile, k-block) space.  Weights are
+    // static, so the first STAGES weight tiles are requested BEFORE the grid-dependency wait: under PDL this
+    // overlaps the previous kernel's tail (and the small kernel in between) with useful HBM traffic.
     if (elect_one()) {
       const uint64_t pol_w = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
-      UnitIter it(total, KB, cta, ncta);
-      int tile, kb0, kb1, slot;
+      const long long begin = (total * cta) / ncta, end = (total * (cta + 1)) / ncta;
+      const int n_kb = (int)(end - begin);
+      auto issue_w = [&](int i, int stage) {
+        const long long pos = begin + i;
+        const int tile = (int)(pos / KB), kb = (int)(pos % KB);
+        void* dst = smem_w + stage * Cfg::W_BYTES;
+        if (stream_weights) tma_load_2d_hint(&wmap, &full_bar[stage], dst, kb * GEMM_BK, (tile / t_tiles) * GEMM_BN, pol_w);
+        else tma_load_2d(&wmap, &full_bar[stage], dst, kb * GEMM_BK, (tile / t_tiles) * GEMM_BN);
+      };
+      const int n_pre = n_kb < STAGES ? n_kb : STAGES;
+      for (int i = 0; i < n_pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+        issue_w(i, i);
+      }
+      griddep_wait();  // activations (and everything the epilogue will touch) are now final
       int stage = 0;
       uint32_t phase = 0;
-      while (it.next(tile, kb0, kb1, slot)) {
-        const int n_tile = tile / t_tiles, t_tile = tile % t_tiles;
-        for (int kb = kb0; kb < kb1; ++kb) {
+      for (int i = 0; i < n_kb; ++i) {
+        if (i >= n_pre) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (stream_weights)
-            tma_load_2d_hint(&wmap, &full_bar[stage], smem_w + stage * Cfg::W_BYTES, kb * GEMM_BK,
-                             n_tile * GEMM_BN, pol_w);
-          else
-            tma_load_2d(&wmap, &full_bar[stage], smem_w + stage * Cfg::W_BYTES, kb * GEMM_BK, n_tile * GEMM_BN);
-          tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, kb * GEMM_BK, t_tile * BT,
-                           pol_x);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          issue_w(i, stage);
+        }
+        const long long pos = begin + i;
+        const int tile = (int)(pos / KB), kb = (int)(pos % KB);
+        tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, kb * GEMM_BK, (tile % t_tiles) * BT,
+                         pol_x);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -231,19 +246,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
 
       if (partial) {
         // stream-K fix-up: last arriver reduces all partials of this tile in CTA order (deterministic)
-        __threadfence();
+        // publish: CTA-wide barrier, then ONE acq_rel atomic (cumulative over the barrier) instead of membar.gl
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
         const long long p0 = (long long)tile * KB;
         const int c_first = unit_owner(p0, total, ncta);
         const int c_last = unit_owner(p0 + KB - 1, total, ncta);
         if (ep_tid == 0) {
-          int old = atomicAdd(&counters[tile], 1);
+          int old;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;\n" : "=r"(old) : "l"(counters + tile) : "memory");
           *flag_smem = (old == (c_last - c_first)) ? 1 : 0;
         }
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
         const int is_last = *flag_smem;
         if (is_last) {
-          __threadfence();
           // Ordered (CTA-rank) reduction with many loads in flight: contributors are walked in groups of FIX_C, tokens
           // in groups of FIX_T, all FIX_C*FIX_T L2 loads of a group are issued before the first add.
           constexpr int FIX_C = 4, FIX_T = 8;
@@ -351,10 +366,17 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, v
   // do not cut finer than 4 k-blocks per CTA: tiny problems use fewer CTAs
   long long max_ctas = (total + 3) / 4;
   int grid = (int)(max_ctas < num_sms ? (max_ctas < 1 ? 1 : max_ctas) : num_sms);
+  // few tiles (decode-shaped qkv / o / down): split every tile by the same integer factor so each CTA owns exactly
+  // one unit inside one tile (one fix-up round instead of two; costs <= 1/(split+1) of the SMs)
+  const long long tiles = (long long)n_tiles * t_tiles;
+  if (tiles <= num_sms / 2) {
+    int split = (int)(num_sms / tiles);
+    if (split > KB / 4) split = KB / 4 > 0 ? KB / 4 : 1;
+    grid = (int)(tiles * split);
+  }
   const int stream_weights = (t_tiles == 1) ? 1 : 0;
-  gemm_bf16_tcgen05_kernel<BT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(wmap, xmap, Y, ldy, T, N, K, ws,
-                                                                                 counters, stream_weights, out_f32);
-  return cudaGetLastError();
+  return launch_k(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
+                  ldy, T, N, K, ws, counters, stream_weights, out_f32);
 }
 
 // xmap must have been built with box_rows == gemm_pick_bt(T)

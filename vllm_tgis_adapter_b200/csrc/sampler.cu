@@ -13,6 +13,7 @@
 // one row; the fp32 row (512 KiB) is read from HBM once and stays in the 126 MB L2 for the extra selection passes
 // (radix-select thresholds instead of the reference's full sorts).  Loads are 16-byte vectorised and coalesced.
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace tgis {
@@ -256,6 +257,8 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   __shared__ float histf[256];
   __shared__ uint32_t bcast[4];
   int* histi = reinterpret_cast<int*>(histf);
+  griddep_launch();
+  griddep_wait();
 
   const int r = blockIdx.x;
   RowCtx c;
@@ -440,19 +443,21 @@ cudaError_t sampler_launch(const float* logits, int ld, int vocab, const SampleR
                            cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   if (vocab % 8 != 0 || ld % 8 != 0) return cudaErrorInvalidValue;
-  tgis_sampler_kernel<<<n_rows, SAMP_THREADS, 0, stream>>>(logits, ld, vocab, rows,
-                                                           const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch,
-                                                           out);
-  return cudaGetLastError();
+  return launch_k(tgis_sampler_kernel, dim3(n_rows), dim3(SAMP_THREADS), 0, stream, logits, ld, vocab, rows,
+                  const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out);
 }
 
 size_t sampler_scratch_floats(int vocab) { return (size_t)vocab; }
 
 // ---------------------------------------------------------------- seen-token bitmap maintenance
 __global__ void bitmap_clear_kernel(uint32_t* bm, int words) {
+  griddep_launch();
+  griddep_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) bm[i] = 0u;
 }
 __global__ void bitmap_set_kernel(uint32_t* bm, int words, const int32_t* slots, const int32_t* tokens, int n) {
+  griddep_launch();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = slots[i], t = tokens[i];
@@ -460,14 +465,12 @@ __global__ void bitmap_set_kernel(uint32_t* bm, int words, const int32_t* slots,
   atomicOr(&bm[(size_t)s * words + (t >> 5)], 1u << (t & 31));
 }
 cudaError_t bitmap_clear_launch(uint32_t* bitmap, int bitmap_words, int slot, cudaStream_t stream) {
-  bitmap_clear_kernel<<<8, 256, 0, stream>>>(bitmap + (size_t)slot * bitmap_words, bitmap_words);
-  return cudaGetLastError();
+  return launch_k(bitmap_clear_kernel, dim3(8), dim3(256), 0, stream, bitmap + (size_t)slot * bitmap_words, bitmap_words);
 }
 cudaError_t bitmap_set_launch(uint32_t* bitmap, int bitmap_words, const int32_t* slots, const int32_t* tokens, int n,
                               cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  bitmap_set_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bitmap, bitmap_words, slots, tokens, n);
-  return cudaGetLastError();
+  return launch_k(bitmap_set_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, bitmap, bitmap_words, slots, tokens, n);
 }
 
 }  // namespace tgis
