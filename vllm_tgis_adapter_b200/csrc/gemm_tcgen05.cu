@@ -128,31 +128,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       const uint64_t pol_x = policy_evict_last();
       const long long begin = (total * cta) / ncta, end = (total * (cta + 1)) / ncta;
       const int n_kb = (int)(end - begin);
-      auto issue_w = [&](int i, int stage) {
-        const long long pos = begin + i;
-        const int tile = (int)(pos / KB), kb = (int)(pos % KB);
+      // (tile, kb) cursors advanced incrementally: no 64-bit divisions on the issue path
+      const int tile0 = (int)(begin / KB), kb0 = (int)(begin % KB);
+      auto issue_w = [&](int tile, int kb, int stage) {
         void* dst = smem_w + stage * Cfg::W_BYTES;
-        if (stream_weights) tma_load_2d_hint(&wmap, &full_bar[stage], dst, kb * GEMM_BK, (tile / t_tiles) * GEMM_BN, pol_w);
-        else tma_load_2d(&wmap, &full_bar[stage], dst, kb * GEMM_BK, (tile / t_tiles) * GEMM_BN);
+        const int row = (t_tiles == 1 ? tile : tile / t_tiles) * GEMM_BN;
+        if (stream_weights) tma_load_2d_hint(&wmap, &full_bar[stage], dst, kb * GEMM_BK, row, pol_w);
+        else tma_load_2d(&wmap, &full_bar[stage], dst, kb * GEMM_BK, row);
       };
       const int n_pre = n_kb < STAGES ? n_kb : STAGES;
+      int w_tile = tile0, w_kb = kb0;
       for (int i = 0; i < n_pre; ++i) {
         mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
-        issue_w(i, i);
+        issue_w(w_tile, w_kb, i);
+        if (++w_kb == KB) { w_kb = 0; ++w_tile; }
       }
       griddep_wait();  // activations (and everything the epilogue will touch) are now final
       int stage = 0;
       uint32_t phase = 0;
+      int x_tile = tile0, x_kb = kb0;
       for (int i = 0; i < n_kb; ++i) {
         if (i >= n_pre) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          issue_w(i, stage);
+          issue_w(w_tile, w_kb, stage);
+          if (++w_kb == KB) { w_kb = 0; ++w_tile; }
         }
-        const long long pos = begin + i;
-        const int tile = (int)(pos / KB), kb = (int)(pos % KB);
-        tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, kb * GEMM_BK, (tile % t_tiles) * BT,
-                         pol_x);
+        tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, x_kb * GEMM_BK,
+                         (t_tiles == 1 ? 0 : x_tile % t_tiles) * BT, pol_x);
+        if (++x_kb == KB) { x_kb = 0; ++x_tile; }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;

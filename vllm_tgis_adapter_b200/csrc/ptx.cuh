@@ -57,8 +57,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded spin: a protocol bug traps (-> sticky CUDA error surfaced to the host) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifdef TGIS_MBAR_TIMEOUT
-  for (uint64_t it = 0; it < (1ull << 22); ++it)
+  const long long t0 = clock64();
+  for (;;) {
     if (mbar_try_wait(bar, parity)) return;
+    if (clock64() - t0 > 4000000000ll) break;  // ~2 s at 2 GHz: no legitimate wait in this code base is that long
+  }
   printf("mbar_wait timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
   __trap();
 #else
