@@ -55,7 +55,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
 
   const int sidx = blockIdx.x / max_splits, split = blockIdx.x % max_splits;
   const int kvh = blockIdx.y;
-  const AttnSeq sq = seqs[seq_ids[sidx]];
+  const AttnSeq sq = seqs[seq_ids ? seq_ids[sidx] : sidx];  // engine: decode sequences are entries 0..n-1
   const int kv_len = sq.kv_len;
   const int n_splits = (kv_len + DEC_TOK - 1) / DEC_TOK;
   if (split >= n_splits) return;
@@ -64,20 +64,20 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   const int n_blk = (n_tok + KV_BLOCK - 1) / KV_BLOCK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) {
-    for (int j = 0; j < DEC_BLOCKS; ++j) mbar_init(&bars[j], 1);
+  // Each warp owns one KV block and its mbarrier: lane 0 initialises the barrier and issues the two TMA bulk copies
+  // of its block, so the 4 block-table look-ups and 8 copies are issued in parallel with no CTA-wide barrier.
+  if (lane == 0) {
+    mbar_init(&bars[warp], 1);
     fence_barrier_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int32_t* bt = block_table + (size_t)sq.block_row * bt_stride + tok0 / KV_BLOCK;
-    for (int j = 0; j < n_blk; ++j) {
-      const size_t tile = ((size_t)bt[j] * n_kv + kvh) * (KV_BLOCK * HEAD_DIM);
-      mbar_arrive_expect_tx(&bars[j], 2 * TILE_BYTES);
-      bulk_load_1d(kv_s + j * 2 * TILE_BYTES, k_cache + tile, TILE_BYTES, &bars[j]);
-      bulk_load_1d(kv_s + j * 2 * TILE_BYTES + TILE_BYTES, v_cache + tile, TILE_BYTES, &bars[j]);
+    if (warp < n_blk) {
+      const int32_t blk = block_table[(size_t)sq.block_row * bt_stride + tok0 / KV_BLOCK + warp];
+      const size_t tile = ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM);
+      mbar_arrive_expect_tx(&bars[warp], 2 * TILE_BYTES);
+      bulk_load_1d(kv_s + warp * 2 * TILE_BYTES, k_cache + tile, TILE_BYTES, &bars[warp]);
+      bulk_load_1d(kv_s + warp * 2 * TILE_BYTES + TILE_BYTES, v_cache + tile, TILE_BYTES, &bars[warp]);
     }
   }
+  __syncwarp();
   // stage the group's queries as fp32 (overlaps the TMA flight time)
   {
     const __nv_bfloat16* q = qkv + (size_t)sq.q_start * qkv_ld + (size_t)kvh * G * HEAD_DIM;

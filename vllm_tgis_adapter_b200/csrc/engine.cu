@@ -447,7 +447,7 @@ struct tgis_engine {
       ++n_launches;
       if (n_dec > 0) {
         const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
-        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_decids), n_dec, d_bt, bt_stride,
+        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, d_seqs, /*seq_ids=*/nullptr, n_dec, d_bt, bt_stride,
                               max_splits, part_o.p, part_ml.p, dec_counters.p, attn_out.p, q_dim, c.n_q_heads,
                               c.n_kv_heads, scale, stream));
         ++n_launches;

@@ -378,6 +378,10 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, v
     if (split > KB / 4) split = KB / 4 > 0 ? KB / 4 : 1;
     grid = (int)(tiles * split);
   }
+  if (const char* e = getenv("TGIS_GEMM_MAX_CTAS")) {  // experiment knob (scripts/gemm_bench.py)
+    const int cap = atoi(e);
+    if (cap > 0 && grid > cap) grid = cap;
+  }
   const int stream_weights = (t_tiles == 1) ? 1 : 0;
   return launch_k(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
                   ldy, T, N, K, ws, counters, stream_weights, out_f32);
