@@ -219,6 +219,20 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
             "ms_per_step": 1e3 * t_full}
 
 
+def reduce_over_ranks(max_vals: list[float], sum_vals: list[float], device: str) -> tuple[list[float], list[float]]:
+    """Whole-job aggregation for the N>1 (data-parallel replicas) path: times -> MAX over ranks, counts -> SUM.
+    Works on any initialised torch.distributed backend (NCCL on the GPU box, gloo in tests/test_multirank_cpu.py)."""
+    import torch
+    import torch.distributed as dist
+
+    vals = torch.tensor(max_vals, dtype=torch.float64, device=device)
+    sums = torch.tensor(sum_vals, dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    return vals.tolist(), sums.tolist()
+
+
 # ----------------------------------------------------------------------------------------------------------- ours
 def run_ours(args) -> dict | None:
     import torch
@@ -338,13 +352,8 @@ def run_ours(args) -> dict | None:
     log(f"profiled pass done: {gemm_calls} GEMM launches, {gemm_ms:.2f} ms")
 
     # ---- reduce over ranks (max time, sum tokens)
-    vals = torch.tensor([dec_ms, decode_wall, wall], dtype=torch.float64, device="cuda")
-    sums = torch.tensor([dec_tok, n_tok, launches], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    dec_ms_m, decode_wall_m, wall_m = vals.tolist()
-    dec_tok_s, n_tok_s, launches_s = sums.tolist()
+    (dec_ms_m, decode_wall_m, wall_m), (dec_tok_s, n_tok_s, launches_s) = reduce_over_ranks(
+        [dec_ms, decode_wall, wall], [dec_tok, n_tok, launches], "cuda" if world > 1 else "cpu")
     eng.close()
     if world > 1:
         dist.destroy_process_group()

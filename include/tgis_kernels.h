@@ -41,6 +41,8 @@ int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v
 int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
                    void* seen_bitmap_dev, void* out_host);
 const char* tgis_k_last_error(void);
+/* debug builds only (-DTGIS_GEMM_TIMELINE): %globaltimer stamps of CTA 0 and CTA grid/2, [4][16] u64; else -2 */
+int tgis_k_gemm_timeline(uint64_t* out64);
 int tgis_k_sizeof_sample_row(void);
 int tgis_k_sizeof_sample_out(void);
 int tgis_k_kv_block(void);

@@ -129,17 +129,28 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       p_w[g * 32 + lane] = p;
     }
     __syncwarp();
-    // ---- PV: lane = dims [lane*4, lane*4+4)
+    // ---- PV: lane = dims [lane*4, lane*4+4).  All 32 slots are processed unconditionally (p == 0 beyond `valid`, and
+    // cache slots always hold finite values), so the loop has a constant trip count and the loads pipeline.
     const int lchunk = lane >> 1, lhalf = lane & 1;
-    for (int tk = 0; tk < valid; ++tk) {
-      const uint2 vv = *reinterpret_cast<const uint2*>(v_t + tk * (HEAD_DIM * 2) + ((lchunk ^ (tk & 7)) * 16) +
-                                                       lhalf * 8);
-      const float v0 = __uint_as_float(vv.x << 16), v1 = __uint_as_float(vv.x & 0xffff0000u);
-      const float v2 = __uint_as_float(vv.y << 16), v3 = __uint_as_float(vv.y & 0xffff0000u);
+#pragma unroll 2
+    for (int tk0 = 0; tk0 < KV_BLOCK; tk0 += 4) {
+      uint2 vv[4];
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float p = p_w[g * 32 + tk];
-        o_w[g][0] += p * v0; o_w[g][1] += p * v1; o_w[g][2] += p * v2; o_w[g][3] += p * v3;
+      for (int j = 0; j < 4; ++j)
+        vv[j] = *reinterpret_cast<const uint2*>(v_t + (tk0 + j) * (HEAD_DIM * 2) + ((lchunk ^ ((tk0 + j) & 7)) * 16) +
+                                                lhalf * 8);
+      float4 pp[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) pp[g] = *reinterpret_cast<const float4*>(p_w + g * 32 + tk0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v0 = __uint_as_float(vv[j].x << 16), v1 = __uint_as_float(vv[j].x & 0xffff0000u);
+        const float v2 = __uint_as_float(vv[j].y << 16), v3 = __uint_as_float(vv[j].y & 0xffff0000u);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float p = j == 0 ? pp[g].x : j == 1 ? pp[g].y : j == 2 ? pp[g].z : pp[g].w;
+          o_w[g][0] += p * v0; o_w[g][1] += p * v1; o_w[g][2] += p * v2; o_w[g][3] += p * v3;
+        }
       }
     }
   }

@@ -64,6 +64,22 @@ __device__ __forceinline__ int unit_owner(long long p, long long total, int ncta
   return (int)(((p + 1) * ncta - 1) / total);
 }
 
+#ifdef TGIS_GEMM_TIMELINE
+__device__ unsigned long long g_gemm_timeline[4][16];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL(slot)                                                                            \
+  do {                                                                                      \
+    if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && (slot) < 16)                    \
+      g_gemm_timeline[blockIdx.x == 0 ? 0 : 1][slot] = gtimer();                            \
+  } while (0)
+#else
+#define TL(slot) do {} while (0)
+#endif
+
 template <int BT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
@@ -87,6 +103,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   int* flag_smem = reinterpret_cast<int*>(tmem_base_smem + 1);
 
   const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) TL(0);  // kernel entry
   const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   const int t_tiles = (T + BT - 1) / BT;
   const int KB = (K + GEMM_BK - 1) / GEMM_BK;
@@ -117,6 +134,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
   griddep_launch();  // PDL: the next kernel may start its prologue now
+  if (threadIdx.x == 0) TL(1);  // setup done (barriers, TMEM)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -143,7 +161,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         issue_w(w_tile, w_kb, i);
         if (++w_kb == KB) { w_kb = 0; ++w_tile; }
       }
+      TL(2);           // weight prefetch issued
       griddep_wait();  // activations (and everything the epilogue will touch) are now final
+      TL(3);           // dependency wait returned
       int stage = 0;
       uint32_t phase = 0;
       int x_tile = tile0, x_kb = kb0;
@@ -162,6 +182,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           phase ^= 1;
         }
       }
+      TL(4);  // last TMA issued
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -217,6 +238,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       const bool partial = (kb0 > 0) || (kb1 < KB);
       mbar_wait(&tmem_full[acc], (acc_bits >> acc) & 1);
       tc_fence_after();
+      if (ep_tid == 0) TL(5);  // accumulator ready (all MMAs of the unit retired)
       const uint32_t taddr = tmem_base + acc * BT + ((uint32_t)(sub * 32) << 16);
       float* my_ws = ws + ((size_t)(cta * 2 + slot) * BT) * GEMM_BN;
 #pragma unroll 1
@@ -248,6 +270,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       acc_bits ^= (1u << acc);
       acc ^= 1;
 
+      if (ep_tid == 0) TL(6);  // TMEM drained, partial/direct stores issued
       if (partial) {
         // stream-K fix-up: last arriver reduces all partials of this tile in CTA order (deterministic)
         // publish: CTA-wide barrier, then ONE acq_rel atomic (cumulative over the barrier) instead of membar.gl
@@ -261,44 +284,71 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           *flag_smem = (old == (c_last - c_first)) ? 1 : 0;
         }
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (ep_tid == 0) TL(7);  // arrival atomic returned
         const int is_last = *flag_smem;
         if (is_last) {
-          // Ordered (CTA-rank) reduction with many loads in flight: contributors are walked in groups of FIX_C, tokens
-          // in groups of FIX_T, all FIX_C*FIX_T L2 loads of a group are issued before the first add.
-          constexpr int FIX_C = 4, FIX_T = 8;
-          for (int t0 = 0; t0 < t_valid; t0 += FIX_T) {
-            float acc[FIX_T];
+          // Ordered (CTA-rank) reduction, one L2 round trip for the common case: thread -> 4 consecutive rows
+          // (one 16-B load per contributor and token), tokens t == ep_tid/32 (mod 4); all FIX_T x FIX_C loads of a
+          // batch are issued before the first add.  Sum order per element is contributor rank order -> deterministic.
+          constexpr int FIX_C = 3, FIX_T = 8;
+          const int r4 = (ep_tid & 31) * 4;   // first of this thread's 4 rows
+          const int tq = ep_tid >> 5;         // token phase 0..3
+          const int n4 = n_tile * GEMM_BN + r4;
+          for (int tb = tq; tb < t_valid; tb += 4 * FIX_T) {
+            float4 acc[FIX_T];
 #pragma unroll
-            for (int j = 0; j < FIX_T; ++j) acc[j] = 0.f;
+            for (int j = 0; j < FIX_T; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int c0g = c_first; c0g <= c_last; c0g += FIX_C) {
-              float v[FIX_C][FIX_T];
+              float4 v[FIX_C][FIX_T];
 #pragma unroll
               for (int ci = 0; ci < FIX_C; ++ci) {
                 const int c = c0g + ci;
                 const bool cv = c <= c_last;
                 const long long cb = cv ? (total * c) / ncta : 0;
                 const int cslot = ((int)(cb / KB) == tile) ? 0 : 1;
-                const float* p = ws + ((size_t)((cv ? c : c_first) * 2 + cslot) * BT + t0) * GEMM_BN + row;
+                const float* p = ws + ((size_t)((cv ? c : c_first) * 2 + cslot) * BT) * GEMM_BN + r4;
 #pragma unroll
-                for (int j = 0; j < FIX_T; ++j)
-                  v[ci][j] = (cv && t0 + j < t_valid) ? __ldcg(p + (size_t)j * GEMM_BN) : 0.f;
+                for (int j = 0; j < FIX_T; ++j) {
+                  const int t = tb + 4 * j;
+                  v[ci][j] = (cv && t < t_valid) ? __ldcg(reinterpret_cast<const float4*>(p + (size_t)t * GEMM_BN))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
               }
 #pragma unroll
               for (int ci = 0; ci < FIX_C; ++ci)
 #pragma unroll
-                for (int j = 0; j < FIX_T; ++j) acc[j] += v[ci][j];
-            }
-            if (n < N) {
-#pragma unroll
-              for (int j = 0; j < FIX_T; ++j)
-                if (t0 + j < t_valid) {
-                  const size_t o = (size_t)(t_base + t0 + j) * ldy + n;
-                  if (out_f32) Yf[o] = acc[j];
-                  else Y[o] = __float2bfloat16_rn(acc[j]);
+                for (int j = 0; j < FIX_T; ++j) {
+                  acc[j].x += v[ci][j].x; acc[j].y += v[ci][j].y; acc[j].z += v[ci][j].z; acc[j].w += v[ci][j].w;
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < FIX_T; ++j) {
+              const int t = tb + 4 * j;
+              if (t < t_valid) {
+                const size_t o = (size_t)(t_base + t) * ldy + n4;
+                const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+                if (n4 + 3 < N && (ldy & 3) == 0) {
+                  if (out_f32) {
+                    *reinterpret_cast<float4*>(Yf + o) = acc[j];
+                  } else {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(av[0], av[1]), hi = __floats2bfloat162_rn(av[2], av[3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(Y + o) = pk;
+                  }
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (n4 + e < N) {
+                      if (out_f32) Yf[o + e] = av[e];
+                      else Y[o + e] = __float2bfloat16_rn(av[e]);
+                    }
+                }
+              }
             }
           }
           if (ep_tid == 0) counters[tile] = 0;
+          if (ep_tid == 0) TL(8);  // ordered reduction done (last arriver only)
         }
         asm volatile("bar.sync 1, 128;\n" ::: "memory");  // flag_smem reuse safety
       }
@@ -307,11 +357,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TL(9);  // all roles done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
+
+#ifdef TGIS_GEMM_TIMELINE
+int gemm_timeline_read(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_gemm_timeline, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#else
+int gemm_timeline_read(unsigned long long*) { return -2; }
+#endif
 
 // ----------------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

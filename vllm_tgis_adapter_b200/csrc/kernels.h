@@ -14,6 +14,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols);
 int gemm_pick_bt(int T);
 size_t gemm_workspace_bytes(int num_sms);
+int gemm_timeline_read(unsigned long long* out64);  // debug builds (-DTGIS_GEMM_TIMELINE) only
 // Y: bf16 [T, ldy] (out_f32 = 0) or fp32 [T, ldy] (out_f32 = 1, used for the lm_head logits)
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32 = 0);
