@@ -93,9 +93,13 @@ class NativeEngine:
 
     def __init__(self, model: ModelConfig, *, max_num_seqs: int = 64, max_batched_tokens: int = 2048,
                  kv_cache_bytes: int = 0, gpu_mem_fraction: float = 0.85, device: int = 0, seed: int = 0,
-                 debug_gemm_ref: bool = False, use_cuda_graphs: bool = True):
+                 debug_gemm_ref: bool = False, use_cuda_graphs: bool | None = None):
         self.lib = _lib.load_library()
         self.model = model
+        if use_cuda_graphs is None:   # default on; TGIS_CUDA_GRAPHS=0 turns decode-step graph replay off
+            import os
+
+            use_cuda_graphs = os.environ.get("TGIS_CUDA_GRAPHS", "1") != "0"
         cfg = TgisConfig()
         cfg.abi_version = _lib.ABI_VERSION
         cfg.n_layers, cfg.hidden, cfg.n_q_heads, cfg.n_kv_heads = model.n_layers, model.hidden, model.n_q_heads, model.n_kv_heads
