@@ -336,8 +336,8 @@ def run_ours(args) -> dict | None:
     d2h = (st1.d2h_bytes - st0.d2h_bytes) / args.steps
 
     # ---- roofline leg: profiled short pass (events around every GEMM launch)
-    eng.set_profiling(True)
-    sp_short = make_sampling_params(greedy=True, max_tokens=9, min_tokens=9, eos_token_id=2)
+    eng.set_profiling(2)   # decode steps only: the HBM-bound regime the roofline is quoted for
+    sp_short = make_sampling_params(greedy=True, max_tokens=17, min_tokens=17, eos_token_id=2)
     g0 = eng.status()
     for i, pr in enumerate(prompts):
         eng.add_request(f"p{i}", pr, sp_short)

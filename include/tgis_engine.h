@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TGIS_ABI_VERSION 1
+#define TGIS_ABI_VERSION 2
 #define TGIS_MAX_REQUEST_ID 96
 #define TGIS_MAX_TOPN 12 /* reference forces max_logprobs >= 11: tgis_utils/args.py:214-216 */
 #define TGIS_MAX_STOP_TOKEN_IDS 8
@@ -59,11 +59,17 @@ typedef struct tgis_config {
   int64_t kv_cache_bytes;     /* 0 = size from gpu_mem_fraction */
   float gpu_mem_fraction;     /* fraction of free HBM the KV cache may take when kv_cache_bytes == 0 */
   int32_t device;             /* CUDA device ordinal */
-  int32_t tp_size;            /* tensor-parallel world (1 = single GPU) */
+  int32_t tp_size;            /* tensor-parallel world (1 = single GPU); heads, ffn and vocab must divide */
   int32_t tp_rank;
   int32_t use_cuda_graphs;    /* capture decode steps into CUDA graphs */
   int32_t debug_gemm_ref;     /* debug only: route GEMMs through the SIMT cross-check kernel */
   uint64_t seed;              /* engine RNG for unseeded sampling requests */
+  /* tensor parallelism (tp_size > 1): one process per GPU on one node.  Column-parallel q/k/v/gate/up, row-parallel
+   * o/down with an NCCL all-reduce, vocab-parallel lm_head with an all-gather; rank 0 schedules and samples, the
+   * other ranks run tgis_engine_worker_run().  nccl_id comes from tgis_nccl_unique_id() on rank 0 (distributed by
+   * the host, e.g. torch.distributed); shm_name names the POSIX shm segment that carries the per-step plan. */
+  uint8_t nccl_id[128];
+  char shm_name[64];
 } tgis_config;
 
 /* What the adapter's proto->SamplingParams mapping (grpc_server.py:508-628) hands to the engine. */
@@ -151,7 +157,12 @@ int tgis_engine_abort(tgis_engine* e, const char* request_id);
 /* Blocks up to timeout_ms for at least one record; returns the number written to out[0..cap) (>= 0) or <0 on error. */
 int tgis_engine_poll(tgis_engine* e, tgis_step_output* out, int32_t cap, int32_t timeout_ms);
 int tgis_engine_status(tgis_engine* e, tgis_status* out);
-/* on != 0: bracket every GEMM launch with CUDA events (costs a little host time; used by bench.py's roofline leg) */
+/* tensor-parallel plumbing (reference seam: tgis_utils/args.py:201-213 --num-gpus/--num-shard -> tensor_parallel_size) */
+int tgis_nccl_unique_id(uint8_t out[128]);
+/* ranks > 0: blocks, executing rank 0's step plans on this rank's shard, until rank 0 shuts down; 0 on clean exit */
+int tgis_engine_worker_run(tgis_engine* e);
+/* on != 0: bracket every GEMM launch with CUDA events (costs a little host time; used by bench.py's roofline leg);
+ * on == 2: only in pure-decode steps */
 int tgis_engine_set_profiling(tgis_engine* e, int32_t on);
 int tgis_engine_max_model_len(tgis_engine* e);
 int tgis_engine_shutdown(tgis_engine* e);

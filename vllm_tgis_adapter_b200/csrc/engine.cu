@@ -26,8 +26,16 @@
 #include <unordered_map>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <nccl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include "../../include/tgis_engine.h"
 #include "kernels.h"
+#include "launch.cuh"
+#include "ptx.cuh"
 
 namespace {
 
@@ -45,6 +53,12 @@ double now_s() {
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
+#define NK(expr)                                                                                        \
+  do {                                                                                                  \
+    ncclResult_t _r = (expr);                                                                           \
+    if (_r != ncclSuccess)                                                                              \
+      throw CudaError(std::string(#expr) + " failed: " + ncclGetErrorString(_r));                       \
+  } while (0)
 #define CK(expr)                                                                                        \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \
@@ -95,6 +109,39 @@ struct LayerW {
   CUtensorMap m_qkv, m_o, m_gu, m_d;
 };
 
+// Tensor-parallel step plan, shared by POSIX shm between the ranks of one node: rank 0 (scheduler) publishes the
+// packed staging buffer + launch header of every step; workers spin on `seq`, copy, acknowledge and launch the same
+// kernel sequence on their shard.  (The data path itself only exchanges through NCCL.)
+struct StepHeader {
+  int32_t T, n_dec, n_tiles, R, max_dec_kv, S;
+  uint64_t copy_bytes;
+};
+struct ShmCtl {
+  std::atomic<uint64_t> seq;
+  std::atomic<uint32_t> shutdown;
+  uint32_t pad;
+  std::atomic<uint64_t> ack[16];
+  StepHeader hdr;
+  // followed by stage bytes (256-B aligned)
+};
+constexpr size_t SHM_STAGE_OFF = 1024;
+
+__global__ void gather_relayout_kernel(const float* __restrict__ gathered, float* __restrict__ out, int R, int Vl,
+                                       int tp) {
+  griddep_launch();
+  griddep_wait();
+  // gathered: [tp][R][Vl] -> out: [R][tp*Vl]
+  const size_t total = (size_t)tp * R * Vl / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int rk = (int)(e / ((size_t)R * Vl));
+    const size_t rem = e % ((size_t)R * Vl);
+    const int r = (int)(rem / Vl), v = (int)(rem % Vl);
+    *reinterpret_cast<float4*>(out + (size_t)r * tp * Vl + (size_t)rk * Vl + v) =
+        *reinterpret_cast<const float4*>(gathered + e);
+  }
+}
+
 constexpr int N_BT = 5;
 const int BT_VALUES[N_BT] = {16, 32, 64, 128, 256};
 int bt_index(int T) {
@@ -112,6 +159,15 @@ struct tgis_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int q_dim = 0, qkv_dim = 0, bt_stride = 0, max_splits_cap = 0, bitmap_words = 0;
+  // tensor parallelism: local (per-rank) head / ffn / vocab-shard sizes
+  int tp = 1, rank = 0, nq = 0, nkv = 0, Fl = 0, Vl = 0;
+  ncclComm_t comm = nullptr;
+  ShmCtl* shm = nullptr;
+  size_t shm_bytes = 0;
+  bool shm_owner = false;
+  std::string shm_name;
+  uint64_t plan_seq = 0;
+  DevBuf<float> logits_shard, logits_gather;
   int T_max = 0, S_max = 0, tiles_max = 0;
 
   // weights
@@ -160,6 +216,7 @@ struct tgis_engine {
   long long decode_steps = 0, decode_tokens = 0, h2d_bytes = 0, d2h_bytes = 0;
   // optional per-GEMM timing (tgis_engine_set_profiling): CUDA events around every GEMM launch of a step
   bool profiling = false;
+  bool prof_decode_only = false, step_is_decode = false;
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
   std::vector<double> prof_bytes;  // algorithmic bytes of the GEMM between events 2i and 2i+1
@@ -173,6 +230,12 @@ struct tgis_engine {
   ~tgis_engine() {
     if (h_stage) cudaFreeHost(h_stage);
     if (h_samp_out) cudaFreeHost(h_samp_out);
+    if (shm) {
+      if (rank == 0) shm->shutdown.store(1, std::memory_order_release);
+      munmap(shm, shm_bytes);
+      if (shm_owner) shm_unlink(shm_name.c_str());
+    }
+    if (comm) ncclCommDestroy(comm);
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (cudaEvent_t ev : prof_events) cudaEventDestroy(ev);
     if (ev0) cudaEventDestroy(ev0);
@@ -192,8 +255,14 @@ struct tgis_engine {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
-    q_dim = c.n_q_heads * HEAD_DIM;
-    qkv_dim = (c.n_q_heads + 2 * c.n_kv_heads) * HEAD_DIM;
+    tp = c.tp_size > 1 ? c.tp_size : 1;
+    rank = tp > 1 ? c.tp_rank : 0;
+    nq = c.n_q_heads / tp;
+    nkv = c.n_kv_heads / tp;
+    Fl = c.ffn / tp;
+    Vl = c.vocab / tp;
+    q_dim = nq * HEAD_DIM;
+    qkv_dim = (nq + 2 * nkv) * HEAD_DIM;
     bt_stride = (c.max_model_len + KV_BLOCK - 1) / KV_BLOCK;
     max_splits_cap = (c.max_model_len + DECODE_SPLIT - 1) / DECODE_SPLIT;
     bitmap_words = (c.vocab + 31) / 32;
@@ -205,7 +274,7 @@ struct tgis_engine {
     rng.seed(c.seed ? c.seed : 0x5DEECE66Dull);
 
     // ---- weights: one arena
-    const size_t H = c.hidden, F = c.ffn, V = c.vocab, L = c.n_layers;
+    const size_t H = c.hidden, F = Fl, V = c.vocab, L = c.n_layers;  // F: this rank's ffn shard
     const size_t per_layer = (size_t)qkv_dim * H + H * q_dim + 2 * F * H + H * F + 2 * H;
     const size_t total = V * H /*embed*/ + V * H /*lm_head*/ + H /*norm*/ + (size_t)c.max_model_len * HEAD_DIM +
                          L * per_layer + 64 * (6 * L + 8);
@@ -241,14 +310,18 @@ struct tgis_engine {
     act.alloc(T_alloc * F);
     last_hidden.alloc(S_alloc * H);
     logits.alloc((size_t)S_max * V);
+    if (tp > 1) {
+      logits_shard.alloc((size_t)S_max * Vl);
+      logits_gather.alloc((size_t)tp * S_max * Vl);
+    }
     xn.zero(); attn_out.zero(); act.zero(); last_hidden.zero();
     gemm_ws.alloc(gemm_workspace_bytes(num_sms) / sizeof(float));
     gemm_counters.alloc(1 << 16);
     gemm_counters.zero();
     const int G = c.n_q_heads / c.n_kv_heads;
-    part_o.alloc((size_t)S_max * c.n_kv_heads * max_splits_cap * G * HEAD_DIM);
-    part_ml.alloc((size_t)S_max * c.n_kv_heads * max_splits_cap * G * 2);
-    dec_counters.alloc((size_t)S_max * c.n_kv_heads);
+    part_o.alloc((size_t)S_max * nkv * max_splits_cap * G * HEAD_DIM);
+    part_ml.alloc((size_t)S_max * nkv * max_splits_cap * G * 2);
+    dec_counters.alloc((size_t)S_max * nkv);
     dec_counters.zero();
     samp_scratch.alloc((size_t)S_max * V);
     seen_bitmap.alloc((size_t)S_max * bitmap_words);
@@ -290,7 +363,7 @@ struct tgis_engine {
       wmap(&l.m_gu, l.wgu, 2 * F, H);
       wmap(&l.m_d, l.wd, H, F);
     }
-    wmap(&m_lm, lm_head, V, H);
+    wmap(&m_lm, lm_head, Vl, H);  // this rank's vocab shard (== V when tp == 1)
     for (int i = 0; i < N_BT; ++i) {
       const int bt = BT_VALUES[i];
       auto xmap = [&](CUtensorMap* m, const bf16* x, size_t rows, size_t cols) {
@@ -304,7 +377,7 @@ struct tgis_engine {
     }
 
     // ---- KV cache
-    const size_t block_elems = (size_t)c.n_kv_heads * KV_BLOCK * HEAD_DIM;  // per layer, per K or V
+    const size_t block_elems = (size_t)nkv * KV_BLOCK * HEAD_DIM;  // per layer, per K or V (this rank's kv heads)
     size_t kv_bytes = c.kv_cache_bytes;
     if (kv_bytes == 0) {
       size_t free_b = 0, total_b = 0;
@@ -329,7 +402,75 @@ struct tgis_engine {
     for (int i = 0; i < S_max; ++i) free_slots[i] = S_max - 1 - i;
     CK(cudaStreamSynchronize(stream));
     CK(cudaDeviceSynchronize());
+    if (tp > 1) init_tp();
     ready = true;
+  }
+
+  void init_tp() {
+    ncclUniqueId id;
+    static_assert(sizeof(id.internal) == 128, "nccl id size");
+    memcpy(id.internal, cfg.nccl_id, 128);
+    NK(ncclCommInitRank(&comm, tp, id, rank));
+    shm_name = cfg.shm_name[0] ? std::string(cfg.shm_name) : std::string("/tgis_tp_plan");
+    shm_bytes = SHM_STAGE_OFF + stage_bytes;
+    int fd = -1;
+    if (rank == 0) {
+      shm_unlink(shm_name.c_str());
+      fd = shm_open(shm_name.c_str(), O_CREAT | O_RDWR, 0600);
+      if (fd < 0 || ftruncate(fd, (off_t)shm_bytes) != 0) throw CudaError("shm_open/ftruncate failed for " + shm_name);
+      shm_owner = true;
+    } else {
+      for (int i = 0; i < 6000 && fd < 0; ++i) {
+        fd = shm_open(shm_name.c_str(), O_RDWR, 0600);
+        if (fd >= 0) {
+          struct stat st;
+          if (fstat(fd, &st) != 0 || (size_t)st.st_size < shm_bytes) { close(fd); fd = -1; }
+        }
+        if (fd < 0) usleep(10000);
+      }
+      if (fd < 0) throw CudaError("worker could not open the TP plan shm " + shm_name);
+    }
+    void* m = mmap(nullptr, shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) throw CudaError("mmap of TP plan failed");
+    shm = reinterpret_cast<ShmCtl*>(m);
+    if (rank == 0) {
+      shm->seq.store(0);
+      shm->shutdown.store(0);
+      for (auto& a : shm->ack) a.store(0);
+    }
+    // first collective doubles as a start-up barrier (and creates NCCL's channels outside the timed path)
+    NK(ncclAllReduce(tmp.p, tmp.p, 1024, ncclBfloat16, ncclSum, comm, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+
+  void publish_plan(const StepHeader& h) {  // rank 0
+    for (int r = 1; r < tp; ++r)
+      while (shm->ack[r].load(std::memory_order_acquire) != plan_seq) {
+        if (stop_flag) return;
+      }
+    memcpy(reinterpret_cast<uint8_t*>(shm) + SHM_STAGE_OFF, h_stage, h.copy_bytes);
+    shm->hdr = h;
+    shm->seq.store(++plan_seq, std::memory_order_release);
+  }
+
+  // worker ranks: follow rank 0's step plans until shutdown
+  int worker_loop() {
+    CK(cudaSetDevice(cfg.device));
+    uint64_t seen = 0;
+    for (;;) {
+      uint64_t s;
+      while ((s = shm->seq.load(std::memory_order_acquire)) == seen) {
+        if (shm->shutdown.load(std::memory_order_acquire)) return 0;
+      }
+      const StepHeader h = shm->hdr;
+      memcpy(h_stage, reinterpret_cast<uint8_t*>(shm) + SHM_STAGE_OFF, h.copy_bytes);
+      seen = s;
+      shm->ack[rank].store(s, std::memory_order_release);
+      launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv);
+      CK(cudaStreamSynchronize(stream));
+      ++n_steps;
+    }
   }
 
   void default_rope_table() {
@@ -346,15 +487,28 @@ struct tgis_engine {
     CK(cudaMemcpy(cos_sin, tab.data(), tab.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   }
 
+  // Copies the FULL (unsharded) tensor's shard for this rank into the arena: row blocks for column-parallel layers
+  // (q/k/v/gate/up, lm_head), column blocks for row-parallel layers (o, down), everything else replicated.
   int load_weight(const std::string& name, const void* ptr, int64_t rows, int64_t cols) {
     const tgis_config& c = cfg;
     const int64_t H = c.hidden, F = c.ffn, V = c.vocab;
+    const uint8_t* src = static_cast<const uint8_t*>(ptr);
     bf16* dst = nullptr;
-    int64_t er = 0, ec = 0;
-    if (name == "model.embed_tokens.weight") { dst = embed; er = V; ec = H; }
-    else if (name == "lm_head.weight") { dst = lm_head; er = V; ec = H; lm_head_loaded = true; }
-    else if (name == "model.norm.weight") { dst = final_norm; er = H; ec = 1; }
-    else if (name == "tgis.rope_cos_sin") { dst = cos_sin; er = c.max_model_len; ec = HEAD_DIM; cos_sin_loaded = true; }
+    int64_t er = 0, ec = 0;             // expected full shape
+    int64_t r0 = 0, nr = 0, c0 = 0, nc = 0;  // shard = rows [r0, r0+nr) x cols [c0, c0+nc)
+    auto rows_shard = [&](bf16* d, int64_t full_rows, int64_t full_cols, int64_t per_rank) {
+      dst = d; er = full_rows; ec = full_cols; r0 = rank * per_rank; nr = per_rank; c0 = 0; nc = full_cols;
+    };
+    auto cols_shard = [&](bf16* d, int64_t full_rows, int64_t full_cols, int64_t per_rank) {
+      dst = d; er = full_rows; ec = full_cols; r0 = 0; nr = full_rows; c0 = rank * per_rank; nc = per_rank;
+    };
+    auto full = [&](bf16* d, int64_t full_rows, int64_t full_cols) {
+      dst = d; er = full_rows; ec = full_cols; r0 = 0; nr = full_rows; c0 = 0; nc = full_cols;
+    };
+    if (name == "model.embed_tokens.weight") full(embed, V, H);
+    else if (name == "lm_head.weight") { rows_shard(lm_head, V, H, Vl); lm_head_loaded = true; }
+    else if (name == "model.norm.weight") full(final_norm, H, 1);
+    else if (name == "tgis.rope_cos_sin") { full(cos_sin, c.max_model_len, HEAD_DIM); cos_sin_loaded = true; }
     else if (name.rfind("model.layers.", 0) == 0) {
       const size_t dot = name.find('.', 13);
       if (dot == std::string::npos) return fail("bad weight name " + name);
@@ -362,37 +516,44 @@ struct tgis_engine {
       if (li < 0 || li >= c.n_layers) return fail("layer index out of range in " + name);
       LayerW& l = layers[li];
       const std::string sub = name.substr(dot + 1);
-      const int64_t kvd = (int64_t)c.n_kv_heads * HEAD_DIM;
-      if (sub == "self_attn.q_proj.weight") { dst = l.wqkv; er = q_dim; ec = H; }
-      else if (sub == "self_attn.k_proj.weight") { dst = l.wqkv + (size_t)q_dim * H; er = kvd; ec = H; }
-      else if (sub == "self_attn.v_proj.weight") { dst = l.wqkv + (size_t)(q_dim + kvd) * H; er = kvd; ec = H; }
-      else if (sub == "self_attn.o_proj.weight") { dst = l.wo; er = H; ec = q_dim; }
-      else if (sub == "mlp.gate_proj.weight") { dst = l.wgu; er = F; ec = H; }
-      else if (sub == "mlp.up_proj.weight") { dst = l.wgu + (size_t)F * H; er = F; ec = H; }
-      else if (sub == "mlp.down_proj.weight") { dst = l.wd; er = H; ec = F; }
-      else if (sub == "input_layernorm.weight") { dst = l.ln1; er = H; ec = 1; }
-      else if (sub == "post_attention_layernorm.weight") { dst = l.ln2; er = H; ec = 1; }
+      const int64_t kvd = (int64_t)nkv * HEAD_DIM;  // local
+      if (sub == "self_attn.q_proj.weight") rows_shard(l.wqkv, (int64_t)c.n_q_heads * HEAD_DIM, H, q_dim);
+      else if (sub == "self_attn.k_proj.weight") rows_shard(l.wqkv + (size_t)q_dim * H, (int64_t)c.n_kv_heads * HEAD_DIM, H, kvd);
+      else if (sub == "self_attn.v_proj.weight") rows_shard(l.wqkv + (size_t)(q_dim + kvd) * H, (int64_t)c.n_kv_heads * HEAD_DIM, H, kvd);
+      else if (sub == "self_attn.o_proj.weight") cols_shard(l.wo, H, (int64_t)c.n_q_heads * HEAD_DIM, q_dim);
+      else if (sub == "mlp.gate_proj.weight") rows_shard(l.wgu, F, H, Fl);
+      else if (sub == "mlp.up_proj.weight") rows_shard(l.wgu + (size_t)Fl * H, F, H, Fl);
+      else if (sub == "mlp.down_proj.weight") cols_shard(l.wd, H, F, Fl);
+      else if (sub == "input_layernorm.weight") full(l.ln1, H, 1);
+      else if (sub == "post_attention_layernorm.weight") full(l.ln2, H, 1);
       else return fail("unknown layer weight " + name);
     } else {
       return fail("unknown weight " + name);
     }
     if (rows * cols != er * ec) return fail("shape mismatch for " + name + ": got " + std::to_string(rows) + "x" +
                                             std::to_string(cols) + " expected " + std::to_string(er) + "x" + std::to_string(ec));
-    cudaError_t e = cudaMemcpy(dst, ptr, (size_t)(er * ec) * sizeof(bf16), cudaMemcpyDefault);
+    cudaError_t e;
+    if (nc == ec) {
+      e = cudaMemcpy(dst, src + (size_t)r0 * ec * sizeof(bf16), (size_t)(nr * ec) * sizeof(bf16), cudaMemcpyDefault);
+    } else {
+      e = cudaMemcpy2D(dst, (size_t)nc * sizeof(bf16), src + (size_t)c0 * sizeof(bf16), (size_t)ec * sizeof(bf16),
+                       (size_t)nc * sizeof(bf16), (size_t)nr, cudaMemcpyDefault);
+    }
     if (e != cudaSuccess) return fail(std::string("cudaMemcpy(weight) failed: ") + cudaGetErrorString(e));
     return 0;
   }
 
   void finalize_weights() {
     if (!lm_head_loaded)  // tie_word_embeddings
-      CK(cudaMemcpy(lm_head, embed, (size_t)cfg.vocab * cfg.hidden * sizeof(bf16), cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(lm_head, embed + (size_t)rank * Vl * cfg.hidden, (size_t)Vl * cfg.hidden * sizeof(bf16),
+                    cudaMemcpyDeviceToDevice));
   }
 
   // ------------------------------------------------------------------------------------------------ device step
   void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, void* Y, int T, int N, int K,
             int out_f32 = 0) {
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (profiling) {
+    if (profiling && (!prof_decode_only || step_is_decode)) {
       while (prof_events.size() < prof_used + 2) {
         cudaEvent_t ev;
         CK(cudaEventCreate(&ev));
@@ -419,21 +580,29 @@ struct tgis_engine {
   template <class T>
   T* ds(size_t off) { return reinterpret_cast<T*>(d_stage.p + off); }
 
+  void all_reduce_tmp(int T) {
+    if (tp > 1) NK(ncclAllReduce(tmp.p, tmp.p, (size_t)T * cfg.hidden, ncclBfloat16, ncclSum, comm, stream));
+  }
+
   // Enqueue one step on `stream`: H2D metadata, layer stack, lm_head + sampler, D2H results.  Reads every per-step
   // quantity from the device staging buffer, so the same sequence can be captured once into a CUDA graph and replayed.
   void launch_step(size_t copy_bytes, int T, int n_dec, int n_tiles, int R, int max_dec_kv) {
     const tgis_config& c = cfg;
-    const int H = c.hidden, F = c.ffn, V = c.vocab;
+    const int H = c.hidden, F = Fl, V = c.vocab;  // F: local ffn shard
     CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
+    step_is_decode = (n_tiles == 0);
 
     const int32_t* d_tok = ds<int32_t>(off_tok);
     const AttnSeq* d_seqs = ds<AttnSeq>(off_seqs);
     const int32_t* d_bt = ds<int32_t>(off_bt);
     const float scale = 1.0f / std::sqrt((float)HEAD_DIM);
 
-    CK(bitmap_set_launch(seen_bitmap.p, bitmap_words, ds<int32_t>(off_tokslot), d_tok, T, stream));
+    if (rank == 0) {
+      CK(bitmap_set_launch(seen_bitmap.p, bitmap_words, ds<int32_t>(off_tokslot), d_tok, T, stream));
+      ++n_launches;
+    }
     CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
-    n_launches += 2;
+    ++n_launches;
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];
       if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
@@ -442,39 +611,53 @@ struct tgis_engine {
       gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H);
       bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
       bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
-      CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, c.n_q_heads,
-                             c.n_kv_heads, stream));
+      CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, nq, nkv,
+                             stream));
       ++n_launches;
       if (n_dec > 0) {
         const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
         CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, d_seqs, /*seq_ids=*/nullptr, n_dec, d_bt, bt_stride,
-                              max_splits, part_o.p, part_ml.p, dec_counters.p, attn_out.p, q_dim, c.n_q_heads,
-                              c.n_kv_heads, scale, stream));
+                              max_splits, part_o.p, part_ml.p, dec_counters.p, attn_out.p, q_dim, nq, nkv, scale,
+                              stream));
         ++n_launches;
       }
       if (n_tiles > 0) {
         CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
-                               n_tiles, d_bt, bt_stride, attn_out.p, q_dim, c.n_q_heads, c.n_kv_heads, scale,
-                               stream));
+                               n_tiles, d_bt, bt_stride, attn_out.p, q_dim, nq, nkv, scale, stream));
         ++n_launches;
       }
       gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim);
+      all_reduce_tmp(T);  // row-parallel partial sums (tp > 1)
       CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
       ++n_launches;
       gemm(xm_xn, l.m_gu, xn.p, l.wgu, gate_up.p, T, 2 * F, H);
       CK(silu_mul_launch(gate_up.p, act.p, T, F, stream));
       ++n_launches;
       gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F);
+      all_reduce_tmp(T);
     }
     if (R > 0) {
       CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
       CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
       n_launches += 2;
-      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, /*out_f32=*/1);
-      CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words, samp_scratch.p,
-                        d_samp_out.p, stream));
-      ++n_launches;
-      CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
+      if (tp == 1) {
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, /*out_f32=*/1);
+      } else {
+        // vocab-parallel lm_head: every rank computes [R, V/tp] fp32, all-gather, re-layout to [R, V]
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, R, Vl, H, /*out_f32=*/1);
+        NK(ncclAllGather(logits_shard.p, logits_gather.p, (size_t)R * Vl, ncclFloat, comm, stream));
+        if (rank == 0) {
+          CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const float*)logits_gather.p,
+                      logits.p, R, Vl, tp));
+          ++n_launches;
+        }
+      }
+      if (rank == 0) {
+        CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words, samp_scratch.p,
+                          d_samp_out.p, stream));
+        ++n_launches;
+        CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
+      }
     }
   }
 
@@ -557,7 +740,8 @@ struct tgis_engine {
     // ---- ship metadata + run the layer stack (one CUDA graph launch for a pure-decode step when enabled)
     const size_t copy_bytes = off_bt + sizeof(int32_t) * (size_t)S * bt_stride;
     CK(cudaEventRecord(ev0, stream));
-    const bool graphable = cfg.use_cuda_graphs && !profiling && n_tiles == 0 && n_dec == S && R == S;
+    if (tp > 1) publish_plan(StepHeader{T, n_dec, n_tiles, R, max_dec_kv, S, (uint64_t)copy_bytes});
+    const bool graphable = cfg.use_cuda_graphs && tp == 1 && !profiling && n_tiles == 0 && n_dec == S && R == S;
     if (graphable) {
       const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
       const uint64_t key = ((uint64_t)S << 16) | (uint64_t)max_splits;
@@ -851,7 +1035,10 @@ int tgis_engine_create(const tgis_config* cfg, tgis_engine** out) {
   if (!(G == 1 || G == 2 || G == 3 || G == 4 || G == 8)) return fail("GQA group size must be 1, 2, 3, 4 or 8");
   if (cfg->hidden % 64 || cfg->ffn % 64 || cfg->vocab % 8) return fail("hidden/ffn must be multiples of 64, vocab of 8");
   if (cfg->hidden > 8192) return fail("hidden > 8192 unsupported");
-  if (cfg->tp_size > 1) return fail("tensor parallelism is not built into this revision (tp_size must be 1)");
+  const int tpv = cfg->tp_size > 1 ? cfg->tp_size : 1;
+  if (tpv > 16 || cfg->tp_rank < 0 || cfg->tp_rank >= tpv) return fail("bad tp_size / tp_rank");
+  if (cfg->n_kv_heads % tpv || cfg->ffn % (64 * tpv) || cfg->vocab % (8 * tpv))
+    return fail("n_kv_heads, ffn/64 and vocab/8 must be divisible by tp_size");
   if (cfg->max_batched_tokens < 16 || cfg->max_num_seqs < 1 || cfg->max_model_len < 2) return fail("bad limits");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -994,9 +1181,31 @@ int tgis_engine_status(tgis_engine* e, tgis_status* out) {
   return 0;
 }
 
+int tgis_nccl_unique_id(uint8_t out[128]) {
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return fail("ncclGetUniqueId failed");
+  memcpy(out, id.internal, 128);
+  return 0;
+}
+
+int tgis_engine_worker_run(tgis_engine* e) {
+  if (!e) return fail("null engine");
+  if (e->tp <= 1 || e->rank == 0) return fail("worker_run is for tensor-parallel ranks > 0");
+  try {
+    e->finalize_weights();
+    e->started = true;
+    return e->worker_loop();
+  } catch (const std::exception& ex) {
+    e->error_msg = ex.what();
+    e->errored = true;
+    return fail(ex.what());
+  }
+}
+
 int tgis_engine_set_profiling(tgis_engine* e, int32_t on) {
   if (!e) return fail("null engine");
   e->profiling = on != 0;
+  e->prof_decode_only = on == 2;  // 2: time only the GEMMs of pure-decode steps (the HBM-bound regime)
   return 0;
 }
 
@@ -1005,6 +1214,7 @@ int tgis_engine_max_model_len(tgis_engine* e) { return e ? e->cfg.max_model_len 
 int tgis_engine_shutdown(tgis_engine* e) {
   if (!e) return fail("null engine");
   e->stop_flag = true;
+  if (e->shm && e->rank == 0) e->shm->shutdown.store(1, std::memory_order_release);
   e->cv_in.notify_all();
   if (e->th.joinable()) e->th.join();
   e->cv_out.notify_all();

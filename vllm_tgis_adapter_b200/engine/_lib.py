@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_REQUEST_ID = 96
 MAX_TOPN = 12
 MAX_STOP_TOKEN_IDS = 8
@@ -26,6 +26,7 @@ class TgisConfig(C.Structure):
         ("max_num_seqs", C.c_int32), ("max_batched_tokens", C.c_int32), ("kv_cache_bytes", C.c_int64),
         ("gpu_mem_fraction", C.c_float), ("device", C.c_int32), ("tp_size", C.c_int32), ("tp_rank", C.c_int32),
         ("use_cuda_graphs", C.c_int32), ("debug_gemm_ref", C.c_int32), ("seed", C.c_uint64),
+        ("nccl_id", C.c_uint8 * 128), ("shm_name", C.c_char * 64),
     ]
 
 
@@ -65,7 +66,7 @@ class TgisStatus(C.Structure):
 ENGINE_SYMBOLS = [
     "tgis_last_error", "tgis_abi_version", "tgis_engine_create", "tgis_engine_load_weight", "tgis_engine_start",
     "tgis_engine_add_request", "tgis_engine_abort", "tgis_engine_poll", "tgis_engine_status",
-    "tgis_engine_max_model_len", "tgis_engine_set_profiling", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
+    "tgis_engine_max_model_len", "tgis_engine_set_profiling", "tgis_nccl_unique_id", "tgis_engine_worker_run", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
 ]
 KERNEL_SYMBOLS = [
     "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_attention",
@@ -104,6 +105,8 @@ def load_library() -> C.CDLL:
     lib.tgis_engine_status.argtypes = [vp, C.POINTER(TgisStatus)]
     lib.tgis_engine_max_model_len.argtypes = [vp]
     lib.tgis_engine_set_profiling.argtypes = [vp, i32]
+    lib.tgis_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8 * 128)]
+    lib.tgis_engine_worker_run.argtypes = [vp]
     lib.tgis_engine_shutdown.argtypes = [vp]
     lib.tgis_engine_destroy.argtypes = [vp]
     lib.tgis_engine_destroy.restype = None

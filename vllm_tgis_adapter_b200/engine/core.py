@@ -93,7 +93,8 @@ class NativeEngine:
 
     def __init__(self, model: ModelConfig, *, max_num_seqs: int = 64, max_batched_tokens: int = 2048,
                  kv_cache_bytes: int = 0, gpu_mem_fraction: float = 0.85, device: int = 0, seed: int = 0,
-                 debug_gemm_ref: bool = False, use_cuda_graphs: bool | None = None):
+                 debug_gemm_ref: bool = False, use_cuda_graphs: bool | None = None, tp_size: int = 1, tp_rank: int = 0,
+                 nccl_id: bytes | None = None, shm_name: str = ""):
         self.lib = _lib.load_library()
         self.model = model
         if use_cuda_graphs is None:   # default on; TGIS_CUDA_GRAPHS=0 turns decode-step graph replay off
@@ -107,7 +108,12 @@ class NativeEngine:
         cfg.rope_theta, cfg.rms_eps, cfg.max_model_len = model.rope_theta, model.rms_eps, model.max_model_len
         cfg.max_num_seqs, cfg.max_batched_tokens = max_num_seqs, max_batched_tokens
         cfg.kv_cache_bytes, cfg.gpu_mem_fraction = kv_cache_bytes, gpu_mem_fraction
-        cfg.device, cfg.tp_size, cfg.tp_rank = device, 1, 0
+        cfg.device, cfg.tp_size, cfg.tp_rank = device, tp_size, tp_rank
+        if tp_size > 1:
+            if nccl_id is None or len(nccl_id) != 128:
+                raise EngineError("tensor parallelism needs the 128-byte NCCL unique id of rank 0")
+            C.memmove(cfg.nccl_id, nccl_id, 128)
+            cfg.shm_name = shm_name.encode()
         cfg.use_cuda_graphs, cfg.debug_gemm_ref, cfg.seed = int(use_cuda_graphs), 1 if debug_gemm_ref else 0, seed
         self._h = C.c_void_p()
         if self.lib.tgis_engine_create(C.byref(cfg), C.byref(self._h)) != 0:
@@ -172,8 +178,22 @@ class NativeEngine:
         self.lib.tgis_engine_status(self._h, C.byref(st))
         return st
 
-    def set_profiling(self, on: bool) -> None:
-        self.lib.tgis_engine_set_profiling(self._h, 1 if on else 0)
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        lib = _lib.load_library()
+        if lib.tgis_nccl_unique_id(C.byref(buf)) != 0:
+            raise EngineError(_lib.last_error(lib))
+        return bytes(buf)
+
+    def worker_run(self) -> None:
+        """Tensor-parallel ranks > 0: execute rank 0's step plans until it shuts down (blocking)."""
+        if self.lib.tgis_engine_worker_run(self._h) != 0:
+            raise EngineError(f"worker_run failed: {_lib.last_error(self.lib)}")
+
+    def set_profiling(self, on: bool | int) -> None:
+        """True/1: time every GEMM launch; 2: only those of pure-decode steps."""
+        self.lib.tgis_engine_set_profiling(self._h, int(on))
 
     @property
     def max_model_len(self) -> int:
