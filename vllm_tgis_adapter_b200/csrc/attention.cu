@@ -19,7 +19,7 @@
 
 namespace tgis {
 
-constexpr int DEC_TOK = 128;                 // tokens per split (4 KV blocks)
+constexpr int DEC_TOK = DECODE_SPLIT;        // tokens per split (2 KV blocks: 36 KB smem/CTA -> 6 CTAs/SM in flight)
 constexpr int DEC_BLOCKS = DEC_TOK / KV_BLOCK;
 constexpr int TILE_BYTES = KV_BLOCK * HEAD_DIM * 2;  // 8192
 static_assert(DEC_TOK == DECODE_SPLIT, "split size mismatch");
@@ -66,7 +66,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
 
   // Each warp owns one KV block and its mbarrier: lane 0 initialises the barrier and issues the two TMA bulk copies
   // of its block, so the 4 block-table look-ups and 8 copies are issued in parallel with no CTA-wide barrier.
-  if (lane == 0) {
+  if (lane == 0 && warp < DEC_BLOCKS) {
     mbar_init(&bars[warp], 1);
     fence_barrier_init();
     if (warp < n_blk) {
@@ -85,24 +85,31 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   }
   __syncthreads();
 
-  float m_w[G], l_w[G], o_w[G][4];
+  // Two warps share every KV block and split the group's G query heads between them (warp w and w+DEC_BLOCKS):
+  // both wait on the block's mbarrier, each runs QK^T / softmax / PV for its heads only.
+  constexpr int GH = (G + 1) / 2;          // heads per warp (first warp of the pair takes the larger half)
+  const int blk = warp % DEC_BLOCKS, half = warp / DEC_BLOCKS;
+  const int g0 = half * GH;                // first head of this warp
+  const int gh = half == 0 ? GH : G - GH;  // number of heads of this warp (0 possible when G == 1)
+  float m_w[GH], l_w[GH], o_w[GH][4];
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
+  for (int g = 0; g < GH; ++g) {
     m_w[g] = -INFINITY;
     l_w[g] = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) o_w[g][e] = 0.f;
   }
 
-  if (warp < n_blk) {
-    const int valid = min(KV_BLOCK, n_tok - warp * KV_BLOCK);
-    mbar_wait(&bars[warp], 0);
-    const uint8_t* k_t = kv_s + warp * 2 * TILE_BYTES;
+  if (blk < n_blk && gh > 0) {
+    const int valid = min(KV_BLOCK, n_tok - blk * KV_BLOCK);
+    mbar_wait(&bars[blk], 0);
+    const uint8_t* k_t = kv_s + blk * 2 * TILE_BYTES;
     const uint8_t* v_t = k_t + TILE_BYTES;
+    const float* q_w = q_s + g0 * HEAD_DIM;
     // ---- scores: lane = token
-    float s[G];
+    float s[GH];
 #pragma unroll
-    for (int g = 0; g < G; ++g) s[g] = 0.f;
+    for (int g = 0; g < GH; ++g) s[g] = 0.f;
 #pragma unroll 4
     for (int c = 0; c < HEAD_DIM / 8; ++c) {
       const uint4 kk = *reinterpret_cast<const uint4*>(k_t + (c * KV_BLOCK + lane) * 16);
@@ -112,19 +119,21 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       kf[4] = __uint_as_float(kk.z << 16); kf[5] = __uint_as_float(kk.z & 0xffff0000u);
       kf[6] = __uint_as_float(kk.w << 16); kf[7] = __uint_as_float(kk.w & 0xffff0000u);
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float4 qa = *reinterpret_cast<const float4*>(q_s + g * HEAD_DIM + c * 8);
-        const float4 qb = *reinterpret_cast<const float4*>(q_s + g * HEAD_DIM + c * 8 + 4);
-        s[g] += qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] +
-                qb.z * kf[6] + qb.w * kf[7];
+      for (int g = 0; g < GH; ++g) {
+        if (g < gh) {
+          const float4 qa = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8);
+          const float4 qb = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8 + 4);
+          s[g] += qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] +
+                  qb.z * kf[6] + qb.w * kf[7];
+        }
       }
     }
-    float* p_w = p_s + warp * G * 32;
+    float* p_w = p_s + warp * GH * 32;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const float sv = (lane < valid) ? s[g] * scale : -INFINITY;
+    for (int g = 0; g < GH; ++g) {
+      const float sv = (lane < valid && g < gh) ? s[g] * scale : -INFINITY;
       m_w[g] = warp_max(sv);
-      const float p = (lane < valid) ? __expf(sv - m_w[g]) : 0.f;
+      const float p = (lane < valid && g < gh) ? __expf(sv - m_w[g]) : 0.f;
       l_w[g] = warp_add(p);
       p_w[g * 32 + lane] = p;
     }
@@ -139,32 +148,35 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       for (int j = 0; j < 4; ++j)
         vv[j] = *reinterpret_cast<const uint2*>(v_t + (tk0 + j) * (HEAD_DIM * 2) + ((lchunk ^ ((tk0 + j) & 7)) * 16) +
                                                 lhalf * 8);
-      float4 pp[G];
+      float4 pp[GH];
 #pragma unroll
-      for (int g = 0; g < G; ++g) pp[g] = *reinterpret_cast<const float4*>(p_w + g * 32 + tk0);
+      for (int g = 0; g < GH; ++g) pp[g] = *reinterpret_cast<const float4*>(p_w + g * 32 + tk0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float v0 = __uint_as_float(vv[j].x << 16), v1 = __uint_as_float(vv[j].x & 0xffff0000u);
         const float v2 = __uint_as_float(vv[j].y << 16), v3 = __uint_as_float(vv[j].y & 0xffff0000u);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
+        for (int g = 0; g < GH; ++g) {
           const float p = j == 0 ? pp[g].x : j == 1 ? pp[g].y : j == 2 ? pp[g].z : pp[g].w;
           o_w[g][0] += p * v0; o_w[g][1] += p * v1; o_w[g][2] += p * v2; o_w[g][3] += p * v3;
         }
       }
     }
   }
-  // ---- combine the (up to) 4 warps of this split.  o_w goes into this warp's own (now dead) K tile.
-  __syncwarp();
+  // ---- combine.  The pair's partial o rows go into the block's K tile, which is dead once BOTH warps of the pair
+  // are past their QK^T loop -> pair barrier (named barrier 1 + blk, 64 threads) before the first write.
+  asm volatile("bar.sync %0, 64;\n" ::"r"(1 + blk) : "memory");
   {
-    float* ow_s = reinterpret_cast<float*>(kv_s + warp * 2 * TILE_BYTES);  // [G][128] <= 4 KiB < 8 KiB
+    float* ow_s = reinterpret_cast<float*>(kv_s + blk * 2 * TILE_BYTES);  // [G][128] floats <= 4 KiB < 8 KiB
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      *reinterpret_cast<float4*>(ow_s + g * HEAD_DIM + lane * 4) =
-          make_float4(o_w[g][0], o_w[g][1], o_w[g][2], o_w[g][3]);
-      if (lane == 0) {
-        ml_s[(warp * G + g) * 2 + 0] = m_w[g];
-        ml_s[(warp * G + g) * 2 + 1] = l_w[g];
+    for (int g = 0; g < GH; ++g) {
+      if (g < gh) {
+        *reinterpret_cast<float4*>(ow_s + (g0 + g) * HEAD_DIM + lane * 4) =
+            make_float4(o_w[g][0], o_w[g][1], o_w[g][2], o_w[g][3]);
+        if (lane == 0) {
+          ml_s[(blk * G + g0 + g) * 2 + 0] = m_w[g];
+          ml_s[(blk * G + g0 + g) * 2 + 1] = l_w[g];
+        }
       }
     }
   }
@@ -213,7 +225,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   // ---- last arriver: merge in split order.  (m, l) of every split are staged in smem by all threads in parallel
   // (the K/V tiles are dead by now), then the o rows are fetched SPB splits at a time so that SPB*G L2 loads are in
   // flight per thread instead of one.
-  float* ml_all = reinterpret_cast<float*>(kv_s + 4 * TILE_BYTES);  // [n_splits][G][2], <= 64*8*2*4 = 4 KiB
+  float* ml_all = reinterpret_cast<float*>(kv_s + TILE_BYTES);  // block 0's dead V tile: [n_splits][G][2] <= 8 KiB
   for (int i = threadIdx.x; i < n_splits * G * 2; i += 128) ml_all[i] = __ldcg(&part_ml[pbase * G * 2 + i]);
   __syncthreads();
   float m_f[G], l_f[G], o_f[G];
