@@ -16,7 +16,8 @@ architecture (BASELINE.json configs[1]: Llama-3-8B bf16, 1xB200, batch 32, 512-i
            which cannot be built offline) timed on the host cores on a bounded sample.
 
 N > 1 (torchrun): data-parallel replicas, one engine per GPU, no data-path collective (requests are independent:
-SURVEY.md §8e (1)); weak scaling.  Tensor parallelism is not in this round.
+SURVEY.md §8e (1)); weak scaling.  (The engine also has tensor parallelism — DESIGN.md §6 — which the 8B config
+does not need: it fits one GPU, so replicas are the faster way to use N GPUs for it.)
 """
 from __future__ import annotations
 

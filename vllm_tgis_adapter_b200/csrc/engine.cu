@@ -217,6 +217,7 @@ struct tgis_engine {
   // optional per-GEMM timing (tgis_engine_set_profiling): CUDA events around every GEMM launch of a step
   bool profiling = false;
   bool prof_decode_only = false, step_is_decode = false;
+  int l2_prefetch_kb = 20;  // k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
   std::vector<double> prof_bytes;  // algorithmic bytes of the GEMM between events 2i and 2i+1
@@ -272,6 +273,7 @@ struct tgis_engine {
     const size_t T_alloc = std::max(T_max, 256), S_alloc = std::max(S_max, 256);
     tiles_max = T_max / 16 + S_max + 1;
     rng.seed(c.seed ? c.seed : 0x5DEECE66Dull);
+    if (const char* e = getenv("TGIS_L2_PREFETCH_KB")) l2_prefetch_kb = atoi(e);
 
     // ---- weights: one arena
     const size_t H = c.hidden, F = Fl, V = c.vocab, L = c.n_layers;  // F: this rank's ffn shard
@@ -550,8 +552,10 @@ struct tgis_engine {
   }
 
   // ------------------------------------------------------------------------------------------------ device step
+  // next_wm / nT,nN,nK describe the GEMM that follows this one in the layer stack: its first weight boxes are
+  // prefetched into L2 by this launch's producer warp (gemm_tcgen05.cu)
   void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, void* Y, int T, int N, int K,
-            int out_f32 = 0) {
+            int out_f32 = 0, const CUtensorMap* next_wm = nullptr, int nT = 0, int nN = 0, int nK = 0) {
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profiling && (!prof_decode_only || step_is_decode)) {
       while (prof_events.size() < prof_used + 2) {
@@ -569,7 +573,10 @@ struct tgis_engine {
     if (cfg.debug_gemm_ref) {
       CK(gemm_bf16_ref_launch(X, K, W, Y, N, T, N, K, stream, out_f32));
     } else {
-      CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, N, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32));
+      GemmNext nx{};
+      if (next_wm && l2_prefetch_kb > 0) nx = gemm_next_desc(nT, nN, nK, num_sms, l2_prefetch_kb);
+      CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, N, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32,
+                          nx.kb_prefetch > 0 ? next_wm : nullptr, nx.kb_prefetch > 0 ? &nx : nullptr));
     }
     if (pe1) CK(cudaEventRecord(pe1, stream));
     ++n_launches;
@@ -608,7 +615,7 @@ struct tgis_engine {
       if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
       else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
       ++n_launches;
-      gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H);
+      gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim);
       bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
       bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
       CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, nq, nkv,
@@ -626,14 +633,15 @@ struct tgis_engine {
                                n_tiles, d_bt, bt_stride, attn_out.p, q_dim, nq, nkv, scale, stream));
         ++n_launches;
       }
-      gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim);
+      gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H);
       all_reduce_tmp(T);  // row-parallel partial sums (tp > 1)
       CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
       ++n_launches;
-      gemm(xm_xn, l.m_gu, xn.p, l.wgu, gate_up.p, T, 2 * F, H);
+      gemm(xm_xn, l.m_gu, xn.p, l.wgu, gate_up.p, T, 2 * F, H, 0, &l.m_d, T, H, F);
       CK(silu_mul_launch(gate_up.p, act.p, T, F, stream));
       ++n_launches;
-      gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F);
+      if (li + 1 < c.n_layers) gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F, 0, &layers[li + 1].m_qkv, T, qkv_dim, H);
+      else gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F, 0, R > 0 ? &m_lm : nullptr, R, Vl, H);
       all_reduce_tmp(T);
     }
     if (R > 0) {

@@ -84,7 +84,8 @@ template <int BT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
                          void* __restrict__ Yv, int ldy, int T, int N, int K, float* __restrict__ ws,
-                         int* __restrict__ counters, int stream_weights, int out_f32) {
+                         int* __restrict__ counters, int stream_weights, int out_f32,
+                         const __grid_constant__ CUtensorMap next_wmap, GemmNext nxt) {
   // output: bf16 (rounded once from the fp32 accumulator, = F.linear in model dtype) or raw fp32 (lm_head logits)
   __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(Yv);
   float* __restrict__ Yf = reinterpret_cast<float*>(Yv);
@@ -183,6 +184,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         }
       }
       TL(4);  // last TMA issued
+      // Cross-kernel weight prefetch: HBM goes idle while this kernel drains its pipeline, reduces split tiles and
+      // exits, and the next GEMM of the layer stack needs ~10 us before its own loads are in flight.  So the boxes
+      // that the next GEMM's CTAs will read FIRST are pulled into the 126 MB L2 now (TMA prefetch, no smem, no
+      // completion tracking): next CTA c2 starts at k-block (total2 * c2 / grid2) of its (tile, k-block) space.
+      if (nxt.kb_prefetch > 0) {
+        const long long total2 = (long long)nxt.n_tiles * nxt.KB;
+        for (int c2 = cta; c2 < nxt.grid; c2 += ncta) {
+          const long long b2 = (total2 * c2) / nxt.grid, e2 = (total2 * (c2 + 1)) / nxt.grid;
+          const int n2 = (int)((e2 - b2) < nxt.kb_prefetch ? (e2 - b2) : nxt.kb_prefetch);
+          int tile2 = (int)(b2 / nxt.KB), kb2 = (int)(b2 % nxt.KB);
+          for (int i = 0; i < n2; ++i) {
+            tma_prefetch_2d(&next_wmap, kb2 * GEMM_BK, tile2 * GEMM_BN);
+            if (++kb2 == nxt.KB) { kb2 = 0; ++tile2; }
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -413,17 +430,9 @@ int gemm_pick_bt(int T) {
 
 size_t gemm_workspace_bytes(int num_sms) { return (size_t)num_sms * 2 * 256 * GEMM_BN * sizeof(float); }
 
-template <int BT>
-static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
-                             float* ws, int* counters, int num_sms, int out_f32, cudaStream_t stream) {
-  using Cfg = GemmCfg<BT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+// Grid size of a launch (pure function of the shape: the NEXT kernel's grid must be known one launch ahead)
+int gemm_grid_size(int T, int N, int K, int num_sms) {
+  const int BT = gemm_pick_bt(T);
   const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
   long long total = (long long)n_tiles * t_tiles * KB;
   // do not cut finer than 4 k-blocks per CTA: tiny problems use fewer CTAs
@@ -437,25 +446,59 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, v
     if (split > KB / 4) split = KB / 4 > 0 ? KB / 4 : 1;
     grid = (int)(tiles * split);
   }
-  if (const char* e = getenv("TGIS_GEMM_MAX_CTAS")) {  // experiment knob (scripts/gemm_bench.py)
+  if (const char* e = getenv("TGIS_GEMM_MAX_CTAS")) {  // experiment knob (scripts/gemm_cta_sweep.py)
     const int cap = atoi(e);
     if (cap > 0 && grid > cap) grid = cap;
   }
+  return grid;
+}
+
+GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_prefetch) {
+  GemmNext n{};
+  const int BT = gemm_pick_bt(T_next);
+  if ((T_next + BT - 1) / BT != 1) return n;  // only decode-shaped successors (one token tile) are prefetched
+  n.n_tiles = (N_next + GEMM_BN - 1) / GEMM_BN;
+  n.KB = (K_next + GEMM_BK - 1) / GEMM_BK;
+  n.grid = gemm_grid_size(T_next, N_next, K_next, num_sms);
+  n.kb_prefetch = kb_prefetch;
+  return n;
+}
+
+template <int BT>
+static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
+                             float* ws, int* counters, int num_sms, int out_f32, cudaStream_t stream,
+                             const CUtensorMap& next_wmap, const GemmNext& nxt) {
+  using Cfg = GemmCfg<BT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int t_tiles = (T + BT - 1) / BT;
+  const int grid = gemm_grid_size(T, N, K, num_sms);
   const int stream_weights = (t_tiles == 1) ? 1 : 0;
   return launch_k(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
-                  ldy, T, N, K, ws, counters, stream_weights, out_f32);
+                  ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt);
 }
 
 // xmap must have been built with box_rows == gemm_pick_bt(T)
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
-                             float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32) {
+                             float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32,
+                             const CUtensorMap* next_wmap, const GemmNext* next) {
+  GemmNext nx{};
+  if (next && next_wmap) nx = *next;
+  const CUtensorMap& nm = (next && next_wmap) ? *next_wmap : wmap;
+#define TGIS_GEMM_CASE(B) return launch_bt<B>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx)
   switch (gemm_pick_bt(T)) {
-    case 16: return launch_bt<16>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
-    case 32: return launch_bt<32>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
-    case 64: return launch_bt<64>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
-    case 128: return launch_bt<128>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
-    default: return launch_bt<256>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream);
+    case 16: TGIS_GEMM_CASE(16);
+    case 32: TGIS_GEMM_CASE(32);
+    case 64: TGIS_GEMM_CASE(64);
+    case 128: TGIS_GEMM_CASE(128);
+    default: TGIS_GEMM_CASE(256);
   }
+#undef TGIS_GEMM_CASE
 }
 
 }  // namespace tgis

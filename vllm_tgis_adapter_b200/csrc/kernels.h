@@ -15,9 +15,17 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int gemm_pick_bt(int T);
 size_t gemm_workspace_bytes(int num_sms);
 int gemm_timeline_read(unsigned long long* out64);  // debug builds (-DTGIS_GEMM_TIMELINE) only
+// Decode-shaped successor of a GEMM launch: lets the running kernel pull the first `kb_prefetch` weight boxes of every
+// CTA of the NEXT GEMM into L2 while its own tail drains (kb_prefetch == 0: off).
+struct GemmNext {
+  int n_tiles, KB, grid, kb_prefetch;
+};
+int gemm_grid_size(int T, int N, int K, int num_sms);
+GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_prefetch);
 // Y: bf16 [T, ldy] (out_f32 = 0) or fp32 [T, ldy] (out_f32 = 1, used for the lm_head logits)
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
-                             float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32 = 0);
+                             float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32 = 0,
+                             const CUtensorMap* next_wmap = nullptr, const GemmNext* next = nullptr);
 
 // ---- gemm_ref.cu (debug cross-check only; never on the product path) ---------------------------------------------
 cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, void* Y, int ldy, int T,

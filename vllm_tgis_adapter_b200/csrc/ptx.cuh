@@ -90,6 +90,13 @@ __device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* m, uint64_t*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// 2D tile prefetch into L2 only (SASS: UTMAPF.L2): no smem destination, no completion tracking
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // 1D bulk copy global->smem (SASS: UBLKCP); size multiple of 16, both addresses 16B aligned
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

@@ -91,7 +91,8 @@ def load_safetensors_dir(eng: NativeEngine, path: Path) -> None:
 
 def build_engine(args) -> AsyncTGISEngine:
     if args.tensor_parallel_size not in (None, 1):
-        raise ValueError("tensor parallelism is not available in this revision: run one replica per GPU")
+        raise ValueError("the server entrypoint runs single-GPU engines; tensor-parallel engines are started one process "
+                         "per GPU (scripts/tp_check.py shows the launch pattern)")
     if not args.model:
         raise ValueError("--model / --model-name is required")
     path = Path(args.model)
