@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--prompt-len", type=int, default=512)
     ap.add_argument("--gen-len", type=int, default=128)
+    ap.add_argument("--parallel", default="dp", choices=["dp", "tp"],
+                    help="N>1: dp = independent replicas (default, weak scaling); tp = ONE tensor-parallel engine over N GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-decode-steps", type=int, default=3)
     ap.add_argument("--cpu-layers", type=int, default=2, help="layers timed by the CPU baseline (extrapolated)")
@@ -184,12 +186,14 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
 
     # thread count: all host threads unless fewer are faster (OpenMP fork/join cost on very wide hosts)
     best_thr, best_t = cores, None
-    for thr in sorted({cores, min(cores, 64), min(cores, 32)}, reverse=True):
+    for thr in sorted({min(cores, 16), min(cores, 32), min(cores, 64), cores}):
         torch.set_num_threads(thr)
         t = decode_steps(1)
         log(f"cpu reference: {thr} threads -> {t:.3f} s per {L_s}-layer decode step (probe)")
         if best_t is None or t < best_t:
             best_thr, best_t = thr, t
+        elif t > 1.5 * best_t:
+            break   # wider is getting slower (fork/join cost): do not pay for the even wider probes
     torch.set_num_threads(best_thr)
     nd = args.cpu_decode_steps
     times = []
@@ -256,9 +260,18 @@ def run_ours(args) -> dict | None:
     blocks = B * ((P + G + 31) // 32 + 2)
     kv_bytes = int(blocks * 2 * cfg.n_layers * cfg.n_kv_heads * 32 * 128 * 2 * 1.1)
     torch.cuda.set_device(local)
-    eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=8192, kv_cache_bytes=kv_bytes, device=local, seed=1234)
-    # synthetic N(0, 0.02) weights generated on the device, one tensor at a time ("PyTorch tensors for weights only")
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    tp = world if (args.parallel == "tp" and world > 1) else 1
+    tp_kw = {}
+    if tp > 1:
+        ids = [NativeEngine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local))
+        tp_kw = dict(tp_size=tp, tp_rank=rank, nccl_id=ids[0], shm_name=f"/tgis_bench_{os.environ.get('MASTER_PORT', '0')}")
+        kv_bytes //= tp
+    eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=8192, kv_cache_bytes=kv_bytes, device=local, seed=1234,
+                       **tp_kw)
+    # synthetic N(0, 0.02) weights generated on the device, one tensor at a time ("PyTorch tensors for weights only");
+    # under tp every rank draws the SAME full tensor (same seed) and the engine keeps its shard
+    gen = torch.Generator(device="cuda").manual_seed(1234 + (rank if tp == 1 else 0))
 
     def rnd(r, c):
         return (torch.randn(r, c, generator=gen, device="cuda", dtype=torch.float32) * 0.02).to(torch.bfloat16)
@@ -281,6 +294,12 @@ def run_ours(args) -> dict | None:
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     log(f"engine built and {cfg.n_layers}-layer synthetic weights loaded")
+    if tp > 1 and rank != 0:   # tensor-parallel worker: follow rank 0's step plans until it closes its engine
+        eng.worker_run()
+        eng.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return None
 
     import numpy as np
 
@@ -309,7 +328,7 @@ def run_ours(args) -> dict | None:
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 and tp == 1:
             dist.barrier()
 
     for i in range(args.warmup):
@@ -353,31 +372,42 @@ def run_ours(args) -> dict | None:
     log(f"profiled pass done: {gemm_calls} GEMM launches, {gemm_ms:.2f} ms")
 
     # ---- reduce over ranks (max time, sum tokens)
-    (dec_ms_m, decode_wall_m, wall_m), (dec_tok_s, n_tok_s, launches_s) = reduce_over_ranks(
-        [dec_ms, decode_wall, wall], [dec_tok, n_tok, launches], "cuda" if world > 1 else "cpu")
-    eng.close()
-    if world > 1:
+    if tp > 1:   # one engine: rank 0 holds the whole-job numbers
+        (dec_ms_m, decode_wall_m, wall_m), (dec_tok_s, n_tok_s, launches_s) = (
+            [dec_ms, decode_wall, wall], [dec_tok, n_tok, launches])
+        eng.close()
+        dist.barrier()
         dist.destroy_process_group()
+    else:
+        (dec_ms_m, decode_wall_m, wall_m), (dec_tok_s, n_tok_s, launches_s) = reduce_over_ranks(
+            [dec_ms, decode_wall, wall], [dec_tok, n_tok, launches], "cuda" if world > 1 else "cpu")
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
     if rank != 0:
         return None
+    n_rep = 1 if tp > 1 else world   # independent replicas
     peak, peak_src = peaks()
     n_params = cfg.n_layers * (cfg.hidden * (cfg.q_dim + 2 * cfg.kv_dim) + cfg.hidden * cfg.q_dim
                                + 3 * cfg.hidden * cfg.ffn) + cfg.vocab * cfg.hidden
     kv_tok = 2 * cfg.n_layers * cfg.n_kv_heads * 128 * 2
-    bytes_step = n_params * 2 + B * (P + G / 2) * kv_tok + B * cfg.vocab * 4
+    # algorithmic bytes of one decode step PER GPU: weights/tp + KV/tp + one fp32 logits scan
+    bytes_step = (n_params * 2 + B * (P + G / 2) * kv_tok) / tp + B * cfg.vocab * 4
     step_ms = dec_ms / max(dec_steps, 1)
     achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else None
     out = {
         "metric": "decode tokens/sec + p50 TTFT, 512-in/128-out batch, 1/2/4/8xB200 vs CPU ref",
         "value": dec_tok_s / (dec_ms_m * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * wall_m / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall_m / args.steps, "higher_is_better": True,
+        "scaling": "strong" if tp > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,0.02) weights, uniform random prompts)",
         "config": {"workload": f"{args.model} bf16, {B} concurrent requests/GPU, {P}-in/{G}-out, greedy "
                                f"(BASELINE.json configs[1])", "batch_per_gpu": B, "prompt_len": P, "gen_len": G,
-                   "parallelism": f"dp{world} (independent replicas, no collective)",
+                   "parallelism": (f"tp{tp} (one engine, NCCL all-reduce after o/down proj, all-gather of logits)"
+                                   if tp > 1 else f"dp{world} (independent replicas, no collective)"),
                    "l2": "inputs larger than L2 (15 GB of weights streamed per decode step)",
                    "timing": "value: CUDA events on the engine stream over pure-decode steps; e2e: wall clock"},
-        "e2e": {"value": (n_tok_s - world * B * args.steps) / decode_wall_m if decode_wall_m > 0 else None,
+        "e2e": {"value": (n_tok_s - n_rep * B * args.steps) / decode_wall_m if decode_wall_m > 0 else None,
                 "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "job_output_tokens_per_s": n_tok_s / wall_m, "ttft_p50_ms": 1e3 * statistics.median(ttfts),
                 "ttft_max_ms": 1e3 * max(ttfts),
