@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,driver_version --format=csv > gpurun_out/gpu_info.txt 2>&1
 nproc >> gpurun_out/gpu_info.txt; free -g | head -2 >> gpurun_out/gpu_info.txt
 STAGES="${1:-kernels engine}"
+NGPU="${NGPU:-2}"
 for st in $STAGES; do
   case $st in
     kernels) timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x --no-header -p no:cacheprovider > gpurun_out/test_kernels.log 2>&1; echo "kernels rc=$?" ;;
@@ -25,6 +26,9 @@ for st in $STAGES; do
     prof_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_decode -s 2 -c 2 -f -o gpurun_out/prof_attn python scripts/profile_decode.py 2 32 512 4 0 > gpurun_out/prof_attn.log 2>&1; echo "prof_attn rc=$?" ;;
     decode_quick) for pdl in 0 1; do for gr in 0 1; do TGIS_PDL=$pdl timeout 300 python scripts/profile_decode.py 8 32 512 24 $gr > gpurun_out/decode_pdl${pdl}_graph${gr}.log 2>&1; done; done; echo "decode_quick rc=$?" ;;
     tp2) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29511 scripts/tp_check.py tiny > gpurun_out/tp2.log 2>&1; echo "tp2 rc=$?"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29512 scripts/tp_check.py tiny > gpurun_out/tp2_b.log 2>&1; echo "tp2 small rc=$?" ;;
+    grpc_bench) timeout 600 python scripts/grpc_bench.py > gpurun_out/grpc_bench.log 2>&1; echo "grpc_bench rc=$?" ;;
+    bench_tp) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $NGPU --parallel tp --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/bench_tp$NGPU.log 2> gpurun_out/bench_tp$NGPU.err; echo "bench_tp rc=$?" ;;
+    bench_dp) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $NGPU --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/bench_dp$NGPU.log 2> gpurun_out/bench_dp$NGPU.err; echo "bench_dp rc=$?" ;;
     timeline) timeout 300 python scripts/gemm_timeline.py > gpurun_out/gemm_timeline.log 2>&1; echo "timeline rc=$?" ;;
     ctasweep) timeout 300 python scripts/gemm_cta_sweep.py > gpurun_out/gemm_cta_sweep.log 2>&1; echo "ctasweep rc=$?" ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
