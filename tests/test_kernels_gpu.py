@@ -60,6 +60,28 @@ def test_gemm_fp32_output_for_logits(g):
     assert float((y - ref).abs().max()) < 2e-5 * float(ref.abs().max()) + 1e-5
 
 
+@pytest.mark.parametrize("T,F,K", [(32, 1536, 512), (7, 14336, 4096), (300, 1024, 256)])
+def test_gemm_fused_swiglu_epilogue(g, T, F, K):
+    """gate_up GEMM with SwiGLU fused in the epilogue (rows interleaved gate_j, up_j) == GEMM -> bf16 -> silu*mul."""
+    gen = torch.Generator(device="cuda").manual_seed(T + F)
+    x = (torch.randn(T, K, generator=gen, device="cuda") * 0.5).bfloat16()
+    wg = (torch.randn(F, K, generator=gen, device="cuda") * 0.05).bfloat16()
+    wu = (torch.randn(F, K, generator=gen, device="cuda") * 0.05).bfloat16()
+    w = torch.stack([wg, wu], dim=1).reshape(2 * F, K).contiguous()   # row 2j = gate_j, row 2j+1 = up_j
+    act, _ = g.gemm(x, w, swiglu=True)
+    gate = (x.float() @ wg.float().t()).bfloat16()
+    up = (x.float() @ wu.float().t()).bfloat16()
+    ref = torch.nn.functional.silu(gate) * up
+    ulp = g.bf16_ulp_diff(act, ref)
+    bad = (ulp > 2.01) & ((act.float() - ref.float()).abs() > 2e-3 * ref.float().abs().mean())
+    assert int(bad.sum()) == 0, float(ulp.max())
+    assert float((ulp == 0).float().mean()) > 0.95
+    act2, _ = g.gemm(x, w, swiglu=True)
+    assert torch.equal(act, act2)
+    actr, _ = g.gemm(x, w, impl=1, swiglu=True)   # SIMT cross-check kernel, same fusion
+    assert float((g.bf16_ulp_diff(act, actr) * ((act.float() - actr.float()).abs() > 2e-4)).max()) <= 2.0
+
+
 def test_gemm_crosscheck_kernel_agrees(g):
     gen = torch.Generator(device="cuda").manual_seed(7)
     x = (torch.randn(48, 1024, generator=gen, device="cuda") * 0.5).bfloat16()

@@ -40,16 +40,17 @@ def i32p(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
-def gemm(x: torch.Tensor, w: torch.Tensor, impl: int = 0, iters: int = 1, out_f32: bool = False
+def gemm(x: torch.Tensor, w: torch.Tensor, impl: int = 0, iters: int = 1, out_f32: bool = False, swiglu: bool = False
          ) -> tuple[torch.Tensor, float]:
     T, K = x.shape
     N = w.shape[0]
     rows = max(T, 256)
     xp = torch.zeros(rows, K, dtype=torch.bfloat16, device="cuda")
     xp[:T] = x
-    y = torch.empty(T, N, dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
+    mode = 2 if swiglu else (1 if out_f32 else 0)
+    y = torch.empty(T, N // 2 if swiglu else N, dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
     ms = C.c_float(0)
-    rc = lib().tgis_k_gemm(ptr(xp), ptr(w), ptr(y), T, N, K, rows, impl, iters, C.byref(ms), 1 if out_f32 else 0)
+    rc = lib().tgis_k_gemm(ptr(xp), ptr(w), ptr(y), T, N, K, rows, impl, iters, C.byref(ms), mode)
     assert rc == 0, kerr()
     return y, ms.value
 

@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs),
-            "-Xcompiler", "-pthread", "-cudart", "static", "-lnccl", "-lrt"]
+            "-Xcompiler", "-pthread", "-cudart", "static", "-lrt", "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -26,6 +26,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <nccl.h>
@@ -53,11 +54,42 @@ double now_s() {
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
+// NCCL is resolved at run time (dlopen) and only when tp_size > 1: a hard link-time dependency would pin whichever
+// libnccl.so.2 the loader finds first and can break a later `import torch` (torch 2.11 needs 2.28 symbols) when this
+// library is loaded before torch.  dlopen by SONAME returns torch's already-loaded copy when there is one.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return;
+    auto sym = [&](const char* n) { return dlsym(h, n); };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.AllGather && api.CommDestroy && api.GetErrorString;
+  });
+  if (!api.ok) throw CudaError("libnccl.so.2 could not be loaded (needed for tp_size > 1)");
+  return api;
+}
 #define NK(expr)                                                                                        \
   do {                                                                                                  \
     ncclResult_t _r = (expr);                                                                           \
     if (_r != ncclSuccess)                                                                              \
-      throw CudaError(std::string(#expr) + " failed: " + ncclGetErrorString(_r));                       \
+      throw CudaError(std::string(#expr) + " failed: " + nccl().GetErrorString(_r));                       \
   } while (0)
 #define CK(expr)                                                                                        \
   do {                                                                                                  \
@@ -236,7 +268,7 @@ struct tgis_engine {
       munmap(shm, shm_bytes);
       if (shm_owner) shm_unlink(shm_name.c_str());
     }
-    if (comm) ncclCommDestroy(comm);
+    if (comm) nccl().CommDestroy(comm);
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (cudaEvent_t ev : prof_events) cudaEventDestroy(ev);
     if (ev0) cudaEventDestroy(ev0);
@@ -308,7 +340,7 @@ struct tgis_engine {
     qkv.alloc(T_alloc * qkv_dim);
     attn_out.alloc(T_alloc * q_dim);
     tmp.alloc(T_alloc * H);
-    gate_up.alloc(T_alloc * 2 * F);
+    gate_up.alloc(64);  // unused since SwiGLU moved into the gate_up GEMM epilogue
     act.alloc(T_alloc * F);
     last_hidden.alloc(S_alloc * H);
     logits.alloc((size_t)S_max * V);
@@ -412,7 +444,7 @@ struct tgis_engine {
     ncclUniqueId id;
     static_assert(sizeof(id.internal) == 128, "nccl id size");
     memcpy(id.internal, cfg.nccl_id, 128);
-    NK(ncclCommInitRank(&comm, tp, id, rank));
+    NK(nccl().CommInitRank(&comm, tp, id, rank));
     shm_name = cfg.shm_name[0] ? std::string(cfg.shm_name) : std::string("/tgis_tp_plan");
     shm_bytes = SHM_STAGE_OFF + stage_bytes;
     int fd = -1;
@@ -442,7 +474,7 @@ struct tgis_engine {
       for (auto& a : shm->ack) a.store(0);
     }
     // first collective doubles as a start-up barrier (and creates NCCL's channels outside the timed path)
-    NK(ncclAllReduce(tmp.p, tmp.p, 1024, ncclBfloat16, ncclSum, comm, stream));
+    NK(nccl().AllReduce(tmp.p, tmp.p, 1024, ncclBfloat16, ncclSum, comm, stream));
     CK(cudaStreamSynchronize(stream));
   }
 
@@ -498,6 +530,7 @@ struct tgis_engine {
     bf16* dst = nullptr;
     int64_t er = 0, ec = 0;             // expected full shape
     int64_t r0 = 0, nr = 0, c0 = 0, nc = 0;  // shard = rows [r0, r0+nr) x cols [c0, c0+nc)
+    int interleave = 0;                      // destination row stride 2 (gate/up pairs)
     auto rows_shard = [&](bf16* d, int64_t full_rows, int64_t full_cols, int64_t per_rank) {
       dst = d; er = full_rows; ec = full_cols; r0 = rank * per_rank; nr = per_rank; c0 = 0; nc = full_cols;
     };
@@ -523,8 +556,9 @@ struct tgis_engine {
       else if (sub == "self_attn.k_proj.weight") rows_shard(l.wqkv + (size_t)q_dim * H, (int64_t)c.n_kv_heads * HEAD_DIM, H, kvd);
       else if (sub == "self_attn.v_proj.weight") rows_shard(l.wqkv + (size_t)(q_dim + kvd) * H, (int64_t)c.n_kv_heads * HEAD_DIM, H, kvd);
       else if (sub == "self_attn.o_proj.weight") cols_shard(l.wo, H, (int64_t)c.n_q_heads * HEAD_DIM, q_dim);
-      else if (sub == "mlp.gate_proj.weight") rows_shard(l.wgu, F, H, Fl);
-      else if (sub == "mlp.up_proj.weight") rows_shard(l.wgu + (size_t)Fl * H, F, H, Fl);
+      // gate / up rows are INTERLEAVED in wgu (row 2j = gate_j, row 2j+1 = up_j) so the GEMM epilogue can fuse SwiGLU
+      else if (sub == "mlp.gate_proj.weight") { rows_shard(l.wgu, F, H, Fl); interleave = 1; }
+      else if (sub == "mlp.up_proj.weight") { rows_shard(l.wgu + H, F, H, Fl); interleave = 1; }
       else if (sub == "mlp.down_proj.weight") cols_shard(l.wd, H, F, Fl);
       else if (sub == "input_layernorm.weight") full(l.ln1, H, 1);
       else if (sub == "post_attention_layernorm.weight") full(l.ln2, H, 1);
@@ -535,7 +569,10 @@ struct tgis_engine {
     if (rows * cols != er * ec) return fail("shape mismatch for " + name + ": got " + std::to_string(rows) + "x" +
                                             std::to_string(cols) + " expected " + std::to_string(er) + "x" + std::to_string(ec));
     cudaError_t e;
-    if (nc == ec) {
+    if (interleave) {
+      e = cudaMemcpy2D(dst, (size_t)2 * ec * sizeof(bf16), src + (size_t)r0 * ec * sizeof(bf16), (size_t)ec * sizeof(bf16),
+                       (size_t)ec * sizeof(bf16), (size_t)nr, cudaMemcpyDefault);
+    } else if (nc == ec) {
       e = cudaMemcpy(dst, src + (size_t)r0 * ec * sizeof(bf16), (size_t)(nr * ec) * sizeof(bf16), cudaMemcpyDefault);
     } else {
       e = cudaMemcpy2D(dst, (size_t)nc * sizeof(bf16), src + (size_t)c0 * sizeof(bf16), (size_t)ec * sizeof(bf16),
@@ -555,7 +592,8 @@ struct tgis_engine {
   // next_wm / nT,nN,nK describe the GEMM that follows this one in the layer stack: its first weight boxes are
   // prefetched into L2 by this launch's producer warp (gemm_tcgen05.cu)
   void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, void* Y, int T, int N, int K,
-            int out_f32 = 0, const CUtensorMap* next_wm = nullptr, int nT = 0, int nN = 0, int nK = 0) {
+            int out_f32 = 0, const CUtensorMap* next_wm = nullptr, int nT = 0, int nN = 0, int nK = 0, int ldy = 0) {
+    if (ldy == 0) ldy = N;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profiling && (!prof_decode_only || step_is_decode)) {
       while (prof_events.size() < prof_used + 2) {
@@ -567,15 +605,15 @@ struct tgis_engine {
       pe1 = prof_events[prof_used + 1];
       prof_used += 2;
       // algorithmic bytes: weights once + activations in + result out
-      prof_bytes.push_back((double)N * K * 2 + (double)T * K * 2 + (double)T * N * (out_f32 ? 4 : 2));
+      prof_bytes.push_back((double)N * K * 2 + (double)T * K * 2 + (double)T * N * (out_f32 == 1 ? 4 : out_f32 == 2 ? 1 : 2));
       CK(cudaEventRecord(pe0, stream));
     }
     if (cfg.debug_gemm_ref) {
-      CK(gemm_bf16_ref_launch(X, K, W, Y, N, T, N, K, stream, out_f32));
+      CK(gemm_bf16_ref_launch(X, K, W, Y, ldy, T, N, K, stream, out_f32));
     } else {
       GemmNext nx{};
       if (next_wm && l2_prefetch_kb > 0) nx = gemm_next_desc(nT, nN, nK, num_sms, l2_prefetch_kb);
-      CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, N, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32,
+      CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, ldy, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32,
                           nx.kb_prefetch > 0 ? next_wm : nullptr, nx.kb_prefetch > 0 ? &nx : nullptr));
     }
     if (pe1) CK(cudaEventRecord(pe1, stream));
@@ -588,7 +626,7 @@ struct tgis_engine {
   T* ds(size_t off) { return reinterpret_cast<T*>(d_stage.p + off); }
 
   void all_reduce_tmp(int T) {
-    if (tp > 1) NK(ncclAllReduce(tmp.p, tmp.p, (size_t)T * cfg.hidden, ncclBfloat16, ncclSum, comm, stream));
+    if (tp > 1) NK(nccl().AllReduce(tmp.p, tmp.p, (size_t)T * cfg.hidden, ncclBfloat16, ncclSum, comm, stream));
   }
 
   // Enqueue one step on `stream`: H2D metadata, layer stack, lm_head + sampler, D2H results.  Reads every per-step
@@ -637,9 +675,8 @@ struct tgis_engine {
       all_reduce_tmp(T);  // row-parallel partial sums (tp > 1)
       CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
       ++n_launches;
-      gemm(xm_xn, l.m_gu, xn.p, l.wgu, gate_up.p, T, 2 * F, H, 0, &l.m_d, T, H, F);
-      CK(silu_mul_launch(gate_up.p, act.p, T, F, stream));
-      ++n_launches;
+      // gate_up GEMM with SwiGLU fused into its epilogue: writes act[T, F] directly (no gate_up round trip)
+      gemm(xm_xn, l.m_gu, xn.p, l.wgu, act.p, T, 2 * F, H, /*out_mode=*/2, &l.m_d, T, H, F, /*ldy=*/F);
       if (li + 1 < c.n_layers) gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F, 0, &layers[li + 1].m_qkv, T, qkv_dim, H);
       else gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F, 0, R > 0 ? &m_lm : nullptr, R, Vl, H);
       all_reduce_tmp(T);
@@ -653,7 +690,7 @@ struct tgis_engine {
       } else {
         // vocab-parallel lm_head: every rank computes [R, V/tp] fp32, all-gather, re-layout to [R, V]
         gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, R, Vl, H, /*out_f32=*/1);
-        NK(ncclAllGather(logits_shard.p, logits_gather.p, (size_t)R * Vl, ncclFloat, comm, stream));
+        NK(nccl().AllGather(logits_shard.p, logits_gather.p, (size_t)R * Vl, ncclFloat, comm, stream));
         if (rank == 0) {
           CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const float*)logits_gather.p,
                       logits.p, R, Vl, tp));
@@ -1191,7 +1228,11 @@ int tgis_engine_status(tgis_engine* e, tgis_status* out) {
 
 int tgis_nccl_unique_id(uint8_t out[128]) {
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return fail("ncclGetUniqueId failed");
+  try {
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return fail("ncclGetUniqueId failed");
+  } catch (const std::exception& ex) {
+    return fail(ex.what());
+  }
   memcpy(out, id.internal, 128);
   return 0;
 }

@@ -80,6 +80,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define TL(slot) do {} while (0)
 #endif
 
+// SwiGLU on one (gate, up) accumulator pair with the rounding points of the unfused path
+// (bf16 GEMM outputs -> bf16(silu(g)) -> bf16(. * u); vllm activation_kernels.cu / HF LlamaMLP)
+__device__ __forceinline__ __nv_bfloat16 swiglu_bf16(float gate_acc, float up_acc) {
+  const float g = bf16_round(gate_acc), u = bf16_round(up_acc);
+  const float sl = bf16_round(g / (1.0f + expf(-g)));
+  return __float2bfloat16_rn(sl * u);
+}
+
 template <int BT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
@@ -265,7 +273,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         tmem_ld_32x32b_x16(taddr + c0, r);
         tmem_ld_wait();
         if (!partial) {
-          if (n < N) {
+          if (out_f32 == 2) {
+            // fused SwiGLU: weight rows are interleaved (2j = gate_j, 2j+1 = up_j) so the pair sits in adjacent
+            // lanes; even lanes produce act[t, n/2]
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), 1);
+              if ((row & 1) == 0 && n < N && c0 + j < t_valid)
+                Y[(size_t)(t_base + c0 + j) * ldy + (n >> 1)] = swiglu_bf16(__uint_as_float(r[j]), other);
+            }
+          } else if (n < N) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (c0 + j < t_valid) {
@@ -344,8 +361,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
               if (t < t_valid) {
                 const size_t o = (size_t)(t_base + t) * ldy + n4;
                 const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
-                if (n4 + 3 < N && (ldy & 3) == 0) {
-                  if (out_f32) {
+                if (out_f32 == 2) {  // fused SwiGLU: rows (n4, n4+1) and (n4+2, n4+3) are (gate, up) pairs
+                  __nv_bfloat16* yo = Y + (size_t)(t_base + t) * ldy + (n4 >> 1);
+                  if (n4 + 1 < N) yo[0] = swiglu_bf16(av[0], av[1]);
+                  if (n4 + 3 < N) yo[1] = swiglu_bf16(av[2], av[3]);
+                } else if (n4 + 3 < N && (ldy & 3) == 0) {
+                  if (out_f32 == 1) {
                     *reinterpret_cast<float4*>(Yf + o) = acc[j];
                   } else {
                     __nv_bfloat162 lo = __floats2bfloat162_rn(av[0], av[1]), hi = __floats2bfloat162_rn(av[2], av[3]);

@@ -22,7 +22,8 @@ struct GemmNext {
 };
 int gemm_grid_size(int T, int N, int K, int num_sms);
 GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_prefetch);
-// Y: bf16 [T, ldy] (out_f32 = 0) or fp32 [T, ldy] (out_f32 = 1, used for the lm_head logits)
+// Y: bf16 [T, ldy] (out_f32 = 0), fp32 [T, ldy] (out_f32 = 1, lm_head logits), or out_f32 = 2: fused SwiGLU — W rows are
+// interleaved (gate_j, up_j) pairs and Y is bf16 [T, ldy >= N/2] = bf16(bf16(silu(gate)) * up)
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32 = 0,
                              const CUtensorMap* next_wmap = nullptr, const GemmNext* next = nullptr);

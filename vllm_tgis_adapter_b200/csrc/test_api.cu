@@ -58,7 +58,7 @@ int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, in
   if (impl == 1) {
     KCK(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i)
-      KCK(gemm_bf16_ref_launch((const bf16*)x_dev, K, (const bf16*)w_dev, y_dev, N, T, N, K, st, out_f32));
+      KCK(gemm_bf16_ref_launch((const bf16*)x_dev, K, (const bf16*)w_dev, y_dev, out_f32 == 2 ? N / 2 : N, T, N, K, st, out_f32));
     KCK(cudaEventRecord(e1, st));
   } else {
     int dev = 0, sms = 148;
@@ -76,7 +76,7 @@ int tgis_k_gemm(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, in
     KCK(cudaMemset(ctr.p, 0, sizeof(int) << 16));
     KCK(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i)
-      KCK(gemm_bf16_launch(wm, xm, y_dev, N, T, N, K, ws.p, ctr.p, sms, st, out_f32));
+      KCK(gemm_bf16_launch(wm, xm, y_dev, out_f32 == 2 ? N / 2 : N, T, N, K, ws.p, ctr.p, sms, st, out_f32));
     KCK(cudaEventRecord(e1, st));
     KCK(cudaStreamSynchronize(st));
   }

@@ -110,6 +110,8 @@ class NativeEngine:
         cfg.kv_cache_bytes, cfg.gpu_mem_fraction = kv_cache_bytes, gpu_mem_fraction
         cfg.device, cfg.tp_size, cfg.tp_rank = device, tp_size, tp_rank
         if tp_size > 1:
+            import torch  # noqa: F401  (load torch's NCCL before the engine dlopens libnccl.so.2)
+
             if nccl_id is None or len(nccl_id) != 128:
                 raise EngineError("tensor parallelism needs the 128-byte NCCL unique id of rank 0")
             C.memmove(cfg.nccl_id, nccl_id, 128)
@@ -180,6 +182,8 @@ class NativeEngine:
 
     @staticmethod
     def nccl_unique_id() -> bytes:
+        import torch  # noqa: F401  (torch's bundled libnccl.so.2 must be the copy in the process: see csrc/engine.cu)
+
         buf = (C.c_uint8 * 128)()
         lib = _lib.load_library()
         if lib.tgis_nccl_unique_id(C.byref(buf)) != 0:
