@@ -158,44 +158,50 @@ cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, in
 }
 
 // ------------------------------------------------------------------------------------------------ RoPE + KV scatter
-// grid = (T, ceil(heads/4)); 256 threads = 4 heads x 64 rotary pairs.
-__global__ void __launch_bounds__(256)
+// grid = (T, ceil(heads/16)); 128 threads = 16 heads x 8 threads; a thread owns 8 consecutive rotary pairs
+// (i..i+7, i+64..i+71): every global access is a 16-byte vector, and 8 consecutive dims are exactly one chunk of the
+// K / V cache layouts, so the scatter is one 16-byte store per half.
+__global__ void __launch_bounds__(128)
 rope_kvwrite_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ positions,
                     const int32_t* __restrict__ slot_mapping, const __nv_bfloat16* __restrict__ cos_sin,
                     __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int n_q, int n_kv) {
   griddep_launch();
   griddep_wait();
   const int t = blockIdx.x;
-  const int head = blockIdx.y * 4 + (threadIdx.x >> 6);
-  const int i = threadIdx.x & 63;
+  const int head = blockIdx.y * 16 + (threadIdx.x >> 3);
+  const int c = threadIdx.x & 7;  // chunk of 8 pairs: dims [8c, 8c+8) and [64+8c, 64+8c+8)
   const int n_heads = n_q + 2 * n_kv;
   if (head >= n_heads) return;
   __nv_bfloat16* h = qkv + ((size_t)t * n_heads + head) * HEAD_DIM;
   const int slot = slot_mapping[t];
+  BF8 lo = reinterpret_cast<const BF8*>(h)[c];
+  BF8 hi = reinterpret_cast<const BF8*>(h)[8 + c];
   if (head < n_q + n_kv) {
     const int pos = positions[t];
-    const float c = __bfloat162float(cos_sin[(size_t)pos * HEAD_DIM + i]);
-    const float s = __bfloat162float(cos_sin[(size_t)pos * HEAD_DIM + 64 + i]);
-    const float x1 = __bfloat162float(h[i]), x2 = __bfloat162float(h[i + 64]);
-    const __nv_bfloat16 o1 = __float2bfloat16_rn(bf16_round(x1 * c) - bf16_round(x2 * s));
-    const __nv_bfloat16 o2 = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * s));
-    h[i] = o1;
-    h[i + 64] = o2;
+    const BF8 cs = reinterpret_cast<const BF8*>(cos_sin + (size_t)pos * HEAD_DIM)[c];
+    const BF8 sn = reinterpret_cast<const BF8*>(cos_sin + (size_t)pos * HEAD_DIM + 64)[c];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x1 = __bfloat162float(lo.v[e]), x2 = __bfloat162float(hi.v[e]);
+      const float cc = __bfloat162float(cs.v[e]), ss = __bfloat162float(sn.v[e]);
+      lo.v[e] = __float2bfloat16_rn(bf16_round(x1 * cc) - bf16_round(x2 * ss));
+      hi.v[e] = __float2bfloat16_rn(bf16_round(x2 * cc) + bf16_round(x1 * ss));
+    }
+    reinterpret_cast<BF8*>(h)[c] = lo;
+    reinterpret_cast<BF8*>(h)[8 + c] = hi;
     if (head >= n_q && slot >= 0) {
       const int kvh = head - n_q;
       const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
-      __nv_bfloat16* kb = k_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM);
-      // K layout: [chunk = d/8][token][d%8]
-      kb[((i >> 3) * KV_BLOCK + off) * 8 + (i & 7)] = o1;
-      kb[(((i + 64) >> 3) * KV_BLOCK + off) * 8 + (i & 7)] = o2;
+      BF8* kb = reinterpret_cast<BF8*>(k_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM));
+      kb[c * KV_BLOCK + off] = lo;        // K layout: [chunk = d/8][token][8]
+      kb[(8 + c) * KV_BLOCK + off] = hi;
     }
   } else if (slot >= 0) {
     const int kvh = head - n_q - n_kv;
     const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
-    __nv_bfloat16* vb = v_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM) + (size_t)off * HEAD_DIM;
-    // V layout: [token][16-byte chunk ^ (token & 7)][8]  (bank-conflict-free ldmatrix / LDS.64 in attention.cu)
-    vb[(((i >> 3) ^ (off & 7)) << 3) + (i & 7)] = h[i];
-    vb[((((i + 64) >> 3) ^ (off & 7)) << 3) + (i & 7)] = h[i + 64];
+    BF8* vb = reinterpret_cast<BF8*>(v_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM) + (size_t)off * HEAD_DIM);
+    vb[c ^ (off & 7)] = lo;               // V layout: [token][16-byte chunk ^ (token & 7)][8]
+    vb[(8 + c) ^ (off & 7)] = hi;
   }
 }
 
@@ -204,8 +210,8 @@ cudaError_t rope_kvwrite_launch(__nv_bfloat16* qkv, const int32_t* positions, co
                                 int n_q, int n_kv, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   const int n_heads = n_q + 2 * n_kv;
-  dim3 grid(T, (n_heads + 3) / 4);
-  return launch_k(rope_kvwrite_kernel, grid, dim3(256), 0, stream, qkv, positions, slot_mapping, cos_sin, k_cache, v_cache,
+  dim3 grid(T, (n_heads + 15) / 16);
+  return launch_k(rope_kvwrite_kernel, grid, dim3(128), 0, stream, qkv, positions, slot_mapping, cos_sin, k_cache, v_cache,
                   n_q, n_kv);
 }
 

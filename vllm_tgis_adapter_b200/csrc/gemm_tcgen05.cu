@@ -31,7 +31,13 @@ struct GemmCfg {
   static constexpr int X_BYTES = BT * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+#ifndef TGIS_GEMM_DECODE_STAGES
+#define TGIS_GEMM_DECODE_STAGES 8
+#endif
+  // decode-shaped launches (BT <= 64) may run with a shallower ring so that two consecutive GEMM kernels' CTAs fit
+  // on one SM (<= ~110 KB each): under PDL the next GEMM then prefetches its weights during this one's fix-up tail
+  static constexpr int STAGES_CAP = BT <= 64 ? TGIS_GEMM_DECODE_STAGES : 8;
+  static constexpr int STAGES = STAGES_RAW > STAGES_CAP ? STAGES_CAP : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BT) < 32 ? 32 : (2 * BT);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -89,7 +95,7 @@ __device__ __forceinline__ __nv_bfloat16 swiglu_bf16(float gate_acc, float up_ac
 }
 
 template <int BT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, (BT <= 64 && TGIS_GEMM_DECODE_STAGES <= 5) ? 2 : 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
                          void* __restrict__ Yv, int ldy, int T, int N, int K, float* __restrict__ ws,
                          int* __restrict__ counters, int stream_weights, int out_f32,

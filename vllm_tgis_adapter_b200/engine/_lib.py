@@ -77,6 +77,9 @@ _LIB: C.CDLL | None = None
 
 
 def library_path() -> Path:
+    override = os.environ.get("TGIS_ENGINE_LIB")   # experiments: an alternative build of the same sources
+    if override:
+        return Path(override)
     return Path(__file__).resolve().parent.parent / "lib" / "libtgis_engine.so"
 
 
