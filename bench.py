@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--gen-len", type=int, default=128)
     ap.add_argument("--parallel", default="dp", choices=["dp", "tp"],
                     help="N>1: dp = independent replicas (default, weak scaling); tp = ONE tensor-parallel engine over N GPUs")
+    ap.add_argument("--sampling", default="greedy", choices=["greedy", "cfg3"],
+                    help="cfg3 = repetition penalty 1.2 + length penalty (64, 1.05) + typical_p 0.9 sampling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-decode-steps", type=int, default=3)
     ap.add_argument("--cpu-layers", type=int, default=2, help="layers timed by the CPU baseline (extrapolated)")
@@ -305,7 +307,11 @@ def run_ours(args) -> dict | None:
 
     rs = np.random.RandomState(1234 + rank)
     prompts = [rs.randint(1000, cfg.vocab - 1000, size=P).tolist() for _ in range(B)]
-    sp = make_sampling_params(greedy=True, max_tokens=G, min_tokens=G, eos_token_id=2)
+    if args.sampling == "cfg3":   # BASELINE.json configs[2]: repetition penalty + ExpDecayLengthPenalty + typical-p sampling
+        sp = make_sampling_params(greedy=False, temperature=1.0, typical_p=0.9, repetition_penalty=1.2,
+                                  length_penalty=(64, 1.05), seed=1234, max_tokens=G, min_tokens=G, eos_token_id=2)
+    else:
+        sp = make_sampling_params(greedy=True, max_tokens=G, min_tokens=G, eos_token_id=2)
 
     def job():
         """One bench step through the C ABI with host buffers. Returns (decode_wall_s, ttfts, n_tokens)."""
@@ -401,7 +407,7 @@ def run_ours(args) -> dict | None:
         "warmup": args.warmup, "ms_per_step": 1e3 * wall_m / args.steps, "higher_is_better": True,
         "scaling": "strong" if tp > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,0.02) weights, uniform random prompts)",
-        "config": {"workload": f"{args.model} bf16, {B} concurrent requests/GPU, {P}-in/{G}-out, greedy "
+        "config": {"workload": f"{args.model} bf16, {B} concurrent requests/GPU, {P}-in/{G}-out, {args.sampling} "
                                f"(BASELINE.json configs[1])", "batch_per_gpu": B, "prompt_len": P, "gen_len": G,
                    "parallelism": (f"tp{tp} (one engine, NCCL all-reduce after o/down proj, all-gather of logits)"
                                    if tp > 1 else f"dp{world} (independent replicas, no collective)"),

