@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TGIS_ABI_VERSION 2
+#define TGIS_ABI_VERSION 3
 #define TGIS_MAX_REQUEST_ID 96
 #define TGIS_MAX_TOPN 12 /* reference forces max_logprobs >= 11: tgis_utils/args.py:214-216 */
 #define TGIS_MAX_STOP_TOKEN_IDS 8
@@ -87,7 +87,7 @@ typedef struct tgis_sampling_params {
   int32_t min_tokens;         /* (:530) */
   int32_t max_tokens;         /* effective per-request maximum (:787-798) */
   int32_t num_logprobs;       /* vLLM `logprobs`: 0 = none, n>=1 = sampled-token logprob+rank and n top entries */
-  int32_t prompt_logprobs;    /* 0 = none (reserved) */
+  int32_t prompt_logprobs;    /* 0 = none; k>=1: per prompt position logprob + rank of the prompt token and k top entries */
   int32_t has_seed;
   uint64_t seed;
   int32_t n_stop_token_ids;
@@ -119,6 +119,10 @@ typedef struct tgis_step_output {
   int32_t n_prompt_tokens;
   int32_t n_output_tokens; /* cumulative */
   double ts_arrival, ts_first_scheduled, ts_first_token, ts_last_token; /* CLOCK_MONOTONIC seconds */
+  int32_t prompt_pos;     /* -1: generation record; >= 1: prompt-logprob record for prompt token `prompt_pos`
+                             (token_id / logprob / rank / topn describe that prompt token given its prefix; emitted
+                             before the request's first generated token; vllm prompt_logprobs semantics) */
+  int32_t reserved;
 } tgis_step_output;
 
 typedef struct tgis_status {

@@ -95,7 +95,7 @@ class FakeNativeEngine:
             topn=[((tok or 0) + j, -0.5 - j) for j in range(n)] if tok is not None else [],
             finish_reason=finish, stop_token_id=stop_tok, n_prompt_tokens=len(st["prompt"]),
             n_output_tokens=len(st["out"]), ts_arrival=st["ts"], ts_first_scheduled=st["ts"] + 1e-4,
-            ts_first_token=st["first"] or now, ts_last_token=now))
+            ts_first_token=st["first"] or now, ts_last_token=now, token_id=tok if tok is not None else -1))
 
     def poll(self, timeout_ms: int = 0):
         outs = []

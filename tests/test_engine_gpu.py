@@ -162,3 +162,40 @@ def test_batch_invariance_and_preemption():
     assert a == b
     for recs in crowd:
         assert len([r for r in recs if r.new_token is not None]) == 40
+
+
+@pytest.mark.parametrize("chunk", [2048, 48])
+def test_prompt_logprobs_match_oracle(chunk):
+    """input_tokens + token_logprobs path (grpc_server.py:438-449, 609-611; vllm prompt_logprobs): per prompt position
+    the logprob / rank of the prompt token given its prefix and the top-k, across chunked-prefill boundaries."""
+    from oracle.llama_oracle import LlamaOracle
+    from vllm_tgis_adapter_b200.engine.core import make_sampling_params
+
+    rng = np.random.RandomState(7)
+    prompts = [rng.randint(3, 1024, size=n).tolist() for n in (100, 9, 37)]
+    sp = make_sampling_params(greedy=True, max_tokens=2, num_logprobs=1, prompt_logprobs=3)
+    cfg, weights, outs, st = _run_engine("tiny", prompts, sp, max_num_seqs=4, max_batched_tokens=chunk,
+                                         kv_cache_bytes=32 << 20)
+    assert st.errored == 0
+    ora = LlamaOracle(cfg, weights)
+    diffs = []
+    for p, recs in zip(prompts, outs):
+        prec = sorted([r for r in recs if r.prompt_pos >= 1], key=lambda r: r.prompt_pos)
+        assert [r.prompt_pos for r in prec] == list(range(1, len(p)))
+        first_gen = next(i for i, r in enumerate(recs) if r.new_token is not None)
+        assert all(r.prompt_pos >= 1 for r in recs[:first_gen])      # prompt records precede the first generated token
+        logits = ora.step([(ora.new_seq(), p)], want_all_logits=True)
+        lp = torch.log_softmax(logits, -1)
+        for r in prec:
+            i = r.prompt_pos
+            assert r.token_id == p[i]
+            ref = float(lp[i - 1, p[i]])
+            diffs.append(abs(r.logprob - ref))
+            ref_rank = int((lp[i - 1] >= lp[i - 1, p[i]]).sum())
+            assert abs(r.rank - ref_rank) <= max(2, ref_rank // 50), (r.rank, ref_rank)   # near-ties may swap
+            assert len(r.topn) == 3
+            top = torch.topk(lp[i - 1], 3)
+            assert r.topn[0][0] == int(top.indices[0]) or float(top.values[0] - top.values[1]) < 0.02
+            assert abs(r.topn[0][1] - float(top.values[0])) < 2e-2
+    diffs = np.array(diffs)
+    assert float(diffs.mean()) < 4e-3 and float(diffs.max()) < 3e-2, (float(diffs.mean()), float(diffs.max()))

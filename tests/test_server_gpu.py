@@ -121,6 +121,31 @@ def test_generate_batch_matches_oracle(live):
         assert r.text == " " + " ".join(t.text for t in r.tokens)
 
 
+def test_input_tokens_with_logprobs(live):
+    """ResponseOptions.input_tokens + token_logprobs + token_ranks -> prompt logprobs (first prompt token has none)."""
+    from vllm_tgis_adapter_b200.engine.tokenizer import synthetic_prompt
+    from vllm_tgis_adapter_b200.grpc.pb import generation_pb2 as pb
+
+    prompt = list(range(40, 70))
+    params = pb.Parameters()
+    params.stopping.max_new_tokens = 2
+    params.response.input_tokens = True
+    params.response.token_logprobs = True
+    params.response.token_ranks = True
+    params.response.top_n_tokens = 2
+    call = live.channel.unary_unary("/fmaas.GenerationService/Generate",
+                                    request_serializer=pb.BatchedGenerationRequest.SerializeToString,
+                                    response_deserializer=pb.BatchedGenerationResponse.FromString)
+    r = call(pb.BatchedGenerationRequest(model_id="m", requests=[pb.GenerationRequest(text=synthetic_prompt(prompt))],
+                                         params=params), timeout=60).responses[0]
+    assert len(r.input_tokens) == len(prompt)
+    assert [t.text for t in r.input_tokens] == [f"t{i}" for i in prompt]
+    assert r.input_tokens[0].logprob == 0.0 and r.input_tokens[0].rank == 0 and not r.input_tokens[0].top_tokens
+    for t in r.input_tokens[1:]:
+        assert t.logprob < 0.0 and t.rank >= 1 and len(t.top_tokens) == 2
+        assert t.top_tokens[0].logprob >= t.top_tokens[1].logprob >= t.logprob - 1e-6 or t.rank <= 2
+
+
 def test_generate_stream_protocol_shape_and_sampling_params(live):
     from vllm_tgis_adapter_b200.engine.tokenizer import synthetic_prompt
     from vllm_tgis_adapter_b200.grpc.pb import generation_pb2 as pb

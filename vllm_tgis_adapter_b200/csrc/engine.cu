@@ -222,6 +222,7 @@ struct tgis_engine {
   DevBuf<uint32_t> seen_bitmap;
   DevBuf<SampleOut> d_samp_out;
   SampleOut* h_samp_out = nullptr;
+  SampleOut* h_plp_out = nullptr;  // prompt-logprob pass results (kept apart from the step's sampled rows)
   // staging
   uint8_t* h_stage = nullptr;
   DevBuf<uint8_t> d_stage;
@@ -263,6 +264,7 @@ struct tgis_engine {
   ~tgis_engine() {
     if (h_stage) cudaFreeHost(h_stage);
     if (h_samp_out) cudaFreeHost(h_samp_out);
+    if (h_plp_out) cudaFreeHost(h_plp_out);
     if (shm) {
       if (rank == 0) shm->shutdown.store(1, std::memory_order_release);
       munmap(shm, shm_bytes);
@@ -362,6 +364,7 @@ struct tgis_engine {
     seen_bitmap.zero();
     d_samp_out.alloc(S_max);
     CK(cudaHostAlloc(&h_samp_out, sizeof(SampleOut) * S_max, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&h_plp_out, sizeof(SampleOut) * S_max, cudaHostAllocDefault));
 
     // ---- staging layout
     size_t o = 0;
@@ -711,6 +714,11 @@ struct tgis_engine {
     const tgis_config& c = cfg;
     const int H = c.hidden, F = c.ffn, V = c.vocab;
     int T = 0, n_dec = 0, n_tiles = 0, R = 0, max_dec_kv = 0;
+    struct PromptRow {
+      int row, target, pos;
+      Request* r;
+    };
+    std::vector<PromptRow> prompt_rows;
     int32_t* tok = hs<int32_t>(off_tok);
     int32_t* pos = hs<int32_t>(off_pos);
     int32_t* slotmap = hs<int32_t>(off_slotmap);
@@ -735,6 +743,13 @@ struct tgis_engine {
         pos[T + j] = p;
         slotmap[T + j] = r.blocks[p / KV_BLOCK] * KV_BLOCK + p % KV_BLOCK;
         tokslot[T + j] = r.slot;
+      }
+      if (r.sp.prompt_logprobs > 0 && r.n_computed < r.n_prompt - 1) {
+        // prompt logprobs (vllm gpu_model_runner.py:3638): position p predicts prompt token p+1
+        for (int j = 0; j < q_len; ++j) {
+          const int p = r.n_computed + j;
+          if (p + 1 < r.n_prompt) prompt_rows.push_back(PromptRow{T + j, r.tokens[p + 1], p + 1, &r});
+        }
       }
       if (q_len == 1) {
         decids[n_dec++] = s;
@@ -845,6 +860,42 @@ struct tgis_engine {
       prof_used = 0;
       prof_bytes.clear();
     }
+    // ---- prompt logprobs: lm_head + forced-token sampler rows over the prompt positions of this step, S_max rows at a
+    // time (512x the decode logits work per prompt: rare, so it stays a simple separate pass on the same stream)
+    if (!prompt_rows.empty()) {
+      if (R == 0) {  // no sampled row this step -> the final norm has not run yet
+        CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
+        ++n_launches;
+      }
+      for (size_t off = 0; off < prompt_rows.size(); off += (size_t)S_max) {
+        const int m = (int)std::min<size_t>(S_max, prompt_rows.size() - off);
+        for (int i = 0; i < m; ++i) {
+          const PromptRow& pr = prompt_rows[off + i];
+          samplesrc[i] = pr.row;
+          SampleRow& row = rows[i];
+          memset(&row, 0, sizeof(row));
+          row.flags = SAMPLE_FORCED | SAMPLE_LOGPROBS;
+          row.n_topn = std::min<int>(pr.r->sp.prompt_logprobs, MAX_TOPN);
+          row.temperature = 1.f;
+          row.top_p = 1.f;
+          row.rep_penalty = 1.f;
+          row.eos_id = -1;
+          row.seq_slot = -1;
+          row.seed_lo = (uint32_t)pr.target;
+          row.logits_row = i;
+        }
+        CK(cudaMemcpyAsync(ds<int32_t>(off_samplesrc), samplesrc, sizeof(int32_t) * m, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(ds<SampleRow>(off_rows), rows, sizeof(SampleRow) * m, cudaMemcpyHostToDevice, stream));
+        CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, m, H, stream));
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, m, V, H, /*out_f32=*/1);
+        CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words, samp_scratch.p,
+                          d_samp_out.p, stream));
+        n_launches += 2;
+        CK(cudaMemcpyAsync(h_plp_out, d_samp_out.p, sizeof(SampleOut) * m, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (int i = 0; i < m; ++i) emit_prompt(*prompt_rows[off + i].r, prompt_rows[off + i].pos, h_plp_out[i]);
+      }
+    }
     return R;
   }
 
@@ -864,10 +915,31 @@ struct tgis_engine {
     }
     return true;
   }
+  void emit_prompt(const Request& r, int pos, const SampleOut& so) {
+    tgis_step_output o;
+    memset(&o, 0, sizeof(o));
+    snprintf(o.request_id, sizeof(o.request_id), "%s", r.id.c_str());
+    o.prompt_pos = pos;
+    o.token_id = so.token;
+    o.logprob = so.logprob;
+    o.rank = so.rank;
+    o.n_topn = so.n_topn;
+    for (int i = 0; i < o.n_topn; ++i) {
+      o.topn_ids[i] = so.topn_ids[i];
+      o.topn_logprobs[i] = so.topn_lps[i];
+    }
+    o.n_prompt_tokens = r.n_prompt;
+    o.ts_arrival = r.ts_arrival;
+    std::lock_guard<std::mutex> lk(mu);
+    outputs.push_back(o);
+    cv_out.notify_all();
+  }
+
   void emit(const Request& r, bool new_token, const SampleOut* so, int finish, int stop_tok) {
     tgis_step_output o;
     memset(&o, 0, sizeof(o));
     snprintf(o.request_id, sizeof(o.request_id), "%s", r.id.c_str());
+    o.prompt_pos = -1;
     o.n_new_tokens = new_token ? 1 : 0;
     if (new_token && so) {
       o.token_id = so->token;
@@ -1157,7 +1229,8 @@ int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_
   if (params->max_tokens < 1) return fail("max_tokens must be >= 1");
   if (params->n_stop_token_ids > TGIS_MAX_STOP_TOKEN_IDS || params->n_stop_token_ids < 0) return fail("too many stop token ids");
   if (!params->greedy && !(params->temperature > 0.f)) return fail("temperature must be > 0 when sampling");
-  if (params->num_logprobs > TGIS_MAX_TOPN) return fail("num_logprobs too large");
+  if (params->num_logprobs > TGIS_MAX_TOPN || params->prompt_logprobs > TGIS_MAX_TOPN) return fail("num_logprobs too large");
+  if (params->prompt_logprobs > 0 && e->tp > 1) return fail("prompt_logprobs is not supported with tensor parallelism yet");
   for (int i = 0; i < n_prompt; ++i)
     if (prompt_ids[i] < 0 || prompt_ids[i] >= e->cfg.vocab) return fail("prompt token id out of range");
   auto r = std::make_unique<Request>();

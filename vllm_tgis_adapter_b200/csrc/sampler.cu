@@ -269,14 +269,16 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   c.lenfac_m1 = (c.p.flags & SAMPLE_LENPEN) ? c.p.len_decay_factor : 0.f;
   c.mask_eos = c.p.n_out < c.p.min_tokens;
   c.typical = false;
-  const bool greedy = c.p.flags & SAMPLE_GREEDY;
+  // FORCED rows (prompt logprobs): the token is given, only its raw logprob / rank / top-n are wanted
+  const bool forced = (c.p.flags & SAMPLE_FORCED) != 0;
+  const bool greedy = (c.p.flags & SAMPLE_GREEDY) && !forced;
   const bool want_lp = (c.p.flags & SAMPLE_LOGPROBS) != 0;
   float* y = scratch + (size_t)r * V;  // processed logits (sampling rows only)
 
   // ---- pass 1: raw max / sum-exp (+ greedy argmax of the processed logits in the same sweep)
   MaxSum ms{-INFINITY, 0.f};
   ValIdx best{-INFINITY, -1};
-  const bool do_typ = (c.p.flags & SAMPLE_TYPICAL) != 0;
+  const bool do_typ = (c.p.flags & SAMPLE_TYPICAL) != 0 && !forced;
   const bool greedy_fast = greedy && !do_typ;  // argmax fused into the first sweep
   for (int i0 = threadIdx.x * 8; i0 < V; i0 += SAMP_THREADS * 8) {
     const float4 ra = *reinterpret_cast<const float4*>(c.x + i0);
@@ -325,7 +327,9 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
     }
   }
   int token;
-  if (greedy) {
+  if (forced) {
+    token = (int)c.p.seed_lo;
+  } else if (greedy) {
     if (!greedy_fast) {  // typical-p + greedy (method SAMPLE, temperature 0): argmax after the mask is known
       for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
         const float yy = process(c, i, load_x(c, i));

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_REQUEST_ID = 96
 MAX_TOPN = 12
 MAX_STOP_TOKEN_IDS = 8
@@ -48,6 +48,7 @@ class TgisStepOutput(C.Structure):
         ("topn_logprobs", C.c_float * MAX_TOPN), ("finish_reason", C.c_int32), ("stop_token_id", C.c_int32),
         ("n_prompt_tokens", C.c_int32), ("n_output_tokens", C.c_int32), ("ts_arrival", C.c_double),
         ("ts_first_scheduled", C.c_double), ("ts_first_token", C.c_double), ("ts_last_token", C.c_double),
+        ("prompt_pos", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -39,6 +39,8 @@ class _ReqState:
         self.queue = queue
         self.token_ids: list[int] = []
         self.logprobs: list[dict[int, Logprob]] = []
+        # vLLM layout: one entry per prompt token, entry 0 is None (grpc_server.py:438-449,721-724)
+        self.prompt_logprobs: list[dict[int, Logprob] | None] = [None] * len(prompt_ids)
         self.done = False
 
 
@@ -140,7 +142,8 @@ class AsyncTGISEngine:
             top_k=sp.top_k if sp.top_k and sp.top_k > 0 else 0, top_p=sp.top_p, typical_p=sp.typical_p,
             repetition_penalty=sp.repetition_penalty, length_penalty=sp.length_penalty,
             eos_token_id=eos if eos is not None else -1, min_tokens=sp.min_tokens, max_tokens=max_tokens,
-            num_logprobs=sp.logprobs or 0, seed=sp.seed if not sp.greedy else None,
+            num_logprobs=sp.logprobs or 0, prompt_logprobs=sp.prompt_logprobs or 0,
+            seed=sp.seed if not sp.greedy else None,
             stop_token_ids=sp.stop_token_ids)
         nid = f"q{next(self._ids)}"
         queue: asyncio.Queue = asyncio.Queue()
@@ -171,6 +174,12 @@ class AsyncTGISEngine:
                 stop_reason: int | str | None = None
                 last = batch[-1]
                 for o in batch:   # one engine step at a time: stop strings are evaluated per step (S10)
+                    if o.prompt_pos >= 1:   # prompt-logprob record (arrives before the first generated token)
+                        plp: dict[int, Logprob] = {o.token_id: Logprob(o.logprob, o.rank)}
+                        for r, (tid, tlp) in enumerate(o.topn, start=1):
+                            plp.setdefault(tid, Logprob(tlp, r))
+                        st.prompt_logprobs[o.prompt_pos] = plp
+                        continue
                     step_finish: str | None = None
                     if o.finish_reason != _lib.FINISH_NONE:
                         if o.finish_reason == _lib.FINISH_ERROR:
@@ -198,6 +207,8 @@ class AsyncTGISEngine:
                             stop_reason = o.stop_token_id
                         last = o
                         break
+                if all(o.prompt_pos >= 1 for o in batch):
+                    continue
                 finished = finish_reason is not None
                 if final_only and not finished:
                     continue
@@ -211,7 +222,8 @@ class AsyncTGISEngine:
                                          if last.ts_first_scheduled else None,
                                          finished_time=last.ts_last_token if finished else None)
                 yield RequestOutput(
-                    request_id=request_id, prompt=None, prompt_token_ids=prompt_ids, prompt_logprobs=None,
+                    request_id=request_id, prompt=None, prompt_token_ids=prompt_ids,
+                    prompt_logprobs=st.prompt_logprobs if sp.prompt_logprobs else None,
                     outputs=[CompletionOutput(index=0, text=text, token_ids=ids, logprobs=lps,
                                               finish_reason=finish_reason, stop_reason=stop_reason)],
                     finished=finished, metrics=metrics)

@@ -56,12 +56,14 @@ class StepOutput:
     ts_first_scheduled: float
     ts_first_token: float
     ts_last_token: float
+    prompt_pos: int = -1   # >= 1: prompt-logprob record for that prompt position
+    token_id: int = -1     # the token the record describes (generated token, or prompt token for prompt records)
 
 
 def make_sampling_params(*, greedy: bool = True, temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0,
                          typical_p: float = 0.0, repetition_penalty: float = 1.0,
                          length_penalty: tuple[int, float] | None = None, eos_token_id: int = 2, min_tokens: int = 0,
-                         max_tokens: int = 16, num_logprobs: int = 0, seed: int | None = None,
+                         max_tokens: int = 16, num_logprobs: int = 0, prompt_logprobs: int = 0, seed: int | None = None,
                          stop_token_ids: Iterable[int] = ()) -> TgisSamplingParams:
     sp = TgisSamplingParams()
     sp.greedy = 1 if greedy else 0
@@ -78,7 +80,7 @@ def make_sampling_params(*, greedy: bool = True, temperature: float = 1.0, top_k
     sp.min_tokens = int(min_tokens)
     sp.max_tokens = int(max_tokens)
     sp.num_logprobs = int(num_logprobs)
-    sp.prompt_logprobs = 0
+    sp.prompt_logprobs = int(prompt_logprobs)
     sp.has_seed = 1 if seed is not None else 0
     sp.seed = int(seed or 0)
     ids = list(stop_token_ids)
@@ -166,7 +168,7 @@ class NativeEngine:
                 topn=[(o.topn_ids[j], o.topn_logprobs[j]) for j in range(o.n_topn)],
                 finish_reason=o.finish_reason, stop_token_id=o.stop_token_id, n_prompt_tokens=o.n_prompt_tokens,
                 n_output_tokens=o.n_output_tokens, ts_arrival=o.ts_arrival, ts_first_scheduled=o.ts_first_scheduled,
-                ts_first_token=o.ts_first_token, ts_last_token=o.ts_last_token))
+                ts_first_token=o.ts_first_token, ts_last_token=o.ts_last_token, prompt_pos=o.prompt_pos, token_id=o.token_id))
         return outs
 
     def run_until_idle(self) -> int:
