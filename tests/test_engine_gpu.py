@@ -191,8 +191,10 @@ def test_prompt_logprobs_match_oracle(chunk):
             assert r.token_id == p[i]
             ref = float(lp[i - 1, p[i]])
             diffs.append(abs(r.logprob - ref))
-            ref_rank = int((lp[i - 1] >= lp[i - 1, p[i]]).sum())
-            assert abs(r.rank - ref_rank) <= max(2, ref_rank // 50), (r.rank, ref_rank)   # near-ties may swap
+            # rank = 1 + #(tokens with larger logprob): exact up to tokens within the bf16 noise band of this one
+            lo = int((lp[i - 1] > ref + 0.03).sum()) + 1
+            hi = int((lp[i - 1] >= ref - 0.03).sum())
+            assert lo <= r.rank <= hi, (r.rank, lo, hi)
             assert len(r.topn) == 3
             top = torch.topk(lp[i - 1], 3)
             assert r.topn[0][0] == int(top.indices[0]) or float(top.values[0] - top.values[1]) < 0.02

@@ -19,7 +19,7 @@
 
 namespace tgis {
 
-constexpr int DEC_TOK = DECODE_SPLIT;        // tokens per split (2 KV blocks: 36 KB smem/CTA -> 6 CTAs/SM in flight)
+constexpr int DEC_TOK = DECODE_SPLIT;        // tokens per split (8 KV blocks streamed through a 4-stage ring)
 constexpr int DEC_BLOCKS = DEC_TOK / KV_BLOCK;
 constexpr int TILE_BYTES = KV_BLOCK * HEAD_DIM * 2;  // 8192
 static_assert(DEC_TOK == DECODE_SPLIT, "split size mismatch");
@@ -36,8 +36,18 @@ __device__ __forceinline__ float warp_add(float v) {
 }
 
 // ================================================================================================ decode
+// Streaming flash-decoding.  One CTA = (sequence, 256-token split, kv head): a producer warp feeds a 4-stage ring of
+// KV blocks (one 8 KiB K tile + one 8 KiB V tile per stage, two 1-D TMA bulk copies completing on the stage's
+// mbarrier); four compute warps consume it: warps {0,1} take even blocks, {2,3} odd blocks, and inside a pair the
+// G query heads of the group are split between the two warps.  Every warp keeps an online-softmax state (m, l, o)
+// across its blocks, the two block lanes are combined through shared memory, and splits (kv_len > 256) are merged by
+// the last-arriving CTA in split order.  The split size is a constant, so the arithmetic of a sequence depends only
+// on its own length, never on what else is in the batch.
+constexpr int DEC_STAGES = 4;
+constexpr int DEC_THREADS = 160;  // 4 compute warps + 1 producer warp
+
 template <int G>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv_bfloat16* __restrict__ k_cache,
                    const __nv_bfloat16* __restrict__ v_cache, const AttnSeq* __restrict__ seqs,
                    const int32_t* __restrict__ seq_ids, const int32_t* __restrict__ block_table, int bt_stride,
@@ -46,12 +56,14 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   extern __shared__ __align__(128) uint8_t smem[];
   griddep_launch();
   griddep_wait();
-  uint8_t* kv_s = smem;                                                       // DEC_BLOCKS x (K 8K | V 8K)
-  float* q_s = reinterpret_cast<float*>(smem + DEC_BLOCKS * 2 * TILE_BYTES);  // [G][128]
-  float* p_s = q_s + G * HEAD_DIM;                                            // [4 warps][G][32]
-  float* ml_s = p_s + 4 * G * 32;                                             // [4 warps][G][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ml_s + 4 * G * 2);             // [DEC_BLOCKS]
-  int* flag_s = reinterpret_cast<int*>(bars + DEC_BLOCKS);
+  constexpr int GH = (G + 1) / 2;  // heads per warp of a pair
+  uint8_t* kv_s = smem;                                                        // DEC_STAGES x (K 8K | V 8K)
+  float* q_s = reinterpret_cast<float*>(smem + DEC_STAGES * 2 * TILE_BYTES);   // [G][128]
+  float* p_s = q_s + G * HEAD_DIM;                                             // [4 warps][GH][32]
+  float* ml_s = p_s + 4 * GH * 32;                                             // [2 lanes][G][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ml_s + 2 * G * 2);          // [DEC_STAGES]
+  uint64_t* empty_bar = full_bar + DEC_STAGES;                                 // [DEC_STAGES]
+  int* flag_s = reinterpret_cast<int*>(empty_bar + DEC_STAGES);
 
   const int sidx = blockIdx.x / max_splits, split = blockIdx.x % max_splits;
   const int kvh = blockIdx.y;
@@ -64,33 +76,43 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   const int n_blk = (n_tok + KV_BLOCK - 1) / KV_BLOCK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // Each warp owns one KV block and its mbarrier: lane 0 initialises the barrier and issues the two TMA bulk copies
-  // of its block, so the 4 block-table look-ups and 8 copies are issued in parallel with no CTA-wide barrier.
-  if (lane == 0 && warp < DEC_BLOCKS) {
-    mbar_init(&bars[warp], 1);
-    fence_barrier_init();
-    if (warp < n_blk) {
-      const int32_t blk = block_table[(size_t)sq.block_row * bt_stride + tok0 / KV_BLOCK + warp];
-      const size_t tile = ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM);
-      mbar_arrive_expect_tx(&bars[warp], 2 * TILE_BYTES);
-      bulk_load_1d(kv_s + warp * 2 * TILE_BYTES, k_cache + tile, TILE_BYTES, &bars[warp]);
-      bulk_load_1d(kv_s + warp * 2 * TILE_BYTES + TILE_BYTES, v_cache + tile, TILE_BYTES, &bars[warp]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DEC_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 2);  // the two warps of the pair that consumed the block
     }
+    fence_barrier_init();
   }
-  __syncwarp();
-  // stage the group's queries as fp32 (overlaps the TMA flight time)
+  __syncthreads();
+
+  if (warp == 4) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      const int32_t* bt = block_table + (size_t)sq.block_row * bt_stride + tok0 / KV_BLOCK;
+      for (int j = 0; j < n_blk; ++j) {
+        const int st = j & (DEC_STAGES - 1);
+        if (j >= DEC_STAGES) mbar_wait(&empty_bar[st], ((j / DEC_STAGES) - 1) & 1);
+        const size_t tile = ((size_t)bt[j] * n_kv + kvh) * (KV_BLOCK * HEAD_DIM);
+        mbar_arrive_expect_tx(&full_bar[st], 2 * TILE_BYTES);
+        bulk_load_1d(kv_s + st * 2 * TILE_BYTES, k_cache + tile, TILE_BYTES, &full_bar[st]);
+        bulk_load_1d(kv_s + st * 2 * TILE_BYTES + TILE_BYTES, v_cache + tile, TILE_BYTES, &full_bar[st]);
+      }
+    }
+    return;
+  }
+
+  // ===================== compute warps (128 threads) =====================
   {
     const __nv_bfloat16* q = qkv + (size_t)sq.q_start * qkv_ld + (size_t)kvh * G * HEAD_DIM;
     for (int i = threadIdx.x; i < G * HEAD_DIM; i += 128) q_s[i] = __bfloat162float(q[i]);
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
 
-  // Two warps share every KV block and split the group's G query heads between them (warp w and w+DEC_BLOCKS):
-  // both wait on the block's mbarrier, each runs QK^T / softmax / PV for its heads only.
-  constexpr int GH = (G + 1) / 2;          // heads per warp (first warp of the pair takes the larger half)
-  const int blk = warp % DEC_BLOCKS, half = warp / DEC_BLOCKS;
-  const int g0 = half * GH;                // first head of this warp
-  const int gh = half == 0 ? GH : G - GH;  // number of heads of this warp (0 possible when G == 1)
+  const int blane = warp >> 1, half = warp & 1;   // block lane (even / odd blocks), head half
+  const int g0 = half * GH;
+  const int gh = half == 0 ? GH : G - GH;         // heads of this warp (0 when G == 1 and half == 1)
+  const float* q_w = q_s + g0 * HEAD_DIM;
+  float* p_w = p_s + warp * GH * 32;
   float m_w[GH], l_w[GH], o_w[GH][4];
 #pragma unroll
   for (int g = 0; g < GH; ++g) {
@@ -99,102 +121,105 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
 #pragma unroll
     for (int e = 0; e < 4; ++e) o_w[g][e] = 0.f;
   }
+  const int lchunk = lane >> 1, lhalf = lane & 1;
 
-  if (blk < n_blk && gh > 0) {
-    const int valid = min(KV_BLOCK, n_tok - blk * KV_BLOCK);
-    mbar_wait(&bars[blk], 0);
-    const uint8_t* k_t = kv_s + blk * 2 * TILE_BYTES;
-    const uint8_t* v_t = k_t + TILE_BYTES;
-    const float* q_w = q_s + g0 * HEAD_DIM;
-    // ---- scores: lane = token
-    float s[GH];
+  for (int j = blane; j < n_blk; j += 2) {
+    const int st = j & (DEC_STAGES - 1);
+    mbar_wait(&full_bar[st], (j / DEC_STAGES) & 1);
+    if (gh > 0) {
+      const int valid = min(KV_BLOCK, n_tok - j * KV_BLOCK);
+      const uint8_t* k_t = kv_s + st * 2 * TILE_BYTES;
+      const uint8_t* v_t = k_t + TILE_BYTES;
+      // ---- scores: lane = token
+      float s[GH];
 #pragma unroll
-    for (int g = 0; g < GH; ++g) s[g] = 0.f;
+      for (int g = 0; g < GH; ++g) s[g] = 0.f;
 #pragma unroll 4
-    for (int c = 0; c < HEAD_DIM / 8; ++c) {
-      const uint4 kk = *reinterpret_cast<const uint4*>(k_t + (c * KV_BLOCK + lane) * 16);
-      float kf[8];
-      kf[0] = __uint_as_float(kk.x << 16); kf[1] = __uint_as_float(kk.x & 0xffff0000u);
-      kf[2] = __uint_as_float(kk.y << 16); kf[3] = __uint_as_float(kk.y & 0xffff0000u);
-      kf[4] = __uint_as_float(kk.z << 16); kf[5] = __uint_as_float(kk.z & 0xffff0000u);
-      kf[6] = __uint_as_float(kk.w << 16); kf[7] = __uint_as_float(kk.w & 0xffff0000u);
-#pragma unroll
-      for (int g = 0; g < GH; ++g) {
-        if (g < gh) {
-          const float4 qa = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8);
-          const float4 qb = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8 + 4);
-          s[g] += qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] +
-                  qb.z * kf[6] + qb.w * kf[7];
-        }
-      }
-    }
-    float* p_w = p_s + warp * GH * 32;
-#pragma unroll
-    for (int g = 0; g < GH; ++g) {
-      const float sv = (lane < valid && g < gh) ? s[g] * scale : -INFINITY;
-      m_w[g] = warp_max(sv);
-      const float p = (lane < valid && g < gh) ? __expf(sv - m_w[g]) : 0.f;
-      l_w[g] = warp_add(p);
-      p_w[g * 32 + lane] = p;
-    }
-    __syncwarp();
-    // ---- PV: lane = dims [lane*4, lane*4+4).  All 32 slots are processed unconditionally (p == 0 beyond `valid`, and
-    // cache slots always hold finite values), so the loop has a constant trip count and the loads pipeline.
-    const int lchunk = lane >> 1, lhalf = lane & 1;
-#pragma unroll 2
-    for (int tk0 = 0; tk0 < KV_BLOCK; tk0 += 4) {
-      uint2 vv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        vv[j] = *reinterpret_cast<const uint2*>(v_t + (tk0 + j) * (HEAD_DIM * 2) + ((lchunk ^ ((tk0 + j) & 7)) * 16) +
-                                                lhalf * 8);
-      float4 pp[GH];
-#pragma unroll
-      for (int g = 0; g < GH; ++g) pp[g] = *reinterpret_cast<const float4*>(p_w + g * 32 + tk0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v0 = __uint_as_float(vv[j].x << 16), v1 = __uint_as_float(vv[j].x & 0xffff0000u);
-        const float v2 = __uint_as_float(vv[j].y << 16), v3 = __uint_as_float(vv[j].y & 0xffff0000u);
+      for (int c = 0; c < HEAD_DIM / 8; ++c) {
+        const uint4 kk = *reinterpret_cast<const uint4*>(k_t + (c * KV_BLOCK + lane) * 16);
+        float kf[8];
+        kf[0] = __uint_as_float(kk.x << 16); kf[1] = __uint_as_float(kk.x & 0xffff0000u);
+        kf[2] = __uint_as_float(kk.y << 16); kf[3] = __uint_as_float(kk.y & 0xffff0000u);
+        kf[4] = __uint_as_float(kk.z << 16); kf[5] = __uint_as_float(kk.z & 0xffff0000u);
+        kf[6] = __uint_as_float(kk.w << 16); kf[7] = __uint_as_float(kk.w & 0xffff0000u);
 #pragma unroll
         for (int g = 0; g < GH; ++g) {
-          const float p = j == 0 ? pp[g].x : j == 1 ? pp[g].y : j == 2 ? pp[g].z : pp[g].w;
-          o_w[g][0] += p * v0; o_w[g][1] += p * v1; o_w[g][2] += p * v2; o_w[g][3] += p * v3;
+          if (g < gh) {
+            const float4 qa = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8);
+            const float4 qb = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8 + 4);
+            s[g] += qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] +
+                    qb.z * kf[6] + qb.w * kf[7];
+          }
         }
       }
-    }
-  }
-  // ---- combine.  The pair's partial o rows go into the block's K tile, which is dead once BOTH warps of the pair
-  // are past their QK^T loop -> pair barrier (named barrier 1 + blk, 64 threads) before the first write.
-  asm volatile("bar.sync %0, 64;\n" ::"r"(1 + blk) : "memory");
-  {
-    float* ow_s = reinterpret_cast<float*>(kv_s + blk * 2 * TILE_BYTES);  // [G][128] floats <= 4 KiB < 8 KiB
+      // ---- online softmax update (per head: running max m, running sum l, rescale of o)
+      float corr[GH];
 #pragma unroll
-    for (int g = 0; g < GH; ++g) {
-      if (g < gh) {
-        *reinterpret_cast<float4*>(ow_s + (g0 + g) * HEAD_DIM + lane * 4) =
-            make_float4(o_w[g][0], o_w[g][1], o_w[g][2], o_w[g][3]);
-        if (lane == 0) {
-          ml_s[(blk * G + g0 + g) * 2 + 0] = m_w[g];
-          ml_s[(blk * G + g0 + g) * 2 + 1] = l_w[g];
+      for (int g = 0; g < GH; ++g) {
+        const float sv = (lane < valid && g < gh) ? s[g] * scale : -INFINITY;
+        const float m_new = fmaxf(m_w[g], warp_max(sv));
+        corr[g] = (m_w[g] == -INFINITY) ? 0.f : __expf(m_w[g] - m_new);
+        const float p = (lane < valid && g < gh) ? __expf(sv - m_new) : 0.f;
+        l_w[g] = l_w[g] * corr[g] + warp_add(p);
+        m_w[g] = m_new;
+        p_w[g * 32 + lane] = p;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o_w[g][e] *= corr[g];
+      }
+      __syncwarp();
+      // ---- PV: lane = dims [lane*4, lane*4+4); all 32 slots unconditionally (p == 0 beyond `valid`, cache slots
+      // always hold finite values) -> constant trip count, loads pipeline
+#pragma unroll 2
+      for (int tk0 = 0; tk0 < KV_BLOCK; tk0 += 4) {
+        uint2 vv[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          vv[jj] = *reinterpret_cast<const uint2*>(v_t + (tk0 + jj) * (HEAD_DIM * 2) +
+                                                   ((lchunk ^ ((tk0 + jj) & 7)) * 16) + lhalf * 8);
+        float4 pp[GH];
+#pragma unroll
+        for (int g = 0; g < GH; ++g) pp[g] = *reinterpret_cast<const float4*>(p_w + g * 32 + tk0);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float v0 = __uint_as_float(vv[jj].x << 16), v1 = __uint_as_float(vv[jj].x & 0xffff0000u);
+          const float v2 = __uint_as_float(vv[jj].y << 16), v3 = __uint_as_float(vv[jj].y & 0xffff0000u);
+#pragma unroll
+          for (int g = 0; g < GH; ++g) {
+            const float p = jj == 0 ? pp[g].x : jj == 1 ? pp[g].y : jj == 2 ? pp[g].z : pp[g].w;
+            o_w[g][0] += p * v0; o_w[g][1] += p * v1; o_w[g][2] += p * v2; o_w[g][3] += p * v3;
+          }
         }
+      }
+      __syncwarp();  // p_w is rewritten by the next block of this warp
+    }
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
+  }
+  // ---- combine the two block lanes.  All blocks are consumed (no TMA write can still be in flight), so the ring
+  // memory is reused as staging: ow_s [2 lanes][G][128] floats.
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
+  float* ow_s = reinterpret_cast<float*>(kv_s);
+#pragma unroll
+  for (int g = 0; g < GH; ++g) {
+    if (g < gh) {
+      *reinterpret_cast<float4*>(ow_s + (blane * G + g0 + g) * HEAD_DIM + lane * 4) =
+          make_float4(o_w[g][0], o_w[g][1], o_w[g][2], o_w[g][3]);
+      if (lane == 0) {
+        ml_s[(blane * G + g0 + g) * 2 + 0] = m_w[g];
+        ml_s[(blane * G + g0 + g) * 2 + 1] = l_w[g];
       }
     }
   }
-  __syncthreads();
-  const int d = threadIdx.x;  // 128 threads = 128 dims
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
+  const int d = threadIdx.x;  // 128 compute threads = 128 dims
   float o_c[G], m_c[G], l_c[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    float m = -INFINITY;
-    for (int w = 0; w < DEC_BLOCKS; ++w) m = fmaxf(m, ml_s[(w * G + g) * 2]);
-    float l = 0.f, o = 0.f;
-    for (int w = 0; w < DEC_BLOCKS; ++w) {
-      const float mw = ml_s[(w * G + g) * 2];
-      const float f = (mw == -INFINITY) ? 0.f : __expf(mw - m);
-      l += ml_s[(w * G + g) * 2 + 1] * f;
-      o += reinterpret_cast<const float*>(kv_s + w * 2 * TILE_BYTES)[g * HEAD_DIM + d] * f;
-    }
-    o_c[g] = o; m_c[g] = m; l_c[g] = l;
+    const float m0 = ml_s[(0 * G + g) * 2], m1 = ml_s[(1 * G + g) * 2];
+    const float m = fmaxf(m0, m1);
+    const float f0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - m), f1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - m);
+    l_c[g] = ml_s[(0 * G + g) * 2 + 1] * f0 + ml_s[(1 * G + g) * 2 + 1] * f1;
+    o_c[g] = ow_s[(0 * G + g) * HEAD_DIM + d] * f0 + ow_s[(1 * G + g) * HEAD_DIM + d] * f1;
+    m_c[g] = m;
   }
   __nv_bfloat16* o_dst = out + (size_t)sq.q_start * out_ld + (size_t)kvh * G * HEAD_DIM;
   if (n_splits == 1) {
@@ -212,22 +237,21 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       part_ml[((pbase + split) * G + g) * 2 + 1] = l_c[g];
     }
   }
-  // publish: CTA barrier + one acq_rel atomic (cumulative over the barrier) instead of membar.gl on every thread
-  __syncthreads();
+  // publish: barrier + one acq_rel atomic (cumulative over the barrier) instead of membar.gl on every thread
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
   if (threadIdx.x == 0) {
     int old;
     asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;\n"
                  : "=r"(old) : "l"(counters + sidx * n_kv + kvh) : "memory");
     *flag_s = (old == n_splits - 1);
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
   if (!*flag_s) return;
-  // ---- last arriver: merge in split order.  (m, l) of every split are staged in smem by all threads in parallel
-  // (the K/V tiles are dead by now), then the o rows are fetched SPB splits at a time so that SPB*G L2 loads are in
-  // flight per thread instead of one.
-  float* ml_all = reinterpret_cast<float*>(kv_s + TILE_BYTES);  // block 0's dead V tile: [n_splits][G][2] <= 8 KiB
+  // ---- last arriver: (m, l) of every split staged in smem by all threads in parallel (ring memory, past ow_s), then the
+  // o rows fetched SPB splits at a time so that SPB*G L2 loads are in flight per thread
+  float* ml_all = reinterpret_cast<float*>(kv_s + 2 * TILE_BYTES);  // [n_splits][G][2]
   for (int i = threadIdx.x; i < n_splits * G * 2; i += 128) ml_all[i] = __ldcg(&part_ml[pbase * G * 2 + i]);
-  __syncthreads();
+  asm volatile("bar.sync 1, 128;\n" ::: "memory");
   float m_f[G], l_f[G], o_f[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -268,7 +292,8 @@ static cudaError_t decode_launch_g(const __nv_bfloat16* qkv, int qkv_ld, const _
                                    int n_seqs, const int32_t* block_table, int bt_stride, int max_splits,
                                    float* part_o, float* part_ml, int* counters, __nv_bfloat16* out, int out_ld,
                                    int n_kv, float scale, cudaStream_t stream) {
-  const int smem = DEC_BLOCKS * 2 * TILE_BYTES + (G * HEAD_DIM + 4 * G * 32 + 4 * G * 2) * 4 + DEC_BLOCKS * 8 + 16;
+  constexpr int GH = (G + 1) / 2;
+  const int smem = DEC_STAGES * 2 * TILE_BYTES + (G * HEAD_DIM + 4 * GH * 32 + 2 * G * 2) * 4 + 2 * DEC_STAGES * 8 + 16;
   static bool attr = false;
   if (!attr) {
     cudaError_t e =
@@ -277,8 +302,8 @@ static cudaError_t decode_launch_g(const __nv_bfloat16* qkv, int qkv_ld, const _
     attr = true;
   }
   dim3 grid(n_seqs * max_splits, n_kv);
-  return launch_k(attn_decode_kernel<G>, grid, dim3(128), smem, stream, qkv, qkv_ld, k_cache, v_cache, seqs, seq_ids,
-                  block_table, bt_stride, max_splits, part_o, part_ml, counters, out, out_ld, n_kv, scale);
+  return launch_k(attn_decode_kernel<G>, grid, dim3(DEC_THREADS), smem, stream, qkv, qkv_ld, k_cache, v_cache, seqs,
+                  seq_ids, block_table, bt_stride, max_splits, part_o, part_ml, counters, out, out_ld, n_kv, scale);
 }
 
 cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,

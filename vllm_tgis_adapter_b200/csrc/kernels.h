@@ -68,7 +68,7 @@ struct AttnSeq {        // one entry per sequence scheduled this step (device ar
   int32_t block_row;    // row in the block table
 };
 // Decode (q_len == 1): split-KV over chunks of DECODE_SPLIT tokens, GQA group packed per CTA.
-constexpr int DECODE_SPLIT = 64;
+constexpr int DECODE_SPLIT = 256;
 cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
                                const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs,
                                const int32_t* block_table, int bt_stride, int max_splits, float* part_o,
