@@ -35,6 +35,11 @@ int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* 
 int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev, const int32_t* seqs_host,
                      int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows, int32_t bt_stride, void* out_dev,
                      int32_t n_q, int32_t n_kv, float scale);
+/* decode-only, timed over `iters` launches rotating through n_layers cache copies; us_out = avg device us per launch */
+int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev,
+                           const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows,
+                           int32_t bt_stride, void* out_dev, int32_t n_q, int32_t n_kv, float scale, int32_t n_layers,
+                           int64_t layer_stride_bytes, int32_t iters, float* us_out);
 /* rows_host: n_rows x 64-byte SampleRow records (see csrc/kernels.h); out_host: n_rows x 112-byte SampleOut records;
  * seen_bitmap_dev: [slots][ceil(vocab/32)] uint32 or NULL */
 /* logits_dev: fp32 [rows, ld] */

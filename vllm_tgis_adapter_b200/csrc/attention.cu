@@ -13,6 +13,8 @@
 //                      last-arriving split combines partials in split order (deterministic).
 // prefill (q_len >= 1): grid (16-query tile, kv_head); one warp per query head of the group; mma.sync m16n8k16 with
 //                      online softmax; KV blocks double-buffered through smem by TMA bulk copies.
+#include <algorithm>
+
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -20,7 +22,6 @@
 namespace tgis {
 
 constexpr int DEC_TOK = DECODE_SPLIT;        // tokens per split (8 KV blocks streamed through a 4-stage ring)
-constexpr int DEC_BLOCKS = DEC_TOK / KV_BLOCK;
 constexpr int TILE_BYTES = KV_BLOCK * HEAD_DIM * 2;  // 8192
 static_assert(DEC_TOK == DECODE_SPLIT, "split size mismatch");
 
@@ -35,301 +36,6 @@ __device__ __forceinline__ float warp_add(float v) {
   return v;
 }
 
-// ================================================================================================ decode
-// Streaming flash-decoding.  One CTA = (sequence, 256-token split, kv head): a producer warp feeds a 4-stage ring of
-// KV blocks (one 8 KiB K tile + one 8 KiB V tile per stage, two 1-D TMA bulk copies completing on the stage's
-// mbarrier); four compute warps consume it: warps {0,1} take even blocks, {2,3} odd blocks, and inside a pair the
-// G query heads of the group are split between the two warps.  Every warp keeps an online-softmax state (m, l, o)
-// across its blocks, the two block lanes are combined through shared memory, and splits (kv_len > 256) are merged by
-// the last-arriving CTA in split order.  The split size is a constant, so the arithmetic of a sequence depends only
-// on its own length, never on what else is in the batch.
-constexpr int DEC_STAGES = 4;
-constexpr int DEC_THREADS = 160;  // 4 compute warps + 1 producer warp
-
-template <int G>
-__global__ void __launch_bounds__(DEC_THREADS)
-attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv_bfloat16* __restrict__ k_cache,
-                   const __nv_bfloat16* __restrict__ v_cache, const AttnSeq* __restrict__ seqs,
-                   const int32_t* __restrict__ seq_ids, const int32_t* __restrict__ block_table, int bt_stride,
-                   int max_splits, float* __restrict__ part_o, float* __restrict__ part_ml,
-                   int* __restrict__ counters, __nv_bfloat16* __restrict__ out, int out_ld, int n_kv, float scale) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  griddep_launch();
-  griddep_wait();
-  constexpr int GH = (G + 1) / 2;  // heads per warp of a pair
-  uint8_t* kv_s = smem;                                                        // DEC_STAGES x (K 8K | V 8K)
-  float* q_s = reinterpret_cast<float*>(smem + DEC_STAGES * 2 * TILE_BYTES);   // [G][128]
-  float* p_s = q_s + G * HEAD_DIM;                                             // [4 warps][GH][32]
-  float* ml_s = p_s + 4 * GH * 32;                                             // [2 lanes][G][2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ml_s + 2 * G * 2);          // [DEC_STAGES]
-  uint64_t* empty_bar = full_bar + DEC_STAGES;                                 // [DEC_STAGES]
-  int* flag_s = reinterpret_cast<int*>(empty_bar + DEC_STAGES);
-
-  const int sidx = blockIdx.x / max_splits, split = blockIdx.x % max_splits;
-  const int kvh = blockIdx.y;
-  const AttnSeq sq = seqs[seq_ids ? seq_ids[sidx] : sidx];  // engine: decode sequences are entries 0..n-1
-  const int kv_len = sq.kv_len;
-  const int n_splits = (kv_len + DEC_TOK - 1) / DEC_TOK;
-  if (split >= n_splits) return;
-  const int tok0 = split * DEC_TOK;
-  const int n_tok = min(DEC_TOK, kv_len - tok0);
-  const int n_blk = (n_tok + KV_BLOCK - 1) / KV_BLOCK;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < DEC_STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 2);  // the two warps of the pair that consumed the block
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  if (warp == 4) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      const int32_t* bt = block_table + (size_t)sq.block_row * bt_stride + tok0 / KV_BLOCK;
-      for (int j = 0; j < n_blk; ++j) {
-        const int st = j & (DEC_STAGES - 1);
-        if (j >= DEC_STAGES) mbar_wait(&empty_bar[st], ((j / DEC_STAGES) - 1) & 1);
-        const size_t tile = ((size_t)bt[j] * n_kv + kvh) * (KV_BLOCK * HEAD_DIM);
-        mbar_arrive_expect_tx(&full_bar[st], 2 * TILE_BYTES);
-        bulk_load_1d(kv_s + st * 2 * TILE_BYTES, k_cache + tile, TILE_BYTES, &full_bar[st]);
-        bulk_load_1d(kv_s + st * 2 * TILE_BYTES + TILE_BYTES, v_cache + tile, TILE_BYTES, &full_bar[st]);
-      }
-    }
-    return;
-  }
-
-  // ===================== compute warps (128 threads) =====================
-  {
-    const __nv_bfloat16* q = qkv + (size_t)sq.q_start * qkv_ld + (size_t)kvh * G * HEAD_DIM;
-    for (int i = threadIdx.x; i < G * HEAD_DIM; i += 128) q_s[i] = __bfloat162float(q[i]);
-  }
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");
-
-  const int blane = warp >> 1, half = warp & 1;   // block lane (even / odd blocks), head half
-  const int g0 = half * GH;
-  const int gh = half == 0 ? GH : G - GH;         // heads of this warp (0 when G == 1 and half == 1)
-  const float* q_w = q_s + g0 * HEAD_DIM;
-  float* p_w = p_s + warp * GH * 32;
-  float m_w[GH], l_w[GH], o_w[GH][4];
-#pragma unroll
-  for (int g = 0; g < GH; ++g) {
-    m_w[g] = -INFINITY;
-    l_w[g] = 0.f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o_w[g][e] = 0.f;
-  }
-  const int lchunk = lane >> 1, lhalf = lane & 1;
-
-  for (int j = blane; j < n_blk; j += 2) {
-    const int st = j & (DEC_STAGES - 1);
-    mbar_wait(&full_bar[st], (j / DEC_STAGES) & 1);
-    if (gh > 0) {
-      const int valid = min(KV_BLOCK, n_tok - j * KV_BLOCK);
-      const uint8_t* k_t = kv_s + st * 2 * TILE_BYTES;
-      const uint8_t* v_t = k_t + TILE_BYTES;
-      // ---- scores: lane = token
-      float s[GH];
-#pragma unroll
-      for (int g = 0; g < GH; ++g) s[g] = 0.f;
-#pragma unroll 4
-      for (int c = 0; c < HEAD_DIM / 8; ++c) {
-        const uint4 kk = *reinterpret_cast<const uint4*>(k_t + (c * KV_BLOCK + lane) * 16);
-        float kf[8];
-        kf[0] = __uint_as_float(kk.x << 16); kf[1] = __uint_as_float(kk.x & 0xffff0000u);
-        kf[2] = __uint_as_float(kk.y << 16); kf[3] = __uint_as_float(kk.y & 0xffff0000u);
-        kf[4] = __uint_as_float(kk.z << 16); kf[5] = __uint_as_float(kk.z & 0xffff0000u);
-        kf[6] = __uint_as_float(kk.w << 16); kf[7] = __uint_as_float(kk.w & 0xffff0000u);
-#pragma unroll
-        for (int g = 0; g < GH; ++g) {
-          if (g < gh) {
-            const float4 qa = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8);
-            const float4 qb = *reinterpret_cast<const float4*>(q_w + g * HEAD_DIM + c * 8 + 4);
-            s[g] += qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] +
-                    qb.z * kf[6] + qb.w * kf[7];
-          }
-        }
-      }
-      // ---- online softmax update (per head: running max m, running sum l, rescale of o)
-      float corr[GH];
-#pragma unroll
-      for (int g = 0; g < GH; ++g) {
-        const float sv = (lane < valid && g < gh) ? s[g] * scale : -INFINITY;
-        const float m_new = fmaxf(m_w[g], warp_max(sv));
-        corr[g] = (m_w[g] == -INFINITY) ? 0.f : __expf(m_w[g] - m_new);
-        const float p = (lane < valid && g < gh) ? __expf(sv - m_new) : 0.f;
-        l_w[g] = l_w[g] * corr[g] + warp_add(p);
-        m_w[g] = m_new;
-        p_w[g * 32 + lane] = p;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o_w[g][e] *= corr[g];
-      }
-      __syncwarp();
-      // ---- PV: lane = dims [lane*4, lane*4+4); all 32 slots unconditionally (p == 0 beyond `valid`, cache slots
-      // always hold finite values) -> constant trip count, loads pipeline
-#pragma unroll 2
-      for (int tk0 = 0; tk0 < KV_BLOCK; tk0 += 4) {
-        uint2 vv[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          vv[jj] = *reinterpret_cast<const uint2*>(v_t + (tk0 + jj) * (HEAD_DIM * 2) +
-                                                   ((lchunk ^ ((tk0 + jj) & 7)) * 16) + lhalf * 8);
-        float4 pp[GH];
-#pragma unroll
-        for (int g = 0; g < GH; ++g) pp[g] = *reinterpret_cast<const float4*>(p_w + g * 32 + tk0);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const float v0 = __uint_as_float(vv[jj].x << 16), v1 = __uint_as_float(vv[jj].x & 0xffff0000u);
-          const float v2 = __uint_as_float(vv[jj].y << 16), v3 = __uint_as_float(vv[jj].y & 0xffff0000u);
-#pragma unroll
-          for (int g = 0; g < GH; ++g) {
-            const float p = jj == 0 ? pp[g].x : jj == 1 ? pp[g].y : jj == 2 ? pp[g].z : pp[g].w;
-            o_w[g][0] += p * v0; o_w[g][1] += p * v1; o_w[g][2] += p * v2; o_w[g][3] += p * v3;
-          }
-        }
-      }
-      __syncwarp();  // p_w is rewritten by the next block of this warp
-    }
-    if (lane == 0) mbar_arrive(&empty_bar[st]);
-  }
-  // ---- combine the two block lanes.  All blocks are consumed (no TMA write can still be in flight), so the ring
-  // memory is reused as staging: ow_s [2 lanes][G][128] floats.
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");
-  float* ow_s = reinterpret_cast<float*>(kv_s);
-#pragma unroll
-  for (int g = 0; g < GH; ++g) {
-    if (g < gh) {
-      *reinterpret_cast<float4*>(ow_s + (blane * G + g0 + g) * HEAD_DIM + lane * 4) =
-          make_float4(o_w[g][0], o_w[g][1], o_w[g][2], o_w[g][3]);
-      if (lane == 0) {
-        ml_s[(blane * G + g0 + g) * 2 + 0] = m_w[g];
-        ml_s[(blane * G + g0 + g) * 2 + 1] = l_w[g];
-      }
-    }
-  }
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");
-  const int d = threadIdx.x;  // 128 compute threads = 128 dims
-  float o_c[G], m_c[G], l_c[G];
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const float m0 = ml_s[(0 * G + g) * 2], m1 = ml_s[(1 * G + g) * 2];
-    const float m = fmaxf(m0, m1);
-    const float f0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - m), f1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - m);
-    l_c[g] = ml_s[(0 * G + g) * 2 + 1] * f0 + ml_s[(1 * G + g) * 2 + 1] * f1;
-    o_c[g] = ow_s[(0 * G + g) * HEAD_DIM + d] * f0 + ow_s[(1 * G + g) * HEAD_DIM + d] * f1;
-    m_c[g] = m;
-  }
-  __nv_bfloat16* o_dst = out + (size_t)sq.q_start * out_ld + (size_t)kvh * G * HEAD_DIM;
-  if (n_splits == 1) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) o_dst[g * HEAD_DIM + d] = __float2bfloat16_rn(o_c[g] / l_c[g]);
-    return;
-  }
-  // ---- multi-split: publish partial, last arriver merges in split order
-  const size_t pbase = ((size_t)(sidx * n_kv + kvh) * max_splits);
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    part_o[((pbase + split) * G + g) * HEAD_DIM + d] = o_c[g];
-    if (d == 0) {
-      part_ml[((pbase + split) * G + g) * 2 + 0] = m_c[g];
-      part_ml[((pbase + split) * G + g) * 2 + 1] = l_c[g];
-    }
-  }
-  // publish: barrier + one acq_rel atomic (cumulative over the barrier) instead of membar.gl on every thread
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");
-  if (threadIdx.x == 0) {
-    int old;
-    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;\n"
-                 : "=r"(old) : "l"(counters + sidx * n_kv + kvh) : "memory");
-    *flag_s = (old == n_splits - 1);
-  }
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");
-  if (!*flag_s) return;
-  // ---- last arriver: (m, l) of every split staged in smem by all threads in parallel (ring memory, past ow_s), then the
-  // o rows fetched SPB splits at a time so that SPB*G L2 loads are in flight per thread
-  float* ml_all = reinterpret_cast<float*>(kv_s + 2 * TILE_BYTES);  // [n_splits][G][2]
-  for (int i = threadIdx.x; i < n_splits * G * 2; i += 128) ml_all[i] = __ldcg(&part_ml[pbase * G * 2 + i]);
-  asm volatile("bar.sync 1, 128;\n" ::: "memory");
-  float m_f[G], l_f[G], o_f[G];
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    float m = -INFINITY;
-    for (int sp = 0; sp < n_splits; ++sp) m = fmaxf(m, ml_all[(sp * G + g) * 2]);
-    m_f[g] = m;
-    l_f[g] = 0.f;
-    o_f[g] = 0.f;
-  }
-  constexpr int SPB = 4;
-  for (int sp0 = 0; sp0 < n_splits; sp0 += SPB) {
-    float ov[SPB][G];
-#pragma unroll
-    for (int j = 0; j < SPB; ++j)
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-        ov[j][g] = (sp0 + j < n_splits) ? __ldcg(&part_o[((pbase + sp0 + j) * G + g) * HEAD_DIM + d]) : 0.f;
-#pragma unroll
-    for (int j = 0; j < SPB; ++j) {
-      if (sp0 + j < n_splits) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float f = __expf(ml_all[((sp0 + j) * G + g) * 2] - m_f[g]);
-          l_f[g] += ml_all[((sp0 + j) * G + g) * 2 + 1] * f;
-          o_f[g] += ov[j][g] * f;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < G; ++g) o_dst[g * HEAD_DIM + d] = __float2bfloat16_rn(o_f[g] / l_f[g]);
-  if (threadIdx.x == 0) counters[sidx * n_kv + kvh] = 0;
-}
-
-template <int G>
-static cudaError_t decode_launch_g(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
-                                   const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* seq_ids,
-                                   int n_seqs, const int32_t* block_table, int bt_stride, int max_splits,
-                                   float* part_o, float* part_ml, int* counters, __nv_bfloat16* out, int out_ld,
-                                   int n_kv, float scale, cudaStream_t stream) {
-  constexpr int GH = (G + 1) / 2;
-  const int smem = DEC_STAGES * 2 * TILE_BYTES + (G * HEAD_DIM + 4 * GH * 32 + 2 * G * 2) * 4 + 2 * DEC_STAGES * 8 + 16;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e =
-        cudaFuncSetAttribute(attn_decode_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  dim3 grid(n_seqs * max_splits, n_kv);
-  return launch_k(attn_decode_kernel<G>, grid, dim3(DEC_THREADS), smem, stream, qkv, qkv_ld, k_cache, v_cache, seqs,
-                  seq_ids, block_table, bt_stride, max_splits, part_o, part_ml, counters, out, out_ld, n_kv, scale);
-}
-
-cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
-                               const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs,
-                               const int32_t* block_table, int bt_stride, int max_splits, float* part_o,
-                               float* part_ml, int* counters, __nv_bfloat16* out, int out_ld, int n_q, int n_kv,
-                               float scale, cudaStream_t stream) {
-  if (n_seqs <= 0) return cudaSuccess;
-  if (n_q % n_kv != 0) return cudaErrorInvalidValue;
-  const int G = n_q / n_kv;
-#define TGIS_DEC(GG)                                                                                            \
-  case GG:                                                                                                      \
-    return decode_launch_g<GG>(qkv, qkv_ld, k_cache, v_cache, seqs, seq_ids, n_seqs, block_table, bt_stride,     \
-                               max_splits, part_o, part_ml, counters, out, out_ld, n_kv, scale, stream)
-  switch (G) {
-    TGIS_DEC(1);
-    TGIS_DEC(2);
-    TGIS_DEC(3);
-    TGIS_DEC(4);
-    TGIS_DEC(8);
-    default: return cudaErrorInvalidValue;
-  }
-#undef TGIS_DEC
-}
-
-// ================================================================================================ prefill
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -346,6 +52,363 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                : "r"(addr));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+// ================================================================================================ decode
+// Persistent, warp-granular flash-decoding on the tensor cores.
+//
+// Work item = (sequence, 128-token split, kv head); the host lists the (sequence, split) entries of the step
+// (DecItem), the kv head is the fastest index.  The grid is 2 CTAs per SM x 4 warps, and every WARP walks its own
+// strided slice of the item list, alone: no CTA-wide synchronisation exists after the barrier initialisation.
+// A warp owns a ring of three 8 KiB tile buffers fed by 1-D TMA bulk copies (K0 V0 K1 V1 ... of its items, the
+// stream does not stop at item boundaries) and a Q buffer; the copy of tile t+3 is requested the moment tile t has
+// been consumed, and the next item's metadata / block ids are fetched one item / one block ahead, so a warp keeps
+// 16-24 KiB in flight while it computes and never waits on a dependent global load in steady state (8 warps per SM).
+//
+// Per 32-token block: the G query heads are rows 0..G-1 of an m16n8k16 A operand (other rows zero); S = Q K^T is 32
+// MMAs with K B-fragments straight from the chunk-major tile by ldmatrix; P (bf16 hi + lo) V is 64 MMAs with
+// ldmatrix.trans on the swizzled V tile; the online-softmax state (m, l, o) stays in registers for the whole item.
+// kv_len > 128: the warp stores its (o, m, l) partial and attn_merge_kernel (next launch, PDL-chained) merges the
+// splits in split order: no atomics or fences in the streaming kernel (a per-item release fence cost 20 % of its
+// time).  The split size is a constant, so the arithmetic of a sequence depends only on its own length, never on what
+// else is in the batch or on which warp ran it.
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_THREADS = DEC_WARPS * 32;
+constexpr int DEC_RING = 3;
+constexpr int DEC_Q_BYTES = 8 * HEAD_DIM * 2;                           // up to 8 heads
+constexpr int DEC_WARP_SMEM = DEC_RING * TILE_BYTES + DEC_Q_BYTES;      // 26 KiB
+constexpr int DEC_SMEM = DEC_WARPS * DEC_WARP_SMEM + DEC_WARPS * 4 * 8; // + 4 mbarriers per warp
+
+template <int G>
+__global__ void __launch_bounds__(DEC_THREADS, 2)
+attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv_bfloat16* __restrict__ k_cache,
+                   const __nv_bfloat16* __restrict__ v_cache, const DecItem* __restrict__ items,
+                   int max_splits, float* __restrict__ part_o, float* __restrict__ part_ml,
+                   __nv_bfloat16* __restrict__ out, int out_ld, int n_kv, float scale) {
+  static_assert(G <= 8, "query heads of a group are rows 0..7 of the MMA tile");
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = smem + warp * DEC_WARP_SMEM;
+  uint8_t* q_s = ring + DEC_RING * TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + DEC_WARPS * DEC_WARP_SMEM) + warp * 4;  // [3] tiles, [3] = Q
+  uint64_t* q_bar = full + 3;
+  if (lane == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  griddep_launch();
+
+  // ---- item list: host-written for this step, not produced by a preceding kernel -> readable before griddep_wait
+  const int4* it4 = reinterpret_cast<const int4*>(items);  // record e = it4[2e] (q_row, kv_len, seq_split, -), it4[2e+1] (blocks)
+  const int n_flat = it4[0].x * n_kv;
+  const int n_slots = gridDim.x * DEC_WARPS;
+  int f = warp * gridDim.x + blockIdx.x;  // consecutive items land on different SMs
+  if (f >= n_flat) return;
+  auto item_at = [&](int ff) { return __ldg(&it4[2 * (1 + ff / n_kv)]); };
+  auto blocks_at = [&](int ff) { return __ldg(&it4[2 * (1 + ff / n_kv) + 1]); };
+  auto n_blk_of = [&](const int4& it) {
+    const int n_tok = min(DEC_TOK, it.y - (it.z >> 16) * DEC_TOK);
+    return (n_tok + KV_BLOCK - 1) / KV_BLOCK;
+  };
+  auto pick = [](const int4& b, int j) { return j == 0 ? b.x : j == 1 ? b.y : j == 2 ? b.z : b.w; };
+  int4 c_it = item_at(f);
+  int4 c_nxt = c_it;
+  // ---- issue cursor: runs DEC_RING tiles ahead of consumption, across item boundaries
+  int i_f = f, i_kvh = f % n_kv, i_jb = 0, i_nblk = n_blk_of(c_it), i_kv = 0, i_buf = 0;
+  int4 i_nxt = c_it, i_blks = blocks_at(f), i_blks_nxt = i_blks;  // block ids of the item being issued / the next one
+  if (f + n_slots < n_flat) {
+    i_nxt = item_at(f + n_slots);
+    i_blks_nxt = blocks_at(f + n_slots);
+  }
+  auto issue_tile = [&]() {
+    if (i_f >= n_flat) return;
+    if (lane == 0) {
+      const __nv_bfloat16* src =
+          (i_kv ? v_cache : k_cache) + ((size_t)pick(i_blks, i_jb) * n_kv + i_kvh) * (KV_BLOCK * HEAD_DIM);
+      mbar_arrive_expect_tx(&full[i_buf], TILE_BYTES);
+      bulk_load_1d(ring + i_buf * TILE_BYTES, src, TILE_BYTES, &full[i_buf]);
+    }
+    i_buf = i_buf == DEC_RING - 1 ? 0 : i_buf + 1;
+    if (i_kv == 0) {
+      i_kv = 1;
+      return;
+    }
+    i_kv = 0;
+    if (++i_jb == i_nblk) {  // next item of this warp; its record was requested one item ago
+      i_f += n_slots;
+      if (i_f >= n_flat) return;
+      i_kvh = i_f % n_kv;
+      i_jb = 0;
+      i_nblk = n_blk_of(i_nxt);
+      i_blks = i_blks_nxt;
+      if (i_f + n_slots < n_flat) {
+        i_nxt = item_at(i_f + n_slots);
+        i_blks_nxt = blocks_at(i_f + n_slots);
+      }
+    }
+  };
+  auto issue_q = [&](const int4& it, int kvh) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_bar, G * HEAD_DIM * 2);
+      bulk_load_1d(q_s, qkv + (size_t)it.x * qkv_ld + (size_t)kvh * G * HEAD_DIM, G * HEAD_DIM * 2, q_bar);
+    }
+  };
+
+  griddep_wait();  // q and the newest cache slot come from the preceding kernels
+  issue_q(c_it, f % n_kv);
+#pragma unroll
+  for (int i = 0; i < DEC_RING; ++i) issue_tile();
+
+  const int hr = lane >> 2, t4 = lane & 3;
+  const int mi = lane >> 3, ri = lane & 7;          // ldmatrix: lane -> (matrix, row)
+  const float sl2 = scale * 1.4426950408889634f;    // exp2 domain
+  const uint32_t ring_base = smem_u32(ring);
+  int c_buf = 0, c_ph = 0, q_ph = 0;
+
+  for (; f < n_flat; f += n_slots) {
+    const int kvh = f % n_kv;
+    const int seq = c_it.z & 0xffff, split = c_it.z >> 16;
+    const int kv_len = c_it.y;
+    const int n_splits = (kv_len + DEC_TOK - 1) / DEC_TOK;
+    const int n_tok = min(DEC_TOK, kv_len - split * DEC_TOK);
+    const int n_blk = (n_tok + KV_BLOCK - 1) / KV_BLOCK;
+    const bool has_next = f + n_slots < n_flat;
+    if (has_next) c_nxt = item_at(f + n_slots);
+    // ---- Q as A fragments: row = head (lane/4), 8 k-steps of 16 dims; rows >= G and rows 8..15 are zero
+    mbar_wait(q_bar, q_ph);
+    q_ph ^= 1;
+    uint32_t qa[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint8_t* qp = q_s + (hr * HEAD_DIM + ks * 16 + t4 * 2) * 2;
+      qa[ks][0] = hr < G ? *reinterpret_cast<const uint32_t*>(qp) : 0u;
+      qa[ks][2] = hr < G ? *reinterpret_cast<const uint32_t*>(qp + 16) : 0u;
+      qa[ks][1] = 0u;
+      qa[ks][3] = 0u;
+    }
+    float o[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_r = -INFINITY, l_r = 0.f;  // l_r: this thread's share of the row sum (quad-reduced at the end)
+
+    for (int jb = 0; jb < n_blk; ++jb) {
+      // ---- S = Q K^T : 4 n-tiles (8 tokens) x 8 k-steps (16 dims = chunks 2ks, 2ks+1); one ldmatrix.x4 = B fragments
+      // of two n-tiles: matrices (chunk 2ks, nt), (chunk 2ks+1, nt), (chunk 2ks, nt+1), (chunk 2ks+1, nt+1)
+      mbar_wait(&full[c_buf], c_ph);
+      const uint32_t k_base = ring_base + c_buf * TILE_BYTES;
+      float s[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+        for (int nt = 0; nt < 4; nt += 2) {
+          uint32_t kb[4];
+          ldmatrix_x4(kb, k_base + (((2 * ks + (mi & 1)) * KV_BLOCK) + (nt + (mi >> 1)) * 8 + ri) * 16);
+          mma_bf16_16816(s[nt], qa[ks], kb[0], kb[1]);
+          mma_bf16_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
+        }
+      }
+      __syncwarp();
+      issue_tile();  // refills the K buffer just consumed (tile t + 3 of this warp's stream)
+      if (++c_buf == DEC_RING) { c_buf = 0; c_ph ^= 1; }
+      if (jb == 0) {  // q_s was copied to registers above; by now the next item's record has arrived
+        __syncwarp();
+        if (has_next) issue_q(c_nxt, (f + n_slots) % n_kv);
+      }
+      // ---- online softmax for head hr over tokens nt*8 + t4*2 + {0,1}
+      const int valid = min(KV_BLOCK, n_tok - jb * KV_BLOCK);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          s[nt][e] = (nt * 8 + t4 * 2 + e < valid) ? s[nt][e] * sl2 : -INFINITY;
+          mx = fmaxf(mx, s[nt][e]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_r, mx);  // finite: token 0 of every block of the split is valid
+      const float corr = (m_r == -INFINITY) ? 0.f : exp2f(m_r - m_new);
+      m_r = m_new;
+      l_r *= corr;
+      uint32_t pa[2][4], pl[2][4];  // P as bf16 hi + bf16 lo (two MMAs): ~16 mantissa bits, tracks the fp32 oracle
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float p0 = exp2f(s[nt][0] - m_new), p1 = exp2f(s[nt][1] - m_new);
+        l_r += p0 + p1;
+        const int kk = nt >> 1, hi = nt & 1;
+        pa[kk][hi * 2] = pack_bf16x2(p0, p1);
+        pl[kk][hi * 2] = pack_bf16x2(p0 - bf16_round(p0), p1 - bf16_round(p1));
+        pa[kk][hi * 2 + 1] = 0u;
+        pl[kk][hi * 2 + 1] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        o[i][0] *= corr;
+        o[i][1] *= corr;
+      }
+      // ---- O += P V : 2 k-steps (16 tokens) x 16 n-tiles (8 dims); V B-fragments by ldmatrix.trans: matrices
+      // (tok lo, nd), (tok hi, nd), (tok lo, nd+1), (tok hi, nd+1).  Slots >= valid carry p = 0 (cache slots finite).
+      mbar_wait(&full[c_buf], c_ph);
+      const uint32_t v_base = ring_base + c_buf * TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+        for (int nd = 0; nd < 16; nd += 2) {
+          const int tok = kk * 16 + (mi & 1) * 8 + ri;
+          const int chunk = nd + (mi >> 1);
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, v_base + tok * (HEAD_DIM * 2) + ((chunk ^ (tok & 7)) * 16));
+          mma_bf16_16816(o[nd], pa[kk], vb[0], vb[1]);
+          mma_bf16_16816(o[nd + 1], pa[kk], vb[2], vb[3]);
+          mma_bf16_16816(o[nd], pl[kk], vb[0], vb[1]);
+          mma_bf16_16816(o[nd + 1], pl[kk], vb[2], vb[3]);
+        }
+      }
+      __syncwarp();
+      issue_tile();
+      if (++c_buf == DEC_RING) { c_buf = 0; c_ph ^= 1; }
+    }
+    l_r += __shfl_xor_sync(0xffffffffu, l_r, 1);
+    l_r += __shfl_xor_sync(0xffffffffu, l_r, 2);
+
+    // ---- item epilogue.  This thread: head hr, dims nd*8 + t4*2 + {0,1}
+    __nv_bfloat16* o_dst = out + (size_t)c_it.x * out_ld + (size_t)(kvh * G + hr) * HEAD_DIM + t4 * 2;
+    if (n_splits == 1) {
+      if (hr < G) {
+        const float inv = 1.f / l_r;
+#pragma unroll
+        for (int nd = 0; nd < 16; ++nd)
+          *reinterpret_cast<__nv_bfloat162*>(o_dst + nd * 8) = __floats2bfloat162_rn(o[nd][0] * inv, o[nd][1] * inv);
+      }
+    } else {
+      // store the partial (m in the exp2 domain); attn_merge_kernel combines the splits in split order
+      const size_t pbase = (size_t)(seq * n_kv + kvh) * max_splits;
+      if (hr < G) {
+        float* po = part_o + ((pbase + split) * G + hr) * HEAD_DIM + t4 * 2;
+#pragma unroll
+        for (int nd = 0; nd < 16; ++nd) *reinterpret_cast<float2*>(po + nd * 8) = make_float2(o[nd][0], o[nd][1]);
+        if (t4 == 0) *reinterpret_cast<float2*>(part_ml + ((pbase + split) * G + hr) * 2) = make_float2(m_r, l_r);
+      }
+    }
+    c_it = c_nxt;
+  }
+}
+
+// Split merge: one CTA per (decode sequence, kv head) with more than one split, thread = dim.  Reads the partials in
+// split order (deterministic), writes the normalised bf16 rows.
+template <int G>
+__global__ void __launch_bounds__(HEAD_DIM)
+attn_merge_kernel(const AttnSeq* __restrict__ seqs, const int32_t* __restrict__ seq_ids, int max_splits,
+                  const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                  __nv_bfloat16* __restrict__ out, int out_ld, int n_kv) {
+  __shared__ float ml_s[64 * G * 2];
+  griddep_launch();
+  const int sidx = blockIdx.x, kvh = blockIdx.y, d = threadIdx.x;
+  const AttnSeq sq = seqs[seq_ids ? seq_ids[sidx] : sidx];  // host-written
+  const int n_splits = (sq.kv_len + DEC_TOK - 1) / DEC_TOK;
+  if (n_splits == 1) return;  // the streaming kernel wrote the row itself
+  griddep_wait();
+  const size_t pbase = (size_t)(sidx * n_kv + kvh) * max_splits;
+  float m_f[G], l_f[G], o_f[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) m_f[g] = -INFINITY, l_f[g] = 0.f, o_f[g] = 0.f;
+  // pass 1: row maxima (the (m, l) pairs go through shared memory in chunks of 64 splits)
+  for (int c0 = 0; c0 < n_splits; c0 += 64) {
+    const int nc = min(64, n_splits - c0);
+    __syncthreads();
+    for (int i = d; i < nc * G * 2; i += HEAD_DIM) ml_s[i] = __ldcg(&part_ml[(pbase + c0) * G * 2 + i]);
+    __syncthreads();
+    for (int sp = 0; sp < nc; ++sp)
+#pragma unroll
+      for (int g = 0; g < G; ++g) m_f[g] = fmaxf(m_f[g], ml_s[(sp * G + g) * 2]);
+  }
+  // pass 2: weighted sums in split order, SPB splits of loads in flight per thread
+  constexpr int SPB = 4;
+  for (int c0 = 0; c0 < n_splits; c0 += 64) {
+    const int nc = min(64, n_splits - c0);
+    if (n_splits > 64) {
+      __syncthreads();
+      for (int i = d; i < nc * G * 2; i += HEAD_DIM) ml_s[i] = __ldcg(&part_ml[(pbase + c0) * G * 2 + i]);
+      __syncthreads();
+    }
+    for (int sp0 = 0; sp0 < nc; sp0 += SPB) {
+      float ov[SPB][G];
+#pragma unroll
+      for (int j = 0; j < SPB; ++j)
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          ov[j][g] = (sp0 + j < nc) ? __ldcg(&part_o[((pbase + c0 + sp0 + j) * G + g) * HEAD_DIM + d]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < SPB; ++j) {
+        if (sp0 + j < nc) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const float fs = exp2f(ml_s[((sp0 + j) * G + g) * 2] - m_f[g]);
+            l_f[g] += ml_s[((sp0 + j) * G + g) * 2 + 1] * fs;
+            o_f[g] += ov[j][g] * fs;
+          }
+        }
+      }
+    }
+  }
+  __nv_bfloat16* o_dst = out + (size_t)sq.q_start * out_ld + (size_t)kvh * G * HEAD_DIM;
+#pragma unroll
+  for (int g = 0; g < G; ++g) o_dst[g * HEAD_DIM + d] = __float2bfloat16_rn(o_f[g] / l_f[g]);
+}
+
+template <int G>
+static cudaError_t decode_launch_g(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
+                                   const __nv_bfloat16* v_cache, const DecItem* items, int max_entries,
+                                   const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs, int max_splits,
+                                   float* part_o, float* part_ml, __nv_bfloat16* out, int out_ld, int n_kv,
+                                   float scale, int num_sms, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e =
+        cudaFuncSetAttribute(attn_decode_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const long long max_flat = (long long)max_entries * n_kv;
+  const int grid = (int)std::min<long long>(2LL * num_sms, (max_flat + DEC_WARPS - 1) / DEC_WARPS);
+  cudaError_t e = launch_k(attn_decode_kernel<G>, dim3(grid), dim3(DEC_THREADS), DEC_SMEM, stream, qkv, qkv_ld,
+                           k_cache, v_cache, items, max_splits, part_o, part_ml, out, out_ld, n_kv, scale);
+  if (e != cudaSuccess || max_splits <= 1) return e;
+  return launch_k(attn_merge_kernel<G>, dim3(n_seqs, n_kv), dim3(HEAD_DIM), 0, stream, seqs, seq_ids, max_splits,
+                  (const float*)part_o, (const float*)part_ml, out, out_ld, n_kv);
+}
+
+cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
+                               const __nv_bfloat16* v_cache, const DecItem* items, int max_entries,
+                               const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs, int max_splits, float* part_o,
+                               float* part_ml, __nv_bfloat16* out, int out_ld, int n_q, int n_kv, float scale,
+                               int num_sms, cudaStream_t stream) {
+  if (max_entries <= 0 || n_seqs <= 0) return cudaSuccess;
+  if (n_q % n_kv != 0) return cudaErrorInvalidValue;
+  const int G = n_q / n_kv;
+#define TGIS_DEC(GG)                                                                                               \
+  case GG:                                                                                                         \
+    return decode_launch_g<GG>(qkv, qkv_ld, k_cache, v_cache, items, max_entries, seqs, seq_ids, n_seqs, max_splits, \
+                               part_o, part_ml, out, out_ld, n_kv, scale, num_sms, stream)
+  switch (G) {
+    TGIS_DEC(1);
+    TGIS_DEC(2);
+    TGIS_DEC(3);
+    TGIS_DEC(4);
+    TGIS_DEC(8);
+    default: return cudaErrorInvalidValue;
+  }
+#undef TGIS_DEC
+}
+
+// ================================================================================================ prefill
 constexpr int PF_QROWS = 16;  // query tokens per tile
 
 // grid (n_tiles, n_kv); blockDim = 32 * G (warp = query head inside the GQA group)

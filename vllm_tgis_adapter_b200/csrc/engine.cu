@@ -384,6 +384,8 @@ struct tgis_engine {
     off_samplesrc = place(4 * (size_t)S_max);
     off_rows = place(sizeof(SampleRow) * (size_t)S_max);
     off_bt = place(4 * (size_t)S_max * bt_stride);
+    // decode work items follow the USED part of the block table (items_off(S)); room for the worst case
+    place(sizeof(DecItem) * (1 + (size_t)S_max * max_splits_cap));
     stage_bytes = o;
     CK(cudaHostAlloc(&h_stage, stage_bytes, cudaHostAllocDefault));
     memset(h_stage, 0, stage_bytes);
@@ -504,7 +506,7 @@ struct tgis_engine {
       memcpy(h_stage, reinterpret_cast<uint8_t*>(shm) + SHM_STAGE_OFF, h.copy_bytes);
       seen = s;
       shm->ack[rank].store(s, std::memory_order_release);
-      launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv);
+      launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S);
       CK(cudaStreamSynchronize(stream));
       ++n_steps;
     }
@@ -634,7 +636,9 @@ struct tgis_engine {
 
   // Enqueue one step on `stream`: H2D metadata, layer stack, lm_head + sampler, D2H results.  Reads every per-step
   // quantity from the device staging buffer, so the same sequence can be captured once into a CUDA graph and replayed.
-  void launch_step(size_t copy_bytes, int T, int n_dec, int n_tiles, int R, int max_dec_kv) {
+  size_t items_off(int S) const { return (off_bt + sizeof(int32_t) * (size_t)S * bt_stride + 255) / 256 * 256; }
+
+  void launch_step(size_t copy_bytes, int T, int n_dec, int n_tiles, int R, int max_dec_kv, int S) {
     const tgis_config& c = cfg;
     const int H = c.hidden, F = Fl, V = c.vocab;  // F: local ffn shard
     CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
@@ -664,10 +668,10 @@ struct tgis_engine {
       ++n_launches;
       if (n_dec > 0) {
         const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
-        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, d_seqs, /*seq_ids=*/nullptr, n_dec, d_bt, bt_stride,
-                              max_splits, part_o.p, part_ml.p, dec_counters.p, attn_out.p, q_dim, nq, nkv, scale,
-                              stream));
-        ++n_launches;
+        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, ds<DecItem>(items_off(S)), n_dec * max_splits, d_seqs,
+                              ds<int32_t>(off_decids), n_dec, max_splits, part_o.p, part_ml.p, attn_out.p, q_dim, nq,
+                              nkv, scale, num_sms, stream));
+        n_launches += max_splits > 1 ? 2 : 1;
       }
       if (n_tiles > 0) {
         CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
@@ -798,7 +802,11 @@ struct tgis_engine {
       T += q_len;
     }
     // ---- ship metadata + run the layer stack (one CUDA graph launch for a pure-decode step when enabled)
-    const size_t copy_bytes = off_bt + sizeof(int32_t) * (size_t)S * bt_stride;
+    // decode work items: (sequence, DECODE_SPLIT-token split) entries; the copy covers the worst case for this
+    // (S, max_splits) so that its size is a function of the CUDA-graph key
+    const int max_splits_step = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+    decode_items_build(hs<DecItem>(items_off(S)), seqs, decids, n_dec, bt, bt_stride);
+    const size_t copy_bytes = items_off(S) + sizeof(DecItem) * (1 + (size_t)n_dec * max_splits_step);
     CK(cudaEventRecord(ev0, stream));
     if (tp > 1) publish_plan(StepHeader{T, n_dec, n_tiles, R, max_dec_kv, S, (uint64_t)copy_bytes});
     const bool graphable = cfg.use_cuda_graphs && tp == 1 && !profiling && n_tiles == 0 && n_dec == S && R == S;
@@ -815,7 +823,7 @@ struct tgis_engine {
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         try {
-          launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv);
+          launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv, S);
         } catch (...) {
           cudaStreamEndCapture(stream, &g);
           if (g) cudaGraphDestroy(g);
@@ -833,7 +841,7 @@ struct tgis_engine {
       n_launches += graph_nodes[key];
       ++n_graph_launches;
     } else {
-      launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv);
+      launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv, S);
     }
     CK(cudaEventRecord(ev1, stream));
     CK(cudaStreamSynchronize(stream));

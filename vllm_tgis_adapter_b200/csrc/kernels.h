@@ -67,13 +67,44 @@ struct AttnSeq {        // one entry per sequence scheduled this step (device ar
   int32_t kv_len;       // context length INCLUDING this step's tokens
   int32_t block_row;    // row in the block table
 };
-// Decode (q_len == 1): split-KV over chunks of DECODE_SPLIT tokens, GQA group packed per CTA.
-constexpr int DECODE_SPLIT = 256;
+// Decode (q_len == 1): split-KV over chunks of DECODE_SPLIT tokens; the host lists the (sequence, split) entries of
+// the step, the kernel crosses them with the kv heads.  items[0].q_row = number of entries, entries follow from [1].
+constexpr int DECODE_SPLIT = 128;
+struct DecItem {       // 32 bytes
+  int32_t q_row;       // row of the sequence's token in qkv / out            ([0]: number of entries)
+  int32_t kv_len;      // of the whole sequence
+  int32_t seq_split;   // seq | split << 16; seq = index among this step's decode sequences (partial buffers)
+  int32_t reserved;
+  int32_t blocks[DECODE_SPLIT / KV_BLOCK];  // physical KV blocks of the split (resolved on the host: no table walk)
+};
+static_assert(DECODE_SPLIT / KV_BLOCK == 4 && sizeof(DecItem) == 32, "DecItem is read as two int4");
+inline int decode_items_build(DecItem* items, const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs,
+                              const int32_t* block_table, int bt_stride) {
+  int n = 0;
+  for (int i = 0; i < n_seqs; ++i) {
+    const AttnSeq& sq = seqs[seq_ids ? seq_ids[i] : i];
+    const int n_splits = (sq.kv_len + DECODE_SPLIT - 1) / DECODE_SPLIT;
+    const int n_blocks = (sq.kv_len + KV_BLOCK - 1) / KV_BLOCK;
+    const int32_t* row = block_table + (size_t)sq.block_row * bt_stride;
+    for (int sp = 0; sp < n_splits; ++sp) {
+      DecItem& it = items[++n];
+      it = DecItem{sq.q_start, sq.kv_len, i | (sp << 16), 0, {0, 0, 0, 0}};
+      for (int j = 0; j < DECODE_SPLIT / KV_BLOCK; ++j) {
+        const int b = sp * (DECODE_SPLIT / KV_BLOCK) + j;
+        it.blocks[j] = b < n_blocks ? row[b] : 0;
+      }
+    }
+  }
+  items[0] = DecItem{n, 0, 0, 0, {0, 0, 0, 0}};
+  return n;
+}
+// Streaming kernel + (max_splits > 1) the split-merge kernel.  seqs / seq_ids / n_seqs: this step's decode sequences in
+// the order decode_items_build numbered them.
 cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
-                               const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs,
-                               const int32_t* block_table, int bt_stride, int max_splits, float* part_o,
-                               float* part_ml, int* counters, __nv_bfloat16* out, int out_ld, int n_q, int n_kv, float scale,
-                               cudaStream_t stream);
+                               const __nv_bfloat16* v_cache, const DecItem* items, int max_entries,
+                               const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs, int max_splits, float* part_o,
+                               float* part_ml, __nv_bfloat16* out, int out_ld, int n_q, int n_kv, float scale,
+                               int num_sms, cudaStream_t stream);
 // Prefill / chunked prefill (q_len >= 1), causal over the paged cache.
 cudaError_t attn_prefill_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
                                 const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* tile_seq,

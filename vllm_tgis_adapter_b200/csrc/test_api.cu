@@ -26,6 +26,13 @@ int kfail(const std::string& m) {
     if (_e != cudaSuccess) return kfail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+int test_num_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
 template <class T>
 struct Tmp {
   T* p = nullptr;
@@ -152,13 +159,71 @@ int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v
   KCK(pml.alloc(nd * n_kv * max_splits * G * 2));
   KCK(ctr.alloc(nd * n_kv));
   KCK(cudaMemset(ctr.p, 0, sizeof(int) * nd * n_kv));
-  KCK(attn_decode_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)k_cache_dev, (const bf16*)v_cache_dev, d_seqs.p,
-                         d_dec.p, (int)dec.size(), d_bt.p, bt_stride, max_splits, po.p, pml.p, ctr.p, (bf16*)out_dev,
-                         out_ld, n_q, n_kv, scale, 0));
+  std::vector<DecItem> items(1 + nd * max_splits);
+  decode_items_build(items.data(), seqs.data(), dec.data(), (int)dec.size(), block_table_host, bt_stride);
+  Tmp<DecItem> d_items;
+  KCK(d_items.upload(items.data(), items.size()));
+  KCK(attn_decode_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)k_cache_dev, (const bf16*)v_cache_dev, d_items.p,
+                         (int)dec.size() * max_splits, d_seqs.p, d_dec.p, (int)dec.size(), max_splits, po.p, pml.p,
+                         (bf16*)out_dev, out_ld, n_q, n_kv, scale, test_num_sms(), 0));
   KCK(attn_prefill_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)k_cache_dev, (const bf16*)v_cache_dev, d_seqs.p,
                           d_tseq.p, d_tq0.p, (int)tseq.size(), d_bt.p, bt_stride, (bf16*)out_dev, out_ld, n_q, n_kv,
                           scale, 0));
   KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// decode attention only, timed: `iters` launches rotating over `n_layers` cache copies (layer_stride_bytes apart) so that
+// a small batch does not simply sit in L2; us_out = average device time per launch
+int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev,
+                           const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows,
+                           int32_t bt_stride, void* out_dev, int32_t n_q, int32_t n_kv, float scale, int32_t n_layers,
+                           int64_t layer_stride_bytes, int32_t iters, float* us_out) {
+  if (n_kv <= 0 || n_q % n_kv) return kfail("bad head counts");
+  const int G = n_q / n_kv;
+  const int qkv_ld = (n_q + 2 * n_kv) * HEAD_DIM, out_ld = n_q * HEAD_DIM;
+  std::vector<AttnSeq> seqs(n_seqs);
+  int max_kv = 1;
+  for (int s = 0; s < n_seqs; ++s) {
+    seqs[s] = AttnSeq{seqs_host[4 * s], seqs_host[4 * s + 1], seqs_host[4 * s + 2], seqs_host[4 * s + 3]};
+    if (seqs[s].q_len != 1) return kfail("decode sequences only");
+    max_kv = std::max(max_kv, seqs[s].kv_len);
+  }
+  Tmp<AttnSeq> d_seqs;
+  Tmp<int32_t> d_bt;
+  Tmp<float> po, pml;
+  Tmp<int> ctr;
+  KCK(d_seqs.upload(seqs.data(), n_seqs));
+  KCK(d_bt.upload(block_table_host, (size_t)bt_rows * bt_stride));
+  const int max_splits = (max_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+  KCK(po.alloc((size_t)n_seqs * n_kv * max_splits * G * HEAD_DIM));
+  KCK(pml.alloc((size_t)n_seqs * n_kv * max_splits * G * 2));
+  KCK(ctr.alloc((size_t)n_seqs * n_kv));
+  KCK(cudaMemset(ctr.p, 0, sizeof(int) * n_seqs * n_kv));
+  std::vector<DecItem> items(1 + (size_t)n_seqs * max_splits);
+  decode_items_build(items.data(), seqs.data(), nullptr, n_seqs, block_table_host, bt_stride);
+  Tmp<DecItem> d_items;
+  KCK(d_items.upload(items.data(), items.size()));
+  const int num_sms = test_num_sms();
+  cudaEvent_t e0, e1;
+  KCK(cudaEventCreate(&e0));
+  KCK(cudaEventCreate(&e1));
+  for (int it = -2; it < iters; ++it) {
+    if (it == 0) KCK(cudaEventRecord(e0, 0));
+    const int l = ((it % n_layers) + n_layers) % n_layers;
+    const char* kc = (const char*)k_cache_dev + (size_t)l * layer_stride_bytes;
+    const char* vc = (const char*)v_cache_dev + (size_t)l * layer_stride_bytes;
+    KCK(attn_decode_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)kc, (const bf16*)vc, d_items.p,
+                           n_seqs * max_splits, d_seqs.p, nullptr, n_seqs, max_splits, po.p, pml.p, (bf16*)out_dev,
+                           out_ld, n_q, n_kv, scale, num_sms, 0));
+  }
+  KCK(cudaEventRecord(e1, 0));
+  KCK(cudaDeviceSynchronize());
+  float ms = 0.f;
+  KCK(cudaEventElapsedTime(&ms, e0, e1));
+  *us_out = ms * 1000.f / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
 }
 
