@@ -52,6 +52,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                : "r"(addr));
 }
 
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {  // 8x8 b16 transpose across the warp
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
+  return d;
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -69,8 +74,9 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
 // been consumed, and the next item's metadata / block ids are fetched one item / one block ahead, so a warp keeps
 // 16-24 KiB in flight while it computes and never waits on a dependent global load in steady state (8 warps per SM).
 //
-// Per 32-token block: the G query heads are rows 0..G-1 of an m16n8k16 A operand (other rows zero); S = Q K^T is 32
-// MMAs with K B-fragments straight from the chunk-major tile by ldmatrix; P (bf16 hi + lo) V is 64 MMAs with
+// Per 32-token block the tokens / dims ride the M dimension of m16n8k16 and the (up to 8) query heads of the group the
+// N dimension, so nothing is padded: S^T = K Q^T is 16 MMAs with K A-fragments straight from the chunk-major tile by
+// ldmatrix; P^T (bf16 hi + lo, moved into B-fragment layout by movmatrix) feeds O^T = V^T P^T, 32 MMAs with
 // ldmatrix.trans on the swizzled V tile; the online-softmax state (m, l, o) stays in registers for the whole item.
 // kv_len > 128: the warp stores its (o, m, l) partial and attn_merge_kernel (next launch, PDL-chained) merges the
 // splits in split order: no atomics or fences in the streaming kernel (a per-item release fence cost 20 % of its
@@ -78,13 +84,19 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
 // else is in the batch or on which warp ran it.
 constexpr int DEC_WARPS = 4;
 constexpr int DEC_THREADS = DEC_WARPS * 32;
-constexpr int DEC_RING = 3;
+#ifndef TGIS_DEC_RING
+#define TGIS_DEC_RING 3  // tile buffers per warp
+#endif
+#ifndef TGIS_DEC_MINB
+#define TGIS_DEC_MINB 2  // CTAs per SM (register cap); shared memory must agree: MINB * 4 * (RING * 8 + 2) KiB <= 227
+#endif
+constexpr int DEC_RING = TGIS_DEC_RING;
 constexpr int DEC_Q_BYTES = 8 * HEAD_DIM * 2;                           // up to 8 heads
 constexpr int DEC_WARP_SMEM = DEC_RING * TILE_BYTES + DEC_Q_BYTES;      // 26 KiB
 constexpr int DEC_SMEM = DEC_WARPS * DEC_WARP_SMEM + DEC_WARPS * 4 * 8; // + 4 mbarriers per warp
 
 template <int G>
-__global__ void __launch_bounds__(DEC_THREADS, 2)
+__global__ void __launch_bounds__(DEC_THREADS, TGIS_DEC_MINB)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv_bfloat16* __restrict__ k_cache,
                    const __nv_bfloat16* __restrict__ v_cache, const DecItem* __restrict__ items,
                    int max_splits, float* __restrict__ part_o, float* __restrict__ part_ml,
@@ -179,122 +191,149 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
     const int n_blk = (n_tok + KV_BLOCK - 1) / KV_BLOCK;
     const bool has_next = f + n_slots < n_flat;
     if (has_next) c_nxt = item_at(f + n_slots);
-    // ---- Q as A fragments: row = head (lane/4), 8 k-steps of 16 dims; rows >= G and rows 8..15 are zero
+    // ---- Q^T as B fragments: n = head (lane/4), 8 k-steps of 16 dims; heads >= G are zero columns
     mbar_wait(q_bar, q_ph);
     q_ph ^= 1;
-    uint32_t qa[8][4];
+    uint32_t qb[8][2];
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
       const uint8_t* qp = q_s + (hr * HEAD_DIM + ks * 16 + t4 * 2) * 2;
-      qa[ks][0] = hr < G ? *reinterpret_cast<const uint32_t*>(qp) : 0u;
-      qa[ks][2] = hr < G ? *reinterpret_cast<const uint32_t*>(qp + 16) : 0u;
-      qa[ks][1] = 0u;
-      qa[ks][3] = 0u;
+      qb[ks][0] = hr < G ? *reinterpret_cast<const uint32_t*>(qp) : 0u;
+      qb[ks][1] = hr < G ? *reinterpret_cast<const uint32_t*>(qp + 16) : 0u;
     }
-    float o[16][4];
+    // this thread's accumulators: heads 2*t4 + {0,1} (e & 1), dims md*16 + hr + {0,8} (e >> 1)
+    float ot[8][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float m_r = -INFINITY, l_r = 0.f;  // l_r: this thread's share of the row sum (quad-reduced at the end)
+    for (int i = 0; i < 8; ++i) ot[i][0] = ot[i][1] = ot[i][2] = ot[i][3] = 0.f;
+    float m_r[2] = {-INFINITY, -INFINITY}, l_r[2] = {0.f, 0.f};  // l_r: this thread's share (reduced at the end)
 
     for (int jb = 0; jb < n_blk; ++jb) {
-      // ---- S = Q K^T : 4 n-tiles (8 tokens) x 8 k-steps (16 dims = chunks 2ks, 2ks+1); one ldmatrix.x4 = B fragments
-      // of two n-tiles: matrices (chunk 2ks, nt), (chunk 2ks+1, nt), (chunk 2ks, nt+1), (chunk 2ks+1, nt+1)
+      // ---- S^T = K Q^T : 2 m-tiles (16 tokens) x 8 k-steps (16 dims = chunks 2ks, 2ks+1); ldmatrix.x4 = one A
+      // fragment: matrices (tok lo, chunk 2ks), (tok hi, chunk 2ks), (tok lo, chunk 2ks+1), (tok hi, chunk 2ks+1)
       mbar_wait(&full[c_buf], c_ph);
       const uint32_t k_base = ring_base + c_buf * TILE_BYTES;
-      float s[4][4];
+      float st[2][4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      for (int mt = 0; mt < 2; ++mt) st[mt][0] = st[mt][1] = st[mt][2] = st[mt][3] = 0.f;
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-        for (int nt = 0; nt < 4; nt += 2) {
-          uint32_t kb[4];
-          ldmatrix_x4(kb, k_base + (((2 * ks + (mi & 1)) * KV_BLOCK) + (nt + (mi >> 1)) * 8 + ri) * 16);
-          mma_bf16_16816(s[nt], qa[ks], kb[0], kb[1]);
-          mma_bf16_16816(s[nt + 1], qa[ks], kb[2], kb[3]);
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t ka[4];
+          ldmatrix_x4(ka, k_base + ((2 * ks + (mi >> 1)) * KV_BLOCK + mt * 16 + (mi & 1) * 8 + ri) * 16);
+          mma_bf16_16816(st[mt], ka, qb[ks][0], qb[ks][1]);
         }
       }
       __syncwarp();
-      issue_tile();  // refills the K buffer just consumed (tile t + 3 of this warp's stream)
+      issue_tile();  // refills the K buffer just consumed (tile t + DEC_RING of this warp's stream)
       if (++c_buf == DEC_RING) { c_buf = 0; c_ph ^= 1; }
       if (jb == 0) {  // q_s was copied to registers above; by now the next item's record has arrived
         __syncwarp();
         if (has_next) issue_q(c_nxt, (f + n_slots) % n_kv);
       }
-      // ---- online softmax for head hr over tokens nt*8 + t4*2 + {0,1}
+      // ---- online softmax; st[mt][e]: token mt*16 + hr + (e>>1)*8, head 2*t4 + (e&1)
       const int valid = min(KV_BLOCK, n_tok - jb * KV_BLOCK);
-      float mx = -INFINITY;
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          s[nt][e] = (nt * 8 + t4 * 2 + e < valid) ? s[nt][e] * sl2 : -INFINITY;
-          mx = fmaxf(mx, s[nt][e]);
+        for (int e = 0; e < 4; ++e) {
+          st[mt][e] = (mt * 16 + hr + (e >> 1) * 8 < valid) ? st[mt][e] * sl2 : -INFINITY;
+          mx[e & 1] = fmaxf(mx[e & 1], st[mt][e]);
         }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float m_new = fmaxf(m_r, mx);  // finite: token 0 of every block of the split is valid
-      const float corr = (m_r == -INFINITY) ? 0.f : exp2f(m_r - m_new);
-      m_r = m_new;
-      l_r *= corr;
-      uint32_t pa[2][4], pl[2][4];  // P as bf16 hi + bf16 lo (two MMAs): ~16 mantissa bits, tracks the fp32 oracle
+      float corr[2];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const float p0 = exp2f(s[nt][0] - m_new), p1 = exp2f(s[nt][1] - m_new);
-        l_r += p0 + p1;
-        const int kk = nt >> 1, hi = nt & 1;
-        pa[kk][hi * 2] = pack_bf16x2(p0, p1);
-        pl[kk][hi * 2] = pack_bf16x2(p0 - bf16_round(p0), p1 - bf16_round(p1));
-        pa[kk][hi * 2 + 1] = 0u;
-        pl[kk][hi * 2 + 1] = 0u;
+      for (int hh = 0; hh < 2; ++hh) {
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 4));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 8));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 16));
+        const float m_new = fmaxf(m_r[hh], mx[hh]);  // finite: token 0 of every block of the split is valid
+        corr[hh] = (m_r[hh] == -INFINITY) ? 0.f : exp2f(m_r[hh] - m_new);
+        m_r[hh] = m_new;
+        l_r[hh] *= corr[hh];
+      }
+      // P^T as B fragments, bf16 hi + bf16 lo (two MMAs): ~16 mantissa bits, tracks the fp32 oracle.  The score layout
+      // (row = token, column pair = heads) is the transpose of the B layout (k = token pair, n = head): movmatrix.
+      uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float p[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p[e] = exp2f(st[mt][e] - m_r[e & 1]);
+          l_r[e & 1] += p[e];
+        }
+        bh[mt][0] = movmatrix_trans(pack_bf16x2(p[0], p[1]));
+        bh[mt][1] = movmatrix_trans(pack_bf16x2(p[2], p[3]));
+        bl[mt][0] = movmatrix_trans(pack_bf16x2(p[0] - bf16_round(p[0]), p[1] - bf16_round(p[1])));
+        bl[mt][1] = movmatrix_trans(pack_bf16x2(p[2] - bf16_round(p[2]), p[3] - bf16_round(p[3])));
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        o[i][0] *= corr;
-        o[i][1] *= corr;
+      for (int i = 0; i < 8; ++i) {
+        ot[i][0] *= corr[0];
+        ot[i][1] *= corr[1];
+        ot[i][2] *= corr[0];
+        ot[i][3] *= corr[1];
       }
-      // ---- O += P V : 2 k-steps (16 tokens) x 16 n-tiles (8 dims); V B-fragments by ldmatrix.trans: matrices
-      // (tok lo, nd), (tok hi, nd), (tok lo, nd+1), (tok hi, nd+1).  Slots >= valid carry p = 0 (cache slots finite).
+      // ---- O^T += V^T P^T : 8 m-tiles (16 dims = chunks 2md, 2md+1) x 2 k-steps (16 tokens); V^T A-fragments by
+      // ldmatrix.trans: matrices (tok lo, chunk 2md), (tok lo, chunk 2md+1), (tok hi, chunk 2md), (tok hi, chunk 2md+1).
+      // Slots >= valid carry p = 0 (cache slots hold finite values).
       mbar_wait(&full[c_buf], c_ph);
       const uint32_t v_base = ring_base + c_buf * TILE_BYTES;
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
+        const int tok = kk * 16 + (mi >> 1) * 8 + ri;
 #pragma unroll
-        for (int nd = 0; nd < 16; nd += 2) {
-          const int tok = kk * 16 + (mi & 1) * 8 + ri;
-          const int chunk = nd + (mi >> 1);
-          uint32_t vb[4];
-          ldmatrix_x4_trans(vb, v_base + tok * (HEAD_DIM * 2) + ((chunk ^ (tok & 7)) * 16));
-          mma_bf16_16816(o[nd], pa[kk], vb[0], vb[1]);
-          mma_bf16_16816(o[nd + 1], pa[kk], vb[2], vb[3]);
-          mma_bf16_16816(o[nd], pl[kk], vb[0], vb[1]);
-          mma_bf16_16816(o[nd + 1], pl[kk], vb[2], vb[3]);
+        for (int md = 0; md < 8; md += 2) {
+          uint32_t va[2][4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            ldmatrix_x4_trans(va[u], v_base + tok * (HEAD_DIM * 2) + (((2 * (md + u) + (mi & 1)) ^ (tok & 7)) * 16));
+          mma_bf16_16816(ot[md], va[0], bh[kk][0], bh[kk][1]);
+          mma_bf16_16816(ot[md + 1], va[1], bh[kk][0], bh[kk][1]);
+          mma_bf16_16816(ot[md], va[0], bl[kk][0], bl[kk][1]);
+          mma_bf16_16816(ot[md + 1], va[1], bl[kk][0], bl[kk][1]);
         }
       }
       __syncwarp();
       issue_tile();
       if (++c_buf == DEC_RING) { c_buf = 0; c_ph ^= 1; }
     }
-    l_r += __shfl_xor_sync(0xffffffffu, l_r, 1);
-    l_r += __shfl_xor_sync(0xffffffffu, l_r, 2);
-
-    // ---- item epilogue.  This thread: head hr, dims nd*8 + t4*2 + {0,1}
-    __nv_bfloat16* o_dst = out + (size_t)c_it.x * out_ld + (size_t)(kvh * G + hr) * HEAD_DIM + t4 * 2;
-    if (n_splits == 1) {
-      if (hr < G) {
-        const float inv = 1.f / l_r;
 #pragma unroll
-        for (int nd = 0; nd < 16; ++nd)
-          *reinterpret_cast<__nv_bfloat162*>(o_dst + nd * 8) = __floats2bfloat162_rn(o[nd][0] * inv, o[nd][1] * inv);
+    for (int hh = 0; hh < 2; ++hh) {
+      l_r[hh] += __shfl_xor_sync(0xffffffffu, l_r[hh], 4);
+      l_r[hh] += __shfl_xor_sync(0xffffffffu, l_r[hh], 8);
+      l_r[hh] += __shfl_xor_sync(0xffffffffu, l_r[hh], 16);
+    }
+
+    // ---- item epilogue
+    if (n_splits == 1) {
+      __nv_bfloat16* o_dst = out + (size_t)c_it.x * out_ld + (size_t)(kvh * G + 2 * t4) * HEAD_DIM + hr;
+      const float inv[2] = {1.f / l_r[0], 1.f / l_r[1]};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (2 * t4 + (e & 1) < G) {
+#pragma unroll
+          for (int md = 0; md < 8; ++md)
+            o_dst[(e & 1) * HEAD_DIM + md * 16 + (e >> 1) * 8] = __float2bfloat16_rn(ot[md][e] * inv[e & 1]);
+        }
       }
     } else {
       // store the partial (m in the exp2 domain); attn_merge_kernel combines the splits in split order
       const size_t pbase = (size_t)(seq * n_kv + kvh) * max_splits;
-      if (hr < G) {
-        float* po = part_o + ((pbase + split) * G + hr) * HEAD_DIM + t4 * 2;
+      float* po = part_o + ((pbase + split) * G + 2 * t4) * HEAD_DIM + hr;
 #pragma unroll
-        for (int nd = 0; nd < 16; ++nd) *reinterpret_cast<float2*>(po + nd * 8) = make_float2(o[nd][0], o[nd][1]);
-        if (t4 == 0) *reinterpret_cast<float2*>(part_ml + ((pbase + split) * G + hr) * 2) = make_float2(m_r, l_r);
+      for (int e = 0; e < 4; ++e) {
+        if (2 * t4 + (e & 1) < G) {
+#pragma unroll
+          for (int md = 0; md < 8; ++md) po[(e & 1) * HEAD_DIM + md * 16 + (e >> 1) * 8] = ot[md][e];
+        }
+      }
+      if (hr == 0) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+          if (2 * t4 + hh < G)
+            *reinterpret_cast<float2*>(part_ml + ((pbase + split) * G + 2 * t4 + hh) * 2) = make_float2(m_r[hh], l_r[hh]);
       }
     }
     c_it = c_nxt;
@@ -377,7 +416,7 @@ static cudaError_t decode_launch_g(const __nv_bfloat16* qkv, int qkv_ld, const _
     attr = true;
   }
   const long long max_flat = (long long)max_entries * n_kv;
-  const int grid = (int)std::min<long long>(2LL * num_sms, (max_flat + DEC_WARPS - 1) / DEC_WARPS);
+  const int grid = (int)std::min<long long>((long long)TGIS_DEC_MINB * num_sms, (max_flat + DEC_WARPS - 1) / DEC_WARPS);
   cudaError_t e = launch_k(attn_decode_kernel<G>, dim3(grid), dim3(DEC_THREADS), DEC_SMEM, stream, qkv, qkv_ld,
                            k_cache, v_cache, items, max_splits, part_o, part_ml, out, out_ld, n_kv, scale);
   if (e != cudaSuccess || max_splits <= 1) return e;
