@@ -33,6 +33,7 @@ for st in $STAGES; do
     bench_batches) for b in 64 128 256; do timeout 400 python bench.py --no-cpu-baseline --steps 1 --warmup 3 --batch $b > gpurun_out/bench_b$b.log 2> gpurun_out/bench_b$b.err; done; timeout 400 python bench.py --no-cpu-baseline --steps 1 --warmup 3 --batch 64 --sampling cfg3 > gpurun_out/bench_b64_cfg3.log 2> gpurun_out/bench_b64_cfg3.err; echo "bench_batches rc=$?" ;;
     timeline) timeout 300 python scripts/gemm_timeline.py > gpurun_out/gemm_timeline.log 2>&1; echo "timeline rc=$?" ;;
     ctasweep) timeout 300 python scripts/gemm_cta_sweep.py > gpurun_out/gemm_cta_sweep.log 2>&1; echo "ctasweep rc=$?" ;;
+    chaintl) TGIS_ENGINE_LIB=$PWD/vllm_tgis_adapter_b200/lib/libtgis_engine_tl.so timeout 300 python scripts/chain_timeline.py > gpurun_out/chain_timeline.log 2>&1; echo "chaintl rc=$?" ;;
     attnbench) timeout 300 python scripts/attn_bench.py > gpurun_out/attn_bench.log 2>&1; echo "attnbench rc=$?" ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
     *) echo "unknown stage $st" ;;

@@ -250,6 +250,12 @@ struct tgis_engine {
   // optional per-GEMM timing (tgis_engine_set_profiling): CUDA events around every GEMM launch of a step
   bool profiling = false;
   bool prof_decode_only = false, step_is_decode = false;
+  // EXPERIMENT (default off, TGIS_CHAIN=1): one persistent chain kernel per layer for decode-shaped steps.  Measured
+  // slower than PDL-chained stand-alone kernels: in-kernel grid-wide step barriers cost 12-15 us each
+  // under full HBM load vs ~9 us per kernel boundary.  Kept because it is bit-identical and documents the experiment.
+  bool use_chain = false;
+  DevBuf<int> chain_sync;
+  int chain_pf_depth = 16;  // TGIS_CHAIN_PF
   int l2_prefetch_kb = 20;  // k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
@@ -308,6 +314,10 @@ struct tgis_engine {
     tiles_max = T_max / 16 + S_max + 1;
     rng.seed(c.seed ? c.seed : 0x5DEECE66Dull);
     if (const char* e = getenv("TGIS_L2_PREFETCH_KB")) l2_prefetch_kb = atoi(e);
+    if (const char* e = getenv("TGIS_CHAIN")) use_chain = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_CHAIN_PF")) chain_pf_depth = atoi(e);
+    chain_sync.alloc(CHAIN_MAX_STEPS + 1);
+    chain_sync.zero();
 
     // ---- weights: one arena
     const size_t H = c.hidden, F = Fl, V = c.vocab, L = c.n_layers;  // F: this rank's ffn shard
@@ -625,6 +635,45 @@ struct tgis_engine {
     ++n_launches;
   }
 
+  // One chain launch (gemm_tcgen05.cu): o-proj -> add+norm -> gate_up/SwiGLU -> down [-> add+norm -> next qkv], or the
+  // stack's head (norm -> qkv of layer 0).  Profiling: timed as one launch, bytes = the steps' weight + activation bytes.
+  ChainParams chain_begin(int T) {
+    ChainParams P;
+    memset(&P, 0, sizeof(P));
+    P.T = T;
+    P.hidden = cfg.hidden;
+    P.eps = cfg.rms_eps;
+    P.ws = gemm_ws.p;
+    P.counters = gemm_counters.p;
+    P.sync = chain_sync.p;
+    P.pf_depth = chain_pf_depth;
+    return P;
+  }
+  void chain_run(const ChainParams& P) {
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (profiling && (!prof_decode_only || step_is_decode)) {
+      while (prof_events.size() < prof_used + 2) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        prof_events.push_back(ev);
+      }
+      pe0 = prof_events[prof_used];
+      pe1 = prof_events[prof_used + 1];
+      prof_used += 2;
+      double by = 0;
+      for (int i = 0; i < P.n_steps; ++i) {
+        const ChainStep& st = P.step[i];
+        if (st.kind == 0) by += (double)st.N * st.K * 2 + (double)P.T * st.K * 2 + (double)P.T * st.N * (st.mode == 2 ? 1 : 2);
+        else by += (double)P.T * P.hidden * 2 * (st.x ? 4 : 2);
+      }
+      prof_bytes.push_back(by);
+      CK(cudaEventRecord(pe0, stream));
+    }
+    CK(chain_launch(P, num_sms, stream));
+    if (pe1) CK(cudaEventRecord(pe1, stream));
+    ++n_launches;
+  }
+
   template <class T>
   T* hs(size_t off) { return reinterpret_cast<T*>(h_stage + off); }
   template <class T>
@@ -655,12 +704,23 @@ struct tgis_engine {
     }
     CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
     ++n_launches;
+    const bool chained = use_chain && tp == 1 && T <= 256 && !cfg.debug_gemm_ref;
+    const int bi = bt_index(T);
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];
-      if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
-      else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
-      ++n_launches;
-      gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim);
+      if (chained) {
+        if (li == 0) {  // head of the stack: norm -> qkv (later layers get theirs from the previous layer's chain)
+          ChainParams P = chain_begin(T);
+          chain_add_norm(P, nullptr, resid.p, l.ln1, xn.p);
+          chain_add_gemm(P, l.m_qkv, xm_xn[bi], qkv.p, qkv_dim, qkv_dim, H, 0, num_sms);
+          chain_run(P);
+        }
+      } else {
+        if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+        else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+        ++n_launches;
+        gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim);
+      }
       bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
       bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
       CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, nq, nkv,
@@ -677,6 +737,19 @@ struct tgis_engine {
         CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
                                n_tiles, d_bt, bt_stride, attn_out.p, q_dim, nq, nkv, scale, stream));
         ++n_launches;
+      }
+      if (chained) {
+        ChainParams P = chain_begin(T);
+        chain_add_gemm(P, l.m_o, xm_attn[bi], tmp.p, H, H, q_dim, 0, num_sms);
+        chain_add_norm(P, tmp.p, resid.p, l.ln2, xn.p);
+        chain_add_gemm(P, l.m_gu, xm_xn[bi], act.p, F, 2 * F, H, /*mode=*/2, num_sms);
+        chain_add_gemm(P, l.m_d, xm_act[bi], tmp.p, H, H, F, 0, num_sms);
+        if (li + 1 < c.n_layers) {
+          chain_add_norm(P, tmp.p, resid.p, layers[li + 1].ln1, xn.p);
+          chain_add_gemm(P, layers[li + 1].m_qkv, xm_xn[bi], qkv.p, qkv_dim, qkv_dim, H, 0, num_sms);
+        }
+        chain_run(P);
+        continue;
       }
       gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H);
       all_reduce_tmp(T);  // row-parallel partial sums (tp > 1)
