@@ -9,21 +9,30 @@
 // Contract order per row: raw log-softmax -> typical-p -> ExpDecay(EOS) -> min_tokens(EOS)
 // -> repetition penalty -> greedy argmax | temperature -> top-k -> top-p -> sample -> logprob / rank / top-n (raw).
 //
-// Shape of the problem: a [rows, V=128256] scan, HBM/L2 bound, integer-ish selection work.  One 1024-thread CTA owns
-// one row; the fp32 row (512 KiB) is read from HBM once and stays in the 126 MB L2 for the extra selection passes
-// (radix-select thresholds instead of the reference's full sorts).  Loads are 16-byte vectorised and coalesced.
+// Shape of the problem: a [rows, V=128256] scan with integer-ish selection work; a sampling row needs ~10 passes of
+// 50-100 instructions per element, which is ISSUE bound on one SM (1 ms per row).  So a row is owned by a thread-block
+// CLUSTER of 8 CTAs x 1024 threads on 8 SMs: each CTA scans one eighth of the vocabulary, block results are exchanged
+// through distributed shared memory and combined in rank order (deterministic).  The fp32 row (512 KiB) is read from
+// HBM once and stays in the 126 MB L2 for the selection passes (radix-select thresholds instead of the reference's
+// full sorts).  Loads are 16-byte vectorised and coalesced.
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace tgis {
 
+constexpr int SAMP_CL = 8;  // CTAs (SMs) per row
 constexpr int SAMP_THREADS = 1024;
 constexpr int SAMP_WARPS = SAMP_THREADS / 32;
 
 struct RowCtx {
   const float* x;          // raw logits (fp32, straight from the lm_head accumulator)
   int V;
+  int lo, hi;              // this CTA's slice of the vocabulary (multiples of 8)
   const uint32_t* seen;    // bitmap of prompt U output tokens (may be null)
   SampleRow p;
   float lenfac_m1;         // (float)(decay^n - 1), 0 => inactive
@@ -143,6 +152,55 @@ __device__ int block_sumi(int v, int* red) {
   return r;
 }
 
+// ---------------------------------------------------------------- cluster reductions (SAMP_CL CTAs, rank order)
+// xch: 4 words of shared memory per CTA at the same offset in every CTA of the cluster
+template <class T>
+__device__ __forceinline__ T dsmem_read(T* local, int rank) {
+  return *cg::this_cluster().map_shared_rank(local, rank);
+}
+__device__ MaxSum cluster_maxsum(MaxSum v, float* red, float* xch) {
+  v = block_maxsum(v, red);
+  if (threadIdx.x == 0) {
+    xch[0] = v.m;
+    xch[1] = v.s;
+  }
+  cg::this_cluster().sync();
+  MaxSum acc{dsmem_read(xch, 0), dsmem_read(xch + 1, 0)};
+  for (int r = 1; r < SAMP_CL; ++r) acc = ms_combine(acc, MaxSum{dsmem_read(xch, r), dsmem_read(xch + 1, r)});
+  cg::this_cluster().sync();  // xch may be rewritten
+  return acc;
+}
+__device__ ValIdx cluster_argmax(ValIdx v, float* redf, int* redi, float* xch) {
+  v = block_argmax(v, redf, redi);
+  if (threadIdx.x == 0) {
+    xch[0] = v.v;
+    xch[1] = __int_as_float(v.i);
+  }
+  cg::this_cluster().sync();
+  ValIdx acc{dsmem_read(xch, 0), __float_as_int(dsmem_read(xch + 1, 0))};
+  for (int r = 1; r < SAMP_CL; ++r) acc = vi_better(acc, ValIdx{dsmem_read(xch, r), __float_as_int(dsmem_read(xch + 1, r))});
+  cg::this_cluster().sync();
+  return acc;
+}
+__device__ float cluster_sumf(float v, float* red, float* xch) {
+  v = block_sumf(v, red);
+  if (threadIdx.x == 0) xch[0] = v;
+  cg::this_cluster().sync();
+  float acc = dsmem_read(xch, 0);
+  for (int r = 1; r < SAMP_CL; ++r) acc += dsmem_read(xch, r);
+  cg::this_cluster().sync();
+  return acc;
+}
+__device__ int cluster_sumi(int v, int* red, float* xch) {
+  v = block_sumi(v, red);
+  if (threadIdx.x == 0) xch[0] = __int_as_float(v);
+  cg::this_cluster().sync();
+  int acc = 0;
+  for (int r = 0; r < SAMP_CL; ++r) acc += __float_as_int(dsmem_read(xch, r));
+  cg::this_cluster().sync();
+  return acc;
+}
+
 // ---------------------------------------------------------------- radix select helpers
 __device__ __forceinline__ uint32_t f2key(float f) {  // order preserving float -> uint
   const uint32_t b = __float_as_uint(f);
@@ -154,29 +212,57 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 
 // Smallest key K (ascending) such that  sum_{key_i <= K} w_i  >= target  (strict: > target).
 // keyf(i) -> uint32 key, wf(i) -> weight.  If never reached returns the largest present key.
+// Cluster-wide: every CTA histograms its slice [lo, hi), the 8 histograms are summed in rank order through DSMEM
+// into histsum, and every CTA runs the same scan on the same numbers.
 template <class KeyF, class WF>
-__device__ uint32_t select_weighted_asc(int V, KeyF keyf, WF wf, float target, bool strict, float* hist /*[256]*/,
-                                        uint32_t* bcast) {
+__device__ uint32_t select_weighted_asc(int lo, int hi, KeyF keyf, WF wf, float target, bool strict,
+                                        float* hist /*[256]*/, float* histsum /*[256]*/, uint32_t* bcast) {
   uint32_t prefix = 0;
   float below = 0.f;  // weight of keys strictly below the current prefix range
   for (int round = 0; round < 4; ++round) {
     const int shift = 24 - 8 * round;
-    __syncthreads();
+    cg::this_cluster().sync();  // nobody still reads last round's histogram
     if (threadIdx.x < 256) hist[threadIdx.x] = 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
-      const float w = wf(i);
-      if (w > 0.f) {
-        const uint32_t k = keyf(i);
-        if (round == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(k >> shift) & 255], w);
+    // Warp-aggregated histogram: in the first rounds nearly every key of a warp falls into the same one or two
+    // digits (shared exponent bits), and 1024 threads hammering one shared-memory word serialise.  Lanes are grouped
+    // by digit, each group is summed with shuffles (lane order: deterministic) and its leader issues ONE atomic.
+    for (int i0 = lo; i0 < hi; i0 += SAMP_THREADS) {
+      const int i = i0 + threadIdx.x;
+      float w = 0.f;
+      uint32_t digit = 0;
+      if (i < hi) {
+        w = wf(i);
+        if (w > 0.f) {
+          const uint32_t k = keyf(i);
+          if (round == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) digit = (k >> shift) & 255;
+          else w = 0.f;
+        }
       }
+      uint32_t todo = __ballot_sync(0xffffffffu, w > 0.f);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const uint32_t ld = __shfl_sync(0xffffffffu, digit, leader);
+        const bool mine = (w > 0.f) && digit == ld;
+        float part = mine ? w : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == leader) atomicAdd(&hist[ld], part);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
+    cg::this_cluster().sync();
+    if (threadIdx.x < 256) {
+      float t = 0.f;
+      for (int r = 0; r < SAMP_CL; ++r) t += dsmem_read(hist + threadIdx.x, r);
+      histsum[threadIdx.x] = t;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       float cum = below;
       int sel = -1, last_nonempty = -1;
       for (int b = 0; b < 256; ++b) {
-        const float h = hist[b];
+        const float h = histsum[b];
         if (h > 0.f) last_nonempty = b;
         const float nc = cum + h;
         if (h > 0.f && (strict ? (nc > target) : (nc >= target))) {
@@ -188,7 +274,7 @@ __device__ uint32_t select_weighted_asc(int V, KeyF keyf, WF wf, float target, b
       if (sel < 0) {  // rounding: total mass < target -> keep everything: choose the largest key
         sel = last_nonempty < 0 ? 255 : last_nonempty;
         cum = below;
-        for (int b = 0; b < sel; ++b) cum += hist[b];
+        for (int b = 0; b < sel; ++b) cum += histsum[b];
       }
       bcast[0] = (uint32_t)sel;
       bcast[1] = __float_as_uint(cum);
@@ -202,27 +288,40 @@ __device__ uint32_t select_weighted_asc(int V, KeyF keyf, WF wf, float target, b
 
 // k-th largest key (k >= 1) by count
 template <class KeyF>
-__device__ uint32_t select_kth_largest(int V, KeyF keyf, int k, int* hist /*[256]*/, uint32_t* bcast) {
+__device__ uint32_t select_kth_largest(int lo, int hi, KeyF keyf, int k, int* hist /*[256]*/, int* histsum /*[256]*/,
+                                       uint32_t* bcast) {
   uint32_t prefix = 0;
   int above = 0;
   for (int round = 0; round < 4; ++round) {
     const int shift = 24 - 8 * round;
-    __syncthreads();
+    cg::this_cluster().sync();
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
-      const uint32_t key = keyf(i);
-      if (round == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255], 1);
+    for (int i0 = lo; i0 < hi; i0 += SAMP_THREADS) {  // warp-aggregated: one atomic per distinct digit per warp
+      const int i = i0 + threadIdx.x;
+      uint32_t digit = 0xffffffffu;  // not counted
+      if (i < hi) {
+        const uint32_t key = keyf(i);
+        if (round == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) digit = (key >> shift) & 255;
+      }
+      const uint32_t grp = __match_any_sync(0xffffffffu, digit);
+      if (digit != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&hist[digit], __popc(grp));
+    }
+    cg::this_cluster().sync();
+    if (threadIdx.x < 256) {
+      int t = 0;
+      for (int r = 0; r < SAMP_CL; ++r) t += dsmem_read(hist + threadIdx.x, r);
+      histsum[threadIdx.x] = t;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       int cum = above, sel = 0;
       for (int b = 255; b >= 0; --b) {
-        if (cum + hist[b] >= k) {
+        if (cum + histsum[b] >= k) {
           sel = b;
           break;
         }
-        cum += hist[b];
+        cum += histsum[b];
       }
       bcast[0] = (uint32_t)sel;
       bcast[1] = (uint32_t)cum;
@@ -248,22 +347,32 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // ---------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(SAMP_THREADS, 1)
+__global__ void __cluster_dims__(SAMP_CL, 1, 1) __launch_bounds__(SAMP_THREADS, 1)
 tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
                     uint32_t* __restrict__ seen_bitmap, int bitmap_words, float* __restrict__ scratch,
                     SampleOut* __restrict__ outs) {
   __shared__ float redf[2 * SAMP_WARPS];
   __shared__ int redi[SAMP_WARPS];
   __shared__ float histf[256];
+  __shared__ float histsumf[256];
   __shared__ uint32_t bcast[4];
+  __shared__ float xch[4];
   int* histi = reinterpret_cast<int*>(histf);
+  int* histsumi = reinterpret_cast<int*>(histsumf);
   griddep_launch();
   griddep_wait();
 
-  const int r = blockIdx.x;
+  const int r = blockIdx.x / SAMP_CL;
+  const int crank = (int)cg::this_cluster().block_rank();
   RowCtx c;
   c.p = rows[r];
   c.V = V;
+  {
+    const int per = ((V + SAMP_CL - 1) / SAMP_CL + 7) / 8 * 8;
+    c.lo = min(V, crank * per);
+    c.hi = min(V, c.lo + per);
+  }
+  const int lo = c.lo, hi = c.hi;
   c.x = logits + (size_t)c.p.logits_row * ld;
   c.seen = (c.p.seq_slot >= 0 && c.p.rep_penalty != 1.0f) ? seen_bitmap + (size_t)c.p.seq_slot * bitmap_words : nullptr;
   c.lenfac_m1 = (c.p.flags & SAMPLE_LENPEN) ? c.p.len_decay_factor : 0.f;
@@ -280,7 +389,7 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   ValIdx best{-INFINITY, -1};
   const bool do_typ = (c.p.flags & SAMPLE_TYPICAL) != 0 && !forced;
   const bool greedy_fast = greedy && !do_typ;  // argmax fused into the first sweep
-  for (int i0 = threadIdx.x * 8; i0 < V; i0 += SAMP_THREADS * 8) {
+  for (int i0 = lo + threadIdx.x * 8; i0 < hi; i0 += SAMP_THREADS * 8) {
     const float4 ra = *reinterpret_cast<const float4*>(c.x + i0);
     const float4 rb = *reinterpret_cast<const float4*>(c.x + i0 + 4);
     const float xs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -299,7 +408,7 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
       }
     }
   }
-  ms = block_maxsum(ms, redf);
+  ms = cluster_maxsum(ms, redf, xch);
   c.raw_max = ms.m;
   c.raw_logz = logf(ms.s);
 
@@ -307,13 +416,13 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   if (do_typ) {
     {
       float part = 0.f;
-      for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+      for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
         const float lp = (load_x(c, i) - c.raw_max) - c.raw_logz;
         const float p = expf(lp);
         const float term = lp * p;
         if (term == term) part += term;  // nansum
       }
-      c.ent = -block_sumf(part, redf);
+      c.ent = -cluster_sumf(part, redf, xch);
       const float rm = c.raw_max, lz = c.raw_logz, ent = c.ent;
       const float* xx = c.x;
       auto keyf = [=](int i) {
@@ -321,7 +430,7 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
         return __float_as_uint(fabsf((-lp) - ent));
       };
       auto wf = [=](int i) { return expf((xx[i] - rm) - lz); };
-      const uint32_t k = select_weighted_asc(V, keyf, wf, c.p.typical_p, false, histf, bcast);
+      const uint32_t k = select_weighted_asc(lo, hi, keyf, wf, c.p.typical_p, false, histf, histsumf, bcast);
       c.typ_thr = __uint_as_float(k);
       c.typical = true;
     }
@@ -331,54 +440,54 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
     token = (int)c.p.seed_lo;
   } else if (greedy) {
     if (!greedy_fast) {  // typical-p + greedy (method SAMPLE, temperature 0): argmax after the mask is known
-      for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+      for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
         const float yy = process(c, i, load_x(c, i));
         if (best.i < 0 || yy > best.v) best = {yy, i};
       }
     }
-    best = block_argmax(best, redf, redi);
+    best = cluster_argmax(best, redf, redi, xch);
     token = best.i;
   } else {
     // ---- processed logits / temperature -> scratch, running max
     float mx = -INFINITY;
     const float temp = c.p.temperature;
-    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+    for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
       float v = process(c, i, load_x(c, i));
       v = __fdiv_rn(v, temp);
       y[i] = v;
       mx = fmaxf(mx, v);
     }
     {
-      MaxSum t = block_maxsum(MaxSum{mx, 0.f}, redf);
+      MaxSum t = cluster_maxsum(MaxSum{mx, 0.f}, redf, xch);
       mx = t.m;
     }
     // ---- top-k (S6): keep y >= k-th largest value
     float lo_thr = -INFINITY;
     if (c.p.top_k > 0 && c.p.top_k < V) {
       auto keyf = [=](int i) { return f2key(y[i]); };
-      lo_thr = key2f(select_kth_largest(V, keyf, c.p.top_k, histi, bcast));
+      lo_thr = key2f(select_kth_largest(lo, hi, keyf, c.p.top_k, histi, histsumi, bcast));
     }
     // ---- top-p (S6): drop the low-probability tail whose cumulative mass <= 1 - p
     if (c.p.top_p < 1.0f) {
       float part = 0.f;
-      for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+      for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
         const float v = y[i];
         if (v >= lo_thr) part += expf(v - mx);
       }
-      const float z = block_sumf(part, redf);
+      const float z = cluster_sumf(part, redf, xch);
       const float lt = lo_thr;
       auto keyf = [=](int i) { return f2key(y[i]); };
       auto wf = [=](int i) {
         const float v = y[i];
         return (v >= lt) ? expf(v - mx) / z : 0.f;
       };
-      const uint32_t k = select_weighted_asc(V, keyf, wf, 1.0f - c.p.top_p, true, histf, bcast);
+      const uint32_t k = select_weighted_asc(lo, hi, keyf, wf, 1.0f - c.p.top_p, true, histf, histsumf, bcast);
       lo_thr = fmaxf(lo_thr, key2f(k));
     }
     // ---- exponential race == Gumbel max over the kept set
     const uint2 key = make_uint2(c.p.seed_lo, c.p.seed_hi);
     ValIdx bs{-INFINITY, -1};
-    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+    for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
       const float v = y[i];
       if (v >= lo_thr && v != -INFINITY) {
         const uint4 rnd = philox4x32(make_uint4((uint32_t)i, c.p.step, 0u, 0u), key);
@@ -387,15 +496,15 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
         if (bs.i < 0 || score > bs.v) bs = {score, i};
       }
     }
-    bs = block_argmax(bs, redf, redi);
+    bs = cluster_argmax(bs, redf, redi, xch);
     token = bs.i;
     if (token < 0) {  // everything masked (degenerate): fall back to raw argmax
       ValIdx b2{-INFINITY, -1};
-      for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+      for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
         const float v = load_x(c, i);
         if (b2.i < 0 || v > b2.v) b2 = {v, i};
       }
-      b2 = block_argmax(b2, redf, redi);
+      b2 = cluster_argmax(b2, redf, redi, xch);
       token = b2.i;
     }
   }
@@ -406,11 +515,11 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   if (want_lp) {
     tok_lp = (load_x(c, token) - c.raw_max) - c.raw_logz;
     int cnt = 0;
-    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+    for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
       const float lp = (load_x(c, i) - c.raw_max) - c.raw_logz;
       cnt += (lp >= tok_lp) ? 1 : 0;
     }
-    rank = block_sumi(cnt, redi);
+    rank = cluster_sumi(cnt, redi, xch);
   }
   SampleOut* o = outs + r;
   const int n_topn = min(c.p.n_topn, MAX_TOPN);
@@ -419,20 +528,20 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   for (int n = 0; n < n_topn; ++n) {
     // next element in (value desc, index asc) order strictly after (prev_v, prev_i)
     ValIdx b{-INFINITY, -1};
-    for (int i = threadIdx.x; i < V; i += SAMP_THREADS) {
+    for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
       const float v = load_x(c, i);
       const bool after = (v < prev_v) || (v == prev_v && i > prev_i);
       if (after && (b.i < 0 || v > b.v)) b = {v, i};
     }
-    b = block_argmax(b, redf, redi);
+    b = cluster_argmax(b, redf, redi, xch);
     prev_v = b.v;
     prev_i = b.i;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && crank == 0) {
       o->topn_ids[n] = b.i;
       o->topn_lps[n] = (b.v - c.raw_max) - c.raw_logz;
     }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && crank == 0) {
     o->token = token;
     o->logprob = tok_lp;
     o->rank = rank;
@@ -447,7 +556,7 @@ cudaError_t sampler_launch(const float* logits, int ld, int vocab, const SampleR
                            cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   if (vocab % 8 != 0 || ld % 8 != 0) return cudaErrorInvalidValue;
-  return launch_k(tgis_sampler_kernel, dim3(n_rows), dim3(SAMP_THREADS), 0, stream, logits, ld, vocab, rows,
+  return launch_k(tgis_sampler_kernel, dim3(n_rows * SAMP_CL), dim3(SAMP_THREADS), 0, stream, logits, ld, vocab, rows,
                   const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out);
 }
 
