@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--gen-len", type=int, default=128)
     ap.add_argument("--parallel", default="dp", choices=["dp", "tp"],
                     help="N>1: dp = independent replicas (default, weak scaling); tp = ONE tensor-parallel engine over N GPUs")
+    ap.add_argument("--max-batched-tokens", type=int, default=2048,
+                    help="scheduler token budget per step (= chunked-prefill size); 2048 = this engine's and vLLM's "
+                         "online-serving default")
     ap.add_argument("--sampling", default="greedy", choices=["greedy", "cfg3"],
                     help="cfg3 = repetition penalty 1.2 + length penalty (64, 1.05) + typical_p 0.9 sampling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -269,7 +272,7 @@ def run_ours(args) -> dict | None:
         dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local))
         tp_kw = dict(tp_size=tp, tp_rank=rank, nccl_id=ids[0], shm_name=f"/tgis_bench_{os.environ.get('MASTER_PORT', '0')}")
         kv_bytes //= tp
-    eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=8192, kv_cache_bytes=kv_bytes, device=local, seed=1234,
+    eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=args.max_batched_tokens, kv_cache_bytes=kv_bytes, device=local, seed=1234,
                        **tp_kw)
     # synthetic N(0, 0.02) weights generated on the device, one tensor at a time ("PyTorch tensors for weights only");
     # under tp every rank draws the SAME full tensor (same seed) and the engine keeps its shard
@@ -411,6 +414,7 @@ def run_ours(args) -> dict | None:
                                f"(BASELINE.json configs[1])", "batch_per_gpu": B, "prompt_len": P, "gen_len": G,
                    "parallelism": (f"tp{tp} (one engine, NCCL all-reduce after o/down proj, all-gather of logits)"
                                    if tp > 1 else f"dp{world} (independent replicas, no collective)"),
+                   "scheduler": f"continuous batching, chunked prefill, {args.max_batched_tokens} tokens per step",
                    "l2": "inputs larger than L2 (15 GB of weights streamed per decode step)",
                    "timing": "value: CUDA events on the engine stream over pure-decode steps; e2e: wall clock"},
         "e2e": {"value": (n_tok_s - n_rep * B * args.steps) / decode_wall_m if decode_wall_m > 0 else None,

@@ -114,7 +114,6 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   }
   __syncwarp();
   griddep_launch();
-
   // ---- item list: host-written for this step, not produced by a preceding kernel -> readable before griddep_wait
   const int4* it4 = reinterpret_cast<const int4*>(items);  // record e = it4[2e] (q_row, kv_len, seq_split, -), it4[2e+1] (blocks)
   const int n_flat = it4[0].x * n_kv;
@@ -128,6 +127,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
     return (n_tok + KV_BLOCK - 1) / KV_BLOCK;
   };
   auto pick = [](const int4& b, int j) { return j == 0 ? b.x : j == 1 ? b.y : j == 2 ? b.z : b.w; };
+  const uint64_t kv_policy = policy_evict_first();
   int4 c_it = item_at(f);
   int4 c_nxt = c_it;
   // ---- issue cursor: runs DEC_RING tiles ahead of consumption, across item boundaries
@@ -143,7 +143,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       const __nv_bfloat16* src =
           (i_kv ? v_cache : k_cache) + ((size_t)pick(i_blks, i_jb) * n_kv + i_kvh) * (KV_BLOCK * HEAD_DIM);
       mbar_arrive_expect_tx(&full[i_buf], TILE_BYTES);
-      bulk_load_1d(ring + i_buf * TILE_BYTES, src, TILE_BYTES, &full[i_buf]);
+      bulk_load_1d_hint(ring + i_buf * TILE_BYTES, src, TILE_BYTES, &full[i_buf], kv_policy);  // read once per step
     }
     i_buf = i_buf == DEC_RING - 1 ? 0 : i_buf + 1;
     if (i_kv == 0) {
