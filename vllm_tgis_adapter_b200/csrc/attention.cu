@@ -118,7 +118,11 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   const int4* it4 = reinterpret_cast<const int4*>(items);  // record e = it4[2e] (q_row, kv_len, seq_split, -), it4[2e+1] (blocks)
   const int n_flat = it4[0].x * n_kv;
   const int n_slots = gridDim.x * DEC_WARPS;
-  int f = warp * gridDim.x + blockIdx.x;  // consecutive items land on different SMs
+  const int gw = warp * gridDim.x + blockIdx.x;  // consecutive items land on different SMs
+  // The host lists the items longest first; round k hands item k*n_slots + (k even ? gw : n_slots-1-gw) to warp gw
+  // (boustrophedon), so the warps that got the longest items of one round get the shortest of the next.
+  auto item_of_round = [&](int k) { return k * n_slots + ((k & 1) ? n_slots - 1 - gw : gw); };
+  int f = gw;
   if (f >= n_flat) return;
   auto item_at = [&](int ff) { return __ldg(&it4[2 * (1 + ff / n_kv)]); };
   auto blocks_at = [&](int ff) { return __ldg(&it4[2 * (1 + ff / n_kv) + 1]); };
@@ -133,9 +137,10 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   // ---- issue cursor: runs DEC_RING tiles ahead of consumption, across item boundaries
   int i_f = f, i_kvh = f % n_kv, i_jb = 0, i_nblk = n_blk_of(c_it), i_kv = 0, i_buf = 0;
   int4 i_nxt = c_it, i_blks = blocks_at(f), i_blks_nxt = i_blks;  // block ids of the item being issued / the next one
-  if (f + n_slots < n_flat) {
-    i_nxt = item_at(f + n_slots);
-    i_blks_nxt = blocks_at(f + n_slots);
+  int i_k = 0, c_k = 0;  // round of the issue cursor / of the consumer
+  if (item_of_round(1) < n_flat) {
+    i_nxt = item_at(item_of_round(1));
+    i_blks_nxt = blocks_at(item_of_round(1));
   }
   auto issue_tile = [&]() {
     if (i_f >= n_flat) return;
@@ -152,15 +157,15 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
     }
     i_kv = 0;
     if (++i_jb == i_nblk) {  // next item of this warp; its record was requested one item ago
-      i_f += n_slots;
+      i_f = item_of_round(++i_k);
       if (i_f >= n_flat) return;
       i_kvh = i_f % n_kv;
       i_jb = 0;
       i_nblk = n_blk_of(i_nxt);
       i_blks = i_blks_nxt;
-      if (i_f + n_slots < n_flat) {
-        i_nxt = item_at(i_f + n_slots);
-        i_blks_nxt = blocks_at(i_f + n_slots);
+      if (item_of_round(i_k + 1) < n_flat) {
+        i_nxt = item_at(item_of_round(i_k + 1));
+        i_blks_nxt = blocks_at(item_of_round(i_k + 1));
       }
     }
   };
@@ -182,15 +187,16 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   const uint32_t ring_base = smem_u32(ring);
   int c_buf = 0, c_ph = 0, q_ph = 0;
 
-  for (; f < n_flat; f += n_slots) {
+  for (; f < n_flat; f = item_of_round(++c_k)) {
     const int kvh = f % n_kv;
     const int seq = c_it.z & 0xffff, split = c_it.z >> 16;
     const int kv_len = c_it.y;
     const int n_splits = (kv_len + DEC_TOK - 1) / DEC_TOK;
     const int n_tok = min(DEC_TOK, kv_len - split * DEC_TOK);
     const int n_blk = (n_tok + KV_BLOCK - 1) / KV_BLOCK;
-    const bool has_next = f + n_slots < n_flat;
-    if (has_next) c_nxt = item_at(f + n_slots);
+    const int f_next = item_of_round(c_k + 1);
+    const bool has_next = f_next < n_flat;
+    if (has_next) c_nxt = item_at(f_next);
     // ---- Q^T as B fragments: n = head (lane/4), 8 k-steps of 16 dims; heads >= G are zero columns
     mbar_wait(q_bar, q_ph);
     q_ph ^= 1;
@@ -229,7 +235,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       if (++c_buf == DEC_RING) { c_buf = 0; c_ph ^= 1; }
       if (jb == 0) {  // q_s was copied to registers above; by now the next item's record has arrived
         __syncwarp();
-        if (has_next) issue_q(c_nxt, (f + n_slots) % n_kv);
+        if (has_next) issue_q(c_nxt, f_next % n_kv);
       }
       // ---- online softmax; st[mt][e]: token mt*16 + hr + (e>>1)*8, head 2*t4 + (e&1)
       const int valid = min(KV_BLOCK, n_tok - jb * KV_BLOCK);

@@ -109,21 +109,28 @@ struct DecItem {       // 32 bytes
   int32_t blocks[DECODE_SPLIT / KV_BLOCK];  // physical KV blocks of the split (resolved on the host: no table walk)
 };
 static_assert(DECODE_SPLIT / KV_BLOCK == 4 && sizeof(DecItem) == 32, "DecItem is read as two int4");
+// Entries are listed longest first (all full splits, then the partial tails by decreasing length): the kernel deals
+// them to its warps round-robin, so the order is the load balance.  Ties keep (sequence, split) order: deterministic.
 inline int decode_items_build(DecItem* items, const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs,
                               const int32_t* block_table, int bt_stride) {
+  constexpr int BPS = DECODE_SPLIT / KV_BLOCK;
   int n = 0;
-  for (int i = 0; i < n_seqs; ++i) {
-    const AttnSeq& sq = seqs[seq_ids ? seq_ids[i] : i];
-    const int n_splits = (sq.kv_len + DECODE_SPLIT - 1) / DECODE_SPLIT;
+  auto emit = [&](int i, const AttnSeq& sq, int sp) {
     const int n_blocks = (sq.kv_len + KV_BLOCK - 1) / KV_BLOCK;
     const int32_t* row = block_table + (size_t)sq.block_row * bt_stride;
-    for (int sp = 0; sp < n_splits; ++sp) {
-      DecItem& it = items[++n];
-      it = DecItem{sq.q_start, sq.kv_len, i | (sp << 16), 0, {0, 0, 0, 0}};
-      for (int j = 0; j < DECODE_SPLIT / KV_BLOCK; ++j) {
-        const int b = sp * (DECODE_SPLIT / KV_BLOCK) + j;
-        it.blocks[j] = b < n_blocks ? row[b] : 0;
-      }
+    DecItem& it = items[++n];
+    it = DecItem{sq.q_start, sq.kv_len, i | (sp << 16), 0, {0, 0, 0, 0}};
+    for (int j = 0; j < BPS; ++j) it.blocks[j] = sp * BPS + j < n_blocks ? row[sp * BPS + j] : 0;
+  };
+  for (int i = 0; i < n_seqs; ++i) {  // full splits
+    const AttnSeq& sq = seqs[seq_ids ? seq_ids[i] : i];
+    for (int sp = 0; sp < sq.kv_len / DECODE_SPLIT; ++sp) emit(i, sq, sp);
+  }
+  for (int nb = BPS; nb >= 1; --nb) {  // tails: 4, 3, 2, 1 blocks (a tail of exactly DECODE_SPLIT tokens was a full split)
+    for (int i = 0; i < n_seqs; ++i) {
+      const AttnSeq& sq = seqs[seq_ids ? seq_ids[i] : i];
+      const int rem = sq.kv_len % DECODE_SPLIT;
+      if (rem > 0 && (rem + KV_BLOCK - 1) / KV_BLOCK == nb) emit(i, sq, sq.kv_len / DECODE_SPLIT);
     }
   }
   items[0] = DecItem{n, 0, 0, 0, {0, 0, 0, 0}};
