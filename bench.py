@@ -229,6 +229,34 @@ def cpu_reference(args, steps: int, warmup: int) -> dict:
             "ms_per_step": 1e3 * t_full}
 
 
+def ncu_traffic_per_launch(n_layers: int):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/, produced by scripts/gpu_check.sh prof_gemm: the qkv, o, gate_up, down and lm_head launches of one decode
+    step at batch 32), weighted like the timed mix: n_layers x the four layer GEMMs + one lm_head."""
+    import csv
+    import glob
+    files = sorted(glob.glob(str(Path(__file__).resolve().parent / "profiles" / "r*_ncu_full_gemm_tcgen05.csv")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            rows = list(csv.DictReader(f))
+        def col(row, name):
+            for k, v in row.items():
+                if k.startswith(name):
+                    unit = k[k.index("[") + 1:k.index("]")] if "[" in k else "byte"
+                    mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+                    return float(v) * mult
+            raise KeyError(name)
+        per = [col(r, "dram__bytes_read.sum") + col(r, "dram__bytes_write.sum") for r in rows]
+        if len(per) != 5:
+            return None, None
+        total = n_layers * sum(per[:4]) + per[4]
+        return total / (4 * n_layers + 1), f"{Path(files[-1]).name} (ncu --set full, cold-cache replay)"
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def reduce_over_ranks(max_vals: list[float], sum_vals: list[float], device: str) -> tuple[list[float], list[float]]:
     """Whole-job aggregation for the N>1 (data-parallel replicas) path: times -> MAX over ranks, counts -> SUM.
     Works on any initialised torch.distributed backend (NCCL on the GPU box, gloo in tests/test_multirank_cpu.py)."""
@@ -404,6 +432,7 @@ def run_ours(args) -> dict | None:
     bytes_step = (n_params * 2 + B * (P + G / 2) * kv_tok) / tp + B * cfg.vocab * 4
     step_ms = dec_ms / max(dec_steps, 1)
     achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else None
+    traffic, traffic_src = ncu_traffic_per_launch(cfg.n_layers) if args.model == "llama3-8b" and tp == 1 else (None, None)
     out = {
         "metric": "decode tokens/sec + p50 TTFT, 512-in/128-out batch, 1/2/4/8xB200 vs CPU ref",
         "value": dec_tok_s / (dec_ms_m * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -425,7 +454,8 @@ def run_ours(args) -> dict | None:
         "gpu_launches": int(launches_s),
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "kernel": "gemm_bf16_tcgen05_kernel", "launches_timed": int(gemm_calls),
                      "algorithmic_bytes_per_launch": gemm_bytes / max(gemm_calls, 1),
                      "avg_launch_us": 1e3 * gemm_ms / max(gemm_calls, 1),

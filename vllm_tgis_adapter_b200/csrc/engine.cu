@@ -256,7 +256,7 @@ struct tgis_engine {
   bool use_chain = false;
   DevBuf<int> chain_sync;
   int chain_pf_depth = 16;  // TGIS_CHAIN_PF
-  int l2_prefetch_kb = 20;  // k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
+  int l2_prefetch_kb = 0;   // (off: measured no gain, costs DRAM traffic in the issuing kernel) k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
   std::vector<double> prof_bytes;  // algorithmic bytes of the GEMM between events 2i and 2i+1
