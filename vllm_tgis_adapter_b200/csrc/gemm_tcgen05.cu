@@ -15,6 +15,11 @@
 //  * persistent stream-K: the (tile, k-block) iteration space is cut into gridDim.x equal contiguous ranges, so all
 //    148 SMs stream the same number of weight bytes whatever N is.  A tile split across CTAs is reduced by the
 //    LAST-arriving CTA summing the fp32 partials in fixed CTA order -> bit-deterministic and independent of timing.
+//  * few-tile GEMMs (qkv / o / down at decode: every tile is split by the same factor s <= 8): the s CTAs of a tile
+//    are launched as ONE thread-block cluster and the split-K reduction never leaves the chip: every CTA parks its
+//    fp32 partial in its own shared memory (the drained smem ring), one cluster barrier, then CTA r reduces the tokens
+//    t = r (mod s) by reading its peers through distributed shared memory in rank order (same sums, same order as the
+//    global-memory fix-up: bit-identical) and writes the final rows.
 #include <string.h>
 
 #include "kernels.h"
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BT <= 64 && TGIS_GEMM_DECODE_ST
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
                          void* __restrict__ Yv, int ldy, int T, int N, int K, float* __restrict__ ws,
                          int* __restrict__ counters, int stream_weights, int out_f32,
-                         const __grid_constant__ CUtensorMap next_wmap, GemmNext nxt) {
+                         const __grid_constant__ CUtensorMap next_wmap, GemmNext nxt, int cluster_split) {
   // output: bf16 (rounded once from the fp32 accumulator, = F.linear in model dtype) or raw fp32 (lm_head logits)
   __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(Yv);
   float* __restrict__ Yf = reinterpret_cast<float*>(Yv);
@@ -159,6 +164,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   const uint32_t tmem_base = *tmem_base_smem;
   griddep_launch();  // PDL: the next kernel may start its prologue now
   if (threadIdx.x == 0) TL(1);  // setup done (barriers, TMEM)
+  int cl_tile = -1, cl_tvalid = 0;  // cluster mode: the split tile this CTA contributed to (epilogue warps)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -307,9 +313,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
               }
           }
         } else {
+          // split tile: fp32 partial to the global workspace, or (cluster mode) to this CTA's own shared memory --
+          // the ring is idle by now: this CTA's only unit has retired all its MMAs
+          float* dst = cluster_split > 0 ? reinterpret_cast<float*>(smem) : my_ws;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < t_valid) my_ws[(size_t)(c0 + j) * GEMM_BN + row] = __uint_as_float(r[j]);
+            if (c0 + j < t_valid) dst[(size_t)(c0 + j) * GEMM_BN + row] = __uint_as_float(r[j]);
         }
       }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
@@ -320,7 +329,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       acc ^= 1;
 
       if (ep_tid == 0) TL(6);  // TMEM drained, partial/direct stores issued
-      if (partial) {
+      if (partial && cluster_split > 0) {
+        cl_tile = tile;  // reduced after the cluster barrier below
+        cl_tvalid = t_valid;
+      } else if (partial) {
         // stream-K fix-up: last arriver reduces all partials of this tile in CTA order (deterministic)
         // publish: CTA-wide barrier, then ONE acq_rel atomic (cumulative over the barrier) instead of membar.gl
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
@@ -408,6 +420,68 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
     }
   }
 
+  if (cluster_split > 0) {
+    // ---- on-chip split-K reduction across the cluster (all threads take part in the two cluster barriers)
+    cluster_sync_all();  // every CTA's partial is in its shared memory
+    if (warp >= 2 && cl_tile >= 0) {
+      const int ep_tid = (warp - 2) * 32 + lane_id();
+      const int crank = (int)cluster_ctarank();
+      const int r4 = (ep_tid & 31) * 4;   // this thread's 4 consecutive weight rows
+      const int tq = ep_tid >> 5;         // token phase 0..3
+      const int n4 = cl_tile * GEMM_BN + r4;
+      const uint32_t stg = smem_u32(smem);
+      constexpr int FIX_T = 4;
+      // tokens of this CTA: t = crank + split * i; thread takes i = tq (mod 4)
+      for (int i0 = tq; crank + cluster_split * i0 < cl_tvalid; i0 += 4 * FIX_T) {
+        float4 acc[FIX_T];
+#pragma unroll
+        for (int j = 0; j < FIX_T; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < cluster_split; ++c) {  // contributor rank order = k order: deterministic
+          const uint32_t peer = dsmem_addr(stg, (uint32_t)c);
+          float4 v[FIX_T];
+#pragma unroll
+          for (int j = 0; j < FIX_T; ++j) {
+            const int t = crank + cluster_split * (i0 + 4 * j);
+            v[j] = t < cl_tvalid ? ld_dsmem_f4(peer + (uint32_t)((t * GEMM_BN + r4) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < FIX_T; ++j) {
+            acc[j].x += v[j].x; acc[j].y += v[j].y; acc[j].z += v[j].z; acc[j].w += v[j].w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < FIX_T; ++j) {
+          const int t = crank + cluster_split * (i0 + 4 * j);
+          if (t < cl_tvalid) {
+            const size_t o = (size_t)t * ldy + n4;
+            const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+            if (out_f32 == 2) {
+              __nv_bfloat16* yo = Y + (size_t)t * ldy + (n4 >> 1);
+              if (n4 + 1 < N) yo[0] = swiglu_bf16(av[0], av[1]);
+              if (n4 + 3 < N) yo[1] = swiglu_bf16(av[2], av[3]);
+            } else if (n4 + 3 < N && (ldy & 3) == 0) {
+              if (out_f32 == 1) {
+                *reinterpret_cast<float4*>(Yf + o) = acc[j];
+              } else {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(av[0], av[1]), hi = __floats2bfloat162_rn(av[2], av[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(Y + o) = pk;
+              }
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (n4 + e < N) {
+                  if (out_f32) Yf[o + e] = av[e];
+                  else Y[o + e] = __float2bfloat16_rn(av[e]);
+                }
+            }
+          }
+        }
+      }
+    }
+    cluster_sync_all();  // nobody exits while a peer may still read its shared memory
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TL(9);  // all roles done
@@ -917,6 +991,15 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
+static bool gemm_cluster_enabled() {  // TGIS_GEMM_CLUSTER=0: always reduce split tiles through global memory
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TGIS_GEMM_CLUSTER");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int gemm_pick_bt(int T) {
   if (T <= 16) return 16;
   if (T <= 32) return 32;
@@ -950,6 +1033,18 @@ int gemm_grid_size(int T, int N, int K, int num_sms) {
   return grid;
 }
 
+// Even-split launches (every tile cut into `split` equal k-ranges owned by `split` consecutive CTAs): the factor, or 0.
+int gemm_even_split(int T, int N, int K, int num_sms) {
+  const int BT = gemm_pick_bt(T);
+  const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
+  const long long tiles = (long long)n_tiles * t_tiles;
+  if (t_tiles != 1 || tiles > num_sms / 2) return 0;
+  const int grid = gemm_grid_size(T, N, K, num_sms);
+  if (grid % tiles != 0) return 0;
+  const int split = (int)(grid / tiles);
+  return (split >= 2 && KB % split == 0) ? split : 0;  // equal k-ranges <=> unit boundaries fall on CTA boundaries
+}
+
 GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_prefetch) {
   GemmNext n{};
   const int BT = gemm_pick_bt(T_next);
@@ -976,8 +1071,33 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, v
   const int t_tiles = (T + BT - 1) / BT;
   const int grid = gemm_grid_size(T, N, K, num_sms);
   const int stream_weights = (t_tiles == 1) ? 1 : 0;
+  // cluster mode: on-chip split-K reduction when every tile is split evenly over <= 8 consecutive CTAs, the fp32
+  // partial fits the drained ring, and all clusters can be co-resident (checked once per (BT, split))
+  static int cluster_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 0 unknown, 1 yes, -1 no
+  int split = gemm_cluster_enabled() ? gemm_even_split(T, N, K, num_sms) : 0;
+  if (split > 8 || (size_t)BT * GEMM_BN * sizeof(float) > (size_t)Cfg::STAGES * Cfg::STAGE_BYTES) split = 0;
+  if (split > 0 && cluster_ok[split] == 0) {
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(split * (num_sms / split));
+    qc.blockDim = dim3(GEMM_THREADS);
+    qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = split;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n_clusters = 0;
+    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, gemm_bf16_tcgen05_kernel<BT>, &qc);
+    cluster_ok[split] = (qe == cudaSuccess && n_clusters * split >= grid) ? 1 : -1;
+    if (qe != cudaSuccess) cudaGetLastError();
+  }
+  if (split > 0 && cluster_ok[split] == 1)
+    return launch_k_cluster(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, split,
+                            wmap, xmap, Y, ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, split);
   return launch_k(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
-                  ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt);
+                  ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, 0);
 }
 
 // xmap must have been built with box_rows == gemm_pick_bt(T)
