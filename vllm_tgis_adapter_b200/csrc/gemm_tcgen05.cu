@@ -1033,7 +1033,7 @@ int gemm_grid_size(int T, int N, int K, int num_sms) {
   return grid;
 }
 
-// Even-split launches (every tile cut into `split` equal k-ranges owned by `split` consecutive CTAs): the factor, or 0.
+// Even-split launches (every tile cut into `split` k-ranges owned by `split` consecutive CTAs): the factor, or 0.
 int gemm_even_split(int T, int N, int K, int num_sms) {
   const int BT = gemm_pick_bt(T);
   const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
@@ -1042,7 +1042,9 @@ int gemm_even_split(int T, int N, int K, int num_sms) {
   const int grid = gemm_grid_size(T, N, K, num_sms);
   if (grid % tiles != 0) return 0;
   const int split = (int)(grid / tiles);
-  return (split >= 2 && KB % split == 0) ? split : 0;  // equal k-ranges <=> unit boundaries fall on CTA boundaries
+  // grid == tiles * split: CTA c's k-range [total*c/grid, total*(c+1)/grid) starts a tile exactly at every multiple of
+  // split, so each CTA owns ONE unit inside ONE tile even when split does not divide KB (qkv: 64 k-blocks over 3 CTAs)
+  return (split >= 2 && KB >= split) ? split : 0;
 }
 
 GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_prefetch) {
