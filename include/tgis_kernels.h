@@ -35,6 +35,10 @@ int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* 
 int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev, const int32_t* seqs_host,
                      int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows, int32_t bt_stride, void* out_dev,
                      int32_t n_q, int32_t n_kv, float scale);
+/* host-only: the decode work-item list of a step (csrc/kernels.h DecItem: q_row, kv_len, seq | split << 16, 0,
+ * blocks[4]); record 0 holds the entry count; entries are listed longest first */
+int tgis_k_decode_items(const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_stride,
+                        int32_t* items_out, int32_t capacity);
 /* decode-only, timed over `iters` launches rotating through n_layers cache copies; us_out = avg device us per launch */
 int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev,
                            const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows,

@@ -48,3 +48,45 @@ def test_no_gpu_means_loud_failure_not_fallback():
     h = C.c_void_p()
     assert lib.tgis_engine_create(C.byref(cfg), C.byref(h)) != 0
     assert b"no CUDA device" in lib.tgis_last_error() or b"CUDA" in lib.tgis_last_error()
+
+
+def test_decode_work_items_host_logic():
+    """The scheduler's decode work-item list (csrc/kernels.h decode_items_build, host code, no GPU): one record per
+    (sequence, 128-token split) with the split's physical block ids resolved from the block table, listed longest first
+    (full splits, then tails by decreasing block count; ties in sequence order) -- the order IS the attention kernel's
+    load balance, and the record contents are what it trusts without re-checking."""
+    import numpy as np
+
+    lib = _lib.load_library()
+    kv_lens = [576, 1, 128, 129, 300, 96, 640]
+    bt_stride = 24
+    rng = np.random.default_rng(0)
+    bt = rng.permutation(len(kv_lens) * bt_stride).astype(np.int32).reshape(len(kv_lens), bt_stride)
+    seqs = np.array([[10 + i, 1, kv, i] for i, kv in enumerate(kv_lens)], dtype=np.int32)
+    cap = 64
+    items = np.zeros((1 + cap, 8), dtype=np.int32)
+    n = lib.tgis_k_decode_items(seqs.ctypes.data_as(C.POINTER(C.c_int32)), len(kv_lens),
+                                bt.ctypes.data_as(C.POINTER(C.c_int32)), bt_stride,
+                                items.ctypes.data_as(C.POINTER(C.c_int32)), cap)
+    assert n == sum((kv + 127) // 128 for kv in kv_lens) == items[0, 0]
+    recs = items[1:1 + n]
+    sizes, seen = [], set()
+    for q_row, kv_len, seq_split, _, *blocks in recs.tolist():
+        seq, split = seq_split & 0xffff, seq_split >> 16
+        assert (seq, split) not in seen
+        seen.add((seq, split))
+        assert q_row == 10 + seq and kv_len == kv_lens[seq]
+        n_tok = min(128, kv_len - split * 128)
+        assert n_tok > 0
+        n_blk = (n_tok + 31) // 32
+        assert blocks[:n_blk] == bt[seq, split * 4:split * 4 + n_blk].tolist() and blocks[n_blk:] == [0] * (4 - n_blk)
+        sizes.append(n_blk if n_tok < 128 else 5)          # full splits sort before 4-block tails
+    assert sizes == sorted(sizes, reverse=True)
+    assert len(seen) == n
+    # ties keep (sequence, split) order
+    full = [(s & 0xffff, s >> 16) for s, z in zip(recs[:, 2].tolist(), sizes) if z == 5]
+    assert full == sorted(full)
+    # capacity is checked, not overrun
+    assert lib.tgis_k_decode_items(seqs.ctypes.data_as(C.POINTER(C.c_int32)), len(kv_lens),
+                                   bt.ctypes.data_as(C.POINTER(C.c_int32)), bt_stride,
+                                   items.ctypes.data_as(C.POINTER(C.c_int32)), 3) == -1

@@ -228,6 +228,22 @@ int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const v
   return 0;
 }
 
+// Host-only: the decode work-item list the scheduler builds for a step (no GPU needed).  seqs_host as in
+// tgis_k_attention (all decode sequences); items_out: (1 + capacity) x 8 int32 records; returns the entry count or -1.
+int tgis_k_decode_items(const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_stride,
+                        int32_t* items_out, int32_t capacity) {
+  std::vector<AttnSeq> seqs(n_seqs);
+  long long need = 0;
+  for (int s = 0; s < n_seqs; ++s) {
+    seqs[s] = AttnSeq{seqs_host[4 * s], seqs_host[4 * s + 1], seqs_host[4 * s + 2], seqs_host[4 * s + 3]};
+    need += (seqs[s].kv_len + DECODE_SPLIT - 1) / DECODE_SPLIT;
+  }
+  if (need > capacity) return kfail("capacity too small");
+  static_assert(sizeof(DecItem) == 32, "8 int32 per record");
+  return decode_items_build(reinterpret_cast<DecItem*>(items_out), seqs.data(), nullptr, n_seqs, block_table_host,
+                            bt_stride);
+}
+
 int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
                    void* seen_bitmap_dev, void* out_host) {
   Tmp<SampleRow> rows;
