@@ -255,6 +255,7 @@ struct tgis_engine {
   // under full HBM load vs ~9 us per kernel boundary.  Kept because it is bit-identical and documents the experiment.
   bool use_chain = false;
   DevBuf<int> chain_sync;
+  bool fuse_rope = true;
   int chain_pf_depth = 16;  // TGIS_CHAIN_PF
   int l2_prefetch_kb = 0;   // (off: measured no gain, costs DRAM traffic in the issuing kernel) k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
   std::vector<cudaEvent_t> prof_events;
@@ -316,6 +317,7 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_L2_PREFETCH_KB")) l2_prefetch_kb = atoi(e);
     if (const char* e = getenv("TGIS_CHAIN")) use_chain = atoi(e) != 0;
     if (const char* e = getenv("TGIS_CHAIN_PF")) chain_pf_depth = atoi(e);
+    if (const char* e = getenv("TGIS_FUSE_ROPE")) fuse_rope = atoi(e) != 0;
     chain_sync.alloc(CHAIN_MAX_STEPS + 1);
     chain_sync.zero();
 
@@ -607,7 +609,8 @@ struct tgis_engine {
   // next_wm / nT,nN,nK describe the GEMM that follows this one in the layer stack: its first weight boxes are
   // prefetched into L2 by this launch's producer warp (gemm_tcgen05.cu)
   void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, void* Y, int T, int N, int K,
-            int out_f32 = 0, const CUtensorMap* next_wm = nullptr, int nT = 0, int nN = 0, int nK = 0, int ldy = 0) {
+            int out_f32 = 0, const CUtensorMap* next_wm = nullptr, int nT = 0, int nN = 0, int nK = 0, int ldy = 0,
+            const GemmRope* rope = nullptr) {
     if (ldy == 0) ldy = N;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profiling && (!prof_decode_only || step_is_decode)) {
@@ -629,7 +632,7 @@ struct tgis_engine {
       GemmNext nx{};
       if (next_wm && l2_prefetch_kb > 0) nx = gemm_next_desc(nT, nN, nK, num_sms, l2_prefetch_kb);
       CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, ldy, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32,
-                          nx.kb_prefetch > 0 ? next_wm : nullptr, nx.kb_prefetch > 0 ? &nx : nullptr));
+                          nx.kb_prefetch > 0 ? next_wm : nullptr, nx.kb_prefetch > 0 ? &nx : nullptr, rope));
     }
     if (pe1) CK(cudaEventRecord(pe1, stream));
     ++n_launches;
@@ -705,6 +708,8 @@ struct tgis_engine {
     CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
     ++n_launches;
     const bool chained = use_chain && tp == 1 && T <= 256 && !cfg.debug_gemm_ref;
+    // RoPE + KV-cache scatter fused into the qkv GEMM's cluster epilogue (decode-shaped steps; TGIS_FUSE_ROPE=0: off)
+    const bool rope_fused = fuse_rope && !chained && !cfg.debug_gemm_ref && gemm_cluster_split(T, qkv_dim, H, num_sms) > 0;
     const int bi = bt_index(T);
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];
@@ -719,13 +724,17 @@ struct tgis_engine {
         if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
         else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
         ++n_launches;
-        gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim);
+        const GemmRope rp{ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin,
+                          k_cache.p + (size_t)li * kv_layer_elems, v_cache.p + (size_t)li * kv_layer_elems, nq, nkv};
+        gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim, 0, rope_fused ? &rp : nullptr);
       }
       bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
       bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
-      CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, nq, nkv,
-                             stream));
-      ++n_launches;
+      if (!rope_fused) {
+        CK(rope_kvwrite_launch(qkv.p, ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, nq, nkv,
+                               stream));
+        ++n_launches;
+      }
       if (n_dec > 0) {
         const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
         CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, ds<DecItem>(items_off(S)), n_dec * max_splits, d_seqs,

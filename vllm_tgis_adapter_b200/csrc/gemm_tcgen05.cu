@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BT <= 64 && TGIS_GEMM_DECODE_ST
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
                          void* __restrict__ Yv, int ldy, int T, int N, int K, float* __restrict__ ws,
                          int* __restrict__ counters, int stream_weights, int out_f32,
-                         const __grid_constant__ CUtensorMap next_wmap, GemmNext nxt, int cluster_split) {
+                         const __grid_constant__ CUtensorMap next_wmap, GemmNext nxt, int cluster_split,
+                         GemmRope rope) {
   // output: bf16 (rounded once from the fp32 accumulator, = F.linear in model dtype) or raw fp32 (lm_head logits)
   __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(Yv);
   float* __restrict__ Yf = reinterpret_cast<float*>(Yv);
@@ -455,7 +456,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           if (t < cl_tvalid) {
             const size_t o = (size_t)t * ldy + n4;
             const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
-            if (out_f32 == 2) {
+            if (rope.positions != nullptr) {
+              // ---- fused RoPE + KV-cache scatter (qkv projection; tile = one 128-dim head; arithmetic and rounding
+              // points of rope_kvwrite_kernel).  This thread holds dims r4..r4+3 of token t; the rotary partner
+              // dims (+-64) live in lane ^ 16.  The branch is warp-uniform (t, tile), so the shuffles are safe.
+              const int head = cl_tile, lane = lane_id();
+              float x[4], pr[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = bf16_round(av[e]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pr[e] = __shfl_xor_sync(0xffffffffu, x[e], 16);
+              const int d = r4 & 63;
+              if (head < rope.n_q + rope.n_kv) {
+                const int pos = __ldg(rope.positions + t);
+                const uint2 cs = __ldg(reinterpret_cast<const uint2*>(rope.cos_sin + (size_t)pos * HEAD_DIM + d));
+                const uint2 sn = __ldg(reinterpret_cast<const uint2*>(rope.cos_sin + (size_t)pos * HEAD_DIM + 64 + d));
+                const float cc[4] = {__uint_as_float(cs.x << 16), __uint_as_float(cs.x & 0xffff0000u),
+                                     __uint_as_float(cs.y << 16), __uint_as_float(cs.y & 0xffff0000u)};
+                const float ss[4] = {__uint_as_float(sn.x << 16), __uint_as_float(sn.x & 0xffff0000u),
+                                     __uint_as_float(sn.y << 16), __uint_as_float(sn.y & 0xffff0000u)};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = bf16_round(x[e] * cc[e]), b = bf16_round(pr[e] * ss[e]);
+                  x[e] = lane < 16 ? a - b : a + b;  // lo' = x1 c - x2 s ; hi' = x2 c + x1 s
+                }
+              }
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&p0);
+              pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              *reinterpret_cast<uint2*>(Y + o) = pk;
+              if (head >= rope.n_q) {
+                const int slot = __ldg(rope.slot_mapping + t);
+                if (slot >= 0) {
+                  const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
+                  const int chunk = r4 >> 3, sub = r4 & 7;  // 16-byte chunk of the head, 0 or 4 inside it
+                  if (head < rope.n_q + rope.n_kv) {  // K tile [chunk][token][8]
+                    __nv_bfloat16* kb = rope.k_cache + ((size_t)blk * rope.n_kv + (head - rope.n_q)) * (KV_BLOCK * HEAD_DIM);
+                    *reinterpret_cast<uint2*>(kb + (chunk * KV_BLOCK + off) * 8 + sub) = pk;
+                  } else {  // V tile [token][chunk ^ (token & 7)][8]
+                    __nv_bfloat16* vb = rope.v_cache +
+                                        ((size_t)blk * rope.n_kv + (head - rope.n_q - rope.n_kv)) * (KV_BLOCK * HEAD_DIM);
+                    *reinterpret_cast<uint2*>(vb + off * HEAD_DIM + ((chunk ^ (off & 7)) * 8) + sub) = pk;
+                  }
+                }
+              }
+            } else if (out_f32 == 2) {
               __nv_bfloat16* yo = Y + (size_t)t * ldy + (n4 >> 1);
               if (n4 + 1 < N) yo[0] = swiglu_bf16(av[0], av[1]);
               if (n4 + 3 < N) yo[1] = swiglu_bf16(av[2], av[3]);
@@ -1058,27 +1104,21 @@ GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_
   return n;
 }
 
+// cluster mode: on-chip split-K reduction when every tile is split evenly over <= 8 consecutive CTAs, the fp32 partial
+// fits the drained ring, and all clusters can be co-resident (checked once per (BT, split)).  Returns the split or 0.
 template <int BT>
-static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
-                             float* ws, int* counters, int num_sms, int out_f32, cudaStream_t stream,
-                             const CUtensorMap& next_wmap, const GemmNext& nxt) {
+static int cluster_split_bt(int T, int N, int K, int num_sms) {
   using Cfg = GemmCfg<BT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  const int t_tiles = (T + BT - 1) / BT;
-  const int grid = gemm_grid_size(T, N, K, num_sms);
-  const int stream_weights = (t_tiles == 1) ? 1 : 0;
-  // cluster mode: on-chip split-K reduction when every tile is split evenly over <= 8 consecutive CTAs, the fp32
-  // partial fits the drained ring, and all clusters can be co-resident (checked once per (BT, split))
   static int cluster_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 0 unknown, 1 yes, -1 no
   int split = gemm_cluster_enabled() ? gemm_even_split(T, N, K, num_sms) : 0;
   if (split > 8 || (size_t)BT * GEMM_BN * sizeof(float) > (size_t)Cfg::STAGES * Cfg::STAGE_BYTES) split = 0;
   if (split > 0 && cluster_ok[split] == 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      attr_set = true;
+    }
+    const int grid = gemm_grid_size(T, N, K, num_sms);
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3(split * (num_sms / split));
     qc.blockDim = dim3(GEMM_THREADS);
@@ -1095,21 +1135,56 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, v
     cluster_ok[split] = (qe == cudaSuccess && n_clusters * split >= grid) ? 1 : -1;
     if (qe != cudaSuccess) cudaGetLastError();
   }
-  if (split > 0 && cluster_ok[split] == 1)
+  return (split > 0 && cluster_ok[split] == 1) ? split : 0;
+}
+
+// The split factor gemm_bf16_launch will run this shape with in cluster mode (0: global-memory fix-up) -- callers that
+// want the fused RoPE epilogue ask first.
+int gemm_cluster_split(int T, int N, int K, int num_sms) {
+  switch (gemm_pick_bt(T)) {
+    case 16: return cluster_split_bt<16>(T, N, K, num_sms);
+    case 32: return cluster_split_bt<32>(T, N, K, num_sms);
+    case 64: return cluster_split_bt<64>(T, N, K, num_sms);
+    case 128: return cluster_split_bt<128>(T, N, K, num_sms);
+    default: return cluster_split_bt<256>(T, N, K, num_sms);
+  }
+}
+
+template <int BT>
+static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
+                             float* ws, int* counters, int num_sms, int out_f32, cudaStream_t stream,
+                             const CUtensorMap& next_wmap, const GemmNext& nxt, const GemmRope& rope) {
+  using Cfg = GemmCfg<BT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int t_tiles = (T + BT - 1) / BT;
+  const int grid = gemm_grid_size(T, N, K, num_sms);
+  const int stream_weights = (t_tiles == 1) ? 1 : 0;
+  const int split = cluster_split_bt<BT>(T, N, K, num_sms);
+  if (rope.positions != nullptr && (split == 0 || out_f32 != 0 || N != (rope.n_q + 2 * rope.n_kv) * HEAD_DIM))
+    return cudaErrorInvalidValue;  // the fused RoPE epilogue lives in the cluster reduction only
+  if (split > 0)
     return launch_k_cluster(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, split,
-                            wmap, xmap, Y, ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, split);
+                            wmap, xmap, Y, ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, split, rope);
   return launch_k(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
-                  ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, 0);
+                  ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, 0, rope);
 }
 
 // xmap must have been built with box_rows == gemm_pick_bt(T)
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32,
-                             const CUtensorMap* next_wmap, const GemmNext* next) {
+                             const CUtensorMap* next_wmap, const GemmNext* next, const GemmRope* rope) {
+  GemmRope rp{};
+  if (rope) rp = *rope;
   GemmNext nx{};
   if (next && next_wmap) nx = *next;
   const CUtensorMap& nm = (next && next_wmap) ? *next_wmap : wmap;
-#define TGIS_GEMM_CASE(B) return launch_bt<B>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx)
+#define TGIS_GEMM_CASE(B) return launch_bt<B>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp)
   switch (gemm_pick_bt(T)) {
     case 16: TGIS_GEMM_CASE(16);
     case 32: TGIS_GEMM_CASE(32);

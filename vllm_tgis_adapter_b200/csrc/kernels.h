@@ -22,12 +22,25 @@ struct GemmNext {
   int n_tiles, KB, grid, kb_prefetch;
 };
 int gemm_grid_size(int T, int N, int K, int num_sms);
+int gemm_even_split(int T, int N, int K, int num_sms);  // every tile cut over this many consecutive CTAs, or 0
 GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_prefetch);
 // Y: bf16 [T, ldy] (out_f32 = 0), fp32 [T, ldy] (out_f32 = 1, lm_head logits), or out_f32 = 2: fused SwiGLU — W rows are
 // interleaved (gate_j, up_j) pairs and Y is bf16 [T, ldy >= N/2] = bf16(bf16(silu(gate)) * up)
+// Optional fused epilogue of the qkv projection (cluster mode only, gemm_cluster_split() > 0): RoPE on the q / k heads
+// and scatter of k / v into the paged cache, replacing rope_kvwrite_kernel.  N must be (n_q + 2 n_kv) * 128.
+struct GemmRope {
+  const int32_t* positions;     // [T]; nullptr = no fusion
+  const int32_t* slot_mapping;  // [T], < 0: do not cache
+  const __nv_bfloat16* cos_sin; // [max_pos][128]: cos (64) | sin (64)
+  __nv_bfloat16* k_cache;       // this layer's caches
+  __nv_bfloat16* v_cache;
+  int32_t n_q, n_kv;
+};
+int gemm_cluster_split(int T, int N, int K, int num_sms);
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32 = 0,
-                             const CUtensorMap* next_wmap = nullptr, const GemmNext* next = nullptr);
+                             const CUtensorMap* next_wmap = nullptr, const GemmNext* next = nullptr,
+                             const GemmRope* rope = nullptr);
 
 // Chain kernel: one persistent launch = a dependent sequence of decode-shaped GEMMs and residual-add + RMSNorm row
 // steps (see gemm_tcgen05.cu).  sync: CHAIN_MAX_STEPS + 1 ints, zero before the first launch (re-armed by the kernel).

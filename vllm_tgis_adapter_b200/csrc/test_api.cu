@@ -228,6 +228,17 @@ int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const v
   return 0;
 }
 
+// Host-only: the launch plan of the GEMM for a shape (pure functions of the shape; no GPU needed): token-tile size,
+// grid, and the even-split factor (0 = stream-K ranges may straddle tiles, reduced through global memory).
+int tgis_k_gemm_plan(int32_t T, int32_t N, int32_t K, int32_t num_sms, int32_t* bt_out, int32_t* grid_out,
+                     int32_t* even_split_out) {
+  if (T <= 0 || N <= 0 || K <= 0 || num_sms <= 0) return kfail("bad shape");
+  *bt_out = gemm_pick_bt(T);
+  *grid_out = gemm_grid_size(T, N, K, num_sms);
+  *even_split_out = gemm_even_split(T, N, K, num_sms);
+  return 0;
+}
+
 // Host-only: the decode work-item list the scheduler builds for a step (no GPU needed).  seqs_host as in
 // tgis_k_attention (all decode sequences); items_out: (1 + capacity) x 8 int32 records; returns the entry count or -1.
 int tgis_k_decode_items(const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_stride,
