@@ -49,18 +49,63 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Prefill-shaped launches (more than one token tile): "data-parallel waves + stream-K tail".  Linear tile index i
+// (see tile_decode) -> the first dp_waves * ncta tiles are whole tiles dealt round-robin, wave w = tiles
+// [w * ncta, (w+1) * ncta): at any moment the 148 CTAs work on ONE compact 8 x ~18 rectangle of (weight tile, token
+// tile) pairs, so both operands of a wave stay in L2 (with contiguous per-CTA ranges the CTAs drift apart, the working
+// set is every weight tile + every activation tile, and ncu showed 11 GB of DRAM reads for 0.3 GB of operands).  The
+// remaining < ncta tiles are cut stream-K style as before.  Decode-shaped launches have dp_waves = 0: unchanged.
+struct GemmSched {
+  int n_tiles, t_tiles, KB, ncta;
+  int dp_waves;        // whole-tile waves
+  int sk_tile0;        // first tile of the stream-K region
+  long long sk_total;  // (tile, k-block) units in the stream-K region
+  __device__ GemmSched(int n_tiles_, int t_tiles_, int KB_, int ncta_)
+      : n_tiles(n_tiles_), t_tiles(t_tiles_), KB(KB_), ncta(ncta_) {
+    const int tiles = n_tiles * t_tiles;
+    dp_waves = t_tiles > 1 ? tiles / ncta : 0;
+    sk_tile0 = dp_waves * ncta;
+    sk_total = (long long)(tiles - sk_tile0) * KB;
+  }
+};
+// linear tile index -> (weight tile, token tile).  One token tile: identity.  Otherwise blocks of 8 weight tiles, token
+// tile next, weight tile fastest: 148 consecutive indices = 8 weight tiles x ~18 token tiles.
+__device__ __forceinline__ void tile_decode(const GemmSched& sc, int tile, int& n_tile, int& t_tile) {
+  if (sc.t_tiles == 1) {
+    n_tile = tile;
+    t_tile = 0;
+    return;
+  }
+  constexpr int NB = 8;
+  const int full = NB * sc.t_tiles;
+  const int nb = tile / full, rem = tile - nb * full;
+  const int nb_n = min(NB, sc.n_tiles - nb * NB);
+  t_tile = rem / nb_n;
+  n_tile = nb * NB + rem - t_tile * nb_n;
+}
+
 struct UnitIter {
-  // contiguous range [pos, end) of the global (tile, kblock) space owned by this CTA
+  // whole tiles wave * ncta + cta for wave < dp_waves, then the contiguous range [pos, end) of the stream-K region's
+  // (tile, kblock) space owned by this CTA
   long long pos, end;
-  int kb_per_tile;
+  int kb_per_tile, wave, dp_waves, cta, ncta, sk_tile0;
   bool first;
-  __device__ UnitIter(long long total, int kb, int cta, int ncta) : kb_per_tile(kb), first(true) {
-    pos = (total * cta) / ncta;
-    end = (total * (cta + 1)) / ncta;
+  __device__ UnitIter(const GemmSched& sc, int cta_)
+      : kb_per_tile(sc.KB), wave(0), dp_waves(sc.dp_waves), cta(cta_), ncta(sc.ncta), sk_tile0(sc.sk_tile0), first(true) {
+    pos = (sc.sk_total * cta_) / sc.ncta;
+    end = (sc.sk_total * (cta_ + 1)) / sc.ncta;
   }
   __device__ bool next(int& tile, int& kb0, int& kb1, int& slot) {
+    if (wave < dp_waves) {
+      tile = wave * ncta + cta;
+      kb0 = 0;
+      kb1 = kb_per_tile;
+      slot = 0;
+      ++wave;
+      return true;
+    }
     if (pos >= end) return false;
-    tile = (int)(pos / kb_per_tile);
+    tile = sk_tile0 + (int)(pos / kb_per_tile);
     kb0 = (int)(pos % kb_per_tile);
     long long rem = end - pos;
     int room = kb_per_tile - kb0;
@@ -137,8 +182,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   const int t_tiles = (T + BT - 1) / BT;
   const int KB = (K + GEMM_BK - 1) / GEMM_BK;
-  const long long total = (long long)n_tiles * t_tiles * KB;
   const int ncta = gridDim.x, cta = blockIdx.x;
+  const GemmSched sched(n_tiles, t_tiles, KB, ncta);
+  const long long total = sched.sk_total;  // stream-K region (== everything for decode-shaped launches)
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&wmap);
@@ -176,38 +222,71 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       const uint64_t pol_w = policy_evict_first();
       const uint64_t pol_x = policy_evict_last();
       const long long begin = (total * cta) / ncta, end = (total * (cta + 1)) / ncta;
-      const int n_kb = (int)(end - begin);
-      // (tile, kb) cursors advanced incrementally: no 64-bit divisions on the issue path
-      const int tile0 = (int)(begin / KB), kb0 = (int)(begin % KB);
-      auto issue_w = [&](int tile, int kb, int stage) {
+      const int n_kb = sched.dp_waves * KB + (int)(end - begin);
+      // (tile, kb) cursors advanced incrementally: no divisions on the per-k-block issue path.  A cursor walks the
+      // CTA's whole tiles (wave order) and then its stream-K range; rows are re-derived only when the tile changes.
+      struct Cur {
+        int wave, tile, kb, w_row, x_row;
+      };
+      auto cur_set_tile = [&](Cur& c, int tile) {
+        c.tile = tile;
+        int n_tile, t_tile;
+        tile_decode(sched, tile, n_tile, t_tile);
+        c.w_row = n_tile * GEMM_BN;
+        c.x_row = t_tile * BT;
+      };
+      auto cur_init = [&](Cur& c) {
+        c.wave = 0;
+        if (sched.dp_waves > 0) {
+          c.kb = 0;
+          cur_set_tile(c, cta);
+        } else {
+          c.kb = (int)(begin % KB);
+          cur_set_tile(c, sched.sk_tile0 + (int)(begin / KB));
+        }
+      };
+      auto cur_next = [&](Cur& c) {
+        if (++c.kb < KB) return;
+        c.kb = 0;
+        if (c.wave < sched.dp_waves) {
+          if (++c.wave < sched.dp_waves) {
+            cur_set_tile(c, c.wave * ncta + cta);
+          } else {  // into the stream-K tail
+            c.kb = (int)(begin % KB);
+            cur_set_tile(c, sched.sk_tile0 + (int)(begin / KB));
+          }
+        } else {
+          cur_set_tile(c, c.tile + 1);
+        }
+      };
+      auto issue_w = [&](const Cur& c, int stage) {
         void* dst = smem_w + stage * Cfg::W_BYTES;
-        const int row = (t_tiles == 1 ? tile : tile / t_tiles) * GEMM_BN;
-        if (stream_weights) tma_load_2d_hint(&wmap, &full_bar[stage], dst, kb * GEMM_BK, row, pol_w);
-        else tma_load_2d(&wmap, &full_bar[stage], dst, kb * GEMM_BK, row);
+        if (stream_weights) tma_load_2d_hint(&wmap, &full_bar[stage], dst, c.kb * GEMM_BK, c.w_row, pol_w);
+        else tma_load_2d(&wmap, &full_bar[stage], dst, c.kb * GEMM_BK, c.w_row);
       };
       const int n_pre = n_kb < STAGES ? n_kb : STAGES;
-      int w_tile = tile0, w_kb = kb0;
+      Cur wc, xc;
+      cur_init(wc);
+      xc = wc;
       for (int i = 0; i < n_pre; ++i) {
         mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
-        issue_w(w_tile, w_kb, i);
-        if (++w_kb == KB) { w_kb = 0; ++w_tile; }
+        issue_w(wc, i);
+        cur_next(wc);
       }
       TL(2);           // weight prefetch issued
       griddep_wait();  // activations (and everything the epilogue will touch) are now final
       TL(3);           // dependency wait returned
       int stage = 0;
       uint32_t phase = 0;
-      int x_tile = tile0, x_kb = kb0;
       for (int i = 0; i < n_kb; ++i) {
         if (i >= n_pre) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          issue_w(w_tile, w_kb, stage);
-          if (++w_kb == KB) { w_kb = 0; ++w_tile; }
+          issue_w(wc, stage);
+          cur_next(wc);
         }
-        tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, x_kb * GEMM_BK,
-                         (t_tiles == 1 ? 0 : x_tile % t_tiles) * BT, pol_x);
-        if (++x_kb == KB) { x_kb = 0; ++x_tile; }
+        tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, xc.kb * GEMM_BK, xc.x_row, pol_x);
+        cur_next(xc);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -234,7 +313,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_bf16(GEMM_BN, BT);
-    UnitIter it(total, KB, cta, ncta);
+    UnitIter it(sched, cta);
     int tile, kb0, kb1, slot;
     int stage = 0;
     uint32_t phase = 0;
@@ -273,12 +352,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
     const int sub = warp & 3;          // TMEM sub-partition this warp may read
     const int row = sub * 32 + lane_id();  // weight row within the tile
     const int ep_tid = (warp - 2) * 32 + lane_id();
-    UnitIter it(total, KB, cta, ncta);
+    UnitIter it(sched, cta);
     int tile, kb0, kb1, slot;
     int acc = 0;
     uint32_t acc_bits = 0;  // per-buffer phase parity
     while (it.next(tile, kb0, kb1, slot)) {
-      const int n_tile = tile / t_tiles, t_tile = tile % t_tiles;
+      int n_tile, t_tile;
+      tile_decode(sched, tile, n_tile, t_tile);
       const int n = n_tile * GEMM_BN + row;
       const int t_base = t_tile * BT;
       const int t_valid = min(BT, T - t_base);
@@ -337,7 +417,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         // stream-K fix-up: last arriver reduces all partials of this tile in CTA order (deterministic)
         // publish: CTA-wide barrier, then ONE acq_rel atomic (cumulative over the barrier) instead of membar.gl
         asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        const long long p0 = (long long)tile * KB;
+        const long long p0 = (long long)(tile - sched.sk_tile0) * KB;  // position inside the stream-K region
         const int c_first = unit_owner(p0, total, ncta);
         const int c_last = unit_owner(p0 + KB - 1, total, ncta);
         if (ep_tid == 0) {
@@ -367,7 +447,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
                 const int c = c0g + ci;
                 const bool cv = c <= c_last;
                 const long long cb = cv ? (total * c) / ncta : 0;
-                const int cslot = ((int)(cb / KB) == tile) ? 0 : 1;
+                const int cslot = ((int)(cb / KB) == tile - sched.sk_tile0) ? 0 : 1;
                 const float* p = ws + ((size_t)((cv ? c : c_first) * 2 + cslot) * BT) * GEMM_BN + r4;
 #pragma unroll
                 for (int j = 0; j < FIX_T; ++j) {
@@ -730,7 +810,8 @@ chain_tcgen05_kernel(const __grid_constant__ ChainParams P) {
       if (st.kind != 0 || cta >= st.ncta) continue;
       const int KB = (st.K + GEMM_BK - 1) / GEMM_BK;
       const long long total = (long long)((st.N + GEMM_BN - 1) / GEMM_BN) * KB;
-      UnitIter it(total, KB, cta, st.ncta);
+      const GemmSched csched((st.N + GEMM_BN - 1) / GEMM_BN, 1, KB, st.ncta);
+      UnitIter it(csched, cta);
       int tile, kb0, kb1, slot;
       while (it.next(tile, kb0, kb1, slot)) {
         mbar_wait(&tmem_empty[acc], ((acc_bits >> acc) & 1) ^ 1);
@@ -856,7 +937,8 @@ chain_tcgen05_kernel(const __grid_constant__ ChainParams P) {
       __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(st.y);
       const int KB = (st.K + GEMM_BK - 1) / GEMM_BK;
       const long long total = (long long)((N + GEMM_BN - 1) / GEMM_BN) * KB;
-      UnitIter it(total, KB, cta, ncta);
+      const GemmSched csched((N + GEMM_BN - 1) / GEMM_BN, 1, KB, ncta);
+      UnitIter it(csched, cta);
       int tile, kb0, kb1, slot;
       while (it.next(tile, kb0, kb1, slot)) {
         const int n = tile * GEMM_BN + row;
