@@ -72,8 +72,10 @@ def launch_list(src: Path, out_agg: Path, out_raw: Path) -> None:
 launch_list(SRC / "launches.csv", DST / f"{tag}_launches_decode_step_summary.csv", DST / f"{tag}_launches_decode_step.csv")
 ncu_raw(SRC / "prof_gemm.ncu-rep", DST / f"{tag}_ncu_full_gemm_tcgen05.csv")
 ncu_raw(SRC / "prof_attn.ncu-rep", DST / f"{tag}_ncu_full_attn_decode.csv")
+ncu_raw(SRC / "prof_gemm_prefill.ncu-rep", DST / f"{tag}_ncu_full_gemm_prefill.csv")
 for name in ("bench.log", "bench_ref.log", "parity_stats.json", "gemm_bench.json", "gemm_cta_sweep.json", "gemm_timeline.log",
-             "gpu_info.txt", "tp2.log", "bench_tp2.log", "bench_tp4.log", "bench_dp2.log"):
+             "gpu_info.txt", "tp2.log", "bench_tp2.log", "bench_tp4.log", "bench_dp2.log", "attn_bench.json", "grpc_bench.log",
+             "bench_b64.log", "bench_b128.log", "bench_b256.log", "bench_b64_cfg3.log"):
     p = SRC / name
     if p.exists() and p.stat().st_size:
         shutil.copy(p, DST / f"{tag}_{name}")
