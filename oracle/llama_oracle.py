@@ -64,6 +64,8 @@ CONFIGS = {
     "small": LlamaConfig(n_layers=4, hidden=512, n_q_heads=4, n_kv_heads=1, ffn=1536, vocab=4096, max_model_len=1024),
     # "opt-125m-size" Llama-class stand-in for BASELINE.json configs[0] (12 layers, hidden 768)
     "125m": LlamaConfig(n_layers=12, hidden=768, n_q_heads=6, n_kv_heads=2, ffn=3072, vocab=50272, max_model_len=2048),
+    # small stack whose 8 kv heads / ffn / vocab split evenly over 2, 4 and 8 tensor-parallel ranks (scripts/tp_check.py)
+    "tp8": LlamaConfig(n_layers=2, hidden=1024, n_q_heads=8, n_kv_heads=8, ffn=2048, vocab=8192, max_model_len=512),
     "llama3-8b": LlamaConfig(n_layers=32, hidden=4096, n_q_heads=32, n_kv_heads=8, ffn=14336, vocab=128256,
                              max_model_len=8192),
     "llama3-70b": LlamaConfig(n_layers=80, hidden=8192, n_q_heads=64, n_kv_heads=8, ffn=28672, vocab=128256,

@@ -125,6 +125,100 @@ cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, 
   return launch_k(rmsnorm_kernel<true>, dim3(T), dim3(NORM_THREADS), 0, stream, x, residual, w, out, hidden, eps);
 }
 
+// ------------------------------------------------------------------------------------------------ TP: fused exchange
+// One-shot all-reduce + residual add + RMSNorm over NVLink peer memory (tensor parallelism, decode-shaped steps).
+// Replaces ncclAllReduce + rmsnorm_kernel<true> after the row-parallel GEMMs (o-proj, down-proj): every rank's GEMM
+// leaves its bf16 partial [T, hidden] in an IPC-shared buffer; this kernel (same launch on every rank)
+//   1. announces "my partial #epoch is complete" by storing `epoch` into every peer's flag word for this rank,
+//   2. waits until all ranks have announced the same epoch (bounded spin),
+//   3. row per CTA: loads the row from every rank's buffer (peer loads over NVSwitch), sums in RANK ORDER in fp32 -- every
+//      rank computes the same bits, so the replicas stay in lockstep --, rounds once to bf16 (the all-reduced GEMM output
+//      in model dtype), adds the residual, normalises: the arithmetic of rmsnorm_kernel<true> from there on.
+// Two buffers / flag sets alternate (o-proj, down-proj): a rank can only overwrite a buffer after every rank has
+// announced the NEXT exchange, i.e. finished reading this one -- no trailing barrier needed.
+__global__ void __launch_bounds__(NORM_THREADS)
+ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, uint32_t epoch, __nv_bfloat16* __restrict__ residual,
+                      const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int hidden, float eps) {
+  __shared__ float red[NORM_THREADS / 32];
+  griddep_launch();
+  griddep_wait();  // this rank's partial (previous kernel) is complete
+  if (blockIdx.x == 0 && threadIdx.x < tp) {
+    __threadfence_system();
+    volatile uint32_t* f = P.flags[threadIdx.x] + rank;  // rank `threadIdx.x`'s flag word for us
+    *f = epoch;
+  }
+  if (threadIdx.x < tp) {
+    const volatile uint32_t* f = P.flags[rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(*f - epoch) < 0) {
+      if (clock64() - t0 > 4000000000ll) {
+        printf("ar_add_rmsnorm: rank %d waiting for rank %d epoch %u (has %u)\n", rank, (int)threadIdx.x, epoch, *f);
+        __trap();
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * hidden;
+  const int nvec = hidden / 8;
+  BF8 z[NORM_MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      for (int q = 0; q < tp; ++q) {  // rank order on every rank
+        const uint4 raw = __ldcv(reinterpret_cast<const uint4*>(P.buf[q] + base) + i);
+        const uint32_t* rw = &raw.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += __uint_as_float(rw[e] << 16);
+          acc[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+        }
+      }
+      const BF8 r = reinterpret_cast<const BF8*>(residual + base)[i];
+      BF8 a;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = __float2bfloat16_rn(bf16_round(acc[e]) + __bfloat162float(r.v[e]));
+      reinterpret_cast<BF8*>(residual + base)[i] = a;
+      z[j] = a;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float f = __bfloat162float(a.v[e]);
+        ss += f * f;
+      }
+    }
+  }
+  const float tot = block_sum<NORM_THREADS>(ss, red);
+  const float rs = rsqrtf(tot / (float)hidden + eps);
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) {
+      BF8 wv = reinterpret_cast<const BF8*>(w)[i];
+      BF8 o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float nrm = bf16_round(__bfloat162float(z[j].v[e]) * rs);
+        o.v[e] = __float2bfloat16_rn(nrm * __bfloat162float(wv.v[e]));
+      }
+      reinterpret_cast<BF8*>(out + base)[i] = o;
+    }
+  }
+}
+
+cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, uint32_t epoch, __nv_bfloat16* residual,
+                                  const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden, float eps,
+                                  cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (tp < 2 || tp > 8 || hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
+  return launch_k(ar_add_rmsnorm_kernel, dim3(T), dim3(NORM_THREADS), 0, stream, peers, tp, rank, epoch, residual, w, out,
+                  hidden, eps);
+}
+
 // ------------------------------------------------------------------------------------------------ SiLU * mul
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gate_up, __nv_bfloat16* __restrict__ act, int T,
                                 int ffn) {

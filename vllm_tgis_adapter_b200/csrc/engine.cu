@@ -256,6 +256,13 @@ struct tgis_engine {
   bool use_chain = false;
   DevBuf<int> chain_sync;
   bool fuse_rope = true;
+  // tensor parallelism, decode-shaped steps: one-shot all-reduce + residual + RMSNorm over NVLink peer memory
+  // (ar_add_rmsnorm_kernel) instead of ncclAllReduce + rmsnorm kernel.  TGIS_TP_FUSED_AR=0: NCCL baseline.
+  bool tp_fused_ar = true;
+  static constexpr int AR_MAX_T = 256;
+  uint8_t* ar_mem = nullptr;        // [2 parities][AR_MAX_T][hidden] bf16 partial buffers, then 2 x 8 flag words
+  uint8_t* ar_peer[8] = {};         // the same allocation of every rank, mapped here (cudaIpc)
+  uint32_t ar_epoch[2] = {0, 0};
   int chain_pf_depth = 16;  // TGIS_CHAIN_PF
   int l2_prefetch_kb = 0;   // (off: measured no gain, costs DRAM traffic in the issuing kernel) k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
   std::vector<cudaEvent_t> prof_events;
@@ -277,6 +284,9 @@ struct tgis_engine {
       munmap(shm, shm_bytes);
       if (shm_owner) shm_unlink(shm_name.c_str());
     }
+    for (int r = 0; r < 8; ++r)
+      if (ar_peer[r] && ar_peer[r] != ar_mem) cudaIpcCloseMemHandle(ar_peer[r]);
+    if (ar_mem) cudaFree(ar_mem);
     if (comm) nccl().CommDestroy(comm);
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (cudaEvent_t ev : prof_events) cudaEventDestroy(ev);
@@ -318,6 +328,7 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_CHAIN")) use_chain = atoi(e) != 0;
     if (const char* e = getenv("TGIS_CHAIN_PF")) chain_pf_depth = atoi(e);
     if (const char* e = getenv("TGIS_FUSE_ROPE")) fuse_rope = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_TP_FUSED_AR")) tp_fused_ar = atoi(e) != 0;
     chain_sync.alloc(CHAIN_MAX_STEPS + 1);
     chain_sync.zero();
 
@@ -493,6 +504,63 @@ struct tgis_engine {
     // first collective doubles as a start-up barrier (and creates NCCL's channels outside the timed path)
     NK(nccl().AllReduce(tmp.p, tmp.p, 1024, ncclBfloat16, ncclSum, comm, stream));
     CK(cudaStreamSynchronize(stream));
+    if (tp_fused_ar && tp <= 8) init_fused_ar();
+    else tp_fused_ar = false;
+  }
+
+  size_t ar_buf_bytes() const { return (size_t)AR_MAX_T * cfg.hidden * sizeof(bf16); }
+  bf16* ar_buf(int parity) { return reinterpret_cast<bf16*>(ar_mem + parity * ar_buf_bytes()); }
+
+  // Every rank allocates its exchange buffer, the cudaIpc handles travel by ncclAllGather, every rank maps the others.
+  // All ranks must take the same decision: the per-rank success bits are summed with an all-reduce.
+  void init_fused_ar() {
+    const size_t bytes = 2 * ar_buf_bytes() + 4096;
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    if (cudaMalloc(&ar_mem, bytes) != cudaSuccess || cudaMemset(ar_mem, 0, bytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, ar_mem) != cudaSuccess) {
+      ok = 0;
+      memset(&mine, 0, sizeof(mine));
+      cudaGetLastError();
+    }
+    DevBuf<uint8_t> hbuf;
+    hbuf.alloc(sizeof(cudaIpcMemHandle_t) * 8);
+    CK(cudaMemcpy(hbuf.p + rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NK(nccl().AllGather(hbuf.p + rank * sizeof(mine), hbuf.p, sizeof(mine), ncclInt8, comm, stream));
+    CK(cudaStreamSynchronize(stream));
+    cudaIpcMemHandle_t all[8];
+    CK(cudaMemcpy(all, hbuf.p, sizeof(mine) * tp, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < tp && ok; ++r) {
+      if (r == rank) {
+        ar_peer[r] = ar_mem;
+      } else if (cudaIpcOpenMemHandle(reinterpret_cast<void**>(&ar_peer[r]), all[r], cudaIpcMemLazyEnablePeerAccess) !=
+                 cudaSuccess) {
+        ar_peer[r] = nullptr;
+        ok = 0;
+        cudaGetLastError();
+      }
+    }
+    DevBuf<float> vote;
+    vote.alloc(1);
+    const float mine_ok = (float)ok;
+    CK(cudaMemcpy(vote.p, &mine_ok, sizeof(float), cudaMemcpyHostToDevice));
+    NK(nccl().AllReduce(vote.p, vote.p, 1, ncclFloat, ncclSum, comm, stream));
+    CK(cudaStreamSynchronize(stream));
+    float total = 0.f;
+    CK(cudaMemcpy(&total, vote.p, sizeof(float), cudaMemcpyDeviceToHost));
+    tp_fused_ar = ((int)(total + 0.5f) == tp);
+  }
+
+  // exchange #parity of a layer (0: after o-proj, 1: after down-proj) + residual add + RMSNorm with weight w
+  void fused_ar_norm(int parity, const bf16* w, int T) {
+    ArPeers P;
+    memset(&P, 0, sizeof(P));
+    for (int r = 0; r < tp; ++r) {
+      P.buf[r] = reinterpret_cast<const bf16*>(ar_peer[r] + parity * ar_buf_bytes());
+      P.flags[r] = reinterpret_cast<uint32_t*>(ar_peer[r] + 2 * ar_buf_bytes()) + parity * 8;
+    }
+    CK(ar_add_rmsnorm_launch(P, tp, rank, ++ar_epoch[parity], resid.p, w, xn.p, T, cfg.hidden, cfg.rms_eps, stream));
+    ++n_launches;
   }
 
   void publish_plan(const StepHeader& h) {  // rank 0
@@ -708,6 +776,7 @@ struct tgis_engine {
     CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
     ++n_launches;
     const bool chained = use_chain && tp == 1 && T <= 256 && !cfg.debug_gemm_ref;
+    const bool ar_fused = tp > 1 && tp_fused_ar && T <= AR_MAX_T;
     // RoPE + KV-cache scatter fused into the qkv GEMM's cluster epilogue (decode-shaped steps; TGIS_FUSE_ROPE=0: off)
     const bool rope_fused = fuse_rope && !chained && !cfg.debug_gemm_ref && gemm_cluster_split(T, qkv_dim, H, num_sms) > 0;
     const int bi = bt_index(T);
@@ -721,9 +790,15 @@ struct tgis_engine {
           chain_run(P);
         }
       } else {
-        if (li == 0) CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
-        else CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
-        ++n_launches;
+        if (li == 0) {
+          CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+          ++n_launches;
+        } else if (ar_fused) {
+          fused_ar_norm(1, l.ln1, T);  // previous layer's down-proj partials
+        } else {
+          CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
+          ++n_launches;
+        }
         const GemmRope rp{ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin,
                           k_cache.p + (size_t)li * kv_layer_elems, v_cache.p + (size_t)li * kv_layer_elems, nq, nkv};
         gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim, 0, rope_fused ? &rp : nullptr);
@@ -760,20 +835,32 @@ struct tgis_engine {
         chain_run(P);
         continue;
       }
-      gemm(xm_attn, l.m_o, attn_out.p, l.wo, tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H);
-      all_reduce_tmp(T);  // row-parallel partial sums (tp > 1)
-      CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
-      ++n_launches;
+      gemm(xm_attn, l.m_o, attn_out.p, l.wo, ar_fused ? ar_buf(0) : tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H);
+      if (ar_fused) {
+        fused_ar_norm(0, l.ln2, T);
+      } else {
+        all_reduce_tmp(T);  // row-parallel partial sums (tp > 1)
+        CK(add_rmsnorm_launch(tmp.p, resid.p, l.ln2, xn.p, T, H, c.rms_eps, stream));
+        ++n_launches;
+      }
       // gate_up GEMM with SwiGLU fused into its epilogue: writes act[T, F] directly (no gate_up round trip)
       gemm(xm_xn, l.m_gu, xn.p, l.wgu, act.p, T, 2 * F, H, /*out_mode=*/2, &l.m_d, T, H, F, /*ldy=*/F);
-      if (li + 1 < c.n_layers) gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F, 0, &layers[li + 1].m_qkv, T, qkv_dim, H);
-      else gemm(xm_act, l.m_d, act.p, l.wd, tmp.p, T, H, F, 0, R > 0 ? &m_lm : nullptr, R, Vl, H);
-      all_reduce_tmp(T);
+      bf16* down_out = ar_fused ? ar_buf(1) : tmp.p;
+      if (li + 1 < c.n_layers) gemm(xm_act, l.m_d, act.p, l.wd, down_out, T, H, F, 0, &layers[li + 1].m_qkv, T, qkv_dim, H);
+      else gemm(xm_act, l.m_d, act.p, l.wd, down_out, T, H, F, 0, R > 0 ? &m_lm : nullptr, R, Vl, H);
+      if (!ar_fused) all_reduce_tmp(T);
     }
+    // The last down-proj exchange is run even when no row is sampled this step (R == 0): it is what guarantees that
+    // every rank has finished READING this step's buffers before a faster rank overwrites them in the next step.
+    if (ar_fused) fused_ar_norm(1, final_norm, T);
     if (R > 0) {
-      CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
+      if (ar_fused) {
+      } else {
+        CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
+        ++n_launches;
+      }
       CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
-      n_launches += 2;
+      ++n_launches;
       if (tp == 1) {
         gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, /*out_f32=*/1);
       } else {

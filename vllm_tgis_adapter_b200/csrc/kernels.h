@@ -85,6 +85,16 @@ cudaError_t rmsnorm_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
 // residual = bf16(x + residual); out = rmsnorm(residual) * w     (vllm: layernorm.py fused_add_rms_norm)
 cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, const __nv_bfloat16* w,
                                __nv_bfloat16* out, int T, int hidden, float eps, cudaStream_t stream);
+// Tensor parallelism, decode-shaped steps: one-shot all-reduce of the row-parallel GEMM partials over NVLink peer memory
+// fused with the residual add + RMSNorm (elementwise.cu).  buf[q] / flags[q]: rank q's partial buffer [T, hidden] and its
+// 8 flag words (one per source rank) for this exchange parity, mapped into this process (own entries = local pointers).
+struct ArPeers {
+  const __nv_bfloat16* buf[8];
+  uint32_t* flags[8];
+};
+cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, uint32_t epoch, __nv_bfloat16* residual,
+                                  const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden, float eps,
+                                  cudaStream_t stream);
 // act[t, i] = bf16(silu(gate_up[t, i])) * gate_up[t, F + i]
 cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn, cudaStream_t stream);
 // gather rows: out[r, :] = x[rows[r], :]
