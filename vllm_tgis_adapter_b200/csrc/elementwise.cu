@@ -127,40 +127,54 @@ cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, 
 
 // ------------------------------------------------------------------------------------------------ TP: fused exchange
 // One-shot all-reduce + residual add + RMSNorm over NVLink peer memory (tensor parallelism, decode-shaped steps).
-// Replaces ncclAllReduce + rmsnorm_kernel<true> after the row-parallel GEMMs (o-proj, down-proj): every rank's GEMM
-// leaves its bf16 partial [T, hidden] in an IPC-shared buffer; this kernel (same launch on every rank)
-//   1. announces "my partial #epoch is complete" by storing `epoch` into every peer's flag word for this rank,
-//   2. waits until all ranks have announced the same epoch (bounded spin),
-//   3. row per CTA: loads the row from every rank's buffer (peer loads over NVSwitch), sums in RANK ORDER in fp32 -- every
-//      rank computes the same bits, so the replicas stay in lockstep --, rounds once to bf16 (the all-reduced GEMM output
-//      in model dtype), adds the residual, normalises: the arithmetic of rmsnorm_kernel<true> from there on.
-// Two buffers / flag sets alternate (o-proj, down-proj): a rank can only overwrite a buffer after every rank has
-// announced the NEXT exchange, i.e. finished reading this one -- no trailing barrier needed.
+// Replaces ncclAllReduce + rmsnorm_kernel<true> after the row-parallel GEMMs (o-proj, down-proj).  Every rank's GEMM
+// leaves its bf16 partial [T, hidden] in local memory; this kernel (same launch on every rank, row per CTA)
+//   1. PUSHES its row to every peer's receive area with 16-byte remote stores that carry their own arrival flags
+//      ({data, epoch, data, epoch}: the "LL" line format -- a line is valid when both flag words equal this
+//      exchange's epoch, so there is no separate flag write, no fence and no round trip: one NVLink traversal),
+//   2. polls its OWN receive area until the peers' lines of this epoch have landed (bounded spin),
+//   3. sums the partials in RANK ORDER in fp32 -- every rank computes the same bits, so the replicas stay in lockstep --,
+//      rounds once to bf16 (the all-reduced GEMM output in model dtype), adds the residual and normalises: the
+//      arithmetic of rmsnorm_kernel<true> from there on.
+// Two receive areas alternate (o-proj, down-proj exchange): a rank can only push exchange k+2 of an area after it
+// has completed exchange k+1 of the other one, i.e. after every peer has pushed k+1, which a peer does only after its
+// kernel of exchange k (the reader of this area) has finished -- no trailing barrier needed.
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)
+               : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(NORM_THREADS)
 ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, uint32_t epoch, __nv_bfloat16* __restrict__ residual,
                       const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int hidden, float eps) {
   __shared__ float red[NORM_THREADS / 32];
   griddep_launch();
   griddep_wait();  // this rank's partial (previous kernel) is complete
-  if (blockIdx.x == 0 && threadIdx.x < tp) {
-    __threadfence_system();
-    volatile uint32_t* f = P.flags[threadIdx.x] + rank;  // rank `threadIdx.x`'s flag word for us
-    *f = epoch;
-  }
-  if (threadIdx.x < tp) {
-    const volatile uint32_t* f = P.flags[rank] + threadIdx.x;
-    const long long t0 = clock64();
-    while ((int32_t)(*f - epoch) < 0) {
-      if (clock64() - t0 > 4000000000ll) {
-        printf("ar_add_rmsnorm: rank %d waiting for rank %d epoch %u (has %u)\n", rank, (int)threadIdx.x, epoch, *f);
-        __trap();
+  const int row = blockIdx.x;
+  const size_t base = (size_t)row * hidden;
+  const int nvec = hidden / 8;
+  // receive-area line index of (source rank, row, vector i): ((src * AR_MAX_ROWS + row) * nvec + i) * 2
+  uint4 own[NORM_MAX_VEC];
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) {
+      own[j] = reinterpret_cast<const uint4*>(P.own + base)[i];
+      const uint4 l0 = make_uint4(own[j].x, epoch, own[j].y, epoch), l1 = make_uint4(own[j].z, epoch, own[j].w, epoch);
+      const size_t line = (((size_t)rank * AR_MAX_ROWS + row) * nvec + i) * 2;
+      for (int q = 0; q < tp; ++q) {
+        if (q == rank) continue;
+        st_volatile_v4(P.recv[q] + line, l0);
+        st_volatile_v4(P.recv[q] + line + 1, l1);
       }
     }
-    __threadfence_system();
   }
-  __syncthreads();
-  const size_t base = (size_t)blockIdx.x * hidden;
-  const int nvec = hidden / 8;
   BF8 z[NORM_MAX_VEC];
   float ss = 0.f;
 #pragma unroll
@@ -171,7 +185,24 @@ ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, uint32_t epoch, __nv_bfloat16
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
       for (int q = 0; q < tp; ++q) {  // rank order on every rank
-        const uint4 raw = __ldcv(reinterpret_cast<const uint4*>(P.buf[q] + base) + i);
+        uint4 raw;
+        if (q == rank) {
+          raw = own[j];
+        } else {
+          const uint4* src = P.recv[rank] + (((size_t)q * AR_MAX_ROWS + row) * nvec + i) * 2;
+          uint4 l0, l1;
+          const long long t0 = clock64();
+          for (;;) {
+            l0 = ld_volatile_v4(src);
+            l1 = ld_volatile_v4(src + 1);
+            if (l0.y == epoch && l0.w == epoch && l1.y == epoch && l1.w == epoch) break;
+            if (clock64() - t0 > 4000000000ll) {
+              printf("ar_add_rmsnorm: rank %d row %d waiting for rank %d epoch %u (has %u)\n", rank, row, q, epoch, l0.y);
+              __trap();
+            }
+          }
+          raw = make_uint4(l0.x, l0.z, l1.x, l1.z);
+        }
         const uint32_t* rw = &raw.x;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -214,7 +245,8 @@ cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, uint32
                                   const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden, float eps,
                                   cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
-  if (tp < 2 || tp > 8 || hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
+  if (tp < 2 || tp > 8 || T > AR_MAX_ROWS || hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC)
+    return cudaErrorInvalidValue;
   return launch_k(ar_add_rmsnorm_kernel, dim3(T), dim3(NORM_THREADS), 0, stream, peers, tp, rank, epoch, residual, w, out,
                   hidden, eps);
 }

@@ -259,8 +259,8 @@ struct tgis_engine {
   // tensor parallelism, decode-shaped steps: one-shot all-reduce + residual + RMSNorm over NVLink peer memory
   // (ar_add_rmsnorm_kernel) instead of ncclAllReduce + rmsnorm kernel.  TGIS_TP_FUSED_AR=0: NCCL baseline.
   bool tp_fused_ar = true;
-  static constexpr int AR_MAX_T = 256;
-  uint8_t* ar_mem = nullptr;        // [2 parities][AR_MAX_T][hidden] bf16 partial buffers, then 2 x 8 flag words
+  static constexpr int AR_MAX_T = AR_MAX_ROWS;
+  uint8_t* ar_mem = nullptr;        // [2 parities] receive areas (ar_recv_bytes each), then the two local partial buffers
   uint8_t* ar_peer[8] = {};         // the same allocation of every rank, mapped here (cudaIpc)
   uint32_t ar_epoch[2] = {0, 0};
   int chain_pf_depth = 16;  // TGIS_CHAIN_PF
@@ -509,12 +509,12 @@ struct tgis_engine {
   }
 
   size_t ar_buf_bytes() const { return (size_t)AR_MAX_T * cfg.hidden * sizeof(bf16); }
-  bf16* ar_buf(int parity) { return reinterpret_cast<bf16*>(ar_mem + parity * ar_buf_bytes()); }
+  bf16* ar_buf(int parity) { return reinterpret_cast<bf16*>(ar_mem + 2 * ar_recv_bytes(cfg.hidden) + parity * ar_buf_bytes()); }
 
   // Every rank allocates its exchange buffer, the cudaIpc handles travel by ncclAllGather, every rank maps the others.
   // All ranks must take the same decision: the per-rank success bits are summed with an all-reduce.
   void init_fused_ar() {
-    const size_t bytes = 2 * ar_buf_bytes() + 4096;
+    const size_t bytes = 2 * ar_recv_bytes(cfg.hidden) + 2 * ar_buf_bytes();
     int ok = 1;
     cudaIpcMemHandle_t mine;
     if (cudaMalloc(&ar_mem, bytes) != cudaSuccess || cudaMemset(ar_mem, 0, bytes) != cudaSuccess ||
@@ -555,10 +555,8 @@ struct tgis_engine {
   void fused_ar_norm(int parity, const bf16* w, int T) {
     ArPeers P;
     memset(&P, 0, sizeof(P));
-    for (int r = 0; r < tp; ++r) {
-      P.buf[r] = reinterpret_cast<const bf16*>(ar_peer[r] + parity * ar_buf_bytes());
-      P.flags[r] = reinterpret_cast<uint32_t*>(ar_peer[r] + 2 * ar_buf_bytes()) + parity * 8;
-    }
+    P.own = ar_buf(parity);
+    for (int r = 0; r < tp; ++r) P.recv[r] = reinterpret_cast<uint4*>(ar_peer[r] + parity * ar_recv_bytes(cfg.hidden));
     CK(ar_add_rmsnorm_launch(P, tp, rank, ++ar_epoch[parity], resid.p, w, xn.p, T, cfg.hidden, cfg.rms_eps, stream));
     ++n_launches;
   }

@@ -86,11 +86,14 @@ cudaError_t rmsnorm_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
 cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, const __nv_bfloat16* w,
                                __nv_bfloat16* out, int T, int hidden, float eps, cudaStream_t stream);
 // Tensor parallelism, decode-shaped steps: one-shot all-reduce of the row-parallel GEMM partials over NVLink peer memory
-// fused with the residual add + RMSNorm (elementwise.cu).  buf[q] / flags[q]: rank q's partial buffer [T, hidden] and its
-// 8 flag words (one per source rank) for this exchange parity, mapped into this process (own entries = local pointers).
+// fused with the residual add + RMSNorm (elementwise.cu).  own: this rank's partial [T, hidden]; recv[q]: rank q's receive
+// area for this exchange parity, mapped into this process (recv[own rank] = local): [8 source ranks][AR_MAX_ROWS rows]
+// [hidden / 8 vectors][2 lines of 16 bytes = {data, epoch, data, epoch}].
+constexpr int AR_MAX_ROWS = 256;
+inline size_t ar_recv_bytes(int hidden) { return (size_t)8 * AR_MAX_ROWS * (hidden / 8) * 2 * 16; }
 struct ArPeers {
-  const __nv_bfloat16* buf[8];
-  uint32_t* flags[8];
+  const __nv_bfloat16* own;
+  uint4* recv[8];
 };
 cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, uint32_t epoch, __nv_bfloat16* residual,
                                   const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden, float eps,
