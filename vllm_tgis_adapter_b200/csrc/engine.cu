@@ -218,7 +218,7 @@ struct tgis_engine {
   DevBuf<float> logits;  // fp32 straight from the lm_head accumulator
   CUtensorMap xm_xn[N_BT], xm_attn[N_BT], xm_act[N_BT], xm_last[N_BT];
   DevBuf<float> gemm_ws, part_o, part_ml, samp_scratch;
-  DevBuf<int> gemm_counters, dec_counters;
+  DevBuf<int> gemm_counters;
   DevBuf<uint32_t> seen_bitmap;
   DevBuf<SampleOut> d_samp_out;
   SampleOut* h_samp_out = nullptr;
@@ -380,8 +380,6 @@ struct tgis_engine {
     const int G = c.n_q_heads / c.n_kv_heads;
     part_o.alloc((size_t)S_max * nkv * max_splits_cap * G * HEAD_DIM);
     part_ml.alloc((size_t)S_max * nkv * max_splits_cap * G * 2);
-    dec_counters.alloc((size_t)S_max * nkv);
-    dec_counters.zero();
     samp_scratch.alloc((size_t)S_max * V);
     seen_bitmap.alloc((size_t)S_max * bitmap_words);
     seen_bitmap.zero();
@@ -883,7 +881,7 @@ struct tgis_engine {
   // returns number of sampled rows
   int run_batch(std::vector<Sched>& batch) {
     const tgis_config& c = cfg;
-    const int H = c.hidden, F = c.ffn, V = c.vocab;
+    const int H = c.hidden, V = c.vocab;
     int T = 0, n_dec = 0, n_tiles = 0, R = 0, max_dec_kv = 0;
     struct PromptRow {
       int row, target, pos;

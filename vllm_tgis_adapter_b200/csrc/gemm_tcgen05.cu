@@ -809,7 +809,6 @@ chain_tcgen05_kernel(const __grid_constant__ ChainParams P) {
       const ChainStep& st = P.step[s];
       if (st.kind != 0 || cta >= st.ncta) continue;
       const int KB = (st.K + GEMM_BK - 1) / GEMM_BK;
-      const long long total = (long long)((st.N + GEMM_BN - 1) / GEMM_BN) * KB;
       const GemmSched csched((st.N + GEMM_BN - 1) / GEMM_BN, 1, KB, st.ncta);
       UnitIter it(csched, cta);
       int tile, kb0, kb1, slot;

@@ -148,7 +148,6 @@ int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v
   Tmp<AttnSeq> d_seqs;
   Tmp<int32_t> d_dec, d_tseq, d_tq0, d_bt;
   Tmp<float> po, pml;
-  Tmp<int> ctr;
   KCK(d_seqs.upload(seqs.data(), n_seqs));
   KCK(d_dec.upload(dec.data(), dec.size()));
   KCK(d_tseq.upload(tseq.data(), tseq.size()));
@@ -158,8 +157,6 @@ int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v
   const size_t nd = dec.size() ? dec.size() : 1;
   KCK(po.alloc(nd * n_kv * max_splits * G * HEAD_DIM));
   KCK(pml.alloc(nd * n_kv * max_splits * G * 2));
-  KCK(ctr.alloc(nd * n_kv));
-  KCK(cudaMemset(ctr.p, 0, sizeof(int) * nd * n_kv));
   std::vector<DecItem> items(1 + nd * max_splits);
   decode_items_build(items.data(), seqs.data(), dec.data(), (int)dec.size(), block_table_host, bt_stride);
   Tmp<DecItem> d_items;
@@ -193,14 +190,11 @@ int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const v
   Tmp<AttnSeq> d_seqs;
   Tmp<int32_t> d_bt;
   Tmp<float> po, pml;
-  Tmp<int> ctr;
   KCK(d_seqs.upload(seqs.data(), n_seqs));
   KCK(d_bt.upload(block_table_host, (size_t)bt_rows * bt_stride));
   const int max_splits = (max_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
   KCK(po.alloc((size_t)n_seqs * n_kv * max_splits * G * HEAD_DIM));
   KCK(pml.alloc((size_t)n_seqs * n_kv * max_splits * G * 2));
-  KCK(ctr.alloc((size_t)n_seqs * n_kv));
-  KCK(cudaMemset(ctr.p, 0, sizeof(int) * n_seqs * n_kv));
   std::vector<DecItem> items(1 + (size_t)n_seqs * max_splits);
   decode_items_build(items.data(), seqs.data(), nullptr, n_seqs, block_table_host, bt_stride);
   Tmp<DecItem> d_items;
