@@ -27,6 +27,7 @@ for st in $STAGES; do
     decode_quick) for pdl in 0 1; do for gr in 0 1; do TGIS_PDL=$pdl timeout 300 python scripts/profile_decode.py 8 32 512 24 $gr > gpurun_out/decode_pdl${pdl}_graph${gr}.log 2>&1; done; done; echo "decode_quick rc=$?" ;;
     tp2) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29511 scripts/tp_check.py tiny > gpurun_out/tp2.log 2>&1; echo "tp2 rc=$?"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29512 scripts/tp_check.py tiny > gpurun_out/tp2_b.log 2>&1; echo "tp2 small rc=$?" ;;
     tpn) timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 127.0.0.1 --master-port 29513 scripts/tp_check.py tp8 > gpurun_out/tp${NGPU}_check.log 2>&1; echo "tpn rc=$?"; tail -2 gpurun_out/tp${NGPU}_check.log ;;
+    tpserver) timeout 600 python scripts/tp_server_smoke.py $NGPU tiny > gpurun_out/tp_server_smoke.log 2>&1; echo "tpserver rc=$?"; tail -3 gpurun_out/tp_server_smoke.log ;;
     grpc_bench) timeout 600 python scripts/grpc_bench.py > gpurun_out/grpc_bench.log 2>&1; echo "grpc_bench rc=$?" ;;
     bench_tp) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $NGPU --parallel tp --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/bench_tp$NGPU.log 2> gpurun_out/bench_tp$NGPU.err; echo "bench_tp rc=$?" ;;
     bench_dp) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $NGPU --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/bench_dp$NGPU.log 2> gpurun_out/bench_dp$NGPU.err; echo "bench_dp rc=$?" ;;

@@ -89,30 +89,71 @@ def load_safetensors_dir(eng: NativeEngine, path: Path) -> None:
                 eng.load_weight(name, sf.get_tensor(name))
 
 
-def build_engine(args) -> AsyncTGISEngine:
-    if args.tensor_parallel_size not in (None, 1):
-        raise ValueError("the server entrypoint runs single-GPU engines; tensor-parallel engines are started one process "
-                         "per GPU (scripts/tp_check.py shows the launch pattern)")
+def _resolve_model(args):
+    """(ModelConfig, checkpoint dir or None) from --model: a HF-format directory or a preset name + --synthetic-weights."""
     if not args.model:
         raise ValueError("--model / --model-name is required")
     path = Path(args.model)
     if path.is_dir():
-        mc = model_config_from_hf(path, args.max_model_len)
-    elif args.model in PRESETS:
+        return model_config_from_hf(path, args.max_model_len), path
+    if args.model in PRESETS:
         if not args.synthetic_weights:
             raise ValueError(f"--model {args.model} is a preset name: pass --synthetic-weights or a model directory")
         mc = dataclasses.replace(PRESETS[args.model])
         if args.max_model_len:
             mc.max_model_len = args.max_model_len
-    else:
-        raise ValueError(f"model path {args.model} does not exist (no network access: hub ids cannot be resolved)")
+        return mc, None
+    raise ValueError(f"model path {args.model} does not exist (no network access: hub ids cannot be resolved)")
+
+
+def _make_native_engine(args, mc: ModelConfig, path, device: int, **tp_kw) -> NativeEngine:
     eng = NativeEngine(mc, max_num_seqs=args.max_num_seqs, max_batched_tokens=args.max_num_batched_tokens,
-                       gpu_mem_fraction=args.gpu_memory_utilization, device=args.device, seed=args.seed)
-    if path.is_dir():
-        load_safetensors_dir(eng, path)
+                       gpu_mem_fraction=args.gpu_memory_utilization, device=device, seed=args.seed, **tp_kw)
+    if path is not None:
+        load_safetensors_dir(eng, path)      # full tensors: a tensor-parallel engine keeps its rank's shard
     else:
-        load_synthetic_weights(eng, mc, args.seed, args.device)
+        load_synthetic_weights(eng, mc, args.seed, device)
     eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
-    tokenizer = load_tokenizer(args.tokenizer or (str(path) if path.is_dir() else None), mc.vocab)
-    logger.info("engine ready: %s", mc)
+    return eng
+
+
+def _tp_worker_main(args, rank: int, tp: int, nccl_id: bytes, shm_name: str) -> None:
+    """Ranks 1..tp-1 of a tensor-parallel server (one spawned process per GPU): build the rank's shard of the same
+    model and follow rank 0's step plans (shared-memory control block, csrc/engine.cu worker_loop) until it shuts down."""
+    import torch  # noqa: F401  (first: resolves libnccl for the engine library)
+
+    mc, path = _resolve_model(args)
+    eng = _make_native_engine(args, mc, path, args.device + rank, tp_size=tp, tp_rank=rank, nccl_id=nccl_id,
+                              shm_name=shm_name)
+    try:
+        eng.worker_run()
+    finally:
+        eng.close()
+
+
+def build_engine(args) -> AsyncTGISEngine:
+    """`--tensor-parallel-size N` (reference: tgis_utils/args.py:139-148 maps --num-gpus / --num-shard onto it): this
+    process is rank 0 (scheduler, sampler, gRPC); ranks 1..N-1 are spawned here, one process per GPU."""
+    tp = args.tensor_parallel_size or 1
+    mc, path = _resolve_model(args)
+    tp_kw = {}
+    if tp > 1:
+        import multiprocessing as mp
+        import os
+
+        import torch  # noqa: F401
+
+        if mc.n_kv_heads % tp or mc.ffn % tp or mc.vocab % tp:
+            raise ValueError(f"tensor_parallel_size {tp} does not divide kv heads / ffn / vocab of {mc}")
+        nccl_id = NativeEngine.nccl_unique_id()
+        shm_name = f"/tgis_tp_{os.getpid()}"
+        ctx = mp.get_context("spawn")
+        workers = [ctx.Process(target=_tp_worker_main, args=(args, r, tp, nccl_id, shm_name), daemon=True,
+                               name=f"tgis-tp-rank{r}") for r in range(1, tp)]
+        for w in workers:
+            w.start()
+        tp_kw = dict(tp_size=tp, tp_rank=0, nccl_id=nccl_id, shm_name=shm_name)
+    eng = _make_native_engine(args, mc, path, args.device, **tp_kw)
+    tokenizer = load_tokenizer(args.tokenizer or (str(path) if path is not None else None), mc.vocab)
+    logger.info("engine ready: %s (tensor_parallel_size=%d)", mc, tp)
     return AsyncTGISEngine(eng, tokenizer, mc)
