@@ -178,6 +178,46 @@ def test_rope_and_kv_scatter_bit_exact(g):
     assert torch.equal(v_dense[slots], qkv[:, cfg.n_q_heads + cfg.n_kv_heads:])
 
 
+@pytest.mark.parametrize("T", [32, 200])
+def test_qkv_gemm_with_fused_rope_epilogue_is_bit_identical(g, T):
+    """The qkv projection's cluster epilogue (gemm_tcgen05.cu: split-K partials reduced through distributed shared memory,
+    then RoPE + scatter into the paged K / V layouts) against the unfused pair (GEMM -> bf16 qkv, then
+    rope_kvwrite_kernel): qkv rows and both caches must be bit-identical.  32 heads = 32 weight tiles, which the launcher
+    splits 4 ways = clusters of 4 on a 148-SM part."""
+    import ctypes as C
+
+    n_q, n_kv, K = 24, 4, 1024
+    n_heads = n_q + 2 * n_kv
+    N = n_heads * 128
+    torch.manual_seed(21)
+    rows = 256
+    x = torch.zeros(rows, K, dtype=torch.bfloat16, device="cuda")
+    x[:T] = (torch.randn(T, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    table = (torch.rand(512, 128, device="cuda") * 2 - 1).bfloat16()       # any cos | sin table: same one for both paths
+    positions = np.random.RandomState(1).randint(0, 512, size=T).astype(np.int32)
+    n_blocks = 16
+    slots = np.random.RandomState(2).permutation(n_blocks * 32)[:T].astype(np.int32)
+    slots[3] = -1                                                            # "do not cache" row
+    kc1 = torch.zeros(n_blocks, n_kv, 16, 32, 8, dtype=torch.bfloat16, device="cuda")
+    vc1 = torch.zeros_like(kc1)
+    kc2, vc2 = torch.zeros_like(kc1), torch.zeros_like(kc1)
+    y1 = torch.zeros(T, N, dtype=torch.bfloat16, device="cuda")
+    rc = g.lib().tgis_k_gemm_rope(g.ptr(x), g.ptr(w), g.ptr(y1), T, n_q, n_kv, K, rows, g.i32p(positions), g.i32p(slots),
+                                  g.ptr(table), g.ptr(kc1), g.ptr(vc1))
+    assert rc in (0, 1), g.kerr()
+    if rc == 1:
+        pytest.skip("this shape does not run in cluster mode on this device")
+    y2 = torch.zeros(T, N, dtype=torch.bfloat16, device="cuda")
+    ms = C.c_float(0)
+    assert g.lib().tgis_k_gemm(g.ptr(x), g.ptr(w), g.ptr(y2), T, N, K, rows, 0, 1, C.byref(ms), 0) == 0, g.kerr()
+    assert g.lib().tgis_k_rope_kv(g.ptr(y2), g.i32p(positions), g.i32p(slots), g.ptr(table), g.ptr(kc2), g.ptr(vc2), T,
+                                  n_q, n_kv) == 0, g.kerr()
+    assert torch.equal(y1, y2)
+    assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+    assert float(kc1.float().abs().sum()) > 0 and float(vc1.float().abs().sum()) > 0
+
+
 def _attention_case(g, n_q, n_kv, seq_specs, seed):
     """seq_specs: list of (context_len_before, q_len).  Returns (out_gpu, out_oracle)."""
     from oracle.llama_oracle import LlamaConfig, LlamaOracle

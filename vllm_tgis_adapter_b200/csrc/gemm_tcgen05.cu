@@ -1186,7 +1186,7 @@ GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_
 }
 
 // cluster mode: on-chip split-K reduction when every tile is split evenly over <= 8 consecutive CTAs, the fp32 partial
-// fits the drained ring, and the device can schedule such a cluster (checked once per (BT, split)).  Returns the split or 0.
+// fits the drained ring, and all clusters can be co-resident (checked once per (BT, split)).  Returns the split or 0.
 template <int BT>
 static int cluster_split_bt(int T, int N, int K, int num_sms) {
   using Cfg = GemmCfg<BT>;
@@ -1212,8 +1212,12 @@ static int cluster_split_bt(int T, int N, int K, int num_sms) {
     qc.numAttrs = 1;
     int n_clusters = 0;
     const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, gemm_bf16_tcgen05_kernel<BT>, &qc);
-    // clusters only depend on their own CTAs, so partial residency (profilers reserve SMs) is slower, not wrong
-    cluster_ok[split] = (qe == cudaSuccess && n_clusters >= 1) ? 1 : -1;
+    // All clusters of the launch must be co-resident: a GPC only hosts floor(SMs / split) of them, and one cluster left
+    // over for a second wave doubles the launch time (measured: qkv with 48 clusters of 3 when 47 fit).
+    cluster_ok[split] = (qe == cudaSuccess && n_clusters * split >= gemm_grid_size(T, N, K, num_sms)) ? 1 : -1;
+    if (getenv("TGIS_GEMM_DEBUG"))
+      fprintf(stderr, "[gemm] BT=%d split=%d: %d clusters fit, grid %d -> cluster mode %s\n", BT, split, n_clusters,
+              gemm_grid_size(T, N, K, num_sms), cluster_ok[split] == 1 ? "on" : "off");
     if (qe != cudaSuccess) cudaGetLastError();
   }
   return (split > 0 && cluster_ok[split] == 1) ? split : 0;

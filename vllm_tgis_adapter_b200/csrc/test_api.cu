@@ -124,6 +124,33 @@ int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* 
   return 0;
 }
 
+// qkv projection with the fused RoPE + KV-scatter epilogue (cluster mode).  Returns 1 when the shape does not run in
+// cluster mode on this device (nothing computed), 0 on success.
+int tgis_k_gemm_rope(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t n_q, int32_t n_kv, int32_t K,
+                     int32_t x_rows_alloc, const int32_t* positions_host, const int32_t* slot_mapping_host,
+                     const void* cos_sin_dev, void* k_cache_dev, void* v_cache_dev) {
+  const int N = (n_q + 2 * n_kv) * HEAD_DIM;
+  const int sms = test_num_sms();
+  if (gemm_cluster_split(T, N, K, sms) <= 0) return 1;
+  CUtensorMap wm, xm;
+  const int bt = gemm_pick_bt(T);
+  if (x_rows_alloc < bt) return kfail("x must have at least one TMA box of rows allocated");
+  if (make_tmap_bf16_2d(&wm, w_dev, N, K, K, 128, 64) != 0) return kfail("weight tensor map failed");
+  if (make_tmap_bf16_2d(&xm, x_dev, x_rows_alloc, K, K, bt, 64) != 0) return kfail("activation tensor map failed");
+  Tmp<float> ws;
+  Tmp<int> ctr;
+  Tmp<int32_t> pos, sm;
+  KCK(ws.alloc(gemm_workspace_bytes(sms) / sizeof(float)));
+  KCK(ctr.alloc(1 << 16));
+  KCK(cudaMemset(ctr.p, 0, sizeof(int) << 16));
+  KCK(pos.upload(positions_host, T));
+  KCK(sm.upload(slot_mapping_host, T));
+  const GemmRope rp{pos.p, sm.p, (const bf16*)cos_sin_dev, (bf16*)k_cache_dev, (bf16*)v_cache_dev, n_q, n_kv};
+  KCK(gemm_bf16_launch(wm, xm, y_dev, N, T, N, K, ws.p, ctr.p, sms, 0, 0, nullptr, nullptr, &rp));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
 int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev, const int32_t* seqs_host,
                      int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows, int32_t bt_stride, void* out_dev,
                      int32_t n_q, int32_t n_kv, float scale) {
