@@ -31,8 +31,9 @@ int tgis_k_rmsnorm(const void* x_dev, void* residual_dev, const void* w_dev, voi
 int tgis_k_silu_mul(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn);
 int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* slot_mapping_host,
                    const void* cos_sin_dev, void* k_cache_dev, void* v_cache_dev, int32_t T, int32_t n_q, int32_t n_kv);
-/* qkv projection y[T, (n_q + 2 n_kv) * 128] = x . w^T with RoPE and the KV-cache scatter fused into the GEMM's cluster
- * epilogue; returns 1 (and computes nothing) when this shape does not run in cluster mode on the device */
+/* qkv projection y[T, (n_q + 2 n_kv) * 128] = x . w^T with RoPE and the KV-cache scatter fused into the GEMM's
+ * split-tile reduction (cluster / DSMEM or global fix-up); returns 1 (and computes nothing) when the launch plan does not
+ * split every weight tile */
 int tgis_k_gemm_rope(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t n_q, int32_t n_kv, int32_t K,
                      int32_t x_rows_alloc, const int32_t* positions_host, const int32_t* slot_mapping_host,
                      const void* cos_sin_dev, void* k_cache_dev, void* v_cache_dev);

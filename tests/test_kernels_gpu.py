@@ -178,15 +178,17 @@ def test_rope_and_kv_scatter_bit_exact(g):
     assert torch.equal(v_dense[slots], qkv[:, cfg.n_q_heads + cfg.n_kv_heads:])
 
 
+@pytest.mark.parametrize("heads", [(24, 4), (32, 8)])
 @pytest.mark.parametrize("T", [32, 200])
-def test_qkv_gemm_with_fused_rope_epilogue_is_bit_identical(g, T):
-    """The qkv projection's cluster epilogue (gemm_tcgen05.cu: split-K partials reduced through distributed shared memory,
-    then RoPE + scatter into the paged K / V layouts) against the unfused pair (GEMM -> bf16 qkv, then
-    rope_kvwrite_kernel): qkv rows and both caches must be bit-identical.  32 heads = 32 weight tiles, which the launcher
-    splits 4 ways = clusters of 4 on a 148-SM part."""
+def test_qkv_gemm_with_fused_rope_epilogue_is_bit_identical(g, T, heads):
+    """The qkv projection's split-tile reduction (gemm_tcgen05.cu) followed in the same kernel by RoPE + scatter into the
+    paged K / V layouts, against the unfused pair (GEMM -> bf16 qkv, then rope_kvwrite_kernel): qkv rows and both caches
+    must be bit-identical.  32 heads = 32 weight tiles split 4 ways = clusters of 4 (reduction through distributed
+    shared memory); 48 heads (the Llama-3-8B shape) = 48 tiles split 3 ways, whose 48 clusters do not fit a 148-SM part
+    at once, so that shape takes the global-memory fix-up path."""
     import ctypes as C
 
-    n_q, n_kv, K = 24, 4, 1024
+    (n_q, n_kv), K = heads, 1024
     n_heads = n_q + 2 * n_kv
     N = n_heads * 128
     torch.manual_seed(21)
@@ -207,7 +209,7 @@ def test_qkv_gemm_with_fused_rope_epilogue_is_bit_identical(g, T):
                                   g.ptr(table), g.ptr(kc1), g.ptr(vc1))
     assert rc in (0, 1), g.kerr()
     if rc == 1:
-        pytest.skip("this shape does not run in cluster mode on this device")
+        pytest.skip("the launch plan does not split every tile on this device")
     y2 = torch.zeros(T, N, dtype=torch.bfloat16, device="cuda")
     ms = C.c_float(0)
     assert g.lib().tgis_k_gemm(g.ptr(x), g.ptr(w), g.ptr(y2), T, N, K, rows, 0, 1, C.byref(ms), 0) == 0, g.kerr()

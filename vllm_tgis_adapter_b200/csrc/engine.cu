@@ -773,8 +773,9 @@ struct tgis_engine {
     ++n_launches;
     const bool chained = use_chain && tp == 1 && T <= 256 && !cfg.debug_gemm_ref;
     const bool ar_fused = tp > 1 && tp_fused_ar && T <= AR_MAX_T;
-    // RoPE + KV-cache scatter fused into the qkv GEMM's cluster epilogue (decode-shaped steps; TGIS_FUSE_ROPE=0: off)
-    const bool rope_fused = fuse_rope && !chained && !cfg.debug_gemm_ref && gemm_cluster_split(T, qkv_dim, H, num_sms) > 0;
+    // RoPE + KV-cache scatter fused into the qkv GEMM's split-tile reduction (decode-shaped steps where every weight
+    // tile is split over several CTAs; TGIS_FUSE_ROPE=0: off)
+    const bool rope_fused = fuse_rope && !chained && !cfg.debug_gemm_ref && gemm_even_split(T, qkv_dim, H, num_sms) >= 2;
     const int bi = bt_index(T);
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];

@@ -153,6 +153,54 @@ __device__ __forceinline__ __nv_bfloat16 swiglu_bf16(float gate_acc, float up_ac
   return __float2bfloat16_rn(sl * u);
 }
 
+// Fused RoPE + KV-cache scatter of the qkv projection's final epilogue (tile = one 128-dim head; arithmetic and rounding
+// points of rope_kvwrite_kernel).  Called by a full warp with a warp-uniform (head, t): this thread holds the fp32 sums of
+// dims r4..r4+3 of token t; the rotary partner dims (+-64) live in lane ^ 16.
+__device__ __forceinline__ void qkv_rope_store(const GemmRope& rope, int head, int t, int r4, const float (&av)[4],
+                                               __nv_bfloat16* y_dst) {
+  const int lane = lane_id();
+  float x[4], pr[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) x[e] = bf16_round(av[e]);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) pr[e] = __shfl_xor_sync(0xffffffffu, x[e], 16);
+  const int d = r4 & 63;
+  if (head < rope.n_q + rope.n_kv) {
+    const int pos = __ldg(rope.positions + t);
+    const uint2 cs = __ldg(reinterpret_cast<const uint2*>(rope.cos_sin + (size_t)pos * HEAD_DIM + d));
+    const uint2 sn = __ldg(reinterpret_cast<const uint2*>(rope.cos_sin + (size_t)pos * HEAD_DIM + 64 + d));
+    const float cc[4] = {__uint_as_float(cs.x << 16), __uint_as_float(cs.x & 0xffff0000u), __uint_as_float(cs.y << 16),
+                         __uint_as_float(cs.y & 0xffff0000u)};
+    const float ss[4] = {__uint_as_float(sn.x << 16), __uint_as_float(sn.x & 0xffff0000u), __uint_as_float(sn.y << 16),
+                         __uint_as_float(sn.y & 0xffff0000u)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = bf16_round(x[e] * cc[e]), b = bf16_round(pr[e] * ss[e]);
+      x[e] = lane < 16 ? a - b : a + b;  // lo' = x1 c - x2 s ; hi' = x2 c + x1 s
+    }
+  }
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&p0);
+  pk.y = *reinterpret_cast<uint32_t*>(&p1);
+  *reinterpret_cast<uint2*>(y_dst) = pk;
+  if (head >= rope.n_q) {
+    const int slot = __ldg(rope.slot_mapping + t);
+    if (slot >= 0) {
+      const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
+      const int chunk = r4 >> 3, sub = r4 & 7;  // 16-byte chunk of the head, 0 or 4 inside it
+      if (head < rope.n_q + rope.n_kv) {  // K tile [chunk][token][8]
+        __nv_bfloat16* kb = rope.k_cache + ((size_t)blk * rope.n_kv + (head - rope.n_q)) * (KV_BLOCK * HEAD_DIM);
+        *reinterpret_cast<uint2*>(kb + (chunk * KV_BLOCK + off) * 8 + sub) = pk;
+      } else {  // V tile [token][chunk ^ (token & 7)][8]
+        __nv_bfloat16* vb =
+            rope.v_cache + ((size_t)blk * rope.n_kv + (head - rope.n_q - rope.n_kv)) * (KV_BLOCK * HEAD_DIM);
+        *reinterpret_cast<uint2*>(vb + off * HEAD_DIM + ((chunk ^ (off & 7)) * 8) + sub) = pk;
+      }
+    }
+  }
+}
+
 template <int BT>
 __global__ void __launch_bounds__(GEMM_THREADS, (BT <= 64 && TGIS_GEMM_DECODE_STAGES <= 5) ? 2 : 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
@@ -469,7 +517,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
               if (t < t_valid) {
                 const size_t o = (size_t)(t_base + t) * ldy + n4;
                 const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
-                if (out_f32 == 2) {  // fused SwiGLU: rows (n4, n4+1) and (n4+2, n4+3) are (gate, up) pairs
+                if (rope.positions != nullptr) {  // qkv projection: RoPE + KV scatter (warp-uniform t and tile)
+                  qkv_rope_store(rope, n_tile, t_base + t, r4, av, Y + o);
+                } else if (out_f32 == 2) {  // fused SwiGLU: rows (n4, n4+1) and (n4+2, n4+3) are (gate, up) pairs
                   __nv_bfloat16* yo = Y + (size_t)(t_base + t) * ldy + (n4 >> 1);
                   if (n4 + 1 < N) yo[0] = swiglu_bf16(av[0], av[1]);
                   if (n4 + 3 < N) yo[1] = swiglu_bf16(av[2], av[3]);
@@ -537,50 +587,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
             const size_t o = (size_t)t * ldy + n4;
             const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
             if (rope.positions != nullptr) {
-              // ---- fused RoPE + KV-cache scatter (qkv projection; tile = one 128-dim head; arithmetic and rounding
-              // points of rope_kvwrite_kernel).  This thread holds dims r4..r4+3 of token t; the rotary partner
-              // dims (+-64) live in lane ^ 16.  The branch is warp-uniform (t, tile), so the shuffles are safe.
-              const int head = cl_tile, lane = lane_id();
-              float x[4], pr[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = bf16_round(av[e]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) pr[e] = __shfl_xor_sync(0xffffffffu, x[e], 16);
-              const int d = r4 & 63;
-              if (head < rope.n_q + rope.n_kv) {
-                const int pos = __ldg(rope.positions + t);
-                const uint2 cs = __ldg(reinterpret_cast<const uint2*>(rope.cos_sin + (size_t)pos * HEAD_DIM + d));
-                const uint2 sn = __ldg(reinterpret_cast<const uint2*>(rope.cos_sin + (size_t)pos * HEAD_DIM + 64 + d));
-                const float cc[4] = {__uint_as_float(cs.x << 16), __uint_as_float(cs.x & 0xffff0000u),
-                                     __uint_as_float(cs.y << 16), __uint_as_float(cs.y & 0xffff0000u)};
-                const float ss[4] = {__uint_as_float(sn.x << 16), __uint_as_float(sn.x & 0xffff0000u),
-                                     __uint_as_float(sn.y << 16), __uint_as_float(sn.y & 0xffff0000u)};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float a = bf16_round(x[e] * cc[e]), b = bf16_round(pr[e] * ss[e]);
-                  x[e] = lane < 16 ? a - b : a + b;  // lo' = x1 c - x2 s ; hi' = x2 c + x1 s
-                }
-              }
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&p0);
-              pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              *reinterpret_cast<uint2*>(Y + o) = pk;
-              if (head >= rope.n_q) {
-                const int slot = __ldg(rope.slot_mapping + t);
-                if (slot >= 0) {
-                  const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
-                  const int chunk = r4 >> 3, sub = r4 & 7;  // 16-byte chunk of the head, 0 or 4 inside it
-                  if (head < rope.n_q + rope.n_kv) {  // K tile [chunk][token][8]
-                    __nv_bfloat16* kb = rope.k_cache + ((size_t)blk * rope.n_kv + (head - rope.n_q)) * (KV_BLOCK * HEAD_DIM);
-                    *reinterpret_cast<uint2*>(kb + (chunk * KV_BLOCK + off) * 8 + sub) = pk;
-                  } else {  // V tile [token][chunk ^ (token & 7)][8]
-                    __nv_bfloat16* vb = rope.v_cache +
-                                        ((size_t)blk * rope.n_kv + (head - rope.n_q - rope.n_kv)) * (KV_BLOCK * HEAD_DIM);
-                    *reinterpret_cast<uint2*>(vb + off * HEAD_DIM + ((chunk ^ (off & 7)) * 8) + sub) = pk;
-                  }
-                }
-              }
+              qkv_rope_store(rope, cl_tile, t, r4, av, Y + o);
             } else if (out_f32 == 2) {
               __nv_bfloat16* yo = Y + (size_t)t * ldy + (n4 >> 1);
               if (n4 + 1 < N) yo[0] = swiglu_bf16(av[0], av[1]);
@@ -1251,8 +1258,10 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, v
   const int grid = gemm_grid_size(T, N, K, num_sms);
   const int stream_weights = (t_tiles == 1) ? 1 : 0;
   const int split = cluster_split_bt<BT>(T, N, K, num_sms);
-  if (rope.positions != nullptr && (split == 0 || out_f32 != 0 || N != (rope.n_q + 2 * rope.n_kv) * HEAD_DIM))
-    return cudaErrorInvalidValue;  // the fused RoPE epilogue lives in the cluster reduction only
+  // the fused RoPE epilogue lives in the two split-tile reductions (cluster and global fix-up): every tile must be split
+  if (rope.positions != nullptr && (gemm_even_split(T, N, K, num_sms) < 2 || out_f32 != 0 ||
+                                    N != (rope.n_q + 2 * rope.n_kv) * HEAD_DIM))
+    return cudaErrorInvalidValue;
   if (split > 0)
     return launch_k_cluster(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, split,
                             wmap, xmap, Y, ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, split, rope);

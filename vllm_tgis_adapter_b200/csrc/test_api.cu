@@ -124,14 +124,14 @@ int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* 
   return 0;
 }
 
-// qkv projection with the fused RoPE + KV-scatter epilogue (cluster mode).  Returns 1 when the shape does not run in
-// cluster mode on this device (nothing computed), 0 on success.
+// qkv projection with the fused RoPE + KV-scatter epilogue (in the cluster or the global split-tile reduction).  Returns 1
+// when the launch plan does not split every tile (nothing computed), 0 on success.
 int tgis_k_gemm_rope(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t n_q, int32_t n_kv, int32_t K,
                      int32_t x_rows_alloc, const int32_t* positions_host, const int32_t* slot_mapping_host,
                      const void* cos_sin_dev, void* k_cache_dev, void* v_cache_dev) {
   const int N = (n_q + 2 * n_kv) * HEAD_DIM;
   const int sms = test_num_sms();
-  if (gemm_cluster_split(T, N, K, sms) <= 0) return 1;
+  if (gemm_even_split(T, N, K, sms) < 2) return 1;
   CUtensorMap wm, xm;
   const int bt = gemm_pick_bt(T);
   if (x_rows_alloc < bt) return kfail("x must have at least one TMA box of rows allocated");
