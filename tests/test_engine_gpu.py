@@ -235,6 +235,7 @@ def test_fused_rope_epilogue_is_bit_identical(model, monkeypatch):
     prompts = [rng.randint(3, 1024, size=n).tolist() for n in (70, 5, 130, 33, 64, 200)]
     sp = make_sampling_params(greedy=True, max_tokens=24, min_tokens=24, num_logprobs=2)
     runs = []
+    monkeypatch.setenv("TGIS_FUSE_ROPE_MAX_T", "256")    # default 32: cover the mixed prefill/decode steps too
     for flag in ("0", "1"):
         monkeypatch.setenv("TGIS_FUSE_ROPE", flag)
         _, _, outs, st = _run_engine(model, prompts, sp, max_num_seqs=8, max_batched_tokens=96, kv_cache_bytes=64 << 20)

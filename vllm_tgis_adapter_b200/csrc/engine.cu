@@ -256,6 +256,7 @@ struct tgis_engine {
   bool use_chain = false;
   DevBuf<int> chain_sync;
   bool fuse_rope = true;
+  int rope_fuse_max_t = 32;
   // tensor parallelism, decode-shaped steps: one-shot all-reduce + residual + RMSNorm over NVLink peer memory
   // (ar_add_rmsnorm_kernel) instead of ncclAllReduce + rmsnorm kernel.  TGIS_TP_FUSED_AR=0: NCCL baseline.
   bool tp_fused_ar = true;
@@ -328,6 +329,7 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_CHAIN")) use_chain = atoi(e) != 0;
     if (const char* e = getenv("TGIS_CHAIN_PF")) chain_pf_depth = atoi(e);
     if (const char* e = getenv("TGIS_FUSE_ROPE")) fuse_rope = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_FUSE_ROPE_MAX_T")) rope_fuse_max_t = atoi(e);
     if (const char* e = getenv("TGIS_TP_FUSED_AR")) tp_fused_ar = atoi(e) != 0;
     chain_sync.alloc(CHAIN_MAX_STEPS + 1);
     chain_sync.zero();
@@ -775,7 +777,10 @@ struct tgis_engine {
     const bool ar_fused = tp > 1 && tp_fused_ar && T <= AR_MAX_T;
     // RoPE + KV-cache scatter fused into the qkv GEMM's split-tile reduction (decode-shaped steps where every weight
     // tile is split over several CTAs; TGIS_FUSE_ROPE=0: off)
-    const bool rope_fused = fuse_rope && !chained && !cfg.debug_gemm_ref && gemm_even_split(T, qkv_dim, H, num_sms) >= 2;
+    // (measured: -2 % per step at 32 tokens, but +2...5 % at 64...256 -- the last-arriving CTA's serial tail grows with
+    // T while the stand-alone kernel spreads over all SMs -- hence the token limit)
+    const bool rope_fused = fuse_rope && !chained && !cfg.debug_gemm_ref && T <= rope_fuse_max_t &&
+                            gemm_even_split(T, qkv_dim, H, num_sms) >= 2;
     const int bi = bt_index(T);
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];
