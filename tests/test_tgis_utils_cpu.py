@@ -61,3 +61,21 @@ def test_inconsistent_legacy_flags_raise():
         parse_args(["--max-sequence-length", "512", "--max-model-len", "256"])
     with pytest.raises(ValueError, match="Inconsistent num_gpus"):
         parse_args(["--num-gpus", "2", "--num-shard", "4"])
+
+
+def test_tensor_parallel_flags_reach_the_engine_builder():
+    """--num-gpus / --num-shard are the TGIS spellings of --tensor-parallel-size (reference tgis_utils/args.py:139-148);
+    the engine builder spawns one worker per extra GPU and refuses, before touching a device, a size that does not
+    divide the model's kv heads / ffn / vocab."""
+    import pytest
+
+    from vllm_tgis_adapter_b200.engine.loader import build_engine
+    from vllm_tgis_adapter_b200.tgis_utils.args import parse_args
+
+    args = parse_args(["--model", "tiny", "--synthetic-weights", "--num-gpus", "4"])
+    assert args.tensor_parallel_size == 4
+    with pytest.raises(ValueError, match="does not divide"):      # tiny has 2 kv heads
+        build_engine(args)
+    args = parse_args(["--model", "no/such/dir", "--tensor-parallel-size", "2"])
+    with pytest.raises(ValueError, match="does not exist"):
+        build_engine(args)
