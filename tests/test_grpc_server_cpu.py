@@ -250,3 +250,38 @@ def test_correlation_id_is_request_id_and_logged(srv, caplog):
     msgs = [r.getMessage() for r in caplog.records]
     assert any("request_id=corr-42-0" in m and "correlation_id=corr-42" in m for m in msgs), msgs
     assert any(m.startswith("Finished processing request") and "Generated 2 tokens" in m for m in msgs)
+
+
+@pytest.mark.parametrize("version", ["v1alpha", "v1"])
+def test_server_reflection_lists_services_and_serves_descriptors(srv, version):
+    """Server reflection (reference grpc_server.py:919-926: health + fmaas.GenerationService + reflection): what
+    `grpcurl -plaintext host:port list / describe fmaas.GenerationService` does -- list_services, then
+    file_containing_symbol, and the returned FileDescriptorProto must describe the real wire surface."""
+    from google.protobuf import descriptor_pb2
+
+    from vllm_tgis_adapter_b200.grpc import reflection
+
+    pkg = reflection.V1ALPHA if version == "v1alpha" else reflection.V1
+    call = srv.channel.stream_stream(f"/{pkg.service_name}/ServerReflectionInfo",
+                                     request_serializer=pkg.Request.SerializeToString,
+                                     response_deserializer=pkg.Response.FromString)
+    reqs = [pkg.Request(list_services=""), pkg.Request(file_containing_symbol="fmaas.GenerationService"),
+            pkg.Request(file_containing_symbol="fmaas.GenerationService.GenerateStream"),
+            pkg.Request(file_containing_symbol="grpc.health.v1.Health"),
+            pkg.Request(file_by_filename="no/such.proto"),
+            pkg.Request(file_containing_symbol="fmaas.Parameters")]
+    resps = list(call(iter(reqs), timeout=10))
+    assert len(resps) == len(reqs)
+    names = {s.name for s in resps[0].list_services_response.service}
+    assert {"fmaas.GenerationService", "grpc.health.v1.Health", pkg.service_name} <= names
+    fd = descriptor_pb2.FileDescriptorProto.FromString(resps[1].file_descriptor_response.file_descriptor_proto[0])
+    assert fd.package == "fmaas"
+    methods = {m.name: (m.client_streaming, m.server_streaming) for m in fd.service[0].method}
+    assert methods == {"Generate": (False, False), "GenerateStream": (False, True), "Tokenize": (False, False),
+                       "ModelInfo": (False, False)}
+    assert resps[2].file_descriptor_response.file_descriptor_proto[0] == resps[1].file_descriptor_response.file_descriptor_proto[0]
+    hfd = descriptor_pb2.FileDescriptorProto.FromString(resps[3].file_descriptor_response.file_descriptor_proto[0])
+    assert hfd.package == "grpc.health.v1" and {m.name for m in hfd.service[0].method} == {"Check", "Watch"}
+    assert resps[4].WhichOneof("message_response") == "error_response" and resps[4].error_response.error_code == 5
+    assert resps[5].original_request.file_containing_symbol == "fmaas.Parameters"
+    assert resps[5].file_descriptor_response.file_descriptor_proto

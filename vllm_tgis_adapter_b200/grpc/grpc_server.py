@@ -26,6 +26,8 @@ from grpc import StatusCode, aio
 
 from ..engine.types import RequestOutput, RequestOutputKind, SamplingParams, TokensPrompt
 from ..tgis_utils import logs
+from . import health as _health
+from . import reflection
 from .health import HealthServicer, SERVING, add_health_servicer
 from .pb import generation_pb2 as pb2
 from .pb.generation_pb2 import (BatchedGenerationResponse, BatchedTokenizeResponse, DecodingMethod,
@@ -447,6 +449,9 @@ async def start_grpc_server(args, engine, stop_event: asyncio.Event) -> aio.Serv
     generation = TextGenerationService(engine, args, health_servicer, stop_event)
     await generation.post_init()
     add_generation_servicer(generation, server)
+    # server reflection for grpcurl & co (:919-926): health, generation and the reflection service itself
+    reflection.enable_server_reflection((_health.SERVICE_NAME, pb2.SERVICE_NAME), server,
+                                        [_health.FILE_DESCRIPTOR_SERIALIZED, pb2.FILE_DESCRIPTOR_SERIALIZED])
     host = "0.0.0.0" if args.host is None else args.host  # noqa: S104
     listen_on = f"{host}:{args.grpc_port}"
     ssl_keyfile, ssl_certfile, ssl_ca_certs = args.ssl_keyfile, args.ssl_certfile, args.ssl_ca_certs

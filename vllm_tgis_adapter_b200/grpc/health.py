@@ -33,13 +33,20 @@ def _build():
     f = resp.field.add()
     f.name, f.number, f.type, f.label = "status", 1, f.TYPE_ENUM, f.LABEL_OPTIONAL
     f.type_name = ".grpc.health.v1.HealthCheckResponse.ServingStatus"
+    svc = fd.service.add()
+    svc.name = "Health"
+    for name, streaming in (("Check", False), ("Watch", True)):
+        m = svc.method.add()
+        m.name, m.server_streaming = name, streaming
+        m.input_type, m.output_type = ".grpc.health.v1.HealthCheckRequest", ".grpc.health.v1.HealthCheckResponse"
     pool = descriptor_pool.DescriptorPool()
     pool.Add(fd)
     return (message_factory.GetMessageClass(pool.FindMessageTypeByName("grpc.health.v1.HealthCheckRequest")),
-            message_factory.GetMessageClass(pool.FindMessageTypeByName("grpc.health.v1.HealthCheckResponse")))
+            message_factory.GetMessageClass(pool.FindMessageTypeByName("grpc.health.v1.HealthCheckResponse")),
+            fd.SerializeToString())
 
 
-HealthCheckRequest, HealthCheckResponse = _build()
+HealthCheckRequest, HealthCheckResponse, FILE_DESCRIPTOR_SERIALIZED = _build()
 
 
 class HealthServicer:
