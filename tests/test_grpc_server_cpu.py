@@ -6,6 +6,7 @@ tests (stop sequences, stop reasons, logprobs/ranks/top-n, validation errors).""
 import argparse
 import asyncio
 import threading
+import time
 
 import grpc
 import pytest
@@ -285,3 +286,39 @@ def test_server_reflection_lists_services_and_serves_descriptors(srv, version):
     assert resps[4].WhichOneof("message_response") == "error_response" and resps[4].error_response.error_code == 5
     assert resps[5].original_request.file_containing_symbol == "fmaas.Parameters"
     assert resps[5].file_descriptor_response.file_descriptor_proto
+
+
+def test_http_sidecar_health_and_vllm_named_metrics(srv):
+    """/health and /metrics of the HTTP side-car (reference http.py:41-99, tests/test_http_server.py:4-34): after a few
+    requests through gRPC the Prometheus text must carry vLLM's metric names with the request counts and histograms."""
+    import urllib.request
+
+    from vllm_tgis_adapter_b200 import http as sidecar
+
+    srv.generate(["t1 t2 t3", "t4 t5"], _params(stopping={"max_new_tokens": 5, "min_new_tokens": 5}))
+    srv.stream("t9 t8 t7", _params(stopping={"max_new_tokens": 3, "min_new_tokens": 3}))
+    args = argparse.Namespace(host="127.0.0.1", port=0)
+    fut = asyncio.run_coroutine_threadsafe(sidecar.run_http_server(args, srv.engine), srv.loop)
+    for _ in range(200):
+        if getattr(sidecar.run_http_server, "bound_port", 0):
+            break
+        time.sleep(0.01)
+    port = sidecar.run_http_server.bound_port
+    try:
+        with urllib.request.urlopen(f"http://127.0.0.1:{port}/health", timeout=5) as r:
+            assert r.status == 200
+        with urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=5) as r:
+            text = r.read().decode()
+    finally:
+        fut.cancel()
+    def value(name):
+        return next(float(line.rsplit(" ", 1)[1]) for line in text.splitlines() if line.startswith(name))
+    import re
+    m = re.search(r'vllm:request_success_total\{[^}]*finished_reason="length"[^}]*\} (\S+)', text)
+    assert m and float(m.group(1)) == 3.0
+    assert value("vllm:generation_tokens_total{") == 13.0
+    assert value("vllm:prompt_tokens_total{") == 8.0
+    assert value("vllm:time_to_first_token_seconds_count{") == 3.0
+    assert value("vllm:e2e_request_latency_seconds_count{") == 3.0
+    assert value("vllm:request_generation_tokens_sum{") == 13.0
+    assert "vllm:num_requests_running{" in text and "vllm:kv_cache_usage_perc{" in text

@@ -18,6 +18,7 @@ from collections.abc import AsyncGenerator
 from . import _lib
 from .core import ModelConfig, NativeEngine, StepOutput, make_sampling_params
 from .detokenizer import IncrementalDetokenizer
+from ..metrics import EngineMetrics
 from .types import (CompletionOutput, Logprob, RequestMetrics, RequestOutput, RequestOutputKind, SamplingParams,
                     TokensPrompt)
 
@@ -57,6 +58,7 @@ class AsyncTGISEngine:
         self._poller: threading.Thread | None = None
         self._stopping = False
         self._dead_error: str | None = None
+        self.metrics = EngineMetrics()
 
     # -- lifecycle ------------------------------------------------------------------------------------------------
     def start(self, loop: asyncio.AbstractEventLoop | None = None) -> None:
@@ -229,6 +231,10 @@ class AsyncTGISEngine:
                     finished=finished, metrics=metrics)
                 if finished:
                     st.done = True
+                    self.metrics.observe_finished(
+                        n_prompt=len(prompt_ids), n_generated=len(st.token_ids), finish_reason=finish_reason,
+                        arrival=last.ts_arrival, first_scheduled=last.ts_first_scheduled,
+                        first_token=last.ts_first_token, last_token=last.ts_last_token)
                     return
         finally:
             if not st.done:   # client went away / generator closed early: free the sequence in the engine

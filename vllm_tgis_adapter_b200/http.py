@@ -10,18 +10,13 @@ logger = logging.getLogger("vllm_tgis_adapter.http")
 
 
 def _metrics(engine) -> bytes:
-    st = engine.engine.status()
-    lines = [
-        "# TYPE vllm:num_requests_running gauge", f"vllm:num_requests_running {st.n_running}",
-        "# TYPE vllm:num_requests_waiting gauge", f"vllm:num_requests_waiting {st.n_waiting}",
-        "# TYPE vllm:gpu_cache_usage_perc gauge",
-        f"vllm:gpu_cache_usage_perc {1.0 - st.free_blocks / max(st.total_blocks, 1):.6f}",
-        "# TYPE vllm:generation_tokens_total counter", f"vllm:generation_tokens_total {st.tokens_generated}",
-        "# TYPE tgis_engine_steps_total counter", f"tgis_engine_steps_total {st.steps}",
-        "# TYPE tgis_engine_kernel_launches_total counter", f"tgis_engine_kernel_launches_total {st.kernel_launches}",
-        "# TYPE tgis_engine_gpu_busy_seconds_total counter", f"tgis_engine_gpu_busy_seconds_total {st.gpu_busy_ms / 1e3:.6f}",
-    ]
-    return ("\n".join(lines) + "\n").encode()
+    """vLLM's metric names (`vllm:*`: gauges from the engine status, request histograms fed by AsyncTGISEngine) plus a few
+    engine counters of our own."""
+    try:
+        st = engine.engine.status()
+    except Exception:  # noqa: BLE001
+        st = None
+    return engine.metrics.render(st)
 
 
 async def run_http_server(args, engine) -> None:
@@ -48,7 +43,8 @@ async def run_http_server(args, engine) -> None:
             writer.close()
 
     server = await asyncio.start_server(handle, args.host or "0.0.0.0", args.port)  # noqa: S104
-    logger.info("HTTP side-car started at %s:%d", args.host or "0.0.0.0", args.port)  # noqa: S104
+    run_http_server.bound_port = server.sockets[0].getsockname()[1]      # (tests bind port 0)
+    logger.info("HTTP side-car started at %s:%d", args.host or "0.0.0.0", run_http_server.bound_port)  # noqa: S104
     try:
         async with server:
             await server.serve_forever()
