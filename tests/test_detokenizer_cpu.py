@@ -45,3 +45,24 @@ def test_min_tokens_suppresses_stop_match():
                                skip_special_tokens=True)
     assert d.update([7], False) is None and d.update([8], False) is None and d.update([9], False) is None
     assert d.update([7], False) == "t7"
+
+
+def test_backend_fast_path_is_text_identical_to_the_wrapper():
+    """The incremental detokenizer calls the Rust tokenizer's decode directly (skipping transformers' Python wrapper);
+    with clean_up_tokenization_spaces=False both must yield the same text, also with special tokens in the stream."""
+    import random
+
+    from vllm_tgis_adapter_b200.engine.detokenizer import IncrementalDetokenizer
+    from vllm_tgis_adapter_b200.engine.tokenizer import build_synthetic_tokenizer
+
+    tok = build_synthetic_tokenizer(512)
+    rnd = random.Random(3)
+    specials = [i for i in (tok.bos_token_id, tok.eos_token_id) if i is not None]
+    for skip in (True, False):
+        d = IncrementalDetokenizer(tok, [5, 6, 7], stop=None, min_tokens=0, include_stop_str_in_output=True,
+                                   skip_special_tokens=skip)
+        assert d._backend_decode is not None
+        for _ in range(50):
+            ids = [rnd.randrange(3, 512) for _ in range(rnd.randrange(1, 6))] + rnd.sample(specials, k=min(1, len(specials)))
+            rnd.shuffle(ids)
+            assert d._decode(ids) == tok.decode(ids, skip_special_tokens=skip, clean_up_tokenization_spaces=False)
