@@ -79,3 +79,48 @@ def test_tensor_parallel_flags_reach_the_engine_builder():
     args = parse_args(["--model", "no/such/dir", "--tensor-parallel-size", "2"])
     with pytest.raises(ValueError, match="does not exist"):
         build_engine(args)
+
+
+def test_startup_failure_is_written_to_the_termination_log(tmp_path, monkeypatch):
+    """Reference tests/test_termination_log.py: a set-up error (here: a model path that does not exist) must crash the
+    entrypoint AND leave the traceback in the k8s termination log, which is only written when the file already exists."""
+    import pytest
+
+    from vllm_tgis_adapter_b200.__main__ import main
+    from vllm_tgis_adapter_b200.utils import write_termination_log
+
+    log = tmp_path / "termination_log.txt"
+    log.touch()
+    monkeypatch.setenv("TERMINATION_LOG_DIR", str(log))
+    with pytest.raises(BaseException):  # noqa: B017,PT011  (ValueError from build_engine, re-raised by the entrypoint)
+        main(["--model", str(tmp_path / "no-such-model"), "--grpc-port", "0", "--port", "0"])
+    text = log.read_text()
+    assert "does not exist" in text and "Traceback" in text
+    missing = tmp_path / "absent.txt"
+    write_termination_log("x", str(missing))          # no file -> nothing created (utils.py:20-40)
+    assert not missing.exists()
+
+
+def test_check_for_failed_tasks_picks_the_task_that_raised():
+    import asyncio
+
+    from vllm_tgis_adapter_b200.utils import check_for_failed_tasks
+
+    async def run():
+        async def ok():
+            await asyncio.sleep(0)
+
+        async def bad():
+            raise RuntimeError("boom")
+
+        async def forever():
+            await asyncio.sleep(10)
+
+        tasks = [asyncio.create_task(ok(), name="ok"), asyncio.create_task(bad(), name="bad"),
+                 asyncio.create_task(forever(), name="pending")]
+        await asyncio.wait(tasks[:2])
+        failed = check_for_failed_tasks(tasks)
+        tasks[2].cancel()
+        return failed.get_name()
+
+    assert asyncio.run(run()) == "bad"
