@@ -47,3 +47,28 @@ def test_single_process_is_identity():
     import bench
 
     assert bench.reduce_over_ranks([3.0], [5.0], "cpu") == ([3.0], [5.0])
+
+
+def test_reference_arm_json_contract_on_cpu():
+    """`bench.py --impl reference` (the CPU port of the reference path on the host cores) must print ONE JSON line with
+    the driver-contract keys: impl, the same metric / unit / higher_is_better as our arm, a cpu_baseline describing the
+    run and an e2e block with zero copy bytes.  Run here on a tiny shape so that the contract is checked without a GPU."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--model", "tiny", "--batch", "4",
+                        "--prompt-len", "32", "--gen-len", "8", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0
+    assert d["metric"].startswith("decode tokens/sec")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
