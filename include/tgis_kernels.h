@@ -58,6 +58,10 @@ int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const v
 /* logits_dev: fp32 [rows, ld] */
 int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
                    void* seen_bitmap_dev, void* out_host);
+/* same, logits_bf16 = 1: logits_dev is bf16 [rows, ld] (the product path's dtype); iters > 1 repeats the launch and
+ * us_out (may be NULL) receives the average device time per launch */
+int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
+                      int32_t n_rows, void* seen_bitmap_dev, void* out_host, int32_t iters, float* us_out);
 const char* tgis_k_last_error(void);
 /* debug builds only (-DTGIS_GEMM_TIMELINE): %globaltimer stamps of CTA 0 and CTA grid/2, [4][16] u64; else -2 */
 int tgis_k_gemm_timeline(uint64_t* out64);

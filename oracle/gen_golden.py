@@ -125,6 +125,47 @@ def llama_fixture() -> dict:
             "rope_theta_used": float(getattr(model.config, "rope_theta", cfg.rope_theta) or cfg.rope_theta)}
 
 
+def llama_bf16_fixture() -> dict:
+    """HF LlamaForCausalLM run in bf16 on CPU (sdpa attention: fp32 softmax inside the fused kernel, like the flash
+    kernels vLLM uses): pins WHERE the oracle rounds to the model dtype (after every linear, after the norm product,
+    after RoPE products, after attention, logits) -- the fp32 fixture above cannot see those points."""
+    from transformers import LlamaConfig as HFConfig
+    from transformers import LlamaForCausalLM
+
+    from oracle.llama_oracle import CONFIGS, synthetic_weights
+
+    out = {"cases": []}
+    for name, seed, prompt_len in (("tiny", 21, 48), ("small", 22, 40)):
+        cfg = CONFIGS[name]
+        hf_cfg = HFConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.ffn,
+                          num_hidden_layers=cfg.n_layers, num_attention_heads=cfg.n_q_heads,
+                          num_key_value_heads=cfg.n_kv_heads, head_dim=cfg.head_dim, rms_norm_eps=cfg.rms_eps,
+                          rope_theta=cfg.rope_theta, max_position_embeddings=cfg.max_model_len,
+                          tie_word_embeddings=False, attn_implementation="sdpa")
+        try:
+            hf_cfg.rope_parameters = {"rope_type": "default", "rope_theta": cfg.rope_theta}
+        except Exception:  # noqa: BLE001
+            pass
+        model = LlamaForCausalLM(hf_cfg).to(torch.bfloat16).eval()
+        w = synthetic_weights(cfg, seed=seed)   # bf16
+        missing, unexpected = model.load_state_dict(w, strict=False)
+        assert not unexpected and all("rotary" in m or "inv_freq" in m for m in missing), (missing, unexpected)
+        g = torch.Generator().manual_seed(seed)
+        prompt = torch.randint(3, cfg.vocab, (prompt_len,), generator=g).tolist()
+        with torch.no_grad():
+            logits = model(torch.tensor([prompt])).logits[0]   # [T, V] bf16
+        assert logits.dtype == torch.bfloat16
+        lf = logits.float()
+        top2 = torch.topk(lf, 2, dim=-1).values
+        out["cases"].append({
+            "config": name, "weights_seed": seed, "prompt": prompt,
+            "argmax_per_pos": lf.argmax(-1).tolist(), "top2_margin_per_pos": f32list(top2[:, 0] - top2[:, 1]),
+            "logsumexp_per_pos": f32list(torch.logsumexp(lf, -1)),
+            "last_logits": f32list(lf[-1]),          # full last row (bf16 values, exactly representable)
+            "mid_logits_head": f32list(lf[prompt_len // 2, :256])})
+    return out
+
+
 def main() -> None:
     OUT.mkdir(parents=True, exist_ok=True)
     import transformers
@@ -138,6 +179,9 @@ def main() -> None:
     m = llama_fixture()
     m["meta"] = meta
     (OUT / "llama_tiny_hf_fp32.json").write_text(json.dumps(m))
+    b = llama_bf16_fixture()
+    b["meta"] = meta
+    (OUT / "llama_hf_bf16.json").write_text(json.dumps(b))
     print("wrote", [p.name for p in OUT.iterdir()])
 
 

@@ -18,9 +18,12 @@ HF-format Llama checkpoint.  Restated here, with the file:line each step follows
   attention          causal softmax(q k^T / sqrt(d)) v with fp32 scores/probabilities (flash-attention semantics:
                      vllm v1/attention/backends/flashinfer.py:1665,1803), output rounded to model dtype
   SiLU * mul         vllm model_executor/layers/activation.py:117-143 ; HF LlamaMLP.forward
-  logits             vllm model_executor/layers/logits_processor.py:89-104 (lm_head on last-token rows); kept in fp32
-                     here and in the engine (strictly more precise than vLLM's bf16 logits, needed for the 1e-3
-                     logprob contract)
+  logits             vllm model_executor/layers/logits_processor.py:89-104 (lm_head on last-token rows): F.linear in
+                     the model dtype, i.e. the fp32 accumulator rounded ONCE to bf16; the sampler then casts to fp32
+                     (v1/sample/sampler.py:91).  Exact ties between bf16 logits (thousands per 128k-vocab row) are
+                     therefore part of the reference's behaviour: they inflate `rank` and decide greedy argmax by
+                     lowest token id.  (Round 1 kept fp32 logits here and in the engine; `logits_fp32=True` restores
+                     that for the experiment switch TGIS_LOGITS_FP32.)
 
 PARITY PINNING: the reference's own tests hold no numeric golden vector for this path ("parity
 unpinned" for token ids / logprobs).  This oracle is therefore pinned against the third-party implementation it
@@ -123,9 +126,11 @@ class SeqState:
 class LlamaOracle:
     """Flat-batch Llama forward with the model-dtype rounding points of the vLLM/HF path."""
 
-    def __init__(self, cfg: LlamaConfig, weights: dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16):
+    def __init__(self, cfg: LlamaConfig, weights: dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16,
+                 logits_fp32: bool = False):
         self.cfg = cfg
         self.dtype = dtype
+        self.logits_fp32 = logits_fp32
         w = {k: v.to(dtype) for k, v in weights.items()}
         self.embed = w["model.embed_tokens.weight"]
         self.lm_head = w.get("lm_head.weight", self.embed)
@@ -225,14 +230,16 @@ class LlamaOracle:
         return self.head(xn, normed=True)
 
     def head(self, x: torch.Tensor, normed: bool = False) -> torch.Tensor:
-        """final RMSNorm (unless already applied) + lm_head.  Logits stay fp32 (no model-dtype round trip): the
-        engine's lm_head epilogue writes the fp32 accumulator.  vLLM rounds them to bf16 first
-        (logits_processor.py:89-104); see DESIGN.md 'logits precision'."""
+        """final RMSNorm (unless already applied) + lm_head -> the fp32 view of the model-dtype logits (what vLLM's
+        sampler sees: logits_processor.py:89-104 rounds to bf16, sampler.py:91 casts up)."""
         if not normed:
             x = self._rms(x, self.norm)
         if self._lm_head_f32 is None:
             self._lm_head_f32 = self.lm_head.float()
-        return x.float() @ self._lm_head_f32.t()
+        acc = x.float() @ self._lm_head_f32.t()
+        if self.logits_fp32:
+            return acc
+        return acc.to(self.dtype).float()
 
     def new_seq(self) -> SeqState:
         return SeqState(self.cfg, self.dtype)

@@ -93,6 +93,37 @@ def test_llama_oracle_matches_hf_fixture_fp32():
     np.testing.assert_allclose(logits[-1, :32].numpy(), np.array(g["last_logits_head"]), atol=2e-4)
 
 
+def test_llama_oracle_bf16_rounding_points_match_hf_bf16_fixture():
+    """The oracle in bf16 vs transformers' LlamaForCausalLM run in bf16 (tests/golden/llama_hf_bf16.json): same rounding
+    points => logits agree to a few bf16 ulps (the two differ only in fp32 summation order inside the matmuls), and
+    greedy argmax agrees wherever HF's own top-2 margin exceeds that."""
+    g = json.loads((GOLD / "llama_hf_bf16.json").read_text())
+    for case in g["cases"]:
+        cfg = CONFIGS[case["config"]]
+        w = synthetic_weights(cfg, seed=case["weights_seed"])
+        ora = LlamaOracle(cfg, w)
+        logits = ora.step([(ora.new_seq(), case["prompt"])], want_all_logits=True)
+        # every value is a bf16 number (the sampler's fp32 view of model-dtype logits)
+        assert torch.equal(logits, logits.to(torch.bfloat16).float())
+        last = torch.tensor(case["last_logits"])
+        d = (logits[-1] - last).abs()
+        # measured: max |diff| = 1-2 bf16 ulps at the row's magnitude, mean ~0.3 ulp, 20-26 % of the logits bit-identical
+        # (HF's CPU matmuls and the oracle's sum the same fp32 products in different orders; upstream bf16 roundings
+        # that land on the other side of a tie move a logit by one ulp)
+        ulp_row = 2.0 ** (torch.floor(torch.log2(last.abs().max())).item() - 7)
+        assert float(d.max()) <= 2.0 * ulp_row, (float(d.max()), ulp_row)
+        assert float(d.mean()) < 0.5 * ulp_row
+        assert float((d == 0).float().mean()) > 0.15
+        mid = torch.tensor(case["mid_logits_head"])
+        dm = (logits[len(case["prompt"]) // 2, :256] - mid).abs()
+        assert float(dm.max()) < 0.05
+        np.testing.assert_allclose(torch.logsumexp(logits, -1).numpy(), np.array(case["logsumexp_per_pos"]), atol=1e-2)
+        am = logits.argmax(-1).tolist()
+        for pos, (a, b, m) in enumerate(zip(am, case["argmax_per_pos"], case["top2_margin_per_pos"])):
+            if m > 0.04:
+                assert a == b, (case["config"], pos, a, b, m)
+
+
 def test_llama_oracle_incremental_equals_prefill_and_bf16_is_close():
     cfg = CONFIGS["tiny"]
     w = synthetic_weights(cfg, seed=4)

@@ -17,7 +17,7 @@ LIB_DIR = PKG / "lib"
 OBJ_DIR = CSRC / "build"
 LIB_PATH = LIB_DIR / "libtgis_engine.so"
 SOURCES = ["gemm_tcgen05.cu", "gemm_ref.cu", "elementwise.cu", "attention.cu", "sampler.cu", "engine.cu", "test_api.cu"]
-HEADERS = ["ptx.cuh", "kernels.h", "../../include/tgis_engine.h", "../../include/tgis_kernels.h"]
+HEADERS = ["ptx.cuh", "launch.cuh", "kernels.h", "../../include/tgis_engine.h", "../../include/tgis_kernels.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -32,6 +32,18 @@ def _nvcc() -> str:
         if cand and (cand == "nvcc" or Path(cand).exists()):
             return cand
     raise RuntimeError("nvcc not found")
+
+
+def have_nvcc() -> bool:
+    try:
+        n = _nvcc()
+    except RuntimeError:
+        return False
+    if n == "nvcc":
+        import shutil
+
+        return shutil.which("nvcc") is not None
+    return True
 
 
 def _digest() -> str:

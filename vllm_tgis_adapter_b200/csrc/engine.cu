@@ -158,19 +158,17 @@ struct ShmCtl {
 };
 constexpr size_t SHM_STAGE_OFF = 1024;
 
-__global__ void gather_relayout_kernel(const float* __restrict__ gathered, float* __restrict__ out, int R, int Vl,
+// gathered: [tp][R][Vl] -> out: [R][tp*Vl], elements of `esz` bytes moved as 16-byte vectors (Vl * esz % 16 == 0)
+__global__ void gather_relayout_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ out, int R, int Vl16,
                                        int tp) {
   griddep_launch();
   griddep_wait();
-  // gathered: [tp][R][Vl] -> out: [R][tp*Vl]
-  const size_t total = (size_t)tp * R * Vl / 4;
+  const size_t total = (size_t)tp * R * Vl16;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t e = i * 4;
-    const int rk = (int)(e / ((size_t)R * Vl));
-    const size_t rem = e % ((size_t)R * Vl);
-    const int r = (int)(rem / Vl), v = (int)(rem % Vl);
-    *reinterpret_cast<float4*>(out + (size_t)r * tp * Vl + (size_t)rk * Vl + v) =
-        *reinterpret_cast<const float4*>(gathered + e);
+    const int rk = (int)(i / ((size_t)R * Vl16));
+    const size_t rem = i % ((size_t)R * Vl16);
+    const int r = (int)(rem / Vl16), v = (int)(rem % Vl16);
+    out[(size_t)r * tp * Vl16 + (size_t)rk * Vl16 + v] = gathered[i];
   }
 }
 
@@ -199,7 +197,7 @@ struct tgis_engine {
   bool shm_owner = false;
   std::string shm_name;
   uint64_t plan_seq = 0;
-  DevBuf<float> logits_shard, logits_gather;
+  DevBuf<uint8_t> logits_shard, logits_gather;  // [R, V/tp] and [tp][R, V/tp] in the logits dtype
   int T_max = 0, S_max = 0, tiles_max = 0;
 
   // weights
@@ -215,7 +213,13 @@ struct tgis_engine {
   std::vector<int32_t> free_blocks;
   // activations
   DevBuf<bf16> resid, xn, qkv, attn_out, tmp, gate_up, act, last_hidden;
-  DevBuf<float> logits;  // fp32 straight from the lm_head accumulator
+  // lm_head output [rows, V].  bf16 = the model dtype, rounded once from the fp32 accumulator exactly where vLLM's
+  // lm_head rounds (vllm model_executor/layers/logits_processor.py:89-104 -> F.linear in bf16; the sampler then casts to
+  // fp32, v1/sample/sampler.py:91): exact ties between bf16 logits, and the ranks / lowest-id argmax they cause, are
+  // reproduced.  TGIS_LOGITS_FP32=1 keeps the raw fp32 accumulator (round 1's behaviour; an experiment switch).
+  DevBuf<uint8_t> logits;
+  bool logits_bf16 = true;
+  size_t lsz = 2;  // bytes per logit
   CUtensorMap xm_xn[N_BT], xm_attn[N_BT], xm_act[N_BT], xm_last[N_BT];
   DevBuf<float> gemm_ws, part_o, part_ml, samp_scratch;
   DevBuf<int> gemm_counters;
@@ -331,6 +335,8 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_FUSE_ROPE")) fuse_rope = atoi(e) != 0;
     if (const char* e = getenv("TGIS_FUSE_ROPE_MAX_T")) rope_fuse_max_t = atoi(e);
     if (const char* e = getenv("TGIS_TP_FUSED_AR")) tp_fused_ar = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_LOGITS_FP32")) logits_bf16 = atoi(e) == 0;
+    lsz = logits_bf16 ? 2 : 4;
     chain_sync.alloc(CHAIN_MAX_STEPS + 1);
     chain_sync.zero();
 
@@ -370,10 +376,10 @@ struct tgis_engine {
     gate_up.alloc(64);  // unused since SwiGLU moved into the gate_up GEMM epilogue
     act.alloc(T_alloc * F);
     last_hidden.alloc(S_alloc * H);
-    logits.alloc((size_t)S_max * V);
+    logits.alloc((size_t)S_max * V * lsz);
     if (tp > 1) {
-      logits_shard.alloc((size_t)S_max * Vl);
-      logits_gather.alloc((size_t)tp * S_max * Vl);
+      logits_shard.alloc((size_t)S_max * Vl * lsz);
+      logits_gather.alloc((size_t)tp * S_max * Vl * lsz);
     }
     xn.zero(); attn_out.zero(); act.zero(); last_hidden.zero();
     gemm_ws.alloc(gemm_workspace_bytes(num_sms) / sizeof(float));
@@ -863,21 +869,22 @@ struct tgis_engine {
       }
       CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
       ++n_launches;
+      const int lm_mode = logits_bf16 ? 0 : 1;
       if (tp == 1) {
-        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, /*out_f32=*/1);
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, lm_mode);
       } else {
-        // vocab-parallel lm_head: every rank computes [R, V/tp] fp32, all-gather, re-layout to [R, V]
-        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, R, Vl, H, /*out_f32=*/1);
-        NK(nccl().AllGather(logits_shard.p, logits_gather.p, (size_t)R * Vl, ncclFloat, comm, stream));
+        // vocab-parallel lm_head: every rank computes [R, V/tp], all-gather, re-layout to [R, V]
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, R, Vl, H, lm_mode);
+        NK(nccl().AllGather(logits_shard.p, logits_gather.p, (size_t)R * Vl * lsz, ncclInt8, comm, stream));
         if (rank == 0) {
-          CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const float*)logits_gather.p,
-                      logits.p, R, Vl, tp));
+          CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const uint4*)logits_gather.p,
+                      (uint4*)logits.p, R, (int)(Vl * lsz / 16), tp));
           ++n_launches;
         }
       }
       if (rank == 0) {
-        CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words, samp_scratch.p,
-                          d_samp_out.p, stream));
+        CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words,
+                          samp_scratch.p, d_samp_out.p, stream));
         ++n_launches;
         CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
       }
@@ -1066,9 +1073,9 @@ struct tgis_engine {
         CK(cudaMemcpyAsync(ds<int32_t>(off_samplesrc), samplesrc, sizeof(int32_t) * m, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(ds<SampleRow>(off_rows), rows, sizeof(SampleRow) * m, cudaMemcpyHostToDevice, stream));
         CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, m, H, stream));
-        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, m, V, H, /*out_f32=*/1);
-        CK(sampler_launch(logits.p, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words, samp_scratch.p,
-                          d_samp_out.p, stream));
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, m, V, H, logits_bf16 ? 0 : 1);
+        CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words,
+                          samp_scratch.p, d_samp_out.p, stream));
         n_launches += 2;
         CK(cudaMemcpyAsync(h_plp_out, d_samp_out.p, sizeof(SampleOut) * m, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -1264,6 +1271,10 @@ struct tgis_engine {
         if (finish == TGIS_FINISH_NONE && ((int)r.tokens.size() >= cfg.max_model_len || n_out >= r.sp.max_tokens))
           finish = TGIS_FINISH_LENGTH;
       }
+      // Safety net outside the min_tokens guard (vLLM's check_stop returns early there; its SamplingParams validation
+      // is what keeps min_tokens <= max_tokens -- add_request enforces the same, so this never changes a result): a
+      // sequence must never outgrow its block-table row / the RoPE table.
+      if (finish == TGIS_FINISH_NONE && (int)r.tokens.size() >= cfg.max_model_len) finish = TGIS_FINISH_LENGTH;
       emit(r, true, &so, finish, stop_tok);
       if (finish != TGIS_FINISH_NONE) finished.push_back(&r);
     }
@@ -1406,6 +1417,11 @@ int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_
   if (n_prompt >= e->cfg.max_model_len) return fail("prompt longer than max_model_len");
   if (strlen(request_id) >= TGIS_MAX_REQUEST_ID) return fail("request id too long");
   if (params->max_tokens < 1) return fail("max_tokens must be >= 1");
+  // vllm sampling_params.py _verify_args: min_tokens <= max_tokens; validation.py:64-77: prompt + min_tokens must fit
+  if (params->min_tokens < 0) return fail("min_tokens must be >= 0");
+  if (params->min_tokens > params->max_tokens) return fail("min_tokens must be less than or equal to max_tokens");
+  if ((long long)n_prompt + params->min_tokens > e->cfg.max_model_len)
+    return fail("prompt length + min_tokens exceeds max_model_len");
   if (params->n_stop_token_ids > TGIS_MAX_STOP_TOKEN_IDS || params->n_stop_token_ids < 0) return fail("too many stop token ids");
   if (!params->greedy && !(params->temperature > 0.f)) return fail("temperature must be > 0 when sampling");
   if (params->num_logprobs > TGIS_MAX_TOPN || params->prompt_logprobs > TGIS_MAX_TOPN) return fail("num_logprobs too large");

@@ -204,8 +204,9 @@ struct SampleOut {            // per row result (pinned host readable)
 };
 constexpr int SAMPLE_GREEDY = 1, SAMPLE_LOGPROBS = 2, SAMPLE_TYPICAL = 4, SAMPLE_LENPEN = 8, SAMPLE_SEEDED = 16;
 constexpr int SAMPLE_FORCED = 32;  // token = seed_lo is given (prompt logprobs): report its logprob / rank / top-n only
-// logits: fp32 [rows, ld] straight from the lm_head GEMM accumulator (no bf16 round trip)
-cudaError_t sampler_launch(const float* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+// logits: [rows, ld] bf16 (logits_bf16 = 1: the lm_head GEMM's model-dtype output, what vLLM's sampler sees after its
+// fp32 cast) or fp32 (kernel-level golden tests)
+cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int vocab, const SampleRow* rows, int n_rows,
                            const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
                            cudaStream_t stream);
 // seen-token bitmap maintenance

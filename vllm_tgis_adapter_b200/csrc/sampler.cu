@@ -29,8 +29,12 @@ constexpr int SAMP_CL = 8;  // CTAs (SMs) per row
 constexpr int SAMP_THREADS = 1024;
 constexpr int SAMP_WARPS = SAMP_THREADS / 32;
 
+// LT = logits element type: __nv_bfloat16 on the product path (vLLM's lm_head emits model-dtype logits and the sampler
+// casts them to fp32: vllm v1/sample/sampler.py:91 -- every bf16 value is exactly representable), float for the
+// kernel-level golden tests (fp32 fixtures generated from the reference's own code).
+template <class LT>
 struct RowCtx {
-  const float* x;          // raw logits (fp32, straight from the lm_head accumulator)
+  const LT* x;             // raw logits
   int V;
   int lo, hi;              // this CTA's slice of the vocabulary (multiples of 8)
   const uint32_t* seen;    // bitmap of prompt U output tokens (may be null)
@@ -42,14 +46,34 @@ struct RowCtx {
   float raw_max, raw_logz, ent, typ_thr;
 };
 
-__device__ __forceinline__ float load_x(const RowCtx& c, int i) { return c.x[i]; }
+__device__ __forceinline__ float lt2f(float v) { return v; }
+__device__ __forceinline__ float lt2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <class LT>
+__device__ __forceinline__ float load_x(const RowCtx<LT>& c, int i) { return lt2f(c.x[i]); }
+// 8 consecutive logits (i0 % 8 == 0) as fp32
+__device__ __forceinline__ void load_x8(const float* x, int i0, float (&o)[8]) {
+  const float4 ra = *reinterpret_cast<const float4*>(x + i0);
+  const float4 rb = *reinterpret_cast<const float4*>(x + i0 + 4);
+  o[0] = ra.x; o[1] = ra.y; o[2] = ra.z; o[3] = ra.w; o[4] = rb.x; o[5] = rb.y; o[6] = rb.z; o[7] = rb.w;
+}
+__device__ __forceinline__ void load_x8(const __nv_bfloat16* x, int i0, float (&o)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(x + i0);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    o[2 * e] = __uint_as_float(w[e] << 16);
+    o[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
 
-__device__ __forceinline__ bool is_seen(const RowCtx& c, int i) {
+template <class LT>
+__device__ __forceinline__ bool is_seen(const RowCtx<LT>& c, int i) {
   return c.seen != nullptr && ((c.seen[i >> 5] >> (i & 31)) & 1u);
 }
 
 // processed logit (before temperature) of vocabulary entry i with raw value x
-__device__ __forceinline__ float process(const RowCtx& c, int i, float x) {
+template <class LT>
+__device__ __forceinline__ float process(const RowCtx<LT>& c, int i, float x) {
   float y = x;
   if (c.typical) {
     const float lp = (x - c.raw_max) - c.raw_logz;
@@ -347,8 +371,9 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // ---------------------------------------------------------------- the kernel
+template <class LT>
 __global__ void __cluster_dims__(SAMP_CL, 1, 1) __launch_bounds__(SAMP_THREADS, 1)
-tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
+tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
                     uint32_t* __restrict__ seen_bitmap, int bitmap_words, float* __restrict__ scratch,
                     SampleOut* __restrict__ outs) {
   __shared__ float redf[2 * SAMP_WARPS];
@@ -364,7 +389,7 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
 
   const int r = blockIdx.x / SAMP_CL;
   const int crank = (int)cg::this_cluster().block_rank();
-  RowCtx c;
+  RowCtx<LT> c;
   c.p = rows[r];
   c.V = V;
   {
@@ -390,9 +415,8 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   const bool do_typ = (c.p.flags & SAMPLE_TYPICAL) != 0 && !forced;
   const bool greedy_fast = greedy && !do_typ;  // argmax fused into the first sweep
   for (int i0 = lo + threadIdx.x * 8; i0 < hi; i0 += SAMP_THREADS * 8) {
-    const float4 ra = *reinterpret_cast<const float4*>(c.x + i0);
-    const float4 rb = *reinterpret_cast<const float4*>(c.x + i0 + 4);
-    const float xs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    float xs[8];
+    load_x8(c.x, i0, xs);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float x = xs[e];
@@ -424,12 +448,12 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
       }
       c.ent = -cluster_sumf(part, redf, xch);
       const float rm = c.raw_max, lz = c.raw_logz, ent = c.ent;
-      const float* xx = c.x;
+      const LT* xx = c.x;
       auto keyf = [=](int i) {
-        const float lp = (xx[i] - rm) - lz;
+        const float lp = (lt2f(xx[i]) - rm) - lz;
         return __float_as_uint(fabsf((-lp) - ent));
       };
-      auto wf = [=](int i) { return expf((xx[i] - rm) - lz); };
+      auto wf = [=](int i) { return expf((lt2f(xx[i]) - rm) - lz); };
       const uint32_t k = select_weighted_asc(lo, hi, keyf, wf, c.p.typical_p, false, histf, histsumf, bcast);
       c.typ_thr = __uint_as_float(k);
       c.typical = true;
@@ -551,13 +575,18 @@ tgis_sampler_kernel(const float* __restrict__ logits, int ld, int V, const Sampl
   }
 }
 
-cudaError_t sampler_launch(const float* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int vocab, const SampleRow* rows, int n_rows,
                            const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
                            cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   if (vocab % 8 != 0 || ld % 8 != 0) return cudaErrorInvalidValue;
-  return launch_k(tgis_sampler_kernel, dim3(n_rows * SAMP_CL), dim3(SAMP_THREADS), 0, stream, logits, ld, vocab, rows,
-                  const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out);
+  if (logits_bf16)
+    return launch_k(tgis_sampler_kernel<__nv_bfloat16>, dim3(n_rows * SAMP_CL), dim3(SAMP_THREADS), 0, stream,
+                    static_cast<const __nv_bfloat16*>(logits), ld, vocab, rows, const_cast<uint32_t*>(seen_bitmap),
+                    bitmap_words, scratch, out);
+  return launch_k(tgis_sampler_kernel<float>, dim3(n_rows * SAMP_CL), dim3(SAMP_THREADS), 0, stream,
+                  static_cast<const float*>(logits), ld, vocab, rows, const_cast<uint32_t*>(seen_bitmap), bitmap_words,
+                  scratch, out);
 }
 
 size_t sampler_scratch_floats(int vocab) { return (size_t)vocab; }

@@ -276,8 +276,10 @@ int tgis_k_decode_items(const int32_t* seqs_host, int32_t n_seqs, const int32_t*
                             bt_stride);
 }
 
-int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
-                   void* seen_bitmap_dev, void* out_host) {
+// logits_bf16 = 0: fp32 logits, 1: bf16 logits.  iters > 1: the launch is repeated and us_out (optional) receives the
+// average device time per launch (CUDA events on the launching stream).
+int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
+                      int32_t n_rows, void* seen_bitmap_dev, void* out_host, int32_t iters, float* us_out) {
   Tmp<SampleRow> rows;
   Tmp<SampleOut> outs;
   Tmp<float> scratch;
@@ -295,10 +297,29 @@ int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void
     KCK(cudaMemset(dummy_bm.p, 0, sizeof(uint32_t) * (size_t)(max_slot + 1) * words));
     bm = dummy_bm.p;
   }
-  KCK(sampler_launch((const float*)logits_dev, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
+  if (iters < 1) iters = 1;
+  cudaEvent_t e0, e1;
+  KCK(cudaEventCreate(&e0));
+  KCK(cudaEventCreate(&e1));
+  if (iters > 1)  // warm-up launch outside the timed region
+    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
+  KCK(cudaEventRecord(e0, 0));
+  for (int it = 0; it < iters; ++it)
+    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
+  KCK(cudaEventRecord(e1, 0));
   KCK(cudaMemcpy(out_host, outs.p, sizeof(SampleOut) * n_rows, cudaMemcpyDeviceToHost));
   KCK(cudaDeviceSynchronize());
+  float ms = 0.f;
+  KCK(cudaEventElapsedTime(&ms, e0, e1));
+  if (us_out) *us_out = 1e3f * ms / (float)iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
+}
+
+int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
+                   void* seen_bitmap_dev, void* out_host) {
+  return tgis_k_sampler_ex(logits_dev, 0, ld, vocab, rows_host, n_rows, seen_bitmap_dev, out_host, 1, nullptr);
 }
 
 }  // extern "C"

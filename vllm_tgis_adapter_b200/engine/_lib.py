@@ -72,7 +72,7 @@ ENGINE_SYMBOLS = [
 KERNEL_SYMBOLS = [
     "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_chain_timeline", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_attention",
     "tgis_k_attention_bench", "tgis_k_decode_items", "tgis_k_gemm_plan",
-    "tgis_k_sampler", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
+    "tgis_k_sampler", "tgis_k_sampler_ex", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
 ]
 
 _LIB: C.CDLL | None = None
@@ -91,10 +91,13 @@ def load_library() -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = library_path()
-    if not path.exists() or os.environ.get("TGIS_FORCE_BUILD"):
-        from vllm_tgis_adapter_b200.csrc.build import build
+    if not os.environ.get("TGIS_ENGINE_LIB"):
+        # build() is a digest compare when the library is current; it rebuilds after ANY source/header edit, so tests
+        # and benchmarks can never validate a stale .so.  Without nvcc (a deployment box) an existing library is used.
+        from vllm_tgis_adapter_b200.csrc.build import build, have_nvcc
 
-        build()
+        if have_nvcc() or not path.exists():
+            build(force=bool(os.environ.get("TGIS_FORCE_BUILD")))
     if not path.exists():
         raise RuntimeError(f"{path} is missing and could not be built: the TGIS B200 engine has no fallback path")
     lib = C.CDLL(str(path))
@@ -122,6 +125,7 @@ def load_library() -> C.CDLL:
     lib.tgis_k_rope_kv.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp, i32, i32, i32]
     lib.tgis_k_attention.argtypes = [vp, vp, vp, C.POINTER(i32), i32, C.POINTER(i32), i32, i32, vp, i32, i32, f32]
     lib.tgis_k_sampler.argtypes = [vp, i32, i32, vp, i32, vp, vp]
+    lib.tgis_k_sampler_ex.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp, i32, C.POINTER(f32)]
     _LIB = lib
     return lib
 

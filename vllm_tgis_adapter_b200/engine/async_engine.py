@@ -153,6 +153,8 @@ class AsyncTGISEngine:
                                        include_stop_str_in_output=sp.include_stop_str_in_output,
                                        skip_special_tokens=sp.skip_special_tokens)
         st = _ReqState(nid, prompt_ids, sp, detok, queue)
+        if request_id in self._states:   # vLLM rejects duplicate in-flight request ids as well
+            raise ValueError(f"request id {request_id!r} is already in flight")
         self._states[nid] = st
         self._states[request_id] = st
         delta = sp.output_kind == RequestOutputKind.DELTA
@@ -185,6 +187,9 @@ class AsyncTGISEngine:
                     step_finish: str | None = None
                     if o.finish_reason != _lib.FINISH_NONE:
                         if o.finish_reason == _lib.FINISH_ERROR:
+                            # the message lives in the engine object (set on the engine thread); status() copies it
+                            # into THIS thread's last-error slot
+                            self.engine.status()
                             raise EngineDeadError(_lib.last_error(self.engine.lib) or "engine error")
                         step_finish = _FINISH[o.finish_reason]
                     if o.new_token is not None:
@@ -241,4 +246,5 @@ class AsyncTGISEngine:
                 self.engine.abort(nid)
                 st.done = True
             self._states.pop(nid, None)
-            self._states.pop(request_id, None)
+            if self._states.get(request_id) is st:
+                del self._states[request_id]

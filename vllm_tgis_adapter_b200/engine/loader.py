@@ -154,6 +154,9 @@ def build_engine(args) -> AsyncTGISEngine:
             w.start()
         tp_kw = dict(tp_size=tp, tp_rank=0, nccl_id=nccl_id, shm_name=shm_name)
     eng = _make_native_engine(args, mc, path, args.device, **tp_kw)
-    tokenizer = load_tokenizer(args.tokenizer or (str(path) if path is not None else None), mc.vocab)
+    # the synthetic vocabulary only for synthetic models (preset + --synthetic-weights); a checkpoint directory without
+    # tokenizer files is a start-up error
+    tokenizer = load_tokenizer(args.tokenizer or (str(path) if path is not None else None), mc.vocab,
+                               allow_synthetic=path is None)
     logger.info("engine ready: %s (tensor_parallel_size=%d)", mc, tp)
     return AsyncTGISEngine(eng, tokenizer, mc)

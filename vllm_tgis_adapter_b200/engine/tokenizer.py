@@ -28,13 +28,19 @@ def build_synthetic_tokenizer(vocab_size: int):
     return fast
 
 
-def load_tokenizer(path: str | None, vocab_size: int):
+def load_tokenizer(path: str | None, vocab_size: int, *, allow_synthetic: bool = False):
+    """HF tokenizer from `path`.  The synthetic tokenizer is only handed out when the caller says the model itself is
+    synthetic (`--synthetic-weights` / a preset): a real checkpoint with a missing or mistyped tokenizer path must fail
+    at start-up like the reference does (vLLM raises from `get_tokenizer`), not serve `t{n}` words."""
     if path and Path(path).is_dir() and any((Path(path) / f).exists()
                                             for f in ("tokenizer.json", "tokenizer.model", "tokenizer_config.json")):
         from transformers import AutoTokenizer
 
         tok = AutoTokenizer.from_pretrained(path, truncation_side="left")
         return tok
+    if not allow_synthetic:
+        raise ValueError(f"no tokenizer files (tokenizer.json / tokenizer.model / tokenizer_config.json) under "
+                         f"{path!r}: pass --tokenizer <dir>, or --synthetic-weights for the synthetic vocabulary")
     return build_synthetic_tokenizer(vocab_size)
 
 
