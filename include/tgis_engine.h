@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TGIS_ABI_VERSION 3
+#define TGIS_ABI_VERSION 4
 #define TGIS_MAX_REQUEST_ID 96
 #define TGIS_MAX_TOPN 12 /* reference forces max_logprobs >= 11: tgis_utils/args.py:214-216 */
 #define TGIS_MAX_STOP_TOKEN_IDS 8
@@ -144,6 +144,9 @@ typedef struct tgis_status {
   double gemm_bytes;         /* ... and their algorithmic bytes (weights + activations in + result out) */
   int64_t gemm_calls;
   int64_t graph_launches;    /* decode steps replayed from a captured CUDA graph */
+  double exchange_ms;        /* with profiling on, tensor parallelism: summed CUDA-event time of every row-parallel
+                                exchange (fused push all-reduce + residual + RMSNorm kernel, or ncclAllReduce) */
+  int64_t exchange_calls;
 } tgis_status;
 
 const char* tgis_last_error(void);

@@ -65,8 +65,6 @@ int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, i
 const char* tgis_k_last_error(void);
 /* debug builds only (-DTGIS_GEMM_TIMELINE): %globaltimer stamps of CTA 0 and CTA grid/2, [4][16] u64; else -2 */
 int tgis_k_gemm_timeline(uint64_t* out64);
-/* chain kernel, last 6-step launch: [2 CTAs][step * 8 + event] %globaltimer stamps; else -2 */
-int tgis_k_chain_timeline(uint64_t* out128);
 int tgis_k_sizeof_sample_row(void);
 int tgis_k_sizeof_sample_out(void);
 int tgis_k_kv_block(void);

@@ -31,11 +31,9 @@ for st in $STAGES; do
     grpc_bench) timeout 600 python scripts/grpc_bench.py > gpurun_out/grpc_bench.log 2>&1; echo "grpc_bench rc=$?" ;;
     bench_tp) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $NGPU --parallel tp --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/bench_tp$NGPU.log 2> gpurun_out/bench_tp$NGPU.err; echo "bench_tp rc=$?" ;;
     bench_dp) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NGPU --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $NGPU --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/bench_dp$NGPU.log 2> gpurun_out/bench_dp$NGPU.err; echo "bench_dp rc=$?" ;;
-    ab_s5) for v in base s5; do if [ $v = s5 ]; then export TGIS_ENGINE_LIB=$PWD/vllm_tgis_adapter_b200/lib/libtgis_engine_s5.so; else unset TGIS_ENGINE_LIB; fi; timeout 300 python scripts/profile_decode.py 8 32 512 24 1 > gpurun_out/ab_decode_$v.log 2>&1; timeout 400 python bench.py --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/ab_bench_$v.log 2> gpurun_out/ab_bench_$v.err; done; unset TGIS_ENGINE_LIB; echo "ab_s5 rc=$?" ;;
     bench_batches) for b in 64 128 256; do timeout 400 python bench.py --no-cpu-baseline --steps 1 --warmup 3 --batch $b > gpurun_out/bench_b$b.log 2> gpurun_out/bench_b$b.err; done; timeout 400 python bench.py --no-cpu-baseline --steps 1 --warmup 3 --batch 64 --sampling cfg3 > gpurun_out/bench_b64_cfg3.log 2> gpurun_out/bench_b64_cfg3.err; echo "bench_batches rc=$?" ;;
     timeline) timeout 300 python scripts/gemm_timeline.py > gpurun_out/gemm_timeline.log 2>&1; echo "timeline rc=$?" ;;
     ctasweep) timeout 300 python scripts/gemm_cta_sweep.py > gpurun_out/gemm_cta_sweep.log 2>&1; echo "ctasweep rc=$?" ;;
-    chaintl) TGIS_ENGINE_LIB=$PWD/vllm_tgis_adapter_b200/lib/libtgis_engine_tl.so timeout 300 python scripts/chain_timeline.py > gpurun_out/chain_timeline.log 2>&1; echo "chaintl rc=$?" ;;
     attnbench) timeout 300 python scripts/attn_bench.py > gpurun_out/attn_bench.log 2>&1; echo "attnbench rc=$?" ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
     *) echo "unknown stage $st" ;;

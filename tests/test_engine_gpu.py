@@ -204,26 +204,6 @@ def test_prompt_logprobs_match_oracle(chunk):
 
 
 @pytest.mark.parametrize("model", ["tiny", "small"])
-def test_chain_kernel_is_bit_identical_to_unfused_path(model, monkeypatch):
-    """The per-layer chain kernel (o-proj -> norm -> gate_up/SwiGLU -> down -> norm -> qkv in one persistent launch) uses
-    the same (tile, k-block) partition and the same arithmetic as the stand-alone kernels: tokens AND logprobs of a
-    mixed prefill/decode run must be bit-identical with TGIS_CHAIN=0 and TGIS_CHAIN=1."""
-    from vllm_tgis_adapter_b200.engine.core import make_sampling_params
-
-    rng = np.random.RandomState(11)
-    prompts = [rng.randint(3, 1024, size=n).tolist() for n in (70, 5, 130, 33, 64)]
-    sp = make_sampling_params(greedy=True, max_tokens=24, min_tokens=24, num_logprobs=2)
-    runs = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("TGIS_CHAIN", flag)
-        _, _, outs, st = _run_engine(model, prompts, sp, max_num_seqs=8, max_batched_tokens=96, kv_cache_bytes=64 << 20)
-        assert st.errored == 0
-        runs.append([[(r.new_token, r.logprob, r.rank, tuple(r.topn)) for r in recs if r.new_token is not None]
-                     for recs in outs])
-    assert runs[0] == runs[1]
-
-
-@pytest.mark.parametrize("model", ["tiny", "small"])
 def test_fused_rope_epilogue_is_bit_identical(model, monkeypatch):
     """Decode-shaped steps apply RoPE and scatter K/V into the paged cache inside the qkv GEMM's cluster epilogue
     (gemm_tcgen05.cu) instead of running rope_kvwrite_kernel; same arithmetic and rounding points, so tokens AND logprobs

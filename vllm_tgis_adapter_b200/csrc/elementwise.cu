@@ -151,11 +151,15 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
 }
 
 __global__ void __launch_bounds__(NORM_THREADS)
-ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, uint32_t epoch, __nv_bfloat16* __restrict__ residual,
-                      const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int hidden, float eps) {
+ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, const uint32_t* __restrict__ epoch_base, uint32_t epoch_idx,
+                      __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ w,
+                      __nv_bfloat16* __restrict__ out, int hidden, float eps) {
   __shared__ float red[NORM_THREADS / 32];
   griddep_launch();
-  griddep_wait();  // this rank's partial (previous kernel) is complete
+  griddep_wait();  // this rank's partial (previous kernel) is complete; the step's metadata copy has landed
+  // The exchange epoch = (value staged by the host for this step) + (index of the exchange inside the step): the
+  // launch arguments are the same for every replay of a captured step, so tensor-parallel decode steps can be CUDA graphs.
+  const uint32_t epoch = __ldg(epoch_base) + epoch_idx;
   const int row = blockIdx.x;
   const size_t base = (size_t)row * hidden;
   const int nvec = hidden / 8;
@@ -241,14 +245,14 @@ ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, uint32_t epoch, __nv_bfloat16
   }
 }
 
-cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, uint32_t epoch, __nv_bfloat16* residual,
-                                  const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden, float eps,
-                                  cudaStream_t stream) {
+cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, const uint32_t* epoch_base, uint32_t epoch_idx,
+                                  __nv_bfloat16* residual, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
+                                  float eps, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   if (tp < 2 || tp > 8 || T > AR_MAX_ROWS || hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC)
     return cudaErrorInvalidValue;
-  return launch_k(ar_add_rmsnorm_kernel, dim3(T), dim3(NORM_THREADS), 0, stream, peers, tp, rank, epoch, residual, w, out,
-                  hidden, eps);
+  return launch_k(ar_add_rmsnorm_kernel, dim3(T), dim3(NORM_THREADS), 0, stream, peers, tp, rank, epoch_base, epoch_idx,
+                  residual, w, out, hidden, eps);
 }
 
 // ------------------------------------------------------------------------------------------------ SiLU * mul

@@ -27,6 +27,8 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <errno.h>
+#include <signal.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <nccl.h>
@@ -146,6 +148,7 @@ struct LayerW {
 // kernel sequence on their shard.  (The data path itself only exchanges through NCCL.)
 struct StepHeader {
   int32_t T, n_dec, n_tiles, R, max_dec_kv, S;
+  int32_t graphable, pad;  // graphable: replay (or capture) the CUDA graph keyed by (S, KV splits) instead of launching
   uint64_t copy_bytes;
 };
 struct ShmCtl {
@@ -153,9 +156,12 @@ struct ShmCtl {
   std::atomic<uint32_t> shutdown;
   uint32_t pad;
   std::atomic<uint64_t> ack[16];
+  std::atomic<int32_t> pid[16];      // liveness: every rank publishes its process id
+  std::atomic<int32_t> failed[16];   // a worker that hit an error says so before it leaves
   StepHeader hdr;
   // followed by stage bytes (256-B aligned)
 };
+static_assert(sizeof(ShmCtl) <= 1024, "ShmCtl must fit below SHM_STAGE_OFF");
 constexpr size_t SHM_STAGE_OFF = 1024;
 
 // gathered: [tp][R][Vl] -> out: [R][tp*Vl], elements of `esz` bytes moved as 16-byte vectors (Vl * esz % 16 == 0)
@@ -197,6 +203,7 @@ struct tgis_engine {
   bool shm_owner = false;
   std::string shm_name;
   uint64_t plan_seq = 0;
+  double tp_timeout_s = 120.0;  // TGIS_TP_TIMEOUT_S: a worker that takes no plan for this long is declared hung
   DevBuf<uint8_t> logits_shard, logits_gather;  // [R, V/tp] and [tp][R, V/tp] in the logits dtype
   int T_max = 0, S_max = 0, tiles_max = 0;
 
@@ -212,7 +219,7 @@ struct tgis_engine {
   int num_blocks = 0;
   std::vector<int32_t> free_blocks;
   // activations
-  DevBuf<bf16> resid, xn, qkv, attn_out, tmp, gate_up, act, last_hidden;
+  DevBuf<bf16> resid, xn, qkv, attn_out, tmp, act, last_hidden;
   // lm_head output [rows, V].  bf16 = the model dtype, rounded once from the fp32 accumulator exactly where vLLM's
   // lm_head rounds (vllm model_executor/layers/logits_processor.py:89-104 -> F.linear in bf16; the sampler then casts to
   // fp32, v1/sample/sampler.py:91): exact ties between bf16 logits, and the ranks / lowest-id argmax they cause, are
@@ -231,7 +238,7 @@ struct tgis_engine {
   uint8_t* h_stage = nullptr;
   DevBuf<uint8_t> d_stage;
   size_t off_tok = 0, off_pos = 0, off_slotmap = 0, off_tokslot = 0, off_seqs = 0, off_decids = 0, off_tileseq = 0,
-         off_tileq0 = 0, off_samplesrc = 0, off_rows = 0, off_bt = 0, stage_bytes = 0;
+         off_tileq0 = 0, off_samplesrc = 0, off_rows = 0, off_epoch = 0, off_bt = 0, stage_bytes = 0;
 
   // host state
   std::mutex mu;
@@ -249,32 +256,49 @@ struct tgis_engine {
   std::mt19937_64 rng;
   // stats
   std::atomic<long long> n_steps{0}, n_tokens{0}, n_launches{0};
+  // scheduler-state snapshot for tgis_engine_status (the queues themselves belong to the engine thread)
+  std::atomic<int> snap_running{0}, snap_waiting{0}, snap_free_blocks{0};
+  void snapshot() {
+    snap_running = (int)running.size();
+    snap_waiting = (int)waiting.size();
+    snap_free_blocks = (int)free_blocks.size();
+  }
   double gpu_ms = 0, gpu_ms_decode = 0, gpu_ms_mixed = 0;
   long long decode_steps = 0, decode_tokens = 0, h2d_bytes = 0, d2h_bytes = 0;
   // optional per-GEMM timing (tgis_engine_set_profiling): CUDA events around every GEMM launch of a step
   bool profiling = false;
   bool prof_decode_only = false, step_is_decode = false;
-  // EXPERIMENT (default off, TGIS_CHAIN=1): one persistent chain kernel per layer for decode-shaped steps.  Measured
-  // slower than PDL-chained stand-alone kernels: in-kernel grid-wide step barriers cost 12-15 us each
-  // under full HBM load vs ~9 us per kernel boundary.  Kept because it is bit-identical and documents the experiment.
-  bool use_chain = false;
-  DevBuf<int> chain_sync;
   bool fuse_rope = true;
   int rope_fuse_max_t = 32;
   // tensor parallelism, decode-shaped steps: one-shot all-reduce + residual + RMSNorm over NVLink peer memory
   // (ar_add_rmsnorm_kernel) instead of ncclAllReduce + rmsnorm kernel.  TGIS_TP_FUSED_AR=0: NCCL baseline.
   bool tp_fused_ar = true;
+  bool tp_graphs = true;  // TGIS_TP_GRAPHS=0: tensor-parallel decode steps are launched kernel by kernel (round 1)
   static constexpr int AR_MAX_T = AR_MAX_ROWS;
   uint8_t* ar_mem = nullptr;        // [2 parities] receive areas (ar_recv_bytes each), then the two local partial buffers
   uint8_t* ar_peer[8] = {};         // the same allocation of every rank, mapped here (cudaIpc)
-  uint32_t ar_epoch[2] = {0, 0};
-  int chain_pf_depth = 16;  // TGIS_CHAIN_PF
+  uint32_t ar_epoch[2] = {0, 0};     // rank 0: epoch of the last exchange of each parity (staged per step: off_epoch)
+  uint32_t step_ar_idx[2] = {0, 0};  // exchanges of each parity enqueued so far in the step being built
   int l2_prefetch_kb = 0;   // (off: measured no gain, costs DRAM traffic in the issuing kernel) k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
-  std::vector<double> prof_bytes;  // algorithmic bytes of the GEMM between events 2i and 2i+1
-  double gemm_ms = 0, gemm_bytes = 0;
-  long long gemm_calls = 0;
+  std::vector<double> prof_bytes;  // algorithmic bytes of the GEMM between events 2i and 2i+1 (< 0: an exchange)
+  double gemm_ms = 0, gemm_bytes = 0, exchange_ms = 0;
+  long long gemm_calls = 0, exchange_calls = 0;
+  // event pair around an exchange (profiling only)
+  cudaEvent_t prof_begin_exchange() {
+    if (!(profiling && (!prof_decode_only || step_is_decode))) return nullptr;
+    while (prof_events.size() < prof_used + 2) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      prof_events.push_back(ev);
+    }
+    cudaEvent_t e1 = prof_events[prof_used + 1];
+    CK(cudaEventRecord(prof_events[prof_used], stream));
+    prof_used += 2;
+    prof_bytes.push_back(-1.0);
+    return e1;
+  }
   // CUDA graphs of pure-decode steps, keyed by (batch size, number of KV splits)
   std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
   std::unordered_map<uint64_t, long long> graph_nodes;
@@ -330,15 +354,13 @@ struct tgis_engine {
     tiles_max = T_max / 16 + S_max + 1;
     rng.seed(c.seed ? c.seed : 0x5DEECE66Dull);
     if (const char* e = getenv("TGIS_L2_PREFETCH_KB")) l2_prefetch_kb = atoi(e);
-    if (const char* e = getenv("TGIS_CHAIN")) use_chain = atoi(e) != 0;
-    if (const char* e = getenv("TGIS_CHAIN_PF")) chain_pf_depth = atoi(e);
     if (const char* e = getenv("TGIS_FUSE_ROPE")) fuse_rope = atoi(e) != 0;
     if (const char* e = getenv("TGIS_FUSE_ROPE_MAX_T")) rope_fuse_max_t = atoi(e);
     if (const char* e = getenv("TGIS_TP_FUSED_AR")) tp_fused_ar = atoi(e) != 0;
     if (const char* e = getenv("TGIS_LOGITS_FP32")) logits_bf16 = atoi(e) == 0;
+    if (const char* e = getenv("TGIS_TP_TIMEOUT_S")) tp_timeout_s = atof(e);
+    if (const char* e = getenv("TGIS_TP_GRAPHS")) tp_graphs = atoi(e) != 0;
     lsz = logits_bf16 ? 2 : 4;
-    chain_sync.alloc(CHAIN_MAX_STEPS + 1);
-    chain_sync.zero();
 
     // ---- weights: one arena
     const size_t H = c.hidden, F = Fl, V = c.vocab, L = c.n_layers;  // F: this rank's ffn shard
@@ -373,7 +395,6 @@ struct tgis_engine {
     qkv.alloc(T_alloc * qkv_dim);
     attn_out.alloc(T_alloc * q_dim);
     tmp.alloc(T_alloc * H);
-    gate_up.alloc(64);  // unused since SwiGLU moved into the gate_up GEMM epilogue
     act.alloc(T_alloc * F);
     last_hidden.alloc(S_alloc * H);
     logits.alloc((size_t)S_max * V * lsz);
@@ -412,6 +433,7 @@ struct tgis_engine {
     off_tileq0 = place(4 * (size_t)tiles_max);
     off_samplesrc = place(4 * (size_t)S_max);
     off_rows = place(sizeof(SampleRow) * (size_t)S_max);
+    off_epoch = place(2 * sizeof(uint32_t));  // tensor parallelism: exchange epochs before this step, per parity
     off_bt = place(4 * (size_t)S_max * bt_stride);
     // decode work items follow the USED part of the block table (items_off(S)); room for the worst case
     place(sizeof(DecItem) * (1 + (size_t)S_max * max_splits_cap));
@@ -468,6 +490,7 @@ struct tgis_engine {
     for (int i = 0; i < num_blocks; ++i) free_blocks[i] = num_blocks - 1 - i;
     free_slots.resize(S_max);
     for (int i = 0; i < S_max; ++i) free_slots[i] = S_max - 1 - i;
+    snapshot();
     CK(cudaStreamSynchronize(stream));
     CK(cudaDeviceSynchronize());
     if (tp > 1) init_tp();
@@ -506,6 +529,9 @@ struct tgis_engine {
       shm->seq.store(0);
       shm->shutdown.store(0);
       for (auto& a : shm->ack) a.store(0);
+      for (auto& a : shm->pid) a.store(0);
+      for (auto& a : shm->failed) a.store(0);
+      shm->pid[0].store((int32_t)getpid(), std::memory_order_release);
     }
     // first collective doubles as a start-up barrier (and creates NCCL's channels outside the timed path)
     NK(nccl().AllReduce(tmp.p, tmp.p, 1024, ncclBfloat16, ncclSum, comm, stream));
@@ -563,36 +589,72 @@ struct tgis_engine {
     memset(&P, 0, sizeof(P));
     P.own = ar_buf(parity);
     for (int r = 0; r < tp; ++r) P.recv[r] = reinterpret_cast<uint4*>(ar_peer[r] + parity * ar_recv_bytes(cfg.hidden));
-    CK(ar_add_rmsnorm_launch(P, tp, rank, ++ar_epoch[parity], resid.p, w, xn.p, T, cfg.hidden, cfg.rms_eps, stream));
+    cudaEvent_t pe = prof_begin_exchange();
+    CK(ar_add_rmsnorm_launch(P, tp, rank, ds<uint32_t>(off_epoch) + parity, ++step_ar_idx[parity], resid.p, w, xn.p, T,
+                             cfg.hidden, cfg.rms_eps, stream));
+    if (pe) CK(cudaEventRecord(pe, stream));
     ++n_launches;
   }
 
-  void publish_plan(const StepHeader& h) {  // rank 0
-    for (int r = 1; r < tp; ++r)
+  static bool pid_alive(int pid) { return pid > 0 && (kill(pid, 0) == 0 || errno == EPERM); }
+
+  // rank 0: wait until every worker has taken the previous plan, then publish this one.  The wait is a spin (the
+  // common case is microseconds) with a liveness check: a worker that died or reported a failure turns into an
+  // exception here -> fail_all -> errored, instead of rank 0 spinning forever behind a healthy-looking /health.
+  void publish_plan(const StepHeader& h) {
+    for (int r = 1; r < tp; ++r) {
+      double t_check = 0;
+      const double t_start = now_s();
       while (shm->ack[r].load(std::memory_order_acquire) != plan_seq) {
         if (stop_flag) return;
+        const double t = now_s();
+        if (t - t_start > 0.002 && t - t_check > 0.05) {
+          t_check = t;
+          if (shm->failed[r].load(std::memory_order_acquire))
+            throw CudaError("tensor-parallel worker rank " + std::to_string(r) + " reported a failure");
+          const int pid = shm->pid[r].load(std::memory_order_acquire);
+          if (pid > 0 && !pid_alive(pid))
+            throw CudaError("tensor-parallel worker rank " + std::to_string(r) + " (pid " + std::to_string(pid) + ") died");
+          if (t - t_start > tp_timeout_s)
+            throw CudaError("tensor-parallel worker rank " + std::to_string(r) + " did not take a step plan for " +
+                            std::to_string((int)tp_timeout_s) + " s");
+        }
       }
+    }
     memcpy(reinterpret_cast<uint8_t*>(shm) + SHM_STAGE_OFF, h_stage, h.copy_bytes);
     shm->hdr = h;
     shm->seq.store(++plan_seq, std::memory_order_release);
   }
 
-  // worker ranks: follow rank 0's step plans until shutdown
+  // worker ranks: follow rank 0's step plans until shutdown (or until rank 0 disappears)
   int worker_loop() {
     CK(cudaSetDevice(cfg.device));
+    shm->pid[rank].store((int32_t)getpid(), std::memory_order_release);
     uint64_t seen = 0;
-    for (;;) {
-      uint64_t s;
-      while ((s = shm->seq.load(std::memory_order_acquire)) == seen) {
-        if (shm->shutdown.load(std::memory_order_acquire)) return 0;
+    try {
+      for (;;) {
+        uint64_t s;
+        double t_check = now_s();
+        while ((s = shm->seq.load(std::memory_order_acquire)) == seen) {
+          if (shm->shutdown.load(std::memory_order_acquire)) return 0;
+          const double t = now_s();
+          if (t - t_check > 0.5) {
+            t_check = t;
+            const int pid0 = shm->pid[0].load(std::memory_order_acquire);
+            if (pid0 > 0 && !pid_alive(pid0)) return fail("rank 0 (pid " + std::to_string(pid0) + ") is gone", -2);
+          }
+        }
+        const StepHeader h = shm->hdr;
+        memcpy(h_stage, reinterpret_cast<uint8_t*>(shm) + SHM_STAGE_OFF, h.copy_bytes);
+        seen = s;
+        shm->ack[rank].store(s, std::memory_order_release);
+        exec_step(h);
+        CK(cudaStreamSynchronize(stream));
+        ++n_steps;
       }
-      const StepHeader h = shm->hdr;
-      memcpy(h_stage, reinterpret_cast<uint8_t*>(shm) + SHM_STAGE_OFF, h.copy_bytes);
-      seen = s;
-      shm->ack[rank].store(s, std::memory_order_release);
-      launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S);
-      CK(cudaStreamSynchronize(stream));
-      ++n_steps;
+    } catch (...) {
+      shm->failed[rank].store(1, std::memory_order_release);
+      throw;
     }
   }
 
@@ -710,52 +772,17 @@ struct tgis_engine {
     ++n_launches;
   }
 
-  // One chain launch (gemm_tcgen05.cu): o-proj -> add+norm -> gate_up/SwiGLU -> down [-> add+norm -> next qkv], or the
-  // stack's head (norm -> qkv of layer 0).  Profiling: timed as one launch, bytes = the steps' weight + activation bytes.
-  ChainParams chain_begin(int T) {
-    ChainParams P;
-    memset(&P, 0, sizeof(P));
-    P.T = T;
-    P.hidden = cfg.hidden;
-    P.eps = cfg.rms_eps;
-    P.ws = gemm_ws.p;
-    P.counters = gemm_counters.p;
-    P.sync = chain_sync.p;
-    P.pf_depth = chain_pf_depth;
-    return P;
-  }
-  void chain_run(const ChainParams& P) {
-    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (profiling && (!prof_decode_only || step_is_decode)) {
-      while (prof_events.size() < prof_used + 2) {
-        cudaEvent_t ev;
-        CK(cudaEventCreate(&ev));
-        prof_events.push_back(ev);
-      }
-      pe0 = prof_events[prof_used];
-      pe1 = prof_events[prof_used + 1];
-      prof_used += 2;
-      double by = 0;
-      for (int i = 0; i < P.n_steps; ++i) {
-        const ChainStep& st = P.step[i];
-        if (st.kind == 0) by += (double)st.N * st.K * 2 + (double)P.T * st.K * 2 + (double)P.T * st.N * (st.mode == 2 ? 1 : 2);
-        else by += (double)P.T * P.hidden * 2 * (st.x ? 4 : 2);
-      }
-      prof_bytes.push_back(by);
-      CK(cudaEventRecord(pe0, stream));
-    }
-    CK(chain_launch(P, num_sms, stream));
-    if (pe1) CK(cudaEventRecord(pe1, stream));
-    ++n_launches;
-  }
-
   template <class T>
   T* hs(size_t off) { return reinterpret_cast<T*>(h_stage + off); }
   template <class T>
   T* ds(size_t off) { return reinterpret_cast<T*>(d_stage.p + off); }
 
   void all_reduce_tmp(int T) {
-    if (tp > 1) NK(nccl().AllReduce(tmp.p, tmp.p, (size_t)T * cfg.hidden, ncclBfloat16, ncclSum, comm, stream));
+    if (tp > 1) {
+      cudaEvent_t pe = prof_begin_exchange();
+      NK(nccl().AllReduce(tmp.p, tmp.p, (size_t)T * cfg.hidden, ncclBfloat16, ncclSum, comm, stream));
+      if (pe) CK(cudaEventRecord(pe, stream));
+    }
   }
 
   // Enqueue one step on `stream`: H2D metadata, layer stack, lm_head + sampler, D2H results.  Reads every per-step
@@ -767,6 +794,7 @@ struct tgis_engine {
     const int H = c.hidden, F = Fl, V = c.vocab;  // F: local ffn shard
     CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
     step_is_decode = (n_tiles == 0);
+    step_ar_idx[0] = step_ar_idx[1] = 0;
 
     const int32_t* d_tok = ds<int32_t>(off_tok);
     const AttnSeq* d_seqs = ds<AttnSeq>(off_seqs);
@@ -779,25 +807,16 @@ struct tgis_engine {
     }
     CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
     ++n_launches;
-    const bool chained = use_chain && tp == 1 && T <= 256 && !cfg.debug_gemm_ref;
     const bool ar_fused = tp > 1 && tp_fused_ar && T <= AR_MAX_T;
     // RoPE + KV-cache scatter fused into the qkv GEMM's split-tile reduction (decode-shaped steps where every weight
     // tile is split over several CTAs; TGIS_FUSE_ROPE=0: off)
     // (measured: -2 % per step at 32 tokens, but +2...5 % at 64...256 -- the last-arriving CTA's serial tail grows with
     // T while the stand-alone kernel spreads over all SMs -- hence the token limit)
-    const bool rope_fused = fuse_rope && !chained && !cfg.debug_gemm_ref && T <= rope_fuse_max_t &&
+    const bool rope_fused = fuse_rope && !cfg.debug_gemm_ref && T <= rope_fuse_max_t &&
                             gemm_even_split(T, qkv_dim, H, num_sms) >= 2;
-    const int bi = bt_index(T);
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];
-      if (chained) {
-        if (li == 0) {  // head of the stack: norm -> qkv (later layers get theirs from the previous layer's chain)
-          ChainParams P = chain_begin(T);
-          chain_add_norm(P, nullptr, resid.p, l.ln1, xn.p);
-          chain_add_gemm(P, l.m_qkv, xm_xn[bi], qkv.p, qkv_dim, qkv_dim, H, 0, num_sms);
-          chain_run(P);
-        }
-      } else {
+      {
         if (li == 0) {
           CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
           ++n_launches;
@@ -829,19 +848,6 @@ struct tgis_engine {
         CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
                                n_tiles, d_bt, bt_stride, attn_out.p, q_dim, nq, nkv, scale, stream));
         ++n_launches;
-      }
-      if (chained) {
-        ChainParams P = chain_begin(T);
-        chain_add_gemm(P, l.m_o, xm_attn[bi], tmp.p, H, H, q_dim, 0, num_sms);
-        chain_add_norm(P, tmp.p, resid.p, l.ln2, xn.p);
-        chain_add_gemm(P, l.m_gu, xm_xn[bi], act.p, F, 2 * F, H, /*mode=*/2, num_sms);
-        chain_add_gemm(P, l.m_d, xm_act[bi], tmp.p, H, H, F, 0, num_sms);
-        if (li + 1 < c.n_layers) {
-          chain_add_norm(P, tmp.p, resid.p, layers[li + 1].ln1, xn.p);
-          chain_add_gemm(P, layers[li + 1].m_qkv, xm_xn[bi], qkv.p, qkv_dim, qkv_dim, H, 0, num_sms);
-        }
-        chain_run(P);
-        continue;
       }
       gemm(xm_attn, l.m_o, attn_out.p, l.wo, ar_fused ? ar_buf(0) : tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H);
       if (ar_fused) {
@@ -889,6 +895,46 @@ struct tgis_engine {
         CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
       }
     }
+  }
+
+  // Enqueue the step described by `h` (metadata already in h_stage): a CUDA-graph replay for pure-decode steps -- one
+  // graph per (batch size, KV splits), captured on first use; every per-step quantity is read from the staged device
+  // buffer, so the captured launch sequence is step-independent -- or the plain launch sequence otherwise.  Rank 0
+  // and the tensor-parallel workers run the same function on the same header.
+  void exec_step(const StepHeader& h) {
+    if (!h.graphable) {
+      launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S);
+      return;
+    }
+    const int max_splits = (h.max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+    const uint64_t key = ((uint64_t)h.S << 16) | (uint64_t)max_splits;
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      if (graphs.size() >= 64) {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+      }
+      const long long launches_before = n_launches;
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S);
+      } catch (...) {
+        cudaStreamEndCapture(stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CK(cudaStreamEndCapture(stream, &g));
+      cudaGraphExec_t ge = nullptr;
+      CK(cudaGraphInstantiate(&ge, g, 0));
+      CK(cudaGraphDestroy(g));
+      graph_nodes[key] = n_launches - launches_before;
+      n_launches = launches_before;
+      it = graphs.emplace(key, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second, stream));
+    n_launches += graph_nodes[key];
+    ++n_graph_launches;
   }
 
   // returns number of sampled rows
@@ -986,41 +1032,20 @@ struct tgis_engine {
     decode_items_build(hs<DecItem>(items_off(S)), seqs, decids, n_dec, bt, bt_stride);
     const size_t copy_bytes = items_off(S) + sizeof(DecItem) * (1 + (size_t)n_dec * max_splits_step);
     CK(cudaEventRecord(ev0, stream));
-    if (tp > 1) publish_plan(StepHeader{T, n_dec, n_tiles, R, max_dec_kv, S, (uint64_t)copy_bytes});
-    const bool graphable = cfg.use_cuda_graphs && tp == 1 && !profiling && n_tiles == 0 && n_dec == S && R == S;
-    if (graphable) {
-      const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
-      const uint64_t key = ((uint64_t)S << 16) | (uint64_t)max_splits;
-      auto it = graphs.find(key);
-      if (it == graphs.end()) {
-        if (graphs.size() >= 64) {
-          for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-          graphs.clear();
-        }
-        const long long launches_before = n_launches;
-        cudaGraph_t g = nullptr;
-        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        try {
-          launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv, S);
-        } catch (...) {
-          cudaStreamEndCapture(stream, &g);
-          if (g) cudaGraphDestroy(g);
-          throw;
-        }
-        CK(cudaStreamEndCapture(stream, &g));
-        cudaGraphExec_t ge = nullptr;
-        CK(cudaGraphInstantiate(&ge, g, 0));
-        CK(cudaGraphDestroy(g));
-        graph_nodes[key] = n_launches - launches_before;
-        n_launches = launches_before;
-        it = graphs.emplace(key, ge).first;
+    const bool graphable = cfg.use_cuda_graphs && (tp == 1 || tp_graphs) && !profiling && n_tiles == 0 && n_dec == S && R == S;
+    StepHeader hdr{T, n_dec, n_tiles, R, max_dec_kv, S, graphable ? 1 : 0, 0, (uint64_t)copy_bytes};
+    if (tp > 1) {
+      // exchange epochs of this step = staged base + index inside the step (ar_add_rmsnorm_kernel)
+      uint32_t* eb = hs<uint32_t>(off_epoch);
+      eb[0] = ar_epoch[0];
+      eb[1] = ar_epoch[1];
+      if (tp_fused_ar && T <= AR_MAX_T) {
+        ar_epoch[0] += (uint32_t)cfg.n_layers;
+        ar_epoch[1] += (uint32_t)cfg.n_layers;
       }
-      CK(cudaGraphLaunch(it->second, stream));
-      n_launches += graph_nodes[key];
-      ++n_graph_launches;
-    } else {
-      launch_step(copy_bytes, T, n_dec, n_tiles, R, max_dec_kv, S);
+      publish_plan(hdr);
     }
+    exec_step(hdr);
     CK(cudaEventRecord(ev1, stream));
     CK(cudaStreamSynchronize(stream));
     float ms = 0.f;
@@ -1039,9 +1064,14 @@ struct tgis_engine {
       for (size_t i = 0; i + 1 < prof_used; i += 2) {
         float gm = 0.f;
         CK(cudaEventElapsedTime(&gm, prof_events[i], prof_events[i + 1]));
-        gemm_ms += gm;
-        gemm_bytes += prof_bytes[i / 2];
-        ++gemm_calls;
+        if (prof_bytes[i / 2] < 0) {
+          exchange_ms += gm;
+          ++exchange_calls;
+        } else {
+          gemm_ms += gm;
+          gemm_bytes += prof_bytes[i / 2];
+          ++gemm_calls;
+        }
       }
       prof_used = 0;
       prof_bytes.clear();
@@ -1180,7 +1210,10 @@ struct tgis_engine {
         waiting.erase(waiting.begin() + i);
       } else ++i;
     }
-    if (running.empty() && waiting.empty()) return false;
+    if (running.empty() && waiting.empty()) {
+      snapshot();
+      return false;
+    }
 
     // ---- schedule
     std::vector<Sched> dec, pre;
@@ -1237,6 +1270,7 @@ struct tgis_engine {
     if (batch.empty()) {
       if (!waiting.empty() && running.empty())
         throw CudaError("request does not fit in the KV cache (" + std::to_string(num_blocks) + " blocks)");
+      snapshot();
       return false;
     }
 
@@ -1286,6 +1320,7 @@ struct tgis_engine {
           break;
         }
     }
+    snapshot();
     return true;
   }
 
@@ -1303,6 +1338,7 @@ struct tgis_engine {
     for (auto& r : running) all.push_back(std::move(r));
     running.clear();
     for (auto& r : all) emit(*r, false, nullptr, TGIS_FINISH_ERROR, -1);
+    snapshot();
   }
 
   void loop() {
@@ -1472,9 +1508,9 @@ int tgis_engine_status(tgis_engine* e, tgis_status* out) {
   std::lock_guard<std::mutex> lk(e->mu);
   out->errored = e->errored ? 1 : 0;
   out->is_running = (e->thread_alive || (e->started && !e->th.joinable() && !e->errored)) ? 1 : 0;
-  out->n_running = (int)e->running.size();
-  out->n_waiting = (int)(e->waiting.size() + e->incoming.size());
-  out->free_blocks = (int)e->free_blocks.size();
+  out->n_running = e->snap_running;
+  out->n_waiting = e->snap_waiting + (int)e->incoming.size();
+  out->free_blocks = e->snap_free_blocks;
   out->total_blocks = e->num_blocks;
   out->steps = e->n_steps;
   out->tokens_generated = e->n_tokens;
@@ -1490,6 +1526,8 @@ int tgis_engine_status(tgis_engine* e, tgis_status* out) {
   out->gemm_bytes = e->gemm_bytes;
   out->gemm_calls = e->gemm_calls;
   out->graph_launches = e->n_graph_launches;
+  out->exchange_ms = e->exchange_ms;
+  out->exchange_calls = e->exchange_calls;
   if (e->errored) g_last_error = e->error_msg;
   return 0;
 }

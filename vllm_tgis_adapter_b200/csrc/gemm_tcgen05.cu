@@ -124,7 +124,6 @@ __device__ __forceinline__ int unit_owner(long long p, long long total, int ncta
 
 #ifdef TGIS_GEMM_TIMELINE
 __device__ unsigned long long g_gemm_timeline[4][16];
-__device__ unsigned long long g_chain_timeline[2][64];  // [cta 0 | cta grid/2][step * 8 + event], 6-step launches only
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -135,14 +134,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && (slot) < 16)                    \
       g_gemm_timeline[blockIdx.x == 0 ? 0 : 1][slot] = gtimer();                            \
   } while (0)
-#define TLC(step, ev)                                                                                       \
-  do {                                                                                                      \
-    if (P.n_steps == 6 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))                                 \
-      g_chain_timeline[blockIdx.x == 0 ? 0 : 1][(step) * 8 + (ev)] = gtimer();                              \
-  } while (0)
 #else
 #define TL(slot) do {} while (0)
-#define TLC(step, ev) do {} while (0)
 #endif
 
 // SwiGLU on one (gate, up) accumulator pair with the rounding points of the unfused path
@@ -624,474 +617,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   }
 }
 
-// ================================================================================================================
-// Chain kernel: ONE persistent launch runs a dependent sequence of decode-shaped linear layers and the row-wise
-// residual-add + RMSNorm steps between them (o-proj -> norm -> gate_up+SwiGLU -> down -> norm -> next qkv).
-//
-// Why: at 32 tokens a layer's GEMMs are 5-36 us of pure weight streaming each, and every kernel boundary costs ~9 us
-// of HBM idle time (drain, split-K fix-up, launch, first TMA round trip).  Weights have no data dependency, only the
-// tiny activation operand does.  So inside one kernel the TMA producer keeps streaming the NEXT step's weight tiles
-// into the smem ring while the previous step's tiles are being reduced / normalised, and only the activation loads
-// wait (acquire-poll of a per-step completion counter in global memory).  Every step uses the same (tile, k-block)
-// partition as its stand-alone launch (ChainStep::ncta = gemm_grid_size), so the results are bit-identical to the
-// unfused path.  Requires all CTAs co-resident (grid <= #SMs, 1 CTA/SM); every spin is time-bounded and traps.
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
-__device__ __forceinline__ void spin_until_ge(const int* p, int target) {
-  const long long t0 = clock64();
-  while (ld_acquire_gpu(p) < target) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("chain: step counter timeout block %d thread %d (%d < %d)\n", blockIdx.x, threadIdx.x, ld_acquire_gpu(p),
-             target);
-      __trap();
-    }
-  }
-}
-
-struct KbCursor {  // this CTA's position in the concatenated k-block sequence of all GEMM steps
-  int s, tile, kb, left, KB;
-};
-
-template <int BT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-chain_tcgen05_kernel(const __grid_constant__ ChainParams P) {
-  using Cfg = GemmCfg<BT>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_w = smem;
-  uint8_t* smem_x = smem + STAGES * Cfg::W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  int* flag_smem = reinterpret_cast<int*>(tmem_base_smem + 1);
-  float* red_smem = reinterpret_cast<float*>(tmem_base_smem + 2);  // [4]
-
-  const int warp = threadIdx.x >> 5;
-  const int cta = blockIdx.x;
-  const int T = P.T;
-  if (warp == 1) {
-    if (elect_one()) {
-      for (int i = 0; i < STAGES; ++i) {
-        mbar_init(&full_bar[i], 1);
-        mbar_init(&empty_bar[i], 1);
-      }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&tmem_full[i], 1);
-        mbar_init(&tmem_empty[i], 4);
-      }
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_base_smem);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
-  griddep_launch();
-
-  if (warp == 0) {
-    // ===================== TMA producer: weights run ahead, activations are gated on the previous step =============
-    if (elect_one()) {
-      const uint64_t pol_w = policy_evict_first();
-      const uint64_t pol_x = policy_evict_last();
-      auto seek = [&](KbCursor& c, int s_from) {
-        for (int s = s_from; s < P.n_steps; ++s) {
-          const ChainStep& st = P.step[s];
-          if (st.kind != 0 || cta >= st.ncta) continue;
-          const int KB = (st.K + GEMM_BK - 1) / GEMM_BK;
-          const long long total = (long long)((st.N + GEMM_BN - 1) / GEMM_BN) * KB;
-          const long long begin = (total * cta) / st.ncta, end = (total * (cta + 1)) / st.ncta;
-          if (end > begin) {
-            c.s = s;
-            c.KB = KB;
-            c.tile = (int)(begin / KB);
-            c.kb = (int)(begin % KB);
-            c.left = (int)(end - begin);
-            return;
-          }
-        }
-        c.s = P.n_steps;
-        c.left = 0;
-      };
-      auto advance = [&](KbCursor& c) {
-        if (--c.left == 0) {
-          seek(c, c.s + 1);
-          return;
-        }
-        if (++c.kb == c.KB) {
-          c.kb = 0;
-          ++c.tile;
-        }
-      };
-      KbCursor wc, xc, pc;  // weight loads, activation loads, L2 prefetch of weights further ahead
-      seek(wc, 0);
-      xc = wc;
-      pc = wc;
-      int pf_issued = 0;
-      int w_issued = 0, x_issued = 0, w_stage = 0, x_stage = 0;
-      uint32_t w_round = 0;     // ring round of the next weight tile
-      int gate_open = -1;       // highest step whose activation input is known complete
-      int w_seen = -1, x_seen = -1;
-      bool dep_waited = false;
-      long long t_idle = 0;
-      while (xc.s < P.n_steps) {
-        bool progress = false;
-        // L2 prefetch: while activation gates keep the smem ring full and idle, HBM keeps streaming the next
-        // pf_depth weight tiles of this CTA into the 126 MB L2 (no smem, no completion tracking)
-        if (pc.s < P.n_steps && pf_issued < w_issued + P.pf_depth) {
-          if (pf_issued >= w_issued) tma_prefetch_2d(&P.step[pc.s].wmap, pc.kb * GEMM_BK, pc.tile * GEMM_BN);
-          advance(pc);
-          ++pf_issued;
-          progress = true;
-        }
-        if (wc.s < P.n_steps && w_issued < x_issued + STAGES &&
-            (w_round == 0 || mbar_try_wait(&empty_bar[w_stage], (w_round - 1) & 1))) {
-          mbar_arrive_expect_tx(&full_bar[w_stage], Cfg::STAGE_BYTES);
-          tma_load_2d_hint(&P.step[wc.s].wmap, &full_bar[w_stage], smem_w + w_stage * Cfg::W_BYTES, wc.kb * GEMM_BK,
-                           wc.tile * GEMM_BN, pol_w);
-          if (wc.s != w_seen) { w_seen = wc.s; TLC(wc.s, 0); }  // first weight tile of the step requested
-          if (wc.left == 1) TLC(wc.s, 7);                        // last weight tile of the step requested
-          advance(wc);
-          ++w_issued;
-          if (++w_stage == STAGES) {
-            w_stage = 0;
-            ++w_round;
-          }
-          progress = true;
-        }
-        if (x_issued < w_issued) {
-          if (!dep_waited) {
-            griddep_wait();  // outputs of the preceding kernels (first activation operand, sync counters' reset)
-            dep_waited = true;
-          }
-          bool open = xc.s <= gate_open || xc.s == 0;
-          if (!open && ld_acquire_gpu(P.sync + xc.s - 1) >= P.step[xc.s - 1].done_target) {
-            fence_proxy_async_all();  // generic-proxy stores of other SMs -> our async-proxy (TMA) loads
-            open = true;
-          }
-          if (open) {
-            gate_open = xc.s;
-            if (xc.s != x_seen) { x_seen = xc.s; TLC(xc.s, 1); }  // gate open: first activation tile requested
-            if (xc.left == 1) TLC(xc.s, 2);                        // last activation tile requested
-            tma_load_2d_hint(&P.step[xc.s].xmap, &full_bar[x_stage], smem_x + x_stage * Cfg::X_BYTES, xc.kb * GEMM_BK, 0,
-                             pol_x);
-            advance(xc);
-            ++x_issued;
-            if (++x_stage == STAGES) x_stage = 0;
-            progress = true;
-          }
-        }
-        if (progress) {
-          t_idle = 0;
-        } else {
-          const long long now = clock64();
-          if (t_idle == 0) t_idle = now;
-          else if (now - t_idle > 4000000000ll) {
-            printf("chain: producer stalled block %d (w %d x %d step %d)\n", cta, w_issued, x_issued, xc.s);
-            __trap();
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BN, BT);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_bits = 0;
-    for (int s = 0; s < P.n_steps; ++s) {
-      const ChainStep& st = P.step[s];
-      if (st.kind != 0 || cta >= st.ncta) continue;
-      const int KB = (st.K + GEMM_BK - 1) / GEMM_BK;
-      const GemmSched csched((st.N + GEMM_BN - 1) / GEMM_BN, 1, KB, st.ncta);
-      UnitIter it(csched, cta);
-      int tile, kb0, kb1, slot;
-      while (it.next(tile, kb0, kb1, slot)) {
-        mbar_wait(&tmem_empty[acc], ((acc_bits >> acc) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BT;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_w + stage * Cfg::W_BYTES));
-            const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_x + stage * Cfg::X_BYTES));
-#pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
-              tc_mma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                         (kb > kb0 || k > 0) ? 1u : 0u);
-            tc_commit(&empty_bar[stage]);
-            if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);
-          }
-          __syncwarp();
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        acc_bits ^= (1u << acc);
-        acc ^= 1;
-      }
-    }
-  } else {
-    // ===================== epilogue / row warps (4 warps = 128 TMEM lanes = 128 threads) =====================
-    griddep_wait();
-    const int sub = warp & 3;
-    const int row = sub * 32 + lane_id();
-    const int ep_tid = (warp - 2) * 32 + lane_id();
-    int acc = 0;
-    uint32_t acc_bits = 0;
-    for (int s = 0; s < P.n_steps; ++s) {
-      const ChainStep& st = P.step[s];
-      if (st.kind == 1) {
-        // ---------- row step: residual add + RMSNorm of rows cta, cta + grid, ... (arithmetic of rmsnorm_kernel)
-        if (cta >= T) continue;
-        if (s > 0) {
-          if (ep_tid == 0) spin_until_ge(P.sync + s - 1, P.step[s - 1].done_target);
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        }
-        if (ep_tid == 0) TLC(s, 5);  // row step: inputs complete
-        const int hidden = P.hidden, nvec = hidden / 8;
-        const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(st.x);
-        __nv_bfloat16* resid = reinterpret_cast<__nv_bfloat16*>(st.resid);
-        const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(st.w);
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(st.y);
-        int rows_done = 0;
-        for (int r = cta; r < T; r += gridDim.x) {
-          const size_t base = (size_t)r * hidden;
-          uint4 z[8];
-          float ss = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int i = ep_tid + j * 128;
-            if (i < nvec) {
-              // .cg: these rows were written by other SMs during this kernel, L1 may hold an older copy
-              uint4 a = __ldcg(reinterpret_cast<const uint4*>(resid + base) + i);
-              if (xin) {
-                const uint4 b = __ldcg(reinterpret_cast<const uint4*>(xin + base) + i);
-                const uint32_t* bw = &b.x;
-                uint32_t* aw = &a.x;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float lo = __uint_as_float(bw[e] << 16) + __uint_as_float(aw[e] << 16);
-                  const float hi = __uint_as_float(bw[e] & 0xffff0000u) + __uint_as_float(aw[e] & 0xffff0000u);
-                  __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-                  aw[e] = *reinterpret_cast<uint32_t*>(&pk);
-                }
-                reinterpret_cast<uint4*>(resid + base)[i] = a;
-              }
-              z[j] = a;
-              const uint32_t* aw = &a.x;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float lo = __uint_as_float(aw[e] << 16), hi = __uint_as_float(aw[e] & 0xffff0000u);
-                ss += lo * lo;
-                ss += hi * hi;
-              }
-            }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");  // red_smem reuse
-          if (lane_id() == 0) red_smem[warp - 2] = ss;
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          const float tot = (red_smem[0] + red_smem[1]) + (red_smem[2] + red_smem[3]);
-          const float rs = rsqrtf(tot / (float)hidden + P.eps);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int i = ep_tid + j * 128;
-            if (i < nvec) {
-              const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + i);
-              const uint32_t* ww = &wv.x;
-              const uint32_t* zw = &z[j].x;
-              uint4 o4;
-              uint32_t* ow = &o4.x;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float n0 = bf16_round(__uint_as_float(zw[e] << 16) * rs);
-                const float n1 = bf16_round(__uint_as_float(zw[e] & 0xffff0000u) * rs);
-                __nv_bfloat162 pk = __floats2bfloat162_rn(n0 * __uint_as_float(ww[e] << 16),
-                                                          n1 * __uint_as_float(ww[e] & 0xffff0000u));
-                ow[e] = *reinterpret_cast<uint32_t*>(&pk);
-              }
-              reinterpret_cast<uint4*>(out + base)[i] = o4;
-            }
-          }
-          ++rows_done;
-        }
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        if (ep_tid == 0 && rows_done > 0) red_release_gpu_add(P.sync + s, rows_done);
-        if (ep_tid == 0) TLC(s, 6);  // row step: rows published
-        continue;
-      }
-      // ---------- GEMM step
-      if (cta >= st.ncta) continue;
-      const int N = st.N, ldy = st.ldy, mode = st.mode, ncta = st.ncta;
-      __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(st.y);
-      const int KB = (st.K + GEMM_BK - 1) / GEMM_BK;
-      const long long total = (long long)((N + GEMM_BN - 1) / GEMM_BN) * KB;
-      const GemmSched csched((N + GEMM_BN - 1) / GEMM_BN, 1, KB, ncta);
-      UnitIter it(csched, cta);
-      int tile, kb0, kb1, slot;
-      while (it.next(tile, kb0, kb1, slot)) {
-        const int n = tile * GEMM_BN + row;
-        const int t_valid = min(BT, T);
-        const bool partial = (kb0 > 0) || (kb1 < KB);
-        mbar_wait(&tmem_full[acc], (acc_bits >> acc) & 1);
-        tc_fence_after();
-        if (ep_tid == 0 && it.pos >= it.end) TLC(s, 3);  // last unit of the step: accumulator ready
-        const uint32_t taddr = tmem_base + acc * BT + ((uint32_t)(sub * 32) << 16);
-        float* my_ws = P.ws + ((size_t)(cta * 2 + slot) * BT) * GEMM_BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BT; c0 += 16) {
-          if (c0 >= t_valid) break;
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(taddr + c0, r);
-          tmem_ld_wait();
-          if (!partial) {
-            if (mode == 2) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), 1);
-                if ((row & 1) == 0 && n < N && c0 + j < t_valid)
-                  Y[(size_t)(c0 + j) * ldy + (n >> 1)] = swiglu_bf16(__uint_as_float(r[j]), other);
-              }
-            } else if (n < N) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < t_valid) Y[(size_t)(c0 + j) * ldy + n] = __float2bfloat16_rn(__uint_as_float(r[j]));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < t_valid) my_ws[(size_t)(c0 + j) * GEMM_BN + row] = __uint_as_float(r[j]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
-        acc_bits ^= (1u << acc);
-        acc ^= 1;
-
-        bool finalized = !partial;
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");  // all stores of this unit issued (publish / completion below)
-        if (partial) {
-          const long long p0 = (long long)tile * KB;
-          const int c_first = unit_owner(p0, total, ncta);
-          const int c_last = unit_owner(p0 + KB - 1, total, ncta);
-          if (ep_tid == 0) {
-            int old;
-            asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;\n"
-                         : "=r"(old) : "l"(P.counters + tile) : "memory");
-            *flag_smem = (old == (c_last - c_first)) ? 1 : 0;
-          }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
-          finalized = *flag_smem != 0;
-          if (finalized) {
-            constexpr int FIX_C = 3, FIX_T = 8;
-            const int r4 = (ep_tid & 31) * 4;
-            const int tq = ep_tid >> 5;
-            const int n4 = tile * GEMM_BN + r4;
-            for (int tb = tq; tb < t_valid; tb += 4 * FIX_T) {
-              float4 av[FIX_T];
-#pragma unroll
-              for (int j = 0; j < FIX_T; ++j) av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int c0g = c_first; c0g <= c_last; c0g += FIX_C) {
-                float4 v[FIX_C][FIX_T];
-#pragma unroll
-                for (int ci = 0; ci < FIX_C; ++ci) {
-                  const int c = c0g + ci;
-                  const bool cv = c <= c_last;
-                  const long long cb = cv ? (total * c) / ncta : 0;
-                  const int cslot = ((int)(cb / KB) == tile) ? 0 : 1;
-                  const float* p = P.ws + ((size_t)((cv ? c : c_first) * 2 + cslot) * BT) * GEMM_BN + r4;
-#pragma unroll
-                  for (int j = 0; j < FIX_T; ++j) {
-                    const int t = tb + 4 * j;
-                    v[ci][j] = (cv && t < t_valid) ? __ldcg(reinterpret_cast<const float4*>(p + (size_t)t * GEMM_BN))
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                  }
-                }
-#pragma unroll
-                for (int ci = 0; ci < FIX_C; ++ci)
-#pragma unroll
-                  for (int j = 0; j < FIX_T; ++j) {
-                    av[j].x += v[ci][j].x; av[j].y += v[ci][j].y; av[j].z += v[ci][j].z; av[j].w += v[ci][j].w;
-                  }
-              }
-#pragma unroll
-              for (int j = 0; j < FIX_T; ++j) {
-                const int t = tb + 4 * j;
-                if (t < t_valid) {
-                  const float a4[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
-                  if (mode == 2) {
-                    __nv_bfloat16* yo = Y + (size_t)t * ldy + (n4 >> 1);
-                    if (n4 + 1 < N) yo[0] = swiglu_bf16(a4[0], a4[1]);
-                    if (n4 + 3 < N) yo[1] = swiglu_bf16(a4[2], a4[3]);
-                  } else if (n4 + 3 < N && (ldy & 3) == 0) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(a4[0], a4[1]), hi = __floats2bfloat162_rn(a4[2], a4[3]);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                    *reinterpret_cast<uint2*>(Y + (size_t)t * ldy + n4) = pk;
-                  } else {
-                    for (int e = 0; e < 4; ++e)
-                      if (n4 + e < N) Y[(size_t)t * ldy + n4 + e] = __float2bfloat16_rn(a4[e]);
-                  }
-                }
-              }
-            }
-            if (ep_tid == 0) P.counters[tile] = 0;
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");  // reduced tile stored by all threads
-          }
-        }
-        // one more finished output tile of step s: the (barrier-ordered) stores above are released to the consumers
-        if (finalized && ep_tid == 0) red_release_gpu_add(P.sync + s, 1);
-        if (ep_tid == 0 && it.pos >= it.end) TLC(s, 4);  // last unit of the step: published / finalised
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-  }
-  // the last CTA out re-arms the step counters for the next launch (everyone else is past its last read of them)
-  if (threadIdx.x == 0) {
-    int old;
-    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;\n"
-                 : "=r"(old) : "l"(P.sync + CHAIN_MAX_STEPS) : "memory");
-    if (old == (int)gridDim.x - 1) {
-      for (int i = 0; i <= CHAIN_MAX_STEPS; ++i) P.sync[i] = 0;
-    }
-  }
-}
-
 #ifdef TGIS_GEMM_TIMELINE
 int gemm_timeline_read(unsigned long long* out) {
   return cudaMemcpyFromSymbol(out, g_gemm_timeline, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -1;
 }
-int chain_timeline_read(unsigned long long* out) {
-  return cudaMemcpyFromSymbol(out, g_chain_timeline, sizeof(unsigned long long) * 128) == cudaSuccess ? 0 : -1;
-}
 #else
 int gemm_timeline_read(unsigned long long*) { return -2; }
-int chain_timeline_read(unsigned long long*) { return -2; }
 #endif
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1287,60 +818,6 @@ cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, v
     default: TGIS_GEMM_CASE(256);
   }
 #undef TGIS_GEMM_CASE
-}
-
-template <int BT>
-static cudaError_t chain_launch_bt(const ChainParams& P, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chain_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  return launch_k(chain_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, P);
-}
-
-void chain_add_gemm(ChainParams& P, const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int N, int K,
-                    int mode, int num_sms) {
-  ChainStep& st = P.step[P.n_steps++];
-  memset(&st, 0, sizeof(st));
-  st.wmap = wmap;
-  st.xmap = xmap;
-  st.y = Y;
-  st.kind = 0;
-  st.ldy = ldy;
-  st.N = N;
-  st.K = K;
-  st.mode = mode;
-  st.ncta = gemm_grid_size(P.T, N, K, num_sms);
-  st.done_target = (N + GEMM_BN - 1) / GEMM_BN;
-}
-
-void chain_add_norm(ChainParams& P, const __nv_bfloat16* x, __nv_bfloat16* resid, const __nv_bfloat16* w,
-                    __nv_bfloat16* out) {
-  ChainStep& st = P.step[P.n_steps++];
-  memset(&st, 0, sizeof(st));
-  st.kind = 1;
-  st.x = x;
-  st.resid = resid;
-  st.w = w;
-  st.y = out;
-  st.done_target = P.T;
-}
-
-// All steps share T (<= 256, one token tile) and the activation tensor maps must have box_rows == gemm_pick_bt(T).
-cudaError_t chain_launch(const ChainParams& P, int num_sms, cudaStream_t stream) {
-  if (P.n_steps <= 0 || P.n_steps > CHAIN_MAX_STEPS || P.T <= 0 || P.T > 256) return cudaErrorInvalidValue;
-  if (P.hidden % 8 != 0 || P.hidden > 8 * 8 * 128) return cudaErrorInvalidValue;
-  switch (gemm_pick_bt(P.T)) {
-    case 16: return chain_launch_bt<16>(P, num_sms, stream);
-    case 32: return chain_launch_bt<32>(P, num_sms, stream);
-    case 64: return chain_launch_bt<64>(P, num_sms, stream);
-    case 128: return chain_launch_bt<128>(P, num_sms, stream);
-    default: return chain_launch_bt<256>(P, num_sms, stream);
-  }
 }
 
 }  // namespace tgis

@@ -15,7 +15,6 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int gemm_pick_bt(int T);
 size_t gemm_workspace_bytes(int num_sms);
 int gemm_timeline_read(unsigned long long* out64);  // debug builds (-DTGIS_GEMM_TIMELINE) only
-int chain_timeline_read(unsigned long long* out128);
 // Decode-shaped successor of a GEMM launch: lets the running kernel pull the first `kb_prefetch` weight boxes of every
 // CTA of the NEXT GEMM into L2 while its own tail drains (kb_prefetch == 0: off).
 struct GemmNext {
@@ -42,36 +41,6 @@ cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, v
                              const CUtensorMap* next_wmap = nullptr, const GemmNext* next = nullptr,
                              const GemmRope* rope = nullptr);
 
-// Chain kernel: one persistent launch = a dependent sequence of decode-shaped GEMMs and residual-add + RMSNorm row
-// steps (see gemm_tcgen05.cu).  sync: CHAIN_MAX_STEPS + 1 ints, zero before the first launch (re-armed by the kernel).
-constexpr int CHAIN_MAX_STEPS = 8;
-struct alignas(64) ChainStep {
-  CUtensorMap wmap, xmap;  // GEMM step: weights [N, K], activations [>= box rows, K]
-  void* y;                 // GEMM: output [T, ldy] bf16 (mode 2: SwiGLU of interleaved gate/up rows -> [T, N/2]); norm: output
-  const void* x;           // norm: addend [T, hidden] or nullptr (plain RMSNorm of resid)
-  void* resid;             // norm: residual stream [T, hidden], updated in place when x != nullptr
-  const void* w;           // norm: weight [hidden]
-  int32_t kind;            // 0 = GEMM, 1 = norm
-  int32_t ldy, N, K, mode;
-  int32_t ncta;            // GEMM: CTAs that share the step (= gemm_grid_size: same partition as the stand-alone launch)
-  int32_t done_target;     // completions that open the next step: output tiles (GEMM) / rows (norm)
-  int32_t pad;
-};
-struct ChainParams {
-  ChainStep step[CHAIN_MAX_STEPS];
-  int32_t n_steps, T, hidden;
-  float eps;
-  int32_t pf_depth;  // weight tiles (16 KiB) per CTA prefetched into L2 ahead of the smem ring
-  float* ws;
-  int* counters;
-  int* sync;
-};
-void chain_add_gemm(ChainParams& P, const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int N, int K,
-                    int mode, int num_sms);
-void chain_add_norm(ChainParams& P, const __nv_bfloat16* x, __nv_bfloat16* resid, const __nv_bfloat16* w,
-                    __nv_bfloat16* out);
-cudaError_t chain_launch(const ChainParams& P, int num_sms, cudaStream_t stream);
-
 // ---- gemm_ref.cu (debug cross-check only; never on the product path) ---------------------------------------------
 cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, void* Y, int ldy, int T,
                                  int N, int K, cudaStream_t stream, int out_f32 = 0);
@@ -95,9 +64,10 @@ struct ArPeers {
   const __nv_bfloat16* own;
   uint4* recv[8];
 };
-cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, uint32_t epoch, __nv_bfloat16* residual,
-                                  const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden, float eps,
-                                  cudaStream_t stream);
+// The exchange's epoch is *epoch_base + epoch_idx (epoch_base: device memory written by the step's metadata copy).
+cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, const uint32_t* epoch_base, uint32_t epoch_idx,
+                                  __nv_bfloat16* residual, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
+                                  float eps, cudaStream_t stream);
 // act[t, i] = bf16(silu(gate_up[t, i])) * gate_up[t, F + i]
 cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn, cudaStream_t stream);
 // gather rows: out[r, :] = x[rows[r], :]

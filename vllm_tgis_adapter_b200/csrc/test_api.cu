@@ -51,7 +51,6 @@ struct Tmp {
 extern "C" {
 
 int tgis_k_gemm_timeline(uint64_t* out64) { return gemm_timeline_read((unsigned long long*)out64); }
-int tgis_k_chain_timeline(uint64_t* out128) { return chain_timeline_read((unsigned long long*)out128); }
 int tgis_k_sizeof_sample_row(void) { return (int)sizeof(SampleRow); }
 int tgis_k_sizeof_sample_out(void) { return (int)sizeof(SampleOut); }
 int tgis_k_kv_block(void) { return KV_BLOCK; }

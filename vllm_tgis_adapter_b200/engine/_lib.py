@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_REQUEST_ID = 96
 MAX_TOPN = 12
 MAX_STOP_TOKEN_IDS = 8
@@ -60,6 +60,7 @@ class TgisStatus(C.Structure):
         ("gpu_decode_ms", C.c_double), ("gpu_mixed_ms", C.c_double), ("decode_steps", C.c_int64),
         ("decode_tokens", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("gemm_ms", C.c_double),
         ("gemm_bytes", C.c_double), ("gemm_calls", C.c_int64), ("graph_launches", C.c_int64),
+        ("exchange_ms", C.c_double), ("exchange_calls", C.c_int64),
     ]
 
 
@@ -70,7 +71,7 @@ ENGINE_SYMBOLS = [
     "tgis_engine_max_model_len", "tgis_engine_set_profiling", "tgis_nccl_unique_id", "tgis_engine_worker_run", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
 ]
 KERNEL_SYMBOLS = [
-    "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_chain_timeline", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_attention",
+    "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_attention",
     "tgis_k_attention_bench", "tgis_k_decode_items", "tgis_k_gemm_plan",
     "tgis_k_sampler", "tgis_k_sampler_ex", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
 ]
