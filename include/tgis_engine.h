@@ -147,6 +147,7 @@ typedef struct tgis_status {
   double exchange_ms;        /* with profiling on, tensor parallelism: summed CUDA-event time of every row-parallel
                                 exchange (fused push all-reduce + residual + RMSNorm kernel, or ncclAllReduce) */
   int64_t exchange_calls;
+  int64_t preemptions;       /* sequences evicted from the KV cache and queued for recomputation (vLLM V1 policy) */
 } tgis_status;
 
 const char* tgis_last_error(void);

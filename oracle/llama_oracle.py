@@ -117,21 +117,25 @@ def rope_table(cfg: LlamaConfig, dtype: torch.dtype = torch.bfloat16) -> torch.T
 class SeqState:
     """Per-sequence KV history (what the paged cache holds for one request)."""
 
-    def __init__(self, cfg: LlamaConfig, dtype: torch.dtype):
-        self.k = [torch.empty(0, cfg.n_kv_heads, cfg.head_dim, dtype=dtype) for _ in range(cfg.n_layers)]
-        self.v = [torch.empty(0, cfg.n_kv_heads, cfg.head_dim, dtype=dtype) for _ in range(cfg.n_layers)]
+    def __init__(self, cfg: LlamaConfig, dtype: torch.dtype, device: str = "cpu"):
+        self.k = [torch.empty(0, cfg.n_kv_heads, cfg.head_dim, dtype=dtype, device=device) for _ in range(cfg.n_layers)]
+        self.v = [torch.empty(0, cfg.n_kv_heads, cfg.head_dim, dtype=dtype, device=device) for _ in range(cfg.n_layers)]
         self.n = 0
 
 
 class LlamaOracle:
-    """Flat-batch Llama forward with the model-dtype rounding points of the vLLM/HF path."""
+    """Flat-batch Llama forward with the model-dtype rounding points of the vLLM/HF path.
+
+    `device`: the same plain-torch restatement can be evaluated on a CUDA device (torch ops only) so that the -m gpu
+    parity tests can afford BASELINE shapes (8B dims, 32 x 512-token prompts); the default and every CPU test use "cpu"."""
 
     def __init__(self, cfg: LlamaConfig, weights: dict[str, torch.Tensor], dtype: torch.dtype = torch.bfloat16,
-                 logits_fp32: bool = False):
+                 logits_fp32: bool = False, device: str = "cpu"):
         self.cfg = cfg
         self.dtype = dtype
         self.logits_fp32 = logits_fp32
-        w = {k: v.to(dtype) for k, v in weights.items()}
+        self.device = device
+        w = {k: v.to(device=device, dtype=dtype) for k, v in weights.items()}
         self.embed = w["model.embed_tokens.weight"]
         self.lm_head = w.get("lm_head.weight", self.embed)
         self.norm = w["model.norm.weight"]
@@ -147,7 +151,7 @@ class LlamaOracle:
                 "ln1": w[p + "input_layernorm.weight"],
                 "ln2": w[p + "post_attention_layernorm.weight"],
             })
-        self.cos_sin = rope_table(cfg, dtype)
+        self.cos_sin = rope_table(cfg, dtype).to(device)
         self._lm_head_f32 = None
 
     # -- building blocks ---------------------------------------------------------------------------------------
@@ -172,8 +176,8 @@ class LlamaOracle:
         vf = v.float().repeat_interleave(g, dim=1)
         s = torch.einsum("qhd,khd->hqk", q.float(), kf) * (1.0 / math.sqrt(cfg.head_dim))
         tq, tk = q.shape[0], k.shape[0]
-        qpos = first_pos + torch.arange(tq)[:, None]
-        mask = torch.arange(tk)[None, :] <= qpos
+        qpos = first_pos + torch.arange(tq, device=q.device)[:, None]
+        mask = torch.arange(tk, device=q.device)[None, :] <= qpos
         s = s.masked_fill(~mask[None], float("-inf"))
         p = torch.softmax(s, dim=-1)
         o = torch.einsum("hqk,khd->qhd", p, vf)
@@ -185,8 +189,8 @@ class LlamaOracle:
         """Append `tokens` to each sequence and return the fp32 view of the model-dtype logits of each sequence's
         last new token ([n_seqs, vocab]); with want_all_logits, of every new token ([T, vocab])."""
         cfg = self.cfg
-        toks = torch.tensor([t for _, ts in work for t in ts], dtype=torch.long)
-        pos = torch.tensor([st.n + j for st, ts in work for j in range(len(ts))], dtype=torch.long)
+        toks = torch.tensor([t for _, ts in work for t in ts], dtype=torch.long, device=self.device)
+        pos = torch.tensor([st.n + j for st, ts in work for j in range(len(ts))], dtype=torch.long, device=self.device)
         resid = self.embed[toks]
         x = None
         T = toks.numel()
@@ -226,7 +230,7 @@ class LlamaOracle:
             for _, ts in work:
                 off += len(ts)
                 last.append(off - 1)
-            xn = xn[torch.tensor(last)]
+            xn = xn[torch.tensor(last, device=self.device)]
         return self.head(xn, normed=True)
 
     def head(self, x: torch.Tensor, normed: bool = False) -> torch.Tensor:
@@ -242,4 +246,4 @@ class LlamaOracle:
         return acc.to(self.dtype).float()
 
     def new_seq(self) -> SeqState:
-        return SeqState(self.cfg, self.dtype)
+        return SeqState(self.cfg, self.dtype, self.device)

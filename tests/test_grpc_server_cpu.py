@@ -322,3 +322,184 @@ def test_http_sidecar_health_and_vllm_named_metrics(srv):
     assert value("vllm:e2e_request_latency_seconds_count{") == 3.0
     assert value("vllm:request_generation_tokens_sum{") == 13.0
     assert "vllm:num_requests_running{" in text and "vllm:kv_cache_usage_perc{" in text
+
+
+# ---------------------------------------------------------------------------------------------- wire schema golden
+def test_proto_descriptor_matches_reference_schema():
+    """The hand-built run-time descriptor (grpc/pb/generation_pb2.py; no protoc in this image) against the golden that
+    oracle/gen_proto_golden.py extracted from the reference's generation.proto: every message, field name, NUMBER, type,
+    label, proto3-optional presence, oneof membership, enum value and RPC signature."""
+    import json
+    from pathlib import Path
+
+    from google.protobuf import descriptor as D
+
+    gold = json.loads((Path(__file__).parent / "golden" / "generation_proto_schema.json").read_text())
+    fd = pb.DESCRIPTOR
+    assert fd.package == gold["package"] == "fmaas"
+    scalar = {D.FieldDescriptor.TYPE_STRING: "string", D.FieldDescriptor.TYPE_UINT32: "uint32",
+              D.FieldDescriptor.TYPE_UINT64: "uint64", D.FieldDescriptor.TYPE_FLOAT: "float",
+              D.FieldDescriptor.TYPE_BOOL: "bool", D.FieldDescriptor.TYPE_INT32: "int32",
+              D.FieldDescriptor.TYPE_INT64: "int64", D.FieldDescriptor.TYPE_DOUBLE: "double",
+              D.FieldDescriptor.TYPE_BYTES: "bytes"}
+
+    def walk(msgs, prefix=""):
+        for m in msgs:
+            yield prefix + m.name, m
+            yield from walk(m.nested_types, prefix + m.name + ".")
+
+    ours = dict(walk(fd.message_types_by_name.values()))
+    assert sorted(ours) == sorted(gold["messages"])
+    n_checked = 0
+    for name, m in ours.items():
+        gf = gold["messages"][name]
+        assert sorted(f.name for f in m.fields) == sorted(gf), name
+        for f in m.fields:
+            g = gf[f.name]
+            assert f.number == g["number"], (name, f.name)
+            if f.type in (D.FieldDescriptor.TYPE_MESSAGE, D.FieldDescriptor.TYPE_ENUM):
+                tname = (f.message_type or f.enum_type).name
+                assert tname == g["type"].split(".")[-1], (name, f.name, tname, g["type"])
+            else:
+                assert scalar[f.type] == g["type"], (name, f.name)
+            rep = f.is_repeated if hasattr(f, "is_repeated") else f.label == D.FieldDescriptor.LABEL_REPEATED
+            assert bool(rep() if callable(rep) else rep) == (g["label"] == "repeated"), (name, f.name)
+            assert bool(f.has_presence and f.containing_oneof is not None and f.containing_oneof.name.startswith("_")) \
+                == (g["label"] == "optional"), (name, f.name)
+            real_oneof = f.containing_oneof.name if f.containing_oneof is not None and \
+                not f.containing_oneof.name.startswith("_") else None
+            assert real_oneof == g["oneof"], (name, f.name)
+            n_checked += 1
+    assert n_checked == gold["meta"]["n_fields"]
+
+    def walk_enums():
+        for e in fd.enum_types_by_name.values():
+            yield e.name, e
+        for name, m in ours.items():
+            for e in m.enum_types:
+                yield name + "." + e.name, e
+
+    enums = dict(walk_enums())
+    assert sorted(enums) == sorted(gold["enums"])
+    for name, e in enums.items():
+        assert {v.name: v.number for v in e.values} == gold["enums"][name], name
+    svc = fd.services_by_name["GenerationService"]
+    assert sorted(m.name for m in svc.methods) == sorted(gold["services"]["GenerationService"])
+    for m in svc.methods:
+        g = gold["services"]["GenerationService"][m.name]
+        assert (m.input_type.name, m.output_type.name) == (g["input"], g["output"])
+        assert bool(m.server_streaming) == g["server_streaming"] and bool(m.client_streaming) == g["client_streaming"]
+
+
+# ---------------------------------------------------------------------------------------------- TLS / mTLS
+def _make_certs(tmp_path):
+    """A throw-away CA, a server certificate for 127.0.0.1/localhost and a client certificate (what the reference's
+    tests/utils.py:226-292 builds with openssl)."""
+    import datetime
+    import ipaddress
+
+    from cryptography import x509
+    from cryptography.hazmat.primitives import hashes, serialization
+    from cryptography.hazmat.primitives.asymmetric import rsa
+    from cryptography.x509.oid import NameOID
+
+    def key():
+        return rsa.generate_private_key(public_exponent=65537, key_size=2048)
+
+    def name(cn):
+        return x509.Name([x509.NameAttribute(NameOID.COMMON_NAME, cn)])
+
+    now = datetime.datetime.now(datetime.timezone.utc)
+    ca_key = key()
+    ca = (x509.CertificateBuilder().subject_name(name("tgis-test-ca")).issuer_name(name("tgis-test-ca"))
+          .public_key(ca_key.public_key()).serial_number(x509.random_serial_number())
+          .not_valid_before(now - datetime.timedelta(days=1)).not_valid_after(now + datetime.timedelta(days=2))
+          .add_extension(x509.BasicConstraints(ca=True, path_length=None), critical=True)
+          .sign(ca_key, hashes.SHA256()))
+
+    def leaf(cn, server):
+        k = key()
+        b = (x509.CertificateBuilder().subject_name(name(cn)).issuer_name(ca.subject).public_key(k.public_key())
+             .serial_number(x509.random_serial_number()).not_valid_before(now - datetime.timedelta(days=1))
+             .not_valid_after(now + datetime.timedelta(days=2)))
+        if server:
+            b = b.add_extension(x509.SubjectAlternativeName([x509.DNSName("localhost"),
+                                                             x509.IPAddress(ipaddress.ip_address("127.0.0.1"))]),
+                                critical=False)
+        return k, b.sign(ca_key, hashes.SHA256())
+
+    def pem_key(k):
+        return k.private_bytes(serialization.Encoding.PEM, serialization.PrivateFormat.TraditionalOpenSSL,
+                               serialization.NoEncryption())
+
+    def pem_cert(c):
+        return c.public_bytes(serialization.Encoding.PEM)
+
+    sk, sc = leaf("localhost", True)
+    ck, cc = leaf("tgis-test-client", False)
+    paths = {}
+    for fname, data in (("ca.pem", pem_cert(ca)), ("server.key", pem_key(sk)), ("server.pem", pem_cert(sc)),
+                        ("client.key", pem_key(ck)), ("client.pem", pem_cert(cc))):
+        p = tmp_path / fname
+        p.write_bytes(data)
+        paths[fname] = p
+    return paths
+
+
+@pytest.mark.parametrize("mtls", [False, True])
+def test_tls_and_mtls_server(tmp_path, mtls):
+    """--ssl-keyfile/--ssl-certfile (TLS) and --ssl-ca-certs (mTLS: client certificate required), reference
+    grpc_server.py:934-962; a Generate call goes through the encrypted channel."""
+    c = _make_certs(tmp_path)
+    srv = Server(ssl_keyfile=str(c["server.key"]), ssl_certfile=str(c["server.pem"]),
+                 ssl_ca_certs=str(c["ca.pem"]) if mtls else None)
+    try:
+        ca = c["ca.pem"].read_bytes()
+        if mtls:
+            creds = grpc.ssl_channel_credentials(ca, c["client.key"].read_bytes(), c["client.pem"].read_bytes())
+        else:
+            creds = grpc.ssl_channel_credentials(ca)
+        opts = (("grpc.ssl_target_name_override", "localhost"),)
+        with grpc.secure_channel(f"127.0.0.1:{srv.port}", creds, options=opts) as ch:
+            call = ch.unary_unary("/fmaas.GenerationService/Generate",
+                                  request_serializer=pb.BatchedGenerationRequest.SerializeToString,
+                                  response_deserializer=pb.BatchedGenerationResponse.FromString)
+            resp = call(pb.BatchedGenerationRequest(model_id="m", requests=[pb.GenerationRequest(text="t5 t6 t7")],
+                                                    params=pb.Parameters(stopping=pb.StoppingCriteria(max_new_tokens=4))),
+                        timeout=20)
+            assert len(resp.responses) == 1 and resp.responses[0].generated_token_count == 4
+        # a plaintext client cannot talk to the TLS port
+        with grpc.insecure_channel(f"127.0.0.1:{srv.port}") as ch:
+            call = ch.unary_unary("/fmaas.GenerationService/ModelInfo",
+                                  request_serializer=pb.ModelInfoRequest.SerializeToString,
+                                  response_deserializer=pb.ModelInfoResponse.FromString)
+            with pytest.raises(grpc.RpcError):
+                call(pb.ModelInfoRequest(model_id="m"), timeout=3)
+        if mtls:   # TLS without a client certificate is rejected when the server demands one
+            with grpc.secure_channel(f"127.0.0.1:{srv.port}", grpc.ssl_channel_credentials(ca), options=opts) as ch:
+                call = ch.unary_unary("/fmaas.GenerationService/ModelInfo",
+                                      request_serializer=pb.ModelInfoRequest.SerializeToString,
+                                      response_deserializer=pb.ModelInfoResponse.FromString)
+                with pytest.raises(grpc.RpcError):
+                    call(pb.ModelInfoRequest(model_id="m"), timeout=3)
+    finally:
+        srv.close()
+
+
+def test_tls_flag_with_unreadable_file_fails_like_reference(tmp_path):
+    """grpc_server.py:940-950: `Error reading `ssl_keyfile` file: ...` as a ValueError at start-up."""
+    args = argparse.Namespace(max_new_tokens=64, output_special_tokens=False, default_include_stop_seqs=True,
+                              disable_prompt_logprobs=False, adapter_cache=None, prefix_store_path=None, host="127.0.0.1",
+                              grpc_port=0, ssl_keyfile=str(tmp_path / "missing.key"), ssl_certfile=str(tmp_path / "m.pem"),
+                              ssl_ca_certs=None)
+    mc = ModelConfig(n_layers=1, hidden=128, n_q_heads=1, n_kv_heads=1, ffn=128, vocab=VOCAB, max_model_len=128)
+    fake = FakeNativeEngine(mc)
+
+    async def go():
+        eng = AsyncTGISEngine(fake, build_synthetic_tokenizer(VOCAB), mc)
+        eng.start(asyncio.get_running_loop())
+        with pytest.raises(ValueError, match="Error reading `ssl_keyfile` file"):
+            await grpc_server.start_grpc_server(args, eng, asyncio.Event())
+
+    asyncio.run(go())
+    fake.close()

@@ -441,3 +441,76 @@ def test_sampler_distribution_matches_softmax(g):
     exp = p * n
     chi2 = float(((counts - exp) ** 2 / np.maximum(exp, 1e-9)).sum())
     assert chi2 < 120.0, chi2  # 63 dof: P(chi2 > 120) ~ 2e-5
+
+
+@pytest.mark.parametrize("V", [1024, 128256])
+def test_sampler_bf16_logits_ties_rank_and_argmax(g, V):
+    """The product path's logits are bf16 (vLLM's lm_head output dtype): thousands of EXACT ties per row.  Greedy must
+    pick the lowest id among equal maxima (torch.argmax), rank counts every tied entry (vllm ops/logprobs.py:27),
+    logprobs come from the fp32 view of the bf16 values -- all index-exact against the oracle on the same bf16 row."""
+    from oracle.sampler_oracle import SamplingCase, sample_row
+
+    torch.manual_seed(V + 7)
+    n = 6
+    logits = (torch.randn(n, V) * 2).to(torch.bfloat16)
+    mx = logits[2].float().max()
+    logits[2, 700] = logits[2, 31] = logits[2, 900] = (mx + 0.5).to(torch.bfloat16)   # three-way tie at the top
+    rows = _rows(g, n)
+    rows["flags"] = g.SAMPLE_GREEDY | g.SAMPLE_LOGPROBS
+    rows["n_topn"] = [1, 3, 5, 11, 2, 1]
+    out = g.run_sampler(logits.cuda(), rows)
+    ties = 0
+    for i in range(n):
+        o = sample_row(logits[i].float(), SamplingCase(greedy=True, num_logprobs=int(rows["n_topn"][i])))
+        assert out["token"][i] == o["token"]
+        assert abs(out["logprob"][i] - o["logprob"]) < 1e-4
+        assert out["rank"][i] == o["rank"]
+        ties += int(o["rank"] > 1)
+        k = int(rows["n_topn"][i])
+        np.testing.assert_allclose(out["topn_lps"][i][:k], o["topn_logprobs"], atol=1e-4)
+        for j in range(k):   # ids agree wherever the values are not tied; tied values are listed lowest id first
+            if out["topn_ids"][i][j] != o["topn_ids"][j]:
+                assert abs(out["topn_lps"][i][j] - o["topn_logprobs"][j]) < 1e-7
+    assert out["token"][2] == 31 and out["rank"][2] == 3 and ties >= 1
+
+
+def test_sampler_bf16_logits_sampling_paths_match_fp32_view(g):
+    """bf16 logits through typical-p / penalties / top-k / top-p / race: bit-identical to running the same kernel on the
+    fp32 copy of those bf16 values (the cast is exact), and equal to the oracle's draw."""
+    from oracle.sampler_oracle import SamplingCase, len_penalty_factor_m1, sample_row
+
+    V = 128256
+    torch.manual_seed(5)
+    cases = [SamplingCase(greedy=False, temperature=1.0, typical_p=0.9, repetition_penalty=1.2, length_penalty=(64, 1.05),
+                          n_out=100, min_tokens=128, seed=1234, num_logprobs=2),
+             SamplingCase(greedy=False, temperature=0.8, top_k=40, top_p=0.9, seed=99, num_logprobs=2),
+             SamplingCase(greedy=True, length_penalty=(2, 1.5), n_out=9, num_logprobs=2)]
+    n = len(cases)
+    lb = (torch.randn(n, V) * 3).to(torch.bfloat16)
+    rows = _rows(g, n)
+    words = (V + 31) // 32
+    bitmap = torch.zeros(n, words, dtype=torch.int32)
+    seen = torch.zeros(n, V, dtype=torch.bool)
+    seen[:, 10:20] = True
+    bitmap[:, 0] = sum(1 << b for b in range(10, 20))
+    for i, c in enumerate(cases):
+        rows["flags"][i] = g.SAMPLE_LOGPROBS | (g.SAMPLE_TYPICAL if (0 < c.typical_p < 1 and not c.greedy) else 0) | \
+            (g.SAMPLE_GREEDY if c.greedy else 0)
+        rows["n_topn"][i] = 2
+        rows["temperature"][i], rows["top_k"][i], rows["top_p"][i] = c.temperature, c.top_k, c.top_p
+        rows["typical_p"][i], rows["rep_penalty"][i] = c.typical_p, c.repetition_penalty
+        rows["n_out"][i], rows["min_tokens"][i], rows["step"][i] = c.n_out, c.min_tokens, c.n_out
+        rows["seed_lo"][i], rows["seed_hi"][i] = c.seed & 0xFFFFFFFF, c.seed >> 32
+        rows["seq_slot"][i] = i
+        if c.length_penalty:
+            f = len_penalty_factor_m1(c.n_out, *c.length_penalty)
+            if f != 0.0:
+                rows["flags"][i] |= g.SAMPLE_LENPEN
+                rows["len_decay_factor"][i] = f
+    a = g.run_sampler(lb.cuda(), rows, bitmap.cuda())
+    b = g.run_sampler(lb.float().cuda(), rows, bitmap.clone().cuda())
+    for f in ("token", "logprob", "rank", "n_topn", "topn_ids", "topn_lps"):
+        assert np.array_equal(a[f], b[f]), f
+    for i, c in enumerate(cases):
+        o = sample_row(lb[i].float(), c, seen[i] if c.repetition_penalty != 1.0 else None)
+        assert int(a["token"][i]) == o["token"] or bool(o["allowed"][int(a["token"][i])])

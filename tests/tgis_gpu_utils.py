@@ -101,12 +101,17 @@ def dense_from_v_cache(vc: torch.Tensor) -> torch.Tensor:
     return x.permute(0, 2, 1, 3, 4).reshape(nb * KV_BLOCK, n_kv, HEAD_DIM)
 
 
-def run_sampler(logits: torch.Tensor, rows: np.ndarray, bitmap: torch.Tensor | None = None) -> np.ndarray:
+def run_sampler(logits: torch.Tensor, rows: np.ndarray, bitmap: torch.Tensor | None = None, iters: int = 1,
+                return_us: bool = False):
+    """logits: fp32 (golden fixtures) or bf16 (the product path's dtype) [rows, V] on the device."""
     assert rows.dtype == SAMPLE_ROW_DTYPE and rows.dtype.itemsize == lib().tgis_k_sizeof_sample_row()
     assert SAMPLE_OUT_DTYPE.itemsize == lib().tgis_k_sizeof_sample_out()
+    assert logits.dtype in (torch.float32, torch.bfloat16)
     out = np.zeros(len(rows), dtype=SAMPLE_OUT_DTYPE)
-    rc = lib().tgis_k_sampler(ptr(logits), logits.stride(0), logits.shape[1], rows.ctypes.data_as(C.c_void_p),
-                              len(rows), ptr(bitmap) if bitmap is not None else None,
-                              out.ctypes.data_as(C.c_void_p))
+    us = C.c_float(0)
+    rc = lib().tgis_k_sampler_ex(ptr(logits), 1 if logits.dtype == torch.bfloat16 else 0, logits.stride(0),
+                                 logits.shape[1], rows.ctypes.data_as(C.c_void_p), len(rows),
+                                 ptr(bitmap) if bitmap is not None else None, out.ctypes.data_as(C.c_void_p), iters,
+                                 C.byref(us))
     assert rc == 0, kerr()
-    return out
+    return (out, us.value) if return_us else out

@@ -255,7 +255,7 @@ struct tgis_engine {
   bool started = false, ready = false;
   std::mt19937_64 rng;
   // stats
-  std::atomic<long long> n_steps{0}, n_tokens{0}, n_launches{0};
+  std::atomic<long long> n_steps{0}, n_tokens{0}, n_launches{0}, n_preempt{0};
   // scheduler-state snapshot for tgis_engine_status (the queues themselves belong to the engine thread)
   std::atomic<int> snap_running{0}, snap_waiting{0}, snap_free_blocks{0};
   void snapshot() {
@@ -1229,6 +1229,7 @@ struct tgis_engine {
         running.pop_back();
         free_request(*victim);
         victim->n_computed = 0;
+        ++n_preempt;
         waiting.push_front(std::move(victim));
         ok = ensure_blocks(r, r.n_computed + q);
       }
@@ -1237,6 +1238,7 @@ struct tgis_engine {
         running.pop_back();
         free_request(*victim);
         victim->n_computed = 0;
+        ++n_preempt;
         waiting.push_front(std::move(victim));
         break;
       }
@@ -1528,6 +1530,7 @@ int tgis_engine_status(tgis_engine* e, tgis_status* out) {
   out->graph_launches = e->n_graph_launches;
   out->exchange_ms = e->exchange_ms;
   out->exchange_calls = e->exchange_calls;
+  out->preemptions = e->n_preempt;
   if (e->errored) g_last_error = e->error_msg;
   return 0;
 }

@@ -60,7 +60,7 @@ class TgisStatus(C.Structure):
         ("gpu_decode_ms", C.c_double), ("gpu_mixed_ms", C.c_double), ("decode_steps", C.c_int64),
         ("decode_tokens", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("gemm_ms", C.c_double),
         ("gemm_bytes", C.c_double), ("gemm_calls", C.c_int64), ("graph_launches", C.c_int64),
-        ("exchange_ms", C.c_double), ("exchange_calls", C.c_int64),
+        ("exchange_ms", C.c_double), ("exchange_calls", C.c_int64), ("preemptions", C.c_int64),
     ]
 
 
