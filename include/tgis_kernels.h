@@ -65,6 +65,10 @@ int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, i
 const char* tgis_k_last_error(void);
 /* debug builds only (-DTGIS_GEMM_TIMELINE): %globaltimer stamps of CTA 0 and CTA grid/2, [4][16] u64; else -2 */
 int tgis_k_gemm_timeline(uint64_t* out64);
+/* debug builds only (-DTGIS_STEP_TIMELINE; else -2): CTA 0 of every kernel launch records {kernel id, %globaltimer at
+ * entry / after the grid-dependency wait / at exit}; read: out[0] = records, then out[8 + 4 i ..] (4096-entry ring) */
+int tgis_k_step_timeline_enable(void);
+int tgis_k_step_timeline_read(uint64_t* out);
 int tgis_k_sizeof_sample_row(void);
 int tgis_k_sizeof_sample_out(void);
 int tgis_k_kv_block(void);

@@ -36,6 +36,11 @@ for st in $STAGES; do
     ctasweep) timeout 300 python scripts/gemm_cta_sweep.py > gpurun_out/gemm_cta_sweep.log 2>&1; echo "ctasweep rc=$?" ;;
     attnbench) timeout 300 python scripts/attn_bench.py > gpurun_out/attn_bench.log 2>&1; echo "attnbench rc=$?" ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
+    xcheck) timeout 1500 python scripts/vllm_crosscheck.py check > gpurun_out/xcheck.log 2>&1; echo "xcheck rc=$?" ;;
+    xcheck_small) timeout 900 python scripts/vllm_crosscheck.py check --configs tiny > gpurun_out/xcheck.log 2>&1; echo "xcheck rc=$?" ;;
+    vllmbench) timeout 1500 python scripts/vllm_crosscheck.py bench --batches 32 64 > gpurun_out/vllmbench.log 2>&1; echo "vllmbench rc=$?" ;;
+    sampbench) timeout 300 python scripts/sampler_bench.py > gpurun_out/sampler_bench.log 2>&1; echo "sampbench rc=$?" ;;
+    bench_cfg0) timeout 600 python bench.py --model 125m --batch 1 --cpu-layers 12 --steps 5 --warmup 3 > gpurun_out/bench_cfg0.log 2> gpurun_out/bench_cfg0.err; echo "bench_cfg0 rc=$?" ;;
     *) echo "unknown stage $st" ;;
   esac
 done

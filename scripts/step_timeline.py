@@ -1,0 +1,81 @@
+"""In-situ timeline of ONE decode step (CUDA-graph replay, PDL) from a -DTGIS_STEP_TIMELINE build:
+    python scripts/build_variant.py stl -DTGIS_STEP_TIMELINE
+    TGIS_ENGINE_LIB=$PWD/vllm_tgis_adapter_b200/lib/libtgis_engine_stl.so python scripts/step_timeline.py [layers] [batch] [prompt]
+CTA 0 / thread 0 of every launch stamps %globaltimer at entry, after griddepcontrol.wait and at exit.  Printed per kernel
+of the last decode step: start (us from the step's first entry), time waiting for its dependency, body time, and the gap
+between the previous kernel's exit and this kernel's dependency-wait return (= exposed boundary latency)."""
+import ctypes as C
+import dataclasses
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from vllm_tgis_adapter_b200.engine import _lib  # noqa: E402
+from vllm_tgis_adapter_b200.engine.core import PRESETS, NativeEngine, make_sampling_params  # noqa: E402
+from vllm_tgis_adapter_b200.engine.loader import load_synthetic_weights, rope_cos_sin  # noqa: E402
+
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+P = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+lib = _lib.load_library()
+rc = lib.tgis_k_step_timeline_enable()
+assert rc == 0, f"not a -DTGIS_STEP_TIMELINE build (rc={rc})"
+mc = dataclasses.replace(PRESETS["llama3-8b"], n_layers=L, max_model_len=1024)
+eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=max(2048, B), kv_cache_bytes=(B * (P + 96) * 2 * L * 8 * 128 * 2 * 5) // 4)
+load_synthetic_weights(eng, mc, 0, 0)
+eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
+rs = np.random.RandomState(0)
+prompts = [rs.randint(1000, mc.vocab - 1000, size=P).tolist() for _ in range(B)]
+G = 40
+sp = make_sampling_params(greedy=True, max_tokens=G, min_tokens=G)
+for i, p in enumerate(prompts):
+    eng.add_request(f"r{i}", p, sp)
+eng.run_until_idle()
+st = eng.status()
+buf = np.zeros(8 + 4096 * 4, dtype=np.uint64)
+assert lib.tgis_k_step_timeline_read(buf.ctypes.data_as(C.POINTER(C.c_uint64))) == 0
+n = int(buf[0])
+recs = buf[8:].reshape(4096, 4)
+idx = [(i % 4096) for i in range(max(0, n - 4096), n)]
+rows = [tuple(int(x) for x in recs[i]) for i in idx if recs[i][3] != 0]
+rows.sort(key=lambda r: r[1])
+NAMES = {1: "norm", 2: "gemm", 3: "attn_decode", 4: "attn_merge", 5: "attn_prefill", 6: "sampler", 9: "ar_norm"}
+# last decode step = everything after the second-to-last sampler record
+samp = [i for i, r in enumerate(rows) if (r[0] & 0xff) == 6]
+lo = samp[-2] + 1 if len(samp) >= 2 else 0
+step = rows[lo:samp[-1] + 1]
+t0 = step[0][1]
+print(f"decode ms/step (engine events) = {st.gpu_decode_ms / max(st.decode_steps, 1):.4f}; graph launches {st.graph_launches}; "
+      f"{len(step)} kernel launches in the last step, span {(step[-1][3] - t0) / 1e3:.1f} us")
+print(f"{'kernel':>14} {'N':>7} {'start':>8} {'wait':>7} {'body':>7} {'gap_prev_exit->waited':>22}")
+prev_exit = None
+agg = {}
+out_rows = []
+for kid, te, tw, tx in step:
+    name = NAMES.get(kid & 0xff, str(kid & 0xff))
+    Nn = kid >> 8
+    tw_ = tw if tw else te
+    gap = (tw_ - prev_exit) / 1e3 if prev_exit else 0.0
+    key = f"{name}:{Nn}" if Nn else name
+    a = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
+    a[0] += 1
+    a[1] += (tw_ - te) / 1e3
+    a[2] += (tx - tw_) / 1e3
+    a[3] += gap
+    out_rows.append({"kernel": key, "start_us": (te - t0) / 1e3, "wait_us": (tw_ - te) / 1e3, "body_us": (tx - tw_) / 1e3,
+                     "gap_us": gap})
+    prev_exit = tx
+for r in out_rows[: 2 + 8 * 2]:   # the first two layers in detail
+    print(f"{r['kernel']:>14} {'':>7} {r['start_us']:8.1f} {r['wait_us']:7.1f} {r['body_us']:7.1f} {r['gap_us']:22.1f}")
+print("---- per kernel type over the whole step: launches, mean wait / body / gap (us), sum of body+gap (us)")
+tot = 0.0
+for k, (c, w, b_, g) in sorted(agg.items(), key=lambda kv: -(kv[1][2] + kv[1][3])):
+    print(f"{k:>18} x{c:3d}  wait {w / c:6.2f}  body {b_ / c:6.2f}  gap {g / c:6.2f}   sum {b_ + g:8.1f}")
+    tot += b_ + g
+print(f"sum of body+gap = {tot:.1f} us")
+Path("gpurun_out").mkdir(exist_ok=True)
+Path("gpurun_out/step_timeline.json").write_text(json.dumps({"layers": L, "batch": B, "prompt": P, "rows": out_rows, "agg": agg}))
+eng.close()

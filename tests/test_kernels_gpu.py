@@ -470,7 +470,7 @@ def test_sampler_bf16_logits_ties_rank_and_argmax(g, V):
         np.testing.assert_allclose(out["topn_lps"][i][:k], o["topn_logprobs"], atol=1e-4)
         for j in range(k):   # ids agree wherever the values are not tied; tied values are listed lowest id first
             if out["topn_ids"][i][j] != o["topn_ids"][j]:
-                assert abs(out["topn_lps"][i][j] - o["topn_logprobs"][j]) < 1e-7
+                assert abs(out["topn_lps"][i][j] - o["topn_logprobs"][j]) < 1e-6   # 2 fp32 ulps at |lp| ~ 6
     assert out["token"][2] == 31 and out["rank"][2] == 3 and ties >= 1
 
 
@@ -509,8 +509,10 @@ def test_sampler_bf16_logits_sampling_paths_match_fp32_view(g):
                 rows["len_decay_factor"][i] = f
     a = g.run_sampler(lb.cuda(), rows, bitmap.cuda())
     b = g.run_sampler(lb.float().cuda(), rows, bitmap.clone().cuda())
-    for f in ("token", "logprob", "rank", "n_topn", "topn_ids", "topn_lps"):
+    for f in ("token", "logprob", "rank", "n_topn"):
         assert np.array_equal(a[f], b[f]), f
+    for f in ("topn_ids", "topn_lps"):      # entries beyond n_topn are not written
+        assert np.array_equal(a[f][:, :2], b[f][:, :2]), f
     for i, c in enumerate(cases):
         o = sample_row(lb[i].float(), c, seen[i] if c.repetition_penalty != 1.0 else None)
         assert int(a["token"][i]) == o["token"] or bool(o["allowed"][int(a["token"][i])])

@@ -21,6 +21,8 @@
 
 namespace tgis {
 
+TGIS_STL_DEFINE(attention)
+
 constexpr int DEC_TOK = DECODE_SPLIT;        // tokens per split (8 KV blocks streamed through a 4-stage ring)
 constexpr int TILE_BYTES = KV_BLOCK * HEAD_DIM * 2;  // 8192
 static_assert(DEC_TOK == DECODE_SPLIT, "split size mismatch");
@@ -113,6 +115,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
     fence_barrier_init();
   }
   __syncwarp();
+  STL_ENTER(3);
   griddep_launch();
   // ---- item list: host-written for this step, not produced by a preceding kernel -> readable before griddep_wait
   const int4* it4 = reinterpret_cast<const int4*>(items);  // record e = it4[2e] (q_row, kv_len, seq_split, -), it4[2e+1] (blocks)
@@ -177,6 +180,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   };
 
   griddep_wait();  // q and the newest cache slot come from the preceding kernels
+  STL_WAITED();
   issue_q(c_it, f % n_kv);
 #pragma unroll
   for (int i = 0; i < DEC_RING; ++i) issue_tile();
@@ -344,6 +348,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
     }
     c_it = c_nxt;
   }
+  STL_EXIT();
 }
 
 // Split merge: one CTA per (decode sequence, kv head) with more than one split, thread = dim.  Reads the partials in
@@ -354,12 +359,14 @@ attn_merge_kernel(const AttnSeq* __restrict__ seqs, const int32_t* __restrict__ 
                   const float* __restrict__ part_o, const float* __restrict__ part_ml,
                   __nv_bfloat16* __restrict__ out, int out_ld, int n_kv) {
   __shared__ float ml_s[64 * G * 2];
+  STL_ENTER(4);
   griddep_launch();
   const int sidx = blockIdx.x, kvh = blockIdx.y, d = threadIdx.x;
   const AttnSeq sq = seqs[seq_ids ? seq_ids[sidx] : sidx];  // host-written
   const int n_splits = (sq.kv_len + DEC_TOK - 1) / DEC_TOK;
   if (n_splits == 1) return;  // the streaming kernel wrote the row itself
   griddep_wait();
+  STL_WAITED();
   const size_t pbase = (size_t)(sidx * n_kv + kvh) * max_splits;
   float m_f[G], l_f[G], o_f[G];
 #pragma unroll
@@ -406,6 +413,7 @@ attn_merge_kernel(const AttnSeq* __restrict__ seqs, const int32_t* __restrict__ 
   __nv_bfloat16* o_dst = out + (size_t)sq.q_start * out_ld + (size_t)kvh * G * HEAD_DIM;
 #pragma unroll
   for (int g = 0; g < G; ++g) o_dst[g * HEAD_DIM + d] = __float2bfloat16_rn(o_f[g] / l_f[g]);
+  STL_EXIT();
 }
 
 template <int G>

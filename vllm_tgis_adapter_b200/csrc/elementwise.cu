@@ -12,6 +12,8 @@
 
 namespace tgis {
 
+TGIS_STL_DEFINE(elementwise)
+
 struct alignas(16) BF8 {
   __nv_bfloat16 v[8];
 };
@@ -68,8 +70,10 @@ __global__ void __launch_bounds__(NORM_THREADS)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int hidden, float eps) {
   __shared__ float red[NORM_THREADS / 32];
+  STL_ENTER(1);
   griddep_launch();
   griddep_wait();
+  STL_WAITED();
   const size_t base = (size_t)blockIdx.x * hidden;
   const int nvec = hidden / 8;
   BF8 z[NORM_MAX_VEC];
@@ -109,6 +113,7 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
       reinterpret_cast<BF8*>(out + base)[i] = o;
     }
   }
+  STL_EXIT();
 }
 
 cudaError_t rmsnorm_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
@@ -155,8 +160,10 @@ ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, const uint32_t* __restrict__ 
                       __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ w,
                       __nv_bfloat16* __restrict__ out, int hidden, float eps) {
   __shared__ float red[NORM_THREADS / 32];
+  STL_ENTER(9);
   griddep_launch();
   griddep_wait();  // this rank's partial (previous kernel) is complete; the step's metadata copy has landed
+  STL_WAITED();
   // The exchange epoch = (value staged by the host for this step) + (index of the exchange inside the step): the
   // launch arguments are the same for every replay of a captured step, so tensor-parallel decode steps can be CUDA graphs.
   const uint32_t epoch = __ldg(epoch_base) + epoch_idx;
@@ -243,6 +250,7 @@ ar_add_rmsnorm_kernel(ArPeers P, int tp, int rank, const uint32_t* __restrict__ 
       reinterpret_cast<BF8*>(out + base)[i] = o;
     }
   }
+  STL_EXIT();
 }
 
 cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, const uint32_t* epoch_base, uint32_t epoch_idx,

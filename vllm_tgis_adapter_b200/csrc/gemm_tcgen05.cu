@@ -28,6 +28,8 @@
 
 namespace tgis {
 
+TGIS_STL_DEFINE(gemm)
+
 constexpr int GEMM_BN = 128;  // weight rows per tile (UMMA_M)
 constexpr int GEMM_BK = 64;   // k per stage (one 128-byte swizzle row of bf16)
 constexpr int GEMM_THREADS = 192;
@@ -219,6 +221,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   int* flag_smem = reinterpret_cast<int*>(tmem_base_smem + 1);
 
   const int warp = threadIdx.x >> 5;
+  STL_ENTER(2 | (N << 8));
   if (threadIdx.x == 0) TL(0);  // kernel entry
   const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   const int t_tiles = (T + BT - 1) / BT;
@@ -317,6 +320,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       TL(2);           // weight prefetch issued
       griddep_wait();  // activations (and everything the epilogue will touch) are now final
       TL(3);           // dependency wait returned
+      if (threadIdx.x == 0) STL_WAITED();
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < n_kb; ++i) {
@@ -611,6 +615,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TL(9);  // all roles done
+  STL_EXIT();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

@@ -15,6 +15,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int gemm_pick_bt(int T);
 size_t gemm_workspace_bytes(int num_sms);
 int gemm_timeline_read(unsigned long long* out64);  // debug builds (-DTGIS_GEMM_TIMELINE) only
+// -DTGIS_STEP_TIMELINE builds: point every translation unit's kernels at the timeline buffer (ptx.cuh); else -2
+int gemm_set_step_timeline(unsigned long long* buf);
+int elementwise_set_step_timeline(unsigned long long* buf);
+int attention_set_step_timeline(unsigned long long* buf);
+int sampler_set_step_timeline(unsigned long long* buf);
 // Decode-shaped successor of a GEMM launch: lets the running kernel pull the first `kb_prefetch` weight boxes of every
 // CTA of the NEXT GEMM into L2 while its own tail drains (kb_prefetch == 0: off).
 struct GemmNext {

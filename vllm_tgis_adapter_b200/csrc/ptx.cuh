@@ -222,4 +222,39 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
+// ---------------------------------------------------------------- in-situ step timeline (debug builds only)
+// -DTGIS_STEP_TIMELINE: CTA 0 / thread 0 of every kernel launch appends {kernel id, %globaltimer at entry, after the
+// grid-dependency wait, at exit} to a device buffer (scripts/step_timeline.py) -- shows, inside CUDA-graph replays with
+// PDL, where a decode step's time goes.  Release builds compile the marks away.
+#ifdef TGIS_STEP_TIMELINE
+__device__ __forceinline__ unsigned long long stl_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TGIS_STL_DEFINE(prefix)                                                                       \
+  static __device__ unsigned long long* g_stl = nullptr;                                              \
+  int prefix##_set_step_timeline(unsigned long long* p) {                                             \
+    return cudaMemcpyToSymbol(g_stl, &p, sizeof(p)) == cudaSuccess ? 0 : -1;                          \
+  }
+#define STL_ENTER(kid)                                                                                \
+  int _stl = -1;                                                                                      \
+  if (g_stl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {                   \
+    _stl = (int)(atomicAdd(g_stl, 1ull) & 4095ull);                                                   \
+    unsigned long long* _r = g_stl + 8 + _stl * 4;                                                    \
+    _r[0] = (unsigned long long)(kid);                                                                \
+    _r[1] = stl_timer();                                                                              \
+    _r[2] = 0;                                                                                        \
+    _r[3] = 0;                                                                                        \
+  }
+#define STL_WAITED() do { if (_stl >= 0) g_stl[8 + _stl * 4 + 2] = stl_timer(); } while (0)
+#define STL_EXIT() do { if (_stl >= 0) g_stl[8 + _stl * 4 + 3] = stl_timer(); } while (0)
+#else
+#define TGIS_STL_DEFINE(prefix) \
+  int prefix##_set_step_timeline(unsigned long long*) { return -2; }
+#define STL_ENTER(kid) do {} while (0)
+#define STL_WAITED() do {} while (0)
+#define STL_EXIT() do {} while (0)
+#endif
+
 }  // namespace tgis

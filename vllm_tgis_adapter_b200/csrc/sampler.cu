@@ -25,6 +25,8 @@ namespace cg = cooperative_groups;
 
 namespace tgis {
 
+TGIS_STL_DEFINE(sampler)
+
 constexpr int SAMP_CL = 8;  // CTAs (SMs) per row
 constexpr int SAMP_THREADS = 1024;
 constexpr int SAMP_WARPS = SAMP_THREADS / 32;
@@ -384,8 +386,10 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
   __shared__ float xch[4];
   int* histi = reinterpret_cast<int*>(histf);
   int* histsumi = reinterpret_cast<int*>(histsumf);
+  STL_ENTER(6);
   griddep_launch();
   griddep_wait();
+  STL_WAITED();
 
   const int r = blockIdx.x / SAMP_CL;
   const int crank = (int)cg::this_cluster().block_rank();
@@ -573,6 +577,7 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
     if (c.p.seq_slot >= 0 && token >= 0)
       atomicOr(&seen_bitmap[(size_t)c.p.seq_slot * bitmap_words + (token >> 5)], 1u << (token & 31));
   }
+  STL_EXIT();
 }
 
 cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int vocab, const SampleRow* rows, int n_rows,

@@ -51,6 +51,29 @@ struct Tmp {
 extern "C" {
 
 int tgis_k_gemm_timeline(uint64_t* out64) { return gemm_timeline_read((unsigned long long*)out64); }
+
+// Step timeline (debug builds, -DTGIS_STEP_TIMELINE): buffer = [8 header words: [0] = records written][4096 x 4 words]
+static unsigned long long* g_step_tl_buf = nullptr;
+int tgis_k_step_timeline_enable(void) {
+  if (!g_step_tl_buf) {
+    if (cudaMalloc(&g_step_tl_buf, sizeof(unsigned long long) * (8 + 4096 * 4)) != cudaSuccess) return kfail("cudaMalloc");
+  }
+  KCK(cudaMemset(g_step_tl_buf, 0, sizeof(unsigned long long) * (8 + 4096 * 4)));
+  int rc = gemm_set_step_timeline(g_step_tl_buf);
+  if (rc != 0) return rc;  // -2: not a timeline build
+  elementwise_set_step_timeline(g_step_tl_buf);
+  attention_set_step_timeline(g_step_tl_buf);
+  sampler_set_step_timeline(g_step_tl_buf);
+  return 0;
+}
+// out: [0] = number of records since the last read, then 4096 x {kernel id, t_entry, t_waited, t_exit} (ns); resets
+int tgis_k_step_timeline_read(uint64_t* out) {
+  if (!g_step_tl_buf) return kfail("step timeline not enabled");
+  KCK(cudaDeviceSynchronize());
+  KCK(cudaMemcpy(out, g_step_tl_buf, sizeof(unsigned long long) * (8 + 4096 * 4), cudaMemcpyDeviceToHost));
+  KCK(cudaMemset(g_step_tl_buf, 0, sizeof(unsigned long long) * 8));
+  return 0;
+}
 int tgis_k_sizeof_sample_row(void) { return (int)sizeof(SampleRow); }
 int tgis_k_sizeof_sample_out(void) { return (int)sizeof(SampleOut); }
 int tgis_k_kv_block(void) { return KV_BLOCK; }
