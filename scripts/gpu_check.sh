@@ -36,6 +36,8 @@ for st in $STAGES; do
     ctasweep) timeout 300 python scripts/gemm_cta_sweep.py > gpurun_out/gemm_cta_sweep.log 2>&1; echo "ctasweep rc=$?" ;;
     attnbench) timeout 300 python scripts/attn_bench.py > gpurun_out/attn_bench.log 2>&1; echo "attnbench rc=$?" ;;
     gemmbench) timeout 600 python scripts/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; echo "gemmbench rc=$?" ;;
+    retest) timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_parity_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "bf16_logits or vllm_fixture or preemption or abort" > gpurun_out/retest.log 2>&1; echo "retest rc=$?" ;;
+    stl) TGIS_DEBUG_LAUNCH=1 TGIS_ENGINE_LIB=$PWD/vllm_tgis_adapter_b200/lib/libtgis_engine_stl.so timeout 300 python scripts/step_timeline.py 32 32 512 > gpurun_out/step_timeline_b32.log 2>&1; echo "stl rc=$?"; TGIS_DEBUG_LAUNCH=1 TGIS_ENGINE_LIB=$PWD/vllm_tgis_adapter_b200/lib/libtgis_engine_stl.so timeout 300 python scripts/step_timeline.py 32 64 512 > gpurun_out/step_timeline_b64.log 2>&1 ;;
     xcheck) timeout 1500 python scripts/vllm_crosscheck.py check > gpurun_out/xcheck.log 2>&1; echo "xcheck rc=$?" ;;
     xcheck_small) timeout 900 python scripts/vllm_crosscheck.py check --configs tiny > gpurun_out/xcheck.log 2>&1; echo "xcheck rc=$?" ;;
     vllmbench) timeout 1500 python scripts/vllm_crosscheck.py bench --batches 32 64 > gpurun_out/vllmbench.log 2>&1; echo "vllmbench rc=$?" ;;

@@ -42,12 +42,21 @@ recs = buf[8:].reshape(4096, 4)
 idx = [(i % 4096) for i in range(max(0, n - 4096), n)]
 rows = [tuple(int(x) for x in recs[i]) for i in idx if recs[i][3] != 0]
 rows.sort(key=lambda r: r[1])
-NAMES = {1: "norm", 2: "gemm", 3: "attn_decode", 4: "attn_merge", 5: "attn_prefill", 6: "sampler", 9: "ar_norm"}
+NAMES = {1: "norm", 2: "gemm", 3: "attn_decode", 4: "attn_merge", 5: "attn_prefill", 6: "sampler", 8: "gather", 9: "ar_norm"}
 # last decode step = everything after the second-to-last sampler record
 samp = [i for i, r in enumerate(rows) if (r[0] & 0xff) == 6]
 lo = samp[-2] + 1 if len(samp) >= 2 else 0
 step = rows[lo:samp[-1] + 1]
 t0 = step[0][1]
+# step-to-step: sampler exit of step k -> first kernel entry / first dependency-wait return of step k+1, and the period
+gaps = []
+for a, b in zip(samp[:-1], samp[1:]):
+    nxt = rows[a + 1]
+    gaps.append(((nxt[1] - rows[a][3]) / 1e3, ((nxt[2] or nxt[1]) - rows[a][3]) / 1e3, (rows[b][3] - rows[a][3]) / 1e3))
+if gaps:
+    g = np.array(gaps[-20:])
+    print(f"last {len(g)} decode steps: sampler exit -> next step's first kernel ENTRY {g[:, 0].mean():.1f} us (min {g[:, 0].min():.1f}), "
+          f"-> first kernel RUNNING {g[:, 1].mean():.1f} us; step period {g[:, 2].mean():.1f} us")
 print(f"decode ms/step (engine events) = {st.gpu_decode_ms / max(st.decode_steps, 1):.4f}; graph launches {st.graph_launches}; "
       f"{len(step)} kernel launches in the last step, span {(step[-1][3] - t0) / 1e3:.1f} us")
 print(f"{'kernel':>14} {'N':>7} {'start':>8} {'wait':>7} {'body':>7} {'gap_prev_exit->waited':>22}")

@@ -39,14 +39,17 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ------------------------------------------------------------------------------------------------ embedding / gather
 __global__ void gather_rows_kernel(const int32_t* __restrict__ idx, const __nv_bfloat16* __restrict__ table,
                                    __nv_bfloat16* __restrict__ out, int hidden, int n_table_rows) {
+  STL_ENTER(8);
   griddep_launch();
   griddep_wait();
+  STL_WAITED();
   const int t = blockIdx.x;
   int row = idx[t];
   if (row < 0 || row >= n_table_rows) row = 0;  // padding rows: any valid row (never consumed)
   const BF8* src = reinterpret_cast<const BF8*>(table + (size_t)row * hidden);
   BF8* dst = reinterpret_cast<BF8*>(out + (size_t)t * hidden);
   for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+  STL_EXIT();
 }
 
 cudaError_t embed_gather_launch(const int32_t* token_ids, const __nv_bfloat16* table, __nv_bfloat16* out, int T,

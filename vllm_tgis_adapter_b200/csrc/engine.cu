@@ -148,7 +148,8 @@ struct LayerW {
 // kernel sequence on their shard.  (The data path itself only exchanges through NCCL.)
 struct StepHeader {
   int32_t T, n_dec, n_tiles, R, max_dec_kv, S;
-  int32_t graphable, pad;  // graphable: replay (or capture) the CUDA graph keyed by (S, KV splits) instead of launching
+  int32_t graphable;     // replay (or capture) the CUDA graph keyed by (S, KV splits, samp_complex) instead of launching
+  int32_t samp_complex;  // some sampled row needs selection passes (sampling): decides the sampler's cluster size
   uint64_t copy_bytes;
 };
 struct ShmCtl {
@@ -303,8 +304,13 @@ struct tgis_engine {
   std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
   std::unordered_map<uint64_t, long long> graph_nodes;
   long long n_graph_launches = 0;
+  bool debug_launch = false;          // TGIS_DEBUG_LAUNCH=1: host time spent inside cudaGraphLaunch, printed at destroy
+  double graph_launch_host_s = 0;
 
   ~tgis_engine() {
+    if (debug_launch && n_graph_launches > 0)
+      fprintf(stderr, "[tgis] rank %d: %lld graph launches, %.1f us host time per cudaGraphLaunch\n", rank,
+              n_graph_launches, 1e6 * graph_launch_host_s / (double)n_graph_launches);
     if (h_stage) cudaFreeHost(h_stage);
     if (h_samp_out) cudaFreeHost(h_samp_out);
     if (h_plp_out) cudaFreeHost(h_plp_out);
@@ -359,6 +365,7 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_TP_FUSED_AR")) tp_fused_ar = atoi(e) != 0;
     if (const char* e = getenv("TGIS_LOGITS_FP32")) logits_bf16 = atoi(e) == 0;
     if (const char* e = getenv("TGIS_TP_TIMEOUT_S")) tp_timeout_s = atof(e);
+    if (const char* e = getenv("TGIS_DEBUG_LAUNCH")) debug_launch = atoi(e) != 0;
     if (const char* e = getenv("TGIS_TP_GRAPHS")) tp_graphs = atoi(e) != 0;
     lsz = logits_bf16 ? 2 : 4;
 
@@ -789,7 +796,7 @@ struct tgis_engine {
   // quantity from the device staging buffer, so the same sequence can be captured once into a CUDA graph and replayed.
   size_t items_off(int S) const { return (off_bt + sizeof(int32_t) * (size_t)S * bt_stride + 255) / 256 * 256; }
 
-  void launch_step(size_t copy_bytes, int T, int n_dec, int n_tiles, int R, int max_dec_kv, int S) {
+  void launch_step(size_t copy_bytes, int T, int n_dec, int n_tiles, int R, int max_dec_kv, int S, int samp_complex) {
     const tgis_config& c = cfg;
     const int H = c.hidden, F = Fl, V = c.vocab;  // F: local ffn shard
     CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
@@ -890,7 +897,7 @@ struct tgis_engine {
       }
       if (rank == 0) {
         CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words,
-                          samp_scratch.p, d_samp_out.p, stream));
+                          samp_scratch.p, d_samp_out.p, stream, samp_complex, num_sms));
         ++n_launches;
         CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
       }
@@ -903,11 +910,11 @@ struct tgis_engine {
   // and the tensor-parallel workers run the same function on the same header.
   void exec_step(const StepHeader& h) {
     if (!h.graphable) {
-      launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S);
+      launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S, h.samp_complex);
       return;
     }
     const int max_splits = (h.max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
-    const uint64_t key = ((uint64_t)h.S << 16) | (uint64_t)max_splits;
+    const uint64_t key = ((uint64_t)(h.samp_complex ? 1 : 0) << 40) | ((uint64_t)h.S << 16) | (uint64_t)max_splits;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
       if (graphs.size() >= 64) {
@@ -918,7 +925,7 @@ struct tgis_engine {
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
       try {
-        launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S);
+        launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S, h.samp_complex);
       } catch (...) {
         cudaStreamEndCapture(stream, &g);
         if (g) cudaGraphDestroy(g);
@@ -932,7 +939,9 @@ struct tgis_engine {
       n_launches = launches_before;
       it = graphs.emplace(key, ge).first;
     }
+    const double t_gl = debug_launch ? now_s() : 0.0;
     CK(cudaGraphLaunch(it->second, stream));
+    if (debug_launch) graph_launch_host_s += now_s() - t_gl;
     n_launches += graph_nodes[key];
     ++n_graph_launches;
   }
@@ -941,7 +950,7 @@ struct tgis_engine {
   int run_batch(std::vector<Sched>& batch) {
     const tgis_config& c = cfg;
     const int H = c.hidden, V = c.vocab;
-    int T = 0, n_dec = 0, n_tiles = 0, R = 0, max_dec_kv = 0;
+    int T = 0, n_dec = 0, n_tiles = 0, R = 0, max_dec_kv = 0, samp_complex = 0;
     struct PromptRow {
       int row, target, pos;
       Request* r;
@@ -995,6 +1004,7 @@ struct tgis_engine {
         const int n_out = r.n_out();
         row.flags = (sp.greedy ? SAMPLE_GREEDY : 0) | (sp.num_logprobs > 0 ? SAMPLE_LOGPROBS : 0) |
                     ((sp.typical_p > 0.f && sp.typical_p < 1.f) ? SAMPLE_TYPICAL : 0);
+        if (!(row.flags & SAMPLE_GREEDY) || (row.flags & SAMPLE_TYPICAL)) samp_complex = 1;
         row.n_topn = std::min<int>(sp.num_logprobs > 0 ? sp.num_logprobs : 0, MAX_TOPN);
         row.temperature = sp.greedy ? 1.f : sp.temperature;
         row.top_k = sp.greedy ? 0 : sp.top_k;
@@ -1033,7 +1043,7 @@ struct tgis_engine {
     const size_t copy_bytes = items_off(S) + sizeof(DecItem) * (1 + (size_t)n_dec * max_splits_step);
     CK(cudaEventRecord(ev0, stream));
     const bool graphable = cfg.use_cuda_graphs && (tp == 1 || tp_graphs) && !profiling && n_tiles == 0 && n_dec == S && R == S;
-    StepHeader hdr{T, n_dec, n_tiles, R, max_dec_kv, S, graphable ? 1 : 0, 0, (uint64_t)copy_bytes};
+    StepHeader hdr{T, n_dec, n_tiles, R, max_dec_kv, S, graphable ? 1 : 0, samp_complex, (uint64_t)copy_bytes};
     if (tp > 1) {
       // exchange epochs of this step = staged base + index inside the step (ar_add_rmsnorm_kernel)
       uint32_t* eb = hs<uint32_t>(off_epoch);
@@ -1105,7 +1115,7 @@ struct tgis_engine {
         CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, m, H, stream));
         gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, m, V, H, logits_bf16 ? 0 : 1);
         CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words,
-                          samp_scratch.p, d_samp_out.p, stream));
+                          samp_scratch.p, d_samp_out.p, stream, /*any_complex=*/0, num_sms));
         n_launches += 2;
         CK(cudaMemcpyAsync(h_plp_out, d_samp_out.p, sizeof(SampleOut) * m, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));

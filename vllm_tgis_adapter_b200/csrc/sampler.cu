@@ -27,9 +27,10 @@ namespace tgis {
 
 TGIS_STL_DEFINE(sampler)
 
-constexpr int SAMP_CL = 8;  // CTAs (SMs) per row
+constexpr int SAMP_MAX_CL = 8;  // CTAs (SMs) per row: 1, 2, 4 or 8, chosen per launch (sampler_launch)
 constexpr int SAMP_THREADS = 1024;
 constexpr int SAMP_WARPS = SAMP_THREADS / 32;
+constexpr float SAMP_FIX = 1073741824.0f;  // 2^30: probabilities are accumulated as fixed-point integers (see below)
 
 // LT = logits element type: __nv_bfloat16 on the product path (vLLM's lm_head emits model-dtype logits and the sampler
 // casts them to fp32: vllm v1/sample/sampler.py:91 -- every bf16 value is exactly representable), float for the
@@ -90,7 +91,7 @@ __device__ __forceinline__ float process(const RowCtx<LT>& c, int i, float x) {
   return y;
 }
 
-// ---------------------------------------------------------------- block reductions (1024 threads)
+// ---------------------------------------------------------------- block reductions (1024 threads, result in every thread)
 struct MaxSum {
   float m, s;
 };
@@ -132,12 +133,16 @@ __device__ __forceinline__ ValIdx vi_better(ValIdx a, ValIdx b) {
   if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
   return a;
 }
-__device__ ValIdx block_argmax(ValIdx v, float* redf, int* redi) {
+__device__ __forceinline__ ValIdx warp_argmax(ValIdx v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ValIdx t{__shfl_xor_sync(0xffffffffu, v.v, o), __shfl_xor_sync(0xffffffffu, v.i, o)};
     v = vi_better(v, t);
   }
+  return v;
+}
+__device__ ValIdx block_argmax(ValIdx v, float* redf, int* redi) {
+  v = warp_argmax(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __syncthreads();
   if (l == 0) {
@@ -145,13 +150,7 @@ __device__ ValIdx block_argmax(ValIdx v, float* redf, int* redi) {
     redi[w] = v.i;
   }
   __syncthreads();
-  ValIdx r{redf[l], redi[l]};
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ValIdx t{__shfl_xor_sync(0xffffffffu, r.v, o), __shfl_xor_sync(0xffffffffu, r.i, o)};
-    r = vi_better(r, t);
-  }
-  return r;
+  return warp_argmax(ValIdx{redf[l], redi[l]});
 }
 __device__ float block_sumf(float v, float* red) {
 #pragma unroll
@@ -178,52 +177,82 @@ __device__ int block_sumi(int v, int* red) {
   return r;
 }
 
-// ---------------------------------------------------------------- cluster reductions (SAMP_CL CTAs, rank order)
-// xch: 4 words of shared memory per CTA at the same offset in every CTA of the cluster
+// ---------------------------------------------------------------- cluster exchange (ncl CTAs, combined in rank order)
+// Every exchange costs ONE cluster barrier: the 4-word slots rotate (exchange e uses slot e & 1), and a CTA can only
+// overwrite slot e & 1 for exchange e + 2 after passing the barrier of exchange e + 1, which every peer reaches only
+// after it has finished reading exchange e.  The histograms of the radix selects rotate the same way.  A launch with
+// one CTA per row (ncl == 1) degenerates to block barriers.
+struct Cl {
+  int ncl, rank;
+  int xe, he;  // exchange / histogram round counters
+  __device__ void sync() const {
+    if (ncl > 1) cg::this_cluster().sync();
+    else __syncthreads();
+  }
+};
 template <class T>
-__device__ __forceinline__ T dsmem_read(T* local, int rank) {
-  return *cg::this_cluster().map_shared_rank(local, rank);
+__device__ __forceinline__ T dsmem_read(const Cl& c, T* local, int rank) {
+  return c.ncl > 1 ? *cg::this_cluster().map_shared_rank(local, rank) : *local;
 }
-__device__ MaxSum cluster_maxsum(MaxSum v, float* red, float* xch) {
+struct Xch4 {
+  float a, b, c, d;
+};
+// publish this CTA's 4 words (already block-reduced: every thread holds them) and return a functor-friendly snapshot
+// of all ranks' words through `get(r)`
+struct XchView {
+  const Cl* cl;
+  float* slot;
+  __device__ Xch4 get(int r) const {
+    return Xch4{dsmem_read(*cl, slot, r), dsmem_read(*cl, slot + 1, r), dsmem_read(*cl, slot + 2, r),
+                dsmem_read(*cl, slot + 3, r)};
+  }
+};
+__device__ XchView cl_publish(Cl& c, float (*xch)[4], Xch4 v) {
+  float* slot = xch[c.xe & 1];
+  ++c.xe;
+  if (threadIdx.x == 0) {
+    slot[0] = v.a;
+    slot[1] = v.b;
+    slot[2] = v.c;
+    slot[3] = v.d;
+  }
+  c.sync();
+  return XchView{&c, slot};
+}
+__device__ MaxSum cluster_maxsum(Cl& c, MaxSum v, float* red, float (*xch)[4]) {
   v = block_maxsum(v, red);
-  if (threadIdx.x == 0) {
-    xch[0] = v.m;
-    xch[1] = v.s;
+  const XchView w = cl_publish(c, xch, Xch4{v.m, v.s, 0.f, 0.f});
+  Xch4 t = w.get(0);
+  MaxSum acc{t.a, t.b};
+  for (int r = 1; r < c.ncl; ++r) {
+    t = w.get(r);
+    acc = ms_combine(acc, MaxSum{t.a, t.b});
   }
-  cg::this_cluster().sync();
-  MaxSum acc{dsmem_read(xch, 0), dsmem_read(xch + 1, 0)};
-  for (int r = 1; r < SAMP_CL; ++r) acc = ms_combine(acc, MaxSum{dsmem_read(xch, r), dsmem_read(xch + 1, r)});
-  cg::this_cluster().sync();  // xch may be rewritten
   return acc;
 }
-__device__ ValIdx cluster_argmax(ValIdx v, float* redf, int* redi, float* xch) {
+__device__ ValIdx cluster_argmax(Cl& c, ValIdx v, float* redf, int* redi, float (*xch)[4]) {
   v = block_argmax(v, redf, redi);
-  if (threadIdx.x == 0) {
-    xch[0] = v.v;
-    xch[1] = __int_as_float(v.i);
+  const XchView w = cl_publish(c, xch, Xch4{v.v, __int_as_float(v.i), 0.f, 0.f});
+  Xch4 t = w.get(0);
+  ValIdx acc{t.a, __float_as_int(t.b)};
+  for (int r = 1; r < c.ncl; ++r) {
+    t = w.get(r);
+    acc = vi_better(acc, ValIdx{t.a, __float_as_int(t.b)});
   }
-  cg::this_cluster().sync();
-  ValIdx acc{dsmem_read(xch, 0), __float_as_int(dsmem_read(xch + 1, 0))};
-  for (int r = 1; r < SAMP_CL; ++r) acc = vi_better(acc, ValIdx{dsmem_read(xch, r), __float_as_int(dsmem_read(xch + 1, r))});
-  cg::this_cluster().sync();
   return acc;
 }
-__device__ float cluster_sumf(float v, float* red, float* xch) {
+__device__ float cluster_sumf(Cl& c, float v, float* red, float (*xch)[4]) {
   v = block_sumf(v, red);
-  if (threadIdx.x == 0) xch[0] = v;
-  cg::this_cluster().sync();
-  float acc = dsmem_read(xch, 0);
-  for (int r = 1; r < SAMP_CL; ++r) acc += dsmem_read(xch, r);
-  cg::this_cluster().sync();
+  const XchView w = cl_publish(c, xch, Xch4{v, 0.f, 0.f, 0.f});
+  float acc = w.get(0).a;
+  for (int r = 1; r < c.ncl; ++r) acc += w.get(r).a;
   return acc;
 }
-__device__ int cluster_sumi(int v, int* red, float* xch) {
+__device__ int cluster_sumi(Cl& c, int v, int* red, float (*xch)[4]) {
   v = block_sumi(v, red);
-  if (threadIdx.x == 0) xch[0] = __int_as_float(v);
-  cg::this_cluster().sync();
+  const XchView w = cl_publish(c, xch, Xch4{__int_as_float(v), 0.f, 0.f, 0.f});
   int acc = 0;
-  for (int r = 0; r < SAMP_CL; ++r) acc += __float_as_int(dsmem_read(xch, r));
-  cg::this_cluster().sync();
+  for (int r = 0; r < c.ncl; ++r) acc += __float_as_int(w.get(r).a);
   return acc;
 }
 
@@ -236,92 +265,130 @@ __device__ __forceinline__ float key2f(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// Smallest key K (ascending) such that  sum_{key_i <= K} w_i  >= target  (strict: > target).
-// keyf(i) -> uint32 key, wf(i) -> weight.  If never reached returns the largest present key.
-// Cluster-wide: every CTA histograms its slice [lo, hi), the 8 histograms are summed in rank order through DSMEM
-// into histsum, and every CTA runs the same scan on the same numbers.
+// One radix round shared by the two selects: the CTA's histogram (hist[256], integer bins) is complete; sum the
+// cluster's histograms in rank order, then warp 0 scans the 256 bins in parallel (8 per lane + a shuffle prefix).
+//   ascending (weighted select): first bin b with  below + sum_{<= b} >= target  (strict: > target); none: last nonempty
+//   descending (k-th largest)  : first bin b from the top with  above + sum_{>= b} >= target
+// Returns (bin, weight strictly before the bin in scan order) to every thread through bcast[0..1].
+__device__ void radix_round_pick(const Cl& c, uint32_t* hist, uint32_t* hsum, uint32_t* bcast, uint32_t before,
+                                 uint32_t target, bool strict, bool descending) {
+  c.sync();  // every CTA's histogram of this round is complete
+  if (threadIdx.x < 256) {
+    uint32_t t = 0;
+    for (int r = 0; r < c.ncl; ++r) t += dsmem_read(c, hist + threadIdx.x, r);
+    hsum[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int l = threadIdx.x;
+    uint32_t h[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = descending ? 255 - (8 * l + j) : 8 * l + j;
+      h[j] = hsum[b];
+      tot += h[j];
+    }
+    uint32_t incl = tot;  // inclusive prefix over lanes (scan order)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (l >= o) incl += t;
+    }
+    uint32_t cum = before + incl - tot;  // weight before this lane's first bin
+    int sel = -1;
+    uint32_t sel_before = 0;
+    int last_nonempty = -1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t nc = cum + h[j];
+      if (h[j] > 0) last_nonempty = 8 * l + j;
+      if (sel < 0 && h[j] > 0 && (strict ? (nc > target) : (nc >= target))) {
+        sel = 8 * l + j;
+        sel_before = cum;
+      }
+      cum = nc;
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, sel >= 0);
+    int out_sel;
+    uint32_t out_before;
+    if (hit) {
+      const int src = __ffs(hit) - 1;
+      out_sel = __shfl_sync(0xffffffffu, sel, src);
+      out_before = __shfl_sync(0xffffffffu, sel_before, src);
+    } else {
+      // rounding: total weight < target -> keep everything: choose the last nonempty bin in scan order
+      int ln = last_nonempty;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ln = max(ln, __shfl_xor_sync(0xffffffffu, ln, o));
+      out_sel = ln < 0 ? 255 : ln;
+      // weight before that bin: lanes below contribute their totals, the owning lane its bins before it
+      uint32_t part = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (8 * l + j < out_sel) part += h[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      out_before = before + part;
+    }
+    if (l == 0) {
+      bcast[0] = (uint32_t)(descending ? 255 - out_sel : out_sel);  // back to a digit value
+      bcast[1] = out_before;
+    }
+  }
+  __syncthreads();
+}
+
+// Smallest key K (ascending) such that  sum_{key_i <= K} w_i  >= target  (strict: > target); if never reached, the
+// largest present key.  keyf(i) -> uint32 key, wf(i) -> probability-like weight in [0, 1] (sums to ~1 over the row).
+// Weights are accumulated as 2^-30 fixed-point integers: integer addition is associative, so the histograms -- and with
+// them the selected threshold and every seeded draw -- are bit-reproducible whatever the order in which warps and CTAs
+// arrive (float atomics were not), and no warp-serialised aggregation loop is needed: lanes of a warp that hit the same
+// bin are found with match.any, summed with one redux and added with ONE shared-memory atomic.
+// 4 rounds of 8 bits; every CTA histograms its slice, the cluster sums them, every CTA runs the same scan.
 template <class KeyF, class WF>
-__device__ uint32_t select_weighted_asc(int lo, int hi, KeyF keyf, WF wf, float target, bool strict,
-                                        float* hist /*[256]*/, float* histsum /*[256]*/, uint32_t* bcast) {
-  uint32_t prefix = 0;
-  float below = 0.f;  // weight of keys strictly below the current prefix range
+__device__ uint32_t select_weighted_asc(Cl& c, int lo, int hi, KeyF keyf, WF wf, float target, bool strict,
+                                        uint32_t (*hist)[256], uint32_t* hsum, uint32_t* bcast) {
+  const uint32_t T = __float2uint_rn(fminf(fmaxf(target, 0.f), 2.f) * SAMP_FIX);
+  uint32_t prefix = 0, below = 0;
   for (int round = 0; round < 4; ++round) {
     const int shift = 24 - 8 * round;
-    cg::this_cluster().sync();  // nobody still reads last round's histogram
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0.f;
+    uint32_t* h = hist[c.he & 1];
+    ++c.he;
+    if (threadIdx.x < 256) h[threadIdx.x] = 0u;
     __syncthreads();
-    // Warp-aggregated histogram: in the first rounds nearly every key of a warp falls into the same one or two
-    // digits (shared exponent bits), and 1024 threads hammering one shared-memory word serialise.  Lanes are grouped
-    // by digit, each group is summed with shuffles (lane order: deterministic) and its leader issues ONE atomic.
     for (int i0 = lo; i0 < hi; i0 += SAMP_THREADS) {
       const int i = i0 + threadIdx.x;
-      float w = 0.f;
-      uint32_t digit = 0;
+      uint32_t w = 0, digit = 0xffffffffu;  // not counted
       if (i < hi) {
-        w = wf(i);
-        if (w > 0.f) {
+        w = __float2uint_rn(wf(i) * SAMP_FIX);
+        if (w > 0) {
           const uint32_t k = keyf(i);
           if (round == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) digit = (k >> shift) & 255;
-          else w = 0.f;
         }
       }
-      uint32_t todo = __ballot_sync(0xffffffffu, w > 0.f);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const uint32_t ld = __shfl_sync(0xffffffffu, digit, leader);
-        const bool mine = (w > 0.f) && digit == ld;
-        float part = mine ? w : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if ((threadIdx.x & 31) == leader) atomicAdd(&hist[ld], part);
-        todo &= ~__ballot_sync(0xffffffffu, mine);
+      const uint32_t grp = __match_any_sync(0xffffffffu, digit);
+      if (digit != 0xffffffffu) {
+        const uint32_t sum = __reduce_add_sync(grp, w);
+        if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&h[digit], sum);
       }
     }
-    cg::this_cluster().sync();
-    if (threadIdx.x < 256) {
-      float t = 0.f;
-      for (int r = 0; r < SAMP_CL; ++r) t += dsmem_read(hist + threadIdx.x, r);
-      histsum[threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float cum = below;
-      int sel = -1, last_nonempty = -1;
-      for (int b = 0; b < 256; ++b) {
-        const float h = histsum[b];
-        if (h > 0.f) last_nonempty = b;
-        const float nc = cum + h;
-        if (h > 0.f && (strict ? (nc > target) : (nc >= target))) {
-          sel = b;
-          break;
-        }
-        cum = nc;
-      }
-      if (sel < 0) {  // rounding: total mass < target -> keep everything: choose the largest key
-        sel = last_nonempty < 0 ? 255 : last_nonempty;
-        cum = below;
-        for (int b = 0; b < sel; ++b) cum += histsum[b];
-      }
-      bcast[0] = (uint32_t)sel;
-      bcast[1] = __float_as_uint(cum);
-    }
-    __syncthreads();
+    radix_round_pick(c, h, hsum, bcast, below, T, strict, /*descending=*/false);
     prefix |= bcast[0] << shift;
-    below = __uint_as_float(bcast[1]);
+    below = bcast[1];
   }
   return prefix;
 }
 
 // k-th largest key (k >= 1) by count
 template <class KeyF>
-__device__ uint32_t select_kth_largest(int lo, int hi, KeyF keyf, int k, int* hist /*[256]*/, int* histsum /*[256]*/,
+__device__ uint32_t select_kth_largest(Cl& c, int lo, int hi, KeyF keyf, int k, uint32_t (*hist)[256], uint32_t* hsum,
                                        uint32_t* bcast) {
-  uint32_t prefix = 0;
-  int above = 0;
+  uint32_t prefix = 0, above = 0;
   for (int round = 0; round < 4; ++round) {
     const int shift = 24 - 8 * round;
-    cg::this_cluster().sync();
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    uint32_t* h = hist[c.he & 1];
+    ++c.he;
+    if (threadIdx.x < 256) h[threadIdx.x] = 0u;
     __syncthreads();
     for (int i0 = lo; i0 < hi; i0 += SAMP_THREADS) {  // warp-aggregated: one atomic per distinct digit per warp
       const int i = i0 + threadIdx.x;
@@ -331,30 +398,11 @@ __device__ uint32_t select_kth_largest(int lo, int hi, KeyF keyf, int k, int* hi
         if (round == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) digit = (key >> shift) & 255;
       }
       const uint32_t grp = __match_any_sync(0xffffffffu, digit);
-      if (digit != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&hist[digit], __popc(grp));
+      if (digit != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&h[digit], (uint32_t)__popc(grp));
     }
-    cg::this_cluster().sync();
-    if (threadIdx.x < 256) {
-      int t = 0;
-      for (int r = 0; r < SAMP_CL; ++r) t += dsmem_read(hist + threadIdx.x, r);
-      histsum[threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int cum = above, sel = 0;
-      for (int b = 255; b >= 0; --b) {
-        if (cum + histsum[b] >= k) {
-          sel = b;
-          break;
-        }
-        cum += histsum[b];
-      }
-      bcast[0] = (uint32_t)sel;
-      bcast[1] = (uint32_t)cum;
-    }
-    __syncthreads();
+    radix_round_pick(c, h, hsum, bcast, above, (uint32_t)k, false, /*descending=*/true);
     prefix |= bcast[0] << shift;
-    above = (int)bcast[1];
+    above = bcast[1];
   }
   return prefix;
 }
@@ -373,31 +421,38 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 }
 
 // ---------------------------------------------------------------- the kernel
+// Grid = rows x ncl CTAs; the ncl CTAs of a row form one thread-block cluster (runtime cluster size) and each scans
+// 1/ncl of the vocabulary.  Pass 1 (every row): raw max / sum-exp, and for plain greedy rows the argmax of the processed
+// logits in the same sweep -- such a row costs ONE vectorised pass over its logits plus one cluster exchange.
 template <class LT>
-__global__ void __cluster_dims__(SAMP_CL, 1, 1) __launch_bounds__(SAMP_THREADS, 1)
+__global__ void __launch_bounds__(SAMP_THREADS, 1)
 tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
                     uint32_t* __restrict__ seen_bitmap, int bitmap_words, float* __restrict__ scratch,
-                    SampleOut* __restrict__ outs) {
+                    SampleOut* __restrict__ outs, int ncl) {
   __shared__ float redf[2 * SAMP_WARPS];
   __shared__ int redi[SAMP_WARPS];
-  __shared__ float histf[256];
-  __shared__ float histsumf[256];
+  __shared__ uint32_t hist[2][256];
+  __shared__ uint32_t hsum[256];
   __shared__ uint32_t bcast[4];
-  __shared__ float xch[4];
-  int* histi = reinterpret_cast<int*>(histf);
-  int* histsumi = reinterpret_cast<int*>(histsumf);
+  __shared__ float xch[2][4];
+  __shared__ float cand_v[MAX_TOPN];
+  __shared__ int cand_i[MAX_TOPN];
   STL_ENTER(6);
   griddep_launch();
   griddep_wait();
   STL_WAITED();
 
-  const int r = blockIdx.x / SAMP_CL;
-  const int crank = (int)cg::this_cluster().block_rank();
+  Cl cl;
+  cl.ncl = ncl;
+  cl.rank = ncl > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  cl.xe = cl.he = 0;
+  const int r = blockIdx.x / ncl;
+  const int crank = cl.rank;
   RowCtx<LT> c;
   c.p = rows[r];
   c.V = V;
   {
-    const int per = ((V + SAMP_CL - 1) / SAMP_CL + 7) / 8 * 8;
+    const int per = ((V + ncl - 1) / ncl + 7) / 8 * 8;
     c.lo = min(V, crank * per);
     c.hi = min(V, c.lo + per);
   }
@@ -413,14 +468,13 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
   const bool want_lp = (c.p.flags & SAMPLE_LOGPROBS) != 0;
   float* y = scratch + (size_t)r * V;  // processed logits (sampling rows only)
 
-  // ---- pass 1: raw max / sum-exp (+ greedy argmax of the processed logits in the same sweep)
+  // ---- pass 1: raw max / sum-exp (+ greedy argmax of the processed logits in the same sweep); two 16-byte loads in
+  // flight per thread
   MaxSum ms{-INFINITY, 0.f};
   ValIdx best{-INFINITY, -1};
   const bool do_typ = (c.p.flags & SAMPLE_TYPICAL) != 0 && !forced;
   const bool greedy_fast = greedy && !do_typ;  // argmax fused into the first sweep
-  for (int i0 = lo + threadIdx.x * 8; i0 < hi; i0 += SAMP_THREADS * 8) {
-    float xs[8];
-    load_x8(c.x, i0, xs);
+  auto consume8 = [&](const float (&xs)[8], int i0) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float x = xs[e];
@@ -435,35 +489,59 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
         if (best.i < 0 || yy > best.v) best = {yy, i0 + e};  // ascending i: strict > keeps the lowest index
       }
     }
+  };
+  for (int i0 = lo + threadIdx.x * 8; i0 < hi; i0 += SAMP_THREADS * 16) {
+    float xa[8], xb[8];
+    const int i1 = i0 + SAMP_THREADS * 8;
+    load_x8(c.x, i0, xa);
+    if (i1 < hi) load_x8(c.x, i1, xb);
+    consume8(xa, i0);
+    if (i1 < hi) consume8(xb, i1);
   }
-  ms = cluster_maxsum(ms, redf, xch);
+  int token;
+  if (greedy_fast) {
+    // one exchange for both reductions: {max, sum-exp, best value, best index}
+    ms = block_maxsum(ms, redf);
+    best = block_argmax(best, redf, redi);
+    const XchView w = cl_publish(cl, xch, Xch4{ms.m, ms.s, best.v, __int_as_float(best.i)});
+    Xch4 t = w.get(0);
+    MaxSum am{t.a, t.b};
+    ValIdx ab{t.c, __float_as_int(t.d)};
+    for (int q = 1; q < ncl; ++q) {
+      t = w.get(q);
+      am = ms_combine(am, MaxSum{t.a, t.b});
+      ab = vi_better(ab, ValIdx{t.c, __float_as_int(t.d)});
+    }
+    ms = am;
+    token = ab.i;
+  } else {
+    ms = cluster_maxsum(cl, ms, redf, xch);
+    token = -1;
+  }
   c.raw_max = ms.m;
   c.raw_logz = logf(ms.s);
 
   // ---- typical-p threshold (R8): entropy, then weighted select over s = |-lp - H| ascending
   if (do_typ) {
-    {
-      float part = 0.f;
-      for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
-        const float lp = (load_x(c, i) - c.raw_max) - c.raw_logz;
-        const float p = expf(lp);
-        const float term = lp * p;
-        if (term == term) part += term;  // nansum
-      }
-      c.ent = -cluster_sumf(part, redf, xch);
-      const float rm = c.raw_max, lz = c.raw_logz, ent = c.ent;
-      const LT* xx = c.x;
-      auto keyf = [=](int i) {
-        const float lp = (lt2f(xx[i]) - rm) - lz;
-        return __float_as_uint(fabsf((-lp) - ent));
-      };
-      auto wf = [=](int i) { return expf((lt2f(xx[i]) - rm) - lz); };
-      const uint32_t k = select_weighted_asc(lo, hi, keyf, wf, c.p.typical_p, false, histf, histsumf, bcast);
-      c.typ_thr = __uint_as_float(k);
-      c.typical = true;
+    float part = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
+      const float lp = (load_x(c, i) - c.raw_max) - c.raw_logz;
+      const float p = expf(lp);
+      const float term = lp * p;
+      if (term == term) part += term;  // nansum
     }
+    c.ent = -cluster_sumf(cl, part, redf, xch);
+    const float rm = c.raw_max, lz = c.raw_logz, ent = c.ent;
+    const LT* xx = c.x;
+    auto keyf = [=](int i) {
+      const float lp = (lt2f(xx[i]) - rm) - lz;
+      return __float_as_uint(fabsf((-lp) - ent));
+    };
+    auto wf = [=](int i) { return expf((lt2f(xx[i]) - rm) - lz); };
+    const uint32_t k = select_weighted_asc(cl, lo, hi, keyf, wf, c.p.typical_p, false, hist, hsum, bcast);
+    c.typ_thr = __uint_as_float(k);
+    c.typical = true;
   }
-  int token;
   if (forced) {
     token = (int)c.p.seed_lo;
   } else if (greedy) {
@@ -472,9 +550,9 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
         const float yy = process(c, i, load_x(c, i));
         if (best.i < 0 || yy > best.v) best = {yy, i};
       }
+      best = cluster_argmax(cl, best, redf, redi, xch);
+      token = best.i;
     }
-    best = cluster_argmax(best, redf, redi, xch);
-    token = best.i;
   } else {
     // ---- processed logits / temperature -> scratch, running max
     float mx = -INFINITY;
@@ -486,14 +564,14 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
       mx = fmaxf(mx, v);
     }
     {
-      MaxSum t = cluster_maxsum(MaxSum{mx, 0.f}, redf, xch);
+      MaxSum t = cluster_maxsum(cl, MaxSum{mx, 0.f}, redf, xch);
       mx = t.m;
     }
     // ---- top-k (S6): keep y >= k-th largest value
     float lo_thr = -INFINITY;
     if (c.p.top_k > 0 && c.p.top_k < V) {
       auto keyf = [=](int i) { return f2key(y[i]); };
-      lo_thr = key2f(select_kth_largest(lo, hi, keyf, c.p.top_k, histi, histsumi, bcast));
+      lo_thr = key2f(select_kth_largest(cl, lo, hi, keyf, c.p.top_k, hist, hsum, bcast));
     }
     // ---- top-p (S6): drop the low-probability tail whose cumulative mass <= 1 - p
     if (c.p.top_p < 1.0f) {
@@ -502,14 +580,14 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
         const float v = y[i];
         if (v >= lo_thr) part += expf(v - mx);
       }
-      const float z = cluster_sumf(part, redf, xch);
+      const float z = cluster_sumf(cl, part, redf, xch);
       const float lt = lo_thr;
       auto keyf = [=](int i) { return f2key(y[i]); };
       auto wf = [=](int i) {
         const float v = y[i];
         return (v >= lt) ? expf(v - mx) / z : 0.f;
       };
-      const uint32_t k = select_weighted_asc(lo, hi, keyf, wf, 1.0f - c.p.top_p, true, histf, histsumf, bcast);
+      const uint32_t k = select_weighted_asc(cl, lo, hi, keyf, wf, 1.0f - c.p.top_p, true, hist, hsum, bcast);
       lo_thr = fmaxf(lo_thr, key2f(k));
     }
     // ---- exponential race == Gumbel max over the kept set
@@ -524,7 +602,7 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
         if (bs.i < 0 || score > bs.v) bs = {score, i};
       }
     }
-    bs = cluster_argmax(bs, redf, redi, xch);
+    bs = cluster_argmax(cl, bs, redf, redi, xch);
     token = bs.i;
     if (token < 0) {  // everything masked (degenerate): fall back to raw argmax
       ValIdx b2{-INFINITY, -1};
@@ -532,7 +610,7 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
         const float v = load_x(c, i);
         if (b2.i < 0 || v > b2.v) b2 = {v, i};
       }
-      b2 = cluster_argmax(b2, redf, redi, xch);
+      b2 = cluster_argmax(cl, b2, redf, redi, xch);
       token = b2.i;
     }
   }
@@ -547,26 +625,55 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
       const float lp = (load_x(c, i) - c.raw_max) - c.raw_logz;
       cnt += (lp >= tok_lp) ? 1 : 0;
     }
-    rank = cluster_sumi(cnt, redi, xch);
+    rank = cluster_sumi(cl, cnt, redi, xch);
   }
   SampleOut* o = outs + r;
   const int n_topn = min(c.p.n_topn, MAX_TOPN);
-  float prev_v = INFINITY;
-  int prev_i = -1;
-  for (int n = 0; n < n_topn; ++n) {
-    // next element in (value desc, index asc) order strictly after (prev_v, prev_i)
-    ValIdx b{-INFINITY, -1};
-    for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
-      const float v = load_x(c, i);
-      const bool after = (v < prev_v) || (v == prev_v && i > prev_i);
-      if (after && (b.i < 0 || v > b.v)) b = {v, i};
+  if (n_topn > 0) {
+    // The row's top-n is contained in the union of the slices' top-n: every CTA extracts its own n best
+    // (value desc, index asc) with n block reductions, ONE cluster barrier publishes the lists, and warp 0 of the
+    // cluster's rank-0 CTA merges the <= 8 x 12 candidates in registers.
+    float prev_v = INFINITY;
+    int prev_i = -1;
+    for (int n = 0; n < n_topn; ++n) {
+      ValIdx b{-INFINITY, -1};
+      for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
+        const float v = load_x(c, i);
+        const bool after = (v < prev_v) || (v == prev_v && i > prev_i);
+        if (after && (b.i < 0 || v > b.v)) b = {v, i};
+      }
+      b = block_argmax(b, redf, redi);
+      prev_v = b.v;
+      prev_i = b.i;
+      if (threadIdx.x == 0) {
+        cand_v[n] = b.v;
+        cand_i[n] = b.i;
+      }
     }
-    b = cluster_argmax(b, redf, redi, xch);
-    prev_v = b.v;
-    prev_i = b.i;
-    if (threadIdx.x == 0 && crank == 0) {
-      o->topn_ids[n] = b.i;
-      o->topn_lps[n] = (b.v - c.raw_max) - c.raw_logz;
+    cl.sync();
+    if (crank == 0 && threadIdx.x < 32) {
+      constexpr int PER_LANE = (SAMP_MAX_CL * MAX_TOPN + 31) / 32;  // 3
+      ValIdx mine[PER_LANE];
+#pragma unroll
+      for (int j = 0; j < PER_LANE; ++j) {
+        const int e = (int)threadIdx.x + 32 * j;
+        const int q = e / MAX_TOPN, n = e % MAX_TOPN;
+        mine[j] = ValIdx{-INFINITY, -1};
+        if (q < ncl && n < n_topn) mine[j] = ValIdx{dsmem_read(cl, cand_v + n, q), dsmem_read(cl, cand_i + n, q)};
+      }
+      for (int n = 0; n < n_topn; ++n) {
+        ValIdx b{-INFINITY, -1};
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) b = vi_better(b, mine[j]);
+        b = warp_argmax(b);
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j)
+          if (mine[j].i == b.i) mine[j].i = -1;  // consumed (indices are unique across slices)
+        if (threadIdx.x == 0) {
+          o->topn_ids[n] = b.i;
+          o->topn_lps[n] = (b.v - c.raw_max) - c.raw_logz;
+        }
+      }
     }
   }
   if (threadIdx.x == 0 && crank == 0) {
@@ -577,21 +684,46 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
     if (c.p.seq_slot >= 0 && token >= 0)
       atomicOr(&seen_bitmap[(size_t)c.p.seq_slot * bitmap_words + (token >> 5)], 1u << (token & 31));
   }
+  if (ncl > 1) cg::this_cluster().sync();  // nobody exits while a peer may still read its shared memory
   STL_EXIT();
+}
+
+// Cluster size of a launch: rows that only need the fused first pass (greedy / forced, no typical-p) get just enough CTAs
+// per row to cover the GPU once; rows with selection passes (sampling) keep 8 CTAs per row.  The choice is a function of
+// (n_rows, any_complex) only, so a captured CUDA graph (keyed by both) replays the same launch.
+int sampler_cluster_size(int n_rows, int any_complex, int num_sms) {
+  if (const char* e = getenv("TGIS_SAMPLER_CLUSTER")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+  }
+  if (any_complex) return n_rows <= 96 ? 8 : (n_rows <= 192 ? 4 : 2);
+  int ncl = 8;
+  while (ncl > 1 && n_rows * ncl > num_sms) ncl >>= 1;
+  return ncl;
+}
+
+template <class LT>
+static cudaError_t sampler_launch_t(const LT* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+                                    uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out, int ncl,
+                                    cudaStream_t stream) {
+  if (ncl > 1)
+    return launch_k_cluster(tgis_sampler_kernel<LT>, dim3(n_rows * ncl), dim3(SAMP_THREADS), 0, stream, ncl, logits, ld,
+                            vocab, rows, seen_bitmap, bitmap_words, scratch, out, ncl);
+  return launch_k(tgis_sampler_kernel<LT>, dim3(n_rows), dim3(SAMP_THREADS), 0, stream, logits, ld, vocab, rows,
+                  seen_bitmap, bitmap_words, scratch, out, 1);
 }
 
 cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int vocab, const SampleRow* rows, int n_rows,
                            const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int any_complex, int num_sms) {
   if (n_rows <= 0) return cudaSuccess;
   if (vocab % 8 != 0 || ld % 8 != 0) return cudaErrorInvalidValue;
+  const int ncl = sampler_cluster_size(n_rows, any_complex, num_sms);
   if (logits_bf16)
-    return launch_k(tgis_sampler_kernel<__nv_bfloat16>, dim3(n_rows * SAMP_CL), dim3(SAMP_THREADS), 0, stream,
-                    static_cast<const __nv_bfloat16*>(logits), ld, vocab, rows, const_cast<uint32_t*>(seen_bitmap),
-                    bitmap_words, scratch, out);
-  return launch_k(tgis_sampler_kernel<float>, dim3(n_rows * SAMP_CL), dim3(SAMP_THREADS), 0, stream,
-                  static_cast<const float*>(logits), ld, vocab, rows, const_cast<uint32_t*>(seen_bitmap), bitmap_words,
-                  scratch, out);
+    return sampler_launch_t(static_cast<const __nv_bfloat16*>(logits), ld, vocab, rows, n_rows,
+                            const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out, ncl, stream);
+  return sampler_launch_t(static_cast<const float*>(logits), ld, vocab, rows, n_rows, const_cast<uint32_t*>(seen_bitmap),
+                          bitmap_words, scratch, out, ncl, stream);
 }
 
 size_t sampler_scratch_floats(int vocab) { return (size_t)vocab; }

@@ -320,14 +320,19 @@ int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, i
     bm = dummy_bm.p;
   }
   if (iters < 1) iters = 1;
+  int any_complex = 0;  // same rule as the engine: a row that is not plain greedy / forced needs selection passes
+  for (int i = 0; i < n_rows; ++i) {
+    const int f = ((const SampleRow*)rows_host)[i].flags;
+    if (!(f & (SAMPLE_GREEDY | SAMPLE_FORCED)) || ((f & SAMPLE_TYPICAL) && !(f & SAMPLE_FORCED))) any_complex = 1;
+  }
   cudaEvent_t e0, e1;
   KCK(cudaEventCreate(&e0));
   KCK(cudaEventCreate(&e1));
   if (iters > 1)  // warm-up launch outside the timed region
-    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
+    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0, any_complex));
   KCK(cudaEventRecord(e0, 0));
   for (int it = 0; it < iters; ++it)
-    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0));
+    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0, any_complex));
   KCK(cudaEventRecord(e1, 0));
   KCK(cudaMemcpy(out_host, outs.p, sizeof(SampleOut) * n_rows, cudaMemcpyDeviceToHost));
   KCK(cudaDeviceSynchronize());
