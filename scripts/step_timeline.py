@@ -42,21 +42,35 @@ recs = buf[8:].reshape(4096, 4)
 idx = [(i % 4096) for i in range(max(0, n - 4096), n)]
 rows = [tuple(int(x) for x in recs[i]) for i in idx if recs[i][3] != 0]
 rows.sort(key=lambda r: r[1])
-NAMES = {1: "norm", 2: "gemm", 3: "attn_decode", 4: "attn_merge", 5: "attn_prefill", 6: "sampler", 8: "gather", 9: "ar_norm"}
+NAMES = {1: "norm", 2: "gemm", 3: "attn_decode", 4: "attn_merge", 5: "attn_prefill", 6: "sampler", 8: "gather", 9: "ar_norm",
+         20: "STEP_BEGIN", 21: "META_LANDED", 22: "STEP_END"}
 # last decode step = everything after the second-to-last sampler record
 samp = [i for i, r in enumerate(rows) if (r[0] & 0xff) == 6]
 lo = samp[-2] + 1 if len(samp) >= 2 else 0
-step = rows[lo:samp[-1] + 1]
+step = [r for r in rows[lo:samp[-1] + 1] if (r[0] & 0xff) not in (20, 21, 22)]
 t0 = step[0][1]
-# step-to-step: sampler exit of step k -> first kernel entry / first dependency-wait return of step k+1, and the period
-gaps = []
-for a, b in zip(samp[:-1], samp[1:]):
-    nxt = rows[a + 1]
-    gaps.append(((nxt[1] - rows[a][3]) / 1e3, ((nxt[2] or nxt[1]) - rows[a][3]) / 1e3, (rows[b][3] - rows[a][3]) / 1e3))
-if gaps:
-    g = np.array(gaps[-20:])
-    print(f"last {len(g)} decode steps: sampler exit -> next step's first kernel ENTRY {g[:, 0].mean():.1f} us (min {g[:, 0].min():.1f}), "
-          f"-> first kernel RUNNING {g[:, 1].mean():.1f} us; step period {g[:, 2].mean():.1f} us")
+# step-to-step decomposition from the marker kernels (20 = before the metadata copy, 21 = after it, 22 = after the result
+# copy) of the last decode steps
+begins = [r for r in rows if (r[0] & 0xff) == 20]
+landed = [r for r in rows if (r[0] & 0xff) == 21]
+ends = [r for r in rows if (r[0] & 0xff) == 22]
+sampx = [rows[i] for i in samp]
+nm = min(len(begins), len(landed), len(ends))
+begins, landed, ends = begins[len(begins) - nm:], landed[len(landed) - nm:], ends[len(ends) - nm:]
+if nm > 4:
+    K = min(20, nm - 1)
+    dec = []
+    for j in range(len(begins) - K, len(begins)):
+        b, l, e, pe = begins[j], landed[j], ends[j], ends[j - 1]
+        sx = [x for x in sampx if b[1] < x[1] < e[1]]
+        first = next((r for r in rows if r[1] > l[3] and (r[0] & 0xff) not in (20, 21, 22)), None)
+        dec.append(((b[1] - pe[3]) / 1e3, (l[3] - b[1]) / 1e3, ((first[2] or first[1]) - l[3]) / 1e3 if first else 0.0,
+                    (e[3] - sx[-1][3]) / 1e3 if sx else 0.0, (e[3] - pe[3]) / 1e3))
+    d = np.array(dec)
+    print(f"last {K} steps (us): prev STEP_END -> STEP_BEGIN (host turnaround + launch latency) mean {d[:, 0].mean():.1f} "
+          f"min {d[:, 0].min():.1f} max {d[:, 0].max():.1f} | metadata copy {d[:, 1].mean():.1f} | -> first kernel running "
+          f"{d[:, 2].mean():.1f} | sampler exit -> STEP_END (result copy) {d[:, 3].mean():.1f} | period {d[:, 4].mean():.1f}")
+    print("  per-step turnaround:", " ".join(f"{x:.0f}" for x in d[:, 0]))
 print(f"decode ms/step (engine events) = {st.gpu_decode_ms / max(st.decode_steps, 1):.4f}; graph launches {st.graph_launches}; "
       f"{len(step)} kernel launches in the last step, span {(step[-1][3] - t0) / 1e3:.1f} us")
 print(f"{'kernel':>14} {'N':>7} {'start':>8} {'wait':>7} {'body':>7} {'gap_prev_exit->waited':>22}")

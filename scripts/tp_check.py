@@ -52,10 +52,24 @@ if rank == 0:
                     ok = False
             worst = max(worst, abs(float(lp[r.new_token]) - r.logprob))
             logits = ora.step([(st, [r.new_token])])[0]
+    # prompt logprobs under tensor parallelism (vocab-parallel lm_head over every prompt position; plan kind 1)
+    pl_prompts = [rng.randint(3, cfg.vocab, size=n).tolist() for n in (40, 9)]
+    sp2 = make_sampling_params(greedy=True, max_tokens=2, num_logprobs=1, prompt_logprobs=2)
+    outs2 = eng.generate_sync(pl_prompts, sp2)
+    worst_plp, n_plp = 0.0, 0
+    for p, recs in zip(pl_prompts, outs2):
+        pos = {r.prompt_pos: r for r in recs if r.prompt_pos >= 1}
+        assert sorted(pos) == list(range(1, len(p))), sorted(pos)
+        lp = torch.log_softmax(ora.step([(ora.new_seq(), p)], want_all_logits=True), -1)
+        for i in range(1, len(p)):
+            assert pos[i].token_id == p[i]
+            worst_plp = max(worst_plp, abs(pos[i].logprob - float(lp[i - 1, p[i]])))
+            n_plp += 1
     st = eng.status()
-    print(f"tp={world} {cfg_name}: max |dlogprob| = {worst:.4g}, near-tie flips = {flips}, steps = {st.steps}, "
-          f"launches = {st.kernel_launches}", flush=True)
-    ok = ok and worst < 2e-2 and st.errored == 0
+    print(f"tp={world} {cfg_name}: max |dlogprob| = {worst:.4g}, near-tie flips = {flips}, prompt logprobs: {n_plp} positions "
+          f"max |d| = {worst_plp:.4g}, steps = {st.steps}, launches = {st.kernel_launches}, graph launches = "
+          f"{st.graph_launches}", flush=True)
+    ok = ok and worst < 2e-2 and worst_plp < 2e-2 and st.errored == 0 and st.graph_launches > 0
     eng.close()       # signals the workers to leave their loop
     print("TP_CHECK_PASS" if ok else "TP_CHECK_FAIL", flush=True)
 else:

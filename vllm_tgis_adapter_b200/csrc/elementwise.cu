@@ -36,6 +36,25 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// ------------------------------------------------------------------------------------------------ timeline markers
+// (debug builds: a one-thread kernel whose only effect is its step-timeline record -- brackets the non-kernel parts of a
+// step: metadata copy, result copy, launch latency)
+__global__ void stl_marker_kernel(int kid) {
+  STL_ENTER(kid);
+  STL_WAITED();
+  STL_EXIT();
+}
+cudaError_t stl_marker_launch(int kid, cudaStream_t stream) {
+#ifdef TGIS_STEP_TIMELINE
+  stl_marker_kernel<<<1, 32, 0, stream>>>(kid);
+  return cudaGetLastError();
+#else
+  (void)kid;
+  (void)stream;
+  return cudaSuccess;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ embedding / gather
 __global__ void gather_rows_kernel(const int32_t* __restrict__ idx, const __nv_bfloat16* __restrict__ table,
                                    __nv_bfloat16* __restrict__ out, int hidden, int n_table_rows) {
@@ -263,6 +282,167 @@ cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, const 
   if (tp < 2 || tp > 8 || T > AR_MAX_ROWS || hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC)
     return cudaErrorInvalidValue;
   return launch_k(ar_add_rmsnorm_kernel, dim3(T), dim3(NORM_THREADS), 0, stream, peers, tp, rank, epoch_base, epoch_idx,
+                  residual, w, out, hidden, eps);
+}
+
+// ------------------------------------------------------------------------------------------------ TP: two-shot exchange
+// Same contract as ar_add_rmsnorm_kernel (all-reduce of the row-parallel partials in rank order + residual add +
+// RMSNorm, identical bits on every rank), for exchanges too large for the one-shot push: there every rank sends its whole
+// partial to every peer in the 2x "LL" format, i.e. 2 (tp-1) T H 2 bytes of NVLink egress per rank (56 MB at T = 256,
+// H = 8192, tp = 8).  Here row t is OWNED by rank t mod tp:
+//   1. reduce-scatter: every rank pushes its partial of row t to the owner (plain 16-byte stores, then fence + one flag);
+//   2. the owner waits for the tp - 1 flags, sums the partials in RANK ORDER in fp32, rounds once to bf16 (the all-reduced
+//      GEMM output in model dtype) and pushes that row to every peer (fence + flag): the all-gather;
+//   3. every rank adds the residual and normalises all rows (replicated, from its local copy of the reduced row).
+// Egress per rank: 2 (tp-1)/tp T H 2 bytes (7 MB in the example).  A row's CTA never waits for another row, so there is
+// no cross-row dependency to dead-lock on; the two parity areas alternate exactly like the one-shot kernel's.
+// Area layout (per rank, per parity):  recv1 [8 src][AR_MAX_ROWS][H] bf16 | recv2 [AR_MAX_ROWS][H] bf16 |
+//                                      flags1 [8 src][AR_MAX_ROWS] u32 | flags2 [AR_MAX_ROWS] u32
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_flag(const uint32_t* p, uint32_t epoch, int rank, int row, int what) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys_u32(p) != epoch) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("ar2_add_rmsnorm: rank %d row %d waiting for %s flag, epoch %u (has %u)\n", rank, row,
+             what == 1 ? "a partial" : "the reduced-row", epoch, ld_acquire_sys_u32(p));
+      __trap();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NORM_THREADS)
+ar2_add_rmsnorm_kernel(Ar2Peers P, int tp, int rank, const uint32_t* __restrict__ epoch_base, uint32_t epoch_idx,
+                       __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ w,
+                       __nv_bfloat16* __restrict__ out, int hidden, float eps) {
+  __shared__ float red[NORM_THREADS / 32];
+  STL_ENTER(9);
+  griddep_launch();
+  griddep_wait();  // this rank's partial (previous kernel) is complete; the step's metadata copy has landed
+  STL_WAITED();
+  const uint32_t epoch = __ldg(epoch_base) + epoch_idx;
+  const int row = blockIdx.x;
+  const int owner = row % tp;
+  const size_t base = (size_t)row * hidden;
+  const int nvec = hidden / 8;
+  const size_t recv2_off = (size_t)8 * AR_MAX_ROWS * hidden * 2;
+  const size_t flags_off = (size_t)9 * AR_MAX_ROWS * hidden * 2;
+  auto recv1 = [&](int q) { return reinterpret_cast<uint4*>(P.area[q]); };
+  auto recv2 = [&](int q) { return reinterpret_cast<uint4*>(P.area[q] + recv2_off); };
+  auto flags1 = [&](int q) { return reinterpret_cast<uint32_t*>(P.area[q] + flags_off); };
+  auto flags2 = [&](int q) { return reinterpret_cast<uint32_t*>(P.area[q] + flags_off) + 8 * AR_MAX_ROWS; };
+  uint4 sum[NORM_MAX_VEC];  // the reduced row, bf16
+  if (owner != rank) {
+    // ---- 1. my partial of this row -> the owner
+    uint4* dst = recv1(owner) + ((size_t)rank * AR_MAX_ROWS + row) * nvec;
+#pragma unroll
+    for (int j = 0; j < NORM_MAX_VEC; ++j) {
+      const int i = threadIdx.x + j * NORM_THREADS;
+      if (i < nvec) dst[i] = reinterpret_cast<const uint4*>(P.own + base)[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys_u32(flags1(owner) + rank * AR_MAX_ROWS + row, epoch);
+    // ---- 3a. wait for the reduced row
+    if (threadIdx.x == 0) spin_flag(flags2(rank) + row, epoch, rank, row, 2);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NORM_MAX_VEC; ++j) {
+      const int i = threadIdx.x + j * NORM_THREADS;
+      if (i < nvec) sum[j] = ld_volatile_v4(recv2(rank) + (size_t)row * nvec + i);
+    }
+  } else {
+    // ---- 2. owner: all partials of this row, summed in rank order
+    if ((int)threadIdx.x < tp && (int)threadIdx.x != rank)
+      spin_flag(flags1(rank) + threadIdx.x * AR_MAX_ROWS + row, epoch, rank, row, 1);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NORM_MAX_VEC; ++j) {
+      const int i = threadIdx.x + j * NORM_THREADS;
+      if (i < nvec) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int q = 0; q < tp; ++q) {
+          const uint4 raw = (q == rank) ? reinterpret_cast<const uint4*>(P.own + base)[i]
+                                        : ld_volatile_v4(recv1(rank) + ((size_t)q * AR_MAX_ROWS + row) * nvec + i);
+          const uint32_t* rw = &raw.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[2 * e] += __uint_as_float(rw[e] << 16);
+            acc[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+          }
+        }
+        uint32_t* sw = &sum[j].x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 pr = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+          sw[e] = *reinterpret_cast<const uint32_t*>(&pr);
+        }
+        for (int q = 0; q < tp; ++q)
+          if (q != rank) recv2(q)[(size_t)row * nvec + i] = sum[j];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < tp && (int)threadIdx.x != rank) st_release_sys_u32(flags2(threadIdx.x) + row, epoch);
+  }
+  // ---- 3b. residual add + RMSNorm (arithmetic of rmsnorm_kernel<true> on the bf16 reduced row)
+  BF8 z[NORM_MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) {
+      const BF8 r = reinterpret_cast<const BF8*>(residual + base)[i];
+      const uint32_t* sw = &sum[j].x;
+      BF8 a;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        a.v[2 * e] = __float2bfloat16_rn(__uint_as_float(sw[e] << 16) + __bfloat162float(r.v[2 * e]));
+        a.v[2 * e + 1] = __float2bfloat16_rn(__uint_as_float(sw[e] & 0xffff0000u) + __bfloat162float(r.v[2 * e + 1]));
+      }
+      reinterpret_cast<BF8*>(residual + base)[i] = a;
+      z[j] = a;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float f = __bfloat162float(a.v[e]);
+        ss += f * f;
+      }
+    }
+  }
+  const float tot = block_sum<NORM_THREADS>(ss, red);
+  const float rs = rsqrtf(tot / (float)hidden + eps);
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) {
+      BF8 wv = reinterpret_cast<const BF8*>(w)[i];
+      BF8 o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float nrm = bf16_round(__bfloat162float(z[j].v[e]) * rs);
+        o.v[e] = __float2bfloat16_rn(nrm * __bfloat162float(wv.v[e]));
+      }
+      reinterpret_cast<BF8*>(out + base)[i] = o;
+    }
+  }
+  STL_EXIT();
+}
+
+cudaError_t ar2_add_rmsnorm_launch(const Ar2Peers& peers, int tp, int rank, const uint32_t* epoch_base, uint32_t epoch_idx,
+                                   __nv_bfloat16* residual, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
+                                   float eps, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (tp < 2 || tp > 8 || T > AR_MAX_ROWS || hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC)
+    return cudaErrorInvalidValue;
+  return launch_k(ar2_add_rmsnorm_kernel, dim3(T), dim3(NORM_THREADS), 0, stream, peers, tp, rank, epoch_base, epoch_idx,
                   residual, w, out, hidden, eps);
 }
 

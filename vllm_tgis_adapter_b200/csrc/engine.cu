@@ -151,6 +151,8 @@ struct StepHeader {
   int32_t graphable;     // replay (or capture) the CUDA graph keyed by (S, KV splits, samp_complex) instead of launching
   int32_t samp_complex;  // some sampled row needs selection passes (sampling): decides the sampler's cluster size
   uint64_t copy_bytes;
+  int32_t kind;          // 0: engine step; 1: prompt-logprob pass over R rows of the step just executed (T = its tokens,
+  int32_t need_norm;     //    need_norm: the final RMSNorm has not run yet)
 };
 struct ShmCtl {
   std::atomic<uint64_t> seq;
@@ -274,6 +276,8 @@ struct tgis_engine {
   // tensor parallelism, decode-shaped steps: one-shot all-reduce + residual + RMSNorm over NVLink peer memory
   // (ar_add_rmsnorm_kernel) instead of ncclAllReduce + rmsnorm kernel.  TGIS_TP_FUSED_AR=0: NCCL baseline.
   bool tp_fused_ar = true;
+  int tp_exchange_force = -1;                 // TGIS_TP_EXCHANGE
+  size_t tp_oneshot_max_bytes = 2u << 20;     // TGIS_TP_ONESHOT_MAX_KB
   bool tp_graphs = true;  // TGIS_TP_GRAPHS=0: tensor-parallel decode steps are launched kernel by kernel (round 1)
   static constexpr int AR_MAX_T = AR_MAX_ROWS;
   uint8_t* ar_mem = nullptr;        // [2 parities] receive areas (ar_recv_bytes each), then the two local partial buffers
@@ -304,6 +308,13 @@ struct tgis_engine {
   std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
   std::unordered_map<uint64_t, long long> graph_nodes;
   long long n_graph_launches = 0;
+  // Experiment switches for the step-to-step turnaround (scripts/step_timeline.py measured ~1 ms between the end of one
+  // graph replay and the first kernel of the next, against ~26 us when the same step is launched kernel by kernel):
+  bool sync_spin = true;              // TGIS_SYNC_SPIN: wait for the step by polling its end event instead of
+                                      // cudaStreamSynchronize (no blocking-wait wake-up latency)
+  bool graph_copy_outside = true;     // TGIS_GRAPH_COPY_OUTSIDE: metadata H2D / result D2H as plain stream copies
+                                      // around the graph launch instead of memcpy nodes inside the graph
+  bool capturing = false;
   bool debug_launch = false;          // TGIS_DEBUG_LAUNCH=1: host time spent inside cudaGraphLaunch, printed at destroy
   double graph_launch_host_s = 0;
 
@@ -366,7 +377,14 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_LOGITS_FP32")) logits_bf16 = atoi(e) == 0;
     if (const char* e = getenv("TGIS_TP_TIMEOUT_S")) tp_timeout_s = atof(e);
     if (const char* e = getenv("TGIS_DEBUG_LAUNCH")) debug_launch = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_SYNC_SPIN")) sync_spin = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_GRAPH_COPY_OUTSIDE")) graph_copy_outside = atoi(e) != 0;
     if (const char* e = getenv("TGIS_TP_GRAPHS")) tp_graphs = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_TP_ONESHOT_MAX_KB")) tp_oneshot_max_bytes = (size_t)atol(e) << 10;
+    if (const char* e = getenv("TGIS_TP_EXCHANGE")) {
+      const std::string v = e;
+      tp_exchange_force = v == "nccl" ? 0 : v == "oneshot" ? 1 : v == "twoshot" ? 2 : -1;
+    }
     lsz = logits_bf16 ? 2 : 4;
 
     // ---- weights: one arena
@@ -548,12 +566,24 @@ struct tgis_engine {
   }
 
   size_t ar_buf_bytes() const { return (size_t)AR_MAX_T * cfg.hidden * sizeof(bf16); }
+  size_t ar2_area_stride() const { return (ar2_area_bytes(cfg.hidden) + 255) / 256 * 256; }
+  size_t ar2_area_off(int parity) const { return 2 * ar_recv_bytes(cfg.hidden) + 2 * ar_buf_bytes() + parity * ar2_area_stride(); }
+  // How the row-parallel partials of a T-token step are exchanged (TGIS_TP_EXCHANGE=auto|oneshot|twoshot|nccl):
+  //   0 ncclAllReduce + add_rmsnorm kernel (prefill-sized steps, or the peer mappings are unavailable)
+  //   1 one-shot push ("LL" lines; one NVLink traversal) while a rank's egress 2 (tp-1) T H 2 B stays small
+  //   2 two-shot (reduce-scatter by row owner + all-gather of the reduced rows)
+  int exchange_mode(int T) const {
+    if (tp <= 1 || !tp_fused_ar || T > AR_MAX_T) return 0;
+    if (tp_exchange_force >= 0) return tp_exchange_force;
+    const size_t oneshot_egress = (size_t)2 * (tp - 1) * T * cfg.hidden * 2;
+    return oneshot_egress <= tp_oneshot_max_bytes ? 1 : 2;
+  }
   bf16* ar_buf(int parity) { return reinterpret_cast<bf16*>(ar_mem + 2 * ar_recv_bytes(cfg.hidden) + parity * ar_buf_bytes()); }
 
   // Every rank allocates its exchange buffer, the cudaIpc handles travel by ncclAllGather, every rank maps the others.
   // All ranks must take the same decision: the per-rank success bits are summed with an all-reduce.
   void init_fused_ar() {
-    const size_t bytes = 2 * ar_recv_bytes(cfg.hidden) + 2 * ar_buf_bytes();
+    const size_t bytes = 2 * ar_recv_bytes(cfg.hidden) + 2 * ar_buf_bytes() + 2 * ar2_area_stride();
     int ok = 1;
     cudaIpcMemHandle_t mine;
     if (cudaMalloc(&ar_mem, bytes) != cudaSuccess || cudaMemset(ar_mem, 0, bytes) != cudaSuccess ||
@@ -592,13 +622,22 @@ struct tgis_engine {
 
   // exchange #parity of a layer (0: after o-proj, 1: after down-proj) + residual add + RMSNorm with weight w
   void fused_ar_norm(int parity, const bf16* w, int T) {
-    ArPeers P;
-    memset(&P, 0, sizeof(P));
-    P.own = ar_buf(parity);
-    for (int r = 0; r < tp; ++r) P.recv[r] = reinterpret_cast<uint4*>(ar_peer[r] + parity * ar_recv_bytes(cfg.hidden));
     cudaEvent_t pe = prof_begin_exchange();
-    CK(ar_add_rmsnorm_launch(P, tp, rank, ds<uint32_t>(off_epoch) + parity, ++step_ar_idx[parity], resid.p, w, xn.p, T,
-                             cfg.hidden, cfg.rms_eps, stream));
+    if (exchange_mode(T) == 2) {
+      Ar2Peers P;
+      memset(&P, 0, sizeof(P));
+      P.own = ar_buf(parity);
+      for (int r = 0; r < tp; ++r) P.area[r] = ar_peer[r] + ar2_area_off(parity);
+      CK(ar2_add_rmsnorm_launch(P, tp, rank, ds<uint32_t>(off_epoch) + parity, ++step_ar_idx[parity], resid.p, w, xn.p, T,
+                                cfg.hidden, cfg.rms_eps, stream));
+    } else {
+      ArPeers P;
+      memset(&P, 0, sizeof(P));
+      P.own = ar_buf(parity);
+      for (int r = 0; r < tp; ++r) P.recv[r] = reinterpret_cast<uint4*>(ar_peer[r] + parity * ar_recv_bytes(cfg.hidden));
+      CK(ar_add_rmsnorm_launch(P, tp, rank, ds<uint32_t>(off_epoch) + parity, ++step_ar_idx[parity], resid.p, w, xn.p, T,
+                               cfg.hidden, cfg.rms_eps, stream));
+    }
     if (pe) CK(cudaEventRecord(pe, stream));
     ++n_launches;
   }
@@ -799,7 +838,10 @@ struct tgis_engine {
   void launch_step(size_t copy_bytes, int T, int n_dec, int n_tiles, int R, int max_dec_kv, int S, int samp_complex) {
     const tgis_config& c = cfg;
     const int H = c.hidden, F = Fl, V = c.vocab;  // F: local ffn shard
-    CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
+    const bool copies_here = !(capturing && graph_copy_outside);
+    CK(stl_marker_launch(20, stream));  // timeline builds: step begin (before the metadata copy)
+    if (copies_here) CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
+    CK(stl_marker_launch(21, stream));  // metadata landed
     step_is_decode = (n_tiles == 0);
     step_ar_idx[0] = step_ar_idx[1] = 0;
 
@@ -814,7 +856,7 @@ struct tgis_engine {
     }
     CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
     ++n_launches;
-    const bool ar_fused = tp > 1 && tp_fused_ar && T <= AR_MAX_T;
+    const bool ar_fused = exchange_mode(T) != 0;
     // RoPE + KV-cache scatter fused into the qkv GEMM's split-tile reduction (decode-shaped steps where every weight
     // tile is split over several CTAs; TGIS_FUSE_ROPE=0: off)
     // (measured: -2 % per step at 32 tokens, but +2...5 % at 64...256 -- the last-arriving CTA's serial tail grows with
@@ -899,8 +941,63 @@ struct tgis_engine {
         CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words,
                           samp_scratch.p, d_samp_out.p, stream, samp_complex, num_sms));
         ++n_launches;
-        CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
+        if (copies_here)
+          CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
       }
+    }
+    CK(stl_marker_launch(22, stream));  // timeline builds: step end (after the result copy)
+  }
+
+  // Prompt-logprob pass (vllm prompt_logprobs; grpc_server.py:609-611): lm_head + FORCED sampler rows over m prompt
+  // positions of the step that has just run (row indices and SampleRows staged at off_samplesrc / off_rows).  Under tensor
+  // parallelism every rank runs its vocabulary shard of the lm_head and the all-gather; rank 0 samples.
+  void plp_pass(int m, int need_norm, int T, size_t copy_bytes) {
+    const tgis_config& c = cfg;
+    const int H = c.hidden, V = c.vocab;
+    CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
+    if (need_norm) {  // no sampled row in the step -> its final norm has not run yet
+      CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
+      ++n_launches;
+    }
+    CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, m, H, stream));
+    ++n_launches;
+    const int lm_mode = logits_bf16 ? 0 : 1;
+    if (tp == 1) {
+      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, m, V, H, lm_mode);
+    } else {
+      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, m, Vl, H, lm_mode);
+      NK(nccl().AllGather(logits_shard.p, logits_gather.p, (size_t)m * Vl * lsz, ncclInt8, comm, stream));
+      if (rank == 0) {
+        CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const uint4*)logits_gather.p,
+                    (uint4*)logits.p, m, (int)(Vl * lsz / 16), tp));
+        ++n_launches;
+      }
+    }
+    if (rank == 0) {
+      CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words,
+                        samp_scratch.p, d_samp_out.p, stream, /*any_complex=*/0, num_sms));
+      ++n_launches;
+      CK(cudaMemcpyAsync(h_plp_out, d_samp_out.p, sizeof(SampleOut) * m, cudaMemcpyDeviceToHost, stream));
+    }
+  }
+
+  // Wait until everything up to ev1 (the step's last operation on the stream) has executed.
+  void wait_step_end() {
+    if (!sync_spin) {
+      CK(cudaStreamSynchronize(stream));
+      return;
+    }
+    for (;;) {
+      const cudaError_t q = cudaEventQuery(ev1);
+      if (q == cudaSuccess) return;
+      if (q != cudaErrorNotReady) CK(q);
+      if (stop_flag) {  // shutting down: do not spin on a possibly wedged device
+        CK(cudaStreamSynchronize(stream));
+        return;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
     }
   }
 
@@ -909,6 +1006,10 @@ struct tgis_engine {
   // buffer, so the captured launch sequence is step-independent -- or the plain launch sequence otherwise.  Rank 0
   // and the tensor-parallel workers run the same function on the same header.
   void exec_step(const StepHeader& h) {
+    if (h.kind == 1) {
+      plp_pass(h.R, h.need_norm, h.T, h.copy_bytes);
+      return;
+    }
     if (!h.graphable) {
       launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S, h.samp_complex);
       return;
@@ -924,13 +1025,16 @@ struct tgis_engine {
       const long long launches_before = n_launches;
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      capturing = true;
       try {
         launch_step(h.copy_bytes, h.T, h.n_dec, h.n_tiles, h.R, h.max_dec_kv, h.S, h.samp_complex);
       } catch (...) {
+        capturing = false;
         cudaStreamEndCapture(stream, &g);
         if (g) cudaGraphDestroy(g);
         throw;
       }
+      capturing = false;
       CK(cudaStreamEndCapture(stream, &g));
       cudaGraphExec_t ge = nullptr;
       CK(cudaGraphInstantiate(&ge, g, 0));
@@ -940,7 +1044,10 @@ struct tgis_engine {
       it = graphs.emplace(key, ge).first;
     }
     const double t_gl = debug_launch ? now_s() : 0.0;
+    if (graph_copy_outside) CK(cudaMemcpyAsync(d_stage.p, h_stage, h.copy_bytes, cudaMemcpyHostToDevice, stream));
     CK(cudaGraphLaunch(it->second, stream));
+    if (graph_copy_outside && rank == 0 && h.R > 0)
+      CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * h.R, cudaMemcpyDeviceToHost, stream));
     if (debug_launch) graph_launch_host_s += now_s() - t_gl;
     n_launches += graph_nodes[key];
     ++n_graph_launches;
@@ -1043,13 +1150,13 @@ struct tgis_engine {
     const size_t copy_bytes = items_off(S) + sizeof(DecItem) * (1 + (size_t)n_dec * max_splits_step);
     CK(cudaEventRecord(ev0, stream));
     const bool graphable = cfg.use_cuda_graphs && (tp == 1 || tp_graphs) && !profiling && n_tiles == 0 && n_dec == S && R == S;
-    StepHeader hdr{T, n_dec, n_tiles, R, max_dec_kv, S, graphable ? 1 : 0, samp_complex, (uint64_t)copy_bytes};
+    StepHeader hdr{T, n_dec, n_tiles, R, max_dec_kv, S, graphable ? 1 : 0, samp_complex, (uint64_t)copy_bytes, 0, 0};
     if (tp > 1) {
       // exchange epochs of this step = staged base + index inside the step (ar_add_rmsnorm_kernel)
       uint32_t* eb = hs<uint32_t>(off_epoch);
       eb[0] = ar_epoch[0];
       eb[1] = ar_epoch[1];
-      if (tp_fused_ar && T <= AR_MAX_T) {
+      if (exchange_mode(T) != 0) {
         ar_epoch[0] += (uint32_t)cfg.n_layers;
         ar_epoch[1] += (uint32_t)cfg.n_layers;
       }
@@ -1057,7 +1164,7 @@ struct tgis_engine {
     }
     exec_step(hdr);
     CK(cudaEventRecord(ev1, stream));
-    CK(cudaStreamSynchronize(stream));
+    wait_step_end();
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     gpu_ms += ms;
@@ -1089,10 +1196,9 @@ struct tgis_engine {
     // ---- prompt logprobs: lm_head + forced-token sampler rows over the prompt positions of this step, S_max rows at a
     // time (512x the decode logits work per prompt: rare, so it stays a simple separate pass on the same stream)
     if (!prompt_rows.empty()) {
-      if (R == 0) {  // no sampled row this step -> the final norm has not run yet
-        CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
-        ++n_launches;
-      }
+      const bool fused_exchange = exchange_mode(T) != 0;   // then the final norm always ran
+      int need_norm = (R == 0 && !fused_exchange) ? 1 : 0;
+      const size_t plp_bytes = off_rows + sizeof(SampleRow) * (size_t)S_max;  // the staged regions up to the sample rows
       for (size_t off = 0; off < prompt_rows.size(); off += (size_t)S_max) {
         const int m = (int)std::min<size_t>(S_max, prompt_rows.size() - off);
         for (int i = 0; i < m; ++i) {
@@ -1110,14 +1216,10 @@ struct tgis_engine {
           row.seed_lo = (uint32_t)pr.target;
           row.logits_row = i;
         }
-        CK(cudaMemcpyAsync(ds<int32_t>(off_samplesrc), samplesrc, sizeof(int32_t) * m, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(ds<SampleRow>(off_rows), rows, sizeof(SampleRow) * m, cudaMemcpyHostToDevice, stream));
-        CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, m, H, stream));
-        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, m, V, H, logits_bf16 ? 0 : 1);
-        CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words,
-                          samp_scratch.p, d_samp_out.p, stream, /*any_complex=*/0, num_sms));
-        n_launches += 2;
-        CK(cudaMemcpyAsync(h_plp_out, d_samp_out.p, sizeof(SampleOut) * m, cudaMemcpyDeviceToHost, stream));
+        StepHeader ph{T, 0, 0, m, 0, 0, 0, 0, (uint64_t)plp_bytes, 1, need_norm};
+        if (tp > 1) publish_plan(ph);
+        exec_step(ph);
+        need_norm = 0;
         CK(cudaStreamSynchronize(stream));
         for (int i = 0; i < m; ++i) emit_prompt(*prompt_rows[off + i].r, prompt_rows[off + i].pos, h_plp_out[i]);
       }
@@ -1473,7 +1575,6 @@ int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_
   if (params->n_stop_token_ids > TGIS_MAX_STOP_TOKEN_IDS || params->n_stop_token_ids < 0) return fail("too many stop token ids");
   if (!params->greedy && !(params->temperature > 0.f)) return fail("temperature must be > 0 when sampling");
   if (params->num_logprobs > TGIS_MAX_TOPN || params->prompt_logprobs > TGIS_MAX_TOPN) return fail("num_logprobs too large");
-  if (params->prompt_logprobs > 0 && e->tp > 1) return fail("prompt_logprobs is not supported with tensor parallelism yet");
   for (int i = 0; i < n_prompt; ++i)
     if (prompt_ids[i] < 0 || prompt_ids[i] >= e->cfg.vocab) return fail("prompt token id out of range");
   auto r = std::make_unique<Request>();

@@ -51,6 +51,7 @@ cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfl
                                  int N, int K, cudaStream_t stream, int out_f32 = 0);
 
 // ---- elementwise.cu ----------------------------------------------------------------------------------------------
+cudaError_t stl_marker_launch(int kid, cudaStream_t stream);  // -DTGIS_STEP_TIMELINE builds only (else a no-op)
 cudaError_t embed_gather_launch(const int32_t* token_ids, const __nv_bfloat16* table, __nv_bfloat16* out, int T,
                                 int hidden, int vocab, cudaStream_t stream);
 // out = rmsnorm(x) * w                                   (first layer: residual := x is done by the caller)
@@ -73,6 +74,16 @@ struct ArPeers {
 cudaError_t ar_add_rmsnorm_launch(const ArPeers& peers, int tp, int rank, const uint32_t* epoch_base, uint32_t epoch_idx,
                                   __nv_bfloat16* residual, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
                                   float eps, cudaStream_t stream);
+// Two-shot variant (reduce-scatter by row owner t mod tp, all-gather of the bf16 reduced rows; elementwise.cu) for
+// exchanges whose one-shot egress would be large.  area[q]: rank q's two-shot area for this exchange parity, mapped here.
+inline size_t ar2_area_bytes(int hidden) { return (size_t)9 * AR_MAX_ROWS * hidden * 2 + (size_t)9 * AR_MAX_ROWS * 4; }
+struct Ar2Peers {
+  const __nv_bfloat16* own;
+  uint8_t* area[8];
+};
+cudaError_t ar2_add_rmsnorm_launch(const Ar2Peers& peers, int tp, int rank, const uint32_t* epoch_base, uint32_t epoch_idx,
+                                   __nv_bfloat16* residual, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
+                                   float eps, cudaStream_t stream);
 // act[t, i] = bf16(silu(gate_up[t, i])) * gate_up[t, F + i]
 cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn, cudaStream_t stream);
 // gather rows: out[r, :] = x[rows[r], :]

@@ -38,6 +38,7 @@ constexpr float SAMP_FIX = 1073741824.0f;  // 2^30: probabilities are accumulate
 template <class LT>
 struct RowCtx {
   const LT* x;             // raw logits
+  const LT* xc;            // this CTA's slice staged in shared memory by pass 1 (xc[i - lo]), or nullptr
   int V;
   int lo, hi;              // this CTA's slice of the vocabulary (multiples of 8)
   const uint32_t* seen;    // bitmap of prompt U output tokens (may be null)
@@ -51,8 +52,26 @@ struct RowCtx {
 
 __device__ __forceinline__ float lt2f(float v) { return v; }
 __device__ __forceinline__ float lt2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+// entry i of this CTA's slice [lo, hi): from the shared-memory copy when the slice was staged (every pass after the first
+// then costs shared-memory latency instead of an L2 round trip per dependent load)
 template <class LT>
-__device__ __forceinline__ float load_x(const RowCtx<LT>& c, int i) { return lt2f(c.x[i]); }
+__device__ __forceinline__ float load_x(const RowCtx<LT>& c, int i) {
+  return lt2f(c.xc != nullptr ? c.xc[i - c.lo] : c.x[i]);
+}
+// any entry of the row (global memory)
+template <class LT>
+__device__ __forceinline__ float load_x_any(const RowCtx<LT>& c, int i) { return lt2f(c.x[i]); }
+__device__ __forceinline__ void store_x8(float* dst, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store_x8(__nv_bfloat16* dst, const float (&v)[8]) {
+  uint4 r;
+  uint32_t* w = &r.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = (__float_as_uint(v[2 * e]) >> 16) | (__float_as_uint(v[2 * e + 1]) & 0xffff0000u);
+  *reinterpret_cast<uint4*>(dst) = r;  // exact: the values came from bf16
+}
 // 8 consecutive logits (i0 % 8 == 0) as fp32
 __device__ __forceinline__ void load_x8(const float* x, int i0, float (&o)[8]) {
   const float4 ra = *reinterpret_cast<const float4*>(x + i0);
@@ -428,7 +447,9 @@ template <class LT>
 __global__ void __launch_bounds__(SAMP_THREADS, 1)
 tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
                     uint32_t* __restrict__ seen_bitmap, int bitmap_words, float* __restrict__ scratch,
-                    SampleOut* __restrict__ outs, int ncl) {
+                    SampleOut* __restrict__ outs, int ncl, int cache_x, int cache_y) {
+  // dynamic shared memory: [slice of the raw logits (cache_x)] [slice of the processed logits, fp32 (cache_y)]
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ float redf[2 * SAMP_WARPS];
   __shared__ int redi[SAMP_WARPS];
   __shared__ uint32_t hist[2][256];
@@ -458,6 +479,9 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
   }
   const int lo = c.lo, hi = c.hi;
   c.x = logits + (size_t)c.p.logits_row * ld;
+  const int per_cta = ((V + ncl - 1) / ncl + 7) / 8 * 8;
+  LT* xs = reinterpret_cast<LT*>(dyn_smem);
+  c.xc = nullptr;  // set after pass 1 has filled it
   c.seen = (c.p.seq_slot >= 0 && c.p.rep_penalty != 1.0f) ? seen_bitmap + (size_t)c.p.seq_slot * bitmap_words : nullptr;
   c.lenfac_m1 = (c.p.flags & SAMPLE_LENPEN) ? c.p.len_decay_factor : 0.f;
   c.mask_eos = c.p.n_out < c.p.min_tokens;
@@ -466,10 +490,12 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
   const bool forced = (c.p.flags & SAMPLE_FORCED) != 0;
   const bool greedy = (c.p.flags & SAMPLE_GREEDY) && !forced;
   const bool want_lp = (c.p.flags & SAMPLE_LOGPROBS) != 0;
-  float* y = scratch + (size_t)r * V;  // processed logits (sampling rows only)
+  // processed logits (sampling rows only): shared memory when the slice fits, else the global scratch row; indexed y[i]
+  float* y = cache_y ? reinterpret_cast<float*>(dyn_smem + (cache_x ? (size_t)per_cta * sizeof(LT) : 0)) - lo
+                     : scratch + (size_t)r * V;
 
-  // ---- pass 1: raw max / sum-exp (+ greedy argmax of the processed logits in the same sweep); two 16-byte loads in
-  // flight per thread
+  // ---- pass 1: raw max / sum-exp (+ greedy argmax of the processed logits in the same sweep); the slice is staged in
+  // shared memory on the way when it fits
   MaxSum ms{-INFINITY, 0.f};
   ValIdx best{-INFINITY, -1};
   const bool do_typ = (c.p.flags & SAMPLE_TYPICAL) != 0 && !forced;
@@ -490,14 +516,24 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
       }
     }
   };
-  for (int i0 = lo + threadIdx.x * 8; i0 < hi; i0 += SAMP_THREADS * 16) {
-    float xa[8], xb[8];
-    const int i1 = i0 + SAMP_THREADS * 8;
-    load_x8(c.x, i0, xa);
-    if (i1 < hi) load_x8(c.x, i1, xb);
-    consume8(xa, i0);
-    if (i1 < hi) consume8(xb, i1);
+  constexpr int P1_UNROLL = 4;  // 16-byte loads in flight per thread (64 KB per SM)
+  for (int i0 = lo + threadIdx.x * 8; i0 < hi; i0 += SAMP_THREADS * 8 * P1_UNROLL) {
+    float xv[P1_UNROLL][8];
+#pragma unroll
+    for (int u = 0; u < P1_UNROLL; ++u) {
+      const int iu = i0 + u * SAMP_THREADS * 8;
+      if (iu < hi) load_x8(c.x, iu, xv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < P1_UNROLL; ++u) {
+      const int iu = i0 + u * SAMP_THREADS * 8;
+      if (iu < hi) {
+        if (cache_x) store_x8(xs + (iu - lo), xv[u]);
+        consume8(xv[u], iu);
+      }
+    }
   }
+  if (cache_x) c.xc = xs;  // visible to every thread after the barriers of the reductions below
   int token;
   if (greedy_fast) {
     // one exchange for both reductions: {max, sum-exp, best value, best index}
@@ -532,7 +568,7 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
     }
     c.ent = -cluster_sumf(cl, part, redf, xch);
     const float rm = c.raw_max, lz = c.raw_logz, ent = c.ent;
-    const LT* xx = c.x;
+    const LT* xx = c.xc != nullptr ? c.xc - lo : c.x;  // indexed xx[i]
     auto keyf = [=](int i) {
       const float lp = (lt2f(xx[i]) - rm) - lz;
       return __float_as_uint(fabsf((-lp) - ent));
@@ -619,7 +655,7 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
   float tok_lp = 0.f;
   int rank = 0;
   if (want_lp) {
-    tok_lp = (load_x(c, token) - c.raw_max) - c.raw_logz;
+    tok_lp = (load_x_any(c, token) - c.raw_max) - c.raw_logz;
     int cnt = 0;
     for (int i = lo + threadIdx.x; i < hi; i += SAMP_THREADS) {
       const float lp = (load_x(c, i) - c.raw_max) - c.raw_logz;
@@ -705,12 +741,26 @@ int sampler_cluster_size(int n_rows, int any_complex, int num_sms) {
 template <class LT>
 static cudaError_t sampler_launch_t(const LT* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
                                     uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out, int ncl,
-                                    cudaStream_t stream) {
+                                    int any_complex, cudaStream_t stream) {
+  // shared-memory staging of the CTA's slice: raw logits always when they fit, the processed row too for sampling rows
+  const size_t per = (size_t)(((vocab + ncl - 1) / ncl + 7) / 8 * 8);
+  constexpr size_t SMEM_BUDGET = 200 * 1024;
+  int cache_x = per * sizeof(LT) <= SMEM_BUDGET ? 1 : 0;
+  int cache_y = (any_complex && cache_x && per * (sizeof(LT) + 4) <= SMEM_BUDGET) ? 1 : 0;
+  if (const char* e = getenv("TGIS_SAMPLER_SMEM"))
+    if (e[0] == '0') cache_x = cache_y = 0;
+  const size_t smem = (cache_x ? per * sizeof(LT) : 0) + (cache_y ? per * 4 : 0);
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(tgis_sampler_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET);
+    if (e != cudaSuccess) return e;
+    attr_bytes = SMEM_BUDGET;
+  }
   if (ncl > 1)
-    return launch_k_cluster(tgis_sampler_kernel<LT>, dim3(n_rows * ncl), dim3(SAMP_THREADS), 0, stream, ncl, logits, ld,
-                            vocab, rows, seen_bitmap, bitmap_words, scratch, out, ncl);
-  return launch_k(tgis_sampler_kernel<LT>, dim3(n_rows), dim3(SAMP_THREADS), 0, stream, logits, ld, vocab, rows,
-                  seen_bitmap, bitmap_words, scratch, out, 1);
+    return launch_k_cluster(tgis_sampler_kernel<LT>, dim3(n_rows * ncl), dim3(SAMP_THREADS), smem, stream, ncl, logits, ld,
+                            vocab, rows, seen_bitmap, bitmap_words, scratch, out, ncl, cache_x, cache_y);
+  return launch_k(tgis_sampler_kernel<LT>, dim3(n_rows), dim3(SAMP_THREADS), smem, stream, logits, ld, vocab, rows,
+                  seen_bitmap, bitmap_words, scratch, out, 1, cache_x, cache_y);
 }
 
 cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int vocab, const SampleRow* rows, int n_rows,
@@ -721,9 +771,9 @@ cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int voca
   const int ncl = sampler_cluster_size(n_rows, any_complex, num_sms);
   if (logits_bf16)
     return sampler_launch_t(static_cast<const __nv_bfloat16*>(logits), ld, vocab, rows, n_rows,
-                            const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out, ncl, stream);
+                            const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out, ncl, any_complex, stream);
   return sampler_launch_t(static_cast<const float*>(logits), ld, vocab, rows, n_rows, const_cast<uint32_t*>(seen_bitmap),
-                          bitmap_words, scratch, out, ncl, stream);
+                          bitmap_words, scratch, out, ncl, any_complex, stream);
 }
 
 size_t sampler_scratch_floats(int vocab) { return (size_t)vocab; }
