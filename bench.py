@@ -60,6 +60,7 @@ def parse_args():
                          "online-serving default")
     ap.add_argument("--sampling", default="greedy", choices=["greedy", "cfg3"],
                     help="cfg3 = repetition penalty 1.2 + length penalty (64, 1.05) + typical_p 0.9 sampling")
+    ap.add_argument("--layers", type=int, default=0, help="experiments: override the preset's layer count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-layers", type=int, default=8, help="layers timed by the CPU baseline (extrapolated)")
     ap.add_argument("--cpu-steps", type=int, default=20, help="decode steps of the ours-arm cpu_baseline leg")
@@ -319,7 +320,7 @@ _ENGINE_SEQ = [0]
 
 
 def _build_engine(model: str, *, max_seqs: int, max_len: int, kv_tokens: int, max_batched: int, tp: int, rank: int,
-                  local: int, weight_seed: int):
+                  local: int, weight_seed: int, layers: int = 0):
     """One engine (tp == 1) or this rank's shard of ONE tensor-parallel engine over `tp` GPUs."""
     import dataclasses
 
@@ -328,6 +329,8 @@ def _build_engine(model: str, *, max_seqs: int, max_len: int, kv_tokens: int, ma
     from vllm_tgis_adapter_b200.engine.core import PRESETS, NativeEngine
 
     cfg = dataclasses.replace(PRESETS[model], max_model_len=max_len)
+    if layers > 0:
+        cfg = dataclasses.replace(cfg, n_layers=layers)
     blocks = kv_tokens // 32 + 2 * max_seqs
     kv_bytes = int(blocks * 2 * cfg.n_layers * (cfg.n_kv_heads // tp) * 32 * 128 * 2 * 1.1)
     tp_kw = {}
@@ -499,7 +502,7 @@ def run_ours(args) -> dict | None:
     named_b = 128 if (tp == 4 and args.named_configs and args.model == "llama3-8b") else 0   # configs[3] shares the engine
     eng, cfg = _build_engine(args.model, max_seqs=max(B, named_b), max_len=max_len,
                              kv_tokens=max(B, named_b) * (P + G + 32), max_batched=args.max_batched_tokens, tp=tp,
-                             rank=rank, local=local, weight_seed=1234 + (rank if tp == 1 else 0))
+                             rank=rank, local=local, weight_seed=1234 + (rank if tp == 1 else 0), layers=args.layers)
     log(f"engine built and {cfg.n_layers}-layer synthetic weights loaded (tp={tp})")
     primary = prof = named = None
     if tp > 1 and rank != 0:   # tensor-parallel worker: follow rank 0's step plans until it closes its engine
@@ -542,7 +545,8 @@ def run_ours(args) -> dict | None:
         # (a) data-parallel replicas of the same workload (weak scaling; what round 1 reported) + the N=1 tokens for the
         #     in-run parity check of the tensor-parallel engine
         e1, c1 = _build_engine(args.model, max_seqs=B, max_len=max_len, kv_tokens=B * (P + G + 32),
-                               max_batched=args.max_batched_tokens, tp=1, rank=rank, local=local, weight_seed=1234)
+                               max_batched=args.max_batched_tokens, tp=1, rank=rank, local=local, weight_seed=1234,
+                               layers=args.layers)
         pr1 = prompts_for(c1, B, 1234)     # every replica runs rank 0's prompt set: rank 0's tokens are the N=1 reference
 
         def barrier_all():

@@ -19,7 +19,7 @@ graphs = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False
 mc = dataclasses.replace(PRESETS["llama3-8b"], n_layers=L, max_model_len=1024)
 import os
 MBT = int(os.environ.get("MBT", max(8192, B * P)))
-eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=MBT, kv_cache_bytes=2 << 30, use_cuda_graphs=graphs)
+eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=MBT, kv_cache_bytes=int(float(os.environ.get('KVGB', '2')) * (1 << 30)), use_cuda_graphs=graphs)
 load_synthetic_weights(eng, mc, 0, 0)
 eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
 rs = np.random.RandomState(0)

@@ -55,7 +55,7 @@ for n, kind in [(32, "greedy"), (64, "greedy"), (128, "greedy"), (256, "greedy")
     bitmap = torch.zeros(n, words, dtype=torch.int32, device="cuda")
     bitmap[:, :20] = 0x55555555
     rows = rows_for(n, kind)
-    variants = [None] + ([1, 2, 4, 8] if kind == "greedy" else [])
+    variants = [None] + ([1, 2, 4, 8] if kind == "greedy" else [2, 4] if kind == "cfg3" else [])
     for ncl in variants:
         if ncl is None:
             os.environ.pop("TGIS_SAMPLER_CLUSTER", None)

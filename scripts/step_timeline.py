@@ -24,12 +24,14 @@ lib = _lib.load_library()
 rc = lib.tgis_k_step_timeline_enable()
 assert rc == 0, f"not a -DTGIS_STEP_TIMELINE build (rc={rc})"
 mc = dataclasses.replace(PRESETS["llama3-8b"], n_layers=L, max_model_len=1024)
-eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=max(2048, B), kv_cache_bytes=(B * (P + 96) * 2 * L * 8 * 128 * 2 * 5) // 4)
+# one prefill step for all prompts: every sequence then decodes in lock step and the LAST steps of the run (the ones the
+# 4096-record ring still holds) are full-batch steps, not the tail of a staggered job
+eng = NativeEngine(mc, max_num_seqs=B, max_batched_tokens=B * P, kv_cache_bytes=(B * (P + 96) * 2 * L * 8 * 128 * 2 * 5) // 4)
 load_synthetic_weights(eng, mc, 0, 0)
 eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
 rs = np.random.RandomState(0)
 prompts = [rs.randint(1000, mc.vocab - 1000, size=P).tolist() for _ in range(B)]
-G = 40
+G = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 sp = make_sampling_params(greedy=True, max_tokens=G, min_tokens=G)
 for i, p in enumerate(prompts):
     eng.add_request(f"r{i}", p, sp)
@@ -71,6 +73,7 @@ if nm > 4:
           f"min {d[:, 0].min():.1f} max {d[:, 0].max():.1f} | metadata copy {d[:, 1].mean():.1f} | -> first kernel running "
           f"{d[:, 2].mean():.1f} | sampler exit -> STEP_END (result copy) {d[:, 3].mean():.1f} | period {d[:, 4].mean():.1f}")
     print("  per-step turnaround:", " ".join(f"{x:.0f}" for x in d[:, 0]))
+    print("  per-step BEGIN->END :", " ".join(f"{x - y:.0f}" for x, y in zip(d[:, 4], d[:, 0])))
 print(f"decode ms/step (engine events) = {st.gpu_decode_ms / max(st.decode_steps, 1):.4f}; graph launches {st.graph_launches}; "
       f"{len(step)} kernel launches in the last step, span {(step[-1][3] - t0) / 1e3:.1f} us")
 print(f"{'kernel':>14} {'N':>7} {'start':>8} {'wait':>7} {'body':>7} {'gap_prev_exit->waited':>22}")

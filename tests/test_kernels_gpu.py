@@ -275,6 +275,20 @@ def test_attention_decode_split_kv(g, n_q, n_kv):
     assert int(big.sum()) == 0, float(ulp.max())
 
 
+@pytest.mark.parametrize("n_q,n_kv", [(8, 2), (8, 1), (2, 2)])
+def test_attention_inkernel_split_merge_is_bit_identical(g, n_q, n_kv, monkeypatch):
+    """The split merge done inside the streaming kernel by the last-arriving warp (default) against the separate
+    attn_merge_kernel (TGIS_ATTN_INKERNEL_MERGE=0): same sums in the same split order -> identical bits, run twice to
+    cover the self re-arming arrival counters."""
+    specs = [(c, 1) for c in (127, 128, 129, 255, 300, 575, 576, 1000, 2047, 31)]
+    outs = []
+    for flag in ("0", "1", "1"):
+        monkeypatch.setenv("TGIS_ATTN_INKERNEL_MERGE", flag)
+        out, ref = _attention_case(g, n_q, n_kv, specs, seed=5)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
 @pytest.mark.parametrize("n_q,n_kv", [(4, 2), (8, 2), (6, 2), (8, 1)])
 def test_attention_prefill_and_mixed(g, n_q, n_kv):
     specs = [(0, 5), (0, 16), (0, 17), (0, 50), (40, 33), (0, 1), (100, 1), (31, 70), (0, 129), (200, 2)]

@@ -6,6 +6,8 @@
 //   vllm: csrc/activation_kernels.cu  (bf16(silu(x)) * y)
 // All of them are 16-byte vectorised, coalesced, one row (or 8 elements) per thread group; no shared-memory reuse is
 // possible (each byte is touched once) so the design target is simply full-width coalesced traffic.
+#include <algorithm>
+
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -444,6 +446,78 @@ cudaError_t ar2_add_rmsnorm_launch(const Ar2Peers& peers, int tp, int rank, cons
     return cudaErrorInvalidValue;
   return launch_k(ar2_add_rmsnorm_kernel, dim3(T), dim3(NORM_THREADS), 0, stream, peers, tp, rank, epoch_base, epoch_idx,
                   residual, w, out, hidden, eps);
+}
+
+// ------------------------------------------------------------------------------------------------ TP: logits gather
+// Vocab-parallel lm_head: rank r > 0 pushes its [R, V/tp] shard straight into rank 0's [R, V] logits buffer (mapped peer
+// memory, 16-byte stores over NVLink), fences, and the last block to finish raises this rank's flag in rank 0's memory;
+// rank 0 (whose own shard was written by its GEMM with ldy = V) waits for the tp - 1 flags before sampling.  Replaces
+// ncclAllGather + a re-layout kernel: a gather to the one rank that samples instead of an all-gather, no NCCL kernel
+// inside the captured decode step.
+__global__ void __launch_bounds__(256)
+logits_push_kernel(const uint4* __restrict__ shard, uint4* __restrict__ dst, int R, int Vl16, int V16, int col16,
+                   uint32_t* __restrict__ remote_flag, int* __restrict__ local_counter,
+                   const uint32_t* __restrict__ epoch_base, uint32_t epoch_idx) {
+  __shared__ int last;
+  STL_ENTER(10);
+  griddep_launch();
+  griddep_wait();
+  STL_WAITED();
+  const size_t total = (size_t)R * Vl16;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / Vl16), v = (int)(i % Vl16);
+    dst[(size_t)r * V16 + col16 + v] = shard[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;\n" : "=r"(old) : "l"(local_counter) : "memory");
+    last = (old == (int)gridDim.x - 1);
+    if (last) {
+      *local_counter = 0;
+      __threadfence_system();
+      st_release_sys_u32(remote_flag, __ldg(epoch_base) + epoch_idx);
+    }
+  }
+  STL_EXIT();
+}
+
+__global__ void logits_wait_kernel(const uint32_t* __restrict__ flags, int tp, const uint32_t* __restrict__ epoch_base,
+                                   uint32_t epoch_idx) {
+  STL_ENTER(11);
+  griddep_launch();
+  griddep_wait();
+  STL_WAITED();
+  const uint32_t epoch = __ldg(epoch_base) + epoch_idx;
+  const int r = threadIdx.x + 1;
+  if (r < tp) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u32(flags + r) != epoch) {
+      if (clock64() - t0 > 4000000000ll) {
+        printf("logits_wait: waiting for rank %d, epoch %u (has %u)\n", r, epoch, ld_acquire_sys_u32(flags + r));
+        __trap();
+      }
+    }
+  }
+  __threadfence_system();
+  STL_EXIT();
+}
+
+cudaError_t logits_push_launch(const void* shard, void* dst_peer0, int R, int Vl_bytes, int V_bytes, int col_bytes,
+                               uint32_t* remote_flag, int* local_counter, const uint32_t* epoch_base, uint32_t epoch_idx,
+                               cudaStream_t stream) {
+  if (R <= 0) return cudaSuccess;
+  if (Vl_bytes % 16 || V_bytes % 16 || col_bytes % 16) return cudaErrorInvalidValue;
+  const size_t total = (size_t)R * (Vl_bytes / 16);
+  const int grid = (int)std::min<size_t>(148 * 2, (total + 255) / 256);
+  return launch_k(logits_push_kernel, dim3(grid), dim3(256), 0, stream, (const uint4*)shard, (uint4*)dst_peer0, R,
+                  Vl_bytes / 16, V_bytes / 16, col_bytes / 16, remote_flag, local_counter, epoch_base, epoch_idx);
+}
+
+cudaError_t logits_wait_launch(const uint32_t* flags, int tp, const uint32_t* epoch_base, uint32_t epoch_idx,
+                               cudaStream_t stream) {
+  return launch_k(logits_wait_kernel, dim3(1), dim3(32), 0, stream, flags, tp, epoch_base, epoch_idx);
 }
 
 // ------------------------------------------------------------------------------------------------ SiLU * mul

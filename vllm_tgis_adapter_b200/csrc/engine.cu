@@ -153,6 +153,8 @@ struct StepHeader {
   uint64_t copy_bytes;
   int32_t kind;          // 0: engine step; 1: prompt-logprob pass over R rows of the step just executed (T = its tokens,
   int32_t need_norm;     //    need_norm: the final RMSNorm has not run yet)
+  int32_t lg_idx;        // index of this plan's logits gather inside the step (epoch = staged base + lg_idx)
+  int32_t pad;
 };
 struct ShmCtl {
   std::atomic<uint64_t> seq;
@@ -232,7 +234,7 @@ struct tgis_engine {
   size_t lsz = 2;  // bytes per logit
   CUtensorMap xm_xn[N_BT], xm_attn[N_BT], xm_act[N_BT], xm_last[N_BT];
   DevBuf<float> gemm_ws, part_o, part_ml, samp_scratch;
-  DevBuf<int> gemm_counters;
+  DevBuf<int> gemm_counters, attn_arrive;
   DevBuf<uint32_t> seen_bitmap;
   DevBuf<SampleOut> d_samp_out;
   SampleOut* h_samp_out = nullptr;
@@ -284,6 +286,9 @@ struct tgis_engine {
   uint8_t* ar_peer[8] = {};         // the same allocation of every rank, mapped here (cudaIpc)
   uint32_t ar_epoch[2] = {0, 0};     // rank 0: epoch of the last exchange of each parity (staged per step: off_epoch)
   uint32_t step_ar_idx[2] = {0, 0};  // exchanges of each parity enqueued so far in the step being built
+  uint32_t lg_epoch = 0;             // rank 0: epoch of the last logits gather (staged per step: off_epoch[2])
+  int lg_idx_step = 0;               // rank 0: gathers issued for the current step (the step's own, then prompt-logprob passes)
+  size_t lg_off = 0;                 // inside ar_mem: [S_max, V] logits receive buffer (rank 0's is the one used), then flags
   int l2_prefetch_kb = 0;   // (off: measured no gain, costs DRAM traffic in the issuing kernel) k-blocks (16 KiB each) per CTA of the NEXT GEMM pulled into L2 by the current one
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
@@ -315,13 +320,28 @@ struct tgis_engine {
   bool graph_copy_outside = true;     // TGIS_GRAPH_COPY_OUTSIDE: metadata H2D / result D2H as plain stream copies
                                       // around the graph launch instead of memcpy nodes inside the graph
   bool capturing = false;
+  bool attn_inkernel_merge = true;    // TGIS_ATTN_INKERNEL_MERGE (read by attention.cu as well): launch accounting only
+  int debug_step_sleep_us = 0;        // TGIS_STEP_SLEEP_US (experiment)
   bool debug_launch = false;          // TGIS_DEBUG_LAUNCH=1: host time spent inside cudaGraphLaunch, printed at destroy
   double graph_launch_host_s = 0;
+  // TGIS_DEBUG_LAUNCH: host-side phase times of the last steps: [sched+build, launch, wait, post] in microseconds
+  struct HostPhase {
+    float sched, launch, wait, post;
+  };
+  std::vector<HostPhase> host_phases;
+  double t_step_begin = 0, t_after_wait = 0;
 
   ~tgis_engine() {
     if (debug_launch && n_graph_launches > 0)
       fprintf(stderr, "[tgis] rank %d: %lld graph launches, %.1f us host time per cudaGraphLaunch\n", rank,
               n_graph_launches, 1e6 * graph_launch_host_s / (double)n_graph_launches);
+    if (debug_launch && !host_phases.empty()) {
+      const size_t n = host_phases.size(), lo = n > 48 ? n - 48 : 0;
+      fprintf(stderr, "[tgis] host phases of the last %zu steps (us): sched+build / launch / wait / post\n", n - lo);
+      for (size_t i = lo; i < n; ++i)
+        fprintf(stderr, "  %5.0f %5.0f %6.0f %5.0f\n", host_phases[i].sched, host_phases[i].launch, host_phases[i].wait,
+                host_phases[i].post);
+    }
     if (h_stage) cudaFreeHost(h_stage);
     if (h_samp_out) cudaFreeHost(h_samp_out);
     if (h_plp_out) cudaFreeHost(h_plp_out);
@@ -333,8 +353,12 @@ struct tgis_engine {
     for (int r = 0; r < 8; ++r)
       if (ar_peer[r] && ar_peer[r] != ar_mem) cudaIpcCloseMemHandle(ar_peer[r]);
     if (ar_mem) cudaFree(ar_mem);
-    if (comm) nccl().CommDestroy(comm);
+    // captured graphs hold NCCL work of `comm` (the logits all-gather of tensor-parallel decode steps): they must be gone
+    // before the communicator is destroyed, or ncclCommDestroy waits for them forever
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+    if (stream) cudaStreamSynchronize(stream);
+    if (comm) nccl().CommDestroy(comm);
     for (cudaEvent_t ev : prof_events) cudaEventDestroy(ev);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -378,6 +402,8 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_TP_TIMEOUT_S")) tp_timeout_s = atof(e);
     if (const char* e = getenv("TGIS_DEBUG_LAUNCH")) debug_launch = atoi(e) != 0;
     if (const char* e = getenv("TGIS_SYNC_SPIN")) sync_spin = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_ATTN_INKERNEL_MERGE")) attn_inkernel_merge = atoi(e) != 0;
+    if (const char* e = getenv("TGIS_STEP_SLEEP_US")) debug_step_sleep_us = atoi(e);
     if (const char* e = getenv("TGIS_GRAPH_COPY_OUTSIDE")) graph_copy_outside = atoi(e) != 0;
     if (const char* e = getenv("TGIS_TP_GRAPHS")) tp_graphs = atoi(e) != 0;
     if (const char* e = getenv("TGIS_TP_ONESHOT_MAX_KB")) tp_oneshot_max_bytes = (size_t)atol(e) << 10;
@@ -431,6 +457,8 @@ struct tgis_engine {
     gemm_ws.alloc(gemm_workspace_bytes(num_sms) / sizeof(float));
     gemm_counters.alloc(1 << 16);
     gemm_counters.zero();
+    attn_arrive.alloc((size_t)S_max * std::max(nkv, 1));
+    attn_arrive.zero();
     const int G = c.n_q_heads / c.n_kv_heads;
     part_o.alloc((size_t)S_max * nkv * max_splits_cap * G * HEAD_DIM);
     part_ml.alloc((size_t)S_max * nkv * max_splits_cap * G * 2);
@@ -458,7 +486,8 @@ struct tgis_engine {
     off_tileq0 = place(4 * (size_t)tiles_max);
     off_samplesrc = place(4 * (size_t)S_max);
     off_rows = place(sizeof(SampleRow) * (size_t)S_max);
-    off_epoch = place(2 * sizeof(uint32_t));  // tensor parallelism: exchange epochs before this step, per parity
+    off_epoch = place(4 * sizeof(uint32_t));  // tensor parallelism: exchange epochs before this step ([0], [1]: per
+                                               // parity) and the logits-gather epoch ([2])
     off_bt = place(4 * (size_t)S_max * bt_stride);
     // decode work items follow the USED part of the block table (items_off(S)); room for the worst case
     place(sizeof(DecItem) * (1 + (size_t)S_max * max_splits_cap));
@@ -566,6 +595,9 @@ struct tgis_engine {
   }
 
   size_t ar_buf_bytes() const { return (size_t)AR_MAX_T * cfg.hidden * sizeof(bf16); }
+  size_t lg_logits_bytes() const { return ((size_t)S_max * cfg.vocab * lsz + 255) / 256 * 256; }
+  // rank 0's full-vocabulary logits: inside the peer-mapped allocation when the ranks can reach each other's memory
+  uint8_t* logits_ptr() { return (tp > 1 && tp_fused_ar && ar_mem) ? ar_mem + lg_off : logits.p; }
   size_t ar2_area_stride() const { return (ar2_area_bytes(cfg.hidden) + 255) / 256 * 256; }
   size_t ar2_area_off(int parity) const { return 2 * ar_recv_bytes(cfg.hidden) + 2 * ar_buf_bytes() + parity * ar2_area_stride(); }
   // How the row-parallel partials of a T-token step are exchanged (TGIS_TP_EXCHANGE=auto|oneshot|twoshot|nccl):
@@ -583,7 +615,8 @@ struct tgis_engine {
   // Every rank allocates its exchange buffer, the cudaIpc handles travel by ncclAllGather, every rank maps the others.
   // All ranks must take the same decision: the per-rank success bits are summed with an all-reduce.
   void init_fused_ar() {
-    const size_t bytes = 2 * ar_recv_bytes(cfg.hidden) + 2 * ar_buf_bytes() + 2 * ar2_area_stride();
+    lg_off = 2 * ar_recv_bytes(cfg.hidden) + 2 * ar_buf_bytes() + 2 * ar2_area_stride();
+    const size_t bytes = lg_off + lg_logits_bytes() + 256;
     int ok = 1;
     cudaIpcMemHandle_t mine;
     if (cudaMalloc(&ar_mem, bytes) != cudaSuccess || cudaMemset(ar_mem, 0, bytes) != cudaSuccess ||
@@ -890,8 +923,8 @@ struct tgis_engine {
         const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
         CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, ds<DecItem>(items_off(S)), n_dec * max_splits, d_seqs,
                               ds<int32_t>(off_decids), n_dec, max_splits, part_o.p, part_ml.p, attn_out.p, q_dim, nq,
-                              nkv, scale, num_sms, stream));
-        n_launches += max_splits > 1 ? 2 : 1;
+                              nkv, scale, num_sms, stream, attn_arrive.p));
+        n_launches += (max_splits > 1 && !attn_inkernel_merge) ? 2 : 1;
       }
       if (n_tiles > 0) {
         CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
@@ -924,21 +957,9 @@ struct tgis_engine {
       }
       CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, R, H, stream));
       ++n_launches;
-      const int lm_mode = logits_bf16 ? 0 : 1;
-      if (tp == 1) {
-        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, R, V, H, lm_mode);
-      } else {
-        // vocab-parallel lm_head: every rank computes [R, V/tp], all-gather, re-layout to [R, V]
-        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, R, Vl, H, lm_mode);
-        NK(nccl().AllGather(logits_shard.p, logits_gather.p, (size_t)R * Vl * lsz, ncclInt8, comm, stream));
-        if (rank == 0) {
-          CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const uint4*)logits_gather.p,
-                      (uint4*)logits.p, R, (int)(Vl * lsz / 16), tp));
-          ++n_launches;
-        }
-      }
+      lm_head_logits(R, 1);
       if (rank == 0) {
-        CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words,
+        CK(sampler_launch(logits_ptr(), logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words,
                           samp_scratch.p, d_samp_out.p, stream, samp_complex, num_sms));
         ++n_launches;
         if (copies_here)
@@ -951,7 +972,40 @@ struct tgis_engine {
   // Prompt-logprob pass (vllm prompt_logprobs; grpc_server.py:609-611): lm_head + FORCED sampler rows over m prompt
   // positions of the step that has just run (row indices and SampleRows staged at off_samplesrc / off_rows).  Under tensor
   // parallelism every rank runs its vocabulary shard of the lm_head and the all-gather; rank 0 samples.
-  void plp_pass(int m, int need_norm, int T, size_t copy_bytes) {
+  // lm_head over `rows` rows of last_hidden -> the full [rows, V] logits on rank 0 (logits_ptr()).  Tensor parallel: every
+  // rank computes its vocabulary shard; with peer mappings the shards are pushed into rank 0's buffer (logits_push_kernel,
+  // no NCCL in the step), otherwise ncclAllGather + re-layout.
+  void lm_head_logits(int rows, int lg_idx) {
+    const tgis_config& c = cfg;
+    const int H = c.hidden, V = c.vocab;
+    const int lm_mode = logits_bf16 ? 0 : 1;
+    if (tp == 1) {
+      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, rows, V, H, lm_mode);
+    } else if (tp_fused_ar) {
+      uint32_t* flags0 = reinterpret_cast<uint32_t*>(ar_peer[0] + lg_off + lg_logits_bytes());  // in rank 0's memory
+      if (rank == 0) {
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_ptr(), rows, Vl, H, lm_mode, nullptr, 0, 0, 0, /*ldy=*/V);
+        CK(logits_wait_launch(flags0, tp, ds<uint32_t>(off_epoch) + 2, (uint32_t)lg_idx, stream));
+      } else {
+        gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, rows, Vl, H, lm_mode);
+        int* counter = reinterpret_cast<int*>(ar_mem + lg_off + lg_logits_bytes() + 128);  // local
+        CK(logits_push_launch(logits_shard.p, ar_peer[0] + lg_off, rows, (int)(Vl * lsz), (int)((size_t)V * lsz),
+                              (int)((size_t)rank * Vl * lsz), flags0 + rank, counter, ds<uint32_t>(off_epoch) + 2,
+                              (uint32_t)lg_idx, stream));
+      }
+      ++n_launches;
+    } else {
+      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, rows, Vl, H, lm_mode);
+      NK(nccl().AllGather(logits_shard.p, logits_gather.p, (size_t)rows * Vl * lsz, ncclInt8, comm, stream));
+      if (rank == 0) {
+        CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const uint4*)logits_gather.p,
+                    (uint4*)logits.p, rows, (int)(Vl * lsz / 16), tp));
+        ++n_launches;
+      }
+    }
+  }
+
+  void plp_pass(int m, int need_norm, int T, size_t copy_bytes, int lg_idx) {
     const tgis_config& c = cfg;
     const int H = c.hidden, V = c.vocab;
     CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
@@ -961,20 +1015,9 @@ struct tgis_engine {
     }
     CK(gather_rows_launch(xn.p, ds<int32_t>(off_samplesrc), last_hidden.p, m, H, stream));
     ++n_launches;
-    const int lm_mode = logits_bf16 ? 0 : 1;
-    if (tp == 1) {
-      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits.p, m, V, H, lm_mode);
-    } else {
-      gemm(xm_last, m_lm, last_hidden.p, lm_head, logits_shard.p, m, Vl, H, lm_mode);
-      NK(nccl().AllGather(logits_shard.p, logits_gather.p, (size_t)m * Vl * lsz, ncclInt8, comm, stream));
-      if (rank == 0) {
-        CK(launch_k(gather_relayout_kernel, dim3(148 * 4), dim3(256), 0, stream, (const uint4*)logits_gather.p,
-                    (uint4*)logits.p, m, (int)(Vl * lsz / 16), tp));
-        ++n_launches;
-      }
-    }
+    lm_head_logits(m, lg_idx);
     if (rank == 0) {
-      CK(sampler_launch(logits.p, logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words,
+      CK(sampler_launch(logits_ptr(), logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), m, seen_bitmap.p, bitmap_words,
                         samp_scratch.p, d_samp_out.p, stream, /*any_complex=*/0, num_sms));
       ++n_launches;
       CK(cudaMemcpyAsync(h_plp_out, d_samp_out.p, sizeof(SampleOut) * m, cudaMemcpyDeviceToHost, stream));
@@ -1007,7 +1050,7 @@ struct tgis_engine {
   // and the tensor-parallel workers run the same function on the same header.
   void exec_step(const StepHeader& h) {
     if (h.kind == 1) {
-      plp_pass(h.R, h.need_norm, h.T, h.copy_bytes);
+      plp_pass(h.R, h.need_norm, h.T, h.copy_bytes, h.lg_idx);
       return;
     }
     if (!h.graphable) {
@@ -1148,14 +1191,18 @@ struct tgis_engine {
     const int max_splits_step = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
     decode_items_build(hs<DecItem>(items_off(S)), seqs, decids, n_dec, bt, bt_stride);
     const size_t copy_bytes = items_off(S) + sizeof(DecItem) * (1 + (size_t)n_dec * max_splits_step);
+    const double t_ev0 = debug_launch ? now_s() : 0.0;
     CK(cudaEventRecord(ev0, stream));
     const bool graphable = cfg.use_cuda_graphs && (tp == 1 || tp_graphs) && !profiling && n_tiles == 0 && n_dec == S && R == S;
-    StepHeader hdr{T, n_dec, n_tiles, R, max_dec_kv, S, graphable ? 1 : 0, samp_complex, (uint64_t)copy_bytes, 0, 0};
+    StepHeader hdr{T, n_dec, n_tiles, R, max_dec_kv, S, graphable ? 1 : 0, samp_complex, (uint64_t)copy_bytes, 0, 0, 1, 0};
     if (tp > 1) {
       // exchange epochs of this step = staged base + index inside the step (ar_add_rmsnorm_kernel)
       uint32_t* eb = hs<uint32_t>(off_epoch);
       eb[0] = ar_epoch[0];
       eb[1] = ar_epoch[1];
+      lg_epoch += (uint32_t)lg_idx_step;  // gathers of the previous step (its own and its prompt-logprob passes)
+      eb[2] = lg_epoch;
+      lg_idx_step = (R > 0) ? 1 : 0;
       if (exchange_mode(T) != 0) {
         ar_epoch[0] += (uint32_t)cfg.n_layers;
         ar_epoch[1] += (uint32_t)cfg.n_layers;
@@ -1164,7 +1211,13 @@ struct tgis_engine {
     }
     exec_step(hdr);
     CK(cudaEventRecord(ev1, stream));
+    const double t_launched = debug_launch ? now_s() : 0.0;
     wait_step_end();
+    if (debug_launch) {
+      t_after_wait = now_s();
+      host_phases.push_back(HostPhase{(float)(1e6 * (t_ev0 - t_step_begin)), (float)(1e6 * (t_launched - t_ev0)),
+                                      (float)(1e6 * (t_after_wait - t_launched)), 0.f});
+    }
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     gpu_ms += ms;
@@ -1216,7 +1269,7 @@ struct tgis_engine {
           row.seed_lo = (uint32_t)pr.target;
           row.logits_row = i;
         }
-        StepHeader ph{T, 0, 0, m, 0, 0, 0, 0, (uint64_t)plp_bytes, 1, need_norm};
+        StepHeader ph{T, 0, 0, m, 0, 0, 0, 0, (uint64_t)plp_bytes, 1, need_norm, ++lg_idx_step, 0};
         if (tp > 1) publish_plan(ph);
         exec_step(ph);
         need_norm = 0;
@@ -1294,6 +1347,8 @@ struct tgis_engine {
 
   // one engine step; returns false when there was nothing to do
   bool step() {
+    if (debug_step_sleep_us > 0) usleep(debug_step_sleep_us);  // experiment: GPU idle time between steps
+    if (debug_launch) t_step_begin = now_s();
     // ---- intake
     {
       std::lock_guard<std::mutex> lk(mu);
@@ -1435,6 +1490,7 @@ struct tgis_engine {
         }
     }
     snapshot();
+    if (debug_launch && !host_phases.empty()) host_phases.back().post = (float)(1e6 * (now_s() - t_after_wait));
     return true;
   }
 

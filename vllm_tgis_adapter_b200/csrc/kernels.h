@@ -84,6 +84,13 @@ struct Ar2Peers {
 cudaError_t ar2_add_rmsnorm_launch(const Ar2Peers& peers, int tp, int rank, const uint32_t* epoch_base, uint32_t epoch_idx,
                                    __nv_bfloat16* residual, const __nv_bfloat16* w, __nv_bfloat16* out, int T, int hidden,
                                    float eps, cudaStream_t stream);
+// Vocab-parallel lm_head without NCCL: ranks > 0 push their shard into rank 0's logits buffer (peer memory) and raise a
+// flag there; rank 0 waits for the flags (elementwise.cu).  Sizes in bytes (multiples of 16).
+cudaError_t logits_push_launch(const void* shard, void* dst_peer0, int R, int Vl_bytes, int V_bytes, int col_bytes,
+                               uint32_t* remote_flag, int* local_counter, const uint32_t* epoch_base, uint32_t epoch_idx,
+                               cudaStream_t stream);
+cudaError_t logits_wait_launch(const uint32_t* flags, int tp, const uint32_t* epoch_base, uint32_t epoch_idx,
+                               cudaStream_t stream);
 // act[t, i] = bf16(silu(gate_up[t, i])) * gate_up[t, F + i]
 cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn, cudaStream_t stream);
 // gather rows: out[r, :] = x[rows[r], :]
@@ -154,7 +161,9 @@ cudaError_t attn_decode_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_
                                const __nv_bfloat16* v_cache, const DecItem* items, int max_entries,
                                const AttnSeq* seqs, const int32_t* seq_ids, int n_seqs, int max_splits, float* part_o,
                                float* part_ml, __nv_bfloat16* out, int out_ld, int n_q, int n_kv, float scale,
-                               int num_sms, cudaStream_t stream);
+                               int num_sms, cudaStream_t stream, int* arrive = nullptr);
+// arrive: [n_seqs * n_kv] ints, zero before the first launch (re-armed by the kernel): with it, the split merge runs inside
+// the streaming kernel (last-arriving warp per (sequence, kv head)) and attn_merge_kernel is not launched.
 // Prefill / chunked prefill (q_len >= 1), causal over the paged cache.
 cudaError_t attn_prefill_launch(const __nv_bfloat16* qkv, int qkv_ld, const __nv_bfloat16* k_cache,
                                 const __nv_bfloat16* v_cache, const AttnSeq* seqs, const int32_t* tile_seq,

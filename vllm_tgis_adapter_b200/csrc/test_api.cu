@@ -210,9 +210,12 @@ int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v
   decode_items_build(items.data(), seqs.data(), dec.data(), (int)dec.size(), block_table_host, bt_stride);
   Tmp<DecItem> d_items;
   KCK(d_items.upload(items.data(), items.size()));
+  Tmp<int> arrive;  // arrival counters of the in-kernel split merge (the launcher ignores them when that path is off)
+  KCK(arrive.alloc(nd * n_kv));
+  KCK(cudaMemset(arrive.p, 0, sizeof(int) * nd * n_kv));
   KCK(attn_decode_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)k_cache_dev, (const bf16*)v_cache_dev, d_items.p,
                          (int)dec.size() * max_splits, d_seqs.p, d_dec.p, (int)dec.size(), max_splits, po.p, pml.p,
-                         (bf16*)out_dev, out_ld, n_q, n_kv, scale, test_num_sms(), 0));
+                         (bf16*)out_dev, out_ld, n_q, n_kv, scale, test_num_sms(), 0, arrive.p));
   KCK(attn_prefill_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)k_cache_dev, (const bf16*)v_cache_dev, d_seqs.p,
                           d_tseq.p, d_tq0.p, (int)tseq.size(), d_bt.p, bt_stride, (bf16*)out_dev, out_ld, n_q, n_kv,
                           scale, 0));
@@ -249,6 +252,9 @@ int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const v
   Tmp<DecItem> d_items;
   KCK(d_items.upload(items.data(), items.size()));
   const int num_sms = test_num_sms();
+  Tmp<int> arrive;
+  KCK(arrive.alloc((size_t)n_seqs * n_kv));
+  KCK(cudaMemset(arrive.p, 0, sizeof(int) * (size_t)n_seqs * n_kv));
   cudaEvent_t e0, e1;
   KCK(cudaEventCreate(&e0));
   KCK(cudaEventCreate(&e1));
@@ -259,7 +265,7 @@ int tgis_k_attention_bench(const void* qkv_dev, const void* k_cache_dev, const v
     const char* vc = (const char*)v_cache_dev + (size_t)l * layer_stride_bytes;
     KCK(attn_decode_launch((const bf16*)qkv_dev, qkv_ld, (const bf16*)kc, (const bf16*)vc, d_items.p,
                            n_seqs * max_splits, d_seqs.p, nullptr, n_seqs, max_splits, po.p, pml.p, (bf16*)out_dev,
-                           out_ld, n_q, n_kv, scale, num_sms, 0));
+                           out_ld, n_q, n_kv, scale, num_sms, 0, arrive.p));
   }
   KCK(cudaEventRecord(e1, 0));
   KCK(cudaDeviceSynchronize());
