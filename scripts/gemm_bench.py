@@ -13,10 +13,16 @@ import tgis_gpu_utils as g  # noqa: E402
 
 SHAPES = [("qkv", 6144, 4096), ("o", 4096, 4096), ("gate_up", 28672, 4096), ("down", 4096, 14336),
           ("lm_head", 128256, 4096)]
+TS = (16, 32, 64, 128, 256, 2048, 8192)
+if len(sys.argv) > 1 and sys.argv[1] == "tp":   # per-GPU shard shapes of the tensor-parallel named configs
+    SHAPES = [("8b_tp4_qkv", 1536, 4096), ("8b_tp4_o", 4096, 1024), ("8b_tp4_gate_up", 7168, 4096), ("8b_tp4_down", 4096, 3584),
+              ("70b_tp8_qkv", 1280, 8192), ("70b_tp8_o", 8192, 1024), ("70b_tp8_gate_up", 7168, 8192),
+              ("70b_tp8_down", 8192, 3584), ("70b_tp8_lm_head", 16032, 8192)]
+    TS = (32, 128, 256)
 PEAK = 6566.7
 res = []
 for name, N, K in SHAPES:
-    for T in (16, 32, 64, 128, 256, 2048, 8192):
+    for T in TS:
         if name == "lm_head" and T > 256:
             continue
         n_buf = max(2, int(600e6 // (N * K * 2)) + 1) if T <= 256 else 1
@@ -44,4 +50,4 @@ for name, N, K in SHAPES:
         del ws, x, y
         torch.cuda.empty_cache()
 Path("gpurun_out").mkdir(exist_ok=True)
-Path("gpurun_out/gemm_bench.json").write_text(json.dumps(res, indent=1))
+Path("gpurun_out/gemm_bench_tp.json" if len(sys.argv) > 1 else "gpurun_out/gemm_bench.json").write_text(json.dumps(res, indent=1))

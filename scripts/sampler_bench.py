@@ -48,20 +48,25 @@ def rows_for(n, kind):
 
 res = []
 torch.manual_seed(0)
-for n, kind in [(32, "greedy"), (64, "greedy"), (128, "greedy"), (256, "greedy"), (32, "greedy_lp1"), (32, "greedy_lp11"),
-                (64, "cfg3"), (32, "cfg3"), (64, "topk_topp")]:
+ONLY = os.environ.get("SAMPLER_BENCH_ONLY")       # e.g. "64:cfg3,32:greedy" (ncu captures): just these cases, 2 launches each
+ITERS = 2 if ONLY else 50
+CASES = [(32, "greedy"), (64, "greedy"), (128, "greedy"), (256, "greedy"), (32, "greedy_lp1"), (32, "greedy_lp11"),
+                (64, "cfg3"), (32, "cfg3"), (64, "topk_topp")]
+if ONLY:
+    CASES = [(int(c.split(":")[0]), c.split(":")[1]) for c in ONLY.split(",")]
+for n, kind in CASES:
     logits = (torch.randn(n, V, device="cuda") * 1.3).to(torch.bfloat16)
     words = (V + 31) // 32
     bitmap = torch.zeros(n, words, dtype=torch.int32, device="cuda")
     bitmap[:, :20] = 0x55555555
     rows = rows_for(n, kind)
-    variants = [None] + ([1, 2, 4, 8] if kind == "greedy" else [2, 4] if kind == "cfg3" else [])
+    variants = [None] + ([] if ONLY else [1, 2, 4, 8] if kind == "greedy" else [2, 4] if kind == "cfg3" else [])
     for ncl in variants:
         if ncl is None:
             os.environ.pop("TGIS_SAMPLER_CLUSTER", None)
         else:
             os.environ["TGIS_SAMPLER_CLUSTER"] = str(ncl)
-        out, us = g.run_sampler(logits, rows, bitmap, iters=50, return_us=True)
+        out, us = g.run_sampler(logits, rows, bitmap, iters=ITERS, return_us=True)
         floor_us = n * V * 2 / HBM * 1e6
         res.append({"rows": n, "kind": kind, "cluster": ncl or "auto", "us": us, "hbm_floor_us": floor_us,
                     "logits_GBps": n * V * 2 / (us * 1e-6) / 1e9})

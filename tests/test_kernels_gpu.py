@@ -277,8 +277,8 @@ def test_attention_decode_split_kv(g, n_q, n_kv):
 
 @pytest.mark.parametrize("n_q,n_kv", [(8, 2), (8, 1), (2, 2)])
 def test_attention_inkernel_split_merge_is_bit_identical(g, n_q, n_kv, monkeypatch):
-    """The split merge done inside the streaming kernel by the last-arriving warp (default) against the separate
-    attn_merge_kernel (TGIS_ATTN_INKERNEL_MERGE=0): same sums in the same split order -> identical bits, run twice to
+    """The split merge done inside the streaming kernel by the last-arriving warp (TGIS_ATTN_INKERNEL_MERGE=1) against the
+    separate attn_merge_kernel (default): same sums in the same split order -> identical bits, run twice to
     cover the self re-arming arrival counters."""
     specs = [(c, 1) for c in (127, 128, 129, 255, 300, 575, 576, 1000, 2047, 31)]
     outs = []

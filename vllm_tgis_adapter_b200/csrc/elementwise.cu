@@ -96,10 +96,18 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
   __shared__ float red[NORM_THREADS / 32];
   STL_ENTER(1);
   griddep_launch();
-  griddep_wait();
-  STL_WAITED();
   const size_t base = (size_t)blockIdx.x * hidden;
   const int nvec = hidden / 8;
+  // the norm weights are static: fetch them (one HBM round trip per layer, they are read once per step) BEFORE waiting
+  // for the producer of x
+  BF8 wv[NORM_MAX_VEC];
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_VEC; ++j) {
+    const int i = threadIdx.x + j * NORM_THREADS;
+    if (i < nvec) wv[j] = reinterpret_cast<const BF8*>(w)[i];
+  }
+  griddep_wait();
+  STL_WAITED();
   BF8 z[NORM_MAX_VEC];
   float ss = 0.f;
 #pragma unroll
@@ -127,12 +135,11 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
   for (int j = 0; j < NORM_MAX_VEC; ++j) {
     const int i = threadIdx.x + j * NORM_THREADS;
     if (i < nvec) {
-      BF8 wv = reinterpret_cast<const BF8*>(w)[i];
       BF8 o;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float nrm = bf16_round(__bfloat162float(z[j].v[e]) * rs);
-        o.v[e] = __float2bfloat16_rn(nrm * __bfloat162float(wv.v[e]));
+        o.v[e] = __float2bfloat16_rn(nrm * __bfloat162float(wv[j].v[e]));
       }
       reinterpret_cast<BF8*>(out + base)[i] = o;
     }
@@ -348,7 +355,8 @@ ar2_add_rmsnorm_kernel(Ar2Peers P, int tp, int rank, const uint32_t* __restrict_
       const int i = threadIdx.x + j * NORM_THREADS;
       if (i < nvec) dst[i] = reinterpret_cast<const uint4*>(P.own + base)[i];
     }
-    __threadfence_system();
+    // publish: CTA barrier, then ONE system-scope release by thread 0 (cumulative over the barrier: covers every thread's
+    // stores) -- no per-thread fence
     __syncthreads();
     if (threadIdx.x == 0) st_release_sys_u32(flags1(owner) + rank * AR_MAX_ROWS + row, epoch);
     // ---- 3a. wait for the reduced row
@@ -391,7 +399,6 @@ ar2_add_rmsnorm_kernel(Ar2Peers P, int tp, int rank, const uint32_t* __restrict_
           if (q != rank) recv2(q)[(size_t)row * nvec + i] = sum[j];
       }
     }
-    __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < tp && (int)threadIdx.x != rank) st_release_sys_u32(flags2(threadIdx.x) + row, epoch);
   }

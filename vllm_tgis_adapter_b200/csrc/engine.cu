@@ -320,7 +320,7 @@ struct tgis_engine {
   bool graph_copy_outside = true;     // TGIS_GRAPH_COPY_OUTSIDE: metadata H2D / result D2H as plain stream copies
                                       // around the graph launch instead of memcpy nodes inside the graph
   bool capturing = false;
-  bool attn_inkernel_merge = true;    // TGIS_ATTN_INKERNEL_MERGE (read by attention.cu as well): launch accounting only
+  bool attn_inkernel_merge = false;   // TGIS_ATTN_INKERNEL_MERGE (read by attention.cu as well): launch accounting only
   int debug_step_sleep_us = 0;        // TGIS_STEP_SLEEP_US (experiment)
   bool debug_launch = false;          // TGIS_DEBUG_LAUNCH=1: host time spent inside cudaGraphLaunch, printed at destroy
   double graph_launch_host_s = 0;

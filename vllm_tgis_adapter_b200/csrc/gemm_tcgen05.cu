@@ -694,6 +694,11 @@ int gemm_grid_size(int T, int N, int K, int num_sms) {
   if (tiles <= num_sms / 2) {
     int split = (int)(num_sms / tiles);
     if (split > KB / 4) split = KB / 4 > 0 ? KB / 4 : 1;
+    // Above 64 tokens a tile's partial is >= 64 KB: a global-memory fix-up in which ONE last-arriving CTA sums more than
+    // 8 of them serialises (70B TP=8 qkv at T = 256: 10 tiles x 14 contributors, 1.8 MB per tile through 128 threads).
+    // Cap the split at the largest cluster (8): the reduction then runs in distributed shared memory, spread over the
+    // cluster's CTAs by token.
+    if (BT > 64 && split > 8) split = 8;
     grid = (int)(tiles * split);
   }
   if (const char* e = getenv("TGIS_GEMM_MAX_CTAS")) {  // experiment knob (scripts/gemm_cta_sweep.py)
