@@ -44,6 +44,8 @@ int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v
 /* host-only: GEMM launch plan for a shape: token tile (16..256), grid, even-split factor (0: stream-K + global fix-up) */
 int tgis_k_gemm_plan(int32_t T, int32_t N, int32_t K, int32_t num_sms, int32_t* bt_out, int32_t* grid_out,
                      int32_t* even_split_out);
+/* weight rows per GEMM unit for a T-token launch (128 x weight tiles per shared activation tile) */
+int tgis_k_gemm_unit_rows(int32_t T);
 /* host-only: the decode work-item list of a step (csrc/kernels.h DecItem: q_row, kv_len, seq | split << 16, 0,
  * blocks[4]); record 0 holds the entry count; entries are listed longest first */
 int tgis_k_decode_items(const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_stride,

@@ -19,6 +19,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "tp":   # per-GPU shard shapes of the te
               ("70b_tp8_qkv", 1280, 8192), ("70b_tp8_o", 8192, 1024), ("70b_tp8_gate_up", 7168, 8192),
               ("70b_tp8_down", 8192, 3584), ("70b_tp8_lm_head", 16032, 8192)]
     TS = (32, 128, 256)
+if len(sys.argv) > 1 and sys.argv[1] == "decode":   # quick A/B of the decode-shaped launches only
+    TS = (32, 64, 128)
 PEAK = 6566.7
 res = []
 for name, N, K in SHAPES:
@@ -50,4 +52,4 @@ for name, N, K in SHAPES:
         del ws, x, y
         torch.cuda.empty_cache()
 Path("gpurun_out").mkdir(exist_ok=True)
-Path("gpurun_out/gemm_bench_tp.json" if len(sys.argv) > 1 else "gpurun_out/gemm_bench.json").write_text(json.dumps(res, indent=1))
+Path(f"gpurun_out/gemm_bench_{sys.argv[1]}.json" if len(sys.argv) > 1 else "gpurun_out/gemm_bench.json").write_text(json.dumps(res, indent=1))

@@ -108,7 +108,9 @@ def test_gemm_launch_plan_host_logic():
             bt, grid, split = bt.value, grid.value, split.value
             assert bt >= T and bt in (16, 32, 64, 128, 256)
             assert 1 <= grid <= sms
-            n_tiles, kb = (N + 127) // 128, (K + 63) // 64
+            unit = lib.tgis_k_gemm_unit_rows(T)       # 128; 256 with the TGIS_GEMM_NW=2 experiment
+            assert unit in (128, 256)
+            n_tiles, kb = (N + unit - 1) // unit, (K + 63) // 64
             total = n_tiles * kb
             bounds = [total * c // grid for c in range(grid + 1)]
             assert bounds[0] == 0 and bounds[-1] == total and all(b1 > b0 for b0, b1 in zip(bounds, bounds[1:]))

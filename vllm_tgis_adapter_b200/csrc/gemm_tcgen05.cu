@@ -34,20 +34,28 @@ constexpr int GEMM_BN = 128;  // weight rows per tile (UMMA_M)
 constexpr int GEMM_BK = 64;   // k per stage (one 128-byte swizzle row of bf16)
 constexpr int GEMM_THREADS = 192;
 
-template <int BT>
+// NW = weight tiles (of GEMM_BN = 128 rows) per unit that share ONE activation tile: every unit re-reads its [BT x 64]
+// activation tile per k-block, and with NW = 2 that tile feeds two MMAs (two accumulators), halving the activation bytes
+// per weight byte.  An experiment (TGIS_GEMM_NW=2, see gemm_nw()): measured slower, so NW = 1 is what runs.
+template <int BT, int NW>
 struct GemmCfg {
-  static constexpr int W_BYTES = GEMM_BN * GEMM_BK * 2;
+  static constexpr int W_TILE_BYTES = GEMM_BN * GEMM_BK * 2;
+  static constexpr int W_BYTES = NW * W_TILE_BYTES;
   static constexpr int X_BYTES = BT * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+#ifndef TGIS_GEMM_SMEM_KB
+#define TGIS_GEMM_SMEM_KB 200
+#endif
+  static constexpr int STAGES_RAW = (TGIS_GEMM_SMEM_KB * 1024) / STAGE_BYTES;
 #ifndef TGIS_GEMM_DECODE_STAGES
 #define TGIS_GEMM_DECODE_STAGES 8
 #endif
-  // decode-shaped launches (BT <= 64) may run with a shallower ring so that two consecutive GEMM kernels' CTAs fit
-  // on one SM (<= ~110 KB each): under PDL the next GEMM then prefetches its weights during this one's fix-up tail
-  static constexpr int STAGES_CAP = BT <= 64 ? TGIS_GEMM_DECODE_STAGES : 8;
+  static constexpr int STAGES_CAP = BT <= 64 ? TGIS_GEMM_DECODE_STAGES : 12;
   static constexpr int STAGES = STAGES_RAW > STAGES_CAP ? STAGES_CAP : STAGES_RAW;
-  static constexpr int TMEM_COLS = (2 * BT) < 32 ? 32 : (2 * BT);
+  static constexpr int ACC_COLS = NW * BT;                               // TMEM columns of one unit's accumulators
+  static constexpr int N_ACC = (2 * ACC_COLS <= 512) ? 2 : 1;            // double-buffered when it fits the 512 columns
+  static constexpr int TMEM_COLS = (N_ACC * ACC_COLS) < 32 ? 32 : (N_ACC * ACC_COLS);
+  static constexpr int PART_FLOATS = NW * BT * GEMM_BN;                  // fp32 partial of one unit
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -196,8 +204,8 @@ __device__ __forceinline__ void qkv_rope_store(const GemmRope& rope, int head, i
   }
 }
 
-template <int BT>
-__global__ void __launch_bounds__(GEMM_THREADS, (BT <= 64 && TGIS_GEMM_DECODE_STAGES <= 5) ? 2 : 1)
+template <int BT, int NW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
                          void* __restrict__ Yv, int ldy, int T, int N, int K, float* __restrict__ ws,
                          int* __restrict__ counters, int stream_weights, int out_f32,
@@ -206,8 +214,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   // output: bf16 (rounded once from the fp32 accumulator, = F.linear in model dtype) or raw fp32 (lm_head logits)
   __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(Yv);
   float* __restrict__ Yf = reinterpret_cast<float*>(Yv);
-  using Cfg = GemmCfg<BT>;
+  using Cfg = GemmCfg<BT, NW>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int BNW = GEMM_BN * NW;            // weight rows per unit
+  constexpr int ACC_COLS = Cfg::ACC_COLS;
+  constexpr int N_ACC = Cfg::N_ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;
@@ -223,7 +234,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   const int warp = threadIdx.x >> 5;
   STL_ENTER(2 | (N << 8));
   if (threadIdx.x == 0) TL(0);  // kernel entry
-  const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
+  const int n_tiles = (N + BNW - 1) / BNW;     // units along N
   const int t_tiles = (T + BT - 1) / BT;
   const int KB = (K + GEMM_BK - 1) / GEMM_BK;
   const int ncta = gridDim.x, cta = blockIdx.x;
@@ -276,7 +287,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         c.tile = tile;
         int n_tile, t_tile;
         tile_decode(sched, tile, n_tile, t_tile);
-        c.w_row = n_tile * GEMM_BN;
+        c.w_row = n_tile * BNW;
         c.x_row = t_tile * BT;
       };
       auto cur_init = [&](Cur& c) {
@@ -304,9 +315,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         }
       };
       auto issue_w = [&](const Cur& c, int stage) {
-        void* dst = smem_w + stage * Cfg::W_BYTES;
-        if (stream_weights) tma_load_2d_hint(&wmap, &full_bar[stage], dst, c.kb * GEMM_BK, c.w_row, pol_w);
-        else tma_load_2d(&wmap, &full_bar[stage], dst, c.kb * GEMM_BK, c.w_row);
+#pragma unroll
+        for (int h = 0; h < NW; ++h) {  // NW boxes of 128 rows (rows beyond N are zero-filled by TMA and still counted)
+          void* dst = smem_w + stage * Cfg::W_BYTES + h * Cfg::W_TILE_BYTES;
+          if (stream_weights) tma_load_2d_hint(&wmap, &full_bar[stage], dst, c.kb * GEMM_BK, c.w_row + h * GEMM_BN, pol_w);
+          else tma_load_2d(&wmap, &full_bar[stage], dst, c.kb * GEMM_BK, c.w_row + h * GEMM_BN);
+        }
       };
       const int n_pre = n_kb < STAGES ? n_kb : STAGES;
       Cur wc, xc;
@@ -349,7 +363,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           const int n2 = (int)((e2 - b2) < nxt.kb_prefetch ? (e2 - b2) : nxt.kb_prefetch);
           int tile2 = (int)(b2 / nxt.KB), kb2 = (int)(b2 % nxt.KB);
           for (int i = 0; i < n2; ++i) {
-            tma_prefetch_2d(&next_wmap, kb2 * GEMM_BK, tile2 * GEMM_BN);
+            for (int h = 0; h < NW; ++h) tma_prefetch_2d(&next_wmap, kb2 * GEMM_BK, tile2 * BNW + h * GEMM_BN);
             if (++kb2 == nxt.KB) { kb2 = 0; ++tile2; }
           }
         }
@@ -367,18 +381,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
     while (it.next(tile, kb0, kb1, slot)) {
       mbar_wait(&tmem_empty[acc], ((acc_bits >> acc) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BT;
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_w + stage * Cfg::W_BYTES));
           const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_x + stage * Cfg::X_BYTES));
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in 16-byte units on the start address
-            tc_mma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                       (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int h = 0; h < NW; ++h) {
+            const uint64_t a_desc =
+                make_smem_desc_sw128(smem_u32(smem_w + stage * Cfg::W_BYTES + h * Cfg::W_TILE_BYTES));
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in 16-byte units on the start address
+              tc_mma_f16(d_tmem + h * BT, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);
@@ -390,7 +408,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         }
       }
       acc_bits ^= (1u << acc);
-      acc ^= 1;
+      acc = (acc + 1) % N_ACC;
     }
   } else {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
@@ -404,55 +422,58 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
     while (it.next(tile, kb0, kb1, slot)) {
       int n_tile, t_tile;
       tile_decode(sched, tile, n_tile, t_tile);
-      const int n = n_tile * GEMM_BN + row;
       const int t_base = t_tile * BT;
       const int t_valid = min(BT, T - t_base);
       const bool partial = (kb0 > 0) || (kb1 < KB);
       mbar_wait(&tmem_full[acc], (acc_bits >> acc) & 1);
       tc_fence_after();
       if (ep_tid == 0) TL(5);  // accumulator ready (all MMAs of the unit retired)
-      const uint32_t taddr = tmem_base + acc * BT + ((uint32_t)(sub * 32) << 16);
-      float* my_ws = ws + ((size_t)(cta * 2 + slot) * BT) * GEMM_BN;
+      float* my_ws = ws + (size_t)(cta * 2 + slot) * Cfg::PART_FLOATS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BT; c0 += 16) {
-        if (c0 >= t_valid) break;
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(taddr + c0, r);
-        tmem_ld_wait();
-        if (!partial) {
-          if (out_f32 == 2) {
-            // fused SwiGLU: weight rows are interleaved (2j = gate_j, 2j+1 = up_j) so the pair sits in adjacent
-            // lanes; even lanes produce act[t, n/2]
+      for (int h = 0; h < NW; ++h) {  // the unit's NW accumulators = weight tiles n_tile * NW + h
+        const int n = (n_tile * NW + h) * GEMM_BN + row;
+        const uint32_t taddr = tmem_base + acc * ACC_COLS + h * BT + ((uint32_t)(sub * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BT; c0 += 16) {
+          if (c0 >= t_valid) break;
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(taddr + c0, r);
+          tmem_ld_wait();
+          if (!partial) {
+            if (out_f32 == 2) {
+              // fused SwiGLU: weight rows are interleaved (2j = gate_j, 2j+1 = up_j) so the pair sits in adjacent
+              // lanes; even lanes produce act[t, n/2]
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), 1);
-              if ((row & 1) == 0 && n < N && c0 + j < t_valid)
-                Y[(size_t)(t_base + c0 + j) * ldy + (n >> 1)] = swiglu_bf16(__uint_as_float(r[j]), other);
+              for (int j = 0; j < 16; ++j) {
+                const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(r[j]), 1);
+                if ((row & 1) == 0 && n < N && c0 + j < t_valid)
+                  Y[(size_t)(t_base + c0 + j) * ldy + (n >> 1)] = swiglu_bf16(__uint_as_float(r[j]), other);
+              }
+            } else if (n < N) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < t_valid) {
+                  const size_t o = (size_t)(t_base + c0 + j) * ldy + n;
+                  if (out_f32) Yf[o] = __uint_as_float(r[j]);
+                  else Y[o] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                }
             }
-          } else if (n < N) {
+          } else {
+            // split tile: fp32 partial to the global workspace, or (cluster mode) to this CTA's own shared memory --
+            // the ring is idle by now: this CTA's only unit has retired all its MMAs
+            float* dst = (cluster_split > 0 ? reinterpret_cast<float*>(smem) : my_ws) + h * (BT * GEMM_BN);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < t_valid) {
-                const size_t o = (size_t)(t_base + c0 + j) * ldy + n;
-                if (out_f32) Yf[o] = __uint_as_float(r[j]);
-                else Y[o] = __float2bfloat16_rn(__uint_as_float(r[j]));
-              }
+              if (c0 + j < t_valid) dst[(size_t)(c0 + j) * GEMM_BN + row] = __uint_as_float(r[j]);
           }
-        } else {
-          // split tile: fp32 partial to the global workspace, or (cluster mode) to this CTA's own shared memory --
-          // the ring is idle by now: this CTA's only unit has retired all its MMAs
-          float* dst = cluster_split > 0 ? reinterpret_cast<float*>(smem) : my_ws;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < t_valid) dst[(size_t)(c0 + j) * GEMM_BN + row] = __uint_as_float(r[j]);
         }
       }
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      // accumulators drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
       acc_bits ^= (1u << acc);
-      acc ^= 1;
+      acc = (acc + 1) % N_ACC;
 
       if (ep_tid == 0) TL(6);  // TMEM drained, partial/direct stores issued
       if (partial && cluster_split > 0) {
@@ -480,7 +501,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           constexpr int FIX_C = 3, FIX_T = 8;
           const int r4 = (ep_tid & 31) * 4;   // first of this thread's 4 rows
           const int tq = ep_tid >> 5;         // token phase 0..3
-          const int n4 = n_tile * GEMM_BN + r4;
+#pragma unroll 1
+          for (int h = 0; h < NW; ++h) {
+          const int nt = n_tile * NW + h;     // weight tile (= head of the qkv projection)
+          const int n4 = nt * GEMM_BN + r4;
           for (int tb = tq; tb < t_valid; tb += 4 * FIX_T) {
             float4 acc[FIX_T];
 #pragma unroll
@@ -493,7 +517,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
                 const bool cv = c <= c_last;
                 const long long cb = cv ? (total * c) / ncta : 0;
                 const int cslot = ((int)(cb / KB) == tile - sched.sk_tile0) ? 0 : 1;
-                const float* p = ws + ((size_t)((cv ? c : c_first) * 2 + cslot) * BT) * GEMM_BN + r4;
+                const float* p = ws + (size_t)((cv ? c : c_first) * 2 + cslot) * Cfg::PART_FLOATS + h * (BT * GEMM_BN) + r4;
 #pragma unroll
                 for (int j = 0; j < FIX_T; ++j) {
                   const int t = tb + 4 * j;
@@ -515,7 +539,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
                 const size_t o = (size_t)(t_base + t) * ldy + n4;
                 const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
                 if (rope.positions != nullptr) {  // qkv projection: RoPE + KV scatter (warp-uniform t and tile)
-                  qkv_rope_store(rope, n_tile, t_base + t, r4, av, Y + o);
+                  qkv_rope_store(rope, nt, t_base + t, r4, av, Y + o);
                 } else if (out_f32 == 2) {  // fused SwiGLU: rows (n4, n4+1) and (n4+2, n4+3) are (gate, up) pairs
                   __nv_bfloat16* yo = Y + (size_t)(t_base + t) * ldy + (n4 >> 1);
                   if (n4 + 1 < N) yo[0] = swiglu_bf16(av[0], av[1]);
@@ -540,6 +564,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
               }
             }
           }
+          }
           if (ep_tid == 0) counters[tile] = 0;
           if (ep_tid == 0) TL(8);  // ordered reduction done (last arriver only)
         }
@@ -556,16 +581,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       const int crank = (int)cluster_ctarank();
       const int r4 = (ep_tid & 31) * 4;   // this thread's 4 consecutive weight rows
       const int tq = ep_tid >> 5;         // token phase 0..3
-      const int n4 = cl_tile * GEMM_BN + r4;
       const uint32_t stg = smem_u32(smem);
       constexpr int FIX_T = 4;
+#pragma unroll 1
+      for (int h = 0; h < NW; ++h) {
+      const int nt = cl_tile * NW + h;    // weight tile (= head of the qkv projection)
+      const int n4 = nt * GEMM_BN + r4;
+      const uint32_t hoff = (uint32_t)(h * BT * GEMM_BN * 4);
       // tokens of this CTA: t = crank + split * i; thread takes i = tq (mod 4)
       for (int i0 = tq; crank + cluster_split * i0 < cl_tvalid; i0 += 4 * FIX_T) {
         float4 acc[FIX_T];
 #pragma unroll
         for (int j = 0; j < FIX_T; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c = 0; c < cluster_split; ++c) {  // contributor rank order = k order: deterministic
-          const uint32_t peer = dsmem_addr(stg, (uint32_t)c);
+          const uint32_t peer = dsmem_addr(stg, (uint32_t)c) + hoff;
           float4 v[FIX_T];
 #pragma unroll
           for (int j = 0; j < FIX_T; ++j) {
@@ -584,7 +613,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
             const size_t o = (size_t)t * ldy + n4;
             const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
             if (rope.positions != nullptr) {
-              qkv_rope_store(rope, cl_tile, t, r4, av, Y + o);
+              qkv_rope_store(rope, nt, t, r4, av, Y + o);
             } else if (out_f32 == 2) {
               __nv_bfloat16* yo = Y + (size_t)t * ldy + (n4 >> 1);
               if (n4 + 1 < N) yo[0] = swiglu_bf16(av[0], av[1]);
@@ -608,6 +637,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
             }
           }
         }
+      }
       }
     }
     cluster_sync_all();  // nobody exits while a peer may still read its shared memory
@@ -678,27 +708,44 @@ int gemm_pick_bt(int T) {
   return 256;
 }
 
-size_t gemm_workspace_bytes(int num_sms) { return (size_t)num_sms * 2 * 256 * GEMM_BN * sizeof(float); }
+// Weight tiles per unit (GemmCfg).  1 everywhere by default.  TGIS_GEMM_NW=2 makes decode-shaped launches share one
+// activation tile between two weight tiles (half the activation re-reads per weight byte): built, parity-green, and
+// MEASURED SLOWER (profiles/r02_gemm_nw_ab.log: gate_up 46 -> 55 us at T = 32, down 31 -> 50 us at T = 64, decode step
+// 3.93 -> 5.05 ms at batch 32): halving the tile count doubles the partial size of every split-K reduction and leaves 5
+// ring stages instead of 8, while the activation re-reads it removes were not what bounds these launches.
+int gemm_nw(int T) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TGIS_GEMM_NW");
+    v = (e && e[0] == '2') ? 2 : 1;
+  }
+  return T <= 256 ? v : 1;
+}
+static int gemm_bn(int T) { return GEMM_BN * gemm_nw(T); }
+
+size_t gemm_workspace_bytes(int num_sms) { return (size_t)num_sms * 2 * 2 * 256 * GEMM_BN * sizeof(float); }
 
 // Grid size of a launch (pure function of the shape: the NEXT kernel's grid must be known one launch ahead)
 int gemm_grid_size(int T, int N, int K, int num_sms) {
-  const int BT = gemm_pick_bt(T);
-  const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
+  const int BT = gemm_pick_bt(T), BN = gemm_bn(T);
+  const int n_tiles = (N + BN - 1) / BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
   long long total = (long long)n_tiles * t_tiles * KB;
   // do not cut finer than 4 k-blocks per CTA: tiny problems use fewer CTAs
   long long max_ctas = (total + 3) / 4;
   int grid = (int)(max_ctas < num_sms ? (max_ctas < 1 ? 1 : max_ctas) : num_sms);
-  // few tiles (decode-shaped qkv / o / down): split every tile by the same integer factor so each CTA owns exactly
+  // few tiles (decode-shaped qkv / o / down at decode): split every tile by the same integer factor so each CTA owns exactly
   // one unit inside one tile (one fix-up round instead of two; costs <= 1/(split+1) of the SMs)
   const long long tiles = (long long)n_tiles * t_tiles;
   if (tiles <= num_sms / 2) {
     int split = (int)(num_sms / tiles);
     if (split > KB / 4) split = KB / 4 > 0 ? KB / 4 : 1;
-    // Above 64 tokens a tile's partial is >= 64 KB: a global-memory fix-up in which ONE last-arriving CTA sums more than
-    // 8 of them serialises (70B TP=8 qkv at T = 256: 10 tiles x 14 contributors, 1.8 MB per tile through 128 threads).
-    // Cap the split at the largest cluster (8): the reduction then runs in distributed shared memory, spread over the
-    // cluster's CTAs by token.
-    if (BT > 64 && split > 8) split = 8;
+    // More than 8 contributors per tile would have to meet in a global-memory fix-up in which ONE last-arriving CTA sums
+    // all partials (70B TP=8 qkv at T = 256: 1.8 MB per tile through 128 threads).  Cap the split at the largest
+    // cluster: the reduction then runs in distributed shared memory, spread over the cluster's CTAs by token.
+    if (split > 8) split = 8;
+    // large token tiles: a partial is >= 64 KB per weight tile; splitting a short k-range (o-proj shards) costs more in
+    // partial traffic than the extra SMs bring -- keep at least 16 k-blocks per CTA
+    while (BT > 64 && split > 1 && KB / split < 16) --split;
     grid = (int)(tiles * split);
   }
   if (const char* e = getenv("TGIS_GEMM_MAX_CTAS")) {  // experiment knob (scripts/gemm_cta_sweep.py)
@@ -710,8 +757,8 @@ int gemm_grid_size(int T, int N, int K, int num_sms) {
 
 // Even-split launches (every tile cut into `split` k-ranges owned by `split` consecutive CTAs): the factor, or 0.
 int gemm_even_split(int T, int N, int K, int num_sms) {
-  const int BT = gemm_pick_bt(T);
-  const int n_tiles = (N + GEMM_BN - 1) / GEMM_BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
+  const int BT = gemm_pick_bt(T), BN = gemm_bn(T);
+  const int n_tiles = (N + BN - 1) / BN, t_tiles = (T + BT - 1) / BT, KB = (K + GEMM_BK - 1) / GEMM_BK;
   const long long tiles = (long long)n_tiles * t_tiles;
   if (t_tiles != 1 || tiles > num_sms / 2) return 0;
   const int grid = gemm_grid_size(T, N, K, num_sms);
@@ -726,7 +773,7 @@ GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_
   GemmNext n{};
   const int BT = gemm_pick_bt(T_next);
   if ((T_next + BT - 1) / BT != 1) return n;  // only decode-shaped successors (one token tile) are prefetched
-  n.n_tiles = (N_next + GEMM_BN - 1) / GEMM_BN;
+  n.n_tiles = (N_next + gemm_bn(T_next) - 1) / gemm_bn(T_next);
   n.KB = (K_next + GEMM_BK - 1) / GEMM_BK;
   n.grid = gemm_grid_size(T_next, N_next, K_next, num_sms);
   n.kb_prefetch = kb_prefetch;
@@ -734,17 +781,22 @@ GemmNext gemm_next_desc(int T_next, int N_next, int K_next, int num_sms, int kb_
 }
 
 // cluster mode: on-chip split-K reduction when every tile is split evenly over <= 8 consecutive CTAs, the fp32 partial
-// fits the drained ring, and all clusters can be co-resident (checked once per (BT, split)).  Returns the split or 0.
-template <int BT>
+// fits the drained ring, and all clusters can be co-resident (checked once per (BT, NW, split, grid)).  Returns the
+// split or 0.
+template <int BT, int NW>
 static int cluster_split_bt(int T, int N, int K, int num_sms) {
-  using Cfg = GemmCfg<BT>;
-  static int cluster_ok[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 0 unknown, 1 yes, -1 no
+  using Cfg = GemmCfg<BT, NW>;
+  static int cluster_ok[9][160];  // [split][grid / split]: 0 unknown, 1 yes, -1 no
   int split = gemm_cluster_enabled() ? gemm_even_split(T, N, K, num_sms) : 0;
-  if (split > 8 || (size_t)BT * GEMM_BN * sizeof(float) > (size_t)Cfg::STAGES * Cfg::STAGE_BYTES) split = 0;
-  if (split > 0 && cluster_ok[split] == 0) {
+  if (split > 8 || (size_t)Cfg::PART_FLOATS * sizeof(float) > (size_t)Cfg::STAGES * Cfg::STAGE_BYTES) split = 0;
+  if (split == 0) return 0;
+  const int grid = gemm_grid_size(T, N, K, num_sms);
+  const int nc = grid / split;
+  if (nc >= 160) return 0;
+  if (cluster_ok[split][nc] == 0) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
       attr_set = true;
     }
     cudaLaunchConfig_t qc{};
@@ -759,38 +811,43 @@ static int cluster_split_bt(int T, int N, int K, int num_sms) {
     qc.attrs = qa;
     qc.numAttrs = 1;
     int n_clusters = 0;
-    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, gemm_bf16_tcgen05_kernel<BT>, &qc);
+    const cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, gemm_bf16_tcgen05_kernel<BT, NW>, &qc);
     // All clusters of the launch must be co-resident: a GPC only hosts floor(SMs / split) of them, and one cluster left
     // over for a second wave doubles the launch time (measured: qkv with 48 clusters of 3 when 47 fit).
-    cluster_ok[split] = (qe == cudaSuccess && n_clusters * split >= gemm_grid_size(T, N, K, num_sms)) ? 1 : -1;
+    cluster_ok[split][nc] = (qe == cudaSuccess && n_clusters >= nc) ? 1 : -1;
     if (getenv("TGIS_GEMM_DEBUG"))
-      fprintf(stderr, "[gemm] BT=%d split=%d: %d clusters fit, grid %d -> cluster mode %s\n", BT, split, n_clusters,
-              gemm_grid_size(T, N, K, num_sms), cluster_ok[split] == 1 ? "on" : "off");
+      fprintf(stderr, "[gemm] BT=%d NW=%d split=%d: %d clusters fit, grid %d -> cluster mode %s\n", BT, NW, split,
+              n_clusters, grid, cluster_ok[split][nc] == 1 ? "on" : "off");
     if (qe != cudaSuccess) cudaGetLastError();
   }
-  return (split > 0 && cluster_ok[split] == 1) ? split : 0;
+  return cluster_ok[split][nc] == 1 ? split : 0;
+}
+
+template <int BT>
+static int cluster_split_nw(int T, int N, int K, int num_sms) {
+  return gemm_nw(T) == 2 ? cluster_split_bt<BT, 2>(T, N, K, num_sms) : cluster_split_bt<BT, 1>(T, N, K, num_sms);
 }
 
 // The split factor gemm_bf16_launch will run this shape with in cluster mode (0: global-memory fix-up) -- callers that
 // want the fused RoPE epilogue ask first.
 int gemm_cluster_split(int T, int N, int K, int num_sms) {
   switch (gemm_pick_bt(T)) {
-    case 16: return cluster_split_bt<16>(T, N, K, num_sms);
-    case 32: return cluster_split_bt<32>(T, N, K, num_sms);
-    case 64: return cluster_split_bt<64>(T, N, K, num_sms);
-    case 128: return cluster_split_bt<128>(T, N, K, num_sms);
-    default: return cluster_split_bt<256>(T, N, K, num_sms);
+    case 16: return cluster_split_nw<16>(T, N, K, num_sms);
+    case 32: return cluster_split_nw<32>(T, N, K, num_sms);
+    case 64: return cluster_split_nw<64>(T, N, K, num_sms);
+    case 128: return cluster_split_nw<128>(T, N, K, num_sms);
+    default: return cluster_split_nw<256>(T, N, K, num_sms);
   }
 }
 
-template <int BT>
+template <int BT, int NW>
 static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, int out_f32, cudaStream_t stream,
                              const CUtensorMap& next_wmap, const GemmNext& nxt, const GemmRope& rope) {
-  using Cfg = GemmCfg<BT>;
+  using Cfg = GemmCfg<BT, NW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -798,15 +855,15 @@ static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, v
   const int t_tiles = (T + BT - 1) / BT;
   const int grid = gemm_grid_size(T, N, K, num_sms);
   const int stream_weights = (t_tiles == 1) ? 1 : 0;
-  const int split = cluster_split_bt<BT>(T, N, K, num_sms);
+  const int split = cluster_split_bt<BT, NW>(T, N, K, num_sms);
   // the fused RoPE epilogue lives in the two split-tile reductions (cluster and global fix-up): every tile must be split
   if (rope.positions != nullptr && (gemm_even_split(T, N, K, num_sms) < 2 || out_f32 != 0 ||
                                     N != (rope.n_q + 2 * rope.n_kv) * HEAD_DIM))
     return cudaErrorInvalidValue;
   if (split > 0)
-    return launch_k_cluster(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, split,
+    return launch_k_cluster(gemm_bf16_tcgen05_kernel<BT, NW>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, split,
                             wmap, xmap, Y, ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, split, rope);
-  return launch_k(gemm_bf16_tcgen05_kernel<BT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
+  return launch_k(gemm_bf16_tcgen05_kernel<BT, NW>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
                   ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, 0, rope);
 }
 
@@ -819,7 +876,10 @@ cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, v
   GemmNext nx{};
   if (next && next_wmap) nx = *next;
   const CUtensorMap& nm = (next && next_wmap) ? *next_wmap : wmap;
-#define TGIS_GEMM_CASE(B) return launch_bt<B>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp)
+  const int nw = gemm_nw(T);
+#define TGIS_GEMM_CASE(B)                                                                                              \
+  return nw == 2 ? launch_bt<B, 2>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp)     \
+                 : launch_bt<B, 1>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp)
   switch (gemm_pick_bt(T)) {
     case 16: TGIS_GEMM_CASE(16);
     case 32: TGIS_GEMM_CASE(32);

@@ -13,6 +13,7 @@ namespace tgis {
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols);
 int gemm_pick_bt(int T);
+int gemm_nw(int T);  // weight tiles (128 rows each) per unit sharing one activation tile: 2 for decode-shaped launches
 size_t gemm_workspace_bytes(int num_sms);
 int gemm_timeline_read(unsigned long long* out64);  // debug builds (-DTGIS_GEMM_TIMELINE) only
 // -DTGIS_STEP_TIMELINE builds: point every translation unit's kernels at the timeline buffer (ptx.cuh); else -2

@@ -288,6 +288,9 @@ int tgis_k_gemm_plan(int32_t T, int32_t N, int32_t K, int32_t num_sms, int32_t* 
   return 0;
 }
 
+// weight rows per GEMM unit (128 x the number of weight tiles that share one activation tile) for a T-token launch
+int tgis_k_gemm_unit_rows(int32_t T) { return 128 * gemm_nw(T); }
+
 // Host-only: the decode work-item list the scheduler builds for a step (no GPU needed).  seqs_host as in
 // tgis_k_attention (all decode sequences); items_out: (1 + capacity) x 8 int32 records; returns the entry count or -1.
 int tgis_k_decode_items(const int32_t* seqs_host, int32_t n_seqs, const int32_t* block_table_host, int32_t bt_stride,

@@ -72,7 +72,7 @@ ENGINE_SYMBOLS = [
 ]
 KERNEL_SYMBOLS = [
     "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_step_timeline_enable", "tgis_k_step_timeline_read", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_attention",
-    "tgis_k_attention_bench", "tgis_k_decode_items", "tgis_k_gemm_plan",
+    "tgis_k_attention_bench", "tgis_k_decode_items", "tgis_k_gemm_plan", "tgis_k_gemm_unit_rows",
     "tgis_k_sampler", "tgis_k_sampler_ex", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
 ]
 
