@@ -11,7 +11,8 @@ architecture (BASELINE.json configs[1]: Llama-3-8B bf16, 1xB200, batch 32, 512-i
            run_until_idle / poll): wall clock of the decode phase, i.e. including the per-step H2D metadata copy, the
            D2H result copy and the host scheduler.  Also reports whole-job output tokens/s and p50 TTFT.
   roofline: dominant kernel = the tcgen05 GEMM; achieved = algorithmic bytes / CUDA-event time per launch, measured in
-           a separate short profiled pass (events around every GEMM launch), against MEASURED_PEAKS.json hbm_gbs.
+           a separate short profiled pass (events around every GEMM launch), against MEASURED_PEAKS.json hbm_gbs;
+           decode_step_frac_of_hbm_roofline = algorithmic bytes of one decode step / measured step time / peak.
   cpu_baseline / --impl reference: the CPU oracle (oracle/llama_oracle.py — the port of the reference's vLLM-CPU path,
            which cannot be built offline) timed on the host cores on a bounded sample.
 
@@ -332,7 +333,7 @@ def _build_engine(model: str, *, max_seqs: int, max_len: int, kv_tokens: int, ma
     cfg = dataclasses.replace(PRESETS[model], max_model_len=max_len)
     if layers > 0:
         cfg = dataclasses.replace(cfg, n_layers=layers)
-    blocks = kv_tokens // 32 + 2 * max_seqs
+    blocks = max(kv_tokens, max_len + 64) // 32 + 2 * max_seqs   # at least one max_model_len sequence (batch-1 runs)
     kv_bytes = int(blocks * 2 * cfg.n_layers * (cfg.n_kv_heads // tp) * 32 * 128 * 2 * 1.1)
     tp_kw = {}
     if tp > 1:

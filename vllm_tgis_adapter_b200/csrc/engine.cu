@@ -275,6 +275,7 @@ struct tgis_engine {
   bool prof_decode_only = false, step_is_decode = false;
   bool fuse_rope = true;
   int rope_fuse_max_t = 32;
+  int rope_fuse_cluster_max_t = 256;
   // tensor parallelism, decode-shaped steps: one-shot all-reduce + residual + RMSNorm over NVLink peer memory
   // (ar_add_rmsnorm_kernel) instead of ncclAllReduce + rmsnorm kernel.  TGIS_TP_FUSED_AR=0: NCCL baseline.
   bool tp_fused_ar = true;
@@ -397,6 +398,7 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_L2_PREFETCH_KB")) l2_prefetch_kb = atoi(e);
     if (const char* e = getenv("TGIS_FUSE_ROPE")) fuse_rope = atoi(e) != 0;
     if (const char* e = getenv("TGIS_FUSE_ROPE_MAX_T")) rope_fuse_max_t = atoi(e);
+    if (const char* e = getenv("TGIS_FUSE_ROPE_CLUSTER_MAX_T")) rope_fuse_cluster_max_t = atoi(e);
     if (const char* e = getenv("TGIS_TP_FUSED_AR")) tp_fused_ar = atoi(e) != 0;
     if (const char* e = getenv("TGIS_LOGITS_FP32")) logits_bf16 = atoi(e) == 0;
     if (const char* e = getenv("TGIS_TP_TIMEOUT_S")) tp_timeout_s = atof(e);
@@ -894,8 +896,11 @@ struct tgis_engine {
     // tile is split over several CTAs; TGIS_FUSE_ROPE=0: off)
     // (measured: -2 % per step at 32 tokens, but +2...5 % at 64...256 -- the last-arriving CTA's serial tail grows with
     // T while the stand-alone kernel spreads over all SMs -- hence the token limit)
-    const bool rope_fused = fuse_rope && !cfg.debug_gemm_ref && T <= rope_fuse_max_t &&
-                            gemm_even_split(T, qkv_dim, H, num_sms) >= 2;
+    // ... unless the qkv launch reduces its split tiles on chip (cluster mode): then the epilogue is spread over the
+    // cluster's CTAs by token and the fusion pays up to 256 tokens (TGIS_FUSE_ROPE_CLUSTER_MAX_T)
+    const int qkv_cluster = cfg.debug_gemm_ref ? 0 : gemm_cluster_split(T, qkv_dim, H, num_sms);
+    const bool rope_fused = fuse_rope && !cfg.debug_gemm_ref && gemm_even_split(T, qkv_dim, H, num_sms) >= 2 &&
+                            T <= (qkv_cluster > 0 ? std::max(rope_fuse_max_t, rope_fuse_cluster_max_t) : rope_fuse_max_t);
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];
       {

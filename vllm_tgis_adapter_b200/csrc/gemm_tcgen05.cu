@@ -691,14 +691,6 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
-static bool gemm_cluster_enabled() {  // TGIS_GEMM_CLUSTER=0: always reduce split tiles through global memory
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TGIS_GEMM_CLUSTER");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
 
 int gemm_pick_bt(int T) {
   if (T <= 16) return 16;
@@ -723,6 +715,60 @@ int gemm_nw(int T) {
 }
 static int gemm_bn(int T) { return GEMM_BN * gemm_nw(T); }
 
+static bool gemm_cluster_enabled() {  // TGIS_GEMM_CLUSTER=0: always reduce split tiles through global memory
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TGIS_GEMM_CLUSTER");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BT, int NW>
+__global__ void gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, void*, int,
+                                         int, int, int, float*, int*, int, int, const __grid_constant__ CUtensorMap,
+                                         GemmNext, int, GemmRope);
+
+// How many clusters of `s` GEMM CTAs (one CTA per SM) the device can hold at once: a GPC hosts floor(its SMs / s) of them
+// (148 SMs: 74 of 2, 45 of 3, 33 of 4, ...).  Queried once per size; without a device (host-only plan tests) the
+// optimistic num_sms / s.
+static int gemm_max_clusters(int s, int num_sms) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (s < 2 || s > 8) return num_sms / (s > 0 ? s : 1);
+  if (cache[s] == 0) {
+    using Cfg = GemmCfg<32, 1>;
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(s * (num_sms / s));
+    qc.blockDim = dim3(GEMM_THREADS);
+    qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = s;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) ==
+            cudaSuccess &&
+        cudaOccupancyMaxActiveClusters(&n, gemm_bf16_tcgen05_kernel<32, 1>, &qc) == cudaSuccess && n > 0) {
+      cache[s] = n;
+    } else {
+      cudaGetLastError();
+      cache[s] = num_sms / s;
+    }
+  }
+  return cache[s];
+}
+static bool gemm_fit_clusters() {  // TGIS_GEMM_FIT_CLUSTERS=0: round-1 policy (largest split, cluster mode only if it fits)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TGIS_GEMM_FIT_CLUSTERS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 size_t gemm_workspace_bytes(int num_sms) { return (size_t)num_sms * 2 * 2 * 256 * GEMM_BN * sizeof(float); }
 
 // Grid size of a launch (pure function of the shape: the NEXT kernel's grid must be known one launch ahead)
@@ -746,6 +792,11 @@ int gemm_grid_size(int T, int N, int K, int num_sms) {
     // large token tiles: a partial is >= 64 KB per weight tile; splitting a short k-range (o-proj shards) costs more in
     // partial traffic than the extra SMs bring -- keep at least 16 k-blocks per CTA
     while (BT > 64 && split > 1 && KB / split < 16) --split;
+    // Prefer a split whose clusters are all co-resident (qkv of the 8B model: 48 tiles x 3 CTAs -- only 45 clusters of 3
+    // fit, so round 1 reduced it through global memory; 48 clusters of 2 fit): the on-chip reduction spreads the fused
+    // RoPE + KV-scatter epilogue over the cluster's CTAs, which is what lets it replace rope_kvwrite_kernel above 32 tokens
+    if (gemm_fit_clusters() && gemm_cluster_enabled() && t_tiles == 1)
+      while (split > 2 && tiles > gemm_max_clusters(split, num_sms)) --split;
     grid = (int)(tiles * split);
   }
   if (const char* e = getenv("TGIS_GEMM_MAX_CTAS")) {  // experiment knob (scripts/gemm_cta_sweep.py)

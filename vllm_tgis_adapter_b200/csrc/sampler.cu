@@ -724,15 +724,18 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
   STL_EXIT();
 }
 
-// Cluster size of a launch: rows that only need the fused first pass (greedy / forced, no typical-p) get just enough CTAs
-// per row to cover the GPU once; rows with selection passes (sampling) keep 8 CTAs per row.  The choice is a function of
-// (n_rows, any_complex) only, so a captured CUDA graph (keyed by both) replays the same launch.
+// Cluster size of a launch: just enough CTAs per row to cover the GPU once.  The choice is a function of the launch shape
+// only, so a captured CUDA graph replays the same launch; any_complex still selects the shared-memory staging of the
+// processed row.
 int sampler_cluster_size(int n_rows, int any_complex, int num_sms) {
   if (const char* e = getenv("TGIS_SAMPLER_CLUSTER")) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) return v;
   }
-  if (any_complex) return n_rows <= 96 ? 8 : (n_rows <= 192 ? 4 : 2);
+  // one wave of clusters over the GPU: the largest power of two with n_rows * ncl <= #SMs.  Measured for sampling rows too
+  // (profiles/r02_sampler_bench.json: 64 configs[2] rows 403 us with 8 CTAs per row = 4 waves of resident clusters, 256 us
+  // with 2; 32 rows 241 vs 137 us with 4), so the rule does not depend on the row type any more.
+  (void)any_complex;
   int ncl = 8;
   while (ncl > 1 && n_rows * ncl > num_sms) ncl >>= 1;
   return ncl;
