@@ -37,6 +37,12 @@ int tgis_k_rope_kv(void* qkv_dev, const int32_t* positions_host, const int32_t* 
 int tgis_k_gemm_rope(const void* x_dev, const void* w_dev, void* y_dev, int32_t T, int32_t n_q, int32_t n_kv, int32_t K,
                      int32_t x_rows_alloc, const int32_t* positions_host, const int32_t* slot_mapping_host,
                      const void* cos_sin_dev, void* k_cache_dev, void* v_cache_dev);
+/* a[T, K1] -> GEMM w1[H, K1] -> residual += . ; RMSNorm(residual) * w_norm -> GEMM w2[N2, H] (out_mode2: 0 bf16, 2 fused
+ * SwiGLU) -> y2.  fused = 0: three launches (gemm, add_rmsnorm, gemm); fused = 1: the add + norm folded into the two GEMMs
+ * (GemmNorm, kernels.h).  Returns 1 (nothing computed) when the launch plan cannot fuse the shape. */
+int tgis_k_gemm_norm_chain(const void* a_dev, int32_t a_rows_alloc, const void* w1_dev, void* residual_dev,
+                           const void* w_norm_dev, const void* w2_dev, void* y2_dev, int32_t T, int32_t K1, int32_t H,
+                           int32_t N2, float eps, int32_t out_mode2, int32_t fused, int32_t iters, float* us_out);
 /* seqs_host: n_seqs x {q_start, q_len, kv_len, block_row}; block_table_host: [rows][bt_stride] */
 int tgis_k_attention(const void* qkv_dev, const void* k_cache_dev, const void* v_cache_dev, const int32_t* seqs_host,
                      int32_t n_seqs, const int32_t* block_table_host, int32_t bt_rows, int32_t bt_stride, void* out_dev,

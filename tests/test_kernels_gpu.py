@@ -220,6 +220,45 @@ def test_qkv_gemm_with_fused_rope_epilogue_is_bit_identical(g, T, heads):
     assert float(kc1.float().abs().sum()) > 0 and float(vc1.float().abs().sum()) > 0
 
 
+@pytest.mark.parametrize("T,K1,H,N2,mode2", [
+    (32, 4096, 4096, 28672, 2),     # o-proj -> post-attention norm -> gate_up (+SwiGLU), Llama-3-8B
+    (32, 14336, 4096, 6144, 0),     # down-proj -> next layer's input norm -> qkv
+    (64, 4096, 4096, 6144, 0),
+    (7, 1024, 1024, 2048, 0),       # ragged token tile (BT = 16), small hidden
+    (17, 512, 768, 2304, 0),        # 125m dims
+])
+def test_fused_residual_rmsnorm_in_gemms_matches_three_launch_path(g, T, K1, H, N2, mode2):
+    """residual add + RMSNorm folded into the producing GEMM's cluster reduction and the consuming GEMM's operand staging
+    (GemmNorm) against gemm -> add_rmsnorm -> gemm: the residual stream must be bit-identical; the normalised operand
+    differs only through the fp32 summation order of sum(h^2), so y2 is allowed rare one-bf16-ulp flips."""
+    torch.manual_seed(5)
+    rows = 256
+    a = torch.zeros(rows, K1, dtype=torch.bfloat16, device="cuda")
+    a[:T] = (torch.randn(T, K1, device="cuda") * 0.5).bfloat16()
+    w1 = (torch.randn(H, K1, device="cuda") * 0.03).bfloat16()
+    w2 = (torch.randn(N2, H, device="cuda") * 0.03).bfloat16()
+    wn = (1.0 + 0.1 * torch.randn(H, device="cuda")).bfloat16()
+    res0 = torch.randn(rows, H, device="cuda").bfloat16()
+    outs = []
+    for fused in (0, 1):
+        res = res0.clone()
+        y2 = torch.zeros(T, N2 // 2 if mode2 == 2 else N2, dtype=torch.bfloat16, device="cuda")
+        us = C.c_float(0)
+        rc = g.lib().tgis_k_gemm_norm_chain(g.ptr(a), rows, g.ptr(w1), g.ptr(res), g.ptr(wn), g.ptr(w2), g.ptr(y2), T, K1,
+                                            H, N2, 1e-5, mode2, fused, 1, C.byref(us))
+        assert rc in (0, 1), g.kerr()
+        if rc == 1:
+            pytest.skip("the launch plan does not reduce this producer shape in cluster mode on this device")
+        outs.append((res, y2))
+    (r0, y0), (r1, y1) = outs
+    assert torch.equal(r0[:T], r1[:T])                      # residual stream: same arithmetic, same rounding points
+    assert torch.equal(r0[T:], res0[T:]) and torch.equal(r1[T:], res0[T:])
+    d = (y0.float() - y1.float()).abs()
+    assert float(d.max()) <= 2.0 ** -7 * float(y0.float().abs().max()), float(d.max())   # <= one bf16 ulp of the largest output
+    assert float((d > 0).float().mean()) < 0.02, float((d > 0).float().mean())
+    assert float(y0.float().abs().sum()) > 0
+
+
 def _attention_case(g, n_q, n_kv, seq_specs, seed):
     """seq_specs: list of (context_len_before, q_len).  Returns (out_gpu, out_oracle)."""
     from oracle.llama_oracle import LlamaConfig, LlamaOracle

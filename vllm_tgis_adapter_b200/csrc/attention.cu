@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(DEC_THREADS, TGIS_DEC_MINB)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv_bfloat16* __restrict__ k_cache,
                    const __nv_bfloat16* __restrict__ v_cache, const DecItem* __restrict__ items,
                    int max_splits, float* __restrict__ part_o, float* __restrict__ part_ml,
-                   __nv_bfloat16* __restrict__ out, int out_ld, int n_kv, float scale, int* __restrict__ arrive) {
+                   __nv_bfloat16* __restrict__ out, int out_ld, int n_kv, float scale, int* __restrict__ arrive,
+                   int prefetch_old) {
   static_assert(G <= 8, "query heads of a group are rows 0..7 of the MMA tile");
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,6 +141,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
   // ---- issue cursor: runs DEC_RING tiles ahead of consumption, across item boundaries
   int i_f = f, i_kvh = f % n_kv, i_jb = 0, i_nblk = n_blk_of(c_it), i_kv = 0, i_buf = 0;
   int4 i_nxt = c_it, i_blks = blocks_at(f), i_blks_nxt = i_blks;  // block ids of the item being issued / the next one
+  int4 i_cur = c_it;                                                // record of the item being issued
   int i_k = 0, c_k = 0;  // round of the issue cursor / of the consumer
   if (item_of_round(1) < n_flat) {
     i_nxt = item_at(item_of_round(1));
@@ -165,6 +167,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
       i_kvh = i_f % n_kv;
       i_jb = 0;
       i_nblk = n_blk_of(i_nxt);
+      i_cur = i_nxt;
       i_blks = i_blks_nxt;
       if (item_of_round(i_k + 1) < n_flat) {
         i_nxt = item_at(item_of_round(i_k + 1));
@@ -179,11 +182,22 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, const __nv
     }
   };
 
+  // Cache blocks that hold only tokens of EARLIER steps do not depend on the preceding kernels: stream them while the
+  // qkv projection is still draining.  The block holding position kv_len-1 (last block of the last split) was written
+  // this step; the in-order issue cursor stops in front of it until the dependency resolves.
+  int n_pre = 0;
+  if (prefetch_old) {
+    while (n_pre < DEC_RING && i_f < n_flat) {
+      const bool tail_block = (i_cur.z >> 16) == (i_cur.y + DEC_TOK - 1) / DEC_TOK - 1 && i_jb == i_nblk - 1;
+      if (tail_block) break;
+      issue_tile();
+      ++n_pre;
+    }
+  }
   griddep_wait();  // q and the newest cache slot come from the preceding kernels
   STL_WAITED();
   issue_q(c_it, f % n_kv);
-#pragma unroll
-  for (int i = 0; i < DEC_RING; ++i) issue_tile();
+  for (int i = n_pre; i < DEC_RING; ++i) issue_tile();
 
   const int hr = lane >> 2, t4 = lane & 3;
   const int mi = lane >> 3, ri = lane & 7;          // ldmatrix: lane -> (matrix, row)
@@ -505,9 +519,11 @@ static cudaError_t decode_launch_g(const __nv_bfloat16* qkv, int qkv_ld, const _
   // -1 % at batch 64.  So the separate kernel stays the default.
   const char* env_merge = getenv("TGIS_ATTN_INKERNEL_MERGE");  // read per launch: the A/B test flips it in-process
   const int inkernel = (env_merge && env_merge[0] == '1') ? 1 : 0;
+  const char* env_pre = getenv("TGIS_ATTN_PREFETCH");  // 0: no cache reads before the grid-dependency wait
+  const int prefetch_old = (env_pre && env_pre[0] == '0') ? 0 : 1;
   int* arr = (inkernel && max_splits > 1) ? arrive : nullptr;
   cudaError_t e = launch_k(attn_decode_kernel<G>, dim3(grid), dim3(DEC_THREADS), DEC_SMEM, stream, qkv, qkv_ld,
-                           k_cache, v_cache, items, max_splits, part_o, part_ml, out, out_ld, n_kv, scale, arr);
+                           k_cache, v_cache, items, max_splits, part_o, part_ml, out, out_ld, n_kv, scale, arr, prefetch_old);
   if (e != cudaSuccess || max_splits <= 1 || arr != nullptr) return e;
   return launch_k(attn_merge_kernel<G>, dim3(n_seqs, n_kv), dim3(HEAD_DIM), 0, stream, seqs, seq_ids, max_splits,
                   (const float*)part_o, (const float*)part_ml, out, out_ld, n_kv);

@@ -232,9 +232,10 @@ struct tgis_engine {
   DevBuf<uint8_t> logits;
   bool logits_bf16 = true;
   size_t lsz = 2;  // bytes per logit
-  CUtensorMap xm_xn[N_BT], xm_attn[N_BT], xm_act[N_BT], xm_last[N_BT];
+  CUtensorMap xm_xn[N_BT], xm_attn[N_BT], xm_act[N_BT], xm_last[N_BT], xm_resid[N_BT];
   DevBuf<float> gemm_ws, part_o, part_ml, samp_scratch;
   DevBuf<int> gemm_counters, attn_arrive;
+  DevBuf<float> norm_ssq;  // [2][GEMM_NORM_MAX_T][hidden / 128] partial sums of h^2 (fused residual RMSNorm)
   DevBuf<uint32_t> seen_bitmap;
   DevBuf<SampleOut> d_samp_out;
   SampleOut* h_samp_out = nullptr;
@@ -276,6 +277,9 @@ struct tgis_engine {
   bool fuse_rope = true;
   int rope_fuse_max_t = 32;
   int rope_fuse_cluster_max_t = 256;
+  // residual add + RMSNorm folded into the o / down projections' cluster reduction and the gate_up / qkv projections'
+  // operand staging (GemmNorm, gemm_tcgen05.cu): tp == 1, steps of at most GEMM_NORM_MAX_T tokens.  TGIS_FUSE_NORM=0: off
+  bool fuse_norm = false;
   // tensor parallelism, decode-shaped steps: one-shot all-reduce + residual + RMSNorm over NVLink peer memory
   // (ar_add_rmsnorm_kernel) instead of ncclAllReduce + rmsnorm kernel.  TGIS_TP_FUSED_AR=0: NCCL baseline.
   bool tp_fused_ar = true;
@@ -399,6 +403,7 @@ struct tgis_engine {
     if (const char* e = getenv("TGIS_FUSE_ROPE")) fuse_rope = atoi(e) != 0;
     if (const char* e = getenv("TGIS_FUSE_ROPE_MAX_T")) rope_fuse_max_t = atoi(e);
     if (const char* e = getenv("TGIS_FUSE_ROPE_CLUSTER_MAX_T")) rope_fuse_cluster_max_t = atoi(e);
+    if (const char* e = getenv("TGIS_FUSE_NORM")) fuse_norm = atoi(e) != 0;
     if (const char* e = getenv("TGIS_TP_FUSED_AR")) tp_fused_ar = atoi(e) != 0;
     if (const char* e = getenv("TGIS_LOGITS_FP32")) logits_bf16 = atoi(e) == 0;
     if (const char* e = getenv("TGIS_TP_TIMEOUT_S")) tp_timeout_s = atof(e);
@@ -461,6 +466,7 @@ struct tgis_engine {
     gemm_counters.zero();
     attn_arrive.alloc((size_t)S_max * std::max(nkv, 1));
     attn_arrive.zero();
+    norm_ssq.alloc((size_t)2 * GEMM_NORM_MAX_T * (c.hidden / 128 + 1));
     const int G = c.n_q_heads / c.n_kv_heads;
     part_o.alloc((size_t)S_max * nkv * max_splits_cap * G * HEAD_DIM);
     part_ml.alloc((size_t)S_max * nkv * max_splits_cap * G * 2);
@@ -517,6 +523,7 @@ struct tgis_engine {
           throw CudaError("cuTensorMapEncodeTiled(activation) failed");
       };
       xmap(&xm_xn[i], xn.p, T_alloc, H);
+      xmap(&xm_resid[i], resid.p, T_alloc, H);  // fused-norm consumers read the residual stream
       xmap(&xm_attn[i], attn_out.p, T_alloc, q_dim);
       xmap(&xm_act[i], act.p, T_alloc, F);
       xmap(&xm_last[i], last_hidden.p, S_alloc, H);
@@ -825,7 +832,7 @@ struct tgis_engine {
   // prefetched into L2 by this launch's producer warp (gemm_tcgen05.cu)
   void gemm(const CUtensorMap* xmaps, const CUtensorMap& wm, const bf16* X, const bf16* W, void* Y, int T, int N, int K,
             int out_f32 = 0, const CUtensorMap* next_wm = nullptr, int nT = 0, int nN = 0, int nK = 0, int ldy = 0,
-            const GemmRope* rope = nullptr) {
+            const GemmRope* rope = nullptr, const GemmNorm* norm = nullptr) {
     if (ldy == 0) ldy = N;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profiling && (!prof_decode_only || step_is_decode)) {
@@ -847,7 +854,7 @@ struct tgis_engine {
       GemmNext nx{};
       if (next_wm && l2_prefetch_kb > 0) nx = gemm_next_desc(nT, nN, nK, num_sms, l2_prefetch_kb);
       CK(gemm_bf16_launch(wm, xmaps[bt_index(T)], Y, ldy, T, N, K, gemm_ws.p, gemm_counters.p, num_sms, stream, out_f32,
-                          nx.kb_prefetch > 0 ? next_wm : nullptr, nx.kb_prefetch > 0 ? &nx : nullptr, rope));
+                          nx.kb_prefetch > 0 ? next_wm : nullptr, nx.kb_prefetch > 0 ? &nx : nullptr, rope, norm));
     }
     if (pe1) CK(cudaEventRecord(pe1, stream));
     ++n_launches;
@@ -901,12 +908,26 @@ struct tgis_engine {
     const int qkv_cluster = cfg.debug_gemm_ref ? 0 : gemm_cluster_split(T, qkv_dim, H, num_sms);
     const bool rope_fused = fuse_rope && !cfg.debug_gemm_ref && gemm_even_split(T, qkv_dim, H, num_sms) >= 2 &&
                             T <= (qkv_cluster > 0 ? std::max(rope_fuse_max_t, rope_fuse_cluster_max_t) : rope_fuse_max_t);
+    // residual add + RMSNorm inside the GEMMs either side of it (single GPU, small steps, both row-"producers" reduced
+    // on chip): o-proj -> [post-attention norm] -> gate_up and down-proj -> [next layer's input norm] -> qkv
+    const bool norm_fused = fuse_norm && tp == 1 && !cfg.debug_gemm_ref && T <= GEMM_NORM_MAX_T && H % 128 == 0 && H / 128 <= GEMM_NORM_MAX_PARTS &&
+                            gemm_cluster_split(T, H, q_dim, num_sms) > 0 && gemm_cluster_split(T, H, F, num_sms) > 0;
+    const int n_parts = H / 128;
+    float* ssq_attn = norm_ssq.p;                                      // written by o-proj, read by gate_up
+    float* ssq_mlp = norm_ssq.p + (size_t)GEMM_NORM_MAX_T * n_parts;   // written by down-proj, read by the next qkv
+    const GemmNorm prod_attn{resid.p, ssq_attn, nullptr, nullptr, nullptr, 0, 0.f};
+    const GemmNorm prod_mlp{resid.p, ssq_mlp, nullptr, nullptr, nullptr, 0, 0.f};
     for (int li = 0; li < c.n_layers; ++li) {
       LayerW& l = layers[li];
+      const GemmNorm cons_qkv{nullptr, nullptr, resid.p, ssq_mlp, l.ln1, n_parts, c.rms_eps};
+      const GemmNorm cons_gu{nullptr, nullptr, resid.p, ssq_attn, l.ln2, n_parts, c.rms_eps};
+      const bool qkv_norm_in = norm_fused && li > 0;
       {
         if (li == 0) {
           CK(rmsnorm_launch(resid.p, l.ln1, xn.p, T, H, c.rms_eps, stream));
           ++n_launches;
+        } else if (qkv_norm_in) {
+          // the previous layer's down-proj left h in resid and sum(h^2) in ssq_mlp; the qkv GEMM normalises on the fly
         } else if (ar_fused) {
           fused_ar_norm(1, l.ln1, T);  // previous layer's down-proj partials
         } else {
@@ -915,7 +936,8 @@ struct tgis_engine {
         }
         const GemmRope rp{ds<int32_t>(off_pos), ds<int32_t>(off_slotmap), cos_sin,
                           k_cache.p + (size_t)li * kv_layer_elems, v_cache.p + (size_t)li * kv_layer_elems, nq, nkv};
-        gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim, 0, rope_fused ? &rp : nullptr);
+        gemm(qkv_norm_in ? xm_resid : xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim, 0,
+             rope_fused ? &rp : nullptr, qkv_norm_in ? &cons_qkv : nullptr);
       }
       bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
       bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
@@ -936,8 +958,10 @@ struct tgis_engine {
                                n_tiles, d_bt, bt_stride, attn_out.p, q_dim, nq, nkv, scale, stream));
         ++n_launches;
       }
-      gemm(xm_attn, l.m_o, attn_out.p, l.wo, ar_fused ? ar_buf(0) : tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H);
-      if (ar_fused) {
+      gemm(xm_attn, l.m_o, attn_out.p, l.wo, ar_fused ? ar_buf(0) : tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H, 0, nullptr,
+           norm_fused ? &prod_attn : nullptr);
+      if (norm_fused) {
+      } else if (ar_fused) {
         fused_ar_norm(0, l.ln2, T);
       } else {
         all_reduce_tmp(T);  // row-parallel partial sums (tp > 1)
@@ -945,9 +969,12 @@ struct tgis_engine {
         ++n_launches;
       }
       // gate_up GEMM with SwiGLU fused into its epilogue: writes act[T, F] directly (no gate_up round trip)
-      gemm(xm_xn, l.m_gu, xn.p, l.wgu, act.p, T, 2 * F, H, /*out_mode=*/2, &l.m_d, T, H, F, /*ldy=*/F);
+      gemm(norm_fused ? xm_resid : xm_xn, l.m_gu, xn.p, l.wgu, act.p, T, 2 * F, H, /*out_mode=*/2, &l.m_d, T, H, F,
+           /*ldy=*/F, nullptr, norm_fused ? &cons_gu : nullptr);
       bf16* down_out = ar_fused ? ar_buf(1) : tmp.p;
-      if (li + 1 < c.n_layers) gemm(xm_act, l.m_d, act.p, l.wd, down_out, T, H, F, 0, &layers[li + 1].m_qkv, T, qkv_dim, H);
+      if (li + 1 < c.n_layers)
+        gemm(xm_act, l.m_d, act.p, l.wd, down_out, T, H, F, 0, &layers[li + 1].m_qkv, T, qkv_dim, H, 0, nullptr,
+             norm_fused ? &prod_mlp : nullptr);
       else gemm(xm_act, l.m_d, act.p, l.wd, down_out, T, H, F, 0, R > 0 ? &m_lm : nullptr, R, Vl, H);
       if (!ar_fused) all_reduce_tmp(T);
     }

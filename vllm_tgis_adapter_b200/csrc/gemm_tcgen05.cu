@@ -33,6 +33,7 @@ TGIS_STL_DEFINE(gemm)
 constexpr int GEMM_BN = 128;  // weight rows per tile (UMMA_M)
 constexpr int GEMM_BK = 64;   // k per stage (one 128-byte swizzle row of bf16)
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS_NORM = 256;  // + 2 activation-transform warps (fused RMSNorm consumer, GemmNorm::h)
 
 // NW = weight tiles (of GEMM_BN = 128 rows) per unit that share ONE activation tile: every unit re-reads its [BT x 64]
 // activation tile per k-block, and with NW = 2 that tile feeds two MMAs (two accumulators), halving the activation bytes
@@ -56,7 +57,10 @@ struct GemmCfg {
   static constexpr int N_ACC = (2 * ACC_COLS <= 512) ? 2 : 1;            // double-buffered when it fits the 512 columns
   static constexpr int TMEM_COLS = (N_ACC * ACC_COLS) < 32 ? 32 : (N_ACC * ACC_COLS);
   static constexpr int PART_FLOATS = NW * BT * GEMM_BN;                  // fp32 partial of one unit
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BAR_BYTES = 512;   // mbarriers (full, empty, tmem, ready), TMEM base, flag
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_BYTES + 256 /*rstd*/;
+  // fused-norm consumers append the norm weights (+ K * 2 bytes, K <= 8192)
+  static constexpr int SMEM_MAX = (SMEM_BYTES + 16384) < 227 * 1024 ? (SMEM_BYTES + 16384) : 227 * 1024;
 };
 
 // Prefill-shaped launches (more than one token tile): "data-parallel waves + stream-K tail".  Linear tile index i
@@ -65,15 +69,24 @@ struct GemmCfg {
 // tile) pairs, so both operands of a wave stay in L2 (with contiguous per-CTA ranges the CTAs drift apart, the working
 // set is every weight tile + every activation tile, and ncu showed 11 GB of DRAM reads for 0.3 GB of operands).  The
 // remaining < ncta tiles are cut stream-K style as before.  Decode-shaped launches have dp_waves = 0: unchanged.
+//
+// Decode-shaped launches with at least one tile per CTA (gate_up: 224 tiles on 148 CTAs, lm_head: 1002) use the same two
+// regions in the OPPOSITE order ("sk_first"): every CTA first works through its < 1 tile share of the stream-K region --
+// the shared tiles, whose last-arriver fix-up (atomic + L2 round trip + ordered sum) then runs in the epilogue warps
+// UNDER the main loop of the following whole tile -- and ends on a whole tile with a direct epilogue.  With the pure
+// stream-K cut most CTAs END on a shared tile piece, and the fix-ups (4-6.5 us at 32 tokens, growing with T) are the
+// launch's tail.  Same tiles, same split points inside a shared tile's k-range order, same rank-ordered sums.
 struct GemmSched {
   int n_tiles, t_tiles, KB, ncta;
   int dp_waves;        // whole-tile waves
   int sk_tile0;        // first tile of the stream-K region
   long long sk_total;  // (tile, k-block) units in the stream-K region
-  __device__ GemmSched(int n_tiles_, int t_tiles_, int KB_, int ncta_)
+  bool sk_first;       // stream-K region before the whole-tile waves
+  __device__ GemmSched(int n_tiles_, int t_tiles_, int KB_, int ncta_, bool sk_first_)
       : n_tiles(n_tiles_), t_tiles(t_tiles_), KB(KB_), ncta(ncta_) {
     const int tiles = n_tiles * t_tiles;
-    dp_waves = t_tiles > 1 ? tiles / ncta : 0;
+    sk_first = sk_first_ && t_tiles == 1 && tiles >= ncta;
+    dp_waves = (t_tiles > 1 || sk_first) ? tiles / ncta : 0;
     sk_tile0 = dp_waves * ncta;
     sk_total = (long long)(tiles - sk_tile0) * KB;
   }
@@ -99,14 +112,15 @@ struct UnitIter {
   // (tile, kblock) space owned by this CTA
   long long pos, end;
   int kb_per_tile, wave, dp_waves, cta, ncta, sk_tile0;
-  bool first;
+  bool first, sk_first;
   __device__ UnitIter(const GemmSched& sc, int cta_)
-      : kb_per_tile(sc.KB), wave(0), dp_waves(sc.dp_waves), cta(cta_), ncta(sc.ncta), sk_tile0(sc.sk_tile0), first(true) {
+      : kb_per_tile(sc.KB), wave(0), dp_waves(sc.dp_waves), cta(cta_), ncta(sc.ncta), sk_tile0(sc.sk_tile0), first(true),
+        sk_first(sc.sk_first) {
     pos = (sc.sk_total * cta_) / sc.ncta;
     end = (sc.sk_total * (cta_ + 1)) / sc.ncta;
   }
   __device__ bool next(int& tile, int& kb0, int& kb1, int& slot) {
-    if (wave < dp_waves) {
+    if (wave < dp_waves && (!sk_first || pos >= end)) {
       tile = wave * ncta + cta;
       kb0 = 0;
       kb1 = kb_per_tile;
@@ -205,12 +219,12 @@ __device__ __forceinline__ void qkv_rope_store(const GemmRope& rope, int head, i
 }
 
 template <int BT, int NW>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS_NORM, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
                          void* __restrict__ Yv, int ldy, int T, int N, int K, float* __restrict__ ws,
                          int* __restrict__ counters, int stream_weights, int out_f32,
                          const __grid_constant__ CUtensorMap next_wmap, GemmNext nxt, int cluster_split,
-                         GemmRope rope) {
+                         GemmRope rope, GemmNorm norm) {
   // output: bf16 (rounded once from the fp32 accumulator, = F.linear in model dtype) or raw fp32 (lm_head logits)
   __nv_bfloat16* __restrict__ Y = reinterpret_cast<__nv_bfloat16*>(Yv);
   float* __restrict__ Yf = reinterpret_cast<float*>(Yv);
@@ -230,15 +244,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   int* flag_smem = reinterpret_cast<int*>(tmem_base_smem + 1);
+  uint64_t* ready_bar = bars + 40;  // [STAGES <= 12] fused-norm consumer: token tile of the stage normalised in place
+  uint64_t* xfull_bar = bars + 52;  // [STAGES <= 12] fused-norm consumer: raw token tile landed (weights: full_bar)
+  float* rstd_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);  // [64]
+  uint8_t* wn_smem = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + 256;                      // [K] bf16 norm weights
+  const bool norm_in = norm.h != nullptr;  // the token operand is RMSNorm(h): warps 6..7 rewrite each landed stage in place
 
   const int warp = threadIdx.x >> 5;
   STL_ENTER(2 | (N << 8));
+  int* stl_slot_smem = flag_smem + 1;
+  STL_SHARE(stl_slot_smem);  // read by the other warps after the set-up barrier
   if (threadIdx.x == 0) TL(0);  // kernel entry
   const int n_tiles = (N + BNW - 1) / BNW;     // units along N
   const int t_tiles = (T + BT - 1) / BT;
   const int KB = (K + GEMM_BK - 1) / GEMM_BK;
   const int ncta = gridDim.x, cta = blockIdx.x;
-  const GemmSched sched(n_tiles, t_tiles, KB, ncta);
+  const GemmSched sched(n_tiles, t_tiles, KB, ncta, (stream_weights & 2) != 0);
+  // cluster mode, push variant: every CTA sends its partial rows straight into the OWNER's receive buffer (tokens
+  // t = r (mod s) belong to rank r), ONE cluster barrier, then each owner sums its own shared memory in rank order -- no
+  // remote read latency and no exit barrier (pull variant: park locally, barrier, read peers, barrier)
+  const bool cl_push = (stream_weights & 4) != 0;
+  stream_weights &= 1;
   const long long total = sched.sk_total;  // stream-K region (== everything for decode-shaped launches)
 
   if (warp == 0 && elect_one()) {
@@ -250,6 +276,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
+        mbar_init(&ready_bar[i], 1);  // the transform warp that owns the stage's k-block (fused-norm consumer)
+        mbar_init(&xfull_bar[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full[i], 1);
@@ -263,10 +291,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // push variant: peers write into this CTA's shared memory as soon as THEY are done -- every CTA of the cluster must be
+  // running before the first remote store (arrive now, wait right before pushing: free by then)
+  if (cl_push) asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_base_smem;
   griddep_launch();  // PDL: the next kernel may start its prologue now
   if (threadIdx.x == 0) TL(1);  // setup done (barriers, TMEM)
   int cl_tile = -1, cl_tvalid = 0;  // cluster mode: the split tile this CTA contributed to (epilogue warps)
+
+  // ---- fused residual-stream RMSNorm (GemmNorm consumer side): xmap points at the residual stream h, so the producer
+  // warp's TMA stages the RAW [BT x 64] token tile (own barrier xfull_bar: it lands long before the weight tile).  A warp
+  // rewrites one landed stage IN PLACE as bf16(bf16(h * rstd) * w) -- 16-byte chunk c of row r sits at
+  // r * 128 + ((c ^ (r & 7)) << 4) under the 128-byte swizzle; lane -> chunk lane & 7, rows (lane >> 3) + 4 j -- and
+  // signals ready_bar, which the MMA warp waits for.  Warps 6 / 7 take the even / odd k-blocks; when the dependency
+  // resolves a whole ring of tiles lands at once, so the (then idle) epilogue warps take k-blocks 2..5 of that burst.
+  constexpr int NJ = BT <= GEMM_NORM_MAX_T ? BT / 4 : 1;
+  const int norm_n_kb = (int)((total * (cta + 1)) / ncta - (total * cta) / ncta);  // decode-shaped: no whole-tile waves
+  const int norm_kb0 = (int)(((total * cta) / ncta) % KB);
+  const bool norm_helpers = norm_in && STAGES >= 6 && norm_n_kb >= 6;
+  auto norm_stage = [&](int i, const float (&rs)[NJ]) {
+    const int lane = lane_id();
+    const int c = lane & 7, r0 = lane >> 3;
+    const int stage = i % STAGES;
+    const uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+    const int kb = (norm_kb0 + i) % KB;
+    uint32_t wb[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(wb[0]), "=r"(wb[1]), "=r"(wb[2]), "=r"(wb[3])
+                 : "r"(smem_u32(wn_smem) + (uint32_t)((kb * GEMM_BK + c * 8) * 2)));
+    mbar_wait(&xfull_bar[stage], phase);
+    const uint32_t st_base = smem_u32(smem_x) + (uint32_t)(stage * Cfg::X_BYTES);
+    uint32_t hb[NJ][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int r = r0 + 4 * j;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+                   : "=r"(hb[j][0]), "=r"(hb[j][1]), "=r"(hb[j][2]), "=r"(hb[j][3])
+                   : "r"(st_base + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))));
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int r = r0 + 4 * j;
+      uint32_t ob[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h0 = __uint_as_float(hb[j][e] << 16), h1 = __uint_as_float(hb[j][e] & 0xffff0000u);
+        const float w0 = __uint_as_float(wb[e] << 16), w1 = __uint_as_float(wb[e] & 0xffff0000u);
+        const __nv_bfloat162 o2 = __floats2bfloat162_rn(bf16_round(h0 * rs[j]) * w0, bf16_round(h1 * rs[j]) * w1);
+        ob[e] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(st_base + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))),
+                   "r"(ob[0]), "r"(ob[1]), "r"(ob[2]), "r"(ob[3])
+                   : "memory");
+    }
+    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ready_bar[stage]);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -282,6 +363,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       // CTA's whole tiles (wave order) and then its stream-K range; rows are re-derived only when the tile changes.
       struct Cur {
         int wave, tile, kb, w_row, x_row;
+        int sk_left;  // sk_first: k-blocks left in the stream-K share (then the whole-tile waves)
       };
       auto cur_set_tile = [&](Cur& c, int tile) {
         c.tile = tile;
@@ -292,7 +374,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       };
       auto cur_init = [&](Cur& c) {
         c.wave = 0;
-        if (sched.dp_waves > 0) {
+        c.sk_left = sched.sk_first ? (int)(end - begin) : 0;
+        if (sched.dp_waves > 0 && c.sk_left == 0) {
           c.kb = 0;
           cur_set_tile(c, cta);
         } else {
@@ -301,6 +384,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         }
       };
       auto cur_next = [&](Cur& c) {
+        if (c.sk_left > 0) {  // sk_first: inside the stream-K share
+          if (--c.sk_left == 0) {  // -> first whole tile
+            c.kb = 0;
+            if (sched.dp_waves > 0) cur_set_tile(c, cta);
+            return;
+          }
+          if (++c.kb == KB) {
+            c.kb = 0;
+            cur_set_tile(c, c.tile + 1);
+          }
+          return;
+        }
         if (++c.kb < KB) return;
         c.kb = 0;
         if (c.wave < sched.dp_waves) {
@@ -326,8 +421,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       Cur wc, xc;
       cur_init(wc);
       xc = wc;
+      // fused-norm consumer: the (small, L2-resident) token tile gets its own barrier, so it is normalised while the
+      // stage's weight tile is still in flight and the rewrite adds nothing to the time a ring slot stays occupied
+      const uint32_t w_tx = norm_in ? (uint32_t)Cfg::W_BYTES : (uint32_t)Cfg::STAGE_BYTES;
       for (int i = 0; i < n_pre; ++i) {
-        mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+        mbar_arrive_expect_tx(&full_bar[i], w_tx);
         issue_w(wc, i);
         cur_next(wc);
       }
@@ -340,11 +438,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       for (int i = 0; i < n_kb; ++i) {
         if (i >= n_pre) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], w_tx);
           issue_w(wc, stage);
           cur_next(wc);
         }
-        tma_load_2d_hint(&xmap, &full_bar[stage], smem_x + stage * Cfg::X_BYTES, xc.kb * GEMM_BK, xc.x_row, pol_x);
+        uint64_t* x_bar = &full_bar[stage];
+        if (norm_in) {
+          x_bar = &xfull_bar[stage];
+          mbar_arrive_expect_tx(x_bar, Cfg::X_BYTES);
+        }
+        tma_load_2d_hint(&xmap, x_bar, smem_x + stage * Cfg::X_BYTES, xc.kb * GEMM_BK, xc.x_row, pol_x);
         cur_next(xc);
         if (++stage == STAGES) {
           stage = 0;
@@ -352,6 +455,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         }
       }
       TL(4);  // last TMA issued
+      STL_EXTRA(STL_MINE(), 1);
       // Cross-kernel weight prefetch: HBM goes idle while this kernel drains its pipeline, reduces split tiles and
       // exits, and the next GEMM of the layer stack needs ~10 us before its own loads are in flight.  So the boxes
       // that the next GEMM's CTAs will read FIRST are pulled into the 126 MB L2 now (TMA prefetch, no smem, no
@@ -378,14 +482,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_bits = 0;  // per-buffer phase parity
+    bool stl_first_done = false;
     while (it.next(tile, kb0, kb1, slot)) {
       mbar_wait(&tmem_empty[acc], ((acc_bits >> acc) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (norm_in) mbar_wait(&ready_bar[stage], phase);  // the token tile has been normalised in place
         tc_fence_after();
         if (elect_one()) {
+          if (!stl_first_done) STL_EXTRA(*stl_slot_smem, 0);  // first MMA of the CTA
+          stl_first_done = true;
           const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_x + stage * Cfg::X_BYTES));
 #pragma unroll
           for (int h = 0; h < NW; ++h) {
@@ -410,11 +518,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       acc_bits ^= (1u << acc);
       acc = (acc + 1) % N_ACC;
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
     const int sub = warp & 3;          // TMEM sub-partition this warp may read
     const int row = sub * 32 + lane_id();  // weight row within the tile
     const int ep_tid = (warp - 2) * 32 + lane_id();
+    if constexpr (BT <= GEMM_NORM_MAX_T) {
+      if (norm_helpers) {  // start-up burst of the fused-norm consumer: k-blocks 2..5
+        asm volatile("bar.sync 2, 192;\n" ::: "memory");  // rstd is in shared memory
+        float rs[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) rs[j] = rstd_smem[(lane_id() >> 3) + 4 * j];
+        norm_stage(warp, rs);  // warps 2..5
+      }
+    }
     UnitIter it(sched, cta);
     int tile, kb0, kb1, slot;
     int acc = 0;
@@ -427,7 +544,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       const bool partial = (kb0 > 0) || (kb1 < KB);
       mbar_wait(&tmem_full[acc], (acc_bits >> acc) & 1);
       tc_fence_after();
+      if (cl_push) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");  // all peers are running
       if (ep_tid == 0) TL(5);  // accumulator ready (all MMAs of the unit retired)
+      if (ep_tid == 0 && !norm_in) STL_EXTRA(*stl_slot_smem, 2);
       float* my_ws = ws + (size_t)(cta * 2 + slot) * Cfg::PART_FLOATS;
 #pragma unroll 1
       for (int h = 0; h < NW; ++h) {  // the unit's NW accumulators = weight tiles n_tile * NW + h
@@ -461,10 +580,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           } else {
             // split tile: fp32 partial to the global workspace, or (cluster mode) to this CTA's own shared memory --
             // the ring is idle by now: this CTA's only unit has retired all its MMAs
+            if (cl_push) {
+              // receive buffer of owner o (behind the ring, never aliased with in-flight stages -- the owner may still be
+              // in its main loop): [source rank][local token index i = t / s][128 rows]; a warp's 32 lanes write one
+              // 128-byte line of the owner's shared memory
+              const int crank_e = (int)cluster_ctarank();
+              const int tpo = (BT + cluster_split - 1) / cluster_split;
+              const uint32_t rbase = smem_u32(wn_smem) + (uint32_t)(row * 4);
+              int o = c0 % cluster_split, i_loc = c0 / cluster_split;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < t_valid) {
+                  const uint32_t ra = dsmem_addr(rbase + (uint32_t)(((crank_e * tpo + i_loc) * GEMM_BN) * 4), (uint32_t)o);
+                  asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(ra), "f"(__uint_as_float(r[j])) : "memory");
+                }
+                if (++o == cluster_split) {
+                  o = 0;
+                  ++i_loc;
+                }
+              }
+            } else {
             float* dst = (cluster_split > 0 ? reinterpret_cast<float*>(smem) : my_ws) + h * (BT * GEMM_BN);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (c0 + j < t_valid) dst[(size_t)(c0 + j) * GEMM_BN + row] = __uint_as_float(r[j]);
+            }
           }
         }
       }
@@ -571,12 +711,60 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         asm volatile("bar.sync 1, 128;\n" ::: "memory");  // flag_smem reuse safety
       }
     }
+  } else if (norm_in) {
+    // ===================== activation transform: fused residual-stream RMSNorm (warps 6..7) =====================
+    // k-blocks alternate between the two warps; the four epilogue warps take k-blocks 2..5 of the start-up burst (see
+    // norm_stage above).  rstd first: lane p fetches partial sum p of every row of this warp's half of the token tile
+    // (all loads independent: one L2 round trip), a fixed shuffle tree adds them (deterministic).
+    if constexpr (BT <= GEMM_NORM_MAX_T) {
+      const int tw = warp - 6;                     // 0 / 1
+      const int tid = threadIdx.x - GEMM_THREADS;  // 0..63
+      const int lane = lane_id();
+      // the norm weights are static: all of them into shared memory before the dependency wait
+      for (int i = tid; i < K / 8; i += 64)
+        reinterpret_cast<uint4*>(wn_smem)[i] = __ldg(reinterpret_cast<const uint4*>(norm.w_norm) + i);
+      griddep_wait();  // the partial sums (and h, through the producer warp's TMA) come from the preceding GEMM
+      if (tid == 0) STL_EXTRA(*stl_slot_smem, 2);  // (timeline builds: fused consumers report this instead of acc-ready)
+      constexpr int RW = BT / 2;
+      const int row0 = tw * RW, np = norm.n_parts;
+      const bool ok0 = lane < np, ok1 = lane + 32 < np;
+      float v[RW];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const int row = row0 + r;
+        const float* pp = norm.sumsq_in + (size_t)(row < T ? row : 0) * np;
+        const float a0 = __ldcg(pp + (ok0 ? lane : 0)), a1 = __ldcg(pp + (ok1 ? lane + 32 : 0));
+        v[r] = (ok0 ? a0 : 0.f) + (ok1 ? a1 : 0.f);
+      }
+      // level by level over ALL rows (RW independent shuffles in flight per level), then lane r finishes row r
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {
+#pragma unroll
+        for (int r = 0; r < RW; ++r) v[r] += __shfl_xor_sync(0xffffffffu, v[r], sh);
+      }
+      float mine = 0.f;
+#pragma unroll
+      for (int r = 0; r < RW; ++r) mine = lane == r ? v[r] : mine;
+      if (lane < RW) rstd_smem[row0 + lane] = row0 + lane < T ? rsqrtf(mine / (float)K + norm.eps) : 0.f;
+      if (norm_helpers) asm volatile("bar.sync 2, 192;\n" ::: "memory");
+      else asm volatile("bar.sync 2, 64;\n" ::: "memory");
+      if (tid == 0) STL_EXTRA(*stl_slot_smem, 3);
+      float rs[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) rs[j] = rstd_smem[(lane >> 3) + 4 * j];
+      int i = tw;
+      if (i < norm_n_kb) norm_stage(i, rs);
+      i += norm_helpers ? 6 : 2;
+      for (; i < norm_n_kb; i += 2) norm_stage(i, rs);
+    }
   }
 
   if (cluster_split > 0) {
-    // ---- on-chip split-K reduction across the cluster (all threads take part in the two cluster barriers)
-    cluster_sync_all();  // every CTA's partial is in its shared memory
-    if (warp >= 2 && cl_tile >= 0) {
+    // ---- on-chip split-K reduction across the cluster (all threads take part in the cluster barriers)
+    // (push variant: the epilogue warps consumed the start-up phase before their remote stores, the others do it here)
+    if (cl_push && !(warp >= 2 && warp < 6)) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    cluster_sync_all();  // every CTA's partial is in its (pull) / its owner's (push) shared memory
+    if (warp >= 2 && warp < 6 && cl_tile >= 0) {
       const int ep_tid = (warp - 2) * 32 + lane_id();
       const int crank = (int)cluster_ctarank();
       const int r4 = (ep_tid & 31) * 4;   // this thread's 4 consecutive weight rows
@@ -593,12 +781,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
         float4 acc[FIX_T];
 #pragma unroll
         for (int j = 0; j < FIX_T; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 resv[FIX_T];  // fused residual add: this thread's residual values, in flight during the DSMEM reads
+        if (norm.sumsq_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < FIX_T; ++j) {
+            const int t = crank + cluster_split * (i0 + 4 * j);
+            resv[j] = t < cl_tvalid ? __ldcg(reinterpret_cast<const uint2*>(norm.residual + (size_t)t * ldy + n4))
+                                    : make_uint2(0u, 0u);
+          }
+        }
         for (int c = 0; c < cluster_split; ++c) {  // contributor rank order = k order: deterministic
           const uint32_t peer = dsmem_addr(stg, (uint32_t)c) + hoff;
+          const int tpo = (BT + cluster_split - 1) / cluster_split;
           float4 v[FIX_T];
 #pragma unroll
           for (int j = 0; j < FIX_T; ++j) {
             const int t = crank + cluster_split * (i0 + 4 * j);
+            if (cl_push)  // own receive buffer: [source rank c][local token index][128 rows]
+              v[j] = t < cl_tvalid ? *reinterpret_cast<const float4*>(wn_smem + (size_t)(((c * tpo + i0 + 4 * j) * GEMM_BN + r4) * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            else
             v[j] = t < cl_tvalid ? ld_dsmem_f4(peer + (uint32_t)((t * GEMM_BN + r4) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
@@ -612,7 +814,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
           if (t < cl_tvalid) {
             const size_t o = (size_t)t * ldy + n4;
             const float av[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
-            if (rope.positions != nullptr) {
+            if (norm.sumsq_out != nullptr) {
+              // h = bf16(bf16(y) + residual) (fused_add_rms_norm's add), back into the residual stream, + this tile's
+              // share of sum(h^2) for the consumer's rstd; t and the tile are warp-uniform
+              const float rr[4] = {__uint_as_float(resv[j].x << 16), __uint_as_float(resv[j].x & 0xffff0000u),
+                                   __uint_as_float(resv[j].y << 16), __uint_as_float(resv[j].y & 0xffff0000u)};
+              float hh[4], ssq = 0.f;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hh[e] = bf16_round(bf16_round(av[e]) + rr[e]);
+                ssq += hh[e] * hh[e];
+              }
+              __nv_bfloat162 lo = __floats2bfloat162_rn(hh[0], hh[1]), hi = __floats2bfloat162_rn(hh[2], hh[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(norm.residual + o) = pk;
+#pragma unroll
+              for (int sh = 16; sh > 0; sh >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, sh);
+              if (lane_id() == 0) norm.sumsq_out[(size_t)t * (N / GEMM_BN) + nt] = ssq;
+            } else if (rope.positions != nullptr) {
               qkv_rope_store(rope, nt, t, r4, av, Y + o);
             } else if (out_f32 == 2) {
               __nv_bfloat16* yo = Y + (size_t)t * ldy + (n4 >> 1);
@@ -640,7 +861,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_
       }
       }
     }
-    cluster_sync_all();  // nobody exits while a peer may still read its shared memory
+    if (!cl_push) cluster_sync_all();  // nobody exits while a peer may still read its shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -727,7 +948,7 @@ static bool gemm_cluster_enabled() {  // TGIS_GEMM_CLUSTER=0: always reduce spli
 template <int BT, int NW>
 __global__ void gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap, const __grid_constant__ CUtensorMap, void*, int,
                                          int, int, int, float*, int*, int, int, const __grid_constant__ CUtensorMap,
-                                         GemmNext, int, GemmRope);
+                                         GemmNext, int, GemmRope, GemmNorm);
 
 // How many clusters of `s` GEMM CTAs (one CTA per SM) the device can hold at once: a GPC hosts floor(its SMs / s) of them
 // (148 SMs: 74 of 2, 45 of 3, 33 of 4, ...).  Queried once per size; without a device (host-only plan tests) the
@@ -749,7 +970,7 @@ static int gemm_max_clusters(int s, int num_sms) {
     qc.attrs = qa;
     qc.numAttrs = 1;
     int n = 0;
-    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) ==
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MAX) ==
             cudaSuccess &&
         cudaOccupancyMaxActiveClusters(&n, gemm_bf16_tcgen05_kernel<32, 1>, &qc) == cudaSuccess && n > 0) {
       cache[s] = n;
@@ -847,7 +1068,7 @@ static int cluster_split_bt(int T, int N, int K, int num_sms) {
   if (cluster_ok[split][nc] == 0) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MAX);
       attr_set = true;
     }
     cudaLaunchConfig_t qc{};
@@ -894,43 +1115,75 @@ int gemm_cluster_split(int T, int N, int K, int num_sms) {
 template <int BT, int NW>
 static cudaError_t launch_bt(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, int out_f32, cudaStream_t stream,
-                             const CUtensorMap& next_wmap, const GemmNext& nxt, const GemmRope& rope) {
+                             const CUtensorMap& next_wmap, const GemmNext& nxt, const GemmRope& rope, const GemmNorm& norm) {
   using Cfg = GemmCfg<BT, NW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+                                         Cfg::SMEM_MAX);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int t_tiles = (T + BT - 1) / BT;
   const int grid = gemm_grid_size(T, N, K, num_sms);
-  const int stream_weights = (t_tiles == 1) ? 1 : 0;
+  // bit 0: weights are read once (evict-first); bit 1: stream-K share before the whole tiles (GemmSched::sk_first;
+  // TGIS_GEMM_SK_FIRST=0: pure stream-K as in round 1).  The fused-norm consumer's transform warps assume the pure cut.
+  // Token tiles above 64 rows keep the pure cut: there the whole tile's direct epilogue (128+ tokens through the TMEM
+  // loads) is a longer tail than the fix-up it replaces (measured: batch 128 +1.2 %, batch 32 / 64 -2.3 / -1.2 %).
+  static int sk_first_env = -1;
+  if (sk_first_env < 0) {
+    const char* e = getenv("TGIS_GEMM_SK_FIRST");
+    sk_first_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  int stream_weights = (t_tiles == 1) ? (1 | ((sk_first_env && norm.h == nullptr && BT <= 64) ? 2 : 0)) : 0;
   const int split = cluster_split_bt<BT, NW>(T, N, K, num_sms);
+  // bit 2: push variant of the cluster reduction (receive buffer of (BT + 8) x 128 floats behind the ring; token tiles of
+  // at most 32 rows, where it fits next to the full ring).  TGIS_GEMM_CLUSTER_PUSH=1 enables it (default: pull variant).
+  static int push_env = -1;
+  if (push_env < 0) {
+    const char* e = getenv("TGIS_GEMM_CLUSTER_PUSH");
+    push_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  const bool push = push_env && split > 0 && BT <= 32 && NW == 1 && norm.h == nullptr;
+  if (push) stream_weights |= 4;
   // the fused RoPE epilogue lives in the two split-tile reductions (cluster and global fix-up): every tile must be split
   if (rope.positions != nullptr && (gemm_even_split(T, N, K, num_sms) < 2 || out_f32 != 0 ||
                                     N != (rope.n_q + 2 * rope.n_kv) * HEAD_DIM))
     return cudaErrorInvalidValue;
+  // fused residual add / RMSNorm (GemmNorm): the producer side lives in the cluster reduction only, the consumer side in
+  // decode-shaped launches with a token tile of at most 64 rows
+  if (norm.sumsq_out != nullptr && (split == 0 || out_f32 != 0 || rope.positions != nullptr || N % GEMM_BN != 0 ||
+                                    norm.residual == nullptr || ldy != N))
+    return cudaErrorInvalidValue;
+  const size_t smem_bytes = (size_t)Cfg::SMEM_BYTES + (norm.h != nullptr ? (size_t)K * 2 : 0) +
+                            (push ? (size_t)(BT + 8) * GEMM_BN * 4 : 0);
+  if (norm.h != nullptr && (t_tiles != 1 || BT > GEMM_NORM_MAX_T || K % GEMM_BK != 0 || NW != 1 || norm.n_parts <= 0 || norm.n_parts > GEMM_NORM_MAX_PARTS ||
+                            smem_bytes > (size_t)Cfg::SMEM_MAX))
+    return cudaErrorInvalidValue;
+  const int threads = norm.h != nullptr ? GEMM_THREADS_NORM : GEMM_THREADS;
   if (split > 0)
-    return launch_k_cluster(gemm_bf16_tcgen05_kernel<BT, NW>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, split,
-                            wmap, xmap, Y, ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, split, rope);
-  return launch_k(gemm_bf16_tcgen05_kernel<BT, NW>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, wmap, xmap, Y,
-                  ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, 0, rope);
+    return launch_k_cluster(gemm_bf16_tcgen05_kernel<BT, NW>, dim3(grid), dim3(threads), smem_bytes, stream, split,
+                            wmap, xmap, Y, ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, split, rope,
+                            norm);
+  return launch_k(gemm_bf16_tcgen05_kernel<BT, NW>, dim3(grid), dim3(threads), smem_bytes, stream, wmap, xmap, Y,
+                  ldy, T, N, K, ws, counters, stream_weights, out_f32, next_wmap, nxt, 0, rope, norm);
 }
 
 // xmap must have been built with box_rows == gemm_pick_bt(T)
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32,
-                             const CUtensorMap* next_wmap, const GemmNext* next, const GemmRope* rope) {
+                             const CUtensorMap* next_wmap, const GemmNext* next, const GemmRope* rope, const GemmNorm* norm) {
   GemmRope rp{};
   if (rope) rp = *rope;
+  GemmNorm nr{};
+  if (norm) nr = *norm;
   GemmNext nx{};
   if (next && next_wmap) nx = *next;
   const CUtensorMap& nm = (next && next_wmap) ? *next_wmap : wmap;
   const int nw = gemm_nw(T);
 #define TGIS_GEMM_CASE(B)                                                                                              \
-  return nw == 2 ? launch_bt<B, 2>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp)     \
-                 : launch_bt<B, 1>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp)
+  return nw == 2 ? launch_bt<B, 2>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp, nr) \
+                 : launch_bt<B, 1>(wmap, xmap, Y, ldy, T, N, K, ws, counters, num_sms, out_f32, stream, nm, nx, rp, nr)
   switch (gemm_pick_bt(T)) {
     case 16: TGIS_GEMM_CASE(16);
     case 32: TGIS_GEMM_CASE(32);

@@ -41,11 +41,31 @@ struct GemmRope {
   __nv_bfloat16* v_cache;
   int32_t n_q, n_kv;
 };
+// Optional fusion of the layer stack's  residual add + RMSNorm  (vllm layernorm.py fused_add_rms_norm; same rounding
+// points as add_rmsnorm_launch) into the two GEMMs either side of it, decode-shaped launches only (one token tile,
+// T <= 64):
+//  * producer (o / down projection, cluster mode required): the split-tile reduction does not write Y; it computes
+//    h = bf16(bf16(acc) + residual), stores h back to `residual` [T, N] and the tile's sum of h^2 to
+//    sumsq_out[t * (N / 128) + tile]  (N % 128 == 0);
+//  * consumer (qkv / gate_up projection): the activation operand is not loaded by TMA; two extra warps build
+//    bf16(bf16(h * rstd) * w_norm) straight into the swizzled shared-memory stage, rstd[t] from the n_parts partial sums
+//    added in tile order (deterministic).  K % 64 == 0.
+struct GemmNorm {
+  __nv_bfloat16* residual;       // producer: in/out [T, N]; nullptr = off
+  float* sumsq_out;              // producer: [T][N / 128]
+  const __nv_bfloat16* h;        // consumer: [T, K]; nullptr = off
+  const float* sumsq_in;         // consumer: [T][n_parts]
+  const __nv_bfloat16* w_norm;   // consumer: [K]
+  int32_t n_parts;
+  float eps;
+};
+constexpr int GEMM_NORM_MAX_T = 64;
+constexpr int GEMM_NORM_MAX_PARTS = 64;  // hidden <= 8192
 int gemm_cluster_split(int T, int N, int K, int num_sms);
 cudaError_t gemm_bf16_launch(const CUtensorMap& wmap, const CUtensorMap& xmap, void* Y, int ldy, int T, int N, int K,
                              float* ws, int* counters, int num_sms, cudaStream_t stream, int out_f32 = 0,
                              const CUtensorMap* next_wmap = nullptr, const GemmNext* next = nullptr,
-                             const GemmRope* rope = nullptr);
+                             const GemmRope* rope = nullptr, const GemmNorm* norm = nullptr);
 
 // ---- gemm_ref.cu (debug cross-check only; never on the product path) ---------------------------------------------
 cudaError_t gemm_bf16_ref_launch(const __nv_bfloat16* X, int ldx, const __nv_bfloat16* W, void* Y, int ldy, int T,

@@ -246,15 +246,35 @@ __device__ __forceinline__ unsigned long long stl_timer() {
     _r[1] = stl_timer();                                                                              \
     _r[2] = 0;                                                                                        \
     _r[3] = 0;                                                                                        \
+    unsigned long long* _x = g_stl + 8 + 4096 * 4 + _stl * 4;                                         \
+    _x[0] = _x[1] = _x[2] = _x[3] = 0;                                                                \
   }
-#define STL_WAITED() do { if (_stl >= 0) g_stl[8 + _stl * 4 + 2] = stl_timer(); } while (0)
-#define STL_EXIT() do { if (_stl >= 0) g_stl[8 + _stl * 4 + 3] = stl_timer(); } while (0)
+// header word [1] = latest exit stamp of ANY warp of any instrumented kernel; the next kernel's CTA 0 stores
+// (its wait-return time - that stamp) in bits 32..51 of its record's word 0, so the "gap" after a kernel splits into
+// the kernel's own tail (last warp exit - CTA 0 exit) and the dependency-resolution latency.
+#define STL_WAITED() do { if (_stl >= 0) {                                                            \
+    const unsigned long long _t = stl_timer();                                                        \
+    g_stl[8 + _stl * 4 + 2] = _t;                                                                     \
+    const unsigned long long _last = *((volatile unsigned long long*)(g_stl + 1));                    \
+    g_stl[8 + _stl * 4 + 0] |= ((_t > _last ? _t - _last : 0ull) & 0xfffffull) << 32; } } while (0)
+#define STL_EXIT() do {                                                                               \
+    if (g_stl != nullptr && (threadIdx.x & 31) == 0) atomicMax(g_stl + 1, stl_timer());               \
+    if (_stl >= 0) g_stl[8 + _stl * 4 + 3] = stl_timer(); } while (0)
+// extra stamps of the instrumented CTA, second half of the buffer: [8 + 4096 * 4 + record * 4 + k].  Other warps learn the
+// record index through a shared-memory word (STL_SHARE by thread 0 before a CTA barrier).
+#define STL_SHARE(smem_int_ptr) do { if (threadIdx.x == 0) *(smem_int_ptr) = _stl; } while (0)
+#define STL_EXTRA(rec, k) do { const int _rc = (rec);                                                 \
+    if (g_stl != nullptr && _rc >= 0) g_stl[8 + 4096 * 4 + _rc * 4 + (k)] = stl_timer(); } while (0)
+#define STL_MINE() (_stl)
 #else
 #define TGIS_STL_DEFINE(prefix) \
   int prefix##_set_step_timeline(unsigned long long*) { return -2; }
 #define STL_ENTER(kid) do {} while (0)
 #define STL_WAITED() do {} while (0)
 #define STL_EXIT() do {} while (0)
+#define STL_SHARE(smem_int_ptr) do {} while (0)
+#define STL_EXTRA(rec, k) do {} while (0)
+#define STL_MINE() (-1)
 #endif
 
 }  // namespace tgis

@@ -53,12 +53,13 @@ extern "C" {
 int tgis_k_gemm_timeline(uint64_t* out64) { return gemm_timeline_read((unsigned long long*)out64); }
 
 // Step timeline (debug builds, -DTGIS_STEP_TIMELINE): buffer = [8 header words: [0] = records written][4096 x 4 words]
+// [4096 x 4 extra stamps of the GEMM records: first MMA issued, last TMA issued, last accumulator ready, rstd ready]
 static unsigned long long* g_step_tl_buf = nullptr;
 int tgis_k_step_timeline_enable(void) {
   if (!g_step_tl_buf) {
-    if (cudaMalloc(&g_step_tl_buf, sizeof(unsigned long long) * (8 + 4096 * 4)) != cudaSuccess) return kfail("cudaMalloc");
+    if (cudaMalloc(&g_step_tl_buf, sizeof(unsigned long long) * (8 + 4096 * 8)) != cudaSuccess) return kfail("cudaMalloc");
   }
-  KCK(cudaMemset(g_step_tl_buf, 0, sizeof(unsigned long long) * (8 + 4096 * 4)));
+  KCK(cudaMemset(g_step_tl_buf, 0, sizeof(unsigned long long) * (8 + 4096 * 8)));
   int rc = gemm_set_step_timeline(g_step_tl_buf);
   if (rc != 0) return rc;  // -2: not a timeline build
   elementwise_set_step_timeline(g_step_tl_buf);
@@ -70,7 +71,7 @@ int tgis_k_step_timeline_enable(void) {
 int tgis_k_step_timeline_read(uint64_t* out) {
   if (!g_step_tl_buf) return kfail("step timeline not enabled");
   KCK(cudaDeviceSynchronize());
-  KCK(cudaMemcpy(out, g_step_tl_buf, sizeof(unsigned long long) * (8 + 4096 * 4), cudaMemcpyDeviceToHost));
+  KCK(cudaMemcpy(out, g_step_tl_buf, sizeof(unsigned long long) * (8 + 4096 * 8), cudaMemcpyDeviceToHost));
   KCK(cudaMemset(g_step_tl_buf, 0, sizeof(unsigned long long) * 8));
   return 0;
 }
@@ -170,6 +171,70 @@ int tgis_k_gemm_rope(const void* x_dev, const void* w_dev, void* y_dev, int32_t 
   const GemmRope rp{pos.p, sm.p, (const bf16*)cos_sin_dev, (bf16*)k_cache_dev, (bf16*)v_cache_dev, n_q, n_kv};
   KCK(gemm_bf16_launch(wm, xm, y_dev, N, T, N, K, ws.p, ctr.p, sms, 0, 0, nullptr, nullptr, &rp));
   KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// Layer-stack slice  a -> [GEMM W1] -> (+ residual, RMSNorm w_norm) -> [GEMM W2 (out_mode2: 0 bf16, 2 fused SwiGLU)] -> y2
+// run either as three launches (fused = 0: gemm, add_rmsnorm_launch, gemm) or as two with the add + norm folded into the
+// two GEMMs (fused = 1, GemmNorm).  residual [T, H] is updated in place either way.  Returns 1 when the launch plan cannot
+// fuse this shape (nothing computed).  iters > 1 times the chain (residual keeps accumulating: timing only).
+int tgis_k_gemm_norm_chain(const void* a_dev, int32_t a_rows_alloc, const void* w1_dev, void* residual_dev,
+                           const void* w_norm_dev, const void* w2_dev, void* y2_dev, int32_t T, int32_t K1, int32_t H,
+                           int32_t N2, float eps, int32_t out_mode2, int32_t fused, int32_t iters, float* us_out) {
+  const int sms = test_num_sms();
+  const int bt = gemm_pick_bt(T);
+  if (fused && (T > GEMM_NORM_MAX_T || gemm_cluster_split(T, H, K1, sms) == 0 || H % 128 != 0)) return 1;
+  if (a_rows_alloc < bt) return kfail("a must have at least one TMA box of rows allocated");
+  Tmp<bf16> y1, xn;
+  Tmp<float> ssq, ws;
+  Tmp<int> ctr;
+  const int rows = T > bt ? T : bt;
+  KCK(y1.alloc((size_t)rows * H));
+  KCK(xn.alloc((size_t)rows * H));
+  KCK(cudaMemset(xn.p, 0, (size_t)rows * H * sizeof(bf16)));
+  KCK(ssq.alloc((size_t)rows * (H / 128 + 1)));
+  KCK(ws.alloc(gemm_workspace_bytes(sms) / sizeof(float)));
+  KCK(ctr.alloc(1 << 16));
+  KCK(cudaMemset(ctr.p, 0, sizeof(int) << 16));
+  CUtensorMap wm1, am, wm2, xm;
+  if (make_tmap_bf16_2d(&wm1, w1_dev, H, K1, K1, 128, 64) != 0) return kfail("w1 tensor map failed");
+  if (make_tmap_bf16_2d(&am, a_dev, a_rows_alloc, K1, K1, bt, 64) != 0) return kfail("a tensor map failed");
+  if (make_tmap_bf16_2d(&wm2, w2_dev, N2, H, H, 128, 64) != 0) return kfail("w2 tensor map failed");
+  // the fused consumer stages the raw residual stream by TMA and normalises it in shared memory
+  if (make_tmap_bf16_2d(&xm, fused ? residual_dev : (void*)xn.p, fused ? a_rows_alloc : rows, H, H, bt, 64) != 0)
+    return kfail("xn tensor map failed");
+  const int ldy2 = out_mode2 == 2 ? N2 / 2 : N2;
+  cudaEvent_t e0, e1;
+  KCK(cudaEventCreate(&e0));
+  KCK(cudaEventCreate(&e1));
+  if (iters < 1) iters = 1;
+  KCK(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) {
+    if (fused) {
+      GemmNorm prod{};
+      prod.residual = (bf16*)residual_dev;
+      prod.sumsq_out = ssq.p;
+      KCK(gemm_bf16_launch(wm1, am, y1.p, H, T, H, K1, ws.p, ctr.p, sms, 0, 0, nullptr, nullptr, nullptr, &prod));
+      GemmNorm cons{};
+      cons.h = (const bf16*)residual_dev;
+      cons.sumsq_in = ssq.p;
+      cons.w_norm = (const bf16*)w_norm_dev;
+      cons.n_parts = H / 128;
+      cons.eps = eps;
+      KCK(gemm_bf16_launch(wm2, xm, y2_dev, ldy2, T, N2, H, ws.p, ctr.p, sms, 0, out_mode2, nullptr, nullptr, nullptr, &cons));
+    } else {
+      KCK(gemm_bf16_launch(wm1, am, y1.p, H, T, H, K1, ws.p, ctr.p, sms, 0, 0));
+      KCK(add_rmsnorm_launch(y1.p, (bf16*)residual_dev, (const bf16*)w_norm_dev, xn.p, T, H, eps, 0));
+      KCK(gemm_bf16_launch(wm2, xm, y2_dev, ldy2, T, N2, H, ws.p, ctr.p, sms, 0, out_mode2));
+    }
+  }
+  KCK(cudaEventRecord(e1, 0));
+  KCK(cudaDeviceSynchronize());
+  float ms = 0.f;
+  KCK(cudaEventElapsedTime(&ms, e0, e1));
+  if (us_out) *us_out = ms * 1000.f / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
 }
 

@@ -71,7 +71,7 @@ ENGINE_SYMBOLS = [
     "tgis_engine_max_model_len", "tgis_engine_set_profiling", "tgis_nccl_unique_id", "tgis_engine_worker_run", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
 ]
 KERNEL_SYMBOLS = [
-    "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_step_timeline_enable", "tgis_k_step_timeline_read", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_attention",
+    "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_step_timeline_enable", "tgis_k_step_timeline_read", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_gemm_norm_chain", "tgis_k_attention",
     "tgis_k_attention_bench", "tgis_k_decode_items", "tgis_k_gemm_plan", "tgis_k_gemm_unit_rows",
     "tgis_k_sampler", "tgis_k_sampler_ex", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
 ]
@@ -122,6 +122,8 @@ def load_library() -> C.CDLL:
     lib.tgis_engine_run_until_idle.argtypes = [vp]
     lib.tgis_k_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(f32), i32]
     lib.tgis_k_rmsnorm.argtypes = [vp, vp, vp, vp, i32, i32, f32]
+    lib.tgis_k_gemm_norm_chain.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, i32,
+                                           C.POINTER(f32)]
     lib.tgis_k_silu_mul.argtypes = [vp, vp, i32, i32]
     lib.tgis_k_rope_kv.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp, i32, i32, i32]
     lib.tgis_k_attention.argtypes = [vp, vp, vp, C.POINTER(i32), i32, C.POINTER(i32), i32, i32, vp, i32, i32, f32]
