@@ -13,6 +13,10 @@
  *   tgis_engine_poll                             <- the AsyncGenerator[RequestOutput] consumed at
  *                                                   grpc_server.py:281 (Generate) and :367 (GenerateStream)
  *   tgis_engine_abort                            <- grpc_server.py:292, :388  `await self.engine.abort(request_id)`
+ *   tgis_engine_set_mask_provider                <- grpc_server.py:581-586 `structured_outputs=get_structured_output_params(
+ *                                                   decoding)` (tgis_utils/structured_outputs.py:14-38): the engine asks the
+ *                                                   host's grammar matcher for each guided request's allowed-token bitmask
+ *                                                   before it samples, and the sampling kernel applies it
  *   tgis_engine_status                           <- grpc_server.py:117 `engine.errored and not engine.is_running`,
  *                                                   __main__.py:71
  *   tgis_engine_max_model_len                    <- grpc_server.py:196-199 `engine.vllm_config.model_config`
@@ -34,7 +38,7 @@
 extern "C" {
 #endif
 
-#define TGIS_ABI_VERSION 4
+#define TGIS_ABI_VERSION 5
 #define TGIS_MAX_REQUEST_ID 96
 #define TGIS_MAX_TOPN 12 /* reference forces max_logprobs >= 11: tgis_utils/args.py:214-216 */
 #define TGIS_MAX_STOP_TOKEN_IDS 8
@@ -92,7 +96,24 @@ typedef struct tgis_sampling_params {
   uint64_t seed;
   int32_t n_stop_token_ids;
   int32_t stop_token_ids[TGIS_MAX_STOP_TOKEN_IDS];
+  int32_t guided;             /* DecodingParameters.guided / format set (structured_outputs.py:14-38): every sampled token
+                                 is restricted to the bitmask the mask provider returns for this request */
+  int32_t reserved;
 } tgis_sampling_params;
+
+/* Guided decoding.  The grammar state machine lives with the host (the reference hands a StructuredOutputsParams to vLLM,
+ * whose scheduler fills one token bitmask per guided request per step: vllm v1/structured_output/__init__.py:204-300
+ * `grammar_bitmask`, and the model runner masks the logits before the sampler: v1/structured_output/utils.py
+ * `apply_grammar_bitmask`).  Here the engine thread calls the provider right before a step that samples for a guided
+ * request: new_tokens[0..n_new) are the tokens generated since the previous call for this request (0 on the first call,
+ * normally 1 afterwards; in order, each reported exactly once -- a preempted and recomputed sequence reports nothing
+ * twice); the provider advances its matcher over them and writes the next step's bitmask: bit (i & 31) of word (i >> 5)
+ * set = token i allowed (xgrammar's int32 token-bitmask layout), n_words = ceil(vocab / 32), bits >= vocab ignored.
+ * allow_bits points into pinned host memory owned by the engine and is valid only during the call.
+ * Return 0: bitmask written; 1: no constraint for this step; < 0: failure -- the request is finished with TGIS_FINISH_ABORT.
+ * The sampling kernel turns the raw logit of every cleared bit into -inf before log-softmax, processors and selection. */
+typedef int (*tgis_mask_fn)(void* user, const char* request_id, const int32_t* new_tokens, int32_t n_new,
+                            uint32_t* allow_bits, int32_t n_words);
 
 enum tgis_finish_reason {
   TGIS_FINISH_NONE = 0,
@@ -162,6 +183,8 @@ int tgis_engine_start(tgis_engine* e);
 int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_t* prompt_ids, int32_t n_prompt,
                             const tgis_sampling_params* params);
 int tgis_engine_abort(tgis_engine* e, const char* request_id);
+/* fn == NULL removes the provider; requests with params->guided != 0 are rejected while none is installed */
+int tgis_engine_set_mask_provider(tgis_engine* e, tgis_mask_fn fn, void* user);
 /* Blocks up to timeout_ms for at least one record; returns the number written to out[0..cap) (>= 0) or <0 on error. */
 int tgis_engine_poll(tgis_engine* e, tgis_step_output* out, int32_t cap, int32_t timeout_ms);
 int tgis_engine_status(tgis_engine* e, tgis_status* out);

@@ -70,6 +70,12 @@ int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void
  * us_out (may be NULL) receives the average device time per launch */
 int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
                       int32_t n_rows, void* seen_bitmap_dev, void* out_host, int32_t iters, float* us_out);
+/* same, with the guided-decoding allow bitmap: allow_bitmap_dev [slots][ceil(vocab/32)] uint32 (bit set = token allowed;
+ * xgrammar's token-bitmask layout) is applied to the rows flagged SAMPLE_MASKED (64) through their seq_slot; a cleared bit
+ * makes the raw logit -inf before every other stage (vllm v1/structured_output/utils.py apply_grammar_bitmask) */
+int tgis_k_sampler_masked(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
+                          int32_t n_rows, void* seen_bitmap_dev, const void* allow_bitmap_dev, void* out_host,
+                          int32_t iters, float* us_out);
 const char* tgis_k_last_error(void);
 /* debug builds only (-DTGIS_GEMM_TIMELINE): %globaltimer stamps of CTA 0 and CTA grid/2, [4][16] u64; else -2 */
 int tgis_k_gemm_timeline(uint64_t* out64);

@@ -29,6 +29,33 @@ class FakeNativeEngine:
         self.errored = False
         self.aborted: list[str] = []
         self.steps = 0
+        self._mask_cb = None
+
+    def set_mask_provider(self, callback) -> None:   # engine.core.NativeEngine.set_mask_provider
+        self._mask_cb = callback
+
+    def _guided_token(self, rid, st, tok):
+        """What the native engine does for a guided row (csrc/engine.cu run_batch): report the tokens generated since
+        the last call, take the bitmask, and sample under it -- here: the first allowed id at or after `tok`, cyclically.
+        Returns None when the provider failed (the request is aborted)."""
+        import ctypes as C
+
+        words = (self.model.vocab + 31) // 32
+        bits = (C.c_uint32 * words)()
+        fed = st.setdefault("fed", 0)
+        new = st["out"][fed:]
+        arr = (C.c_int32 * max(1, len(new)))(*new)
+        rc = self._mask_cb(None, rid.encode(), arr, len(new), bits, words)
+        st["fed"] = len(st["out"])
+        if rc < 0:
+            return None
+        if rc == 1:
+            return tok
+        for d in range(self.model.vocab):
+            i = (tok + d) % self.model.vocab
+            if (bits[i >> 5] >> (i & 31)) & 1:
+                return i
+        return None
 
     def start(self) -> None:
         self._thread = threading.Thread(target=self._loop, daemon=True)
@@ -71,6 +98,13 @@ class FakeNativeEngine:
                     tok = fake_next_token(st["prompt"], len(st["out"]), self.model.vocab)
                 if len(st["out"]) < sp.min_tokens and tok == sp.eos_token_id:
                     tok = 3
+                if getattr(sp, "guided", 0) and self._mask_cb is not None:
+                    tok = self._guided_token(rid, st, tok)
+                    if tok is None:
+                        self._active.pop(rid)
+                        self.aborted.append(rid)
+                        self._emit(rid, st, None, _lib.FINISH_ABORT, -1)
+                        continue
                 st["out"].append(tok)
                 now = time.monotonic()
                 st["first"] = st["first"] or now

@@ -22,6 +22,7 @@ SAMPLE_OUT_DTYPE = np.dtype([
     ("topn_lps", "<f4", (12,)),
 ])
 SAMPLE_GREEDY, SAMPLE_LOGPROBS, SAMPLE_TYPICAL, SAMPLE_LENPEN, SAMPLE_SEEDED = 1, 2, 4, 8, 16
+SAMPLE_MASKED = 64
 
 
 def lib():
@@ -102,16 +103,18 @@ def dense_from_v_cache(vc: torch.Tensor) -> torch.Tensor:
 
 
 def run_sampler(logits: torch.Tensor, rows: np.ndarray, bitmap: torch.Tensor | None = None, iters: int = 1,
-                return_us: bool = False):
+                return_us: bool = False, allow: torch.Tensor | None = None):
     """logits: fp32 (golden fixtures) or bf16 (the product path's dtype) [rows, V] on the device."""
     assert rows.dtype == SAMPLE_ROW_DTYPE and rows.dtype.itemsize == lib().tgis_k_sizeof_sample_row()
     assert SAMPLE_OUT_DTYPE.itemsize == lib().tgis_k_sizeof_sample_out()
     assert logits.dtype in (torch.float32, torch.bfloat16)
     out = np.zeros(len(rows), dtype=SAMPLE_OUT_DTYPE)
     us = C.c_float(0)
-    rc = lib().tgis_k_sampler_ex(ptr(logits), 1 if logits.dtype == torch.bfloat16 else 0, logits.stride(0),
-                                 logits.shape[1], rows.ctypes.data_as(C.c_void_p), len(rows),
-                                 ptr(bitmap) if bitmap is not None else None, out.ctypes.data_as(C.c_void_p), iters,
-                                 C.byref(us))
+    # allow: [slots, ceil(V/32)] int32 guided-decoding bitmask on the device, used by rows flagged SAMPLE_MASKED
+    rc = lib().tgis_k_sampler_masked(ptr(logits), 1 if logits.dtype == torch.bfloat16 else 0, logits.stride(0),
+                                     logits.shape[1], rows.ctypes.data_as(C.c_void_p), len(rows),
+                                     ptr(bitmap) if bitmap is not None else None,
+                                     ptr(allow) if allow is not None else None, out.ctypes.data_as(C.c_void_p),
+                                     iters, C.byref(us))
     assert rc == 0, kerr()
     return (out, us.value) if return_us else out

@@ -114,6 +114,7 @@ struct Request {
   std::vector<int32_t> blocks;
   bool aborted = false;
   uint64_t seed = 0;
+  int guided_fed = 0;  // generated tokens already reported to the mask provider (guided decoding)
   double ts_arrival = 0, ts_first_sched = 0, ts_first_token = 0, ts_last_token = 0;
   int n_out() const { return (int)tokens.size() - n_prompt; }
 };
@@ -149,7 +150,8 @@ struct LayerW {
 struct StepHeader {
   int32_t T, n_dec, n_tiles, R, max_dec_kv, S;
   int32_t graphable;     // replay (or capture) the CUDA graph keyed by (S, KV splits, samp_complex) instead of launching
-  int32_t samp_complex;  // some sampled row needs selection passes (sampling): decides the sampler's cluster size
+  int32_t samp_complex;  // bit 0: some sampled row needs selection passes (sampling): decides the sampler's cluster
+                         // size; bit 1: some row carries a guided-decoding bitmask (the masked sampler instantiation)
   uint64_t copy_bytes;
   int32_t kind;          // 0: engine step; 1: prompt-logprob pass over R rows of the step just executed (T = its tokens,
   int32_t need_norm;     //    need_norm: the final RMSNorm has not run yet)
@@ -237,6 +239,13 @@ struct tgis_engine {
   DevBuf<int> gemm_counters, attn_arrive;
   DevBuf<float> norm_ssq;  // [2][GEMM_NORM_MAX_T][hidden / 128] partial sums of h^2 (fused residual RMSNorm)
   DevBuf<uint32_t> seen_bitmap;
+  // guided decoding: allowed-token bits of the step, one row per sequence slot (same geometry as seen_bitmap); the
+  // provider writes the pinned host row, the row is copied in front of the step, the sampler reads it for SAMPLE_MASKED rows
+  DevBuf<uint32_t> allow_bitmap;
+  uint32_t* h_allow = nullptr;
+  tgis_mask_fn mask_fn = nullptr;
+  void* mask_user = nullptr;
+  long long guided_rows = 0;
   DevBuf<SampleOut> d_samp_out;
   SampleOut* h_samp_out = nullptr;
   SampleOut* h_plp_out = nullptr;  // prompt-logprob pass results (kept apart from the step's sampled rows)
@@ -349,6 +358,7 @@ struct tgis_engine {
     }
     if (h_stage) cudaFreeHost(h_stage);
     if (h_samp_out) cudaFreeHost(h_samp_out);
+    if (h_allow) cudaFreeHost(h_allow);
     if (h_plp_out) cudaFreeHost(h_plp_out);
     if (shm) {
       if (rank == 0) shm->shutdown.store(1, std::memory_order_release);
@@ -473,6 +483,10 @@ struct tgis_engine {
     samp_scratch.alloc((size_t)S_max * V);
     seen_bitmap.alloc((size_t)S_max * bitmap_words);
     seen_bitmap.zero();
+    if (rank == 0) {  // only the sampling rank needs the masks
+      allow_bitmap.alloc((size_t)S_max * bitmap_words);
+      CK(cudaHostAlloc(&h_allow, sizeof(uint32_t) * (size_t)S_max * bitmap_words, cudaHostAllocDefault));
+    }
     d_samp_out.alloc(S_max);
     CK(cudaHostAlloc(&h_samp_out, sizeof(SampleOut) * S_max, cudaHostAllocDefault));
     CK(cudaHostAlloc(&h_plp_out, sizeof(SampleOut) * S_max, cudaHostAllocDefault));
@@ -992,7 +1006,8 @@ struct tgis_engine {
       lm_head_logits(R, 1);
       if (rank == 0) {
         CK(sampler_launch(logits_ptr(), logits_bf16 ? 1 : 0, V, V, ds<SampleRow>(off_rows), R, seen_bitmap.p, bitmap_words,
-                          samp_scratch.p, d_samp_out.p, stream, samp_complex, num_sms));
+                          samp_scratch.p, d_samp_out.p, stream, samp_complex & 1, num_sms,
+                          (samp_complex & 2) ? allow_bitmap.p : nullptr));
         ++n_launches;
         if (copies_here)
           CK(cudaMemcpyAsync(h_samp_out, d_samp_out.p, sizeof(SampleOut) * R, cudaMemcpyDeviceToHost, stream));
@@ -1090,7 +1105,7 @@ struct tgis_engine {
       return;
     }
     const int max_splits = (h.max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
-    const uint64_t key = ((uint64_t)(h.samp_complex ? 1 : 0) << 40) | ((uint64_t)h.S << 16) | (uint64_t)max_splits;
+    const uint64_t key = ((uint64_t)(h.samp_complex & 3) << 40) | ((uint64_t)h.S << 16) | (uint64_t)max_splits;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
       if (graphs.size() >= 64) {
@@ -1186,7 +1201,7 @@ struct tgis_engine {
         const int n_out = r.n_out();
         row.flags = (sp.greedy ? SAMPLE_GREEDY : 0) | (sp.num_logprobs > 0 ? SAMPLE_LOGPROBS : 0) |
                     ((sp.typical_p > 0.f && sp.typical_p < 1.f) ? SAMPLE_TYPICAL : 0);
-        if (!(row.flags & SAMPLE_GREEDY) || (row.flags & SAMPLE_TYPICAL)) samp_complex = 1;
+        if (!(row.flags & SAMPLE_GREEDY) || (row.flags & SAMPLE_TYPICAL)) samp_complex |= 1;
         row.n_topn = std::min<int>(sp.num_logprobs > 0 ? sp.num_logprobs : 0, MAX_TOPN);
         row.temperature = sp.greedy ? 1.f : sp.temperature;
         row.top_k = sp.greedy ? 0 : sp.top_k;
@@ -1212,6 +1227,32 @@ struct tgis_engine {
         row.seed_hi = (uint32_t)(r.seed >> 32);
         row.step = (uint32_t)n_out;
         row.logits_row = R;
+        if (sp.guided) {
+          // guided decoding: report the tokens generated since the last call, get this step's allowed-token bits
+          // (vllm v1/structured_output/__init__.py:204-300 grammar_bitmask) and ship them ahead of the step
+          tgis_mask_fn fn;
+          void* user;
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = mask_fn;
+            user = mask_user;
+          }
+          int rc = -1;
+          uint32_t* hm = h_allow + (size_t)r.slot * bitmap_words;
+          if (fn != nullptr)
+            rc = fn(user, r.id.c_str(), r.tokens.data() + r.n_prompt + r.guided_fed, n_out - r.guided_fed, hm, bitmap_words);
+          r.guided_fed = n_out;
+          if (rc == 0) {
+            row.flags |= SAMPLE_MASKED;
+            samp_complex |= 2;
+            CK(cudaMemcpyAsync(allow_bitmap.p + (size_t)r.slot * bitmap_words, hm, sizeof(uint32_t) * bitmap_words,
+                               cudaMemcpyHostToDevice, stream));
+            h2d_bytes += (long long)sizeof(uint32_t) * bitmap_words;
+            ++guided_rows;
+          } else if (rc < 0) {
+            r.aborted = true;  // the provider failed: the request ends with TGIS_FINISH_ABORT at the next step
+          }
+        }
         samplesrc[R] = T + q_len - 1;
         ++R;
       }
@@ -1569,6 +1610,7 @@ struct tgis_engine {
 extern "C" {
 
 const char* tgis_last_error(void) { return g_last_error.c_str(); }
+static_assert(sizeof(tgis_sampling_params) == 120, "ctypes mirror: engine/_lib.py TgisSamplingParams");
 int tgis_abi_version(void) { return TGIS_ABI_VERSION; }
 
 int tgis_engine_create(const tgis_config* cfg, tgis_engine** out) {
@@ -1665,6 +1707,10 @@ int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_
   if (params->num_logprobs > TGIS_MAX_TOPN || params->prompt_logprobs > TGIS_MAX_TOPN) return fail("num_logprobs too large");
   for (int i = 0; i < n_prompt; ++i)
     if (prompt_ids[i] < 0 || prompt_ids[i] >= e->cfg.vocab) return fail("prompt token id out of range");
+  if (params->guided) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->mask_fn == nullptr) return fail("guided decoding requested but no mask provider is installed");
+  }
   auto r = std::make_unique<Request>();
   r->id = request_id;
   r->tokens.assign(prompt_ids, prompt_ids + n_prompt);
@@ -1687,6 +1733,14 @@ int tgis_engine_abort(tgis_engine* e, const char* request_id) {
     e->abort_ids.emplace_back(request_id);
   }
   e->cv_in.notify_all();
+  return 0;
+}
+
+int tgis_engine_set_mask_provider(tgis_engine* e, tgis_mask_fn fn, void* user) {
+  if (!e) return fail("null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->mask_fn = fn;
+  e->mask_user = user;
   return 0;
 }
 

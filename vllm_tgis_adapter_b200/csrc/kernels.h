@@ -219,13 +219,15 @@ struct SampleOut {            // per row result (pinned host readable)
   float topn_lps[MAX_TOPN];
 };
 constexpr int SAMPLE_GREEDY = 1, SAMPLE_LOGPROBS = 2, SAMPLE_TYPICAL = 4, SAMPLE_LENPEN = 8, SAMPLE_SEEDED = 16;
+constexpr int SAMPLE_MASKED = 64;  // guided decoding: row seq_slot of the allow bitmap holds this step's allowed-token bits
 constexpr int SAMPLE_FORCED = 32;  // token = seed_lo is given (prompt logprobs): report its logprob / rank / top-n only
 // logits: [rows, ld] bf16 (logits_bf16 = 1: the lm_head GEMM's model-dtype output, what vLLM's sampler sees after its
 // fp32 cast) or fp32 (kernel-level golden tests).  any_complex: some row needs selection passes (sampling rows: typical-p /
 // top-k / top-p / race) -> 8 CTAs per row; otherwise the cluster size shrinks with the row count (sampler_cluster_size).
 cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int vocab, const SampleRow* rows, int n_rows,
                            const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
-                           cudaStream_t stream, int any_complex = 1, int num_sms = 148);
+                           cudaStream_t stream, int any_complex = 1, int num_sms = 148,
+                           const uint32_t* allow_bitmap = nullptr /* [slots][bitmap_words], rows flagged SAMPLE_MASKED */);
 int sampler_cluster_size(int n_rows, int any_complex, int num_sms);
 // seen-token bitmap maintenance
 cudaError_t bitmap_clear_launch(uint32_t* bitmap, int bitmap_words, int slot, cudaStream_t stream);

@@ -42,6 +42,9 @@ struct RowCtx {
   int V;
   int lo, hi;              // this CTA's slice of the vocabulary (multiples of 8)
   const uint32_t* seen;    // bitmap of prompt U output tokens (may be null)
+  const uint32_t* allow;   // guided decoding: bit i set = token i allowed this step (null: unconstrained).  A cleared bit
+                           // turns the RAW logit into -inf before anything else looks at it, which is where vLLM applies
+                           // its grammar bitmask (v1/worker/gpu_model_runner.py apply_grammar_bitmask, before the sampler)
   SampleRow p;
   float lenfac_m1;         // (float)(decay^n - 1), 0 => inactive
   bool mask_eos;           // min_tokens not reached
@@ -55,12 +58,19 @@ __device__ __forceinline__ float lt2f(__nv_bfloat16 v) { return __bfloat162float
 // entry i of this CTA's slice [lo, hi): from the shared-memory copy when the slice was staged (every pass after the first
 // then costs shared-memory latency instead of an L2 round trip per dependent load)
 template <class LT>
-__device__ __forceinline__ float load_x(const RowCtx<LT>& c, int i) {
-  return lt2f(c.xc != nullptr ? c.xc[i - c.lo] : c.x[i]);
+__device__ __forceinline__ bool is_allowed(const RowCtx<LT>& c, int i) {
+  return c.allow == nullptr || ((c.allow[i >> 5] >> (i & 31)) & 1u);
 }
 // any entry of the row (global memory)
 template <class LT>
-__device__ __forceinline__ float load_x_any(const RowCtx<LT>& c, int i) { return lt2f(c.x[i]); }
+__device__ __forceinline__ float load_x_any(const RowCtx<LT>& c, int i) {
+  return is_allowed(c, i) ? lt2f(c.x[i]) : -INFINITY;
+}
+// (the staged copy already carries the -inf of disallowed tokens: pass 1 masks before it stores)
+template <class LT>
+__device__ __forceinline__ float load_x(const RowCtx<LT>& c, int i) {
+  return c.xc != nullptr ? lt2f(c.xc[i - c.lo]) : load_x_any(c, i);
+}
 __device__ __forceinline__ void store_x8(float* dst, const float (&v)[8]) {
   *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -443,11 +453,14 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 // Grid = rows x ncl CTAs; the ncl CTAs of a row form one thread-block cluster (runtime cluster size) and each scans
 // 1/ncl of the vocabulary.  Pass 1 (every row): raw max / sum-exp, and for plain greedy rows the argmax of the processed
 // logits in the same sweep -- such a row costs ONE vectorised pass over its logits plus one cluster exchange.
-template <class LT>
+// MASKED: some row of the launch carries a guided-decoding bitmask (a separate instantiation, so that launches without
+// guided rows -- every benchmark configuration -- run exactly the code they ran before the mask existed).
+template <class LT, bool MASKED>
 __global__ void __launch_bounds__(SAMP_THREADS, 1)
 tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRow* __restrict__ rows,
                     uint32_t* __restrict__ seen_bitmap, int bitmap_words, float* __restrict__ scratch,
-                    SampleOut* __restrict__ outs, int ncl, int cache_x, int cache_y) {
+                    SampleOut* __restrict__ outs, int ncl, int cache_x, int cache_y,
+                    const uint32_t* __restrict__ allow_bitmap) {
   // dynamic shared memory: [slice of the raw logits (cache_x)] [slice of the processed logits, fp32 (cache_y)]
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ float redf[2 * SAMP_WARPS];
@@ -483,6 +496,8 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
   LT* xs = reinterpret_cast<LT*>(dyn_smem);
   c.xc = nullptr;  // set after pass 1 has filled it
   c.seen = (c.p.seq_slot >= 0 && c.p.rep_penalty != 1.0f) ? seen_bitmap + (size_t)c.p.seq_slot * bitmap_words : nullptr;
+  c.allow = (MASKED && (c.p.flags & SAMPLE_MASKED) && c.p.seq_slot >= 0)
+                ? allow_bitmap + (size_t)c.p.seq_slot * bitmap_words : nullptr;
   c.lenfac_m1 = (c.p.flags & SAMPLE_LENPEN) ? c.p.len_decay_factor : 0.f;
   c.mask_eos = c.p.n_out < c.p.min_tokens;
   c.typical = false;
@@ -528,6 +543,12 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
     for (int u = 0; u < P1_UNROLL; ++u) {
       const int iu = i0 + u * SAMP_THREADS * 8;
       if (iu < hi) {
+        if (MASKED && c.allow != nullptr) {  // iu % 8 == 0: the 8 bits of this group sit in one byte of the bitmap
+          const uint32_t bits = (c.allow[iu >> 5] >> (iu & 31)) & 0xffu;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (!((bits >> e) & 1u)) xv[u][e] = -INFINITY;
+        }
         if (cache_x) store_x8(xs + (iu - lo), xv[u]);
         consume8(xv[u], iu);
       }
@@ -568,12 +589,15 @@ tgis_sampler_kernel(const LT* __restrict__ logits, int ld, int V, const SampleRo
     }
     c.ent = -cluster_sumf(cl, part, redf, xch);
     const float rm = c.raw_max, lz = c.raw_logz, ent = c.ent;
-    const LT* xx = c.xc != nullptr ? c.xc - lo : c.x;  // indexed xx[i]
+    const LT* xx = c.xc != nullptr ? c.xc - lo : c.x;  // indexed xx[i]; the staged copy is already masked
+    const RowCtx<LT>& cr = c;
+    const bool mask_here = MASKED && c.allow != nullptr && c.xc == nullptr;
+    auto xval = [=, &cr](int i) { return mask_here ? load_x_any(cr, i) : lt2f(xx[i]); };
     auto keyf = [=](int i) {
-      const float lp = (lt2f(xx[i]) - rm) - lz;
+      const float lp = (xval(i) - rm) - lz;
       return __float_as_uint(fabsf((-lp) - ent));
     };
-    auto wf = [=](int i) { return expf((lt2f(xx[i]) - rm) - lz); };
+    auto wf = [=](int i) { return expf((xval(i) - rm) - lz); };
     const uint32_t k = select_weighted_asc(cl, lo, hi, keyf, wf, c.p.typical_p, false, hist, hsum, bcast);
     c.typ_thr = __uint_as_float(k);
     c.typical = true;
@@ -741,10 +765,10 @@ int sampler_cluster_size(int n_rows, int any_complex, int num_sms) {
   return ncl;
 }
 
-template <class LT>
-static cudaError_t sampler_launch_t(const LT* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+template <class LT, bool MASKED>
+static cudaError_t sampler_launch_tm(const LT* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
                                     uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out, int ncl,
-                                    int any_complex, cudaStream_t stream) {
+                                    int any_complex, cudaStream_t stream, const uint32_t* allow_bitmap) {
   // shared-memory staging of the CTA's slice: raw logits always when they fit, the processed row too for sampling rows
   const size_t per = (size_t)(((vocab + ncl - 1) / ncl + 7) / 8 * 8);
   constexpr size_t SMEM_BUDGET = 200 * 1024;
@@ -755,28 +779,40 @@ static cudaError_t sampler_launch_t(const LT* logits, int ld, int vocab, const S
   const size_t smem = (cache_x ? per * sizeof(LT) : 0) + (cache_y ? per * 4 : 0);
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(tgis_sampler_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET);
+    cudaError_t e = cudaFuncSetAttribute(tgis_sampler_kernel<LT, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET);
     if (e != cudaSuccess) return e;
     attr_bytes = SMEM_BUDGET;
   }
   if (ncl > 1)
-    return launch_k_cluster(tgis_sampler_kernel<LT>, dim3(n_rows * ncl), dim3(SAMP_THREADS), smem, stream, ncl, logits, ld,
-                            vocab, rows, seen_bitmap, bitmap_words, scratch, out, ncl, cache_x, cache_y);
-  return launch_k(tgis_sampler_kernel<LT>, dim3(n_rows), dim3(SAMP_THREADS), smem, stream, logits, ld, vocab, rows,
-                  seen_bitmap, bitmap_words, scratch, out, 1, cache_x, cache_y);
+    return launch_k_cluster(tgis_sampler_kernel<LT, MASKED>, dim3(n_rows * ncl), dim3(SAMP_THREADS), smem, stream, ncl, logits, ld,
+                            vocab, rows, seen_bitmap, bitmap_words, scratch, out, ncl, cache_x, cache_y, allow_bitmap);
+  return launch_k(tgis_sampler_kernel<LT, MASKED>, dim3(n_rows), dim3(SAMP_THREADS), smem, stream, logits, ld, vocab, rows,
+                  seen_bitmap, bitmap_words, scratch, out, 1, cache_x, cache_y, allow_bitmap);
+}
+
+template <class LT>
+static cudaError_t sampler_launch_t(const LT* logits, int ld, int vocab, const SampleRow* rows, int n_rows,
+                                    uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out, int ncl,
+                                    int any_complex, cudaStream_t stream, const uint32_t* allow_bitmap) {
+  if (allow_bitmap != nullptr)
+    return sampler_launch_tm<LT, true>(logits, ld, vocab, rows, n_rows, seen_bitmap, bitmap_words, scratch, out, ncl,
+                                       any_complex, stream, allow_bitmap);
+  return sampler_launch_tm<LT, false>(logits, ld, vocab, rows, n_rows, seen_bitmap, bitmap_words, scratch, out, ncl,
+                                      any_complex, stream, nullptr);
 }
 
 cudaError_t sampler_launch(const void* logits, int logits_bf16, int ld, int vocab, const SampleRow* rows, int n_rows,
                            const uint32_t* seen_bitmap, int bitmap_words, float* scratch, SampleOut* out,
-                           cudaStream_t stream, int any_complex, int num_sms) {
+                           cudaStream_t stream, int any_complex, int num_sms, const uint32_t* allow_bitmap) {
   if (n_rows <= 0) return cudaSuccess;
   if (vocab % 8 != 0 || ld % 8 != 0) return cudaErrorInvalidValue;
   const int ncl = sampler_cluster_size(n_rows, any_complex, num_sms);
   if (logits_bf16)
     return sampler_launch_t(static_cast<const __nv_bfloat16*>(logits), ld, vocab, rows, n_rows,
-                            const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out, ncl, any_complex, stream);
+                            const_cast<uint32_t*>(seen_bitmap), bitmap_words, scratch, out, ncl, any_complex, stream,
+                            allow_bitmap);
   return sampler_launch_t(static_cast<const float*>(logits), ld, vocab, rows, n_rows, const_cast<uint32_t*>(seen_bitmap),
-                          bitmap_words, scratch, out, ncl, any_complex, stream);
+                          bitmap_words, scratch, out, ncl, any_complex, stream, allow_bitmap);
 }
 
 size_t sampler_scratch_floats(int vocab) { return (size_t)vocab; }

@@ -374,8 +374,9 @@ int tgis_k_decode_items(const int32_t* seqs_host, int32_t n_seqs, const int32_t*
 
 // logits_bf16 = 0: fp32 logits, 1: bf16 logits.  iters > 1: the launch is repeated and us_out (optional) receives the
 // average device time per launch (CUDA events on the launching stream).
-int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
-                      int32_t n_rows, void* seen_bitmap_dev, void* out_host, int32_t iters, float* us_out) {
+int tgis_k_sampler_masked(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
+                          int32_t n_rows, void* seen_bitmap_dev, const void* allow_bitmap_dev, void* out_host,
+                          int32_t iters, float* us_out) {
   Tmp<SampleRow> rows;
   Tmp<SampleOut> outs;
   Tmp<float> scratch;
@@ -403,10 +404,12 @@ int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, i
   KCK(cudaEventCreate(&e0));
   KCK(cudaEventCreate(&e1));
   if (iters > 1)  // warm-up launch outside the timed region
-    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0, any_complex));
+    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0, any_complex, 148,
+                       (const uint32_t*)allow_bitmap_dev));
   KCK(cudaEventRecord(e0, 0));
   for (int it = 0; it < iters; ++it)
-    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0, any_complex));
+    KCK(sampler_launch(logits_dev, logits_bf16, ld, vocab, rows.p, n_rows, bm, words, scratch.p, outs.p, 0, any_complex, 148,
+                       (const uint32_t*)allow_bitmap_dev));
   KCK(cudaEventRecord(e1, 0));
   KCK(cudaMemcpy(out_host, outs.p, sizeof(SampleOut) * n_rows, cudaMemcpyDeviceToHost));
   KCK(cudaDeviceSynchronize());
@@ -416,6 +419,12 @@ int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, i
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return 0;
+}
+
+int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
+                      int32_t n_rows, void* seen_bitmap_dev, void* out_host, int32_t iters, float* us_out) {
+  return tgis_k_sampler_masked(logits_dev, logits_bf16, ld, vocab, rows_host, n_rows, seen_bitmap_dev, nullptr, out_host,
+                               iters, us_out);
 }
 
 int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,

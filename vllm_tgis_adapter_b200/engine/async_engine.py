@@ -59,6 +59,7 @@ class AsyncTGISEngine:
         self._stopping = False
         self._dead_error: str | None = None
         self.metrics = EngineMetrics()
+        self._mask_provider = None   # guided decoding: created with the first guided request (imports xgrammar)
 
     # -- lifecycle ------------------------------------------------------------------------------------------------
     def start(self, loop: asyncio.AbstractEventLoop | None = None) -> None:
@@ -114,6 +115,18 @@ class AsyncTGISEngine:
     def dead_error(self) -> BaseException:
         return EngineDeadError(self._dead_error or "engine dead")
 
+    @property
+    def supports_guided_decoding(self) -> bool:
+        return True
+
+    def _guided(self):
+        if self._mask_provider is None:
+            from .guided import GrammarCompiler, MaskProvider
+
+            self._mask_provider = MaskProvider(GrammarCompiler(self.tokenizer, self._model_config.vocab))
+            self.engine.set_mask_provider(self._mask_provider.callback)
+        return self._mask_provider
+
     async def get_model_config(self):
         return self.vllm_config.model_config
 
@@ -146,7 +159,7 @@ class AsyncTGISEngine:
             eos_token_id=eos if eos is not None else -1, min_tokens=sp.min_tokens, max_tokens=max_tokens,
             num_logprobs=sp.logprobs or 0, prompt_logprobs=sp.prompt_logprobs or 0,
             seed=sp.seed if not sp.greedy else None,
-            stop_token_ids=sp.stop_token_ids)
+            stop_token_ids=sp.stop_token_ids, guided=sp.structured_outputs is not None)
         nid = f"q{next(self._ids)}"
         queue: asyncio.Queue = asyncio.Queue()
         detok = IncrementalDetokenizer(self.tokenizer, prompt_ids, stop=sp.stop, min_tokens=sp.min_tokens,
@@ -160,6 +173,8 @@ class AsyncTGISEngine:
         delta = sp.output_kind == RequestOutputKind.DELTA
         final_only = sp.output_kind == RequestOutputKind.FINAL_ONLY
         try:
+            if sp.structured_outputs is not None:   # compile before the request exists: a bad spec is a ValueError
+                self._guided().register(nid, sp.structured_outputs)
             self.engine.add_request(nid, prompt_ids, native)
             sent_tokens = 0
             while True:
@@ -186,6 +201,9 @@ class AsyncTGISEngine:
                         continue
                     step_finish: str | None = None
                     if o.finish_reason != _lib.FINISH_NONE:
+                        if (o.finish_reason == _lib.FINISH_ABORT and self._mask_provider is not None
+                                and (gerr := self._mask_provider.error_of(nid))):
+                            raise RuntimeError(f"guided decoding failed: {gerr}")
                         if o.finish_reason == _lib.FINISH_ERROR:
                             # the message lives in the engine object (set on the engine thread); status() copies it
                             # into THIS thread's last-error slot
@@ -245,6 +263,8 @@ class AsyncTGISEngine:
             if not st.done:   # client went away / generator closed early: free the sequence in the engine
                 self.engine.abort(nid)
                 st.done = True
+            if self._mask_provider is not None:
+                self._mask_provider.unregister(nid)
             self._states.pop(nid, None)
             if self._states.get(request_id) is st:
                 del self._states[request_id]

@@ -64,7 +64,7 @@ def make_sampling_params(*, greedy: bool = True, temperature: float = 1.0, top_k
                          typical_p: float = 0.0, repetition_penalty: float = 1.0,
                          length_penalty: tuple[int, float] | None = None, eos_token_id: int = 2, min_tokens: int = 0,
                          max_tokens: int = 16, num_logprobs: int = 0, prompt_logprobs: int = 0, seed: int | None = None,
-                         stop_token_ids: Iterable[int] = ()) -> TgisSamplingParams:
+                         stop_token_ids: Iterable[int] = (), guided: bool = False) -> TgisSamplingParams:
     sp = TgisSamplingParams()
     sp.greedy = 1 if greedy else 0
     sp.temperature = float(temperature)
@@ -87,6 +87,7 @@ def make_sampling_params(*, greedy: bool = True, temperature: float = 1.0, top_k
     sp.n_stop_token_ids = len(ids)
     for i, t in enumerate(ids):
         sp.stop_token_ids[i] = int(t)
+    sp.guided = 1 if guided else 0
     return sp
 
 
@@ -154,6 +155,13 @@ class NativeEngine:
 
     def abort(self, request_id: str) -> None:
         self.lib.tgis_engine_abort(self._h, request_id.encode())
+
+    def set_mask_provider(self, callback) -> None:
+        """callback: a `guided.MASK_FN` C function pointer (the caller keeps it alive), or None to remove it."""
+        self._mask_cb = callback   # the engine stores the raw pointer: keep the ctypes object alive with the engine
+        fn = C.cast(callback, C.c_void_p) if callback is not None else None
+        if self.lib.tgis_engine_set_mask_provider(self._h, fn, None) != 0:
+            raise EngineError(_lib.last_error(self.lib))
 
     def poll(self, timeout_ms: int = 0) -> list[StepOutput]:
         n = self.lib.tgis_engine_poll(self._h, self._poll_buf, len(self._poll_buf), timeout_ms)

@@ -15,6 +15,28 @@ class RequestOutputKind(enum.Enum):
 
 
 @dataclasses.dataclass
+class StructuredOutputsParams:
+    """vllm/sampling_params.py `StructuredOutputsParams`, the members the adapter sets
+    (/root/reference/src/vllm_tgis_adapter/tgis_utils/structured_outputs.py:14-38): exactly one of them."""
+
+    json: str | dict | None = None
+    regex: str | None = None
+    choice: list[str] | None = None
+    grammar: str | None = None
+    json_object: bool | None = None
+
+    def __post_init__(self) -> None:
+        count = sum(v is not None and v is not False for v in
+                    (self.json, self.regex, self.choice, self.grammar, self.json_object))
+        if count > 1:
+            raise ValueError("You can only use one kind of structured outputs constraint "
+                             f"but multiple are specified: {dataclasses.asdict(self)}")
+        if count < 1:
+            raise ValueError("You must use one kind of structured outputs constraint "
+                             f"but none are specified: {dataclasses.asdict(self)}")
+
+
+@dataclasses.dataclass
 class SamplingParams:
     """Field names follow vllm/sampling_params.py; normalisation rules follow :398-440."""
 
@@ -36,6 +58,7 @@ class SamplingParams:
     length_penalty: tuple[int, float] | None = None
     eos_token_id: int | None = None
     stop_token_ids: list[int] = dataclasses.field(default_factory=list)
+    structured_outputs: StructuredOutputsParams | None = None   # grpc_server.py:580-586
 
     def __post_init__(self) -> None:
         if self.temperature < 0.0:

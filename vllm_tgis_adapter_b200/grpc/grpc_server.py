@@ -7,7 +7,10 @@ lines whose behaviour it reproduces.  Differences, all deliberate and documented
   * `max_tokens` is computed per request instead of mutating the shared SamplingParams (:792-797; SURVEY §3.2 note);
   * the two per-request logits processors (:560-578) travel as data (typical_p / length_penalty) into the fused
     sampling kernel instead of Python callables;
-  * adapters (:234) and guided decoding (:582-587) are rejected with INVALID_ARGUMENT.
+  * guided decoding (:580-586, tgis_utils/structured_outputs.py:14-38): the `guided` oneof becomes a
+    StructuredOutputsParams; the engine façade compiles it (engine/guided.py) and the sampling kernel applies the
+    per-step token bitmask;
+  * adapters (:234) are rejected with INVALID_ARGUMENT.
 """
 from __future__ import annotations
 
@@ -24,7 +27,7 @@ from typing import Any
 import grpc
 from grpc import StatusCode, aio
 
-from ..engine.types import RequestOutput, RequestOutputKind, SamplingParams, TokensPrompt
+from ..engine.types import RequestOutput, RequestOutputKind, SamplingParams, StructuredOutputsParams, TokensPrompt
 from ..tgis_utils import logs
 from . import health as _health
 from . import reflection
@@ -38,6 +41,25 @@ logger = logging.getLogger("vllm_tgis_adapter.grpc")
 
 ADD_SPECIAL_TOKENS: bool = os.getenv("ADD_SPECIAL_TOKENS", "true").lower() not in ("0", "false")  # :88-91
 CORRELATION_ID_HEADER = "x-correlation-id"  # :92
+
+
+def _structured_output_params(decoding) -> StructuredOutputsParams | None:
+    """tgis_utils/structured_outputs.py:14-38 as a table: which member of the `guided` oneof is set -> the one
+    StructuredOutputsParams field it fills.  Error cases as there: fewer than two choices; `format` other than JSON."""
+    which = decoding.WhichOneof("guided")
+    if not which:
+        return None
+    if which == "choice":
+        options = list(decoding.choice.choices)
+        if len(options) < 2:
+            raise ValueError("Must provide at least two choices")
+        return StructuredOutputsParams(choice=options)
+    if which == "format":
+        if decoding.format != pb2.DecodingParameters.JSON:
+            raise ValueError(which)
+        return StructuredOutputsParams(json_object=True)
+    field = {"json_schema": "json", "regex": "regex", "grammar": "grammar"}[which]
+    return StructuredOutputsParams(**{field: getattr(decoding, which)})
 
 
 def with_default(value, default):  # :95-96
@@ -276,7 +298,8 @@ class TextGenerationService:
             if greedy and resp_options.token_logprobs:
                 logprobs -= 1
         logprobs = with_default(logprobs, None)
-        if decoding.WhichOneof("guided") is not None:                                           # :582-587 (out of scope)
+        structured_outputs = _structured_output_params(decoding)                                # :580-586
+        if structured_outputs is not None and not getattr(self.engine, "supports_guided_decoding", False):
             await context.abort(StatusCode.INVALID_ARGUMENT, TGISValidationError.GuidedUnsupported.value)
         typical_p = sampling.typical_p if (not greedy and 0.0 < sampling.typical_p < 1.0) else 0.0   # :562-565
         length_penalty = ((decoding.length_penalty.start_index, decoding.length_penalty.decay_factor)
@@ -301,7 +324,7 @@ class TextGenerationService:
                 if stopping.HasField("include_stop_sequence") else self.default_include_stop_seqs,
                 skip_special_tokens=self.skip_special_tokens,
                 typical_p=typical_p, length_penalty=length_penalty,
-                eos_token_id=getattr(tokenizer, "eos_token_id", None), **rnd)
+                eos_token_id=getattr(tokenizer, "eos_token_id", None), structured_outputs=structured_outputs, **rnd)
         except ValueError as e:
             await context.abort(StatusCode.INVALID_ARGUMENT, str(e))
         return sampling_params, deadline
