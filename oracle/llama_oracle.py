@@ -123,6 +123,20 @@ class SeqState:
         self.n = 0
 
 
+LORA_MODULES = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+
+
+def lora_add(y: torch.Tensor, x: torch.Tensor, a: torch.Tensor, b_scaled: torch.Tensor) -> torch.Tensor:
+    """y + LoRA delta of x with the rounding points of vLLM's punica path (vllm/lora/punica_wrapper/punica_gpu.py
+    add_lora_linear; reference semantics in vllm/lora/ops/torch_ops/lora_ops.py bgmv_shrink / bgmv_expand, which
+    tests/golden/lora_torch_ops.json pins): shrink x . A^T accumulates into an fp32 buffer; the buffer is cast to the model
+    dtype; expand buffer . B^T is rounded to the model dtype; the sum y + delta is a model-dtype add.  `b_scaled` already
+    carries alpha / r (vllm/lora/lora_weights.py `optimize` folds it into lora_b in the model dtype at load time)."""
+    buf = x.float() @ a.float().t()
+    delta = (buf.to(y.dtype).float() @ b_scaled.float().t()).to(y.dtype)
+    return y + delta
+
+
 class LlamaOracle:
     """Flat-batch Llama forward with the model-dtype rounding points of the vLLM/HF path.
 
@@ -185,10 +199,25 @@ class LlamaOracle:
 
     # -- one engine step over a flat batch ----------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, work: list[tuple[SeqState, list[int]]], want_all_logits: bool = False) -> torch.Tensor:
+    def step(self, work: list[tuple[SeqState, list[int]]], want_all_logits: bool = False,
+             lora: list[dict | None] | None = None) -> torch.Tensor:
         """Append `tokens` to each sequence and return the fp32 view of the model-dtype logits of each sequence's
-        last new token ([n_seqs, vocab]); with want_all_logits, of every new token ([T, vocab])."""
+        last new token ([n_seqs, vocab]); with want_all_logits, of every new token ([T, vocab]).
+        lora: per work item None or an adapter {(layer, module): (A [r, in], B_scaled [out, r])} with module in
+        LORA_MODULES (vLLM applies the adapter of each token's request: vllm/lora/layers/base_linear.py `apply`)."""
         cfg = self.cfg
+        spans, o0 = [], 0
+        for i, (_, ts) in enumerate(work):
+            spans.append((o0, o0 + len(ts), lora[i] if lora is not None else None))
+            o0 += len(ts)
+
+        def adapt(y: torch.Tensor, x: torch.Tensor, li: int, module: str, c0: int = 0, c1: int | None = None) -> None:
+            for s0, s1, ad in spans:
+                if ad is not None and (li, module) in ad:
+                    a, b = ad[(li, module)]
+                    a, b = a.to(device=self.device, dtype=self.dtype), b.to(device=self.device, dtype=self.dtype)
+                    y[s0:s1, c0:c1] = lora_add(y[s0:s1, c0:c1], x[s0:s1], a, b)
+
         toks = torch.tensor([t for _, ts in work for t in ts], dtype=torch.long, device=self.device)
         pos = torch.tensor([st.n + j for st, ts in work for j in range(len(ts))], dtype=torch.long, device=self.device)
         resid = self.embed[toks]
@@ -201,6 +230,9 @@ class LlamaOracle:
                 resid = x + resid
                 xn = self._rms(resid, L["ln1"])
             qkv = F.linear(xn, L["qkv"])
+            adapt(qkv, xn, li, "q_proj", 0, cfg.q_dim)
+            adapt(qkv, xn, li, "k_proj", cfg.q_dim, cfg.q_dim + cfg.kv_dim)
+            adapt(qkv, xn, li, "v_proj", cfg.q_dim + cfg.kv_dim, None)
             q = qkv[:, : cfg.q_dim].reshape(T, cfg.n_q_heads, cfg.head_dim)
             k = qkv[:, cfg.q_dim: cfg.q_dim + cfg.kv_dim].reshape(T, cfg.n_kv_heads, cfg.head_dim)
             v = qkv[:, cfg.q_dim + cfg.kv_dim:].reshape(T, cfg.n_kv_heads, cfg.head_dim)
@@ -216,11 +248,15 @@ class LlamaOracle:
                 off += n
             attn = torch.cat(outs, dim=0).reshape(T, cfg.q_dim)
             x = F.linear(attn, L["o"])
+            adapt(x, attn, li, "o_proj")
             resid = x + resid
             xn = self._rms(resid, L["ln2"])
             gu = F.linear(xn, L["gu"])
+            adapt(gu, xn, li, "gate_proj", 0, cfg.ffn)
+            adapt(gu, xn, li, "up_proj", cfg.ffn, None)
             act = F.silu(gu[:, : cfg.ffn]) * gu[:, cfg.ffn:]
             x = F.linear(act, L["d"])
+            adapt(x, act, li, "down_proj")
         resid = x + resid
         xn = self._rms(resid, self.norm)
         for st, ts in work:

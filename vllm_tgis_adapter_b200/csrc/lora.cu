@@ -1,0 +1,197 @@
+// Multi-adapter LoRA on the token stream of one engine step: y[t] += B_s (A_s x[t]) with s = the adapter slot of token t.
+//
+// Reference seam: /root/reference/src/vllm_tgis_adapter/grpc/adapters.py:63-163 turns a request's adapter_id into a
+// `lora_request=LoRARequest(...)` kwarg of engine.generate (grpc_server.py:205-225); the arithmetic is vLLM's:
+//   vllm/lora/layers/base_linear.py `apply`            y = base_layer(x); punica.add_lora_linear(y, x, A, B, scale=1.0)
+//   vllm/lora/punica_wrapper/punica_gpu.py             buffer = zeros(fp32); add_shrink(buffer, x, A, scale);
+//                                                      add_expand(y, buffer, B, add_inputs=True)
+//   vllm/lora/ops/triton_ops/lora_shrink_op.py         fp32 accumulation of x . A^T, stored to the fp32 buffer
+//   vllm/lora/ops/triton_ops/lora_expand_op.py         buffer cast to the weight dtype (bf16), fp32 accumulation of
+//                                                      buffer . B^T, result cast to bf16, then y = y + result (bf16 add)
+//   vllm/lora/lora_weights.py `optimize`               the alpha/r scaling is folded into B once at load time (host side)
+// Rounding points restated here exactly: fp32 shrink sums -> bf16 -> fp32 expand sums -> bf16 delta -> bf16(y + delta).
+//
+// Shape of the problem: HBM/L2-bound skinny products (rank 8..64 against K, N of 1k..14k), integer slot look-ups per
+// token; no tensor-core shape worth having.  Two kernels per adapted projection group:
+//   shrink : CTA = (tile of 8 tokens, 8 rank rows of one module), one warp per rank row; an A row is streamed once per
+//            tile with 16-byte loads and used for all 8 tokens when they share the adapter (prefill chunks and
+//            same-adapter decode batches); mixed tiles fall back to one row stream per token.
+//   expand : thread = (token, 8 consecutive output columns); B rows of 8 adjacent columns are one contiguous run, so a
+//            warp reads 32 consecutive runs -- fully coalesced; the token's rank vector is staged once per CTA.
+// Adapter storage (engine.cu): per layer and module  A [slots][Rm][K] and B [slots][N][Rm] bf16, zero padded to the module's
+// rank capacity Rm, so no kernel needs the adapter's true rank.  gate_proj / up_proj are stored as ONE module of capacity
+// 2R over the interleaved gate_up projection (row 2j = gate_j, row 2j+1 = up_j: block-sparse B), see engine.cu.
+#include "kernels.h"
+#include "launch.cuh"
+#include "ptx.cuh"
+
+namespace tgis {
+
+namespace {
+
+struct alignas(16) BF8L {
+  __nv_bfloat16 v[8];
+};
+
+__device__ __forceinline__ float dot8(const BF8L& a, const BF8L& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s = fmaf(__bfloat162float(a.v[e]), __bfloat162float(b.v[e]), s);
+  return s;
+}
+
+constexpr int LORA_TT = 8;  // tokens per shrink tile
+
+__global__ void __launch_bounds__(256)
+lora_shrink_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* __restrict__ tok_slot, LoraGroup g,
+                   float* __restrict__ v, int T) {
+  griddep_launch();
+  griddep_wait();
+  // blockIdx.y enumerates (module, chunk of 8 rank rows)
+  int m = 0, chunk = (int)blockIdx.y;
+  while (m + 1 < g.n_mods && chunk >= g.mod[m].Rm / 8) {
+    chunk -= g.mod[m].Rm / 8;
+    ++m;
+  }
+  const LoraModule md = g.mod[m];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = chunk * 8 + warp;
+  const int t0 = (int)blockIdx.x * LORA_TT;
+  int slot[LORA_TT];
+  bool any = false, uniform = true;
+#pragma unroll
+  for (int j = 0; j < LORA_TT; ++j) {
+    slot[j] = (t0 + j < T) ? tok_slot[t0 + j] : 0;
+    any |= slot[j] > 0;
+    uniform &= (t0 + j >= T) || slot[j] == slot[0];
+  }
+  if (!any) return;
+  float acc[LORA_TT];
+#pragma unroll
+  for (int j = 0; j < LORA_TT; ++j) acc[j] = 0.f;
+  const int nvec = md.K / 8;
+  if (uniform) {
+    const BF8L* arow = reinterpret_cast<const BF8L*>(md.A + ((size_t)(slot[0] - 1) * md.Rm + r) * md.K);
+    for (int kv = lane; kv < nvec; kv += 32) {
+      const BF8L a = arow[kv];
+#pragma unroll
+      for (int j = 0; j < LORA_TT; ++j)
+        if (t0 + j < T) acc[j] += dot8(a, reinterpret_cast<const BF8L*>(x + (size_t)(t0 + j) * ldx)[kv]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < LORA_TT; ++j) {
+      if (slot[j] <= 0) continue;
+      const BF8L* arow = reinterpret_cast<const BF8L*>(md.A + ((size_t)(slot[j] - 1) * md.Rm + r) * md.K);
+      const BF8L* xrow = reinterpret_cast<const BF8L*>(x + (size_t)(t0 + j) * ldx);
+      for (int kv = lane; kv < nvec; kv += 32) acc[j] += dot8(arow[kv], xrow[kv]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LORA_TT; ++j) {
+    float s = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && t0 + j < T && slot[j] > 0) v[(size_t)(t0 + j) * g.v_ld + md.v_off + r] = s;
+  }
+}
+
+constexpr int LORA_MAX_RM = 128;
+
+__global__ void __launch_bounds__(256)
+lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_slot, LoraGroup g,
+                   __nv_bfloat16* __restrict__ y, int ldy) {
+  __shared__ float vs[LORA_MAX_RM];
+  griddep_launch();
+  griddep_wait();
+  const int t = (int)blockIdx.y;
+  const LoraModule md = g.mod[blockIdx.z];
+  const int slot = tok_slot[t];
+  if (slot <= 0) return;
+  if ((int)blockIdx.x * 2048 >= md.N) return;
+  // the fp32 shrink sums enter the second product as bf16 (lora_expand_op.py casts the buffer to the weight dtype)
+  if ((int)threadIdx.x < md.Rm) vs[threadIdx.x] = bf16_round(v[(size_t)t * g.v_ld + md.v_off + threadIdx.x]);
+  __syncthreads();
+  const int n0 = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 8;
+  if (n0 >= md.N) return;
+  const __nv_bfloat16* brow = md.B + ((size_t)(slot - 1) * md.N + n0) * md.Rm;
+  __nv_bfloat16* yp = y + (size_t)t * ldy + md.col0 + n0;
+  BF8L yv = *reinterpret_cast<const BF8L*>(yp);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float s = 0.f;
+    const BF8L* b = reinterpret_cast<const BF8L*>(brow + (size_t)e * md.Rm);
+    for (int rv = 0; rv < md.Rm / 8; ++rv) {
+      const BF8L bb = b[rv];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s = fmaf(vs[rv * 8 + q], __bfloat162float(bb.v[q]), s);
+    }
+    yv.v[e] = __float2bfloat16_rn(__bfloat162float(yv.v[e]) + bf16_round(s));
+  }
+  *reinterpret_cast<BF8L*>(yp) = yv;
+}
+
+// gate_up [T, 2F] with interleaved columns (2j = gate_j, 2j+1 = up_j) -> act [T, F]; the rounding points of the GEMM's
+// fused SwiGLU epilogue (gemm_tcgen05.cu swiglu_bf16) and of silu_mul_kernel
+__global__ void silu_mul_interleaved_kernel(const __nv_bfloat16* __restrict__ gate_up, __nv_bfloat16* __restrict__ act,
+                                            int T, int ffn) {
+  griddep_launch();
+  griddep_wait();
+  const int vec_per_row = ffn / 4;  // 4 outputs from one 16-byte load
+  const long long total = (long long)T * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / vec_per_row), c = (int)(i % vec_per_row);
+    const BF8L gu = reinterpret_cast<const BF8L*>(gate_up + (size_t)t * 2 * ffn)[c];
+    __nv_bfloat16 o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gx = __bfloat162float(gu.v[2 * e]), ux = __bfloat162float(gu.v[2 * e + 1]);
+      const float sl = bf16_round(gx / (1.0f + expf(-gx)));
+      o[e] = __float2bfloat16_rn(sl * ux);
+    }
+    *reinterpret_cast<uint2*>(act + (size_t)t * ffn + 4 * c) = *reinterpret_cast<const uint2*>(o);
+  }
+}
+
+}  // namespace
+
+static bool lora_group_ok(const LoraGroup& g) {
+  if (g.n_mods < 1 || g.n_mods > LORA_GROUP_MAX) return false;
+  for (int m = 0; m < g.n_mods; ++m) {
+    const LoraModule& md = g.mod[m];
+    if (md.Rm < 8 || md.Rm > LORA_MAX_RM || md.Rm % 8 != 0 || md.K % 8 != 0 || md.N % 8 != 0 || md.col0 % 8 != 0) return false;
+  }
+  return true;
+}
+
+cudaError_t lora_shrink_launch(const __nv_bfloat16* x, int ldx, const int32_t* tok_slot, const LoraGroup& g, float* v, int T,
+                               cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (!lora_group_ok(g) || ldx % 8 != 0) return cudaErrorInvalidValue;
+  int chunks = 0;
+  for (int m = 0; m < g.n_mods; ++m) chunks += g.mod[m].Rm / 8;
+  return launch_k(lora_shrink_kernel, dim3((T + LORA_TT - 1) / LORA_TT, chunks), dim3(256), 0, stream, x, ldx, tok_slot, g, v,
+                  T);
+}
+
+cudaError_t lora_expand_launch(const float* v, const int32_t* tok_slot, const LoraGroup& g, __nv_bfloat16* y, int ldy, int T,
+                               cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (!lora_group_ok(g) || ldy % 8 != 0) return cudaErrorInvalidValue;
+  int max_n = 0;
+  for (int m = 0; m < g.n_mods; ++m) max_n = g.mod[m].N > max_n ? g.mod[m].N : max_n;
+  return launch_k(lora_expand_kernel, dim3((max_n + 2047) / 2048, T, g.n_mods), dim3(256), 0, stream, v, tok_slot, g, y, ldy);
+}
+
+cudaError_t silu_mul_interleaved_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn,
+                                        cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  if (ffn % 4 != 0) return cudaErrorInvalidValue;
+  const long long total = (long long)T * (ffn / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  return launch_k(silu_mul_interleaved_kernel, dim3((int)blocks), dim3(256), 0, stream, gate_up, act, T, ffn);
+}
+
+}  // namespace tgis

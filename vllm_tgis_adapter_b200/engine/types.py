@@ -131,5 +131,14 @@ class RequestOutput:
 
 
 @dataclasses.dataclass
+class LoRARequest:
+    """vllm/lora/request.py, the members the adapter layer sets (grpc/adapters.py:146-155 via load_lora_adapter)."""
+
+    lora_name: str
+    lora_int_id: int
+    lora_path: str
+
+
+@dataclasses.dataclass
 class TokensPrompt:
     prompt_token_ids: list[int]
