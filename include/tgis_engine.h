@@ -17,6 +17,7 @@
  *                                                   decoding)` (tgis_utils/structured_outputs.py:14-38): the engine asks the
  *                                                   host's grammar matcher for each guided request's allowed-token bitmask
  *                                                   before it samples, and the sampling kernel applies it
+ *   tgis_engine_load_adapter_weight / _clear_adapter <- grpc/adapters.py:139-155 `load_lora_adapter(LoadLoRAAdapterRequest)`
  *   tgis_engine_status                           <- grpc_server.py:117 `engine.errored and not engine.is_running`,
  *                                                   __main__.py:71
  *   tgis_engine_max_model_len                    <- grpc_server.py:196-199 `engine.vllm_config.model_config`
@@ -38,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TGIS_ABI_VERSION 5
+#define TGIS_ABI_VERSION 6
 #define TGIS_MAX_REQUEST_ID 96
 #define TGIS_MAX_TOPN 12 /* reference forces max_logprobs >= 11: tgis_utils/args.py:214-216 */
 #define TGIS_MAX_STOP_TOKEN_IDS 8
@@ -74,6 +75,11 @@ typedef struct tgis_config {
    * the host, e.g. torch.distributed); shm_name names the POSIX shm segment that carries the per-step plan. */
   uint8_t nccl_id[128];
   char shm_name[64];
+  /* LoRA adapters (reference: grpc/adapters.py:63-163 -> lora_request; vLLM --enable-lora / --max-loras / --max-lora-rank):
+   * max_loras > 0 reserves that many adapter slots of rank capacity max_lora_rank (multiple of 8, <= 64) over the seven
+   * projections of every layer.  Single GPU only (tp_size == 1). */
+  int32_t max_loras;
+  int32_t max_lora_rank;
 } tgis_config;
 
 /* What the adapter's proto->SamplingParams mapping (grpc_server.py:508-628) hands to the engine. */
@@ -98,7 +104,7 @@ typedef struct tgis_sampling_params {
   int32_t stop_token_ids[TGIS_MAX_STOP_TOKEN_IDS];
   int32_t guided;             /* DecodingParameters.guided / format set (structured_outputs.py:14-38): every sampled token
                                  is restricted to the bitmask the mask provider returns for this request */
-  int32_t reserved;
+  int32_t lora_slot;          /* 0: base model; s in 1..max_loras: the adapter loaded into slot s (lora_request, :205-225) */
 } tgis_sampling_params;
 
 /* Guided decoding.  The grammar state machine lives with the host (the reference hands a StructuredOutputsParams to vLLM,
@@ -183,6 +189,13 @@ int tgis_engine_start(tgis_engine* e);
 int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_t* prompt_ids, int32_t n_prompt,
                             const tgis_sampling_params* params);
 int tgis_engine_abort(tgis_engine* e, const char* request_id);
+/* LoRA adapter slots.  name: "layers.<i>.<module>.lora_A" ([r, in] bf16) or "...lora_B" ([out, r] bf16, alpha / r already
+ * folded in by the host: vllm lora_weights.py `optimize`), module in q_proj k_proj v_proj o_proj gate_proj up_proj down_proj;
+ * r <= max_lora_rank (the slot is zero padded).  ptr may be host or device memory.  A slot must not be cleared or rewritten
+ * while a queued or running request names it (checked).  tgis_engine_clear_adapter zeroes every tensor of the slot. */
+int tgis_engine_load_adapter_weight(tgis_engine* e, int32_t slot, const char* name, const void* ptr, int64_t rows,
+                                    int64_t cols);
+int tgis_engine_clear_adapter(tgis_engine* e, int32_t slot);
 /* fn == NULL removes the provider; requests with params->guided != 0 are rejected while none is installed */
 int tgis_engine_set_mask_provider(tgis_engine* e, tgis_mask_fn fn, void* user);
 /* Blocks up to timeout_ms for at least one record; returns the number written to out[0..cap) (>= 0) or <0 on error. */

@@ -76,6 +76,13 @@ int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, i
 int tgis_k_sampler_masked(const void* logits_dev, int32_t logits_bf16, int32_t ld, int32_t vocab, const void* rows_host,
                           int32_t n_rows, void* seen_bitmap_dev, const void* allow_bitmap_dev, void* out_host,
                           int32_t iters, float* us_out);
+/* LoRA (csrc/lora.cu; vllm lora/punica_wrapper/punica_gpu.py add_lora_linear): x [T, ldx] bf16, tok_slot [T] int32 (0 = no
+ * adapter, s >= 1 = slot s), A [slots][Rm][K] bf16, B [slots][N][Rm] bf16 (scaling folded in); in place on y [T, ldy] bf16:
+ * y[t, col0 + n] = bf16(y + bf16(B_s[n, :] . bf16(A_s x[t]))) */
+int tgis_k_lora(const void* x_dev, int32_t ldx, const int32_t* tok_slot_dev, const void* a_dev, const void* b_dev, int32_t K,
+                int32_t N, int32_t Rm, int32_t col0, void* y_dev, int32_t ldy, int32_t T);
+/* act[t, j] = bf16(silu(gate_up[t, 2j])) * gate_up[t, 2j + 1] */
+int tgis_k_silu_mul_interleaved(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn);
 const char* tgis_k_last_error(void);
 /* debug builds only (-DTGIS_GEMM_TIMELINE): %globaltimer stamps of CTA 0 and CTA grid/2, [4][16] u64; else -2 */
 int tgis_k_gemm_timeline(uint64_t* out64);

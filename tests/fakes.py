@@ -30,6 +30,12 @@ class FakeNativeEngine:
         self.aborted: list[str] = []
         self.steps = 0
         self._mask_cb = None
+        self.max_loras, self.max_lora_rank = 0, 16   # tests that exercise adapters raise max_loras
+        self.adapter_loads: list[tuple[int, int]] = []
+        self.lora_slots_seen: list[int] = []
+
+    def load_adapter(self, slot, weights) -> None:    # engine.core.NativeEngine.load_adapter
+        self.adapter_loads.append((slot, len(weights)))
 
     def set_mask_provider(self, callback) -> None:   # engine.core.NativeEngine.set_mask_provider
         self._mask_cb = callback
@@ -74,6 +80,7 @@ class FakeNativeEngine:
                     msg = self._in.get_nowait()
                     if msg[0] == "add":
                         _, rid, prompt, sp, ts = msg
+                        self.lora_slots_seen.append(getattr(sp, "lora_slot", 0))
                         self._active[rid] = {"prompt": prompt, "sp": sp, "out": [], "ts": ts, "first": 0.0}
                     else:
                         if msg[1] in self._active:

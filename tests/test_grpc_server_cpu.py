@@ -27,6 +27,7 @@ class Server:
         self.mc = ModelConfig(n_layers=1, hidden=128, n_q_heads=1, n_kv_heads=1, ffn=128, vocab=VOCAB,
                               max_model_len=max_model_len)
         self.fake = FakeNativeEngine(self.mc, script=script)
+        self.fake.max_loras = argkw.pop("max_loras", 0)
         self.tok = build_synthetic_tokenizer(VOCAB)
         self.args = argparse.Namespace(max_new_tokens=64, output_special_tokens=False, default_include_stop_seqs=True,
                                        disable_prompt_logprobs=False, adapter_cache=None, prefix_store_path=None,

@@ -179,3 +179,43 @@ def test_lora_manager_slots_are_pinned_while_in_use_and_recycled_lru(tmp_path):
     assert native.loaded == [(sa, 14), (sb, 14), (sb, 14), (sa, 14)]
     with pytest.raises(LoRAConfigError):
         mgr.register(LoRARequest("big", 9, str(make_peft_dir(tmp_path, "big", r=32))))
+
+
+def test_adapter_id_over_grpc_reaches_the_engine_as_a_pinned_slot(tmp_path, monkeypatch):
+    """Host path on the fake engine: adapter cache flag -> AdapterStore -> validate_adapters -> LoRAManager -> add_request
+    with lora_slot; one weight load for two requests; the slot is released when the request ends."""
+    import grpc
+    from test_grpc_server_cpu import Server, _params
+    from vllm_tgis_adapter_b200.grpc.pb import generation_pb2 as pb
+
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    make_peft_dir(cache, "my-lora", n_layers=1, hidden=128, q_dim=128, kv_dim=128, ffn=128)
+    monkeypatch.chdir(tmp_path)
+    srv = Server(adapter_cache=str(cache), max_loras=2)
+    try:
+        call = srv.channel.unary_unary("/fmaas.GenerationService/Generate",
+                                       request_serializer=pb.BatchedGenerationRequest.SerializeToString,
+                                       response_deserializer=pb.BatchedGenerationResponse.FromString)
+        p = _params(stopping={"max_new_tokens": 3})
+        for _ in range(2):
+            r = call(pb.BatchedGenerationRequest(model_id="m", adapter_id="my-lora",
+                                                 requests=[pb.GenerationRequest(text="t5 t6")], params=p), timeout=30)
+            assert r.responses[0].generated_token_count == 3
+        call(pb.BatchedGenerationRequest(model_id="m", requests=[pb.GenerationRequest(text="t5 t6")], params=p), timeout=30)
+        assert srv.fake.lora_slots_seen == [1, 1, 0]
+        assert srv.fake.adapter_loads == [(1, 7)]
+        assert srv.engine._lora._users == {1: 0}
+        with pytest.raises(grpc.RpcError) as ei:
+            call(pb.BatchedGenerationRequest(model_id="m", adapter_id="nope",
+                                             requests=[pb.GenerationRequest(text="t5")], params=p), timeout=30)
+        assert ei.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+        assert ei.value.details() == "can't retrieve adapter with id 'nope': directory does not exist"
+        # Tokenize validates the adapter id too (grpc_server.py:828)
+        tok = srv.channel.unary_unary("/fmaas.GenerationService/Tokenize",
+                                      request_serializer=pb.BatchedTokenizeRequest.SerializeToString,
+                                      response_deserializer=pb.BatchedTokenizeResponse.FromString)
+        assert tok(pb.BatchedTokenizeRequest(model_id="m", adapter_id="my-lora",
+                                             requests=[pb.TokenizeRequest(text="t5 t6")]), timeout=30).responses[0].token_count == 2
+    finally:
+        srv.close()

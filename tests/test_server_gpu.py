@@ -16,7 +16,7 @@ CFG = "tiny"
 
 
 class LiveServer:
-    def __init__(self, cfg_name=CFG, seed=21, max_new_tokens=64):
+    def __init__(self, cfg_name=CFG, seed=21, max_new_tokens=64, adapter_cache=None, max_loras=0, max_lora_rank=16):
         from oracle.llama_oracle import CONFIGS, rope_table, synthetic_weights
         from vllm_tgis_adapter_b200.engine.async_engine import AsyncTGISEngine
         from vllm_tgis_adapter_b200.engine.core import ModelConfig, NativeEngine
@@ -29,12 +29,13 @@ class LiveServer:
         mc = ModelConfig(n_layers=c.n_layers, hidden=c.hidden, n_q_heads=c.n_q_heads, n_kv_heads=c.n_kv_heads,
                          ffn=c.ffn, vocab=c.vocab, rope_theta=c.rope_theta, rms_eps=c.rms_eps,
                          max_model_len=c.max_model_len)
-        native = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=256, kv_cache_bytes=64 << 20)
+        native = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=256, kv_cache_bytes=64 << 20, max_loras=max_loras,
+                              max_lora_rank=max_lora_rank)
         native.load_weights(self.weights)
         native.load_weight("tgis.rope_cos_sin", rope_table(c))
         self.tok = build_synthetic_tokenizer(c.vocab)
         self.args = argparse.Namespace(max_new_tokens=max_new_tokens, output_special_tokens=False, default_include_stop_seqs=True,
-                                       disable_prompt_logprobs=False, adapter_cache=None, prefix_store_path=None,
+                                       disable_prompt_logprobs=False, adapter_cache=adapter_cache, prefix_store_path=None,
                                        host="127.0.0.1", grpc_port=0, ssl_keyfile=None, ssl_certfile=None,
                                        ssl_ca_certs=None)
         self.loop = asyncio.new_event_loop()

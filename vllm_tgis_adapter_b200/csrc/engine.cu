@@ -14,6 +14,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <deque>
@@ -151,7 +152,8 @@ struct StepHeader {
   int32_t T, n_dec, n_tiles, R, max_dec_kv, S;
   int32_t graphable;     // replay (or capture) the CUDA graph keyed by (S, KV splits, samp_complex) instead of launching
   int32_t samp_complex;  // bit 0: some sampled row needs selection passes (sampling): decides the sampler's cluster
-                         // size; bit 1: some row carries a guided-decoding bitmask (the masked sampler instantiation)
+                         // size; bit 1: some row carries a guided-decoding bitmask (the masked sampler instantiation);
+                         // bit 2: some token carries a LoRA adapter (unfused projections + lora.cu kernels)
   uint64_t copy_bytes;
   int32_t kind;          // 0: engine step; 1: prompt-logprob pass over R rows of the step just executed (T = its tokens,
   int32_t need_norm;     //    need_norm: the final RMSNorm has not run yet)
@@ -246,6 +248,18 @@ struct tgis_engine {
   tgis_mask_fn mask_fn = nullptr;
   void* mask_user = nullptr;
   long long guided_rows = 0;
+  // LoRA adapters (lora.cu): per layer and module  A [slots][Rm][K], B [slots][N][Rm] bf16, zero padded to the rank capacity;
+  // gate_proj / up_proj form ONE module of capacity 2R over the interleaved gate_up projection
+  int max_loras = 0, lora_R = 0;
+  struct LoraLayerW {
+    bf16 *A_q, *B_q, *A_k, *B_k, *A_v, *B_v, *A_o, *B_o, *A_gu, *B_gu, *A_d, *B_d;
+  };
+  DevBuf<bf16> lora_arena;
+  size_t lora_slot_elems = 0;  // (unused by the kernels; bookkeeping for clear)
+  std::vector<LoraLayerW> lora_layers;
+  DevBuf<float> lora_v;   // [T][3R] fp32 shrink sums
+  DevBuf<bf16> gu_buf;    // [T][2F] raw (interleaved) gate_up output of steps that carry adapter tokens
+  long long lora_steps = 0;
   DevBuf<SampleOut> d_samp_out;
   SampleOut* h_samp_out = nullptr;
   SampleOut* h_plp_out = nullptr;  // prompt-logprob pass results (kept apart from the step's sampled rows)
@@ -253,7 +267,7 @@ struct tgis_engine {
   uint8_t* h_stage = nullptr;
   DevBuf<uint8_t> d_stage;
   size_t off_tok = 0, off_pos = 0, off_slotmap = 0, off_tokslot = 0, off_seqs = 0, off_decids = 0, off_tileseq = 0,
-         off_tileq0 = 0, off_samplesrc = 0, off_rows = 0, off_epoch = 0, off_bt = 0, stage_bytes = 0;
+         off_tileq0 = 0, off_samplesrc = 0, off_rows = 0, off_epoch = 0, off_bt = 0, off_toklora = 0, stage_bytes = 0;
 
   // host state
   std::mutex mu;
@@ -464,6 +478,32 @@ struct tgis_engine {
     attn_out.alloc(T_alloc * q_dim);
     tmp.alloc(T_alloc * H);
     act.alloc(T_alloc * F);
+    if (c.max_loras > 0) {
+      max_loras = c.max_loras;
+      lora_R = c.max_lora_rank;
+      const size_t R = lora_R, Sl = max_loras, kvd = (size_t)nkv * HEAD_DIM;
+      const size_t per_layer = Sl * (R * H + q_dim * R + 2 * (R * H + kvd * R) + R * q_dim + H * R + 2 * R * H +
+                                     (size_t)2 * F * 2 * R + R * F + H * R);
+      lora_arena.alloc(per_layer * L);
+      lora_arena.zero();
+      lora_layers.resize(L);
+      bf16* p = lora_arena.p;
+      auto take = [&](size_t n) {
+        bf16* r = p;
+        p += n;
+        return r;
+      };
+      for (auto& ll : lora_layers) {
+        ll.A_q = take(Sl * R * H);      ll.B_q = take(Sl * q_dim * R);
+        ll.A_k = take(Sl * R * H);      ll.B_k = take(Sl * kvd * R);
+        ll.A_v = take(Sl * R * H);      ll.B_v = take(Sl * kvd * R);
+        ll.A_o = take(Sl * R * q_dim);  ll.B_o = take(Sl * H * R);
+        ll.A_gu = take(Sl * 2 * R * H); ll.B_gu = take(Sl * (size_t)2 * F * 2 * R);
+        ll.A_d = take(Sl * R * F);      ll.B_d = take(Sl * H * R);
+      }
+      lora_v.alloc(T_alloc * 3 * R);
+      gu_buf.alloc(T_alloc * (size_t)2 * F);
+    }
     last_hidden.alloc(S_alloc * H);
     logits.alloc((size_t)S_max * V * lsz);
     if (tp > 1) {
@@ -502,6 +542,7 @@ struct tgis_engine {
     off_pos = place(4 * (size_t)T_max);
     off_slotmap = place(4 * (size_t)T_max);
     off_tokslot = place(4 * (size_t)T_max);
+    off_toklora = place(4 * (size_t)T_max);  // adapter slot of every token (0: base model)
     off_seqs = place(sizeof(AttnSeq) * (size_t)S_max);
     off_decids = place(4 * (size_t)S_max);
     off_tileseq = place(4 * (size_t)tiles_max);
@@ -835,6 +876,79 @@ struct tgis_engine {
     return 0;
   }
 
+  // ---- LoRA adapter slots (host threads other than the engine thread call these: legacy-stream copies into tensors no
+  // running step reads -- the host pins a slot while a request names it, engine/lora.py LoRAManager)
+  int lora_slot_check(int32_t slot) const {
+    if (max_loras == 0) return fail("the engine was created without LoRA slots (max_loras = 0)");
+    if (slot < 1 || slot > max_loras) return fail("adapter slot out of range");
+    return 0;
+  }
+  template <class Fn>
+  void lora_for_each(int32_t slot, Fn fn) {
+    const size_t R = lora_R, H = cfg.hidden, F = Fl, kvd = (size_t)nkv * HEAD_DIM, s = (size_t)(slot - 1);
+    for (auto& ll : lora_layers) {
+      fn(ll.A_q + s * R * H, R * H);              fn(ll.B_q + s * q_dim * R, (size_t)q_dim * R);
+      fn(ll.A_k + s * R * H, R * H);              fn(ll.B_k + s * kvd * R, kvd * R);
+      fn(ll.A_v + s * R * H, R * H);              fn(ll.B_v + s * kvd * R, kvd * R);
+      fn(ll.A_o + s * R * q_dim, R * q_dim);      fn(ll.B_o + s * H * R, H * R);
+      fn(ll.A_gu + s * 2 * R * H, 2 * R * H);     fn(ll.B_gu + s * 2 * F * 2 * R, 2 * F * 2 * R);
+      fn(ll.A_d + s * R * F, R * F);              fn(ll.B_d + s * H * R, H * R);
+    }
+  }
+  int clear_adapter(int32_t slot) {
+    if (int rc = lora_slot_check(slot)) return rc;
+    CK(cudaSetDevice(cfg.device));
+    lora_for_each(slot, [&](bf16* p, size_t n) { CK(cudaMemset(p, 0, n * sizeof(bf16))); });
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
+    return 0;
+  }
+  int load_adapter_weight(int32_t slot, const std::string& name, const void* ptr, int64_t rows, int64_t cols) {
+    if (int rc = lora_slot_check(slot)) return rc;
+    if (name.rfind("layers.", 0) != 0) return fail("bad adapter weight name " + name);
+    const size_t dot = name.find('.', 7);
+    if (dot == std::string::npos) return fail("bad adapter weight name " + name);
+    const int li = atoi(name.substr(7, dot - 7).c_str());
+    if (li < 0 || li >= cfg.n_layers) return fail("layer index out of range in " + name);
+    const std::string rest = name.substr(dot + 1);
+    const size_t dot2 = rest.find('.');
+    if (dot2 == std::string::npos) return fail("bad adapter weight name " + name);
+    const std::string mod = rest.substr(0, dot2), which = rest.substr(dot2 + 1);
+    if (which != "lora_A" && which != "lora_B") return fail("bad adapter weight name " + name);
+    const bool isA = which == "lora_A";
+    const int64_t R = lora_R, H = cfg.hidden, F = Fl, kvd = (int64_t)nkv * HEAD_DIM, s = slot - 1;
+    LoraLayerW& ll = lora_layers[li];
+    bf16* dst = nullptr;
+    int64_t fin = 0, fout = 0, cap = R;   // module geometry; cap: rank capacity of the stored tensor (row length of B)
+    int64_t b_row_stride = 0;             // B: destination elements between consecutive source rows
+    if (mod == "q_proj") { fin = H; fout = q_dim; dst = isA ? ll.A_q + s * R * H : ll.B_q + s * q_dim * R; }
+    else if (mod == "k_proj") { fin = H; fout = kvd; dst = isA ? ll.A_k + s * R * H : ll.B_k + s * kvd * R; }
+    else if (mod == "v_proj") { fin = H; fout = kvd; dst = isA ? ll.A_v + s * R * H : ll.B_v + s * kvd * R; }
+    else if (mod == "o_proj") { fin = q_dim; fout = H; dst = isA ? ll.A_o + s * R * q_dim : ll.B_o + s * H * R; }
+    else if (mod == "down_proj") { fin = F; fout = H; dst = isA ? ll.A_d + s * R * F : ll.B_d + s * H * R; }
+    else if (mod == "gate_proj" || mod == "up_proj") {
+      // one module of capacity 2R over the interleaved projection: A rows [0, R) gate / [R, 2R) up; B row 2j = gate_j
+      // (columns [0, R)), row 2j + 1 = up_j (columns [R, 2R))
+      const bool up = mod == "up_proj";
+      fin = H; fout = F; cap = 2 * R;
+      if (isA) dst = ll.A_gu + s * 2 * R * H + (up ? R * H : 0);
+      else { dst = ll.B_gu + s * 2 * F * 2 * R + (up ? 2 * R + R : 0); b_row_stride = 2 * cap; }
+    } else return fail("unsupported LoRA module " + mod);
+    const int64_t r = isA ? rows : cols;
+    if (r < 1 || r > R) return fail("adapter rank " + std::to_string(r) + " exceeds max_lora_rank " + std::to_string(R));
+    if (isA ? cols != fin : rows != fout)
+      return fail("shape mismatch for " + name + ": got " + std::to_string(rows) + "x" + std::to_string(cols));
+    CK(cudaSetDevice(cfg.device));
+    if (isA) {
+      CK(cudaMemcpy(dst, ptr, (size_t)(rows * cols) * sizeof(bf16), cudaMemcpyDefault));
+    } else {
+      if (b_row_stride == 0) b_row_stride = cap;
+      CK(cudaMemcpy2D(dst, (size_t)b_row_stride * sizeof(bf16), ptr, (size_t)cols * sizeof(bf16), (size_t)cols * sizeof(bf16),
+                      (size_t)rows, cudaMemcpyDefault));
+    }
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
+    return 0;
+  }
+
   void finalize_weights() {
     if (!lm_head_loaded)  // tie_word_embeddings
       CK(cudaMemcpy(lm_head, embed + (size_t)rank * Vl * cfg.hidden, (size_t)Vl * cfg.hidden * sizeof(bf16),
@@ -920,11 +1034,22 @@ struct tgis_engine {
     // ... unless the qkv launch reduces its split tiles on chip (cluster mode): then the epilogue is spread over the
     // cluster's CTAs by token and the fusion pays up to 256 tokens (TGIS_FUSE_ROPE_CLUSTER_MAX_T)
     const int qkv_cluster = cfg.debug_gemm_ref ? 0 : gemm_cluster_split(T, qkv_dim, H, num_sms);
-    const bool rope_fused = fuse_rope && !cfg.debug_gemm_ref && gemm_even_split(T, qkv_dim, H, num_sms) >= 2 &&
+    // LoRA steps: the adapter deltas are added to the RAW projections (before RoPE, before SwiGLU, before the residual
+    // add), so the fused epilogues are switched off for the step and the deltas land between the GEMM and its consumer
+    const bool lora = (samp_complex & 4) != 0 && max_loras > 0;
+    const int32_t* d_toklora = ds<int32_t>(off_toklora);
+    const int LR = lora_R, kvd = nkv * HEAD_DIM;
+    auto lora_apply = [&](const LoraGroup& g, const bf16* x, int ldx, bf16* y, int ldy) {
+      CK(lora_shrink_launch(x, ldx, d_toklora, g, lora_v.p, T, stream));
+      CK(lora_expand_launch(lora_v.p, d_toklora, g, y, ldy, T, stream));
+      n_launches += 2;
+    };
+    if (lora) ++lora_steps;
+    const bool rope_fused = !lora && fuse_rope && !cfg.debug_gemm_ref && gemm_even_split(T, qkv_dim, H, num_sms) >= 2 &&
                             T <= (qkv_cluster > 0 ? std::max(rope_fuse_max_t, rope_fuse_cluster_max_t) : rope_fuse_max_t);
     // residual add + RMSNorm inside the GEMMs either side of it (single GPU, small steps, both row-"producers" reduced
     // on chip): o-proj -> [post-attention norm] -> gate_up and down-proj -> [next layer's input norm] -> qkv
-    const bool norm_fused = fuse_norm && tp == 1 && !cfg.debug_gemm_ref && T <= GEMM_NORM_MAX_T && H % 128 == 0 && H / 128 <= GEMM_NORM_MAX_PARTS &&
+    const bool norm_fused = !lora && fuse_norm && tp == 1 && !cfg.debug_gemm_ref && T <= GEMM_NORM_MAX_T && H % 128 == 0 && H / 128 <= GEMM_NORM_MAX_PARTS &&
                             gemm_cluster_split(T, H, q_dim, num_sms) > 0 && gemm_cluster_split(T, H, F, num_sms) > 0;
     const int n_parts = H / 128;
     float* ssq_attn = norm_ssq.p;                                      // written by o-proj, read by gate_up
@@ -952,6 +1077,16 @@ struct tgis_engine {
                           k_cache.p + (size_t)li * kv_layer_elems, v_cache.p + (size_t)li * kv_layer_elems, nq, nkv};
         gemm(qkv_norm_in ? xm_resid : xm_xn, l.m_qkv, xn.p, l.wqkv, qkv.p, T, qkv_dim, H, 0, &l.m_o, T, H, q_dim, 0,
              rope_fused ? &rp : nullptr, qkv_norm_in ? &cons_qkv : nullptr);
+        if (lora) {
+          const LoraLayerW& ll = lora_layers[li];
+          LoraGroup g{};
+          g.n_mods = 3;
+          g.v_ld = 3 * LR;
+          g.mod[0] = LoraModule{ll.A_q, ll.B_q, H, q_dim, LR, 0, 0};
+          g.mod[1] = LoraModule{ll.A_k, ll.B_k, H, kvd, LR, q_dim, LR};
+          g.mod[2] = LoraModule{ll.A_v, ll.B_v, H, kvd, LR, q_dim + kvd, 2 * LR};
+          lora_apply(g, xn.p, H, qkv.p, qkv_dim);
+        }
       }
       bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
       bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
@@ -974,6 +1109,13 @@ struct tgis_engine {
       }
       gemm(xm_attn, l.m_o, attn_out.p, l.wo, ar_fused ? ar_buf(0) : tmp.p, T, H, q_dim, 0, &l.m_gu, T, 2 * F, H, 0, nullptr,
            norm_fused ? &prod_attn : nullptr);
+      if (lora) {
+        LoraGroup g{};
+        g.n_mods = 1;
+        g.v_ld = 3 * LR;
+        g.mod[0] = LoraModule{lora_layers[li].A_o, lora_layers[li].B_o, q_dim, H, LR, 0, 0};
+        lora_apply(g, attn_out.p, q_dim, tmp.p, H);
+      }
       if (norm_fused) {
       } else if (ar_fused) {
         fused_ar_norm(0, l.ln2, T);
@@ -983,6 +1125,17 @@ struct tgis_engine {
         ++n_launches;
       }
       // gate_up GEMM with SwiGLU fused into its epilogue: writes act[T, F] directly (no gate_up round trip)
+      if (lora) {
+        // raw interleaved gate_up -> + adapter deltas (gate and up as one module of capacity 2R) -> SwiGLU
+        gemm(xm_xn, l.m_gu, xn.p, l.wgu, gu_buf.p, T, 2 * F, H, /*out_mode=*/0, &l.m_d, T, H, F, /*ldy=*/2 * F);
+        LoraGroup g{};
+        g.n_mods = 1;
+        g.v_ld = 3 * LR;
+        g.mod[0] = LoraModule{lora_layers[li].A_gu, lora_layers[li].B_gu, H, 2 * F, 2 * LR, 0, 0};
+        lora_apply(g, xn.p, H, gu_buf.p, 2 * F);
+        CK(silu_mul_interleaved_launch(gu_buf.p, act.p, T, F, stream));
+        ++n_launches;
+      } else
       gemm(norm_fused ? xm_resid : xm_xn, l.m_gu, xn.p, l.wgu, act.p, T, 2 * F, H, /*out_mode=*/2, &l.m_d, T, H, F,
            /*ldy=*/F, nullptr, norm_fused ? &cons_gu : nullptr);
       bf16* down_out = ar_fused ? ar_buf(1) : tmp.p;
@@ -990,6 +1143,13 @@ struct tgis_engine {
         gemm(xm_act, l.m_d, act.p, l.wd, down_out, T, H, F, 0, &layers[li + 1].m_qkv, T, qkv_dim, H, 0, nullptr,
              norm_fused ? &prod_mlp : nullptr);
       else gemm(xm_act, l.m_d, act.p, l.wd, down_out, T, H, F, 0, R > 0 ? &m_lm : nullptr, R, Vl, H);
+      if (lora) {
+        LoraGroup g{};
+        g.n_mods = 1;
+        g.v_ld = 3 * LR;
+        g.mod[0] = LoraModule{lora_layers[li].A_d, lora_layers[li].B_d, F, H, LR, 0, 0};
+        lora_apply(g, act.p, F, down_out, H);
+      }
       if (!ar_fused) all_reduce_tmp(T);
     }
     // The last down-proj exchange is run even when no row is sampled this step (R == 0): it is what guarantees that
@@ -1105,7 +1265,7 @@ struct tgis_engine {
       return;
     }
     const int max_splits = (h.max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
-    const uint64_t key = ((uint64_t)(h.samp_complex & 3) << 40) | ((uint64_t)h.S << 16) | (uint64_t)max_splits;
+    const uint64_t key = ((uint64_t)(h.samp_complex & 7) << 40) | ((uint64_t)h.S << 16) | (uint64_t)max_splits;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
       if (graphs.size() >= 64) {
@@ -1157,6 +1317,7 @@ struct tgis_engine {
     int32_t* pos = hs<int32_t>(off_pos);
     int32_t* slotmap = hs<int32_t>(off_slotmap);
     int32_t* tokslot = hs<int32_t>(off_tokslot);
+    int32_t* toklora = hs<int32_t>(off_toklora);
     AttnSeq* seqs = hs<AttnSeq>(off_seqs);
     int32_t* decids = hs<int32_t>(off_decids);
     int32_t* tileseq = hs<int32_t>(off_tileseq);
@@ -1177,7 +1338,9 @@ struct tgis_engine {
         pos[T + j] = p;
         slotmap[T + j] = r.blocks[p / KV_BLOCK] * KV_BLOCK + p % KV_BLOCK;
         tokslot[T + j] = r.slot;
+        toklora[T + j] = r.sp.lora_slot;
       }
+      if (r.sp.lora_slot > 0) samp_complex |= 4;  // step flag: some token carries a LoRA adapter
       if (r.sp.prompt_logprobs > 0 && r.n_computed < r.n_prompt - 1) {
         // prompt logprobs (vllm gpu_model_runner.py:3638): position p predicts prompt token p+1
         for (int j = 0; j < q_len; ++j) {
@@ -1610,6 +1773,7 @@ struct tgis_engine {
 extern "C" {
 
 const char* tgis_last_error(void) { return g_last_error.c_str(); }
+static_assert(offsetof(tgis_sampling_params, lora_slot) == 112, "ctypes mirror: engine/_lib.py TgisSamplingParams");
 static_assert(sizeof(tgis_sampling_params) == 120, "ctypes mirror: engine/_lib.py TgisSamplingParams");
 int tgis_abi_version(void) { return TGIS_ABI_VERSION; }
 
@@ -1627,6 +1791,12 @@ int tgis_engine_create(const tgis_config* cfg, tgis_engine** out) {
   if (cfg->n_kv_heads % tpv || cfg->ffn % (64 * tpv) || cfg->vocab % (8 * tpv))
     return fail("n_kv_heads, ffn/64 and vocab/8 must be divisible by tp_size");
   if (cfg->max_batched_tokens < 16 || cfg->max_num_seqs < 1 || cfg->max_model_len < 2) return fail("bad limits");
+  if (cfg->max_loras < 0 || cfg->max_loras > 64) return fail("max_loras must be in [0, 64]");
+  if (cfg->max_loras > 0) {
+    if (tpv > 1) return fail("LoRA adapters are supported on a single GPU only (tp_size must be 1)");
+    if (cfg->max_lora_rank < 8 || cfg->max_lora_rank > 64 || cfg->max_lora_rank % 8)
+      return fail("max_lora_rank must be a multiple of 8 in [8, 64]");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("no CUDA device: the TGIS engine has no CPU fallback");
@@ -1707,6 +1877,8 @@ int tgis_engine_add_request(tgis_engine* e, const char* request_id, const int32_
   if (params->num_logprobs > TGIS_MAX_TOPN || params->prompt_logprobs > TGIS_MAX_TOPN) return fail("num_logprobs too large");
   for (int i = 0; i < n_prompt; ++i)
     if (prompt_ids[i] < 0 || prompt_ids[i] >= e->cfg.vocab) return fail("prompt token id out of range");
+  if (params->lora_slot < 0 || params->lora_slot > e->max_loras)
+    return fail("lora_slot out of range (the engine was created with max_loras = " + std::to_string(e->max_loras) + ")");
   if (params->guided) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (e->mask_fn == nullptr) return fail("guided decoding requested but no mask provider is installed");
@@ -1734,6 +1906,25 @@ int tgis_engine_abort(tgis_engine* e, const char* request_id) {
   }
   e->cv_in.notify_all();
   return 0;
+}
+
+int tgis_engine_load_adapter_weight(tgis_engine* e, int32_t slot, const char* name, const void* ptr, int64_t rows,
+                                    int64_t cols) {
+  if (!e || !name || !ptr) return fail("null argument");
+  try {
+    return e->load_adapter_weight(slot, name, ptr, rows, cols);
+  } catch (const std::exception& ex) {
+    return fail(ex.what());
+  }
+}
+
+int tgis_engine_clear_adapter(tgis_engine* e, int32_t slot) {
+  if (!e) return fail("null argument");
+  try {
+    return e->clear_adapter(slot);
+  } catch (const std::exception& ex) {
+    return fail(ex.what());
+  }
 }
 
 int tgis_engine_set_mask_provider(tgis_engine* e, tgis_mask_fn fn, void* user) {

@@ -114,6 +114,27 @@ cudaError_t logits_wait_launch(const uint32_t* flags, int tp, const uint32_t* ep
                                cudaStream_t stream);
 // act[t, i] = bf16(silu(gate_up[t, i])) * gate_up[t, F + i]
 cudaError_t silu_mul_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn, cudaStream_t stream);
+// ---- multi-adapter LoRA (lora.cu): y[t, col0 + n] += bf16(B_s[n, :] . bf16(A_s x[t])), s = tok_slot[t] (0 = no adapter)
+struct LoraModule {
+  const __nv_bfloat16* A;  // [slots][Rm][K]  (slot s >= 1 lives at index s - 1), zero padded to Rm rows
+  const __nv_bfloat16* B;  // [slots][N][Rm]  (alpha / r already folded in), zero padded to Rm columns
+  int K, N, Rm;            // Rm: rank capacity of the module (multiple of 8, <= 128)
+  int col0;                // first output column of the module in y (multiple of 8)
+  int v_off;               // offset of the module's rank vector inside a token's row of the shrink buffer
+};
+constexpr int LORA_GROUP_MAX = 3;  // modules that read the same x (q, k, v)
+struct LoraGroup {
+  LoraModule mod[LORA_GROUP_MAX];
+  int n_mods;
+  int v_ld;                // floats per token in the shrink buffer
+};
+cudaError_t lora_shrink_launch(const __nv_bfloat16* x, int ldx, const int32_t* tok_slot, const LoraGroup& g, float* v, int T,
+                               cudaStream_t stream);
+cudaError_t lora_expand_launch(const float* v, const int32_t* tok_slot, const LoraGroup& g, __nv_bfloat16* y, int ldy, int T,
+                               cudaStream_t stream);
+// act[t, j] = bf16(silu(gate_up[t, 2j])) * gate_up[t, 2j + 1]  (the interleaved gate_up layout the fused GEMM epilogue reads)
+cudaError_t silu_mul_interleaved_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn,
+                                        cudaStream_t stream);
 // gather rows: out[r, :] = x[rows[r], :]
 cudaError_t gather_rows_launch(const __nv_bfloat16* x, const int32_t* rows, __nv_bfloat16* out, int R, int hidden,
                                cudaStream_t stream);

@@ -427,6 +427,27 @@ int tgis_k_sampler_ex(const void* logits_dev, int32_t logits_bf16, int32_t ld, i
                                iters, us_out);
 }
 
+// one LoRA module through both kernels: y[t, col0 + n] += B_s[n, :] . (A_s x[t]) for tokens with tok_slot[t] = s >= 1
+int tgis_k_lora(const void* x_dev, int32_t ldx, const int32_t* tok_slot_dev, const void* a_dev, const void* b_dev, int32_t K,
+                int32_t N, int32_t Rm, int32_t col0, void* y_dev, int32_t ldy, int32_t T) {
+  Tmp<float> v;
+  KCK(v.alloc((size_t)T * Rm));
+  LoraGroup g{};
+  g.n_mods = 1;
+  g.v_ld = Rm;
+  g.mod[0] = LoraModule{(const __nv_bfloat16*)a_dev, (const __nv_bfloat16*)b_dev, K, N, Rm, col0, 0};
+  KCK(lora_shrink_launch((const __nv_bfloat16*)x_dev, ldx, tok_slot_dev, g, v.p, T, 0));
+  KCK(lora_expand_launch(v.p, tok_slot_dev, g, (__nv_bfloat16*)y_dev, ldy, T, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tgis_k_silu_mul_interleaved(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn) {
+  KCK(silu_mul_interleaved_launch((const __nv_bfloat16*)gate_up_dev, (__nv_bfloat16*)act_dev, T, ffn, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
 int tgis_k_sampler(const void* logits_dev, int32_t ld, int32_t vocab, const void* rows_host, int32_t n_rows,
                    void* seen_bitmap_dev, void* out_host) {
   return tgis_k_sampler_ex(logits_dev, 0, ld, vocab, rows_host, n_rows, seen_bitmap_dev, out_host, 1, nullptr);

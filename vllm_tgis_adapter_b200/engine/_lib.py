@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_REQUEST_ID = 96
 MAX_TOPN = 12
 MAX_STOP_TOKEN_IDS = 8
@@ -27,6 +27,7 @@ class TgisConfig(C.Structure):
         ("gpu_mem_fraction", C.c_float), ("device", C.c_int32), ("tp_size", C.c_int32), ("tp_rank", C.c_int32),
         ("use_cuda_graphs", C.c_int32), ("debug_gemm_ref", C.c_int32), ("seed", C.c_uint64),
         ("nccl_id", C.c_uint8 * 128), ("shm_name", C.c_char * 64),
+        ("max_loras", C.c_int32), ("max_lora_rank", C.c_int32),
     ]
 
 
@@ -38,7 +39,7 @@ class TgisSamplingParams(C.Structure):
         ("min_tokens", C.c_int32), ("max_tokens", C.c_int32), ("num_logprobs", C.c_int32),
         ("prompt_logprobs", C.c_int32), ("has_seed", C.c_int32), ("seed", C.c_uint64),
         ("n_stop_token_ids", C.c_int32), ("stop_token_ids", C.c_int32 * MAX_STOP_TOKEN_IDS),
-        ("guided", C.c_int32), ("reserved", C.c_int32),
+        ("guided", C.c_int32), ("lora_slot", C.c_int32),
     ]
 
 
@@ -68,13 +69,13 @@ class TgisStatus(C.Structure):
 # Every symbol include/tgis_engine.h and include/tgis_kernels.h declare (tests/test_abi_cpu.py checks the export list)
 ENGINE_SYMBOLS = [
     "tgis_last_error", "tgis_abi_version", "tgis_engine_create", "tgis_engine_load_weight", "tgis_engine_start",
-    "tgis_engine_add_request", "tgis_engine_abort", "tgis_engine_set_mask_provider", "tgis_engine_poll", "tgis_engine_status",
+    "tgis_engine_add_request", "tgis_engine_abort", "tgis_engine_set_mask_provider", "tgis_engine_load_adapter_weight", "tgis_engine_clear_adapter", "tgis_engine_poll", "tgis_engine_status",
     "tgis_engine_max_model_len", "tgis_engine_set_profiling", "tgis_nccl_unique_id", "tgis_engine_worker_run", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
 ]
 KERNEL_SYMBOLS = [
     "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_step_timeline_enable", "tgis_k_step_timeline_read", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_gemm_norm_chain", "tgis_k_attention",
     "tgis_k_attention_bench", "tgis_k_decode_items", "tgis_k_gemm_plan", "tgis_k_gemm_unit_rows",
-    "tgis_k_sampler", "tgis_k_sampler_ex", "tgis_k_sampler_masked", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
+    "tgis_k_sampler", "tgis_k_sampler_ex", "tgis_k_sampler_masked", "tgis_k_lora", "tgis_k_silu_mul_interleaved", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
 ]
 
 _LIB: C.CDLL | None = None
@@ -112,6 +113,8 @@ def load_library() -> C.CDLL:
     lib.tgis_engine_add_request.argtypes = [vp, C.c_char_p, C.POINTER(i32), i32, C.POINTER(TgisSamplingParams)]
     lib.tgis_engine_abort.argtypes = [vp, C.c_char_p]
     lib.tgis_engine_set_mask_provider.argtypes = [vp, vp, vp]
+    lib.tgis_engine_load_adapter_weight.argtypes = [vp, i32, C.c_char_p, vp, i64, i64]
+    lib.tgis_engine_clear_adapter.argtypes = [vp, i32]
     lib.tgis_engine_poll.argtypes = [vp, C.POINTER(TgisStepOutput), i32, i32]
     lib.tgis_engine_status.argtypes = [vp, C.POINTER(TgisStatus)]
     lib.tgis_engine_max_model_len.argtypes = [vp]
@@ -131,6 +134,8 @@ def load_library() -> C.CDLL:
     lib.tgis_k_attention.argtypes = [vp, vp, vp, C.POINTER(i32), i32, C.POINTER(i32), i32, i32, vp, i32, i32, f32]
     lib.tgis_k_sampler.argtypes = [vp, i32, i32, vp, i32, vp, vp]
     lib.tgis_k_sampler_ex.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp, i32, C.POINTER(f32)]
+    lib.tgis_k_lora.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32]
+    lib.tgis_k_silu_mul_interleaved.argtypes = [vp, vp, i32, i32]
     lib.tgis_k_sampler_masked.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp, vp, i32, C.POINTER(f32)]
     _LIB = lib
     return lib

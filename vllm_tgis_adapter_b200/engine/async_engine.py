@@ -60,6 +60,15 @@ class AsyncTGISEngine:
         self._dead_error: str | None = None
         self.metrics = EngineMetrics()
         self._mask_provider = None   # guided decoding: created with the first guided request (imports xgrammar)
+        # LoRA: adapter name -> engine slot; `lora_requests` is what grpc/adapters.py consults (the reference asks
+        # vLLM's OpenAIServingModels.lora_requests, adapters.py:157-172)
+        self._lora = None
+        max_loras = getattr(engine, "max_loras", 0)
+        if max_loras > 0:
+            from .lora import LoRAManager
+
+            self._lora = LoRAManager(engine, n_layers=model_config.n_layers, max_loras=max_loras,
+                                     max_rank=getattr(engine, "max_lora_rank", 16))
 
     # -- lifecycle ------------------------------------------------------------------------------------------------
     def start(self, loop: asyncio.AbstractEventLoop | None = None) -> None:
@@ -119,6 +128,21 @@ class AsyncTGISEngine:
     def supports_guided_decoding(self) -> bool:
         return True
 
+    @property
+    def lora_requests(self) -> dict:
+        return self._lora.lora_requests if self._lora is not None else {}
+
+    async def load_lora_adapter(self, *, lora_name: str, lora_path: str, lora_int_id: int) -> None:
+        """vLLM `OpenAIServingModels.load_lora_adapter` as adapters.py:139-155 uses it: validate the checkpoint and
+        remember the LoRARequest; a bad adapter is a ValueError.  The weights move into an engine slot when the first
+        request that names the adapter is scheduled (LoRAManager.acquire)."""
+        from .types import LoRARequest
+
+        if self._lora is None:
+            raise ValueError("LoRA is not enabled: start the server with --enable-lora")
+        req = LoRARequest(lora_name=lora_name, lora_int_id=lora_int_id, lora_path=lora_path)
+        await asyncio.get_running_loop().run_in_executor(None, self._lora.register, req)
+
     def _guided(self):
         if self._mask_provider is None:
             from .guided import GrammarCompiler, MaskProvider
@@ -146,8 +170,9 @@ class AsyncTGISEngine:
                        ) -> AsyncGenerator[RequestOutput, None]:
         if self._dead_error is not None:
             raise EngineDeadError(self._dead_error)
-        if lora_request is not None:
-            raise ValueError("LoRA adapters are not supported by this engine")
+        lora_slot = 0
+        if lora_request is not None and self._lora is None:
+            raise ValueError("LoRA is not enabled: start the server with --enable-lora")
         prompt_ids = list(prompt["prompt_token_ids"] if isinstance(prompt, dict) else prompt.prompt_token_ids)
         sp = sampling_params
         eos = sp.eos_token_id if sp.eos_token_id is not None else getattr(self.tokenizer, "eos_token_id", None)
@@ -175,6 +200,9 @@ class AsyncTGISEngine:
         try:
             if sp.structured_outputs is not None:   # compile before the request exists: a bad spec is a ValueError
                 self._guided().register(nid, sp.structured_outputs)
+            if lora_request is not None:   # pins the adapter's slot (loading the weights if it has none) until `finally`
+                lora_slot = await asyncio.get_running_loop().run_in_executor(None, self._lora.acquire, lora_request)
+                native.lora_slot = lora_slot
             self.engine.add_request(nid, prompt_ids, native)
             sent_tokens = 0
             while True:
@@ -265,6 +293,8 @@ class AsyncTGISEngine:
                 st.done = True
             if self._mask_provider is not None:
                 self._mask_provider.unregister(nid)
+            if lora_slot:
+                self._lora.release(lora_slot)
             self._states.pop(nid, None)
             if self._states.get(request_id) is st:
                 del self._states[request_id]

@@ -64,7 +64,8 @@ def make_sampling_params(*, greedy: bool = True, temperature: float = 1.0, top_k
                          typical_p: float = 0.0, repetition_penalty: float = 1.0,
                          length_penalty: tuple[int, float] | None = None, eos_token_id: int = 2, min_tokens: int = 0,
                          max_tokens: int = 16, num_logprobs: int = 0, prompt_logprobs: int = 0, seed: int | None = None,
-                         stop_token_ids: Iterable[int] = (), guided: bool = False) -> TgisSamplingParams:
+                         stop_token_ids: Iterable[int] = (), guided: bool = False,
+                         lora_slot: int = 0) -> TgisSamplingParams:
     sp = TgisSamplingParams()
     sp.greedy = 1 if greedy else 0
     sp.temperature = float(temperature)
@@ -88,6 +89,7 @@ def make_sampling_params(*, greedy: bool = True, temperature: float = 1.0, top_k
     for i, t in enumerate(ids):
         sp.stop_token_ids[i] = int(t)
     sp.guided = 1 if guided else 0
+    sp.lora_slot = int(lora_slot)
     return sp
 
 
@@ -97,7 +99,7 @@ class NativeEngine:
     def __init__(self, model: ModelConfig, *, max_num_seqs: int = 64, max_batched_tokens: int = 2048,
                  kv_cache_bytes: int = 0, gpu_mem_fraction: float = 0.85, device: int = 0, seed: int = 0,
                  debug_gemm_ref: bool = False, use_cuda_graphs: bool | None = None, tp_size: int = 1, tp_rank: int = 0,
-                 nccl_id: bytes | None = None, shm_name: str = ""):
+                 nccl_id: bytes | None = None, shm_name: str = "", max_loras: int = 0, max_lora_rank: int = 16):
         self.lib = _lib.load_library()
         self.model = model
         if use_cuda_graphs is None:   # default on; TGIS_CUDA_GRAPHS=0 turns decode-step graph replay off
@@ -120,6 +122,8 @@ class NativeEngine:
             C.memmove(cfg.nccl_id, nccl_id, 128)
             cfg.shm_name = shm_name.encode()
         cfg.use_cuda_graphs, cfg.debug_gemm_ref, cfg.seed = int(use_cuda_graphs), 1 if debug_gemm_ref else 0, seed
+        cfg.max_loras, cfg.max_lora_rank = int(max_loras), int(max_lora_rank) if max_loras else 0
+        self.max_loras, self.max_lora_rank = int(max_loras), int(max_lora_rank)
         self._h = C.c_void_p()
         if self.lib.tgis_engine_create(C.byref(cfg), C.byref(self._h)) != 0:
             raise EngineError(f"tgis_engine_create failed: {_lib.last_error(self.lib)}")
@@ -155,6 +159,21 @@ class NativeEngine:
 
     def abort(self, request_id: str) -> None:
         self.lib.tgis_engine_abort(self._h, request_id.encode())
+
+    def load_adapter(self, slot: int, weights: dict) -> None:
+        """weights: {(layer, module): (A [r, in] bf16, B_scaled [out, r] bf16)} as engine/lora.py `read_adapter` returns
+        them.  The slot is zeroed first (modules the adapter does not target contribute nothing)."""
+        import torch
+
+        if self.lib.tgis_engine_clear_adapter(self._h, slot) != 0:
+            raise EngineError(f"clear_adapter({slot}) failed: {_lib.last_error(self.lib)}")
+        for (layer, module), (a, b) in weights.items():
+            for which, t in (("lora_A", a), ("lora_B", b)):
+                t = t.detach().to(torch.bfloat16).contiguous()
+                name = f"layers.{layer}.{module}.{which}".encode()
+                if self.lib.tgis_engine_load_adapter_weight(self._h, slot, name, C.c_void_p(t.data_ptr()), t.shape[0],
+                                                            t.shape[1]) != 0:
+                    raise EngineError(f"load_adapter_weight({name.decode()}) failed: {_lib.last_error(self.lib)}")
 
     def set_mask_provider(self, callback) -> None:
         """callback: a `guided.MASK_FN` C function pointer (the caller keeps it alive), or None to remove it."""

@@ -108,7 +108,9 @@ def _resolve_model(args):
 
 def _make_native_engine(args, mc: ModelConfig, path, device: int, **tp_kw) -> NativeEngine:
     eng = NativeEngine(mc, max_num_seqs=args.max_num_seqs, max_batched_tokens=args.max_num_batched_tokens,
-                       gpu_mem_fraction=args.gpu_memory_utilization, device=device, seed=args.seed, **tp_kw)
+                       gpu_mem_fraction=args.gpu_memory_utilization, device=device, seed=args.seed,
+                       max_loras=args.max_loras if getattr(args, "enable_lora", False) else 0,
+                       max_lora_rank=getattr(args, "max_lora_rank", 16), **tp_kw)
     if path is not None:
         load_safetensors_dir(eng, path)      # full tensors: a tensor-parallel engine keeps its rank's shard
     else:

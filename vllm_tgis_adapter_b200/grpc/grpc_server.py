@@ -10,7 +10,8 @@ lines whose behaviour it reproduces.  Differences, all deliberate and documented
   * guided decoding (:580-586, tgis_utils/structured_outputs.py:14-38): the `guided` oneof becomes a
     StructuredOutputsParams; the engine façade compiles it (engine/guided.py) and the sampling kernel applies the
     per-step token bitmask;
-  * adapters (:234) are rejected with INVALID_ARGUMENT.
+  * LoRA adapters (:234, grpc/adapters.py): the adapter's weights live in an engine slot and lora.cu applies them per token;
+    other PEFT types are rejected with the reference's error string.
 """
 from __future__ import annotations
 
@@ -35,6 +36,7 @@ from .health import HealthServicer, SERVING, add_health_servicer
 from .pb import generation_pb2 as pb2
 from .pb.generation_pb2 import (BatchedGenerationResponse, BatchedTokenizeResponse, DecodingMethod,
                                 GenerationResponse, ModelInfoResponse, StopReason, TokenInfo, TokenizeResponse)
+from .adapters import AdapterStore, validate_adapters
 from .validation import TGISValidationError, validate_input, validate_params
 
 logger = logging.getLogger("vllm_tgis_adapter.grpc")
@@ -140,8 +142,8 @@ class TextGenerationService:
         self.skip_special_tokens = not args.output_special_tokens           # :182
         self.default_include_stop_seqs = args.default_include_stop_seqs     # :183
         self.disable_prompt_logprobs = args.disable_prompt_logprobs         # :184
-        self.adapter_store_configured = bool(getattr(args, "adapter_cache", None)
-                                             or getattr(args, "prefix_store_path", None))
+        adapter_cache_path = getattr(args, "adapter_cache", None) or getattr(args, "prefix_store_path", None)  # :187-192
+        self.adapter_store = AdapterStore(cache_path=adapter_cache_path, adapters={}) if adapter_cache_path else None
         self.health_servicer = health_servicer
 
     async def post_init(self) -> None:  # :195-203
@@ -155,7 +157,7 @@ class TextGenerationService:
     @log_rpc_handler_errors
     async def Generate(self, request, context) -> BatchedGenerationResponse:  # noqa: N802  (:227-312)
         request_id = self.request_id(context)
-        await self._validate_adapters(request, context)
+        adapter_kwargs = await self._validate_adapters(request, context)
         tokenizer = await self.engine.get_tokenizer()
         sampling_params, deadline = await self._validate_and_convert_params(request.params, tokenizer, context)
         sampling_params.output_kind = RequestOutputKind.FINAL_ONLY
@@ -171,7 +173,7 @@ class TextGenerationService:
             request_id_i = f"{request_id}-{i}"
             logs.set_correlation_id(request_id_i, headers.get(CORRELATION_ID_HEADER))
             generators.append(logs.logged_generate(self._make_generator, prompt=req.text, prompt_token_ids=input_ids,
-                                                   sampling_params=sp_i, request_id=request_id_i))
+                                                   sampling_params=sp_i, request_id=request_id_i, **adapter_kwargs))
         resp_options = request.params.response
         responses: list = [None] * request_count
         time_limit_reached = False
@@ -197,7 +199,7 @@ class TextGenerationService:
     @log_rpc_handler_errors
     async def GenerateStream(self, request, context) -> AsyncIterator[GenerationResponse]:  # noqa: N802 (:314-428)
         request_id = self.request_id(context)
-        await self._validate_adapters(request, context)
+        adapter_kwargs = await self._validate_adapters(request, context)
         tokenizer = await self.engine.get_tokenizer()
         sampling_params, deadline = await self._validate_and_convert_params(request.params, tokenizer, context)
         sampling_params.output_kind = RequestOutputKind.DELTA
@@ -209,7 +211,7 @@ class TextGenerationService:
             logs.set_correlation_id(request_id, headers.get(CORRELATION_ID_HEADER))
         result_generator = logs.logged_generate(self._make_generator, prompt=request.request.text,
                                                 prompt_token_ids=input_ids, sampling_params=sampling_params,
-                                                request_id=request_id)
+                                                request_id=request_id, **adapter_kwargs)
         resp_options = request.params.response
         first_response = None
         last_response = None
@@ -329,13 +331,14 @@ class TextGenerationService:
             await context.abort(StatusCode.INVALID_ARGUMENT, str(e))
         return sampling_params, deadline
 
-    async def _validate_adapters(self, request, context) -> None:
-        """adapters.py:63-90 reduced to its no-store behaviour: an adapter_id/prefix_id is an INVALID_ARGUMENT."""
-        adapter_id = request.adapter_id if request.HasField("adapter_id") else None
-        if adapter_id is None and request.HasField("prefix_id"):
-            adapter_id = request.prefix_id
-        if adapter_id:
-            await context.abort(StatusCode.INVALID_ARGUMENT, TGISValidationError.AdaptersDisabled.value)
+    async def _validate_adapters(self, request, context) -> dict[str, Any]:
+        """:630-646 -- adapter_id -> the `lora_request` kwarg of engine.generate; every ValueError of the adapter layer
+        (no store, unknown id, bad id, unsupported type, unloadable checkpoint) is an INVALID_ARGUMENT."""
+        try:
+            return await validate_adapters(request, self.adapter_store, self.engine)
+        except ValueError as e:
+            await context.abort(StatusCode.INVALID_ARGUMENT, str(e))
+        return {}
 
     @staticmethod
     def _convert_reason(output, *, max_is_token_limit: bool, time_limit_reached: bool, tokenizer):  # :662-699

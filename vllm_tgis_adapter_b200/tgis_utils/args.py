@@ -94,6 +94,10 @@ def make_engine_arg_parser() -> argparse.ArgumentParser:
     p.add_argument("--synthetic-weights", action="store_true",
                    help="seeded N(0,0.02) weights for --model <preset> (no checkpoint needed)")
     p.add_argument("--device", type=int, default=0)
+    # vLLM's LoRA flags (the reference's adapter store needs --enable-lora on the engine side: adapters.py:139-155)
+    p.add_argument("--enable-lora", action="store_true")
+    p.add_argument("--max-loras", type=int, default=4, help="adapter slots resident on the GPU")
+    p.add_argument("--max-lora-rank", type=int, default=16, help="rank capacity of a slot (multiple of 8, <= 64)")
     return p
 
 
