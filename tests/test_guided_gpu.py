@@ -76,7 +76,7 @@ def test_sampler_greedy_under_mask_matches_oracle(g, V, n, dtype):
             got = out["topn_lps"][i][j]
             assert (np.isinf(want) and np.isinf(got)) or abs(got - want) < 1e-3, (i, j, got, want)
             if np.isfinite(want) and out["topn_ids"][i][j] != o["topn_ids"][j]:
-                assert abs(got - want) < 1e-6   # tie
+                assert abs(got - want) < 1e-5   # tie between equal bf16 logits (fp32 noise of the two log-sum-exps)
 
 
 @pytest.mark.parametrize("V,dtype", [(2048, torch.float32), (128256, torch.bfloat16)])
@@ -194,10 +194,12 @@ def test_engine_guided_greedy_matches_oracle_and_language():
         StructuredOutputsParams(regex=r"(t1\d){6}"),
         StructuredOutputsParams(choice=["t10t11t12", "t13", "t14t15"]),
         StructuredOutputsParams(grammar='root ::= "t10" ("t11" | "t12")+ "t13"'),
-        StructuredOutputsParams(regex=r"(t1\d\d){3}(t2\d\d)*t999"),
+        StructuredOutputsParams(regex=r"(t1\d){3}(t2\d)*t13"),
         None,                                              # an unguided request rides in the same batch
-        StructuredOutputsParams(regex=r"(t[1-9]\d\d)+"),   # 900 allowed tokens + EOS after the first
+        StructuredOutputsParams(regex=r"(t[12]\d)+"),       # 20 allowed tokens, + EOS after the first
     ]
+    # (every pattern is dead-end free on the synthetic vocabulary: no allowed token is a proper prefix of a longer
+    # alternative that only a non-existent bare-digit token could complete -- "t1" / "t2" are not tokens, "t10" is)
     prompts = [rng.randint(3, cfg.vocab, size=n).tolist() for n in (5, 40, 17, 70, 9, 33)]
     n_new = 12
     for i, (p, spec) in enumerate(zip(prompts, specs)):
@@ -216,8 +218,8 @@ def test_engine_guided_greedy_matches_oracle_and_language():
     st = eng.status()
     eng.close()
     assert st.errored == 0
-    assert prov.calls >= sum(len(r) for i, r in enumerate(res) if specs[i] is not None)
-    lang = [r"(t1\d){6}", r"t10t11t12|t13|t14t15", r"t10(t11|t12)+t13", r"(t1\d\d){3}(t2\d\d)*t999", None, r"(t[1-9]\d\d)+"]
+    assert prov.calls >= sum(1 for i, r in enumerate(res) if specs[i] is not None for o in r if o.new_token is not None)
+    lang = [r"(t1\d){6}", r"t10t11t12|t13|t14t15", r"t10(t11|t12)+t13", r"(t1\d){3}(t2\d)*t13", None, r"(t[12]\d)+"]
     checked = 0
     for i, (p, spec, recs) in enumerate(zip(prompts, specs, res)):
         toks = [r.new_token for r in recs if r.new_token is not None]
@@ -263,7 +265,7 @@ def test_engine_guided_survives_preemption_and_provider_failure():
     rng = np.random.RandomState(9)
     n_new = 40
     for i in range(6):
-        prov.register(f"r{i}", StructuredOutputsParams(regex=r"(t[1-9]\d\d)+"))
+        prov.register(f"r{i}", StructuredOutputsParams(regex=r"(t[12]\d)+"))
         eng.add_request(f"r{i}", rng.randint(3, cfg.vocab, size=120).tolist(),
                         make_sampling_params(greedy=True, max_tokens=n_new, min_tokens=n_new, eos_token_id=2, guided=True))
     eng.add_request("r6", [5, 6, 7], make_sampling_params(greedy=True, max_tokens=4, eos_token_id=2, guided=True))
@@ -281,7 +283,7 @@ def test_engine_guided_survives_preemption_and_provider_failure():
     for i in range(6):
         toks = [r.new_token for r in res[f"r{i}"] if r.new_token is not None]
         assert prov.error_of(f"r{i}") is None
-        assert len(toks) == n_new and all(100 <= t <= 999 for t in toks), toks
+        assert len(toks) == n_new and all(10 <= t <= 29 for t in toks), toks
         assert res[f"r{i}"][-1].finish_reason == 1
     assert res["r6"][-1].finish_reason == 4   # ABORT: nobody registered a grammar for it
 
