@@ -81,6 +81,10 @@ int tgis_k_sampler_masked(const void* logits_dev, int32_t logits_bf16, int32_t l
  * y[t, col0 + n] = bf16(y + bf16(B_s[n, :] . bf16(A_s x[t]))) */
 int tgis_k_lora(const void* x_dev, int32_t ldx, const int32_t* tok_slot_dev, const void* a_dev, const void* b_dev, int32_t K,
                 int32_t N, int32_t Rm, int32_t col0, void* y_dev, int32_t ldy, int32_t T);
+/* same kernels, col0 = 0, timed: iters launches of each, average device microseconds per launch */
+int tgis_k_lora_bench(const void* x_dev, int32_t ldx, const int32_t* tok_slot_dev, const void* a_dev, const void* b_dev,
+                      int32_t K, int32_t N, int32_t Rm, void* y_dev, int32_t ldy, int32_t T, int32_t iters,
+                      float* us_shrink, float* us_expand);
 /* act[t, j] = bf16(silu(gate_up[t, 2j])) * gate_up[t, 2j + 1] */
 int tgis_k_silu_mul_interleaved(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn);
 const char* tgis_k_last_error(void);

@@ -16,8 +16,9 @@
 //   shrink : CTA = (tile of 8 tokens, 8 rank rows of one module), one warp per rank row; an A row is streamed once per
 //            tile with 16-byte loads and used for all 8 tokens when they share the adapter (prefill chunks and
 //            same-adapter decode batches); mixed tiles fall back to one row stream per token.
-//   expand : thread = (token, 8 consecutive output columns); B rows of 8 adjacent columns are one contiguous run, so a
-//            warp reads 32 consecutive runs -- fully coalesced; the token's rank vector is staged once per CTA.
+//   expand : CTA = (tile of 8 tokens, 2048 output columns), thread = 8 consecutive columns; the 8 B rows of a thread are
+//            one contiguous run (a warp reads 32 consecutive runs -- fully coalesced) and are read ONCE for the 8 tokens of
+//            a same-adapter tile; the tile's rank vectors are staged in shared memory (broadcast reads).
 // Adapter storage (engine.cu): per layer and module  A [slots][Rm][K] and B [slots][N][Rm] bf16, zero padded to the module's
 // rank capacity Rm, so no kernel needs the adapter's true rank.  gate_proj / up_proj are stored as ONE module of capacity
 // 2R over the interleaved gate_up projection (row 2j = gate_j, row 2j+1 = up_j: block-sparse B), see engine.cu.
@@ -100,35 +101,83 @@ constexpr int LORA_MAX_RM = 128;
 
 __global__ void __launch_bounds__(256)
 lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_slot, LoraGroup g,
-                   __nv_bfloat16* __restrict__ y, int ldy) {
-  __shared__ float vs[LORA_MAX_RM];
+                   __nv_bfloat16* __restrict__ y, int ldy, int T) {
+  __shared__ float vs[LORA_TT][LORA_MAX_RM];
   griddep_launch();
   griddep_wait();
-  const int t = (int)blockIdx.y;
+  const int t0 = (int)blockIdx.y * LORA_TT;
   const LoraModule md = g.mod[blockIdx.z];
-  const int slot = tok_slot[t];
-  if (slot <= 0) return;
   if ((int)blockIdx.x * 2048 >= md.N) return;
+  int slot0 = 0;
+  bool any = false, uniform = true;
+#pragma unroll
+  for (int j = 0; j < LORA_TT; ++j) {
+    const int sj = (t0 + j < T) ? tok_slot[t0 + j] : 0;
+    if (j == 0) slot0 = sj;
+    any |= sj > 0;
+    uniform &= (t0 + j >= T) || sj == slot0;
+  }
+  if (!any) return;
   // the fp32 shrink sums enter the second product as bf16 (lora_expand_op.py casts the buffer to the weight dtype)
-  if ((int)threadIdx.x < md.Rm) vs[threadIdx.x] = bf16_round(v[(size_t)t * g.v_ld + md.v_off + threadIdx.x]);
+  for (int i = threadIdx.x; i < LORA_TT * md.Rm; i += 256) {
+    const int j = i / md.Rm, r = i - j * md.Rm;
+    const bool live = t0 + j < T && tok_slot[t0 + j] > 0;
+    vs[j][r] = live ? bf16_round(v[(size_t)(t0 + j) * g.v_ld + md.v_off + r]) : 0.f;
+  }
   __syncthreads();
   const int n0 = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 8;
   if (n0 >= md.N) return;
-  const __nv_bfloat16* brow = md.B + ((size_t)(slot - 1) * md.N + n0) * md.Rm;
-  __nv_bfloat16* yp = y + (size_t)t * ldy + md.col0 + n0;
-  BF8L yv = *reinterpret_cast<const BF8L*>(yp);
+  if (uniform) {
+    // one pass over the 8 B rows of this thread serves the whole token tile (a prefill chunk, a same-adapter decode batch)
+    const __nv_bfloat16* brow = md.B + ((size_t)(slot0 - 1) * md.N + n0) * md.Rm;
+    float acc[LORA_TT][8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    float s = 0.f;
-    const BF8L* b = reinterpret_cast<const BF8L*>(brow + (size_t)e * md.Rm);
-    for (int rv = 0; rv < md.Rm / 8; ++rv) {
-      const BF8L bb = b[rv];
+    for (int j = 0; j < LORA_TT; ++j)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s = fmaf(vs[rv * 8 + q], __bfloat162float(bb.v[q]), s);
+      for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const BF8L* b = reinterpret_cast<const BF8L*>(brow + (size_t)e * md.Rm);
+      for (int rv = 0; rv < md.Rm / 8; ++rv) {
+        const BF8L bb = b[rv];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float bf = __bfloat162float(bb.v[q]);
+#pragma unroll
+          for (int j = 0; j < LORA_TT; ++j) acc[j][e] = fmaf(vs[j][rv * 8 + q], bf, acc[j][e]);
+        }
+      }
     }
-    yv.v[e] = __float2bfloat16_rn(__bfloat162float(yv.v[e]) + bf16_round(s));
+#pragma unroll
+    for (int j = 0; j < LORA_TT; ++j) {
+      if (t0 + j >= T) break;
+      __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
+      BF8L yv = *reinterpret_cast<const BF8L*>(yp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv.v[e] = __float2bfloat16_rn(__bfloat162float(yv.v[e]) + bf16_round(acc[j][e]));
+      *reinterpret_cast<BF8L*>(yp) = yv;
+    }
+  } else {
+    for (int j = 0; j < LORA_TT && t0 + j < T; ++j) {
+      const int sj = tok_slot[t0 + j];
+      if (sj <= 0) continue;
+      const __nv_bfloat16* brow = md.B + ((size_t)(sj - 1) * md.N + n0) * md.Rm;
+      __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
+      BF8L yv = *reinterpret_cast<const BF8L*>(yp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float s = 0.f;
+        const BF8L* b = reinterpret_cast<const BF8L*>(brow + (size_t)e * md.Rm);
+        for (int rv = 0; rv < md.Rm / 8; ++rv) {
+          const BF8L bb = b[rv];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s = fmaf(vs[j][rv * 8 + q], __bfloat162float(bb.v[q]), s);
+        }
+        yv.v[e] = __float2bfloat16_rn(__bfloat162float(yv.v[e]) + bf16_round(s));
+      }
+      *reinterpret_cast<BF8L*>(yp) = yv;
+    }
   }
-  *reinterpret_cast<BF8L*>(yp) = yv;
 }
 
 // gate_up [T, 2F] with interleaved columns (2j = gate_j, 2j+1 = up_j) -> act [T, F]; the rounding points of the GEMM's
@@ -181,7 +230,8 @@ cudaError_t lora_expand_launch(const float* v, const int32_t* tok_slot, const Lo
   if (!lora_group_ok(g) || ldy % 8 != 0) return cudaErrorInvalidValue;
   int max_n = 0;
   for (int m = 0; m < g.n_mods; ++m) max_n = g.mod[m].N > max_n ? g.mod[m].N : max_n;
-  return launch_k(lora_expand_kernel, dim3((max_n + 2047) / 2048, T, g.n_mods), dim3(256), 0, stream, v, tok_slot, g, y, ldy);
+  return launch_k(lora_expand_kernel, dim3((max_n + 2047) / 2048, (T + LORA_TT - 1) / LORA_TT, g.n_mods), dim3(256), 0, stream,
+                  v, tok_slot, g, y, ldy, T);
 }
 
 cudaError_t silu_mul_interleaved_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn,

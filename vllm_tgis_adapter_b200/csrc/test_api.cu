@@ -442,6 +442,40 @@ int tgis_k_lora(const void* x_dev, int32_t ldx, const int32_t* tok_slot_dev, con
   return 0;
 }
 
+// timing variant: `iters` back-to-back launches of each kernel on the default stream, CUDA events around each group
+int tgis_k_lora_bench(const void* x_dev, int32_t ldx, const int32_t* tok_slot_dev, const void* a_dev, const void* b_dev,
+                      int32_t K, int32_t N, int32_t Rm, void* y_dev, int32_t ldy, int32_t T, int32_t iters,
+                      float* us_shrink, float* us_expand) {
+  Tmp<float> v;
+  KCK(v.alloc((size_t)T * Rm));
+  LoraGroup g{};
+  g.n_mods = 1;
+  g.v_ld = Rm;
+  g.mod[0] = LoraModule{(const __nv_bfloat16*)a_dev, (const __nv_bfloat16*)b_dev, K, N, Rm, 0, 0};
+  cudaEvent_t e0, e1, e2;
+  KCK(cudaEventCreate(&e0));
+  KCK(cudaEventCreate(&e1));
+  KCK(cudaEventCreate(&e2));
+  if (iters < 1) iters = 1;
+  KCK(lora_shrink_launch((const __nv_bfloat16*)x_dev, ldx, tok_slot_dev, g, v.p, T, 0));
+  KCK(lora_expand_launch(v.p, tok_slot_dev, g, (__nv_bfloat16*)y_dev, ldy, T, 0));
+  KCK(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) KCK(lora_shrink_launch((const __nv_bfloat16*)x_dev, ldx, tok_slot_dev, g, v.p, T, 0));
+  KCK(cudaEventRecord(e1, 0));
+  for (int i = 0; i < iters; ++i) KCK(lora_expand_launch(v.p, tok_slot_dev, g, (__nv_bfloat16*)y_dev, ldy, T, 0));
+  KCK(cudaEventRecord(e2, 0));
+  KCK(cudaDeviceSynchronize());
+  float ms = 0.f;
+  KCK(cudaEventElapsedTime(&ms, e0, e1));
+  if (us_shrink) *us_shrink = 1e3f * ms / (float)iters;
+  KCK(cudaEventElapsedTime(&ms, e1, e2));
+  if (us_expand) *us_expand = 1e3f * ms / (float)iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  return 0;
+}
+
 int tgis_k_silu_mul_interleaved(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn) {
   KCK(silu_mul_interleaved_launch((const __nv_bfloat16*)gate_up_dev, (__nv_bfloat16*)act_dev, T, ffn, 0));
   KCK(cudaDeviceSynchronize());
