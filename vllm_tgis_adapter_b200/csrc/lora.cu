@@ -30,14 +30,36 @@ namespace tgis {
 
 namespace {
 
-struct alignas(16) BF8L {
-  __nv_bfloat16 v[8];
+// 8 consecutive bf16 values as fp32 through ONE 16-byte load (an aggregate of eight __nv_bfloat16 read element-wise compiles
+// to eight 2-byte loads: the first version of these kernels ran 10x slower for exactly that reason, profiles/r02_ncu_lora.csv)
+struct F8 {
+  float v[8];
 };
-
-__device__ __forceinline__ float dot8(const BF8L& a, const BF8L& b) {
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    o.v[2 * e] = __uint_as_float(w[e] << 16);
+    o.v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+  return o;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& f) {  // round to nearest even, one 16-byte store
+  uint4 r;
+  uint32_t* w = &r.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * e], f.v[2 * e + 1]);
+    w[e] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = r;
+}
+__device__ __forceinline__ float dot8(const F8& a, const F8& b) {
   float s = 0.f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) s = fmaf(__bfloat162float(a.v[e]), __bfloat162float(b.v[e]), s);
+  for (int e = 0; e < 8; ++e) s = fmaf(a.v[e], b.v[e], s);
   return s;
 }
 
@@ -72,20 +94,24 @@ lora_shrink_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* 
   for (int j = 0; j < LORA_TT; ++j) acc[j] = 0.f;
   const int nvec = md.K / 8;
   if (uniform) {
-    const BF8L* arow = reinterpret_cast<const BF8L*>(md.A + ((size_t)(slot[0] - 1) * md.Rm + r) * md.K);
+    const __nv_bfloat16* arow = md.A + ((size_t)(slot[0] - 1) * md.Rm + r) * md.K;
+    const int nt = min(LORA_TT, T - t0);
     for (int kv = lane; kv < nvec; kv += 32) {
-      const BF8L a = arow[kv];
+      const F8 a = ld8(arow + 8 * kv);
+      F8 xv[LORA_TT];
 #pragma unroll
-      for (int j = 0; j < LORA_TT; ++j)
-        if (t0 + j < T) acc[j] += dot8(a, reinterpret_cast<const BF8L*>(x + (size_t)(t0 + j) * ldx)[kv]);
+      for (int j = 0; j < LORA_TT; ++j)  // all loads of the iteration in flight before the first use
+        xv[j] = ld8(x + (size_t)(t0 + (j < nt ? j : 0)) * ldx + 8 * kv);
+#pragma unroll
+      for (int j = 0; j < LORA_TT; ++j) acc[j] += dot8(a, xv[j]);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < LORA_TT; ++j) {
       if (slot[j] <= 0) continue;
-      const BF8L* arow = reinterpret_cast<const BF8L*>(md.A + ((size_t)(slot[j] - 1) * md.Rm + r) * md.K);
-      const BF8L* xrow = reinterpret_cast<const BF8L*>(x + (size_t)(t0 + j) * ldx);
-      for (int kv = lane; kv < nvec; kv += 32) acc[j] += dot8(arow[kv], xrow[kv]);
+      const __nv_bfloat16* arow = md.A + ((size_t)(slot[j] - 1) * md.Rm + r) * md.K;
+      const __nv_bfloat16* xrow = x + (size_t)(t0 + j) * ldx;
+      for (int kv = lane; kv < nvec; kv += 32) acc[j] += dot8(ld8(arow + 8 * kv), ld8(xrow + 8 * kv));
     }
   }
 #pragma unroll
@@ -137,14 +163,13 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
       for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const BF8L* b = reinterpret_cast<const BF8L*>(brow + (size_t)e * md.Rm);
+      const __nv_bfloat16* b = brow + (size_t)e * md.Rm;
       for (int rv = 0; rv < md.Rm / 8; ++rv) {
-        const BF8L bb = b[rv];
+        const F8 bb = ld8(b + 8 * rv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float bf = __bfloat162float(bb.v[q]);
 #pragma unroll
-          for (int j = 0; j < LORA_TT; ++j) acc[j][e] = fmaf(vs[j][rv * 8 + q], bf, acc[j][e]);
+          for (int j = 0; j < LORA_TT; ++j) acc[j][e] = fmaf(vs[j][rv * 8 + q], bb.v[q], acc[j][e]);
         }
       }
     }
@@ -152,10 +177,10 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
     for (int j = 0; j < LORA_TT; ++j) {
       if (t0 + j >= T) break;
       __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
-      BF8L yv = *reinterpret_cast<const BF8L*>(yp);
+      F8 yv = ld8(yp);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yv.v[e] = __float2bfloat16_rn(__bfloat162float(yv.v[e]) + bf16_round(acc[j][e]));
-      *reinterpret_cast<BF8L*>(yp) = yv;
+      for (int e = 0; e < 8; ++e) yv.v[e] += bf16_round(acc[j][e]);
+      st8(yp, yv);
     }
   } else {
     for (int j = 0; j < LORA_TT && t0 + j < T; ++j) {
@@ -163,19 +188,19 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
       if (sj <= 0) continue;
       const __nv_bfloat16* brow = md.B + ((size_t)(sj - 1) * md.N + n0) * md.Rm;
       __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
-      BF8L yv = *reinterpret_cast<const BF8L*>(yp);
+      F8 yv = ld8(yp);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         float s = 0.f;
-        const BF8L* b = reinterpret_cast<const BF8L*>(brow + (size_t)e * md.Rm);
+        const __nv_bfloat16* b = brow + (size_t)e * md.Rm;
         for (int rv = 0; rv < md.Rm / 8; ++rv) {
-          const BF8L bb = b[rv];
+          const F8 bb = ld8(b + 8 * rv);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) s = fmaf(vs[j][rv * 8 + q], __bfloat162float(bb.v[q]), s);
+          for (int q = 0; q < 8; ++q) s = fmaf(vs[j][rv * 8 + q], bb.v[q], s);
         }
-        yv.v[e] = __float2bfloat16_rn(__bfloat162float(yv.v[e]) + bf16_round(s));
+        yv.v[e] += bf16_round(s);
       }
-      *reinterpret_cast<BF8L*>(yp) = yv;
+      st8(yp, yv);
     }
   }
 }
@@ -191,15 +216,21 @@ __global__ void silu_mul_interleaved_kernel(const __nv_bfloat16* __restrict__ ga
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i / vec_per_row), c = (int)(i % vec_per_row);
-    const BF8L gu = reinterpret_cast<const BF8L*>(gate_up + (size_t)t * 2 * ffn)[c];
-    __nv_bfloat16 o[4];
+    const F8 gu = ld8(gate_up + (size_t)t * 2 * ffn + 8 * c);
+    uint2 pk;
+    uint32_t* w = &pk.x;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float gx = __bfloat162float(gu.v[2 * e]), ux = __bfloat162float(gu.v[2 * e + 1]);
-      const float sl = bf16_round(gx / (1.0f + expf(-gx)));
-      o[e] = __float2bfloat16_rn(sl * ux);
+    for (int e = 0; e < 2; ++e) {
+      float o2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float gx = gu.v[4 * e + 2 * h], ux = gu.v[4 * e + 2 * h + 1];
+        o2[h] = bf16_round(gx / (1.0f + expf(-gx))) * ux;
+      }
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(o2[0], o2[1]);
+      w[e] = *reinterpret_cast<const uint32_t*>(&hh);
     }
-    *reinterpret_cast<uint2*>(act + (size_t)t * ffn + 4 * c) = *reinterpret_cast<const uint2*>(o);
+    *reinterpret_cast<uint2*>(act + (size_t)t * ffn + 4 * c) = pk;
   }
 }
 

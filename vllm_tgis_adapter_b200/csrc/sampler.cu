@@ -389,16 +389,20 @@ __device__ uint32_t select_weighted_asc(Cl& c, int lo, int hi, KeyF keyf, WF wf,
       const int i = i0 + threadIdx.x;
       uint32_t w = 0, digit = 0xffffffffu;  // not counted
       if (i < hi) {
-        w = __float2uint_rn(wf(i) * SAMP_FIX);
-        if (w > 0) {
-          const uint32_t k = keyf(i);
-          if (round == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) digit = (k >> shift) & 255;
+        // after the first round only ~1/256 of the entries still carry the selected prefix: test the (cheap) key first
+        // and evaluate the weight (an expf) for those only
+        const uint32_t k = keyf(i);
+        if (round == 0 || (k >> (shift + 8)) == (prefix >> (shift + 8))) {
+          w = __float2uint_rn(wf(i) * SAMP_FIX);
+          if (w > 0) digit = (k >> shift) & 255;
         }
       }
-      const uint32_t grp = __match_any_sync(0xffffffffu, digit);
-      if (digit != 0xffffffffu) {
-        const uint32_t sum = __reduce_add_sync(grp, w);
-        if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&h[digit], sum);
+      if (__any_sync(0xffffffffu, digit != 0xffffffffu)) {  // warp-uniform: most warps of rounds 1..3 have nothing to add
+        const uint32_t grp = __match_any_sync(0xffffffffu, digit);
+        if (digit != 0xffffffffu) {
+          const uint32_t sum = __reduce_add_sync(grp, w);
+          if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&h[digit], sum);
+        }
       }
     }
     radix_round_pick(c, h, hsum, bcast, below, T, strict, /*descending=*/false);
@@ -426,8 +430,10 @@ __device__ uint32_t select_kth_largest(Cl& c, int lo, int hi, KeyF keyf, int k, 
         const uint32_t key = keyf(i);
         if (round == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) digit = (key >> shift) & 255;
       }
-      const uint32_t grp = __match_any_sync(0xffffffffu, digit);
-      if (digit != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&h[digit], (uint32_t)__popc(grp));
+      if (__any_sync(0xffffffffu, digit != 0xffffffffu)) {
+        const uint32_t grp = __match_any_sync(0xffffffffu, digit);
+        if (digit != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&h[digit], (uint32_t)__popc(grp));
+      }
     }
     radix_round_pick(c, h, hsum, bcast, above, (uint32_t)k, false, /*descending=*/true);
     prefix |= bcast[0] << shift;
