@@ -13,7 +13,7 @@
 //
 // Shape of the problem: HBM/L2-bound skinny products (rank 8..64 against K, N of 1k..14k), integer slot look-ups per
 // token; no tensor-core shape worth having.  Two kernels per adapted projection group:
-//   shrink : CTA = (tile of 8 tokens, 8 rank rows of one module), one warp per rank row; an A row is streamed once per
+//   shrink : CTA = (tile of 8 tokens, one rank row of one module), its 8 warps split K; an A row is streamed once per
 //            tile with 16-byte loads and used for all 8 tokens when they share the adapter (prefill chunks and
 //            same-adapter decode batches); mixed tiles fall back to one row stream per token.
 //   expand : CTA = (tile of 8 tokens, 2048 output columns), thread = 8 consecutive columns; the 8 B rows of a thread are
@@ -63,55 +63,83 @@ __device__ __forceinline__ float dot8(const F8& a, const F8& b) {
   return s;
 }
 
-constexpr int LORA_TT = 8;  // tokens per shrink tile
+constexpr int LORA_TT = 8;  // tokens per tile
+constexpr int LORA_MAX_RM = 128;
 
+__device__ __forceinline__ F8 cvt8(const uint4& r) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  F8 o;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    o.v[2 * e] = __uint_as_float(w[e] << 16);
+    o.v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+  return o;
+}
+
+// shrink: CTA = (tile of 8 tokens, ONE rank row of one module); its 8 warps split K (warp w owns the 16-byte vectors
+// w*32 + lane + 256 i), so a decode-shaped launch is 64 .. 200 CTAs of two to seven dependent load rounds each instead of a
+// handful of warps walking a whole row (the first version: 16 .. 56 serial memory latencies per launch).  Two rounds are
+// kept in flight (raw 16-byte vectors, converted at use).  Partial sums meet in shared memory and are added in warp
+// order: deterministic.
 __global__ void __launch_bounds__(256)
 lora_shrink_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* __restrict__ tok_slot, LoraGroup g,
                    float* __restrict__ v, int T) {
+  __shared__ float part[8][LORA_TT];
   griddep_launch();
   griddep_wait();
-  // blockIdx.y enumerates (module, chunk of 8 rank rows)
-  int m = 0, chunk = (int)blockIdx.y;
-  while (m + 1 < g.n_mods && chunk >= g.mod[m].Rm / 8) {
-    chunk -= g.mod[m].Rm / 8;
+  int m = 0, r = (int)blockIdx.y;  // blockIdx.y enumerates (module, rank row)
+  while (m + 1 < g.n_mods && r >= g.mod[m].Rm) {
+    r -= g.mod[m].Rm;
     ++m;
   }
   const LoraModule md = g.mod[m];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = chunk * 8 + warp;
   const int t0 = (int)blockIdx.x * LORA_TT;
-  int slot[LORA_TT];
+  const int nt = min(LORA_TT, T - t0);
+  int slot0 = 0;
   bool any = false, uniform = true;
 #pragma unroll
   for (int j = 0; j < LORA_TT; ++j) {
-    slot[j] = (t0 + j < T) ? tok_slot[t0 + j] : 0;
-    any |= slot[j] > 0;
-    uniform &= (t0 + j >= T) || slot[j] == slot[0];
+    const int sj = (j < nt) ? tok_slot[t0 + j] : 0;
+    if (j == 0) slot0 = sj;
+    any |= sj > 0;
+    uniform &= (j >= nt) || sj == slot0;
   }
   if (!any) return;
   float acc[LORA_TT];
 #pragma unroll
   for (int j = 0; j < LORA_TT; ++j) acc[j] = 0.f;
   const int nvec = md.K / 8;
+  const uint4* xq = reinterpret_cast<const uint4*>(x);
+  const size_t ldq = (size_t)ldx / 8;
   if (uniform) {
-    const __nv_bfloat16* arow = md.A + ((size_t)(slot[0] - 1) * md.Rm + r) * md.K;
-    const int nt = min(LORA_TT, T - t0);
-    for (int kv = lane; kv < nvec; kv += 32) {
-      const F8 a = ld8(arow + 8 * kv);
-      F8 xv[LORA_TT];
+    const uint4* arow = reinterpret_cast<const uint4*>(md.A + ((size_t)(slot0 - 1) * md.Rm + r) * md.K);
+    for (int kv = warp * 32 + lane; kv < nvec; kv += 512) {
+      const bool two = kv + 256 < nvec;
+      const int kv1 = two ? kv + 256 : kv;
+      uint4 a0 = arow[kv], a1 = arow[kv1], x0[LORA_TT], x1[LORA_TT];
 #pragma unroll
-      for (int j = 0; j < LORA_TT; ++j)  // all loads of the iteration in flight before the first use
-        xv[j] = ld8(x + (size_t)(t0 + (j < nt ? j : 0)) * ldx + 8 * kv);
+      for (int j = 0; j < LORA_TT; ++j) {  // every load of both rounds is issued before the first use
+        const size_t row = (size_t)(t0 + (j < nt ? j : 0)) * ldq;
+        x0[j] = xq[row + kv];
+        x1[j] = xq[row + kv1];
+      }
+      const F8 fa0 = cvt8(a0), fa1 = cvt8(a1);
 #pragma unroll
-      for (int j = 0; j < LORA_TT; ++j) acc[j] += dot8(a, xv[j]);
+      for (int j = 0; j < LORA_TT; ++j) {
+        acc[j] += dot8(fa0, cvt8(x0[j]));
+        if (two) acc[j] += dot8(fa1, cvt8(x1[j]));
+      }
     }
   } else {
 #pragma unroll
     for (int j = 0; j < LORA_TT; ++j) {
-      if (slot[j] <= 0) continue;
-      const __nv_bfloat16* arow = md.A + ((size_t)(slot[j] - 1) * md.Rm + r) * md.K;
-      const __nv_bfloat16* xrow = x + (size_t)(t0 + j) * ldx;
-      for (int kv = lane; kv < nvec; kv += 32) acc[j] += dot8(ld8(arow + 8 * kv), ld8(xrow + 8 * kv));
+      const int sj = (j < nt) ? tok_slot[t0 + j] : 0;
+      if (sj <= 0) continue;
+      const uint4* arow = reinterpret_cast<const uint4*>(md.A + ((size_t)(sj - 1) * md.Rm + r) * md.K);
+      const uint4* xrow = xq + (size_t)(t0 + j) * ldq;
+      for (int kv = warp * 32 + lane; kv < nvec; kv += 256) acc[j] += dot8(cvt8(arow[kv]), cvt8(xrow[kv]));
     }
   }
 #pragma unroll
@@ -119,16 +147,27 @@ lora_shrink_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* 
     float s = acc[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && t0 + j < T && slot[j] > 0) v[(size_t)(t0 + j) * g.v_ld + md.v_off + r] = s;
+    if (lane == 0) part[warp][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < LORA_TT) {
+    const int j = threadIdx.x;
+    if (j < nt && tok_slot[t0 + j] > 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += part[w][j];
+      v[(size_t)(t0 + j) * g.v_ld + md.v_off + r] = s;
+    }
   }
 }
 
-constexpr int LORA_MAX_RM = 128;
-
+// expand: CTA = (tile of 8 tokens, 2048 output columns), thread = 8 consecutive columns.  Same-adapter tile: per 8 rank
+// indices the thread holds its 8 x 8 block of B in registers and, per rank index, the tile's 8 rank values arrive as two
+// broadcast 16-byte shared-memory loads -- 64 FMAs per 2 LDS (the first version paid one LDS per FMA).
 __global__ void __launch_bounds__(256)
 lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_slot, LoraGroup g,
                    __nv_bfloat16* __restrict__ y, int ldy, int T) {
-  __shared__ float vs[LORA_TT][LORA_MAX_RM];
+  __shared__ __align__(16) float vsT[LORA_MAX_RM][LORA_TT];  // [rank index][token of the tile]
   griddep_launch();
   griddep_wait();
   const int t0 = (int)blockIdx.y * LORA_TT;
@@ -148,29 +187,31 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
   for (int i = threadIdx.x; i < LORA_TT * md.Rm; i += 256) {
     const int j = i / md.Rm, r = i - j * md.Rm;
     const bool live = t0 + j < T && tok_slot[t0 + j] > 0;
-    vs[j][r] = live ? bf16_round(v[(size_t)(t0 + j) * g.v_ld + md.v_off + r]) : 0.f;
+    vsT[r][j] = live ? bf16_round(v[(size_t)(t0 + j) * g.v_ld + md.v_off + r]) : 0.f;
   }
   __syncthreads();
   const int n0 = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 8;
   if (n0 >= md.N) return;
   if (uniform) {
-    // one pass over the 8 B rows of this thread serves the whole token tile (a prefill chunk, a same-adapter decode batch)
     const __nv_bfloat16* brow = md.B + ((size_t)(slot0 - 1) * md.N + n0) * md.Rm;
     float acc[LORA_TT][8];
 #pragma unroll
     for (int j = 0; j < LORA_TT; ++j)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+    for (int rv = 0; rv < md.Rm / 8; ++rv) {
+      F8 bb[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const __nv_bfloat16* b = brow + (size_t)e * md.Rm;
-      for (int rv = 0; rv < md.Rm / 8; ++rv) {
-        const F8 bb = ld8(b + 8 * rv);
+      for (int e = 0; e < 8; ++e) bb[e] = ld8(brow + (size_t)e * md.Rm + 8 * rv);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 8; ++q) {
+        const float4 va = *reinterpret_cast<const float4*>(&vsT[rv * 8 + q][0]);
+        const float4 vb = *reinterpret_cast<const float4*>(&vsT[rv * 8 + q][4]);
+        const float vv[LORA_TT] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-          for (int j = 0; j < LORA_TT; ++j) acc[j][e] = fmaf(vs[j][rv * 8 + q], bb.v[q], acc[j][e]);
-        }
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+          for (int j = 0; j < LORA_TT; ++j) acc[j][e] = fmaf(vv[j], bb[e].v[q], acc[j][e]);
       }
     }
 #pragma unroll
@@ -196,7 +237,7 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
         for (int rv = 0; rv < md.Rm / 8; ++rv) {
           const F8 bb = ld8(b + 8 * rv);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) s = fmaf(vs[j][rv * 8 + q], bb.v[q], s);
+          for (int q = 0; q < 8; ++q) s = fmaf(vsT[rv * 8 + q][j], bb.v[q], s);
         }
         yv.v[e] += bf16_round(s);
       }
@@ -249,10 +290,9 @@ cudaError_t lora_shrink_launch(const __nv_bfloat16* x, int ldx, const int32_t* t
                                cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   if (!lora_group_ok(g) || ldx % 8 != 0) return cudaErrorInvalidValue;
-  int chunks = 0;
-  for (int m = 0; m < g.n_mods; ++m) chunks += g.mod[m].Rm / 8;
-  return launch_k(lora_shrink_kernel, dim3((T + LORA_TT - 1) / LORA_TT, chunks), dim3(256), 0, stream, x, ldx, tok_slot, g, v,
-                  T);
+  int rows = 0;
+  for (int m = 0; m < g.n_mods; ++m) rows += g.mod[m].Rm;
+  return launch_k(lora_shrink_kernel, dim3((T + LORA_TT - 1) / LORA_TT, rows), dim3(256), 0, stream, x, ldx, tok_slot, g, v, T);
 }
 
 cudaError_t lora_expand_launch(const float* v, const int32_t* tok_slot, const LoraGroup& g, __nv_bfloat16* y, int ldy, int T,
