@@ -13,10 +13,10 @@
 //
 // Shape of the problem: HBM/L2-bound skinny products (rank 8..64 against K, N of 1k..14k), integer slot look-ups per
 // token; no tensor-core shape worth having.  Two kernels per adapted projection group:
-//   shrink : CTA = (tile of 8 tokens, one rank row of one module), its 8 warps split K; an A row is streamed once per
+//   shrink : CTA = (tile of 8 tokens, 4 rank rows of one module), its 8 warps split K; the A rows are streamed once per
 //            tile with 16-byte loads and used for all 8 tokens when they share the adapter (prefill chunks and
 //            same-adapter decode batches); mixed tiles fall back to one row stream per token.
-//   expand : CTA = (tile of 8 tokens, 2048 output columns), thread = 8 consecutive columns; the 8 B rows of a thread are
+//   expand : CTA = (tile of 8 tokens, 1024 output columns), thread = 4 consecutive columns; the 4 B rows of a thread are
 //            one contiguous run (a warp reads 32 consecutive runs -- fully coalesced) and are read ONCE for the 8 tokens of
 //            a same-adapter tile; the tile's rank vectors are staged in shared memory (broadcast reads).
 // Adapter storage (engine.cu): per layer and module  A [slots][Rm][K] and B [slots][N][Rm] bf16, zero padded to the module's
@@ -46,16 +46,6 @@ __device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
   }
   return o;
 }
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& f) {  // round to nearest even, one 16-byte store
-  uint4 r;
-  uint32_t* w = &r.x;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * e], f.v[2 * e + 1]);
-    w[e] = *reinterpret_cast<const uint32_t*>(&h);
-  }
-  *reinterpret_cast<uint4*>(p) = r;
-}
 __device__ __forceinline__ float dot8(const F8& a, const F8& b) {
   float s = 0.f;
 #pragma unroll
@@ -77,20 +67,21 @@ __device__ __forceinline__ F8 cvt8(const uint4& r) {
   return o;
 }
 
-// shrink: CTA = (tile of 8 tokens, ONE rank row of one module); its 8 warps split K (warp w owns the 16-byte vectors
-// w*32 + lane + 256 i), so a decode-shaped launch is 64 .. 200 CTAs of two to seven dependent load rounds each instead of a
-// handful of warps walking a whole row (the first version: 16 .. 56 serial memory latencies per launch).  Two rounds are
-// kept in flight (raw 16-byte vectors, converted at use).  Partial sums meet in shared memory and are added in warp
-// order: deterministic.
+// shrink: CTA = (tile of 8 tokens, LORA_RPC = 4 rank rows of one module); its 8 warps split K (warp w owns the 16-byte
+// vectors w*32 + lane + 256 i), so a decode-shaped launch is 16 .. 50 CTAs of two to seven dependent load rounds each
+// instead of a handful of warps walking a whole row (the first version: 16 .. 56 serial memory latencies per launch), and
+// the tile's x vectors are loaded once for the four rows (one row per CTA made a prefill chunk L2-bandwidth bound:
+// 16 CTAs re-read the same 64 KB of x).  Partial sums meet in shared memory and are added in warp order: deterministic.
+constexpr int LORA_RPC = 4;
 __global__ void __launch_bounds__(256)
 lora_shrink_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* __restrict__ tok_slot, LoraGroup g,
                    float* __restrict__ v, int T) {
-  __shared__ float part[8][LORA_TT];
+  __shared__ float part[8][LORA_RPC][LORA_TT];
   griddep_launch();
   griddep_wait();
-  int m = 0, r = (int)blockIdx.y;  // blockIdx.y enumerates (module, rank row)
-  while (m + 1 < g.n_mods && r >= g.mod[m].Rm) {
-    r -= g.mod[m].Rm;
+  int m = 0, r0 = (int)blockIdx.y * LORA_RPC;  // blockIdx.y enumerates (module, group of LORA_RPC rank rows)
+  while (m + 1 < g.n_mods && r0 >= g.mod[m].Rm) {
+    r0 -= g.mod[m].Rm;
     ++m;
   }
   const LoraModule md = g.mod[m];
@@ -107,29 +98,27 @@ lora_shrink_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* 
     uniform &= (j >= nt) || sj == slot0;
   }
   if (!any) return;
-  float acc[LORA_TT];
+  float acc[LORA_RPC][LORA_TT];
 #pragma unroll
-  for (int j = 0; j < LORA_TT; ++j) acc[j] = 0.f;
+  for (int q = 0; q < LORA_RPC; ++q)
+#pragma unroll
+    for (int j = 0; j < LORA_TT; ++j) acc[q][j] = 0.f;
   const int nvec = md.K / 8;
   const uint4* xq = reinterpret_cast<const uint4*>(x);
   const size_t ldq = (size_t)ldx / 8;
   if (uniform) {
-    const uint4* arow = reinterpret_cast<const uint4*>(md.A + ((size_t)(slot0 - 1) * md.Rm + r) * md.K);
-    for (int kv = warp * 32 + lane; kv < nvec; kv += 512) {
-      const bool two = kv + 256 < nvec;
-      const int kv1 = two ? kv + 256 : kv;
-      uint4 a0 = arow[kv], a1 = arow[kv1], x0[LORA_TT], x1[LORA_TT];
+    const uint4* a0 = reinterpret_cast<const uint4*>(md.A + ((size_t)(slot0 - 1) * md.Rm + r0) * md.K);
+    for (int kv = warp * 32 + lane; kv < nvec; kv += 256) {
+      uint4 ar[LORA_RPC], xr[LORA_TT];
 #pragma unroll
-      for (int j = 0; j < LORA_TT; ++j) {  // every load of both rounds is issued before the first use
-        const size_t row = (size_t)(t0 + (j < nt ? j : 0)) * ldq;
-        x0[j] = xq[row + kv];
-        x1[j] = xq[row + kv1];
-      }
-      const F8 fa0 = cvt8(a0), fa1 = cvt8(a1);
+      for (int q = 0; q < LORA_RPC; ++q) ar[q] = a0[(size_t)q * nvec + kv];
+#pragma unroll
+      for (int j = 0; j < LORA_TT; ++j) xr[j] = xq[(size_t)(t0 + (j < nt ? j : 0)) * ldq + kv];
 #pragma unroll
       for (int j = 0; j < LORA_TT; ++j) {
-        acc[j] += dot8(fa0, cvt8(x0[j]));
-        if (two) acc[j] += dot8(fa1, cvt8(x1[j]));
+        const F8 xf = cvt8(xr[j]);
+#pragma unroll
+        for (int q = 0; q < LORA_RPC; ++q) acc[q][j] += dot8(cvt8(ar[q]), xf);
       }
     }
   } else {
@@ -137,33 +126,57 @@ lora_shrink_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* 
     for (int j = 0; j < LORA_TT; ++j) {
       const int sj = (j < nt) ? tok_slot[t0 + j] : 0;
       if (sj <= 0) continue;
-      const uint4* arow = reinterpret_cast<const uint4*>(md.A + ((size_t)(sj - 1) * md.Rm + r) * md.K);
+      const uint4* a0 = reinterpret_cast<const uint4*>(md.A + ((size_t)(sj - 1) * md.Rm + r0) * md.K);
       const uint4* xrow = xq + (size_t)(t0 + j) * ldq;
-      for (int kv = warp * 32 + lane; kv < nvec; kv += 256) acc[j] += dot8(cvt8(arow[kv]), cvt8(xrow[kv]));
+      for (int kv = warp * 32 + lane; kv < nvec; kv += 256) {
+        const F8 xf = cvt8(xrow[kv]);
+#pragma unroll
+        for (int q = 0; q < LORA_RPC; ++q) acc[q][j] += dot8(cvt8(a0[(size_t)q * nvec + kv]), xf);
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < LORA_TT; ++j) {
-    float s = acc[j];
+  for (int q = 0; q < LORA_RPC; ++q)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) part[warp][j] = s;
-  }
+    for (int j = 0; j < LORA_TT; ++j) {
+      float s = acc[q][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) part[warp][q][j] = s;
+    }
   __syncthreads();
-  if (threadIdx.x < LORA_TT) {
-    const int j = threadIdx.x;
+  if (threadIdx.x < LORA_RPC * LORA_TT) {
+    const int q = threadIdx.x / LORA_TT, j = threadIdx.x % LORA_TT;
     if (j < nt && tok_slot[t0 + j] > 0) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += part[w][j];
-      v[(size_t)(t0 + j) * g.v_ld + md.v_off + r] = s;
+      for (int w = 0; w < 8; ++w) s += part[w][q][j];
+      v[(size_t)(t0 + j) * g.v_ld + md.v_off + r0 + q] = s;
     }
   }
 }
 
-// expand: CTA = (tile of 8 tokens, 2048 output columns), thread = 8 consecutive columns.  Same-adapter tile: per 8 rank
-// indices the thread holds its 8 x 8 block of B in registers and, per rank index, the tile's 8 rank values arrive as two
-// broadcast 16-byte shared-memory loads -- 64 FMAs per 2 LDS (the first version paid one LDS per FMA).
+// expand: CTA = (tile of 8 tokens, 1024 output columns), thread = LORA_EC = 4 consecutive columns (~100 registers: two
+// CTAs per SM).  Same-adapter tile: per 8 rank indices the thread holds its 4 x 8 block of B in registers -- the next
+// block is already in flight while this one is used -- and, per rank index, the tile's 8 rank values arrive as two
+// broadcast 16-byte shared-memory loads (32 FMAs per 2 LDS; the first version paid one LDS per FMA and one exposed memory
+// latency per block).
+constexpr int LORA_EC = 4;
+constexpr int LORA_ECOLS = 256 * LORA_EC;  // columns per CTA
+__device__ __forceinline__ void ld4f(const __nv_bfloat16* p, float (&o)[4]) {  // 4 bf16 through one 8-byte load
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  o[0] = __uint_as_float(r.x << 16);
+  o[1] = __uint_as_float(r.x & 0xffff0000u);
+  o[2] = __uint_as_float(r.y << 16);
+  o[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ void st4f(__nv_bfloat16* p, const float (&f)[4]) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+  uint2 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&lo);
+  r.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = r;
+}
 __global__ void __launch_bounds__(256)
 lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_slot, LoraGroup g,
                    __nv_bfloat16* __restrict__ y, int ldy, int T) {
@@ -172,7 +185,7 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
   griddep_wait();
   const int t0 = (int)blockIdx.y * LORA_TT;
   const LoraModule md = g.mod[blockIdx.z];
-  if ((int)blockIdx.x * 2048 >= md.N) return;
+  if ((int)blockIdx.x * LORA_ECOLS >= md.N) return;
   int slot0 = 0;
   bool any = false, uniform = true;
 #pragma unroll
@@ -190,26 +203,34 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
     vsT[r][j] = live ? bf16_round(v[(size_t)(t0 + j) * g.v_ld + md.v_off + r]) : 0.f;
   }
   __syncthreads();
-  const int n0 = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 8;
+  const int n0 = ((int)blockIdx.x * 256 + (int)threadIdx.x) * LORA_EC;
   if (n0 >= md.N) return;
   if (uniform) {
     const __nv_bfloat16* brow = md.B + ((size_t)(slot0 - 1) * md.N + n0) * md.Rm;
-    float acc[LORA_TT][8];
+    float acc[LORA_TT][LORA_EC];
 #pragma unroll
     for (int j = 0; j < LORA_TT; ++j)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-    for (int rv = 0; rv < md.Rm / 8; ++rv) {
-      F8 bb[8];
+      for (int e = 0; e < LORA_EC; ++e) acc[j][e] = 0.f;
+    const int nrv = md.Rm / 8;
+    uint4 nxt[LORA_EC];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) bb[e] = ld8(brow + (size_t)e * md.Rm + 8 * rv);
+    for (int e = 0; e < LORA_EC; ++e) nxt[e] = *reinterpret_cast<const uint4*>(brow + (size_t)e * md.Rm);
+    for (int rv = 0; rv < nrv; ++rv) {
+      F8 bb[LORA_EC];
+#pragma unroll
+      for (int e = 0; e < LORA_EC; ++e) bb[e] = cvt8(nxt[e]);
+      if (rv + 1 < nrv) {
+#pragma unroll
+        for (int e = 0; e < LORA_EC; ++e) nxt[e] = *reinterpret_cast<const uint4*>(brow + (size_t)e * md.Rm + 8 * (rv + 1));
+      }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 va = *reinterpret_cast<const float4*>(&vsT[rv * 8 + q][0]);
         const float4 vb = *reinterpret_cast<const float4*>(&vsT[rv * 8 + q][4]);
         const float vv[LORA_TT] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
+        for (int e = 0; e < LORA_EC; ++e)
 #pragma unroll
           for (int j = 0; j < LORA_TT; ++j) acc[j][e] = fmaf(vv[j], bb[e].v[q], acc[j][e]);
       }
@@ -218,10 +239,11 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
     for (int j = 0; j < LORA_TT; ++j) {
       if (t0 + j >= T) break;
       __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
-      F8 yv = ld8(yp);
+      float yv[LORA_EC];
+      ld4f(yp, yv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yv.v[e] += bf16_round(acc[j][e]);
-      st8(yp, yv);
+      for (int e = 0; e < LORA_EC; ++e) yv[e] += bf16_round(acc[j][e]);
+      st4f(yp, yv);
     }
   } else {
     for (int j = 0; j < LORA_TT && t0 + j < T; ++j) {
@@ -229,9 +251,10 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
       if (sj <= 0) continue;
       const __nv_bfloat16* brow = md.B + ((size_t)(sj - 1) * md.N + n0) * md.Rm;
       __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
-      F8 yv = ld8(yp);
+      float yv[LORA_EC];
+      ld4f(yp, yv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < LORA_EC; ++e) {
         float s = 0.f;
         const __nv_bfloat16* b = brow + (size_t)e * md.Rm;
         for (int rv = 0; rv < md.Rm / 8; ++rv) {
@@ -239,9 +262,9 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
 #pragma unroll
           for (int q = 0; q < 8; ++q) s = fmaf(vsT[rv * 8 + q][j], bb.v[q], s);
         }
-        yv.v[e] += bf16_round(s);
+        yv[e] += bf16_round(s);
       }
-      st8(yp, yv);
+      st4f(yp, yv);
     }
   }
 }
@@ -290,9 +313,9 @@ cudaError_t lora_shrink_launch(const __nv_bfloat16* x, int ldx, const int32_t* t
                                cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   if (!lora_group_ok(g) || ldx % 8 != 0) return cudaErrorInvalidValue;
-  int rows = 0;
-  for (int m = 0; m < g.n_mods; ++m) rows += g.mod[m].Rm;
-  return launch_k(lora_shrink_kernel, dim3((T + LORA_TT - 1) / LORA_TT, rows), dim3(256), 0, stream, x, ldx, tok_slot, g, v, T);
+  int groups = 0;
+  for (int m = 0; m < g.n_mods; ++m) groups += g.mod[m].Rm / LORA_RPC;
+  return launch_k(lora_shrink_kernel, dim3((T + LORA_TT - 1) / LORA_TT, groups), dim3(256), 0, stream, x, ldx, tok_slot, g, v, T);
 }
 
 cudaError_t lora_expand_launch(const float* v, const int32_t* tok_slot, const LoraGroup& g, __nv_bfloat16* y, int ldy, int T,
@@ -301,8 +324,8 @@ cudaError_t lora_expand_launch(const float* v, const int32_t* tok_slot, const Lo
   if (!lora_group_ok(g) || ldy % 8 != 0) return cudaErrorInvalidValue;
   int max_n = 0;
   for (int m = 0; m < g.n_mods; ++m) max_n = g.mod[m].N > max_n ? g.mod[m].N : max_n;
-  return launch_k(lora_expand_kernel, dim3((max_n + 2047) / 2048, (T + LORA_TT - 1) / LORA_TT, g.n_mods), dim3(256), 0, stream,
-                  v, tok_slot, g, y, ldy, T);
+  return launch_k(lora_expand_kernel, dim3((max_n + LORA_ECOLS - 1) / LORA_ECOLS, (T + LORA_TT - 1) / LORA_TT, g.n_mods),
+                  dim3(256), 0, stream, v, tok_slot, g, y, ldy, T);
 }
 
 cudaError_t silu_mul_interleaved_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn,
