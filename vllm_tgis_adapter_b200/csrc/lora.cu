@@ -196,6 +196,20 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
     uniform &= (t0 + j >= T) || sj == slot0;
   }
   if (!any) return;
+  const int n0 = ((int)blockIdx.x * 256 + (int)threadIdx.x) * LORA_EC;
+  const bool col_ok = n0 < md.N;
+  // same-adapter tile: the thread's y values and its first block of B do not depend on the rank vectors -- request them
+  // before the staging barrier so that their latency runs under it (a CTA is only a few microseconds of work)
+  uint2 yraw[LORA_TT];
+  uint4 nxt[LORA_EC];
+  const __nv_bfloat16* brow = md.B + ((size_t)(max(slot0, 1) - 1) * md.N + (col_ok ? n0 : 0)) * md.Rm;
+  if (uniform && col_ok) {
+#pragma unroll
+    for (int e = 0; e < LORA_EC; ++e) nxt[e] = *reinterpret_cast<const uint4*>(brow + (size_t)e * md.Rm);
+#pragma unroll
+    for (int j = 0; j < LORA_TT; ++j)
+      yraw[j] = *reinterpret_cast<const uint2*>(y + (size_t)(t0 + (t0 + j < T ? j : 0)) * ldy + md.col0 + n0);
+  }
   // the fp32 shrink sums enter the second product as bf16 (lora_expand_op.py casts the buffer to the weight dtype)
   for (int i = threadIdx.x; i < LORA_TT * md.Rm; i += 256) {
     const int j = i / md.Rm, r = i - j * md.Rm;
@@ -203,19 +217,14 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
     vsT[r][j] = live ? bf16_round(v[(size_t)(t0 + j) * g.v_ld + md.v_off + r]) : 0.f;
   }
   __syncthreads();
-  const int n0 = ((int)blockIdx.x * 256 + (int)threadIdx.x) * LORA_EC;
-  if (n0 >= md.N) return;
+  if (!col_ok) return;
   if (uniform) {
-    const __nv_bfloat16* brow = md.B + ((size_t)(slot0 - 1) * md.N + n0) * md.Rm;
     float acc[LORA_TT][LORA_EC];
 #pragma unroll
     for (int j = 0; j < LORA_TT; ++j)
 #pragma unroll
       for (int e = 0; e < LORA_EC; ++e) acc[j][e] = 0.f;
     const int nrv = md.Rm / 8;
-    uint4 nxt[LORA_EC];
-#pragma unroll
-    for (int e = 0; e < LORA_EC; ++e) nxt[e] = *reinterpret_cast<const uint4*>(brow + (size_t)e * md.Rm);
     for (int rv = 0; rv < nrv; ++rv) {
       F8 bb[LORA_EC];
 #pragma unroll
@@ -239,8 +248,8 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
     for (int j = 0; j < LORA_TT; ++j) {
       if (t0 + j >= T) break;
       __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
-      float yv[LORA_EC];
-      ld4f(yp, yv);
+      float yv[LORA_EC] = {__uint_as_float(yraw[j].x << 16), __uint_as_float(yraw[j].x & 0xffff0000u),
+                           __uint_as_float(yraw[j].y << 16), __uint_as_float(yraw[j].y & 0xffff0000u)};
 #pragma unroll
       for (int e = 0; e < LORA_EC; ++e) yv[e] += bf16_round(acc[j][e]);
       st4f(yp, yv);
@@ -249,14 +258,14 @@ lora_expand_kernel(const float* __restrict__ v, const int32_t* __restrict__ tok_
     for (int j = 0; j < LORA_TT && t0 + j < T; ++j) {
       const int sj = tok_slot[t0 + j];
       if (sj <= 0) continue;
-      const __nv_bfloat16* brow = md.B + ((size_t)(sj - 1) * md.N + n0) * md.Rm;
+      const __nv_bfloat16* brow_j = md.B + ((size_t)(sj - 1) * md.N + n0) * md.Rm;
       __nv_bfloat16* yp = y + (size_t)(t0 + j) * ldy + md.col0 + n0;
       float yv[LORA_EC];
       ld4f(yp, yv);
 #pragma unroll
       for (int e = 0; e < LORA_EC; ++e) {
         float s = 0.f;
-        const __nv_bfloat16* b = brow + (size_t)e * md.Rm;
+        const __nv_bfloat16* b = brow_j + (size_t)e * md.Rm;
         for (int rv = 0; rv < md.Rm / 8; ++rv) {
           const F8 bb = ld8(b + 8 * rv);
 #pragma unroll
