@@ -1,0 +1,85 @@
+"""Pin the OPT oracle (oracle/opt_oracle.py) against transformers' OPTForCausalLM run in this container
+(oracle/gen_opt_golden.py -> tests/golden/opt_hf_{fp32,bf16}.json).  The reference's OPT fixture is facebook/opt-125m
+(/root/reference/tests/conftest.py:83-91); the fixtures carry seeded random weights of that architecture."""
+import dataclasses
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from oracle.opt_oracle import OPT_CONFIGS, OPTOracle, synthetic_opt_weights
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def case_cfg(name):
+    if name == "opt-125m-2l":
+        return dataclasses.replace(OPT_CONFIGS["opt-125m"], n_layers=2)
+    return OPT_CONFIGS[name]
+
+
+def test_opt_oracle_matches_hf_fp32_fixture_prefill_and_cached_decode():
+    g = json.loads((GOLD / "opt_hf_fp32.json").read_text())
+    for c in g["cases"]:
+        cfg = case_cfg(c["config"])
+        ora = OPTOracle(cfg, synthetic_opt_weights(cfg, seed=c["weights_seed"]), dtype=torch.float32)
+        st = ora.new_seq()
+        logits = ora.step([(st, c["prompt"])], want_all_logits=True)
+        assert logits.argmax(-1).tolist() == c["argmax_per_pos"]
+        np.testing.assert_allclose(torch.logsumexp(logits, -1).numpy(), np.array(c["logsumexp_per_pos"]), atol=2e-5)
+        np.testing.assert_allclose(logits[-1, :512].numpy(), np.array(c["last_logits_head"]), atol=2e-5)
+        np.testing.assert_allclose(logits[len(c["prompt"]) // 2, :256].numpy(), np.array(c["mid_logits_head"]), atol=2e-5)
+        # HF's KV-cache decode: one position per call, teacher-forced on HF's own greedy tokens
+        for i, tok in enumerate(c["decode_tokens"]):
+            row = ora.step([(st, [tok])])[0]
+            np.testing.assert_allclose(row[:128].numpy(), np.array(c["decode_logits_head"][i]), atol=2e-5)
+            assert abs(float(torch.logsumexp(row, -1)) - c["decode_logsumexp"][i]) < 2e-5
+            if i + 1 < len(c["decode_tokens"]):
+                assert int(row.argmax()) == c["decode_tokens"][i + 1]
+
+
+def test_opt_oracle_bf16_rounding_points_match_hf_bf16_fixture():
+    """Same rounding points as HF's bf16 run => logits within 2 bf16 ulps of the row's magnitude (fp32 summation order
+    inside the matmuls differs), a good share bit-identical, argmax equal off ties."""
+    g = json.loads((GOLD / "opt_hf_bf16.json").read_text())
+    for c in g["cases"]:
+        cfg = case_cfg(c["config"])
+        ora = OPTOracle(cfg, synthetic_opt_weights(cfg, seed=c["weights_seed"]))
+        st = ora.new_seq()
+        logits = ora.step([(st, c["prompt"])], want_all_logits=True)
+        assert torch.equal(logits, logits.to(torch.bfloat16).float())
+        last = torch.tensor(c["last_logits_head"])
+        ulp = 2.0 ** (torch.floor(torch.log2(logits[-1].abs().max())).item() - 7)
+        d = (logits[-1, :512] - last).abs()
+        assert float(d.max()) <= 2.0 * ulp, (float(d.max()), ulp)
+        assert float(d.mean()) < 0.5 * ulp
+        assert float((d == 0).float().mean()) > 0.15
+        np.testing.assert_allclose(torch.logsumexp(logits, -1).numpy(), np.array(c["logsumexp_per_pos"]), atol=5e-3)
+        for pos, (a, b, m) in enumerate(zip(logits.argmax(-1).tolist(), c["argmax_per_pos"], c["top2_margin_per_pos"])):
+            if m > 2.0 * ulp:
+                assert a == b, (c["config"], pos, a, b, m)
+        for i, tok in enumerate(c["decode_tokens"]):
+            row = ora.step([(st, [tok])])[0]
+            dd = (row[:128] - torch.tensor(c["decode_logits_head"][i])).abs()
+            assert float(dd.max()) <= 2.0 * ulp
+            assert abs(float(torch.logsumexp(row, -1)) - c["decode_logsumexp"][i]) < 5e-3
+
+
+def test_opt_oracle_incremental_equals_prefill():
+    cfg = OPT_CONFIGS["opt-tiny"]
+    w = synthetic_opt_weights(cfg, seed=5)
+    prompt = list(range(40, 75))
+    a = OPTOracle(cfg, w, dtype=torch.float32)
+    full = a.step([(a.new_seq(), prompt)], want_all_logits=True)
+    b = OPTOracle(cfg, w, dtype=torch.float32)
+    st = b.new_seq()
+    rows = [b.step([(st, prompt[:20])])[0]]
+    for t in prompt[20:]:
+        rows.append(b.step([(st, [t])])[0])
+    np.testing.assert_allclose(torch.stack(rows).numpy(), full[19:].numpy(), atol=1e-5)
+    # two sequences in one flat batch do not see each other
+    c = OPTOracle(cfg, w, dtype=torch.float32)
+    two = c.step([(c.new_seq(), prompt), (c.new_seq(), prompt[:11])])
+    np.testing.assert_allclose(two[0].numpy(), full[-1].numpy(), atol=1e-5)
+    np.testing.assert_allclose(two[1].numpy(), full[10].numpy(), atol=1e-5)
