@@ -293,6 +293,13 @@ def _load_synthetic(eng, cfg, seed: int) -> None:
     Under tensor parallelism every rank draws the SAME full tensor (same seed) and the engine keeps its shard."""
     import torch
 
+    if getattr(cfg, "arch", "llama") == "opt":   # --model opt-125m (BASELINE configs[0] on the architecture it names)
+        from vllm_tgis_adapter_b200.engine.loader import load_synthetic_weights
+
+        load_synthetic_weights(eng, cfg, seed, torch.cuda.current_device())
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return
     gen = torch.Generator(device="cuda").manual_seed(seed)
 
     def rnd(r, c):
@@ -466,6 +473,12 @@ def _teacher_forced_parity(eng, prompts, tokens) -> dict:
 
 def _step_bytes(cfg, B: int, mean_ctx: float, tp: int) -> float:
     """Algorithmic bytes of one decode step PER GPU: weights/tp + KV/tp + one bf16 logits scan."""
+    if getattr(cfg, "arch", "llama") == "opt":
+        # algorithmic = the model's own dims (64-dim heads); the engine streams zero-padded 128-dim head slots, which shows
+        # up as a lower roofline fraction, not as smaller algorithmic bytes
+        n_params = cfg.n_layers * (4 * cfg.hidden * cfg.hidden + 2 * cfg.hidden * cfg.ffn) + cfg.vocab * cfg.hidden
+        kv_tok = 2 * cfg.n_layers * cfg.n_kv_heads * cfg.head_dim * 2
+        return (n_params * 2 + B * mean_ctx * kv_tok) / tp + B * cfg.vocab * 2
     q_dim, kv_dim = cfg.n_q_heads * 128, cfg.n_kv_heads * 128
     n_params = cfg.n_layers * (cfg.hidden * (q_dim + 2 * kv_dim) + cfg.hidden * q_dim + 3 * cfg.hidden * cfg.ffn) \
         + cfg.vocab * cfg.hidden

@@ -39,25 +39,36 @@
 extern "C" {
 #endif
 
-#define TGIS_ABI_VERSION 6
+#define TGIS_ABI_VERSION 7
 #define TGIS_MAX_REQUEST_ID 96
 #define TGIS_MAX_TOPN 12 /* reference forces max_logprobs >= 11: tgis_utils/args.py:214-216 */
 #define TGIS_MAX_STOP_TOKEN_IDS 8
 
 typedef struct tgis_engine tgis_engine;
 
-/* Model + runtime configuration (Llama-architecture decoder: RMSNorm, neox RoPE, GQA, SwiGLU; bf16). */
+/* Architectures (tgis_config.arch).  The reference names a model by --model-name (tgis_utils/args.py:104,185-186) and lets
+ * vLLM pick the architecture from the checkpoint's config.json; the host-side loader does the same and passes it here.
+ *   LLAMA: RMSNorm, neox RoPE, GQA, SwiGLU, no biases (BASELINE configs[1..4])
+ *   OPT:   learned positions (offset 2), LayerNorm with bias, biased q/k/v/out/fc1/fc2, ReLU, tied lm_head,
+ *          do_layer_norm_before = true, word_embed_proj_dim == hidden -- facebook/opt-125m, the reference's own test
+ *          model (/root/reference/tests/conftest.py:79-91 (no --model: vLLM's default, facebook/opt-125m) and tests/test_hub.py:17; BASELINE configs[0]).  64-dim heads (head_dim = 64) run on the
+ *          128-dim attention tiles: the engine zero-pads every head's q/k/v rows and out_proj columns at load time, which
+ *          leaves every dot product unchanged.  Single GPU, no LoRA slots. */
+#define TGIS_ARCH_LLAMA 0
+#define TGIS_ARCH_OPT 1
+
+/* Model + runtime configuration (bf16 decoder-only transformer; see TGIS_ARCH_*). */
 typedef struct tgis_config {
   int32_t abi_version; /* must be TGIS_ABI_VERSION */
   int32_t n_layers;
   int32_t hidden;
   int32_t n_q_heads;
   int32_t n_kv_heads;
-  int32_t head_dim; /* must be 128 */
+  int32_t head_dim; /* 128; OPT: 64 or 128 */
   int32_t ffn;
   int32_t vocab;
   float rope_theta;
-  float rms_eps;
+  float rms_eps;              /* RMSNorm epsilon; OPT: the LayerNorm epsilon */
   int32_t max_model_len;      /* reference: --max-sequence-length / --max-model-len (tgis_utils/args.py:187-192) */
   int32_t max_num_seqs;       /* concurrent sequences in the running batch */
   int32_t max_batched_tokens; /* token budget of one step (prefill chunk size) */
@@ -80,6 +91,8 @@ typedef struct tgis_config {
    * projections of every layer.  Single GPU only (tp_size == 1). */
   int32_t max_loras;
   int32_t max_lora_rank;
+  int32_t arch;               /* TGIS_ARCH_LLAMA / TGIS_ARCH_OPT */
+  int32_t reserved0;
 } tgis_config;
 
 /* What the adapter's proto->SamplingParams mapping (grpc_server.py:508-628) hands to the engine. */
@@ -182,7 +195,9 @@ int tgis_abi_version(void);
 
 int tgis_engine_create(const tgis_config* cfg, tgis_engine** out);
 /* name: HF Llama parameter name ("model.layers.3.self_attn.q_proj.weight", "lm_head.weight", ...) or
- * "tgis.rope_cos_sin" ([max_model_len,128] bf16 = cos|sin).  ptr may be host or device memory (cudaMemcpyDefault);
+ * "tgis.rope_cos_sin" ([max_model_len,128] bf16 = cos|sin); arch OPT: HF OPT parameter names
+ * ("model.decoder.layers.3.self_attn.q_proj.bias", "model.decoder.embed_positions.weight" with >= max_model_len + 2 rows,
+ * ...; a 1-D tensor is passed as rows = n, cols = 1).  ptr may be host or device memory (cudaMemcpyDefault);
  * dtype 0 = bf16.  rows/cols describe the full (unsharded) tensor. */
 int tgis_engine_load_weight(tgis_engine* e, const char* name, const void* ptr, int64_t rows, int64_t cols, int32_t dtype);
 int tgis_engine_start(tgis_engine* e);

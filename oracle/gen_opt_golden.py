@@ -3,7 +3,7 @@
 
     python -m oracle.gen_opt_golden
 
-The reference's OPT fixture is the hub checkpoint facebook/opt-125m (/root/reference/tests/conftest.py:83-91), which is
+The reference's OPT fixture is the hub checkpoint facebook/opt-125m (/root/reference/tests/conftest.py:79-91 (no --model: vLLM's default, facebook/opt-125m) and tests/test_hub.py:17), which is
 not obtainable here (no network); the fixtures use seeded random weights of the same architecture
 (oracle/opt_oracle.py::synthetic_opt_weights) loaded into an HF OPTForCausalLM built from the same config keys
 facebook/opt-125m's config.json carries (do_layer_norm_before, enable_bias, layer_norm_elementwise_affine, relu, tied
@@ -90,7 +90,7 @@ def main() -> None:
     OUT.mkdir(parents=True, exist_ok=True)
     meta = {"generated_by": "oracle/gen_opt_golden.py", "torch": torch.__version__,
             "transformers": transformers.__version__,
-            "reference": "opendatahub-io/vllm-tgis-adapter (/root/reference) tests/conftest.py:83-91 (facebook/opt-125m)"}
+            "reference": "opendatahub-io/vllm-tgis-adapter (/root/reference) tests/conftest.py:79-91 (no --model: vLLM's default, facebook/opt-125m) and tests/test_hub.py:17 (facebook/opt-125m)"}
     f = fixture(torch.float32, "eager")
     f["meta"] = meta
     (OUT / "opt_hf_fp32.json").write_text(json.dumps(f))

@@ -4,7 +4,7 @@ configs[0]") — TEST INFRASTRUCTURE ONLY.
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module; the product path never does.
 
 The reference's own OPT fixture is `facebook/opt-125m` served through `self.engine.generate(...)`
-(/root/reference/tests/conftest.py:83-91, tests/test_grpc_server.py:42-49, grpc/grpc_server.py:222); the arithmetic is
+(/root/reference/tests/conftest.py:79-91 (no --model: vLLM's default, facebook/opt-125m) and tests/test_hub.py:17, tests/test_grpc_server.py:42-49, grpc/grpc_server.py:222); the arithmetic is
 the un-vendored dependency vLLM (installed 0.22.0).  Restated here in plain torch ops with the model-dtype rounding
 points of that path, each step citing the file:line it follows:
 
@@ -23,7 +23,7 @@ points of that path, each step citing the file:line it follows:
   logits             opt.py:364-420: final_layer_norm, lm_head tied to embed_tokens, no bias; rounded to the model dtype
                      (vllm layers/logits_processor.py:89-104), the sampler casts to fp32 (v1/sample/sampler.py:91)
 
-PARITY PINNING: tests/test_oracle_cpu.py checks this module against transformers' OPTForCausalLM (random-init, fp32 and
+PARITY PINNING: tests/test_opt_oracle_cpu.py checks this module against transformers' OPTForCausalLM (random-init, fp32 and
 bf16, eager attention) through the fixtures tests/golden/opt_hf_{fp32,bf16}.json written by oracle/gen_opt_golden.py.
 The real facebook/opt-125m weights are not obtainable here (no network): the fixtures use seeded random weights of the
 same architecture, which pins the arithmetic but not a checkpoint.

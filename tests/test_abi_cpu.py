@@ -29,6 +29,7 @@ def test_struct_layouts_match_the_header_sizes():
     assert lib.tgis_k_sizeof_sample_out() == 112
     assert lib.tgis_k_kv_block() == 32
     assert C.sizeof(_lib.TgisSamplingParams) == 120   # static_assert in csrc/engine.cu
+    assert C.sizeof(_lib.TgisConfig) == 304           # static_assert in csrc/engine.cu (ABI v7: + arch)
     # id, 5 ints, 2 arrays, 4 ints, pad, 4 doubles, prompt_pos + reserved
     assert C.sizeof(_lib.TgisStepOutput) == 96 + 4 * 5 + 48 + 48 + 4 * 4 + 4 + 32 + 8
 

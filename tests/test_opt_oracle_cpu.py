@@ -1,6 +1,6 @@
 """Pin the OPT oracle (oracle/opt_oracle.py) against transformers' OPTForCausalLM run in this container
 (oracle/gen_opt_golden.py -> tests/golden/opt_hf_{fp32,bf16}.json).  The reference's OPT fixture is facebook/opt-125m
-(/root/reference/tests/conftest.py:83-91); the fixtures carry seeded random weights of that architecture."""
+(/root/reference/tests/conftest.py:79-91 (no --model: vLLM's default, facebook/opt-125m) and tests/test_hub.py:17); the fixtures carry seeded random weights of that architecture."""
 import dataclasses
 import json
 from pathlib import Path
@@ -83,3 +83,29 @@ def test_opt_oracle_incremental_equals_prefill():
     two = c.step([(c.new_seq(), prompt), (c.new_seq(), prompt[:11])])
     np.testing.assert_allclose(two[0].numpy(), full[-1].numpy(), atol=1e-5)
     np.testing.assert_allclose(two[1].numpy(), full[10].numpy(), atol=1e-5)
+
+
+def test_loader_maps_opt_config_json_and_refuses_unsupported_variants(tmp_path):
+    """Host side of the OPT family (engine/loader.py): facebook/opt-125m's config.json keys -> ModelConfig(arch="opt");
+    the variants that need modules the engine does not have (opt-350m: post-LayerNorm, project_in/out) fail at start-up
+    like an unsupported architecture does in the reference's engine, not at request time."""
+    import pytest
+
+    from vllm_tgis_adapter_b200.engine.core import PRESETS
+    from vllm_tgis_adapter_b200.engine.loader import model_config_from_hf
+
+    opt125m = {"architectures": ["OPTForCausalLM"], "model_type": "opt", "hidden_size": 768, "num_hidden_layers": 12,
+               "num_attention_heads": 12, "ffn_dim": 3072, "vocab_size": 50272, "max_position_embeddings": 2048,
+               "word_embed_proj_dim": 768, "do_layer_norm_before": True, "activation_function": "relu",
+               "enable_bias": True, "layer_norm_elementwise_affine": True, "_remove_final_layer_norm": False}
+    (tmp_path / "config.json").write_text(json.dumps(opt125m))
+    mc = model_config_from_hf(tmp_path, None)
+    assert mc == PRESETS["opt-125m"]
+    assert model_config_from_hf(tmp_path, 512).max_model_len == 512
+    with pytest.raises(ValueError, match="max_position_embeddings"):
+        model_config_from_hf(tmp_path, 4096)
+    opt350m = {**opt125m, "hidden_size": 1024, "num_attention_heads": 16, "ffn_dim": 4096, "num_hidden_layers": 24,
+               "word_embed_proj_dim": 512, "do_layer_norm_before": False}
+    (tmp_path / "config.json").write_text(json.dumps(opt350m))
+    with pytest.raises(ValueError, match="unsupported OPT variant"):
+        model_config_from_hf(tmp_path, None)

@@ -23,16 +23,28 @@ class LiveServer:
         from vllm_tgis_adapter_b200.engine.tokenizer import build_synthetic_tokenizer
         from vllm_tgis_adapter_b200.grpc import grpc_server
 
-        self.cfg = CONFIGS[cfg_name]
-        self.weights = synthetic_weights(self.cfg, seed=seed)
-        c = self.cfg
-        mc = ModelConfig(n_layers=c.n_layers, hidden=c.hidden, n_q_heads=c.n_q_heads, n_kv_heads=c.n_kv_heads,
-                         ffn=c.ffn, vocab=c.vocab, rope_theta=c.rope_theta, rms_eps=c.rms_eps,
-                         max_model_len=c.max_model_len)
-        native = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=256, kv_cache_bytes=64 << 20, max_loras=max_loras,
-                              max_lora_rank=max_lora_rank)
-        native.load_weights(self.weights)
-        native.load_weight("tgis.rope_cos_sin", rope_table(c))
+        if cfg_name.startswith("opt-"):   # OPT family (tests/test_zz_opt_gpu.py): HF OPT names, no rotary table
+            from oracle.opt_oracle import OPT_CONFIGS, synthetic_opt_weights
+
+            self.cfg = c = OPT_CONFIGS[cfg_name]
+            self.weights = synthetic_opt_weights(c, seed=seed)
+            mc = ModelConfig(n_layers=c.n_layers, hidden=c.hidden, n_q_heads=c.n_heads, n_kv_heads=c.n_heads, ffn=c.ffn,
+                             vocab=c.vocab, head_dim=c.head_dim, rms_eps=c.ln_eps, max_model_len=c.max_model_len,
+                             arch="opt")
+            # 12 kv heads in 128-dim slots: one 2048-token sequence alone is 151 MB of cache at opt-125m's depth
+            native = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=256, kv_cache_bytes=512 << 20)
+            native.load_weights(self.weights)
+        else:
+            self.cfg = CONFIGS[cfg_name]
+            self.weights = synthetic_weights(self.cfg, seed=seed)
+            c = self.cfg
+            mc = ModelConfig(n_layers=c.n_layers, hidden=c.hidden, n_q_heads=c.n_q_heads, n_kv_heads=c.n_kv_heads,
+                             ffn=c.ffn, vocab=c.vocab, rope_theta=c.rope_theta, rms_eps=c.rms_eps,
+                             max_model_len=c.max_model_len)
+            native = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=256, kv_cache_bytes=64 << 20,
+                                  max_loras=max_loras, max_lora_rank=max_lora_rank)
+            native.load_weights(self.weights)
+            native.load_weight("tgis.rope_cos_sin", rope_table(c))
         self.tok = build_synthetic_tokenizer(c.vocab)
         self.args = argparse.Namespace(max_new_tokens=max_new_tokens, output_special_tokens=False, default_include_stop_seqs=True,
                                        disable_prompt_logprobs=False, adapter_cache=adapter_cache, prefix_store_path=None,

@@ -16,7 +16,7 @@ PKG = CSRC.parent
 LIB_DIR = PKG / "lib"
 OBJ_DIR = CSRC / "build"
 LIB_PATH = LIB_DIR / "libtgis_engine.so"
-SOURCES = ["gemm_tcgen05.cu", "gemm_ref.cu", "elementwise.cu", "attention.cu", "sampler.cu", "lora.cu", "engine.cu", "test_api.cu"]
+SOURCES = ["gemm_tcgen05.cu", "gemm_ref.cu", "elementwise.cu", "attention.cu", "sampler.cu", "lora.cu", "opt.cu", "engine.cu", "test_api.cu"]
 HEADERS = ["ptx.cuh", "launch.cuh", "kernels.h", "../../include/tgis_engine.h", "../../include/tgis_kernels.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -142,6 +142,9 @@ struct DevBuf {
 
 struct LayerW {
   bf16 *wqkv, *wo, *wgu, *wd, *ln1, *ln2;
+  // OPT only (tgis_config.arch == TGIS_ARCH_OPT): wgu holds fc1 [ffn, hidden] (not interleaved), wd holds fc2; biases of
+  // the four projections (q/k/v concatenated, head-padded like wqkv) and of the two LayerNorms
+  bf16 *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr, *ln1_b = nullptr, *ln2_b = nullptr;
   CUtensorMap m_qkv, m_o, m_gu, m_d;
 };
 
@@ -220,6 +223,13 @@ struct tgis_engine {
   DevBuf<bf16> w_arena;
   bf16 *embed = nullptr, *lm_head = nullptr, *final_norm = nullptr, *cos_sin = nullptr;
   bool lm_head_loaded = false, cos_sin_loaded = false;
+  // OPT (opt.cu): learned positions [max_model_len + 2, hidden], final LayerNorm bias; model head dim (64 or 128: every
+  // head is zero-padded to the 128-dim attention tiles at load time); fp32 GEMM accumulators of the biased projections
+  bool opt = false;
+  bf16 *pos_embed = nullptr, *final_norm_b = nullptr;
+  int pos_rows = 0, model_head_dim = HEAD_DIM;
+  float attn_scale = 0.f;
+  DevBuf<float> y32;
   std::vector<LayerW> layers;
   CUtensorMap m_lm{};
   // kv cache
@@ -412,6 +422,10 @@ struct tgis_engine {
     nkv = c.n_kv_heads / tp;
     Fl = c.ffn / tp;
     Vl = c.vocab / tp;
+    opt = c.arch == TGIS_ARCH_OPT;
+    model_head_dim = opt ? c.head_dim : HEAD_DIM;
+    attn_scale = 1.0f / std::sqrt((float)model_head_dim);  // zero-padded head dims add nothing to q . k
+    pos_rows = opt ? c.max_model_len + 2 : 0;
     q_dim = nq * HEAD_DIM;
     qkv_dim = (nq + 2 * nkv) * HEAD_DIM;
     bt_stride = (c.max_model_len + KV_BLOCK - 1) / KV_BLOCK;
@@ -447,9 +461,11 @@ struct tgis_engine {
     // ---- weights: one arena
     const size_t H = c.hidden, F = Fl, V = c.vocab, L = c.n_layers;  // F: this rank's ffn shard
     const size_t per_layer = (size_t)qkv_dim * H + H * q_dim + 2 * F * H + H * F + 2 * H;
+    const size_t opt_extra = opt ? (size_t)pos_rows * H + H + L * ((size_t)qkv_dim + 4 * H + F) + 64 * (6 * L + 4) : 0;
     const size_t total = V * H /*embed*/ + V * H /*lm_head*/ + H /*norm*/ + (size_t)c.max_model_len * HEAD_DIM +
-                         L * per_layer + 64 * (6 * L + 8);
+                         L * per_layer + 64 * (6 * L + 8) + opt_extra;
     w_arena.alloc(total);
+    if (opt) w_arena.zero();  // the padded head dims of q/k/v rows, out_proj columns and their biases stay zero
     bf16* p = w_arena.p;
     auto take = [&](size_t n) {
       bf16* r = p;
@@ -468,8 +484,22 @@ struct tgis_engine {
       l.wd = take(H * F);
       l.ln1 = take(H);
       l.ln2 = take(H);
+      if (opt) {
+        l.b_qkv = take(qkv_dim);
+        l.b_o = take(H);
+        l.b_fc1 = take(F);
+        l.b_fc2 = take(H);
+        l.ln1_b = take(H);
+        l.ln2_b = take(H);
+      }
     }
-    default_rope_table();
+    if (opt) {
+      pos_embed = take((size_t)pos_rows * H);
+      final_norm_b = take(H);
+      identity_rope_table();  // no rotary embedding: rope_kvwrite_kernel degenerates to the paged-KV scatter
+    } else {
+      default_rope_table();
+    }
 
     // ---- activations
     resid.alloc(T_alloc * H);
@@ -478,6 +508,7 @@ struct tgis_engine {
     attn_out.alloc(T_alloc * q_dim);
     tmp.alloc(T_alloc * H);
     act.alloc(T_alloc * F);
+    if (opt) y32.alloc(T_alloc * std::max<size_t>({(size_t)qkv_dim, F, H}));
     if (c.max_loras > 0) {
       max_loras = c.max_loras;
       lora_R = c.max_lora_rank;
@@ -567,7 +598,7 @@ struct tgis_engine {
     for (auto& l : layers) {
       wmap(&l.m_qkv, l.wqkv, qkv_dim, H);
       wmap(&l.m_o, l.wo, H, q_dim);
-      wmap(&l.m_gu, l.wgu, 2 * F, H);
+      wmap(&l.m_gu, l.wgu, opt ? F : 2 * F, H);  // OPT: fc1
       wmap(&l.m_d, l.wd, H, F);
     }
     wmap(&m_lm, lm_head, Vl, H);  // this rank's vocab shard (== V when tp == 1)
@@ -801,6 +832,18 @@ struct tgis_engine {
     }
   }
 
+  // OPT has no rotary embedding: cos = 1, sin = 0 makes every product of the rotation exact (x * 1 - y * 0 == x in bf16)
+  void identity_rope_table() {
+    const int half = HEAD_DIM / 2;
+    std::vector<bf16> tab((size_t)cfg.max_model_len * HEAD_DIM);
+    for (int pos = 0; pos < cfg.max_model_len; ++pos)
+      for (int i = 0; i < half; ++i) {
+        tab[(size_t)pos * HEAD_DIM + i] = __float2bfloat16_rn(1.0f);
+        tab[(size_t)pos * HEAD_DIM + half + i] = __float2bfloat16_rn(0.0f);
+      }
+    CK(cudaMemcpy(cos_sin, tab.data(), tab.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
+
   void default_rope_table() {
     // HF LlamaRotaryEmbedding: inv_freq fp32, freqs = pos * inv_freq (fp32), cos/sin fp32 -> model dtype.
     const int half = HEAD_DIM / 2;
@@ -817,7 +860,72 @@ struct tgis_engine {
 
   // Copies the FULL (unsharded) tensor's shard for this rank into the arena: row blocks for column-parallel layers
   // (q/k/v/gate/up, lm_head), column blocks for row-parallel layers (o, down), everything else replicated.
+  // OPT checkpoints (HF names, "model.decoder." or "decoder." prefix).  Single GPU: every tensor is kept whole.  q/k/v rows,
+  // out_proj columns and the q/k/v biases are spread head by head over 128-dim head slots (the upper 128 - head_dim dims of
+  // every slot stay zero: the arena was zeroed), so the attention kernels and the paged cache keep their one geometry.
+  int load_weight_opt(const std::string& full_name, const void* ptr, int64_t rows, int64_t cols) {
+    const tgis_config& c = cfg;
+    const int64_t H = c.hidden, F = c.ffn, V = c.vocab, hd = model_head_dim, nh = c.n_q_heads;
+    std::string name = full_name;
+    if (name.rfind("model.", 0) == 0) name = name.substr(6);
+    auto shape_err = [&]() {
+      return fail("shape mismatch for " + full_name + ": got " + std::to_string(rows) + "x" + std::to_string(cols));
+    };
+    auto copy = [&](bf16* dst, int64_t n) -> int {
+      if (rows * cols != n) return shape_err();
+      const cudaError_t e = cudaMemcpy(dst, ptr, (size_t)n * sizeof(bf16), cudaMemcpyDefault);
+      return e == cudaSuccess ? 0 : fail(std::string("cudaMemcpy(weight) failed: ") + cudaGetErrorString(e));
+    };
+    // n_rows source rows of `w` elements each -> destination rows `dpitch` elements apart
+    auto copy2d = [&](bf16* dst, int64_t dpitch, int64_t w, int64_t n_rows) -> int {
+      if (rows * cols != w * n_rows) return shape_err();
+      const cudaError_t e = cudaMemcpy2D(dst, (size_t)dpitch * sizeof(bf16), ptr, (size_t)w * sizeof(bf16),
+                                         (size_t)w * sizeof(bf16), (size_t)n_rows, cudaMemcpyDefault);
+      return e == cudaSuccess ? 0 : fail(std::string("cudaMemcpy2D(weight) failed: ") + cudaGetErrorString(e));
+    };
+    if (name == "lm_head.weight") { lm_head_loaded = true; return copy(lm_head, V * H); }
+    if (name.rfind("decoder.", 0) != 0) return fail("unknown weight " + full_name);
+    name = name.substr(8);
+    if (name == "embed_tokens.weight") return copy(embed, V * H);
+    if (name == "embed_positions.weight") {
+      // the checkpoint's table covers max_position_embeddings + 2 rows; the engine keeps what max_model_len can reach
+      if (cols != H || rows < pos_rows) return shape_err();
+      const cudaError_t e = cudaMemcpy(pos_embed, ptr, (size_t)pos_rows * H * sizeof(bf16), cudaMemcpyDefault);
+      return e == cudaSuccess ? 0 : fail(std::string("cudaMemcpy(weight) failed: ") + cudaGetErrorString(e));
+    }
+    if (name == "final_layer_norm.weight") return copy(final_norm, H);
+    if (name == "final_layer_norm.bias") return copy(final_norm_b, H);
+    if (name.rfind("layers.", 0) != 0) return fail("unknown weight " + full_name);
+    const size_t dot = name.find('.', 7);
+    if (dot == std::string::npos) return fail("bad weight name " + full_name);
+    const int li = atoi(name.substr(7, dot - 7).c_str());
+    if (li < 0 || li >= c.n_layers) return fail("layer index out of range in " + full_name);
+    LayerW& l = layers[li];
+    const std::string sub = name.substr(dot + 1);
+    const int64_t slot_w = (int64_t)HEAD_DIM * H;  // elements of one padded head's rows in wqkv
+    for (int j = 0; j < 3; ++j) {
+      static const char* const qkv_names[3] = {"q_proj", "k_proj", "v_proj"};
+      const std::string base = std::string("self_attn.") + qkv_names[j];
+      // head h's hd rows of [H] -> rows [h * 128, h * 128 + hd) of the projection's block
+      if (sub == base + ".weight") return copy2d(l.wqkv + (size_t)j * nh * slot_w, slot_w, hd * H, nh);
+      if (sub == base + ".bias") return copy2d(l.b_qkv + (size_t)j * nh * HEAD_DIM, HEAD_DIM, hd, nh);
+    }
+    // out_proj [H, nh * hd]: (row, head) pairs are the source rows of hd elements, 128 apart in wo [H, nh * 128]
+    if (sub == "self_attn.out_proj.weight") return copy2d(l.wo, HEAD_DIM, hd, H * nh);
+    if (sub == "self_attn.out_proj.bias") return copy(l.b_o, H);
+    if (sub == "self_attn_layer_norm.weight") return copy(l.ln1, H);
+    if (sub == "self_attn_layer_norm.bias") return copy(l.ln1_b, H);
+    if (sub == "fc1.weight") return copy(l.wgu, F * H);
+    if (sub == "fc1.bias") return copy(l.b_fc1, F);
+    if (sub == "fc2.weight") return copy(l.wd, H * F);
+    if (sub == "fc2.bias") return copy(l.b_fc2, H);
+    if (sub == "final_layer_norm.weight") return copy(l.ln2, H);
+    if (sub == "final_layer_norm.bias") return copy(l.ln2_b, H);
+    return fail("unknown layer weight " + full_name);
+  }
+
   int load_weight(const std::string& name, const void* ptr, int64_t rows, int64_t cols) {
+    if (opt) return load_weight_opt(name, ptr, rows, cols);
     const tgis_config& c = cfg;
     const int64_t H = c.hidden, F = c.ffn, V = c.vocab;
     const uint8_t* src = static_cast<const uint8_t*>(ptr);
@@ -1018,14 +1126,18 @@ struct tgis_engine {
     const int32_t* d_tok = ds<int32_t>(off_tok);
     const AttnSeq* d_seqs = ds<AttnSeq>(off_seqs);
     const int32_t* d_bt = ds<int32_t>(off_bt);
-    const float scale = 1.0f / std::sqrt((float)HEAD_DIM);
+    const float scale = attn_scale;
 
     if (rank == 0) {
       CK(bitmap_set_launch(seen_bitmap.p, bitmap_words, ds<int32_t>(off_tokslot), d_tok, T, stream));
       ++n_launches;
     }
-    CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
-    ++n_launches;
+    if (opt) {
+      opt_layers(T, n_dec, n_tiles, max_dec_kv, S, R);  // embeddings + layer stack + final LayerNorm -> xn
+    } else {
+      CK(embed_gather_launch(d_tok, embed, resid.p, T, H, V, stream));
+      ++n_launches;
+    }
     const bool ar_fused = exchange_mode(T) != 0;
     // RoPE + KV-cache scatter fused into the qkv GEMM's split-tile reduction (decode-shaped steps where every weight
     // tile is split over several CTAs; TGIS_FUSE_ROPE=0: off)
@@ -1056,7 +1168,7 @@ struct tgis_engine {
     float* ssq_mlp = norm_ssq.p + (size_t)GEMM_NORM_MAX_T * n_parts;   // written by down-proj, read by the next qkv
     const GemmNorm prod_attn{resid.p, ssq_attn, nullptr, nullptr, nullptr, 0, 0.f};
     const GemmNorm prod_mlp{resid.p, ssq_mlp, nullptr, nullptr, nullptr, 0, 0.f};
-    for (int li = 0; li < c.n_layers; ++li) {
+    for (int li = 0; li < (opt ? 0 : c.n_layers); ++li) {  // Llama stack (OPT: opt_layers() above)
       LayerW& l = layers[li];
       const GemmNorm cons_qkv{nullptr, nullptr, resid.p, ssq_mlp, l.ln1, n_parts, c.rms_eps};
       const GemmNorm cons_gu{nullptr, nullptr, resid.p, ssq_attn, l.ln2, n_parts, c.rms_eps};
@@ -1156,7 +1268,7 @@ struct tgis_engine {
     // every rank has finished READING this step's buffers before a faster rank overwrites them in the next step.
     if (ar_fused) fused_ar_norm(1, final_norm, T);
     if (R > 0) {
-      if (ar_fused) {
+      if (ar_fused || opt) {
       } else {
         CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
         ++n_launches;
@@ -1174,6 +1286,59 @@ struct tgis_engine {
       }
     }
     CK(stl_marker_launch(22, stream));  // timeline builds: step end (after the result copy)
+  }
+
+  // OPT layer stack (vllm model_executor/models/opt.py:170-197, do_layer_norm_before): the tcgen05 GEMMs write their fp32
+  // accumulators (out mode 1) and the kernels of opt.cu add the bias before the single rounding to bf16; the paged
+  // attention kernels run unchanged on zero-padded 128-dim heads with the model's softmax scale.  Per layer:
+  //   LN1 [+ previous fc2 bias/residual] -> qkv GEMM -> bias -> KV scatter -> attention -> out_proj GEMM ->
+  //   LN2 + out_proj bias/residual -> fc1 GEMM -> bias + ReLU -> fc2 GEMM;  final LayerNorm after the last layer.
+  void opt_layers(int T, int n_dec, int n_tiles, int max_dec_kv, int S, int R) {
+    const tgis_config& c = cfg;
+    const int H = c.hidden, F = Fl, V = c.vocab;
+    const int32_t* d_tok = ds<int32_t>(off_tok);
+    const int32_t* d_pos = ds<int32_t>(off_pos);
+    const AttnSeq* d_seqs = ds<AttnSeq>(off_seqs);
+    const int32_t* d_bt = ds<int32_t>(off_bt);
+    CK(opt_embed_launch(d_tok, d_pos, embed, pos_embed, resid.p, T, H, V, pos_rows, /*offset=*/2, stream));
+    ++n_launches;
+    for (int li = 0; li < c.n_layers; ++li) {
+      LayerW& l = layers[li];
+      // h += fc2 of the previous layer (its fp32 accumulators are still in y32), then LN1
+      CK(opt_layernorm_launch(li == 0 ? nullptr : y32.p, li == 0 ? nullptr : layers[li - 1].b_fc2, resid.p, l.ln1, l.ln1_b,
+                              xn.p, T, H, c.rms_eps, stream));
+      gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, y32.p, T, qkv_dim, H, /*out_f32=*/1, &l.m_o, T, H, q_dim);
+      CK(opt_bias_act_launch(y32.p, qkv_dim, l.b_qkv, qkv.p, qkv_dim, T, qkv_dim, /*relu=*/0, num_sms, stream));
+      bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
+      bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
+      // identity rotation table: this is the k / v scatter into the paged cache
+      CK(rope_kvwrite_launch(qkv.p, d_pos, ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, nq, nkv, stream));
+      n_launches += 3;
+      if (n_dec > 0) {
+        const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
+        CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, ds<DecItem>(items_off(S)), n_dec * max_splits, d_seqs,
+                              ds<int32_t>(off_decids), n_dec, max_splits, part_o.p, part_ml.p, attn_out.p, q_dim, nq,
+                              nkv, attn_scale, num_sms, stream, attn_arrive.p));
+        n_launches += (max_splits > 1 && !attn_inkernel_merge) ? 2 : 1;
+      }
+      if (n_tiles > 0) {
+        CK(attn_prefill_launch(qkv.p, qkv_dim, kc, vc, d_seqs, ds<int32_t>(off_tileseq), ds<int32_t>(off_tileq0),
+                               n_tiles, d_bt, bt_stride, attn_out.p, q_dim, nq, nkv, attn_scale, stream));
+        ++n_launches;
+      }
+      gemm(xm_attn, l.m_o, attn_out.p, l.wo, y32.p, T, H, q_dim, /*out_f32=*/1, &l.m_gu, T, F, H);
+      CK(opt_layernorm_launch(y32.p, l.b_o, resid.p, l.ln2, l.ln2_b, xn.p, T, H, c.rms_eps, stream));
+      gemm(xm_xn, l.m_gu, xn.p, l.wgu, y32.p, T, F, H, /*out_f32=*/1, &l.m_d, T, H, F);
+      CK(opt_bias_act_launch(y32.p, F, l.b_fc1, act.p, F, T, F, /*relu=*/1, num_sms, stream));
+      // (the successor's first weight boxes are pulled into L2 by this launch's producer warp, as on the Llama path)
+      if (li + 1 < c.n_layers) gemm(xm_act, l.m_d, act.p, l.wd, y32.p, T, H, F, /*out_f32=*/1, &layers[li + 1].m_qkv, T, qkv_dim, H);
+      else gemm(xm_act, l.m_d, act.p, l.wd, y32.p, T, H, F, /*out_f32=*/1, R > 0 ? &m_lm : nullptr, R, Vl, H);
+      n_launches += 2;
+    }
+    // always run (even when no row is sampled this step): a prompt-logprob pass may read xn afterwards
+    CK(opt_layernorm_launch(y32.p, layers[c.n_layers - 1].b_fc2, resid.p, final_norm, final_norm_b, xn.p, T, H, c.rms_eps,
+                            stream));
+    ++n_launches;
   }
 
   // Prompt-logprob pass (vllm prompt_logprobs; grpc_server.py:609-611): lm_head + FORCED sampler rows over m prompt
@@ -1216,7 +1381,7 @@ struct tgis_engine {
     const tgis_config& c = cfg;
     const int H = c.hidden, V = c.vocab;
     CK(cudaMemcpyAsync(d_stage.p, h_stage, copy_bytes, cudaMemcpyHostToDevice, stream));
-    if (need_norm) {  // no sampled row in the step -> its final norm has not run yet
+    if (need_norm && !opt) {  // no sampled row in the step -> its final norm has not run yet (OPT: always run)
       CK(add_rmsnorm_launch(tmp.p, resid.p, final_norm, xn.p, T, H, c.rms_eps, stream));
       ++n_launches;
     }
@@ -1679,6 +1844,17 @@ struct tgis_engine {
       return false;
     }
 
+    // LoRA: sequences that share an adapter sit next to each other in the step, so that lora.cu's 8-token tiles are
+    // same-adapter tiles (A / B rows read once per tile) instead of falling back to one pass per token.  Every kernel's
+    // result for a token is independent of its neighbours, and post-processing below walks the same order.
+    if (max_loras > 0) {
+      bool any_lora = false;
+      for (const Sched& s : batch) any_lora |= s.r->sp.lora_slot > 0;
+      if (any_lora)
+        std::stable_sort(batch.begin(), batch.end(),
+                         [](const Sched& a, const Sched& b) { return a.r->sp.lora_slot < b.r->sp.lora_slot; });
+    }
+
     // ---- run
     run_batch(batch);
     ++n_steps;
@@ -1775,12 +1951,22 @@ extern "C" {
 const char* tgis_last_error(void) { return g_last_error.c_str(); }
 static_assert(offsetof(tgis_sampling_params, lora_slot) == 112, "ctypes mirror: engine/_lib.py TgisSamplingParams");
 static_assert(sizeof(tgis_sampling_params) == 120, "ctypes mirror: engine/_lib.py TgisSamplingParams");
+static_assert(sizeof(tgis_config) == 304, "ctypes mirror: engine/_lib.py TgisConfig");
 int tgis_abi_version(void) { return TGIS_ABI_VERSION; }
 
 int tgis_engine_create(const tgis_config* cfg, tgis_engine** out) {
   if (!cfg || !out) return fail("null argument");
   if (cfg->abi_version != TGIS_ABI_VERSION) return fail("ABI version mismatch");
-  if (cfg->head_dim != HEAD_DIM) return fail("head_dim must be 128");
+  if (cfg->arch != TGIS_ARCH_LLAMA && cfg->arch != TGIS_ARCH_OPT) return fail("unknown arch");
+  if (cfg->arch == TGIS_ARCH_OPT) {
+    if (cfg->head_dim != 64 && cfg->head_dim != HEAD_DIM) return fail("OPT: head_dim must be 64 or 128");
+    if (cfg->n_q_heads != cfg->n_kv_heads) return fail("OPT: n_kv_heads must equal n_q_heads (multi-head attention)");
+    if (cfg->hidden != cfg->n_q_heads * cfg->head_dim) return fail("OPT: hidden must be n_q_heads * head_dim");
+    if (cfg->tp_size > 1) return fail("OPT runs on a single GPU only (tp_size must be 1)");
+    if (cfg->max_loras > 0) return fail("OPT: LoRA adapter slots are not supported (max_loras must be 0)");
+  } else if (cfg->head_dim != HEAD_DIM) {
+    return fail("head_dim must be 128");
+  }
   if (cfg->n_kv_heads <= 0 || cfg->n_q_heads % cfg->n_kv_heads != 0) return fail("n_q_heads must be a multiple of n_kv_heads");
   const int G = cfg->n_q_heads / cfg->n_kv_heads;
   if (!(G == 1 || G == 2 || G == 3 || G == 4 || G == 8)) return fail("GQA group size must be 1, 2, 3, 4 or 8");

@@ -135,6 +135,19 @@ cudaError_t lora_expand_launch(const float* v, const int32_t* tok_slot, const Lo
 // act[t, j] = bf16(silu(gate_up[t, 2j])) * gate_up[t, 2j + 1]  (the interleaved gate_up layout the fused GEMM epilogue reads)
 cudaError_t silu_mul_interleaved_launch(const __nv_bfloat16* gate_up, __nv_bfloat16* act, int T, int ffn,
                                         cudaStream_t stream);
+// ---- opt.cu (OPT layer stack: learned positions, biased projections, ReLU, LayerNorm) ------------------------------
+// out[t] = bf16(tok_table[tok[t]] + pos_table[pos[t] + offset])
+cudaError_t opt_embed_launch(const int32_t* token_ids, const int32_t* positions, const __nv_bfloat16* tok_table,
+                             const __nv_bfloat16* pos_table, __nv_bfloat16* out, int T, int hidden, int vocab,
+                             int n_pos_rows, int offset, cudaStream_t stream);
+// acc != nullptr: residual = bf16(residual + bf16(acc + acc_bias)) first (acc: fp32 GEMM accumulators [T, hidden]);
+// out = LayerNorm(residual) * w + b
+cudaError_t opt_layernorm_launch(const float* acc, const __nv_bfloat16* acc_bias, __nv_bfloat16* residual,
+                                 const __nv_bfloat16* w, const __nv_bfloat16* b, __nv_bfloat16* out, int T, int hidden,
+                                 float eps, cudaStream_t stream);
+// out[t, n] = bf16(act(acc[t, n] + bias[n])), act = ReLU or identity
+cudaError_t opt_bias_act_launch(const float* acc, int ld_acc, const __nv_bfloat16* bias, __nv_bfloat16* out, int ld_out,
+                                int T, int N, int relu, int num_sms, cudaStream_t stream);
 // gather rows: out[r, :] = x[rows[r], :]
 cudaError_t gather_rows_launch(const __nv_bfloat16* x, const int32_t* rows, __nv_bfloat16* out, int R, int hidden,
                                cudaStream_t stream);

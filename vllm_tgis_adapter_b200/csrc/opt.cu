@@ -1,5 +1,5 @@
 // Elementwise / row-reduction kernels of the OPT layer stack (the reference's own test model is
-// facebook/opt-125m, /root/reference/tests/conftest.py:83-91).  The GEMMs, the paged attention kernels, the lm_head and
+// facebook/opt-125m, /root/reference/tests/conftest.py:79-91 (no --model: vLLM's default, facebook/opt-125m) and tests/test_hub.py:17).  The GEMMs, the paged attention kernels, the lm_head and
 // the sampler are the Llama path's; what OPT adds is
 //   * learned position embeddings with offset 2                    vllm model_executor/models/opt.py:61-70, :268-290
 //   * biased projections: the tcgen05 GEMM hands over its fp32 accumulators and the bias is added BEFORE the single

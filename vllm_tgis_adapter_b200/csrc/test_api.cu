@@ -130,6 +130,28 @@ int tgis_k_rmsnorm(const void* x_dev, void* residual_dev, const void* w_dev, voi
   return 0;
 }
 
+int tgis_k_opt_layernorm(const void* acc_dev, const void* acc_bias_dev, void* residual_dev, const void* w_dev,
+                         const void* b_dev, void* out_dev, int32_t T, int32_t hidden, float eps) {
+  KCK(opt_layernorm_launch((const float*)acc_dev, (const bf16*)acc_bias_dev, (bf16*)residual_dev, (const bf16*)w_dev,
+                           (const bf16*)b_dev, (bf16*)out_dev, T, hidden, eps, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tgis_k_opt_bias_act(const void* acc_dev, const void* bias_dev, void* out_dev, int32_t T, int32_t N, int32_t relu) {
+  KCK(opt_bias_act_launch((const float*)acc_dev, N, (const bf16*)bias_dev, (bf16*)out_dev, N, T, N, relu, 148, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tgis_k_opt_embed(const void* tok_dev, const void* pos_dev, const void* tok_table_dev, const void* pos_table_dev,
+                     void* out_dev, int32_t T, int32_t hidden, int32_t vocab, int32_t n_pos_rows, int32_t offset) {
+  KCK(opt_embed_launch((const int32_t*)tok_dev, (const int32_t*)pos_dev, (const bf16*)tok_table_dev,
+                       (const bf16*)pos_table_dev, (bf16*)out_dev, T, hidden, vocab, n_pos_rows, offset, 0));
+  KCK(cudaDeviceSynchronize());
+  return 0;
+}
+
 int tgis_k_silu_mul(const void* gate_up_dev, void* act_dev, int32_t T, int32_t ffn) {
   KCK(silu_mul_launch((const bf16*)gate_up_dev, (bf16*)act_dev, T, ffn, 0));
   KCK(cudaDeviceSynchronize());

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 6
+ABI_VERSION = 7
+ARCH_LLAMA, ARCH_OPT = 0, 1
 MAX_REQUEST_ID = 96
 MAX_TOPN = 12
 MAX_STOP_TOKEN_IDS = 8
@@ -27,7 +28,7 @@ class TgisConfig(C.Structure):
         ("gpu_mem_fraction", C.c_float), ("device", C.c_int32), ("tp_size", C.c_int32), ("tp_rank", C.c_int32),
         ("use_cuda_graphs", C.c_int32), ("debug_gemm_ref", C.c_int32), ("seed", C.c_uint64),
         ("nccl_id", C.c_uint8 * 128), ("shm_name", C.c_char * 64),
-        ("max_loras", C.c_int32), ("max_lora_rank", C.c_int32),
+        ("max_loras", C.c_int32), ("max_lora_rank", C.c_int32), ("arch", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -73,7 +74,7 @@ ENGINE_SYMBOLS = [
     "tgis_engine_max_model_len", "tgis_engine_set_profiling", "tgis_nccl_unique_id", "tgis_engine_worker_run", "tgis_engine_shutdown", "tgis_engine_destroy", "tgis_engine_run_until_idle",
 ]
 KERNEL_SYMBOLS = [
-    "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_step_timeline_enable", "tgis_k_step_timeline_read", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_gemm_norm_chain", "tgis_k_attention",
+    "tgis_k_last_error", "tgis_k_gemm_timeline", "tgis_k_step_timeline_enable", "tgis_k_step_timeline_read", "tgis_k_gemm", "tgis_k_rmsnorm", "tgis_k_opt_layernorm", "tgis_k_opt_bias_act", "tgis_k_opt_embed", "tgis_k_silu_mul", "tgis_k_rope_kv", "tgis_k_gemm_rope", "tgis_k_gemm_norm_chain", "tgis_k_attention",
     "tgis_k_attention_bench", "tgis_k_decode_items", "tgis_k_gemm_plan", "tgis_k_gemm_unit_rows",
     "tgis_k_sampler", "tgis_k_sampler_ex", "tgis_k_sampler_masked", "tgis_k_lora", "tgis_k_lora_bench", "tgis_k_silu_mul_interleaved", "tgis_k_sizeof_sample_row", "tgis_k_sizeof_sample_out", "tgis_k_kv_block",
 ]
@@ -130,6 +131,9 @@ def load_library() -> C.CDLL:
     lib.tgis_k_gemm_norm_chain.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, i32,
                                            C.POINTER(f32)]
     lib.tgis_k_silu_mul.argtypes = [vp, vp, i32, i32]
+    lib.tgis_k_opt_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32]
+    lib.tgis_k_opt_bias_act.argtypes = [vp, vp, vp, i32, i32, i32]
+    lib.tgis_k_opt_embed.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
     lib.tgis_k_rope_kv.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp, i32, i32, i32]
     lib.tgis_k_attention.argtypes = [vp, vp, vp, C.POINTER(i32), i32, C.POINTER(i32), i32, i32, vp, i32, i32, f32]
     lib.tgis_k_sampler.argtypes = [vp, i32, i32, vp, i32, vp, vp]

@@ -15,7 +15,9 @@ class EngineError(RuntimeError):
 
 @dataclasses.dataclass
 class ModelConfig:
-    """Llama-architecture dims (HF config.json names in comments)."""
+    """Decoder dims (HF config.json names in comments).  arch "llama": RMSNorm / RoPE / GQA / SwiGLU; arch "opt": learned
+    positions / LayerNorm / biased projections / ReLU (n_kv_heads == n_q_heads, head_dim 64 or 128, ffn = ffn_dim,
+    rms_eps carries the LayerNorm epsilon, rope_theta unused) -- include/tgis_engine.h TGIS_ARCH_*."""
 
     n_layers: int        # num_hidden_layers
     hidden: int          # hidden_size
@@ -27,6 +29,7 @@ class ModelConfig:
     rope_theta: float = 500000.0
     rms_eps: float = 1e-5
     max_model_len: int = 2048
+    arch: str = "llama"
 
 
 # Named architectures (real dims; this offline build runs them on synthetic weights — SURVEY.md §0)
@@ -34,6 +37,11 @@ PRESETS: dict[str, ModelConfig] = {
     "tiny": ModelConfig(n_layers=2, hidden=256, n_q_heads=4, n_kv_heads=2, ffn=512, vocab=1024, max_model_len=512),
     "small": ModelConfig(n_layers=4, hidden=512, n_q_heads=4, n_kv_heads=1, ffn=1536, vocab=4096, max_model_len=1024),
     "125m": ModelConfig(n_layers=12, hidden=768, n_q_heads=6, n_kv_heads=2, ffn=3072, vocab=50272, max_model_len=2048),
+    # facebook/opt-125m (the reference's own test model; BASELINE configs[0]) and a CPU-oracle-sized sibling
+    "opt-125m": ModelConfig(n_layers=12, hidden=768, n_q_heads=12, n_kv_heads=12, ffn=3072, vocab=50272, head_dim=64,
+                            max_model_len=2048, arch="opt"),
+    "opt-tiny": ModelConfig(n_layers=2, hidden=256, n_q_heads=4, n_kv_heads=4, ffn=1024, vocab=1024, head_dim=64,
+                            max_model_len=512, arch="opt"),
     "llama3-8b": ModelConfig(n_layers=32, hidden=4096, n_q_heads=32, n_kv_heads=8, ffn=14336, vocab=128256,
                              max_model_len=8192),
     "llama3-70b": ModelConfig(n_layers=80, hidden=8192, n_q_heads=64, n_kv_heads=8, ffn=28672, vocab=128256,
@@ -123,6 +131,9 @@ class NativeEngine:
             cfg.shm_name = shm_name.encode()
         cfg.use_cuda_graphs, cfg.debug_gemm_ref, cfg.seed = int(use_cuda_graphs), 1 if debug_gemm_ref else 0, seed
         cfg.max_loras, cfg.max_lora_rank = int(max_loras), int(max_lora_rank) if max_loras else 0
+        if model.arch not in ("llama", "opt"):
+            raise EngineError(f"unknown architecture {model.arch!r}")
+        cfg.arch = _lib.ARCH_OPT if model.arch == "opt" else _lib.ARCH_LLAMA
         self.max_loras, self.max_lora_rank = int(max_loras), int(max_lora_rank)
         self._h = C.c_void_p()
         if self.lib.tgis_engine_create(C.byref(cfg), C.byref(self._h)) != 0:

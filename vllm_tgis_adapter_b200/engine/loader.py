@@ -21,9 +21,11 @@ logger = logging.getLogger("vllm_tgis_adapter.engine")
 def model_config_from_hf(path: Path, max_model_len: int | None) -> ModelConfig:
     cfg = json.loads((path / "config.json").read_text())
     archs = cfg.get("architectures") or []
+    if cfg.get("model_type") == "opt" or any("OPT" in a for a in archs):
+        return _opt_model_config(cfg, max_model_len)
     if cfg.get("model_type") != "llama" and not any("Llama" in a for a in archs):
         raise ValueError(f"unsupported model architecture {archs or cfg.get('model_type')}: only Llama-family "
-                         "decoders (RMSNorm, RoPE, GQA, SwiGLU) are implemented")
+                         "decoders (RMSNorm, RoPE, GQA, SwiGLU) and OPT are implemented")
     hidden, heads = cfg["hidden_size"], cfg["num_attention_heads"]
     head_dim = cfg.get("head_dim") or hidden // heads
     if head_dim != 128:
@@ -37,6 +39,34 @@ def model_config_from_hf(path: Path, max_model_len: int | None) -> ModelConfig:
                        n_kv_heads=cfg.get("num_key_value_heads", heads), ffn=cfg["intermediate_size"],
                        vocab=cfg["vocab_size"], head_dim=head_dim, rope_theta=float(cfg.get("rope_theta", 10000.0)),
                        rms_eps=float(cfg.get("rms_norm_eps", 1e-5)), max_model_len=max_model_len or min(derived, 8192))
+
+
+def _opt_model_config(cfg: dict, max_model_len: int | None) -> ModelConfig:
+    """facebook/opt-* config.json -> ModelConfig(arch="opt").  The variants vLLM's OPT model handles with extra modules
+    (opt-350m: post-LayerNorm + project_in/out) are refused rather than silently mis-served."""
+    hidden, heads = cfg["hidden_size"], cfg["num_attention_heads"]
+    head_dim = hidden // heads
+    problems = []
+    if head_dim not in (64, 128):
+        problems.append(f"head_dim {head_dim} (64 or 128)")
+    if not cfg.get("do_layer_norm_before", True):
+        problems.append("do_layer_norm_before=false")
+    if cfg.get("word_embed_proj_dim", hidden) != hidden:
+        problems.append("word_embed_proj_dim != hidden_size")
+    if cfg.get("activation_function", "relu") != "relu":
+        problems.append(f"activation_function {cfg.get('activation_function')}")
+    if not cfg.get("enable_bias", True) or not cfg.get("layer_norm_elementwise_affine", True):
+        problems.append("enable_bias / layer_norm_elementwise_affine = false")
+    if cfg.get("_remove_final_layer_norm", False):
+        problems.append("_remove_final_layer_norm")
+    if problems:
+        raise ValueError("unsupported OPT variant: " + ", ".join(problems))
+    derived = cfg.get("max_position_embeddings", 2048)
+    if max_model_len is not None and max_model_len > derived:
+        raise ValueError(f"max_model_len {max_model_len} exceeds the model's max_position_embeddings {derived}")
+    return ModelConfig(n_layers=cfg["num_hidden_layers"], hidden=hidden, n_q_heads=heads, n_kv_heads=heads,
+                       ffn=cfg["ffn_dim"], vocab=cfg["vocab_size"], head_dim=head_dim, rms_eps=1e-5,  # nn.LayerNorm default
+                       max_model_len=max_model_len or derived, arch="opt")
 
 
 def rope_cos_sin(mc: ModelConfig):
@@ -56,6 +86,32 @@ def load_synthetic_weights(eng: NativeEngine, mc: ModelConfig, seed: int, device
 
     def rnd(r, c):
         return (torch.randn(r, c, generator=gen, device=f"cuda:{device}", dtype=torch.float32) * 0.02).to(torch.bfloat16)
+
+    if mc.arch == "opt":
+        # HF OPT parameter names; LayerNorm weights around 1, small random biases (HF's init has zeros: random ones exercise
+        # the bias paths).  lm_head is tied to embed_tokens (not loaded).
+        H = mc.hidden
+
+        def vec(n, s=0.02, base=0.0):
+            return (base + torch.randn(n, generator=gen, device=f"cuda:{device}", dtype=torch.float32) * s).to(torch.bfloat16)
+
+        eng.load_weight("model.decoder.embed_tokens.weight", rnd(mc.vocab, H))
+        eng.load_weight("model.decoder.embed_positions.weight", rnd(mc.max_model_len + 2, H))
+        eng.load_weight("model.decoder.final_layer_norm.weight", vec(H, 0.05, 1.0))
+        eng.load_weight("model.decoder.final_layer_norm.bias", vec(H))
+        for i in range(mc.n_layers):
+            p = f"model.decoder.layers.{i}."
+            for m in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                eng.load_weight(p + f"self_attn.{m}.weight", rnd(H, H))
+                eng.load_weight(p + f"self_attn.{m}.bias", vec(H))
+            eng.load_weight(p + "fc1.weight", rnd(mc.ffn, H))
+            eng.load_weight(p + "fc1.bias", vec(mc.ffn))
+            eng.load_weight(p + "fc2.weight", rnd(H, mc.ffn))
+            eng.load_weight(p + "fc2.bias", vec(H))
+            for ln in ("self_attn_layer_norm", "final_layer_norm"):
+                eng.load_weight(p + ln + ".weight", vec(H, 0.05, 1.0))
+                eng.load_weight(p + ln + ".bias", vec(H))
+        return
 
     q_dim, kv_dim = mc.n_q_heads * mc.head_dim, mc.n_kv_heads * mc.head_dim
     ones = torch.ones(mc.hidden, dtype=torch.bfloat16, device=f"cuda:{device}")
@@ -80,7 +136,15 @@ def load_safetensors_dir(eng: NativeEngine, path: Path) -> None:
 
     files = sorted(path.glob("*.safetensors"))
     if not files:
-        raise ValueError(f"no *.safetensors files under {path}")
+        bins = sorted(path.glob("pytorch_model*.bin"))   # facebook/opt-125m ships pytorch_model.bin
+        if not bins:
+            raise ValueError(f"no *.safetensors or pytorch_model*.bin files under {path}")
+        import torch
+
+        for f in bins:
+            for name, t in torch.load(str(f), map_location="cpu", weights_only=True).items():
+                eng.load_weight(name, t)
+        return
     for f in files:
         with safe_open(str(f), framework="pt", device="cpu") as sf:
             for name in sf.keys():  # noqa: SIM118
@@ -115,7 +179,8 @@ def _make_native_engine(args, mc: ModelConfig, path, device: int, **tp_kw) -> Na
         load_safetensors_dir(eng, path)      # full tensors: a tensor-parallel engine keeps its rank's shard
     else:
         load_synthetic_weights(eng, mc, args.seed, device)
-    eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
+    if mc.arch != "opt":   # OPT has learned positions (part of the checkpoint), no rotary table
+        eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
     return eng
 
 
