@@ -139,6 +139,8 @@ def cpu_reference(args, steps: int, warmup: int, budget_s: float | None = None) 
 
     import torch
 
+    if args.model.startswith("opt-"):
+        return cpu_reference_opt(args, steps, warmup, budget_s)
     from oracle.llama_oracle import CONFIGS, LlamaOracle, SeqState
 
     cfg_full = CONFIGS[args.model]
@@ -240,6 +242,47 @@ def cpu_reference(args, steps: int, warmup: int, budget_s: float | None = None) 
                       f"(oracle/llama_oracle.py), {threads} of {cores} threads",
             "ms_per_step": 1e3 * t_full, "sample_ms_per_step": 1e3 * t_step, "prefill_one_prompt_s": t_pf, "ttft_p50_est_ms": 1e3 * t_pf * (B + 1) / 2,
             "step_times_s": [round(t, 4) for t in times]}
+
+
+def cpu_reference_opt(args, steps: int, warmup: int, budget_s: float | None = None) -> dict:
+    """BASELINE configs[0] on the architecture it names (facebook/opt-125m dims, seeded random weights): the OPT oracle
+    (oracle/opt_oracle.py) timed IN FULL on the host cores -- all layers, the real prefill of every prompt, then real
+    batched decode steps with greedy sampling until gen_len tokens or the time budget; no extrapolation."""
+    import numpy as np
+    import torch
+
+    from oracle.opt_oracle import OPT_CONFIGS, OPTOracle, synthetic_opt_weights
+
+    cfg = OPT_CONFIGS[args.model]
+    cores = os.cpu_count() or 1
+    threads = int(os.environ.get("TGIS_CPU_THREADS", min(cores, 32)))
+    torch.set_num_threads(threads)
+    ora = OPTOracle(cfg, synthetic_opt_weights(cfg, seed=7))
+    B, P, G = args.batch, args.prompt_len, args.gen_len
+    rng = np.random.RandomState(1234)
+    prompts = [rng.randint(3, cfg.vocab, size=P).tolist() for _ in range(B)]
+    sts = [ora.new_seq() for _ in range(B)]
+    t0 = time.perf_counter()
+    toks, ttfts = [], []
+    for st, p in zip(sts, prompts):   # prompts served FIFO, one prefill each (the reference engine's CPU scheduler)
+        toks.append(int(torch.argmax(torch.log_softmax(ora.step([(st, p)])[0], -1))))
+        ttfts.append(time.perf_counter() - t0)
+    times = []
+    t_end = time.perf_counter() + (budget_s if budget_s else 1e9)
+    for it in range(G - 1):
+        t1 = time.perf_counter()
+        logits = ora.step([(st, [t]) for st, t in zip(sts, toks)])
+        toks = torch.argmax(torch.log_softmax(logits, -1), -1).tolist()
+        times.append(time.perf_counter() - t1)
+        if time.perf_counter() > t_end and len(times) >= max(3, steps):
+            break
+    t_step = statistics.median(times)
+    return {"value": B / t_step, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": f"{args.model} (all {cfg.n_layers} layers) B={B}: {P}-token prefill of every prompt + {len(times)} real "
+                      f"batched decode steps with greedy sampling, nothing extrapolated; torch CPU bfloat16 oracle "
+                      f"(oracle/opt_oracle.py), {threads} of {cores} threads",
+            "ms_per_step": 1e3 * t_step, "sample_ms_per_step": 1e3 * t_step, "prefill_one_prompt_s": ttfts[0],
+            "ttft_p50_est_ms": 1e3 * statistics.median(ttfts), "step_times_s": [round(t, 4) for t in times[:64]]}
 
 
 def ncu_traffic_per_launch(n_layers: int):

@@ -131,6 +131,7 @@ class OPTOracle:
                 "ln2": (w[p + "final_layer_norm.weight"], w[p + "final_layer_norm.bias"]),
             })
         self._lm_head_f32 = None
+        self._f32: dict[int, tuple[torch.Tensor, torch.Tensor]] = {}
 
     def _ln(self, x: torch.Tensor, wb: tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
         xf = x.float()
@@ -140,7 +141,12 @@ class OPTOracle:
         return y.to(self.dtype)
 
     def _linear(self, x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        return (x.float() @ w.float().t() + b.float()).to(self.dtype)
+        # fp32 copies of the (static) parameters are cached: same arithmetic, no per-step conversion of the weights
+        key = w.data_ptr()
+        if key not in self._f32:
+            self._f32[key] = (w.float().t().contiguous(), b.float())
+        wt, bf = self._f32[key]
+        return (x.float() @ wt + bf).to(self.dtype)
 
     def _attend(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, first_pos: int) -> torch.Tensor:
         s = torch.einsum("qhd,khd->hqk", q.float(), k.float()) * (self.cfg.head_dim ** -0.5)

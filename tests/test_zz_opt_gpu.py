@@ -29,7 +29,7 @@ def _p(t):
 
 
 # ---------------------------------------------------------------------------------------------------- kernels
-@pytest.mark.parametrize("T,H", [(1, 256), (37, 768), (300, 4096), (5, 8192)])
+@pytest.mark.parametrize("T,H", [(1, 256), (37, 768), (2048, 768), (300, 4096), (5, 8192)])
 @pytest.mark.parametrize("add", [False, True])
 def test_opt_layernorm_kernel_matches_torch_layernorm(T, H, add):
     lib = _lib()
@@ -58,7 +58,7 @@ def test_opt_layernorm_kernel_matches_torch_layernorm(T, H, add):
     assert float((d == 0).float().mean()) > 0.98
 
 
-@pytest.mark.parametrize("T,N,relu", [(1, 768, 0), (33, 3072, 1), (257, 4608, 0), (2048, 1024, 1)])
+@pytest.mark.parametrize("T,N,relu", [(1, 768, 0), (33, 3072, 1), (257, 4608, 0), (2048, 3072, 1)])
 def test_opt_bias_act_kernel_is_exact(T, N, relu):
     lib = _lib()
     g = torch.Generator(device="cuda").manual_seed(N + T)
@@ -88,6 +88,19 @@ def test_opt_embed_kernel_is_exact():
 
 
 # ---------------------------------------------------------------------------------------------------- engine
+def _record(name, stats):
+    """Parity statistics kept as evidence (copied into profiles/ after a GPU run)."""
+    import json
+    import os
+
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = "gpurun_out/parity_stats_opt.json"
+    allstats = json.load(open(path)) if os.path.exists(path) else {}
+    allstats[name] = stats
+    with open(path, "w") as f:
+        json.dump(allstats, f, indent=1)
+
+
 def _opt_cfg(name):
     from oracle.opt_oracle import OPT_CONFIGS
 
@@ -155,6 +168,9 @@ def test_opt_greedy_generation_matches_oracle(name, chunk, device):
             elif margin > 2 * ulp:
                 assert r.rank == orank == 1
     diffs = np.array(diffs)
+    _record(f"opt_greedy_{name}_{chunk}", {"steps": total, "token_flips": flips, "logprob_absdiff_ulps_max": float(diffs.max()),
+                                            "logprob_absdiff_ulps_mean": float(diffs.mean()),
+                                            "frac_identical": float((diffs == 0).mean())})
     assert flips <= max(1, total // 20), (flips, total)
     # same envelope as the Llama engine tests, in bf16 ulps of the logits: two independent stacks differ by whole ulps of
     # single logits wherever an upstream bf16 rounding lands on the other side of a tie

@@ -496,7 +496,7 @@ struct tgis_engine {
     if (opt) {
       pos_embed = take((size_t)pos_rows * H);
       final_norm_b = take(H);
-      identity_rope_table();  // no rotary embedding: rope_kvwrite_kernel degenerates to the paged-KV scatter
+      // no rotary embedding: cos_sin stays unused (zeroed with the arena)
     } else {
       default_rope_table();
     }
@@ -830,18 +830,6 @@ struct tgis_engine {
       shm->failed[rank].store(1, std::memory_order_release);
       throw;
     }
-  }
-
-  // OPT has no rotary embedding: cos = 1, sin = 0 makes every product of the rotation exact (x * 1 - y * 0 == x in bf16)
-  void identity_rope_table() {
-    const int half = HEAD_DIM / 2;
-    std::vector<bf16> tab((size_t)cfg.max_model_len * HEAD_DIM);
-    for (int pos = 0; pos < cfg.max_model_len; ++pos)
-      for (int i = 0; i < half; ++i) {
-        tab[(size_t)pos * HEAD_DIM + i] = __float2bfloat16_rn(1.0f);
-        tab[(size_t)pos * HEAD_DIM + half + i] = __float2bfloat16_rn(0.0f);
-      }
-    CK(cudaMemcpy(cos_sin, tab.data(), tab.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   }
 
   void default_rope_table() {
@@ -1291,7 +1279,7 @@ struct tgis_engine {
   // OPT layer stack (vllm model_executor/models/opt.py:170-197, do_layer_norm_before): the tcgen05 GEMMs write their fp32
   // accumulators (out mode 1) and the kernels of opt.cu add the bias before the single rounding to bf16; the paged
   // attention kernels run unchanged on zero-padded 128-dim heads with the model's softmax scale.  Per layer:
-  //   LN1 [+ previous fc2 bias/residual] -> qkv GEMM -> bias -> KV scatter -> attention -> out_proj GEMM ->
+  //   LN1 [+ previous fc2 bias/residual] -> qkv GEMM -> bias + KV scatter -> attention -> out_proj GEMM ->
   //   LN2 + out_proj bias/residual -> fc1 GEMM -> bias + ReLU -> fc2 GEMM;  final LayerNorm after the last layer.
   void opt_layers(int T, int n_dec, int n_tiles, int max_dec_kv, int S, int R) {
     const tgis_config& c = cfg;
@@ -1308,12 +1296,11 @@ struct tgis_engine {
       CK(opt_layernorm_launch(li == 0 ? nullptr : y32.p, li == 0 ? nullptr : layers[li - 1].b_fc2, resid.p, l.ln1, l.ln1_b,
                               xn.p, T, H, c.rms_eps, stream));
       gemm(xm_xn, l.m_qkv, xn.p, l.wqkv, y32.p, T, qkv_dim, H, /*out_f32=*/1, &l.m_o, T, H, q_dim);
-      CK(opt_bias_act_launch(y32.p, qkv_dim, l.b_qkv, qkv.p, qkv_dim, T, qkv_dim, /*relu=*/0, num_sms, stream));
       bf16* kc = k_cache.p + (size_t)li * kv_layer_elems;
       bf16* vc = v_cache.p + (size_t)li * kv_layer_elems;
-      // identity rotation table: this is the k / v scatter into the paged cache
-      CK(rope_kvwrite_launch(qkv.p, d_pos, ds<int32_t>(off_slotmap), cos_sin, kc, vc, T, nq, nkv, stream));
-      n_launches += 3;
+      // bias + rounding; q -> qkv buffer, k / v -> paged cache (no rotary embedding in between)
+      CK(opt_qkv_bias_kvwrite_launch(y32.p, l.b_qkv, qkv.p, ds<int32_t>(off_slotmap), kc, vc, T, nq, nkv, stream));
+      n_launches += 2;
       if (n_dec > 0) {
         const int max_splits = (max_dec_kv + DECODE_SPLIT - 1) / DECODE_SPLIT;
         CK(attn_decode_launch(qkv.p, qkv_dim, kc, vc, ds<DecItem>(items_off(S)), n_dec * max_splits, d_seqs,

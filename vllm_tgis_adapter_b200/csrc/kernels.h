@@ -148,6 +148,11 @@ cudaError_t opt_layernorm_launch(const float* acc, const __nv_bfloat16* acc_bias
 // out[t, n] = bf16(act(acc[t, n] + bias[n])), act = ReLU or identity
 cudaError_t opt_bias_act_launch(const float* acc, int ld_acc, const __nv_bfloat16* bias, __nv_bfloat16* out, int ld_out,
                                 int T, int N, int relu, int num_sms, cudaStream_t stream);
+// qkv epilogue: q_out[t, head, :] = bf16(acc + bias) for the q heads; k / v heads go straight into the paged cache
+// (slot_mapping[t] < 0: not cached).  acc fp32 [T, (n_q + 2 n_kv) * 128], q_out bf16 with the same row stride.
+cudaError_t opt_qkv_bias_kvwrite_launch(const float* acc, const __nv_bfloat16* bias, __nv_bfloat16* q_out,
+                                        const int32_t* slot_mapping, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int T,
+                                        int n_q, int n_kv, cudaStream_t stream);
 // gather rows: out[r, :] = x[rows[r], :]
 cudaError_t gather_rows_launch(const __nv_bfloat16* x, const int32_t* rows, __nv_bfloat16* out, int R, int hidden,
                                cudaStream_t stream);

@@ -170,7 +170,61 @@ opt_bias_act_kernel(const float* __restrict__ acc, int ld_acc, const __nv_bfloat
   }
 }
 
+// qkv projection epilogue of the OPT stack: bias add + the single rounding to bf16 (F.linear(x, W, b)) fused with the scatter of
+// the new k / v rows into the paged cache -- OPT has no rotary embedding, so nothing else happens between the projection and
+// the cache.  acc: fp32 [T, (n_q + 2 n_kv) * 128] (head slots, upper dims zero for 64-dim heads); q rows go to `q_out` with
+// the same row stride (the attention kernels read q from there), k / v rows straight into the cache layouts of
+// attention.cu (K: [chunk = d/8][token][8]; V: [token][16-byte chunk ^ (token & 7)][8]).
+// grid = (T, ceil(heads / 16)); 256 threads = 16 heads x 16 chunks of 8 dims; every access is a 16- or 32-byte vector.
+__global__ void __launch_bounds__(256)
+opt_qkv_bias_kvwrite_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ bias,
+                            __nv_bfloat16* __restrict__ q_out, const int32_t* __restrict__ slot_mapping,
+                            __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache, int n_q, int n_kv) {
+  griddep_launch();
+  const int t = blockIdx.x;
+  const int head = blockIdx.y * 16 + (threadIdx.x >> 4);
+  const int ch = threadIdx.x & 15;
+  const int n_heads = n_q + 2 * n_kv;
+  const bool live = head < n_heads;
+  const size_t col = (size_t)(live ? head : 0) * HEAD_DIM + (size_t)ch * 8;
+  const B8 bb = *reinterpret_cast<const B8*>(bias + col);  // static: before the dependency wait
+  griddep_wait();
+  if (!live) return;
+  const float* a = acc + (size_t)t * n_heads * HEAD_DIM + col;
+  const float4 a0 = reinterpret_cast<const float4*>(a)[0];
+  const float4 a1 = reinterpret_cast<const float4*>(a)[1];
+  const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  B8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = __float2bfloat16_rn(av[e] + __bfloat162float(bb.v[e]));
+  if (head < n_q) {
+    *reinterpret_cast<B8*>(q_out + (size_t)t * n_heads * HEAD_DIM + col) = o;
+    return;
+  }
+  const int slot = slot_mapping[t];
+  if (slot < 0) return;
+  const int blk = slot / KV_BLOCK, off = slot % KV_BLOCK;
+  if (head < n_q + n_kv) {
+    const int kvh = head - n_q;
+    B8* kb = reinterpret_cast<B8*>(k_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM));
+    kb[ch * KV_BLOCK + off] = o;
+  } else {
+    const int kvh = head - n_q - n_kv;
+    B8* vb = reinterpret_cast<B8*>(v_cache + ((size_t)blk * n_kv + kvh) * (KV_BLOCK * HEAD_DIM) + (size_t)off * HEAD_DIM);
+    vb[ch ^ (off & 7)] = o;
+  }
+}
+
 }  // namespace
+
+cudaError_t opt_qkv_bias_kvwrite_launch(const float* acc, const __nv_bfloat16* bias, __nv_bfloat16* q_out,
+                                        const int32_t* slot_mapping, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int T,
+                                        int n_q, int n_kv, cudaStream_t stream) {
+  if (T <= 0) return cudaSuccess;
+  const int n_heads = n_q + 2 * n_kv;
+  return launch_k(opt_qkv_bias_kvwrite_kernel, dim3(T, (n_heads + 15) / 16), dim3(256), 0, stream, acc, bias, q_out,
+                  slot_mapping, k_cache, v_cache, n_q, n_kv);
+}
 
 cudaError_t opt_embed_launch(const int32_t* token_ids, const int32_t* positions, const __nv_bfloat16* tok_table,
                              const __nv_bfloat16* pos_table, __nv_bfloat16* out, int T, int hidden, int vocab,
