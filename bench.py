@@ -722,7 +722,11 @@ def run_ours(args) -> dict | None:
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,0.02) weights, uniform random prompts)",
         "ttft_p50_ms": ttft_p50, "job_output_tokens_per_s": n_tok_s / wall_m,
         "config": {"workload": f"{args.model} bf16, {B} concurrent requests{'/GPU' if tp == 1 and world > 1 else ''}, "
-                               f"{P}-in/{G}-out, {args.sampling} (BASELINE.json configs[1])",
+                               f"{P}-in/{G}-out, {args.sampling} (BASELINE.json "
+                               + ("configs[1])" if args.model == "llama3-8b" and B == 32 and args.sampling == "greedy" else
+                                  "configs[0]: the 125m-class single greedy request)" if B == 1 and args.model in ("125m", "opt-125m")
+                                  else "configs[2])" if args.model == "llama3-8b" and B == 64 and args.sampling == "cfg3"
+                                  else "shape, not a named config)"),
                    "batch": B, "prompt_len": P, "gen_len": G,
                    "parallelism": (f"tp{tp} (ONE engine over {tp} GPUs: column-parallel qkv/gate_up, row-parallel o/down "
                                    f"with a fused push all-reduce + residual + RMSNorm kernel over NVLink peer memory, "

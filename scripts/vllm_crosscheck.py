@@ -49,10 +49,41 @@ def configs():
     from oracle.llama_oracle import CONFIGS
 
     c = dict(CONFIGS)
+    # OPT family (the reference's own test model is facebook/opt-125m): its dims in full depth, and the CPU-suite sibling
+    from oracle.opt_oracle import OPT_CONFIGS
+
+    c["opt-tiny"] = OPT_CONFIGS["opt-tiny"]
+    c["opt-125m"] = dataclasses.replace(OPT_CONFIGS["opt-125m"], max_model_len=1024)
     # Llama-3-8B dims (hidden 4096, 32/8 heads, ffn 14336, V 128256), 2 layers: BASELINE shapes at a size the CPU
     # oracle and a fixture can carry
     c["8b2l"] = dataclasses.replace(CONFIGS["llama3-8b"], n_layers=2, max_model_len=1024)
     return c
+
+
+def is_opt(cfg_name: str) -> bool:
+    return cfg_name.startswith("opt-")
+
+
+def make_engine(cfg_name: str):
+    """This repo's engine over the checkpoint directory vLLM loads.  OPT goes through the product loader end to end
+    (config.json -> ModelConfig(arch="opt"), HF parameter names -> the engine's head-padded layout)."""
+    from vllm_tgis_adapter_b200.engine.core import ModelConfig, NativeEngine
+    from vllm_tgis_adapter_b200.engine.loader import load_safetensors_dir, model_config_from_hf, rope_cos_sin
+
+    cfg = configs()[cfg_name]
+    d = make_model_dir(cfg_name)
+    if is_opt(cfg_name):
+        mc = model_config_from_hf(d, cfg.max_model_len)
+        eng = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=2048, kv_cache_bytes=1 << 30)
+        load_safetensors_dir(eng, d)
+        return eng
+    mc = ModelConfig(n_layers=cfg.n_layers, hidden=cfg.hidden, n_q_heads=cfg.n_q_heads, n_kv_heads=cfg.n_kv_heads,
+                     ffn=cfg.ffn, vocab=cfg.vocab, rope_theta=cfg.rope_theta, rms_eps=cfg.rms_eps,
+                     max_model_len=cfg.max_model_len)
+    eng = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=2048, kv_cache_bytes=256 << 20)
+    load_safetensors_dir(eng, d)
+    eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
+    return eng
 
 
 def request_sets(cfg_name: str, vocab: int) -> dict:
@@ -82,6 +113,24 @@ def make_model_dir(cfg_name: str) -> Path:
     if (d / "model.safetensors").exists() and (d / "config.json").exists():
         return d
     d.mkdir(parents=True, exist_ok=True)
+    if is_opt(cfg_name):
+        from oracle.opt_oracle import synthetic_opt_weights
+
+        hf = {   # the keys of facebook/opt-125m's config.json
+            "architectures": ["OPTForCausalLM"], "model_type": "opt", "torch_dtype": "bfloat16", "dtype": "bfloat16",
+            "vocab_size": cfg.vocab, "hidden_size": cfg.hidden, "ffn_dim": cfg.ffn, "num_hidden_layers": cfg.n_layers,
+            "num_attention_heads": cfg.n_heads, "max_position_embeddings": cfg.max_positions,
+            "word_embed_proj_dim": cfg.hidden, "do_layer_norm_before": True, "activation_function": "relu",
+            "enable_bias": True, "layer_norm_elementwise_affine": True, "_remove_final_layer_norm": False,
+            "dropout": 0.0, "attention_dropout": 0.0, "layerdrop": 0.0, "init_std": 0.02, "tie_word_embeddings": True,
+            "bos_token_id": 1, "eos_token_id": EOS, "pad_token_id": 0, "prefix": "</s>", "use_cache": True,
+        }
+        (d / "config.json").write_text(json.dumps(hf, indent=1))
+        (d / "generation_config.json").write_text(json.dumps({"bos_token_id": 1, "eos_token_id": EOS, "do_sample": False}))
+        w = synthetic_opt_weights(cfg, seed=WEIGHT_SEED)
+        save_file({k: v.contiguous() for k, v in w.items()}, str(d / "model.safetensors"), metadata={"format": "pt"})
+        build_synthetic_tokenizer(cfg.vocab).save_pretrained(str(d))
+        return d
     hf = {
         "architectures": ["LlamaForCausalLM"], "model_type": "llama", "torch_dtype": "bfloat16", "dtype": "bfloat16",
         "vocab_size": cfg.vocab, "hidden_size": cfg.hidden, "intermediate_size": cfg.ffn,
@@ -217,18 +266,11 @@ def vllm_run(cfg_name: str, out_path: str) -> None:
 
 # ======================================================================================================== our side
 def engine_run(cfg_name: str) -> dict:
-    from vllm_tgis_adapter_b200.engine.core import ModelConfig, NativeEngine, make_sampling_params
-    from vllm_tgis_adapter_b200.engine.loader import load_safetensors_dir, rope_cos_sin
+    from vllm_tgis_adapter_b200.engine.core import make_sampling_params
 
     cfg = configs()[cfg_name]
-    d = make_model_dir(cfg_name)
     rs = request_sets(cfg_name, cfg.vocab)
-    mc = ModelConfig(n_layers=cfg.n_layers, hidden=cfg.hidden, n_q_heads=cfg.n_q_heads, n_kv_heads=cfg.n_kv_heads,
-                     ffn=cfg.ffn, vocab=cfg.vocab, rope_theta=cfg.rope_theta, rms_eps=cfg.rms_eps,
-                     max_model_len=cfg.max_model_len)
-    eng = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=2048, kv_cache_bytes=256 << 20)
-    load_safetensors_dir(eng, d)
-    eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
+    eng = make_engine(cfg_name)
 
     def entry(r):
         return {"logprob": r.logprob, "rank": r.rank, "top": [[t, l, i + 1] for i, (t, l) in enumerate(r.topn)]}
@@ -261,17 +303,9 @@ def engine_run(cfg_name: str) -> dict:
 
 def engine_teacher_forced(cfg_name: str, seqs: list[list[int]], n_prompt: list[int]) -> list[list[dict]]:
     """logprob / rank of tokens seqs[i][n_prompt[i]:] given their prefix, through the engine's prompt-logprob pass."""
-    from vllm_tgis_adapter_b200.engine.core import ModelConfig, NativeEngine, make_sampling_params
-    from vllm_tgis_adapter_b200.engine.loader import load_safetensors_dir, rope_cos_sin
+    from vllm_tgis_adapter_b200.engine.core import make_sampling_params
 
-    cfg = configs()[cfg_name]
-    d = make_model_dir(cfg_name)
-    mc = ModelConfig(n_layers=cfg.n_layers, hidden=cfg.hidden, n_q_heads=cfg.n_q_heads, n_kv_heads=cfg.n_kv_heads,
-                     ffn=cfg.ffn, vocab=cfg.vocab, rope_theta=cfg.rope_theta, rms_eps=cfg.rms_eps,
-                     max_model_len=cfg.max_model_len)
-    eng = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=2048, kv_cache_bytes=256 << 20)
-    load_safetensors_dir(eng, d)
-    eng.load_weight("tgis.rope_cos_sin", rope_cos_sin(mc))
+    eng = make_engine(cfg_name)
     sp = make_sampling_params(greedy=True, max_tokens=1, num_logprobs=1, prompt_logprobs=1, eos_token_id=EOS)
     outs = eng.generate_sync(seqs, sp)
     eng.close()
@@ -290,8 +324,13 @@ def oracle_run(cfg_name: str, vllm_res: dict) -> dict:
     from oracle.llama_oracle import LlamaOracle, synthetic_weights
 
     cfg = configs()[cfg_name]
-    w = synthetic_weights(cfg, seed=WEIGHT_SEED)
-    ora = LlamaOracle(cfg, w)
+    if is_opt(cfg_name):
+        from oracle.opt_oracle import OPTOracle, synthetic_opt_weights
+
+        ora = OPTOracle(cfg, synthetic_opt_weights(cfg, seed=WEIGHT_SEED))
+    else:
+        w = synthetic_weights(cfg, seed=WEIGHT_SEED)
+        ora = LlamaOracle(cfg, w)
     rs = request_sets(cfg_name, cfg.vocab)
     torch.set_num_threads(min(32, os.cpu_count() or 8))
     greedy = []
@@ -452,7 +491,8 @@ def cmd_check(args) -> None:
         # only gpurun_out/ travels back from the GPU box: the fixture is copied from there into tests/golden/ and committed
         (outdir / "golden").mkdir(exist_ok=True)
         (outdir / "golden" / f"vllm_{name}.json").write_text(json.dumps(_round(fx)))
-        (outdir / "vllm_crosscheck.json").write_text(json.dumps(summary, indent=1))
+        tag = "_opt" if all(is_opt(n) for n in args.configs) else ""
+        (outdir / f"vllm_crosscheck{tag}.json").write_text(json.dumps(summary, indent=1))
     print(json.dumps(summary, indent=1))
 
 

@@ -6,6 +6,7 @@ import json
 from pathlib import Path
 
 import numpy as np
+import pytest
 import torch
 
 from oracle.opt_oracle import OPT_CONFIGS, OPTOracle, synthetic_opt_weights
@@ -109,3 +110,54 @@ def test_loader_maps_opt_config_json_and_refuses_unsupported_variants(tmp_path):
     (tmp_path / "config.json").write_text(json.dumps(opt350m))
     with pytest.raises(ValueError, match="unsupported OPT variant"):
         model_config_from_hf(tmp_path, None)
+
+
+def _vllm_request_sets(vocab):
+    rng = np.random.RandomState(0)
+    greedy = [rng.randint(3, vocab, size=n).tolist() for n in (5, 33, 64, 100, 17, 250)]
+    rng = np.random.RandomState(7)
+    plp = [rng.randint(3, vocab, size=96).tolist() for _ in range(4)]
+    return greedy, plp
+
+
+@pytest.mark.parametrize("name,top_logit", [("opt-tiny", 1.0), ("opt-125m", 2.0)])
+def test_opt_oracle_matches_vllm_fixture(name, top_logit):
+    """The OPT oracle against the reference's REAL engine path: vLLM 0.22.0 (its own OPTForCausalLM, FlashInfer) on a B200
+    over the same seeded checkpoint and requests (tests/golden/vllm_<name>.json, scripts/vllm_crosscheck.py check --configs
+    opt-tiny opt-125m).  Teacher-forced on vLLM's tokens, in bf16 ulps of the logits, like the Llama fixtures."""
+    import math
+
+    path = GOLD / f"vllm_{name}.json"
+    if not path.exists():
+        pytest.skip(f"{path.name} not generated yet (scripts/vllm_crosscheck.py check on the GPU box)")
+    fx = json.loads(path.read_text())
+    cfg = dataclasses.replace(OPT_CONFIGS[name], max_model_len=1024) if name == "opt-125m" else OPT_CONFIGS[name]
+    ora = OPTOracle(cfg, synthetic_opt_weights(cfg, seed=fx["meta"]["weights_seed"]))
+    u = 2.0 ** (math.floor(math.log2(top_logit)) - 7)
+    greedy, plp = _vllm_request_sets(cfg.vocab)
+    diffs, flips_ok, steps = [], 0, 0
+    for p, v in zip(greedy, fx["greedy"]):
+        st = ora.new_seq()
+        logits = ora.step([(st, p)])[0]
+        for tok, vs in zip(v["tokens"], v["steps"]):
+            lp = torch.log_softmax(logits, -1)
+            top = sorted(vs["top"], key=lambda t: -t[1])
+            margin = top[0][1] - top[1][1]
+            diffs.append(abs(float(lp[tok]) - vs["logprob"]))
+            steps += 1
+            if int(torch.argmax(logits)) != tok:
+                assert margin <= 2 * u + 1e-6, (name, margin)
+                flips_ok += 1
+            elif margin > 2 * u:
+                assert int((lp >= lp[tok]).sum()) == vs["rank"]
+            logits = ora.step([(st, [tok])])[0]
+    diffs = np.array(diffs)
+    assert float(diffs.max()) <= 3 * u + 1e-4 and float(diffs.mean()) <= 0.6 * u, (float(diffs.max()), float(diffs.mean()))
+    assert flips_ok <= steps // 10
+    pd = []
+    for p, v in zip(plp, fx["plp"]):
+        lp = torch.log_softmax(ora.step([(ora.new_seq(), p)], want_all_logits=True), -1)
+        for i, vp in zip(range(1, len(p)), v["positions"]):
+            pd.append(abs(float(lp[i - 1, p[i]]) - vp["logprob"]))
+    pd = np.array(pd)
+    assert float(pd.max()) <= 3 * u + 1e-4 and float(pd.mean()) <= 0.6 * u, (float(pd.max()), float(pd.mean()))

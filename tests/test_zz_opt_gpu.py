@@ -53,8 +53,11 @@ def test_opt_layernorm_kernel_matches_torch_layernorm(T, H, add):
     assert torch.equal(resid, h)                       # residual stream: bit-exact
     d = (out.float() - ref.float()).abs()
     # fp32 reductions in a different order than torch's: a result may land on the other side of a bf16 rounding tie
-    ulp = 2.0 ** (torch.floor(torch.log2(ref.float().abs().clamp_min(1e-30))) - 7)
-    assert bool((d <= ulp).all()), float((d / ulp).max())
+    # (ulp of the larger of the two: a pair that straddles a power of two is one ulp of the upper binade apart)
+    ulp = 2.0 ** (torch.floor(torch.log2(torch.maximum(ref.float().abs(), out.float().abs()).clamp_min(1e-30))) - 7)
+    # ... and an output next to zero is a cancellation of two terms of size ~|b|: there the fp32 noise of the terms (not
+    # the bf16 grid of the tiny result) bounds the difference
+    assert bool(((d <= ulp) | (d <= 1e-6)).all()), float((d / ulp).max())
     assert float((d == 0).float().mean()) > 0.98
 
 
@@ -240,6 +243,80 @@ def test_opt_engine_refuses_what_it_does_not_implement():
     with pytest.raises(EngineError, match="head_dim"):
         NativeEngine(ModelConfig(**{**base, "head_dim": 32, "n_q_heads": 8, "n_kv_heads": 8}), max_num_seqs=2,
                      max_batched_tokens=64, kv_cache_bytes=8 << 20)
+
+
+@pytest.mark.parametrize("name,top_logit", [("opt-tiny", 1.0), ("opt-125m", 2.0)])
+def test_opt_engine_matches_vllm_fixture(name, top_logit):
+    """Engine (C ABI) vs what vLLM 0.22.0's own OPT implementation produced on a B200 for the same seeded checkpoint and
+    requests (tests/golden/vllm_<name>.json from scripts/vllm_crosscheck.py check --configs opt-tiny opt-125m): vLLM's
+    greedy continuations scored by the engine's prompt-logprob pass (every step compared, teacher-forced), vLLM's prompt
+    logprobs, and the free-running greedy prefix.  In bf16 ulps of the logits, like the Llama fixtures."""
+    import json
+    import math
+    from pathlib import Path
+
+    from oracle.opt_oracle import OPT_CONFIGS, synthetic_opt_weights
+    from vllm_tgis_adapter_b200.engine.core import ModelConfig, NativeEngine, make_sampling_params
+
+    path = Path(__file__).resolve().parent / "golden" / f"vllm_{name}.json"
+    if not path.exists():
+        pytest.skip(f"{path.name} not generated yet (scripts/vllm_crosscheck.py check on the GPU box)")
+    fx = json.loads(path.read_text())
+    cfg = dataclasses.replace(OPT_CONFIGS[name], max_model_len=1024) if name == "opt-125m" else OPT_CONFIGS[name]
+    weights = synthetic_opt_weights(cfg, seed=fx["meta"]["weights_seed"])
+    u = 2.0 ** (math.floor(math.log2(top_logit)) - 7)
+    rng = np.random.RandomState(0)
+    greedy = [rng.randint(3, cfg.vocab, size=n).tolist() for n in (5, 33, 64, 100, 17, 250)]
+    rng = np.random.RandomState(7)
+    plp = [rng.randint(3, cfg.vocab, size=96).tolist() for _ in range(4)]
+    mc = ModelConfig(n_layers=cfg.n_layers, hidden=cfg.hidden, n_q_heads=cfg.n_heads, n_kv_heads=cfg.n_heads, ffn=cfg.ffn,
+                     vocab=cfg.vocab, head_dim=cfg.head_dim, rms_eps=cfg.ln_eps, max_model_len=cfg.max_model_len,
+                     arch="opt")
+    eng = NativeEngine(mc, max_num_seqs=16, max_batched_tokens=2048, kv_cache_bytes=1 << 30)
+    eng.load_weights(weights)
+    # free-running greedy: identical to vLLM's tokens up to the first near-tie
+    n_new = len(fx["greedy"][0]["tokens"])
+    sp = make_sampling_params(greedy=True, max_tokens=n_new, min_tokens=n_new, num_logprobs=3, eos_token_id=2)
+    outs = eng.generate_sync(greedy, sp)
+    compared = 0
+    for recs, v in zip(outs, fx["greedy"]):
+        recs = [r for r in recs if r.new_token is not None]
+        for r, vt, vs in zip(recs, v["tokens"], v["steps"]):
+            top = sorted(vs["top"], key=lambda t: -t[1])
+            if r.new_token != vt:
+                assert top[0][1] - top[1][1] <= 2 * u + 1e-6
+                break
+            compared += 1
+    # teacher-forced on vLLM's continuations
+    seqs = [p + v["tokens"] for p, v in zip(greedy, fx["greedy"])]
+    sp = make_sampling_params(greedy=True, max_tokens=1, num_logprobs=1, prompt_logprobs=1, eos_token_id=2)
+    outs = eng.generate_sync(seqs, sp)
+    tf, argmax_bad = [], 0
+    for p, v, recs in zip(greedy, fx["greedy"], outs):
+        pos = {r.prompt_pos: r for r in recs if r.prompt_pos >= 1}
+        for k, (vt, vs) in enumerate(zip(v["tokens"], v["steps"])):
+            r = pos[len(p) + k]
+            tf.append(abs(r.logprob - vs["logprob"]))
+            top = sorted(vs["top"], key=lambda t: -t[1])
+            if top[0][1] - top[1][1] > 2 * u:
+                argmax_bad += int(r.topn[0][0] != vt)
+    sp = make_sampling_params(greedy=True, max_tokens=1, num_logprobs=2, prompt_logprobs=2, eos_token_id=2)
+    outs = eng.generate_sync(plp, sp)
+    pd = []
+    for p, recs, v in zip(plp, outs, fx["plp"]):
+        pos = {r.prompt_pos: r for r in recs if r.prompt_pos >= 1}
+        for i, vp in zip(range(1, len(p)), v["positions"]):
+            pd.append(abs(pos[i].logprob - vp["logprob"]))
+    eng.close()
+    tf, pd = np.array(tf), np.array(pd)
+    _record(f"opt_vllm_fixture_{name}", {"free_running_steps_identical": compared, "teacher_forced_steps": int(tf.size),
+                                         "tf_absdiff_ulps_max": float(tf.max() / u), "tf_absdiff_ulps_mean": float(tf.mean() / u),
+                                         "tf_argmax_mismatch_off_ties": argmax_bad, "prompt_positions": int(pd.size),
+                                         "plp_absdiff_ulps_max": float(pd.max() / u), "plp_absdiff_ulps_mean": float(pd.mean() / u)})
+    assert tf.size == sum(len(v["tokens"]) for v in fx["greedy"]) and argmax_bad == 0
+    assert float(tf.max()) <= 3 * u + 1e-4 and float(tf.mean()) <= 0.6 * u, (float(tf.max()), float(tf.mean()), u)
+    assert float(pd.max()) <= 4 * u + 1e-4 and float(pd.mean()) <= 0.6 * u, (float(pd.max()), float(pd.mean()), u)
+    assert compared >= 0.5 * sum(len(v["tokens"]) for v in fx["greedy"]), compared
 
 
 # ---------------------------------------------------------------------------------------------------- gRPC (configs[0])

@@ -89,7 +89,10 @@ cudaError_t gather_rows_launch(const __nv_bfloat16* x, const int32_t* rows, __nv
 constexpr int NORM_THREADS = 256;
 constexpr int NORM_MAX_VEC = 4;  // hidden <= 256 * 8 * 4 = 8192
 
-template <bool ADD>
+// NORM_MAX_VEC (vectors per thread) is a template parameter: the row lives in registers, and the 8192-wide instantiation's
+// 80 registers cap a prefill chunk at 3 CTAs per SM; hidden = 4096 needs two vectors per thread.  Same thread -> element
+// map and the same reduction tree for every instantiation: results do not depend on it.
+template <bool ADD, int NORM_MAX_VEC>
 __global__ void __launch_bounds__(NORM_THREADS)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int hidden, float eps) {
@@ -151,14 +154,23 @@ cudaError_t rmsnorm_launch(const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_
                            float eps, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   if (hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
-  return launch_k(rmsnorm_kernel<false>, dim3(T), dim3(NORM_THREADS), 0, stream, x, (__nv_bfloat16*)nullptr, w, out, hidden, eps);
+  __nv_bfloat16* none = nullptr;
+  if (hidden <= NORM_THREADS * 8)
+    return launch_k(rmsnorm_kernel<false, 1>, dim3(T), dim3(NORM_THREADS), 0, stream, x, none, w, out, hidden, eps);
+  if (hidden <= NORM_THREADS * 16)
+    return launch_k(rmsnorm_kernel<false, 2>, dim3(T), dim3(NORM_THREADS), 0, stream, x, none, w, out, hidden, eps);
+  return launch_k(rmsnorm_kernel<false, 4>, dim3(T), dim3(NORM_THREADS), 0, stream, x, none, w, out, hidden, eps);
 }
 
 cudaError_t add_rmsnorm_launch(const __nv_bfloat16* x, __nv_bfloat16* residual, const __nv_bfloat16* w,
                                __nv_bfloat16* out, int T, int hidden, float eps, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
   if (hidden % 8 != 0 || hidden > NORM_THREADS * 8 * NORM_MAX_VEC) return cudaErrorInvalidValue;
-  return launch_k(rmsnorm_kernel<true>, dim3(T), dim3(NORM_THREADS), 0, stream, x, residual, w, out, hidden, eps);
+  if (hidden <= NORM_THREADS * 8)
+    return launch_k(rmsnorm_kernel<true, 1>, dim3(T), dim3(NORM_THREADS), 0, stream, x, residual, w, out, hidden, eps);
+  if (hidden <= NORM_THREADS * 16)
+    return launch_k(rmsnorm_kernel<true, 2>, dim3(T), dim3(NORM_THREADS), 0, stream, x, residual, w, out, hidden, eps);
+  return launch_k(rmsnorm_kernel<true, 4>, dim3(T), dim3(NORM_THREADS), 0, stream, x, residual, w, out, hidden, eps);
 }
 
 // ------------------------------------------------------------------------------------------------ TP: fused exchange

@@ -29,15 +29,18 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 
-constexpr int LN_THREADS = 256;
-constexpr int LN_MAX_VEC = 4;  // hidden <= 256 * 8 * 4 = 8192
-
+// Row geometry by hidden size: THREADS threads x NVEC 16-byte vectors each.  The per-thread state (row values in fp32, the
+// affine parameters, the projection bias) lives in registers, so NVEC is as small as the row allows: the 8192-wide
+// instantiation needs 117 registers (2 CTAs of 256 threads per SM), the <= 2048-wide ones 40.  Measured on the first version
+// (one 256 x 4 instantiation for every width, profiles/r02_ncu_opt_v1.csv): a 2048-row prefill chunk of opt-125m
+// (hidden 768: 96 of 256 threads busy, seven waves of CTAs) took 17.3 us for 15.7 MB.
+template <int THREADS>
 __device__ __forceinline__ float bsum(float v, float* red) {
   v = wsum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) red[w] = v;
   __syncthreads();
-  float t = (l < LN_THREADS / 32) ? red[l] : 0.f;
+  float t = (l < THREADS / 32) ? red[l] : 0.f;
   t = wsum(t);
   __syncthreads();
   return t;
@@ -71,7 +74,7 @@ opt_embed_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ po
 //   y = bf16(acc + acc_bias)   (the projection's output in the model dtype)
 //   h = bf16(residual + y)     (residual add in the model dtype), written back to `residual`
 // then out = bf16((h - mean) * rstd * w + b) with fp32 statistics over the bf16 values of h.
-template <bool ADD>
+template <bool ADD, int LN_THREADS, int LN_MAX_VEC>
 __global__ void __launch_bounds__(LN_THREADS)
 opt_layernorm_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ acc_bias,
                      __nv_bfloat16* __restrict__ residual, const __nv_bfloat16* __restrict__ w,
@@ -117,7 +120,7 @@ opt_layernorm_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restr
       }
     }
   }
-  const float mean = bsum(s, red) / (float)hidden;
+  const float mean = bsum<LN_THREADS>(s, red) / (float)hidden;
   float q = 0.f;
 #pragma unroll
   for (int j = 0; j < LN_MAX_VEC; ++j) {
@@ -130,7 +133,7 @@ opt_layernorm_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restr
       }
     }
   }
-  const float rstd = rsqrtf(bsum(q, red) / (float)hidden + eps);
+  const float rstd = rsqrtf(bsum<LN_THREADS>(q, red) / (float)hidden + eps);
 #pragma unroll
   for (int j = 0; j < LN_MAX_VEC; ++j) {
     const int i = threadIdx.x + j * LN_THREADS;
@@ -235,16 +238,26 @@ cudaError_t opt_embed_launch(const int32_t* token_ids, const int32_t* positions,
                   vocab, n_pos_rows, offset);
 }
 
+template <int THREADS, int NVEC>
+static cudaError_t layernorm_launch_g(const float* acc, const __nv_bfloat16* acc_bias, __nv_bfloat16* residual,
+                                      const __nv_bfloat16* w, const __nv_bfloat16* b, __nv_bfloat16* out, int T, int hidden,
+                                      float eps, cudaStream_t stream) {
+  if (acc != nullptr)
+    return launch_k(opt_layernorm_kernel<true, THREADS, NVEC>, dim3(T), dim3(THREADS), 0, stream, acc, acc_bias, residual, w,
+                    b, out, hidden, eps);
+  return launch_k(opt_layernorm_kernel<false, THREADS, NVEC>, dim3(T), dim3(THREADS), 0, stream, (const float*)nullptr,
+                  (const __nv_bfloat16*)nullptr, residual, w, b, out, hidden, eps);
+}
+
 cudaError_t opt_layernorm_launch(const float* acc, const __nv_bfloat16* acc_bias, __nv_bfloat16* residual,
                                  const __nv_bfloat16* w, const __nv_bfloat16* b, __nv_bfloat16* out, int T, int hidden,
                                  float eps, cudaStream_t stream) {
   if (T <= 0) return cudaSuccess;
-  if (hidden % 8 != 0 || hidden > LN_THREADS * 8 * LN_MAX_VEC) return cudaErrorInvalidValue;
-  if (acc != nullptr)
-    return launch_k(opt_layernorm_kernel<true>, dim3(T), dim3(LN_THREADS), 0, stream, acc, acc_bias, residual, w, b, out,
-                    hidden, eps);
-  return launch_k(opt_layernorm_kernel<false>, dim3(T), dim3(LN_THREADS), 0, stream, (const float*)nullptr,
-                  (const __nv_bfloat16*)nullptr, residual, w, b, out, hidden, eps);
+  if (hidden % 8 != 0 || hidden > 8192) return cudaErrorInvalidValue;
+  if (hidden <= 1024) return layernorm_launch_g<128, 1>(acc, acc_bias, residual, w, b, out, T, hidden, eps, stream);
+  if (hidden <= 2048) return layernorm_launch_g<256, 1>(acc, acc_bias, residual, w, b, out, T, hidden, eps, stream);
+  if (hidden <= 4096) return layernorm_launch_g<256, 2>(acc, acc_bias, residual, w, b, out, T, hidden, eps, stream);
+  return layernorm_launch_g<256, 4>(acc, acc_bias, residual, w, b, out, T, hidden, eps, stream);
 }
 
 cudaError_t opt_bias_act_launch(const float* acc, int ld_acc, const __nv_bfloat16* bias, __nv_bfloat16* out, int ld_out,
