@@ -243,6 +243,18 @@ def test_opt_engine_refuses_what_it_does_not_implement():
     with pytest.raises(EngineError, match="head_dim"):
         NativeEngine(ModelConfig(**{**base, "head_dim": 32, "n_q_heads": 8, "n_kv_heads": 8}), max_num_seqs=2,
                      max_batched_tokens=64, kv_cache_bytes=8 << 20)
+    # a checkpoint with tensors missing must fail at start-up, not serve zeros
+    from oracle.opt_oracle import OPTConfig, synthetic_opt_weights
+
+    w = synthetic_opt_weights(OPTConfig(n_layers=1, hidden=256, n_heads=4, ffn=512, vocab=1024, max_positions=128,
+                                        max_model_len=128), seed=1)
+    eng = NativeEngine(ModelConfig(**base), max_num_seqs=2, max_batched_tokens=64, kv_cache_bytes=8 << 20)
+    for k, v in w.items():
+        if not k.endswith("fc2.bias"):
+            eng.load_weight(k, v)
+    with pytest.raises(EngineError, match="incomplete"):
+        eng.start()
+    eng.close()
 
 
 @pytest.mark.parametrize("name,top_logit", [("opt-tiny", 1.0), ("opt-125m", 2.0)])

@@ -10,6 +10,7 @@
 //       All per-step metadata is packed into ONE pinned staging buffer and shipped with ONE H2D copy; results come
 //       back with ONE D2H copy of SampleOut records.
 #include <algorithm>
+#include <set>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -230,6 +231,7 @@ struct tgis_engine {
   int pos_rows = 0, model_head_dim = HEAD_DIM;
   float attn_scale = 0.f;
   DevBuf<float> y32;
+  std::set<std::string> opt_loaded;  // tensor names seen by load_weight_opt (completeness check at start)
   std::vector<LayerW> layers;
   CUtensorMap m_lm{};
   // kv cache
@@ -874,6 +876,7 @@ struct tgis_engine {
     if (name == "lm_head.weight") { lm_head_loaded = true; return copy(lm_head, V * H); }
     if (name.rfind("decoder.", 0) != 0) return fail("unknown weight " + full_name);
     name = name.substr(8);
+    opt_loaded.insert(name);  // (a failed copy fails the load as a whole)
     if (name == "embed_tokens.weight") return copy(embed, V * H);
     if (name == "embed_positions.weight") {
       // the checkpoint's table covers max_position_embeddings + 2 rows; the engine keeps what max_model_len can reach
@@ -1046,6 +1049,13 @@ struct tgis_engine {
   }
 
   void finalize_weights() {
+    if (opt) {
+      // an OPT checkpoint with a tensor missing must not come up healthy on zeros (the reference's engine fails the load)
+      const size_t expected = 4 + (size_t)16 * cfg.n_layers;
+      if (opt_loaded.size() < expected)
+        throw CudaError("OPT checkpoint incomplete: " + std::to_string(opt_loaded.size()) + " of " + std::to_string(expected) +
+                        " tensors loaded (embed_tokens, embed_positions, final_layer_norm.{weight,bias} and 16 per layer)");
+    }
     if (!lm_head_loaded)  // tie_word_embeddings
       CK(cudaMemcpy(lm_head, embed + (size_t)rank * Vl * cfg.hidden, (size_t)Vl * cfg.hidden * sizeof(bf16),
                     cudaMemcpyDeviceToDevice));
