@@ -161,3 +161,28 @@ def test_opt_oracle_matches_vllm_fixture(name, top_logit):
             pd.append(abs(float(lp[i - 1, p[i]]) - vp["logprob"]))
     pd = np.array(pd)
     assert float(pd.max()) <= 3 * u + 1e-4 and float(pd.mean()) <= 0.6 * u, (float(pd.max()), float(pd.mean()))
+
+
+def test_loader_streams_a_pytorch_model_bin_directory(tmp_path):
+    """facebook/opt-125m ships `pytorch_model.bin` (no safetensors): the loader must stream it tensor by tensor under the
+    checkpoint's own names, and refuse a directory with neither format."""
+    from vllm_tgis_adapter_b200.engine.loader import load_safetensors_dir
+
+    class Recorder:
+        def __init__(self):
+            self.seen = {}
+
+        def load_weight(self, name, t):
+            self.seen[name] = tuple(t.shape)
+
+    cfg = OPT_CONFIGS["opt-tiny"]
+    w = synthetic_opt_weights(cfg, seed=3)
+    torch.save({**w, "lm_head.weight": w["model.decoder.embed_tokens.weight"]}, tmp_path / "pytorch_model.bin")
+    rec = Recorder()
+    load_safetensors_dir(rec, tmp_path)
+    assert set(rec.seen) == set(w) | {"lm_head.weight"}
+    assert rec.seen["model.decoder.embed_positions.weight"] == (cfg.max_positions + 2, cfg.hidden)
+    assert rec.seen["model.decoder.layers.1.fc1.bias"] == (cfg.ffn,)
+    (tmp_path / "pytorch_model.bin").unlink()
+    with pytest.raises(ValueError, match="safetensors or pytorch_model"):
+        load_safetensors_dir(rec, tmp_path)
