@@ -230,6 +230,31 @@ def test_tokenize_model_info_health(srv):
     assert health(HealthCheckRequest(service="fmaas.GenerationService"), timeout=10).status == 1
 
 
+def test_healthcheck_cli_against_a_live_server(srv, capsys):
+    """The k8s probe CLI (reference healthcheck.py:1-96, console script grpc_healthcheck): exit status and the two output
+    shapes against a live server, an unknown service and a dead port; same flags and defaults as the reference's."""
+    from vllm_tgis_adapter.healthcheck import cli, health_check, parse_args
+
+    d = parse_args([])
+    assert (d.server_url, d.timeout, d.service_name, d.insecure) == ("localhost:8033", 1, "fmaas.GenerationService", True)
+    assert parse_args(["--secure"]).insecure is False
+    with pytest.raises(SystemExit):      # --insecure and --secure exclude each other
+        parse_args(["--secure", "--insecure"])
+    url = f"127.0.0.1:{srv.port}"
+    assert health_check(server_url=url, service="fmaas.GenerationService", timeout=10) is True
+    assert capsys.readouterr().out == "health check...status: SERVING\n"
+    assert health_check(server_url=url, service=None, timeout=10) is True          # the server as a whole
+    cli(["--server-url", url, "--timeout", "10"])                                  # exit status 0: returns
+    capsys.readouterr()
+    assert health_check(server_url=url, service="no.such.Service", timeout=10) is False
+    out = capsys.readouterr().out
+    assert out.startswith("health check...Health.Check failed: code=StatusCode.NOT_FOUND")
+    with pytest.raises(SystemExit) as ei:
+        cli(["--server-url", "127.0.0.1:1", "--timeout", "0.5"])
+    assert ei.value.code == 1
+    assert "Health.Check failed: code=StatusCode." in capsys.readouterr().out
+
+
 def test_time_limit_stream_aborts_engine_request():
     s = Server()
     s.fake.step_delay = 0.05
