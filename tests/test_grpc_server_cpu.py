@@ -136,6 +136,82 @@ def test_generate_stream_chunk_count_and_delta_text(srv):
     assert all(c.tokens[0].logprob < 0 and c.tokens[0].rank >= 1 for c in chunks[1:])
 
 
+def test_stream_coalescing_merges_deltas_only_when_the_consumer_is_behind(monkeypatch):
+    """TGIS_STREAM_COALESCE=1 (vLLM's RequestOutputCollector behaviour: a DELTA output that has not been taken yet absorbs the
+    next one): the stream carries the same tokens, text, logprobs and final counts in FEWER messages when the engine runs
+    ahead of the consumer, and exactly one message per token when it does not."""
+    import time as _time
+
+    monkeypatch.setenv("TGIS_STREAM_COALESCE", "1")
+    p = [7, 8, 9, 10]
+    toks = expected_tokens(p, 40)
+    # (1) the records of all 40 steps reach the request's queue together (one poll): ONE merged DELTA output
+    import types
+
+    from vllm_tgis_adapter_b200.engine import _lib
+    from vllm_tgis_adapter_b200.engine.core import StepOutput
+    from vllm_tgis_adapter_b200.engine.types import RequestOutputKind, SamplingParams
+
+    class BurstEngine:
+        max_loras = 0
+
+        def __init__(self):
+            self.lib = types.SimpleNamespace(tgis_last_error=lambda: b"")
+            self.batch = None
+
+        def start(self):
+            pass
+
+        def add_request(self, rid, prompt_ids, sp):
+            self.batch = [StepOutput(request_id=rid, new_token=t, logprob=-0.5, rank=1, topn=[(t, -0.5)],
+                                     finish_reason=_lib.FINISH_LENGTH if k == 39 else _lib.FINISH_NONE, stop_token_id=-1,
+                                     n_prompt_tokens=len(prompt_ids), n_output_tokens=k + 1, ts_arrival=1.0,
+                                     ts_first_scheduled=1.0, ts_first_token=1.0, ts_last_token=1.0, token_id=t)
+                          for k, t in enumerate(toks)]
+
+        def poll(self, timeout_ms=0):
+            if self.batch is None:
+                _time.sleep(0.002)
+                return []
+            b, self.batch = self.batch, None
+            return b
+
+        def abort(self, rid):
+            pass
+
+        def status(self):
+            return types.SimpleNamespace(errored=0, is_running=1)
+
+        def close(self):
+            pass
+
+    mc = ModelConfig(n_layers=1, hidden=128, n_q_heads=1, n_kv_heads=1, ffn=128, vocab=VOCAB, max_model_len=128)
+
+    async def run(coalesce):
+        eng = AsyncTGISEngine(BurstEngine(), build_synthetic_tokenizer(VOCAB), mc, coalesce_streams=coalesce)
+        eng.start(asyncio.get_running_loop())
+        sp = SamplingParams(max_tokens=40, min_tokens=40, logprobs=1, output_kind=RequestOutputKind.DELTA)
+        outs = [o async for o in eng.generate({"prompt_token_ids": p}, sp, request_id="r1")]
+        eng.shutdown()
+        return outs
+
+    merged = asyncio.run(run(True))
+    assert len(merged) == 1 and merged[0].finished and merged[0].outputs[0].finish_reason == "length"
+    assert list(merged[0].outputs[0].token_ids) == toks and len(merged[0].outputs[0].logprobs) == 40
+    assert merged[0].outputs[0].text == " " + " ".join(f"t{t}" for t in toks)
+    plain = asyncio.run(run(False))
+    assert len(plain) == 40 and [t for o in plain for t in o.outputs[0].token_ids] == toks
+    assert "".join(o.outputs[0].text for o in plain) == merged[0].outputs[0].text
+    # (2) an engine slower than the consumer: nothing to merge, one message per token as without the switch
+    s = Server()
+    s.fake.step_delay = 0.01
+    try:
+        chunks = s.stream(synthetic_prompt(p), _params(stopping={"max_new_tokens": 10}, response={"generated_tokens": True}))
+        assert len(chunks) == 11 and [c.generated_token_count for c in chunks[1:]] == list(range(1, 11))
+    finally:
+        s.close()
+
+
 def test_stop_reasons_eos_token_limit_and_stop_sequence():
     p = [20, 21]
     s = Server(script={tuple(p): [40, 41, 2, 50]})

@@ -10,6 +10,7 @@ Threading: the C++ engine runs its own step-loop thread; one Python poller threa
 from __future__ import annotations
 
 import asyncio
+import collections
 import itertools
 import threading
 import types as _types
@@ -46,8 +47,18 @@ class _ReqState:
 
 
 class AsyncTGISEngine:
-    def __init__(self, engine: NativeEngine, tokenizer, model_config: ModelConfig):
+    def __init__(self, engine: NativeEngine, tokenizer, model_config: ModelConfig, coalesce_streams: bool | None = None):
         self.engine = engine
+        # DELTA (GenerateStream) outputs of several engine steps merge into one RequestOutput when the consumer is behind,
+        # as vLLM's RequestOutputCollector does (vllm v1/engine/output_processor.py `put`: aggregate when the previous output
+        # has not been taken).  The per-message cost of grpc.aio (~40 us) caps the host stack at ~13 k streamed messages/s
+        # (scripts/host_stack_bench.py); merging lifts the cap exactly when it binds.  Off by default: an idle server then
+        # sends one message per token, which the reference's tests count (tests/test_grpc_server.py:60-69).
+        if coalesce_streams is None:
+            import os
+
+            coalesce_streams = os.environ.get("TGIS_STREAM_COALESCE", "0") not in ("", "0")
+        self._coalesce_streams = bool(coalesce_streams)
         self.tokenizer = tokenizer
         self._model_config = model_config
         mc = _types.SimpleNamespace(max_model_len=model_config.max_model_len)
@@ -58,6 +69,8 @@ class AsyncTGISEngine:
         self._poller: threading.Thread | None = None
         self._stopping = False
         self._dead_error: str | None = None
+        self._pending: collections.deque = collections.deque()   # poller thread -> event loop (see _poll_loop)
+        self._drain_scheduled = False
         self.metrics = EngineMetrics()
         self._mask_provider = None   # guided decoding: created with the first guided request (imports xgrammar)
         # LoRA: adapter name -> engine slot; `lora_requests` is what grpc/adapters.py consults (the reference asks
@@ -95,12 +108,26 @@ class AsyncTGISEngine:
                 if st.errored:
                     self._dead_error = _lib.last_error(self.engine.lib) or "engine errored"
             if (outs or self._dead_error) and self._loop is not None:
-                try:
-                    self._loop.call_soon_threadsafe(self._dispatch, outs, self._dead_error)
-                except RuntimeError:
-                    return  # loop closed
+                # hand-off to the event loop: records wait in `_pending`, and at most ONE drain callback is in the loop's
+                # ready queue.  When the loop is behind, the records of several engine steps therefore reach the per-request
+                # queues together (which is what lets stream coalescing see a backlog) instead of queueing one callback
+                # per step behind the coroutines of the previous one.
+                self._pending.append((outs, self._dead_error))
+                if not self._drain_scheduled:
+                    self._drain_scheduled = True
+                    try:
+                        self._loop.call_soon_threadsafe(self._drain)
+                    except RuntimeError:
+                        return  # loop closed
             if self._dead_error:
                 return
+
+    def _drain(self) -> None:
+        # cleared FIRST: a record appended after this line schedules the next drain; one appended before it is popped below
+        self._drain_scheduled = False
+        while self._pending:
+            outs, dead = self._pending.popleft()
+            self._dispatch(outs, dead)
 
     def _dispatch(self, outs: list[StepOutput], dead: str | None) -> None:
         for o in outs:
@@ -211,8 +238,9 @@ class AsyncTGISEngine:
                     raise item
                 batch = [item]
                 # DELTA streams emit one RequestOutput per engine step (the reference's tests pin "N tokens -> N+1
-                # messages", tests/test_grpc_server.py:60-69); FINAL_ONLY may swallow whatever has already arrived.
-                while not delta and not queue.empty():
+                # messages", tests/test_grpc_server.py:60-69) unless stream coalescing is on; FINAL_ONLY may swallow
+                # whatever has already arrived.
+                while (not delta or self._coalesce_streams) and not queue.empty():
                     nxt = queue.get_nowait()
                     if isinstance(nxt, BaseException):
                         raise nxt
