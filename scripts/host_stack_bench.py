@@ -181,7 +181,7 @@ def main():
         asyncio.set_event_loop(loop)
 
         async def amain():
-            engine = AsyncTGISEngine(eng, tok, mc)   # TGIS_STREAM_COALESCE=1: merge deltas when the consumer is behind
+            engine = AsyncTGISEngine(eng, tok, mc)   # TGIS_STREAM_COALESCE=auto (default: by load) | 1 | 0
             engine.start(loop)
             box["stop"] = asyncio.Event()
             server = await grpc_server.start_grpc_server(args, engine, box["stop"])
@@ -226,7 +226,7 @@ def main():
     eng.close()
     best = max(n / t for n, t, _ in res)
     print(json.dumps({"host_stack_tokens_per_s": best, "n_streams": n_streams, "gen_len": gen_len,
-                      "stream_coalesce": os.environ.get("TGIS_STREAM_COALESCE", "0"), "client_processes": n_clients, "event_loop": "uvloop" if use_uvloop else "asyncio", "engine_step_interval_ms": step_ms,
+                      "stream_coalesce": os.environ.get("TGIS_STREAM_COALESCE", "auto"), "client_processes": n_clients, "event_loop": "uvloop" if use_uvloop else "asyncio", "engine_step_interval_ms": step_ms,
                       "engine_paced_tokens_per_s": (n_streams / (step_ms * 1e-3)) if step_ms else None,
                       "rounds": [{"tokens": n, "messages": m, "s": round(t, 3)} for n, t, m in res],
                       "note": "replay engine (no GPU): streamed tokens delivered per second by the Python host stack"}))

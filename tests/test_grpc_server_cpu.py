@@ -137,9 +137,10 @@ def test_generate_stream_chunk_count_and_delta_text(srv):
 
 
 def test_stream_coalescing_merges_deltas_only_when_the_consumer_is_behind(monkeypatch):
-    """TGIS_STREAM_COALESCE=1 (vLLM's RequestOutputCollector behaviour: a DELTA output that has not been taken yet absorbs the
-    next one): the stream carries the same tokens, text, logprobs and final counts in FEWER messages when the engine runs
-    ahead of the consumer, and exactly one message per token when it does not."""
+    """Stream coalescing (vLLM's RequestOutputCollector behaviour: a DELTA output that has not been taken yet absorbs the next
+    one; on under load by default, TGIS_STREAM_COALESCE=1 / 0 forces it): the stream carries the same tokens, text, logprobs
+    and final counts in FEWER messages when the engine runs ahead of the consumer, and exactly one message per token when
+    it does not."""
     import time as _time
 
     monkeypatch.setenv("TGIS_STREAM_COALESCE", "1")
@@ -202,6 +203,13 @@ def test_stream_coalescing_merges_deltas_only_when_the_consumer_is_behind(monkey
     plain = asyncio.run(run(False))
     assert len(plain) == 40 and [t for o in plain for t in o.outputs[0].token_ids] == toks
     assert "".join(o.outputs[0].text for o in plain) == merged[0].outputs[0].text
+    # the default ("auto"): by load -- merging starts once TGIS_STREAM_COALESCE_MIN_STREAMS requests are in flight
+    monkeypatch.setenv("TGIS_STREAM_COALESCE", "auto")
+    assert len(asyncio.run(run(None))) == 40                    # one request in flight, threshold 64: one message per token
+    monkeypatch.setenv("TGIS_STREAM_COALESCE_MIN_STREAMS", "1")
+    auto = asyncio.run(run(None))
+    assert len(auto) == 1 and list(auto[0].outputs[0].token_ids) == toks
+    monkeypatch.setenv("TGIS_STREAM_COALESCE", "1")
     # (2) an engine slower than the consumer: nothing to merge, one message per token as without the switch
     s = Server()
     s.fake.step_delay = 0.01

@@ -51,14 +51,20 @@ class AsyncTGISEngine:
         self.engine = engine
         # DELTA (GenerateStream) outputs of several engine steps merge into one RequestOutput when the consumer is behind,
         # as vLLM's RequestOutputCollector does (vllm v1/engine/output_processor.py `put`: aggregate when the previous output
-        # has not been taken).  The per-message cost of grpc.aio (~40 us) caps the host stack at ~13 k streamed messages/s
-        # (scripts/host_stack_bench.py); merging lifts the cap exactly when it binds.  Off by default: an idle server then
-        # sends one message per token, which the reference's tests count (tests/test_grpc_server.py:60-69).
-        if coalesce_streams is None:
-            import os
+        # has not been taken).  The per-message cost of grpc.aio (~60 us) caps the host stack near 14 k streamed messages/s
+        # (scripts/host_stack_bench.py); merging lifts the cap exactly when it binds.
+        #   coalesce_streams / TGIS_STREAM_COALESCE = None / "auto" (default): merge only while at least
+        #       TGIS_STREAM_COALESCE_MIN_STREAMS (64) requests are in flight -- below that the engine's decode rate is under
+        #       the host's ceiling, and a lightly loaded server keeps sending exactly one message per token, which the
+        #       reference's tests count (tests/test_grpc_server.py:60-69);
+        #   True / "1": always;  False / "0": never.
+        import os
 
-            coalesce_streams = os.environ.get("TGIS_STREAM_COALESCE", "0") not in ("", "0")
-        self._coalesce_streams = bool(coalesce_streams)
+        if coalesce_streams is None:
+            env = os.environ.get("TGIS_STREAM_COALESCE", "auto").strip().lower()
+            coalesce_streams = None if env in ("", "auto") else env not in ("0", "false", "off")
+        self._coalesce_streams = coalesce_streams          # None: by load
+        self._coalesce_min_streams = int(os.environ.get("TGIS_STREAM_COALESCE_MIN_STREAMS", "64"))
         self.tokenizer = tokenizer
         self._model_config = model_config
         mc = _types.SimpleNamespace(max_model_len=model_config.max_model_len)
@@ -240,7 +246,8 @@ class AsyncTGISEngine:
                 # DELTA streams emit one RequestOutput per engine step (the reference's tests pin "N tokens -> N+1
                 # messages", tests/test_grpc_server.py:60-69) unless stream coalescing is on; FINAL_ONLY may swallow
                 # whatever has already arrived.
-                while (not delta or self._coalesce_streams) and not queue.empty():
+                while not queue.empty() and (not delta or self._coalesce_streams or (
+                        self._coalesce_streams is None and len(self._states) >= 2 * self._coalesce_min_streams)):
                     nxt = queue.get_nowait()
                     if isinstance(nxt, BaseException):
                         raise nxt
